@@ -1,0 +1,210 @@
+"""ctypes binding of the CPU oracle (oracle/tsdf_oracle.{h,cc}).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product (coxgraph_b200/) never imports this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libtsdf_oracle.so")
+
+VOXELS_PER_BLOCK = 4096
+VOXEL_DTYPE = np.dtype([("distance", "<f4"), ("weight", "<f4"), ("rgba", "u1", (4,))])
+assert VOXEL_DTYPE.itemsize == 12
+
+
+class IntegratorConfig(C.Structure):
+    """Mirror of orc_integrator_config (voxblox TsdfIntegratorBase::Config)."""
+
+    _fields_ = [
+        ("default_truncation_distance", C.c_float),
+        ("max_weight", C.c_float),
+        ("voxel_carving_enabled", C.c_int32),
+        ("min_ray_length_m", C.c_float),
+        ("max_ray_length_m", C.c_float),
+        ("use_const_weight", C.c_int32),
+        ("allow_clear", C.c_int32),
+        ("use_weight_dropoff", C.c_int32),
+        ("use_sparsity_compensation_factor", C.c_int32),
+        ("sparsity_compensation_factor", C.c_float),
+        ("enable_anti_grazing", C.c_int32),
+        ("method", C.c_int32),
+        ("integration_order_mode", C.c_int32),
+        ("start_voxel_subsampling_factor", C.c_float),
+        ("max_consecutive_ray_collisions", C.c_int32),
+    ]
+
+
+def build(force=False):
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
+        os.path.getmtime(os.path.join(_HERE, f)) for f in ("tsdf_oracle.cc", "tsdf_oracle.h")
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        L = _lib
+        L.orc_layer_create.restype = C.c_void_p
+        L.orc_layer_create.argtypes = [C.c_float, C.c_int32]
+        L.orc_layer_destroy.argtypes = [C.c_void_p]
+        L.orc_layer_clear.argtypes = [C.c_void_p]
+        L.orc_layer_num_blocks.restype = C.c_size_t
+        L.orc_layer_num_blocks.argtypes = [C.c_void_p]
+        L.orc_layer_download.argtypes = [C.c_void_p] * 4
+        L.orc_layer_upload.argtypes = [C.c_void_p] * 4 + [C.c_size_t]
+        L.orc_default_config.argtypes = [C.POINTER(IntegratorConfig)]
+        L.orc_integrate_pointcloud.restype = C.c_int32
+        L.orc_integrate_pointcloud.argtypes = [
+            C.c_void_p, C.POINTER(IntegratorConfig), C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_size_t, C.c_int32, C.POINTER(C.c_uint64)]
+        L.orc_integrate_pointcloud_mt.restype = C.c_int32
+        L.orc_integrate_pointcloud_mt.argtypes = [
+            C.c_void_p, C.POINTER(IntegratorConfig), C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_size_t, C.c_int32, C.c_int32]
+        L.orc_merge_layer_into_layer.restype = C.c_int32
+        L.orc_merge_layer_into_layer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.POINTER(C.c_uint64)]
+        L.orc_merge_layer_into_layer_mt.restype = C.c_int32
+        L.orc_merge_layer_into_layer_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                                    C.POINTER(C.c_uint64)]
+        L.orc_transform_point.argtypes = [C.c_void_p] * 3
+        L.orc_inverse_transform.argtypes = [C.c_void_p] * 2
+        L.orc_cast_ray.restype = C.c_size_t
+        L.orc_cast_ray.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
+                                   C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_size_t]
+        L.orc_interp_voxel.restype = C.c_int32
+        L.orc_interp_voxel.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_float),
+                                       C.POINTER(C.c_float), C.c_void_p]
+    return _lib
+
+
+def default_config(**over):
+    cfg = IntegratorConfig()
+    lib().orc_default_config(C.byref(cfg))
+    for k, v in over.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Layer:
+    """Oracle Layer<TsdfVoxel>."""
+
+    def __init__(self, voxel_size, voxels_per_side=16):
+        self._h = lib().orc_layer_create(float(voxel_size), int(voxels_per_side))
+        if not self._h:
+            raise ValueError("bad layer parameters")
+        self.voxel_size = float(np.float32(voxel_size))
+        self.last_blocks_touched = 0
+        self.last_blocks_out = 0
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_layer_destroy(self._h)
+            self._h = None
+
+    def clear(self):
+        lib().orc_layer_clear(self._h)
+
+    @property
+    def num_blocks(self):
+        return lib().orc_layer_num_blocks(self._h)
+
+    def integrate(self, cfg, T_G_C, points, colors, freespace=False, threads=0):
+        pts = _f32(points, (-1, 3))
+        cols = np.ascontiguousarray(colors, dtype=np.uint8).reshape(-1, 4)
+        assert len(pts) == len(cols)
+        T = _f32(T_G_C, (7,))
+        if threads and threads > 0:
+            rc = lib().orc_integrate_pointcloud_mt(self._h, C.byref(cfg), _ptr(T), _ptr(pts),
+                                                   _ptr(cols), len(pts), int(freespace), threads)
+        else:
+            touched = C.c_uint64(0)
+            rc = lib().orc_integrate_pointcloud(self._h, C.byref(cfg), _ptr(T), _ptr(pts),
+                                                _ptr(cols), len(pts), int(freespace),
+                                                C.byref(touched))
+            self.last_blocks_touched = touched.value
+        if rc != 0:
+            raise RuntimeError(f"oracle integrate failed rc={rc}")
+
+    def merge_from(self, layer_a, T_B_A, threads=0):
+        """mergeLayerAintoLayerB(layer_a, T_B_A, self)."""
+        T = _f32(T_B_A, (7,))
+        out = C.c_uint64(0)
+        if threads and threads > 1:
+            rc = lib().orc_merge_layer_into_layer_mt(layer_a._h, _ptr(T), self._h, threads,
+                                                     C.byref(out))
+        else:
+            rc = lib().orc_merge_layer_into_layer(layer_a._h, _ptr(T), self._h, C.byref(out))
+        self.last_blocks_out = out.value
+        if rc != 0:
+            raise RuntimeError(f"oracle merge failed rc={rc}")
+
+    def download(self):
+        """-> (block_idx int32 [B,3] sorted (z,y,x), voxels [B,4096] VOXEL_DTYPE, flags u8 [B])."""
+        n = self.num_blocks
+        idx = np.zeros((n, 3), np.int32)
+        vox = np.zeros((n, VOXELS_PER_BLOCK), VOXEL_DTYPE)
+        flags = np.zeros((n,), np.uint8)
+        if n:
+            lib().orc_layer_download(self._h, _ptr(idx), _ptr(vox), _ptr(flags))
+        return idx, vox, flags
+
+    def upload(self, idx, vox, flags=None):
+        idx = np.ascontiguousarray(idx, np.int32).reshape(-1, 3)
+        vox = np.ascontiguousarray(vox, VOXEL_DTYPE).reshape(len(idx), VOXELS_PER_BLOCK)
+        fl = None if flags is None else np.ascontiguousarray(flags, np.uint8)
+        lib().orc_layer_upload(self._h, _ptr(idx), _ptr(vox), None if fl is None else _ptr(fl),
+                               len(idx))
+
+    def interp(self, pos, interpolate=True):
+        p = _f32(pos, (3,))
+        d, w = C.c_float(0), C.c_float(0)
+        rgba = np.zeros(4, np.uint8)
+        ok = lib().orc_interp_voxel(self._h, _ptr(p), int(interpolate), C.byref(d), C.byref(w),
+                                    _ptr(rgba))
+        return bool(ok), d.value, w.value, rgba
+
+
+def transform_point(T, p):
+    out = np.zeros(3, np.float32)
+    lib().orc_transform_point(_ptr(_f32(T, (7,))), _ptr(_f32(p, (3,))), _ptr(out))
+    return out
+
+
+def inverse_transform(T):
+    out = np.zeros(7, np.float32)
+    lib().orc_inverse_transform(_ptr(_f32(T, (7,))), _ptr(out))
+    return out
+
+
+def cast_ray(origin, point_G, clearing, carving, max_ray, voxel_size_inv, trunc,
+             cast_from_origin=True, cap=100000):
+    out = np.zeros((cap, 3), np.int64)
+    n = lib().orc_cast_ray(_ptr(_f32(origin, (3,))), _ptr(_f32(point_G, (3,))), int(clearing),
+                           int(carving), float(max_ray), float(voxel_size_inv), float(trunc),
+                           int(cast_from_origin), _ptr(out), cap)
+    return out[: min(n, cap)].copy()

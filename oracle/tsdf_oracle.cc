@@ -1,0 +1,1054 @@
+// tsdf_oracle.cc — CPU ORACLE for the coxgraph TSDF hot path.  TEST INFRASTRUCTURE ONLY
+// (see tsdf_oracle.h).  PARITY UNPINNED: restates upstream voxblox semantics (the forks the
+// reference depends on are not vendored, coxgraph_ssh.rosinstall:1-8,55-58).
+//
+// Everything here is written against the *published* voxblox algorithm, independently of
+// the CUDA implementation under coxgraph_b200/csrc (no shared headers), with the float
+// operation order of voxblox/Eigen/minkindr spelled out.  Compile without FMA contraction
+// (-ffp-contract=off) so that every rounding step is the IEEE single-precision one.
+//
+// Section tags R1..R10 follow SURVEY.md §8(a).  Reference call sites:
+//   integratePointCloud  : coxgraph/include/coxgraph/map_comm/tsdf_recover.h:75
+//   mergeLayerAintoLayerB: coxgraph/src/client/map_server.cpp:67-69,
+//                          coxgraph/src/server/visualizer/server_visualizer.cpp:123-126
+#include "tsdf_oracle.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+namespace {
+
+constexpr float kEps = 1e-6f;  // voxblox kEpsilon == kFloatEpsilon == kCoordinateEpsilon
+constexpr int kVps = 16;
+constexpr int kVoxelsPerBlock = kVps * kVps * kVps;
+
+// ---------------------------------------------------------------- small vector algebra
+struct V3 {
+  float x, y, z;
+};
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+// Eigen fixed-size-3 reduction unrolls as a0 + (a1 + a2) (redux_novec_unroller halves).
+inline float dot(V3 a, V3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
+inline float norm(V3 a) { return std::sqrt(dot(a, a)); }
+inline V3 cross(V3 a, V3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+inline V3 normalized(V3 a) {  // Eigen MatrixBase::normalized()
+  float z = dot(a, a);
+  if (z > 0.0f) return a / std::sqrt(z);
+  return a;
+}
+
+struct Xform {  // kindr::minimal::QuatTransformationTemplate<float>
+  float w;
+  V3 v;  // quaternion (w, vec)
+  V3 t;
+};
+inline Xform load_xform(const float T[7]) { return {T[0], {T[1], T[2], T[3]}, {T[4], T[5], T[6]}}; }
+// Eigen QuaternionBase::_transformVector
+inline V3 rotate(float w, V3 qv, V3 p) {
+  V3 uv = cross(qv, p);
+  uv = uv + uv;
+  V3 c = cross(qv, uv);
+  return {(p.x + w * uv.x) + c.x, (p.y + w * uv.y) + c.y, (p.z + w * uv.z) + c.z};
+}
+inline V3 apply(const Xform& T, V3 p) { return rotate(T.w, T.v, p) + T.t; }  // R2
+inline Xform inverse(const Xform& T) {  // (q*, -(q* (x) t))
+  V3 cv = {-T.v.x, -T.v.y, -T.v.z};
+  V3 r = rotate(T.w, cv, T.t);
+  return {T.w, cv, {-r.x, -r.y, -r.z}};
+}
+
+// ---------------------------------------------------------------- voxel / colour
+struct Color {
+  uint8_t r = 0, g = 0, b = 0, a = 255;
+};
+struct Voxel {  // voxblox::TsdfVoxel, 12 bytes
+  float distance = 0.0f;
+  float weight = 0.0f;
+  Color color;
+};
+static_assert(sizeof(Voxel) == 12, "TsdfVoxel layout");
+
+inline uint8_t round_u8(float v) { return static_cast<uint8_t>(std::round(v)); }
+// Color::blendTwoColors
+inline Color blend(Color c1, float w1, Color c2, float w2) {
+  float total = w1 + w2;
+  w1 /= total;
+  w2 /= total;
+  Color o;
+  o.r = round_u8(c1.r * w1 + c2.r * w2);
+  o.g = round_u8(c1.g * w1 + c2.g * w2);
+  o.b = round_u8(c1.b * w1 + c2.b * w2);
+  o.a = round_u8(c1.a * w1 + c2.a * w2);
+  return o;
+}
+
+// ---------------------------------------------------------------- indices
+struct I3 {
+  int32_t x, y, z;
+  bool operator==(const I3& o) const { return x == o.x && y == o.y && z == o.z; }
+  bool operator!=(const I3& o) const { return !(*this == o); }
+};
+struct L3 {
+  int64_t x, y, z;
+  bool operator==(const L3& o) const { return x == o.x && y == o.y && z == o.z; }
+  bool operator!=(const L3& o) const { return !(*this == o); }
+};
+struct I3Hash {  // voxblox AnyIndexHash
+  size_t operator()(const I3& i) const {
+    constexpr size_t sl = 17191, sl2 = sl * sl;
+    return static_cast<unsigned int>(i.x + i.y * sl + i.z * sl2);
+  }
+};
+struct L3Hash {  // voxblox LongIndexHash
+  size_t operator()(const L3& i) const {
+    constexpr size_t sl = 17191, sl2 = sl * sl;
+    return static_cast<unsigned int>(i.x + i.y * sl + i.z * sl2);
+  }
+};
+inline bool zyx_less(const L3& a, const L3& b) {
+  if (a.z != b.z) return a.z < b.z;
+  if (a.y != b.y) return a.y < b.y;
+  return a.x < b.x;
+}
+inline bool zyx_less_i(const I3& a, const I3& b) {
+  if (a.z != b.z) return a.z < b.z;
+  if (a.y != b.y) return a.y < b.y;
+  return a.x < b.x;
+}
+
+// getGridIndexFromPoint(point, inv): floor(p*inv + 1e-6)
+inline L3 grid_index_long(V3 p, float inv) {
+  return {static_cast<int64_t>(std::floor(p.x * inv + kEps)),
+          static_cast<int64_t>(std::floor(p.y * inv + kEps)),
+          static_cast<int64_t>(std::floor(p.z * inv + kEps))};
+}
+inline L3 grid_index_long(V3 scaled) {
+  return {static_cast<int64_t>(std::floor(scaled.x + kEps)),
+          static_cast<int64_t>(std::floor(scaled.y + kEps)),
+          static_cast<int64_t>(std::floor(scaled.z + kEps))};
+}
+inline I3 grid_index_int(V3 p, float inv) {
+  return {static_cast<int32_t>(std::floor(p.x * inv + kEps)),
+          static_cast<int32_t>(std::floor(p.y * inv + kEps)),
+          static_cast<int32_t>(std::floor(p.z * inv + kEps))};
+}
+// getCenterPointFromGridIndex: (float(idx) + 0.5) * grid_size, evaluated in double and
+// rounded once to float (the 0.5 literal is a double in the upstream source).
+inline float center_coord(int64_t idx, float grid) {
+  return static_cast<float>((static_cast<double>(static_cast<float>(idx)) + 0.5) *
+                            static_cast<double>(grid));
+}
+inline V3 center_point(L3 i, float grid) {
+  return {center_coord(i.x, grid), center_coord(i.y, grid), center_coord(i.z, grid)};
+}
+inline V3 origin_point(I3 i, float grid) {  // getOriginPointFromGridIndex
+  return {static_cast<float>(i.x) * grid, static_cast<float>(i.y) * grid,
+          static_cast<float>(i.z) * grid};
+}
+// R4: getBlockIndexFromGlobalVoxelIndex / getLocalFromGlobalVoxelIndex
+inline I3 block_of_voxel(L3 v, float vps_inv) {
+  return {static_cast<int32_t>(std::floor(static_cast<float>(v.x) * vps_inv)),
+          static_cast<int32_t>(std::floor(static_cast<float>(v.y) * vps_inv)),
+          static_cast<int32_t>(std::floor(static_cast<float>(v.z) * vps_inv))};
+}
+inline int local_linear(L3 v) {
+  constexpr int64_t offset = int64_t(1) << 31;
+  int lx = static_cast<int>((v.x + offset) & (kVps - 1));
+  int ly = static_cast<int>((v.y + offset) & (kVps - 1));
+  int lz = static_cast<int>((v.z + offset) & (kVps - 1));
+  return lx + kVps * (ly + kVps * lz);
+}
+
+// ---------------------------------------------------------------- layer
+struct Block {
+  Voxel voxels[kVoxelsPerBlock];
+  bool has_data = false;
+  bool updated = false;
+};
+using BlockMap = std::unordered_map<I3, std::unique_ptr<Block>, I3Hash>;
+
+}  // namespace
+
+struct orc_layer {
+  float voxel_size;
+  float voxel_size_inv;
+  float block_size;
+  float block_size_inv;
+  float vps_inv;
+  BlockMap blocks;
+  const Block* find(I3 idx) const {
+    auto it = blocks.find(idx);
+    return it == blocks.end() ? nullptr : it->second.get();
+  }
+  Block* find(I3 idx) {
+    auto it = blocks.find(idx);
+    return it == blocks.end() ? nullptr : it->second.get();
+  }
+  Block* get_or_create(I3 idx) {
+    auto& p = blocks[idx];
+    if (!p) p.reset(new Block());
+    return p.get();
+  }
+};
+
+namespace {
+
+// ---------------------------------------------------------------- R3 RayCaster
+struct RayCaster {
+  L3 curr;
+  uint32_t steps = 0;
+  uint32_t current_step = 0;
+  int sign[3];
+  float t_next[3];
+  float t_step[3];
+  bool valid = true;
+
+  RayCaster(V3 origin, V3 point_G, bool clearing, bool carving, float max_ray,
+            float voxel_size_inv, float trunc, bool cast_from_origin = true) {
+    const V3 unit_ray = normalized(point_G - origin);
+    V3 ray_start, ray_end;
+    if (clearing) {
+      float ray_length = norm(point_G - origin);
+      ray_length = std::min(std::max(ray_length - trunc, 0.0f), max_ray);
+      ray_end = origin + unit_ray * ray_length;
+      ray_start = carving ? origin : ray_end;
+    } else {
+      ray_end = point_G + unit_ray * trunc;
+      ray_start = carving ? origin : (point_G - unit_ray * trunc);
+    }
+    const V3 s = ray_start * voxel_size_inv;
+    const V3 e = ray_end * voxel_size_inv;
+    if (cast_from_origin)
+      setup(s, e);
+    else
+      setup(e, s);
+  }
+
+  static int signum(float v) { return (v == 0.0f) ? 0 : (v < 0.0f ? -1 : 1); }
+
+  void setup(V3 start, V3 end) {
+    if (std::isnan(start.x) || std::isnan(start.y) || std::isnan(start.z) ||
+        std::isnan(end.x) || std::isnan(end.y) || std::isnan(end.z)) {
+      valid = false;  // upstream leaves the caster unusable; we emit nothing
+      return;
+    }
+    curr = grid_index_long(start);
+    const L3 e = grid_index_long(end);
+    const int64_t dx = e.x - curr.x, dy = e.y - curr.y, dz = e.z - curr.z;
+    steps = static_cast<uint32_t>(std::llabs(dx) + std::llabs(dy) + std::llabs(dz));
+    const float ray[3] = {end.x - start.x, end.y - start.y, end.z - start.z};
+    const float shifted[3] = {start.x - static_cast<float>(curr.x),
+                              start.y - static_cast<float>(curr.y),
+                              start.z - static_cast<float>(curr.z)};
+    for (int a = 0; a < 3; ++a) {
+      sign[a] = signum(ray[a]);
+      const float corrected = static_cast<float>(std::max(0, sign[a]));
+      const float dist_to_boundary = corrected - shifted[a];
+      // upstream guards with (abs(ray) < 0.0), which is never true: plain IEEE division,
+      // inf / NaN included.
+      t_next[a] = dist_to_boundary / ray[a];
+      t_step[a] = static_cast<float>(sign[a]) / ray[a];
+    }
+  }
+
+  bool next(L3* out) {
+    if (!valid) return false;
+    if (current_step++ > steps) return false;
+    *out = curr;
+    // Eigen minCoeff visitor: res = coeff(0); later coeffs replace it only if (value < res).
+    int m = 0;
+    float best = t_next[0];
+    if (t_next[1] < best) {
+      best = t_next[1];
+      m = 1;
+    }
+    if (t_next[2] < best) {
+      best = t_next[2];
+      m = 2;
+    }
+    if (m == 0)
+      curr.x += sign[0];
+    else if (m == 1)
+      curr.y += sign[1];
+    else
+      curr.z += sign[2];
+    t_next[m] += t_step[m];
+    return true;
+  }
+};
+
+// ---------------------------------------------------------------- integrator core
+struct Cfg {
+  orc_integrator_config c;
+  float voxel_size, voxel_size_inv, vps_inv;
+};
+
+// R1 isPointValid (+ non-finite points are dropped, as voxblox_ros TsdfServer does before
+// the integrator ever sees them).
+inline bool point_valid(const Cfg& cfg, V3 p, bool freespace, bool* clearing) {
+  if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) return false;
+  const float d = norm(p);
+  if (d < cfg.c.min_ray_length_m) return false;
+  if (d > cfg.c.max_ray_length_m) {
+    if (cfg.c.allow_clear || freespace) {
+      *clearing = true;
+      return true;
+    }
+    return false;
+  }
+  *clearing = freespace;
+  return true;
+}
+
+inline float voxel_weight(const Cfg& cfg, V3 p_C) {  // getVoxelWeight
+  if (cfg.c.use_const_weight) return 1.0f;
+  const float dz = std::fabs(p_C.z);
+  if (dz > kEps) return 1.0f / (dz * dz);
+  return 0.0f;
+}
+
+inline float compute_distance(V3 origin, V3 point_G, V3 voxel_center) {
+  const V3 v_voxel_origin = voxel_center - origin;
+  const V3 v_point_origin = point_G - origin;
+  const float dist_G = norm(v_point_origin);
+  const float dist_G_V = dot(v_voxel_origin, v_point_origin) / dist_G;
+  return dist_G - dist_G_V;
+}
+
+// R5 updateTsdfVoxel (the voxel lock is the caller's business)
+template <class Lock>
+inline void update_voxel(const Cfg& cfg, V3 origin, V3 point_G, L3 gvi, Color color,
+                         float weight, Voxel* voxel, Lock&& lock) {
+  const V3 center = center_point(gvi, cfg.voxel_size);
+  const float sdf = compute_distance(origin, point_G, center);
+  const float trunc = cfg.c.default_truncation_distance;
+  float updated_weight = weight;
+  const float dropoff_epsilon = cfg.voxel_size;
+  if (cfg.c.use_weight_dropoff && sdf < -dropoff_epsilon) {
+    updated_weight = weight * (trunc + sdf) / (trunc - dropoff_epsilon);
+    updated_weight = std::max(updated_weight, 0.0f);
+  }
+  if (cfg.c.use_sparsity_compensation_factor) {
+    if (std::fabs(sdf) < trunc) updated_weight *= cfg.c.sparsity_compensation_factor;
+  }
+  auto guard = lock(gvi);
+  (void)guard;
+  const float new_weight = voxel->weight + updated_weight;
+  if (new_weight < kEps) return;
+  const float new_sdf = (sdf * updated_weight + voxel->distance * voxel->weight) / new_weight;
+  if (std::fabs(sdf) < trunc)
+    voxel->color = blend(voxel->color, voxel->weight, color, updated_weight);
+  voxel->distance = (new_sdf > 0.0f) ? std::min(trunc, new_sdf) : std::max(-trunc, new_sdf);
+  voxel->weight = std::min(cfg.c.max_weight, new_weight);
+}
+
+struct NoLock {
+  int operator()(const L3&) const { return 0; }
+};
+
+// MixedThreadSafeIndex: sequential counter k -> point index
+struct IndexOrder {
+  size_t n, groups;
+  int mode;
+  IndexOrder(size_t n_, int mode_) : n(n_), groups(n_ / 1024), mode(mode_) {}
+  size_t at(size_t k) const {
+    if (mode != 0) return k;
+    if (groups * 1024 <= k) return k;
+    return (k % groups) * 1024 + (k / groups);
+  }
+};
+
+// Block storage during one integratePointCloud call: existing layer blocks are used in
+// place, new ones are collected and committed at the end (updateLayerWithStoredBlocks).
+struct CallStorage {
+  orc_layer* layer;
+  BlockMap temp;
+  std::unordered_set<I3, I3Hash> touched;
+  explicit CallStorage(orc_layer* l) : layer(l) {}
+  Voxel* voxel_ptr(const Cfg& cfg, L3 gvi) {  // allocateStorageAndGetVoxelPtr
+    const I3 bi = block_of_voxel(gvi, cfg.vps_inv);
+    touched.insert(bi);
+    Block* b = layer->find(bi);
+    if (!b) {
+      auto& p = temp[bi];
+      if (!p) p.reset(new Block());
+      b = p.get();
+    }
+    b->updated = true;
+    return &b->voxels[local_linear(gvi)];
+  }
+  void commit() {
+    for (auto& kv : temp) layer->blocks[kv.first] = std::move(kv.second);
+    temp.clear();
+  }
+};
+
+struct Bundle {
+  L3 key;
+  std::vector<size_t> pts;
+};
+
+// R6 bundleRays: single-threaded, points visited in index-getter order (as upstream)
+void bundle_rays(const Cfg& cfg, const Xform& T, const float* pts, size_t n, bool freespace,
+                 std::vector<Bundle>* normal, std::vector<Bundle>* clear) {
+  std::unordered_map<L3, size_t, L3Hash> nmap, cmap;
+  IndexOrder order(n, cfg.c.integration_order_mode);
+  for (size_t k = 0; k < n; ++k) {
+    const size_t i = order.at(k);
+    const V3 p_C = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    bool clearing = false;
+    if (!point_valid(cfg, p_C, freespace, &clearing)) continue;
+    const V3 p_G = apply(T, p_C);
+    const L3 key = grid_index_long(p_G, cfg.voxel_size_inv);
+    auto& map = clearing ? cmap : nmap;
+    auto* vec = clearing ? clear : normal;
+    auto it = map.find(key);
+    if (it == map.end()) {
+      map.emplace(key, vec->size());
+      vec->push_back(Bundle{key, {i}});
+    } else {
+      (*vec)[it->second].pts.push_back(i);
+    }
+  }
+  // canonical order over bundles (upstream: unordered_map order x thread interleaving)
+  auto by_key = [](const Bundle& a, const Bundle& b) { return zyx_less(a.key, b.key); };
+  std::sort(normal->begin(), normal->end(), by_key);
+  std::sort(clear->begin(), clear->end(), by_key);
+}
+
+struct MergedRay {
+  V3 point_G;
+  Color color;
+  float weight;
+};
+
+// MergedTsdfIntegrator::integrateVoxel, first half
+MergedRay fold_bundle(const Cfg& cfg, const Xform& T, const float* pts, const uint8_t* cols,
+                      const Bundle& b, bool clearing) {
+  Color merged_color;
+  V3 merged_point_C = {0.0f, 0.0f, 0.0f};
+  float merged_weight = 0.0f;
+  for (size_t i : b.pts) {
+    const V3 p_C = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    Color c;
+    c.r = cols[4 * i];
+    c.g = cols[4 * i + 1];
+    c.b = cols[4 * i + 2];
+    c.a = cols[4 * i + 3];
+    const float w = voxel_weight(cfg, p_C);
+    if (w < kEps) continue;
+    merged_point_C = (merged_point_C * merged_weight + p_C * w) / (merged_weight + w);
+    merged_color = blend(merged_color, merged_weight, c, w);
+    merged_weight += w;
+    if (clearing) break;  // only take first point when clearing
+  }
+  return {apply(T, merged_point_C), merged_color, merged_weight};
+}
+
+template <class Storage, class Lock>
+void integrate_bundle(const Cfg& cfg, const Xform& T, const float* pts, const uint8_t* cols,
+                      const Bundle& b, bool clearing,
+                      const std::unordered_set<L3, L3Hash>* grazing_set, Storage& st,
+                      Lock&& lock) {
+  if (b.pts.empty()) return;
+  const V3 origin = T.t;
+  const MergedRay r = fold_bundle(cfg, T, pts, cols, b, clearing);
+  RayCaster rc(origin, r.point_G, clearing, cfg.c.voxel_carving_enabled != 0,
+               cfg.c.max_ray_length_m, cfg.voxel_size_inv, cfg.c.default_truncation_distance);
+  L3 gvi;
+  while (rc.next(&gvi)) {
+    if (grazing_set) {
+      if ((clearing || gvi != b.key) && grazing_set->count(gvi)) continue;
+    }
+    Voxel* v = st.voxel_ptr(cfg, gvi);
+    update_voxel(cfg, origin, r.point_G, gvi, r.color, r.weight, v, lock);
+  }
+}
+
+int integrate_merged(orc_layer* layer, const Cfg& cfg, const Xform& T, const float* pts,
+                     const uint8_t* cols, size_t n, bool freespace, uint64_t* touched) {
+  std::vector<Bundle> normal, clear;
+  bundle_rays(cfg, T, pts, n, freespace, &normal, &clear);
+  std::unordered_set<L3, L3Hash> grazing;
+  if (cfg.c.enable_anti_grazing)
+    for (const auto& b : normal) grazing.insert(b.key);
+  const auto* gs = cfg.c.enable_anti_grazing ? &grazing : nullptr;
+  CallStorage st(layer);
+  for (const auto& b : normal) integrate_bundle(cfg, T, pts, cols, b, false, gs, st, NoLock());
+  st.commit();
+  for (const auto& b : clear) integrate_bundle(cfg, T, pts, cols, b, true, gs, st, NoLock());
+  st.commit();
+  if (touched) *touched = st.touched.size();
+  return 0;
+}
+
+int integrate_simple(orc_layer* layer, const Cfg& cfg, const Xform& T, const float* pts,
+                     const uint8_t* cols, size_t n, bool freespace, uint64_t* touched) {
+  CallStorage st(layer);
+  IndexOrder order(n, cfg.c.integration_order_mode);
+  const V3 origin = T.t;
+  for (size_t k = 0; k < n; ++k) {
+    const size_t i = order.at(k);
+    const V3 p_C = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    bool clearing = false;
+    if (!point_valid(cfg, p_C, freespace, &clearing)) continue;
+    const V3 p_G = apply(T, p_C);
+    Color c;
+    c.r = cols[4 * i];
+    c.g = cols[4 * i + 1];
+    c.b = cols[4 * i + 2];
+    c.a = cols[4 * i + 3];
+    RayCaster rc(origin, p_G, clearing, cfg.c.voxel_carving_enabled != 0,
+                 cfg.c.max_ray_length_m, cfg.voxel_size_inv, cfg.c.default_truncation_distance);
+    L3 gvi;
+    while (rc.next(&gvi)) {
+      Voxel* v = st.voxel_ptr(cfg, gvi);
+      const float w = voxel_weight(cfg, p_C);
+      update_voxel(cfg, origin, p_G, gvi, c, w, v, NoLock());
+    }
+  }
+  st.commit();
+  if (touched) *touched = st.touched.size();
+  return 0;
+}
+
+// FastTsdfIntegrator, one thread, approximate hash sets reset every call
+// (clear_checks_every_n_frames = 1).
+struct ApproxSet {
+  static constexpr size_t kBits = 20;
+  std::vector<size_t> slots;
+  ApproxSet() : slots(size_t(1) << kBits, ~size_t(0)) {}
+  bool replace(const L3& idx) {
+    const size_t h = L3Hash()(idx);
+    size_t& s = slots[h & ((size_t(1) << kBits) - 1)];
+    if (s == h) return false;
+    s = h;
+    return true;
+  }
+};
+
+int integrate_fast(orc_layer* layer, const Cfg& cfg, const Xform& T, const float* pts,
+                   const uint8_t* cols, size_t n, bool freespace, uint64_t* touched) {
+  CallStorage st(layer);
+  IndexOrder order(n, cfg.c.integration_order_mode);
+  ApproxSet start_set, observed_set;
+  const V3 origin = T.t;
+  for (size_t k = 0; k < n; ++k) {
+    const size_t i = order.at(k);
+    const V3 p_C = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    bool clearing = false;
+    if (!point_valid(cfg, p_C, freespace, &clearing)) continue;
+    const V3 p_G = apply(T, p_C);
+    Color c;
+    c.r = cols[4 * i];
+    c.g = cols[4 * i + 1];
+    c.b = cols[4 * i + 2];
+    c.a = cols[4 * i + 3];
+    L3 gvi = grid_index_long(p_G, cfg.c.start_voxel_subsampling_factor * cfg.voxel_size_inv);
+    if (!start_set.replace(gvi)) continue;
+    RayCaster rc(origin, p_G, clearing, cfg.c.voxel_carving_enabled != 0,
+                 cfg.c.max_ray_length_m, cfg.voxel_size_inv, cfg.c.default_truncation_distance,
+                 /*cast_from_origin=*/false);
+    int64_t collisions = 0;
+    while (rc.next(&gvi)) {
+      if (!observed_set.replace(gvi))
+        ++collisions;
+      else
+        collisions = 0;
+      if (collisions > cfg.c.max_consecutive_ray_collisions) break;
+      Voxel* v = st.voxel_ptr(cfg, gvi);
+      const float w = voxel_weight(cfg, p_C);
+      update_voxel(cfg, origin, p_G, gvi, c, w, v, NoLock());
+    }
+  }
+  st.commit();
+  if (touched) *touched = st.touched.size();
+  return 0;
+}
+
+// ---------------------------------------------------------------- threaded timing variant
+struct MtStorage {
+  orc_layer* layer;
+  BlockMap temp;
+  std::mutex temp_mutex;
+  explicit MtStorage(orc_layer* l) : layer(l) {}
+  Voxel* voxel_ptr(const Cfg& cfg, L3 gvi) {
+    const I3 bi = block_of_voxel(gvi, cfg.vps_inv);
+    Block* b = layer->find(bi);
+    if (!b) {
+      std::lock_guard<std::mutex> g(temp_mutex);
+      auto& p = temp[bi];
+      if (!p) p.reset(new Block());
+      b = p.get();
+    }
+    b->updated = true;
+    return &b->voxels[local_linear(gvi)];
+  }
+  void commit() {
+    for (auto& kv : temp) layer->blocks[kv.first] = std::move(kv.second);
+    temp.clear();
+  }
+};
+struct StripedLocks {  // voxblox ApproxHashArray<12, std::mutex, ...>
+  std::mutex m[4096];
+  std::unique_lock<std::mutex> operator()(const L3& i) {
+    return std::unique_lock<std::mutex>(m[L3Hash()(i) & 4095]);
+  }
+};
+
+int integrate_mt(orc_layer* layer, const Cfg& cfg, const Xform& T, const float* pts,
+                 const uint8_t* cols, size_t n, bool freespace, int threads) {
+  if (threads < 1) threads = 1;
+  static StripedLocks locks;
+  MtStorage st(layer);
+  const V3 origin = T.t;
+  if (cfg.c.method == 1) {
+    std::vector<Bundle> normal, clear;
+    bundle_rays(cfg, T, pts, n, freespace, &normal, &clear);
+    for (int pass = 0; pass < 2; ++pass) {
+      const auto& list = pass == 0 ? normal : clear;
+      std::vector<std::thread> pool;
+      for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&, t, pass]() {
+          for (size_t i = t; i < list.size(); i += threads)
+            integrate_bundle(cfg, T, pts, cols, list[i], pass == 1, nullptr, st, locks);
+        });
+      for (auto& th : pool) th.join();
+      st.commit();
+    }
+    return 0;
+  }
+  if (cfg.c.method != 0) return -2;  // fast: single thread only in this oracle
+  std::atomic<size_t> counter{0};
+  IndexOrder order(n, cfg.c.integration_order_mode);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&]() {
+      size_t k;
+      while ((k = counter.fetch_add(1)) < n) {
+        const size_t i = order.at(k);
+        const V3 p_C = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+        bool clearing = false;
+        if (!point_valid(cfg, p_C, freespace, &clearing)) continue;
+        const V3 p_G = apply(T, p_C);
+        Color c;
+        c.r = cols[4 * i];
+        c.g = cols[4 * i + 1];
+        c.b = cols[4 * i + 2];
+        c.a = cols[4 * i + 3];
+        RayCaster rc(origin, p_G, clearing, cfg.c.voxel_carving_enabled != 0,
+                     cfg.c.max_ray_length_m, cfg.voxel_size_inv,
+                     cfg.c.default_truncation_distance);
+        L3 gvi;
+        while (rc.next(&gvi)) {
+          Voxel* v = st.voxel_ptr(cfg, gvi);
+          update_voxel(cfg, origin, p_G, gvi, c, voxel_weight(cfg, p_C), v, locks);
+        }
+      }
+    });
+  for (auto& th : pool) th.join();
+  st.commit();
+  return 0;
+}
+
+// ---------------------------------------------------------------- R8/R9 Interpolator
+inline I3 block_index_from_coords(const orc_layer& L, V3 p) {
+  return grid_index_int(p, L.block_size_inv);
+}
+inline V3 block_origin(const orc_layer& L, I3 bi) { return origin_point(bi, L.block_size); }
+inline V3 voxel_coords(const orc_layer& L, I3 bi, I3 vi) {  // computeCoordinatesFromVoxelIndex
+  const V3 o = block_origin(L, bi);
+  const V3 c = center_point(L3{vi.x, vi.y, vi.z}, L.voxel_size);
+  return o + c;
+}
+inline int linear_of(I3 v) { return v.x + kVps * (v.y + kVps * v.z); }
+
+// 8x8 table from the SPIE PM159 trilinear formulation used by voxblox
+const int kInterpTable[8][8] = {
+    {1, 0, 0, 0, 0, 0, 0, 0},   {-1, 0, 0, 0, 1, 0, 0, 0},  {-1, 0, 1, 0, 0, 0, 0, 0},
+    {-1, 1, 0, 0, 0, 0, 0, 0},  {1, 0, -1, 0, -1, 0, 1, 0}, {1, -1, -1, 1, 0, 0, 0, 0},
+    {1, -1, 0, 0, -1, 1, 0, 0}, {-1, 1, 1, -1, 1, -1, -1, 1}};
+
+inline float interp_member(const float q[8], const float data[8]) {
+  // q . (M . data); rows accumulated left to right over the non-zero entries, then the
+  // dot product accumulated left to right (order fixed by this oracle).
+  float acc = 0.0f;
+  for (int r = 0; r < 8; ++r) {
+    float row = 0.0f;
+    bool first = true;
+    for (int c = 0; c < 8; ++c) {
+      const int m = kInterpTable[r][c];
+      if (m == 0) continue;
+      const float term = (m > 0) ? data[c] : -data[c];
+      row = first ? term : row + term;
+      first = false;
+    }
+    const float prod = q[r] * row;
+    acc = (r == 0) ? prod : acc + prod;
+  }
+  return acc;
+}
+inline uint8_t trunc_u8(float v) {  // static_cast<uint8_t>(float): truncation; clamped here
+  if (!(v > 0.0f)) return 0;
+  if (v >= 255.0f) return 255;
+  return static_cast<uint8_t>(static_cast<int>(v));
+}
+
+bool interp_trilinear(const orc_layer& L, V3 pos, Voxel* out) {
+  // setIndexes
+  I3 bi = block_index_from_coords(L, pos);
+  if (!L.find(bi)) return false;
+  const V3 rel = pos - block_origin(L, bi);
+  I3 vi = grid_index_int(rel, L.voxel_size_inv);  // un-clamped
+  const V3 off = pos - voxel_coords(L, bi, vi);
+  int* vip[3] = {&vi.x, &vi.y, &vi.z};
+  int* bip[3] = {&bi.x, &bi.y, &bi.z};
+  const float offs[3] = {off.x, off.y, off.z};
+  for (int a = 0; a < 3; ++a) {
+    if (offs[a] < 0.0f) {
+      (*vip[a])--;
+      if (*vip[a] < 0) {
+        (*bip[a])--;
+        *vip[a] += kVps;
+      }
+    }
+  }
+  static const int kOff[8][3] = {{0, 0, 0}, {0, 0, 1}, {0, 1, 0}, {0, 1, 1},
+                                 {1, 0, 0}, {1, 0, 1}, {1, 1, 0}, {1, 1, 1}};
+  const Voxel* vox[8];
+  float q[8];
+  for (int i = 0; i < 8; ++i) {
+    // getVoxelsAndQVector: the base block must exist for every neighbour
+    const Block* blk = L.find(bi);
+    if (!blk) return false;
+    I3 nvi = {vi.x + kOff[i][0], vi.y + kOff[i][1], vi.z + kOff[i][2]};
+    I3 nbi = bi;
+    if (nvi.x >= kVps || nvi.y >= kVps || nvi.z >= kVps) {
+      if (nvi.x >= kVps) {
+        nbi.x++;
+        nvi.x -= kVps;
+      }
+      if (nvi.y >= kVps) {
+        nbi.y++;
+        nvi.y -= kVps;
+      }
+      if (nvi.z >= kVps) {
+        nbi.z++;
+        nvi.z -= kVps;
+      }
+      blk = L.find(nbi);
+      if (!blk) return false;
+    }
+    if (i == 0) {  // getQVector
+      const V3 vpos = voxel_coords(L, nbi, nvi);
+      const V3 o = (pos - vpos) * L.voxel_size_inv;
+      q[0] = 1.0f;
+      q[1] = o.x;
+      q[2] = o.y;
+      q[3] = o.z;
+      q[4] = o.x * o.y;
+      q[5] = o.y * o.z;
+      q[6] = o.z * o.x;
+      q[7] = o.x * o.y * o.z;
+    }
+    const Voxel& v = blk->voxels[linear_of(nvi)];
+    vox[i] = &v;
+    if (!(v.weight > kEps)) return false;  // utils::isObservedVoxel
+  }
+  float d[8];
+  for (int i = 0; i < 8; ++i) d[i] = vox[i]->distance;
+  out->distance = interp_member(q, d);
+  for (int i = 0; i < 8; ++i) d[i] = vox[i]->weight;
+  out->weight = interp_member(q, d);
+  for (int i = 0; i < 8; ++i) d[i] = static_cast<float>(vox[i]->color.r);
+  out->color.r = trunc_u8(interp_member(q, d));
+  for (int i = 0; i < 8; ++i) d[i] = static_cast<float>(vox[i]->color.g);
+  out->color.g = trunc_u8(interp_member(q, d));
+  for (int i = 0; i < 8; ++i) d[i] = static_cast<float>(vox[i]->color.b);
+  out->color.b = trunc_u8(interp_member(q, d));
+  for (int i = 0; i < 8; ++i) d[i] = static_cast<float>(vox[i]->color.a);
+  out->color.a = trunc_u8(interp_member(q, d));
+  return true;
+}
+
+bool interp_nearest(const orc_layer& L, V3 pos, Voxel* out) {  // R9
+  const I3 bi = block_index_from_coords(L, pos);
+  const Block* blk = L.find(bi);
+  if (!blk) return false;
+  const V3 rel = pos - block_origin(L, bi);
+  I3 vi = grid_index_int(rel, L.voxel_size_inv);
+  vi.x = std::max(std::min(vi.x, kVps - 1), 0);
+  vi.y = std::max(std::min(vi.y, kVps - 1), 0);
+  vi.z = std::max(std::min(vi.z, kVps - 1), 0);
+  *out = blk->voxels[linear_of(vi)];
+  return out->weight > kEps;
+}
+
+// ---------------------------------------------------------------- R7 transformLayer, R10 merge
+void candidate_blocks(const orc_layer& in, const Xform& T, float block_size_out,
+                      std::vector<I3>* out) {
+  std::unordered_set<I3, I3Hash> set;
+  const float inv_out = 1.0f / block_size_out;
+  const float kDiag = static_cast<float>(std::sqrt(3.0));
+  for (const auto& kv : in.blocks) {
+    const I3 bi = kv.first;
+    const V3 c_in = center_point(L3{bi.x, bi.y, bi.z}, in.block_size);
+    const V3 c_out = apply(T, c_in);
+    const float offset = kDiag * in.block_size * 0.5f;
+    for (float x = c_out.x - offset; x < c_out.x + offset; x += block_size_out)
+      for (float y = c_out.y - offset; y < c_out.y + offset; y += block_size_out)
+        for (float z = c_out.z - offset; z < c_out.z + offset; z += block_size_out)
+          set.insert(grid_index_int(V3{x, y, z}, inv_out));
+  }
+  out->assign(set.begin(), set.end());
+  std::sort(out->begin(), out->end(), zyx_less_i);
+}
+
+// resample one candidate block of the output grid; returns has_data
+bool resample_block(const orc_layer& in, const orc_layer& grid_out, const Xform& T_in_out, I3 bi,
+                    Block* blk) {
+  bool has = false;
+  for (int lin = 0; lin < kVoxelsPerBlock; ++lin) {
+    const I3 vi = {lin % kVps, (lin / kVps) % kVps, lin / (kVps * kVps)};
+    const V3 center_out = voxel_coords(grid_out, bi, vi);
+    const V3 p = apply(T_in_out, center_out);
+    Voxel v;
+    if (interp_trilinear(in, p, &v)) {
+      blk->voxels[lin] = v;
+      has = true;
+    } else if (interp_nearest(in, p, &v)) {
+      blk->voxels[lin] = v;
+      has = true;
+    } else {
+      // upstream passes the destination voxel itself into getVoxel; a failed nearest
+      // lookup that found a block still overwrites it with the unobserved source voxel
+      // (v stays default-constructed when no block was found).
+      blk->voxels[lin] = v;
+    }
+  }
+  return has;
+}
+
+inline void merge_voxel(const Voxel& a, Voxel* b) {  // mergeVoxelAIntoVoxelB
+  const float cw = a.weight + b->weight;
+  if (cw > 0.0f) {
+    b->distance = (a.distance * a.weight + b->distance * b->weight) / cw;
+    b->color = blend(a.color, a.weight, b->color, b->weight);
+    b->weight = cw;
+  }
+}
+
+int merge_layers(const orc_layer* A, const Xform& T_B_A, orc_layer* B, int threads,
+                 uint64_t* blocks_out) {
+  std::vector<I3> cand;
+  candidate_blocks(*A, T_B_A, B->block_size, &cand);
+  const Xform T_A_B = inverse(T_B_A);
+  std::vector<std::unique_ptr<Block>> temp(cand.size());
+  std::vector<char> has(cand.size(), 0);
+  auto work = [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i) {
+      temp[i].reset(new Block());
+      has[i] = resample_block(*A, *B, T_A_B, cand[i], temp[i].get()) ? 1 : 0;
+    }
+  };
+  if (threads <= 1) {
+    work(0, cand.size());
+  } else {
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+      pool.emplace_back([&]() {
+        size_t i;
+        while ((i = next.fetch_add(8)) < cand.size()) work(i, std::min(cand.size(), i + 8));
+      });
+    for (auto& th : pool) th.join();
+  }
+  uint64_t nout = 0;
+  for (size_t i = 0; i < cand.size(); ++i) {
+    if (!has[i]) continue;  // block removed from the transformed layer
+    ++nout;
+    Block* dst = B->get_or_create(cand[i]);
+    dst->has_data = true;
+    dst->updated = true;
+    for (int lin = 0; lin < kVoxelsPerBlock; ++lin)
+      merge_voxel(temp[i]->voxels[lin], &dst->voxels[lin]);
+  }
+  if (blocks_out) *blocks_out = nout;
+  return 0;
+}
+
+Cfg make_cfg(const orc_layer* layer, const orc_integrator_config* c) {
+  Cfg cfg;
+  cfg.c = *c;
+  cfg.voxel_size = layer->voxel_size;
+  cfg.voxel_size_inv = layer->voxel_size_inv;
+  cfg.vps_inv = layer->vps_inv;
+  return cfg;
+}
+
+}  // namespace
+
+// ================================================================== C interface
+extern "C" {
+
+void orc_default_config(orc_integrator_config* c) {
+  c->default_truncation_distance = 0.1f;
+  c->max_weight = 10000.0f;
+  c->voxel_carving_enabled = 1;
+  c->min_ray_length_m = 0.1f;
+  c->max_ray_length_m = 5.0f;
+  c->use_const_weight = 0;
+  c->allow_clear = 1;
+  c->use_weight_dropoff = 1;
+  c->use_sparsity_compensation_factor = 0;
+  c->sparsity_compensation_factor = 1.0f;
+  c->enable_anti_grazing = 0;
+  c->method = 1;
+  c->integration_order_mode = 0;
+  c->start_voxel_subsampling_factor = 2.0f;
+  c->max_consecutive_ray_collisions = 2;
+}
+
+orc_layer* orc_layer_create(float voxel_size, int32_t vps) {
+  if (vps != kVps || !(voxel_size > 0.0f)) return nullptr;
+  orc_layer* l = new orc_layer();
+  l->voxel_size = voxel_size;
+  l->voxel_size_inv = 1.0f / voxel_size;
+  l->block_size = voxel_size * static_cast<float>(vps);
+  l->block_size_inv = 1.0f / l->block_size;
+  l->vps_inv = 1.0f / static_cast<float>(vps);
+  return l;
+}
+void orc_layer_destroy(orc_layer* l) { delete l; }
+void orc_layer_clear(orc_layer* l) { l->blocks.clear(); }
+size_t orc_layer_num_blocks(const orc_layer* l) { return l->blocks.size(); }
+
+void orc_layer_download(const orc_layer* l, int32_t* idx, void* voxels, uint8_t* flags) {
+  std::vector<I3> keys;
+  keys.reserve(l->blocks.size());
+  for (const auto& kv : l->blocks) keys.push_back(kv.first);
+  std::sort(keys.begin(), keys.end(), zyx_less_i);
+  for (size_t i = 0; i < keys.size(); ++i) {
+    const Block* b = l->find(keys[i]);
+    if (idx) {
+      idx[3 * i] = keys[i].x;
+      idx[3 * i + 1] = keys[i].y;
+      idx[3 * i + 2] = keys[i].z;
+    }
+    if (voxels)
+      std::memcpy(static_cast<char*>(voxels) + i * sizeof(Voxel) * kVoxelsPerBlock, b->voxels,
+                  sizeof(Voxel) * kVoxelsPerBlock);
+    if (flags) flags[i] = (b->has_data ? 1 : 0) | (b->updated ? 2 : 0);
+  }
+}
+
+void orc_layer_upload(orc_layer* l, const int32_t* idx, const void* voxels, const uint8_t* flags,
+                      size_t n) {
+  for (size_t i = 0; i < n; ++i) {
+    Block* b = l->get_or_create(I3{idx[3 * i], idx[3 * i + 1], idx[3 * i + 2]});
+    std::memcpy(b->voxels, static_cast<const char*>(voxels) + i * sizeof(Voxel) * kVoxelsPerBlock,
+                sizeof(Voxel) * kVoxelsPerBlock);
+    b->has_data = flags ? (flags[i] & 1) != 0 : true;
+    b->updated = flags ? (flags[i] & 2) != 0 : false;
+  }
+}
+
+int32_t orc_integrate_pointcloud(orc_layer* layer, const orc_integrator_config* c,
+                                 const float T[7], const float* pts, const uint8_t* cols,
+                                 size_t n, int32_t freespace, uint64_t* touched) {
+  if (!layer || !c || !T || (n && (!pts || !cols))) return -1;
+  const Cfg cfg = make_cfg(layer, c);
+  const Xform X = load_xform(T);
+  switch (c->method) {
+    case 0:
+      return integrate_simple(layer, cfg, X, pts, cols, n, freespace != 0, touched);
+    case 1:
+      return integrate_merged(layer, cfg, X, pts, cols, n, freespace != 0, touched);
+    case 2:
+      return integrate_fast(layer, cfg, X, pts, cols, n, freespace != 0, touched);
+  }
+  return -2;
+}
+
+int32_t orc_integrate_pointcloud_mt(orc_layer* layer, const orc_integrator_config* c,
+                                    const float T[7], const float* pts, const uint8_t* cols,
+                                    size_t n, int32_t freespace, int32_t threads) {
+  if (!layer || !c || !T || (n && (!pts || !cols))) return -1;
+  return integrate_mt(layer, make_cfg(layer, c), load_xform(T), pts, cols, n, freespace != 0,
+                      threads);
+}
+
+int32_t orc_merge_layer_into_layer(const orc_layer* a, const float T[7], orc_layer* b,
+                                   uint64_t* blocks_out) {
+  if (!a || !b || !T) return -1;
+  return merge_layers(a, load_xform(T), b, 1, blocks_out);
+}
+int32_t orc_merge_layer_into_layer_mt(const orc_layer* a, const float T[7], orc_layer* b,
+                                      int32_t threads, uint64_t* blocks_out) {
+  if (!a || !b || !T) return -1;
+  return merge_layers(a, load_xform(T), b, threads, blocks_out);
+}
+
+void orc_transform_point(const float T[7], const float p[3], float out[3]) {
+  const V3 r = apply(load_xform(T), V3{p[0], p[1], p[2]});
+  out[0] = r.x;
+  out[1] = r.y;
+  out[2] = r.z;
+}
+void orc_inverse_transform(const float T[7], float Ti[7]) {
+  const Xform i = inverse(load_xform(T));
+  Ti[0] = i.w;
+  Ti[1] = i.v.x;
+  Ti[2] = i.v.y;
+  Ti[3] = i.v.z;
+  Ti[4] = i.t.x;
+  Ti[5] = i.t.y;
+  Ti[6] = i.t.z;
+}
+size_t orc_cast_ray(const float o[3], const float p[3], int32_t clearing, int32_t carving,
+                    float max_ray, float vinv, float trunc, int32_t from_origin, int64_t* out,
+                    size_t cap) {
+  RayCaster rc(V3{o[0], o[1], o[2]}, V3{p[0], p[1], p[2]}, clearing != 0, carving != 0, max_ray,
+               vinv, trunc, from_origin != 0);
+  size_t n = 0;
+  L3 g;
+  while (rc.next(&g)) {
+    if (n < cap) {
+      out[3 * n] = g.x;
+      out[3 * n + 1] = g.y;
+      out[3 * n + 2] = g.z;
+    }
+    ++n;
+  }
+  return n;
+}
+int32_t orc_interp_voxel(const orc_layer* l, const float pos[3], int32_t interpolate, float* d,
+                         float* w, uint8_t rgba[4]) {
+  Voxel v;
+  const V3 p = {pos[0], pos[1], pos[2]};
+  const bool ok = interpolate ? interp_trilinear(*l, p, &v) : interp_nearest(*l, p, &v);
+  if (d) *d = v.distance;
+  if (w) *w = v.weight;
+  if (rgba) {
+    rgba[0] = v.color.r;
+    rgba[1] = v.color.g;
+    rgba[2] = v.color.b;
+    rgba[3] = v.color.a;
+  }
+  return ok ? 1 : 0;
+}
+
+}  // extern "C"

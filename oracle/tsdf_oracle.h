@@ -1,0 +1,105 @@
+/*
+ * tsdf_oracle.h — C interface of the CPU ORACLE for the coxgraph TSDF hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and there only as the checker / CPU baseline.
+ *
+ * PARITY UNPINNED: the reference tree (/root/reference) holds no source of the
+ * arithmetic on this path (it lives in the un-vendored forks LXYYY/voxblox,
+ * LXYYY/cblox, LXYYY/voxgraph, branch names only, coxgraph_ssh.rosinstall:1-8,55-58),
+ * no tests and no golden vectors.  This oracle restates the published upstream
+ * voxblox algorithm (integrator/tsdf_integrator.cc, integrator/integrator_utils.cc,
+ * integrator/merge_integration.h, interpolator/interpolator_inl.h, core/voxel.cc,
+ * core/color.h, core/common.h) and is anchored on the reference's call sites:
+ *   coxgraph/include/coxgraph/map_comm/tsdf_recover.h:59-99 (integratePointCloud :75)
+ *   coxgraph/src/client/map_server.cpp:59-73            (mergeLayerAintoLayerB :67-69)
+ *   coxgraph/src/server/visualizer/server_visualizer.cpp:123-126 (getProjectedMap)
+ * It is pinned by analytic / algebraic known-answer tests (tests/test_oracle_*.py)
+ * and by frozen digests under tests/golden/.
+ */
+#ifndef TSDF_ORACLE_H_
+#define TSDF_ORACLE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_layer orc_layer;
+
+/* Mirrors voxblox::TsdfIntegratorBase::Config (upstream defaults in comments). */
+typedef struct orc_integrator_config {
+  float default_truncation_distance;  /* 0.1 */
+  float max_weight;                   /* 10000 */
+  int32_t voxel_carving_enabled;      /* 1 */
+  float min_ray_length_m;             /* 0.1 */
+  float max_ray_length_m;             /* 5.0 */
+  int32_t use_const_weight;           /* 0 */
+  int32_t allow_clear;                /* 1 */
+  int32_t use_weight_dropoff;         /* 1 */
+  int32_t use_sparsity_compensation_factor; /* 0 */
+  float sparsity_compensation_factor; /* 1.0 */
+  int32_t enable_anti_grazing;        /* 0 */
+  int32_t method;                     /* 0 simple, 1 merged, 2 fast */
+  int32_t integration_order_mode;     /* 0 mixed (default), 1 natural index order */
+  float start_voxel_subsampling_factor;     /* 2.0 (fast) */
+  int32_t max_consecutive_ray_collisions;   /* 2   (fast) */
+} orc_integrator_config;
+
+void orc_default_config(orc_integrator_config* cfg);
+
+orc_layer* orc_layer_create(float voxel_size, int32_t voxels_per_side);
+void orc_layer_destroy(orc_layer* layer);
+void orc_layer_clear(orc_layer* layer); /* Layer::removeAllBlocks */
+size_t orc_layer_num_blocks(const orc_layer* layer);
+
+/* Blocks are returned sorted by (z, y, x) block index.  voxels: B*4096 records of
+ * {float distance; float weight; uint8 r,g,b,a} (voxblox TsdfVoxel AoS, linear index
+ * x + 16*(y + 16*z)).  flags: bit0 has_data, bit1 updated.  Any pointer may be NULL. */
+void orc_layer_download(const orc_layer* layer, int32_t* block_idx_xyz, void* voxels,
+                        uint8_t* flags);
+void orc_layer_upload(orc_layer* layer, const int32_t* block_idx_xyz, const void* voxels,
+                      const uint8_t* flags, size_t num_blocks);
+
+/* TsdfIntegratorBase::integratePointCloud(T_G_C, points_C, colors, freespace_points).
+ * T = {qw,qx,qy,qz,tx,ty,tz}.  Single thread, canonical deterministic order.
+ * Returns 0, or <0 on error.  *blocks_touched (optional) = distinct blocks visited. */
+int32_t orc_integrate_pointcloud(orc_layer* layer, const orc_integrator_config* cfg,
+                                 const float T_G_C[7], const float* points_xyz,
+                                 const uint8_t* colors_rgba, size_t n,
+                                 int32_t freespace_points, uint64_t* blocks_touched);
+
+/* Timing variant: voxblox-style threading (striped voxel mutexes, allocation mutex).
+ * Result is order-nondeterministic like the real thing; used only as CPU baseline. */
+int32_t orc_integrate_pointcloud_mt(orc_layer* layer, const orc_integrator_config* cfg,
+                                    const float T_G_C[7], const float* points_xyz,
+                                    const uint8_t* colors_rgba, size_t n,
+                                    int32_t freespace_points, int32_t threads);
+
+/* voxblox::mergeLayerAintoLayerB(layer_A, T_B_A, layer_B) = transformLayer + merge.
+ * *blocks_out (optional) = blocks of the transformed layer that carried data. */
+int32_t orc_merge_layer_into_layer(const orc_layer* layer_a, const float T_B_A[7],
+                                   orc_layer* layer_b, uint64_t* blocks_out);
+/* Same, candidate blocks resampled by `threads` workers (block-parallel; deterministic). */
+int32_t orc_merge_layer_into_layer_mt(const orc_layer* layer_a, const float T_B_A[7],
+                                      orc_layer* layer_b, int32_t threads,
+                                      uint64_t* blocks_out);
+
+/* Small pieces exposed for known-answer tests. */
+void orc_transform_point(const float T[7], const float p[3], float out[3]);
+void orc_inverse_transform(const float T[7], float Tinv[7]);
+/* Ray-cast; writes up to cap voxel indices (int64 xyz), returns number produced. */
+size_t orc_cast_ray(const float origin[3], const float point_G[3], int32_t clearing,
+                    int32_t carving, float max_ray, float voxel_size_inv, float trunc,
+                    int32_t cast_from_origin, int64_t* out_xyz, size_t cap);
+/* Interpolator<TsdfVoxel>::getVoxel(pos, &voxel, interpolate). returns 1 on success. */
+int32_t orc_interp_voxel(const orc_layer* layer, const float pos[3], int32_t interpolate,
+                         float* distance, float* weight, uint8_t rgba[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSDF_ORACLE_H_ */
