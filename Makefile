@@ -1,0 +1,30 @@
+# Builds libcoxgraph_b200.so (sm_100a only) and the CPU oracle (test infrastructure).
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH  = -gencode arch=compute_100a,code=sm_100a
+# -fmad=false / -ffp-contract=off: no FMA contraction anywhere — every float op on the path is
+# the plain IEEE single-precision one, which is what makes block allocation bit-exact.
+NVFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
+          -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-Wall -Iinclude --expt-relaxed-constexpr
+SRC  = coxgraph_b200/csrc
+OBJ  = build/obj
+LIB  = coxgraph_b200/lib/libcoxgraph_b200.so
+HDRS = $(SRC)/cg_math.cuh $(SRC)/cg_internal.cuh include/coxgraph_b200.h
+OBJS = $(OBJ)/layer.o $(OBJ)/integrate.o $(OBJ)/merge.o $(OBJ)/exchange.o
+
+all: $(LIB) oracle
+
+$(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	@mkdir -p coxgraph_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
+
+oracle:
+	$(MAKE) -C oracle -s
+
+clean:
+	rm -rf build coxgraph_b200/lib oracle/_build
+
+.PHONY: all oracle clean

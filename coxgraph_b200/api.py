@@ -1,0 +1,199 @@
+"""Host-side mirror of the reference's interface for the hot path, on top of the C ABI.
+
+Names and argument meaning follow the calls the reference makes into voxblox / cblox:
+  * ``TsdfIntegrator.integratePointCloud(T_G_C, points_C, colors, freespace_points=False)``
+    — voxblox::TsdfIntegratorBase::integratePointCloud, called at
+    coxgraph/include/coxgraph/map_comm/tsdf_recover.h:75;
+  * ``mergeLayerAintoLayerB(layer_A, T_B_A, layer_B)`` — coxgraph/src/client/map_server.cpp:67-69;
+  * ``getProjectedMap(submaps, poses, global_layer)`` — cblox SubmapCollection::getProjectedMap,
+    reached from coxgraph/src/server/visualizer/server_visualizer.cpp:123-126;
+  * ``Layer.removeAllBlocks()`` — tsdf_recover.h:62, map_server.cpp:65.
+The C++ twin of this file is coxgraph_b200/host/coxgraph_b200.hpp.  Inputs may be numpy arrays
+(host memory; copied by the library inside the call) or torch CUDA tensors (device memory on the
+layer's GPU; no copy).  Errors raise CgError — the reference aborts through glog CHECK instead.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+VOXEL_DTYPE = np.dtype([("distance", "<f4"), ("weight", "<f4"), ("rgba", "u1", (4,))])
+
+
+def _is_cuda_tensor(x):
+    return hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def TsdfIntegratorConfig(**overrides):
+    """voxblox::TsdfIntegratorBase::Config with the upstream defaults."""
+    cfg = capi.IntegratorConfig()
+    capi.load().cg_integrator_config_default(C.byref(cfg))
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(f"unknown integrator config field {k}")
+        setattr(cfg, k, v)
+    return cfg
+
+
+class Context:
+    """One per GPU (per process rank)."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        capi.check(capi.load().cg_context_create(int(device), C.c_void_p(stream or 0),
+                                                 C.byref(self._h)))
+        self.device = int(device)
+
+    def synchronize(self):
+        capi.check(capi.load().cg_context_synchronize(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.load().cg_context_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Layer:
+    """voxblox::Layer<TsdfVoxel> living in HBM (block hash + block pool)."""
+
+    def __init__(self, ctx, voxel_size, voxels_per_side=16, max_blocks=4096):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        capi.check(capi.load().cg_layer_create(ctx._h, float(voxel_size), int(voxels_per_side),
+                                               int(max_blocks), C.byref(self._h)))
+        self.voxel_size = float(np.float32(voxel_size))
+        self.max_blocks = int(max_blocks)
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            capi.load().cg_layer_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def removeAllBlocks(self):
+        capi.check(capi.load().cg_layer_clear(self._h))
+
+    clear = removeAllBlocks
+
+    def getNumberOfAllocatedBlocks(self):
+        return int(capi.load().cg_layer_num_blocks(self._h))
+
+    num_blocks = property(getNumberOfAllocatedBlocks)
+
+    def block_indices(self):
+        n = self.num_blocks
+        idx = np.zeros((n, 3), np.int32)
+        out = C.c_size_t(0)
+        capi.check(capi.load().cg_layer_block_indices(self._h, n, _ptr(idx), C.byref(out)))
+        return idx
+
+    def download(self):
+        """-> (block_idx int32 [B,3] sorted (z,y,x), voxels [B,4096] VOXEL_DTYPE, flags u8 [B])."""
+        n = self.num_blocks
+        idx = np.zeros((n, 3), np.int32)
+        vox = np.zeros((n, capi.VOXELS_PER_BLOCK), VOXEL_DTYPE)
+        flags = np.zeros((n,), np.uint8)
+        out = C.c_size_t(0)
+        capi.check(capi.load().cg_layer_download(self._h, n, _ptr(idx), _ptr(vox), _ptr(flags),
+                                                 C.byref(out)))
+        return idx, vox, flags
+
+    def upload(self, block_idx, voxels, flags=None):
+        idx = np.ascontiguousarray(block_idx, np.int32).reshape(-1, 3)
+        vox = np.ascontiguousarray(voxels, VOXEL_DTYPE).reshape(len(idx), capi.VOXELS_PER_BLOCK)
+        fl = None if flags is None else np.ascontiguousarray(flags, np.uint8)
+        capi.check(capi.load().cg_layer_upload(self._h, len(idx), _ptr(idx), _ptr(vox),
+                                               None if fl is None else _ptr(fl)))
+
+
+class TsdfIntegrator:
+    """Drop-in for voxblox::TsdfIntegratorBase (Simple / Merged) bound to one layer."""
+
+    def __init__(self, config, layer):
+        self.config = config
+        self.layer = layer
+        self.last_stats = capi.IntegrateStats()
+
+    def integratePointCloud(self, T_G_C, points_C, colors, freespace_points=False):
+        lib = capi.load()
+        T = np.ascontiguousarray(T_G_C, np.float32).reshape(7)
+        if _is_cuda_tensor(points_C):
+            assert points_C.dtype.is_floating_point and points_C.element_size() == 4
+            assert points_C.is_contiguous() and colors.is_contiguous() and _is_cuda_tensor(colors)
+            n = points_C.numel() // 3
+            assert colors.numel() * colors.element_size() == 4 * n
+            capi.check(lib.cg_integrate_pointcloud_device(
+                self.layer._h, C.byref(self.config), _ptr(T), C.c_void_p(points_C.data_ptr()),
+                C.c_void_p(colors.data_ptr()), n, int(freespace_points),
+                C.byref(self.last_stats)))
+        else:
+            pts = np.ascontiguousarray(points_C, np.float32).reshape(-1, 3)
+            cols = np.ascontiguousarray(colors, np.uint8).reshape(-1, 4)
+            if len(pts) != len(cols):
+                raise ValueError("points_C and colors differ in length")
+            capi.check(lib.cg_integrate_pointcloud(
+                self.layer._h, C.byref(self.config), _ptr(T), _ptr(pts), _ptr(cols), len(pts),
+                int(freespace_points), C.byref(self.last_stats)))
+        return self.last_stats
+
+    def integrateBatch(self, poses, points_C, colors, frame_offsets, freespace_points=False):
+        """F integratePointCloud calls (the loop of tsdf_recover.h:71-86) as one job."""
+        lib = capi.load()
+        P = np.ascontiguousarray(poses, np.float32).reshape(-1, 7)
+        offs = np.ascontiguousarray(frame_offsets, np.uint64).reshape(-1)
+        if len(offs) != len(P) + 1:
+            raise ValueError("frame_offsets must have F+1 entries")
+        if _is_cuda_tensor(points_C):
+            assert points_C.is_contiguous() and colors.is_contiguous() and _is_cuda_tensor(colors)
+            capi.check(lib.cg_integrate_batch_device(
+                self.layer._h, C.byref(self.config), len(P), _ptr(P),
+                C.c_void_p(points_C.data_ptr()), C.c_void_p(colors.data_ptr()), _ptr(offs),
+                int(freespace_points), C.byref(self.last_stats)))
+        else:
+            pts = np.ascontiguousarray(points_C, np.float32).reshape(-1, 3)
+            cols = np.ascontiguousarray(colors, np.uint8).reshape(-1, 4)
+            capi.check(lib.cg_integrate_batch(
+                self.layer._h, C.byref(self.config), len(P), _ptr(P), _ptr(pts), _ptr(cols),
+                _ptr(offs), int(freespace_points), C.byref(self.last_stats)))
+        return self.last_stats
+
+
+def mergeLayerAintoLayerB(layer_A, T_B_A, layer_B):
+    """voxblox::mergeLayerAintoLayerB(layer_A, T_B_A, &layer_B); returns MergeStats."""
+    T = np.ascontiguousarray(T_B_A, np.float32).reshape(7)
+    st = capi.MergeStats()
+    capi.check(capi.load().cg_merge_layer_into_layer(layer_A._h, _ptr(T), layer_B._h,
+                                                     C.byref(st)))
+    return st
+
+
+def getProjectedMap(submap_layers, submap_poses, global_layer, want_stats=False):
+    """cblox SubmapCollection::getProjectedMap(): merge every submap into global_layer in order."""
+    n = len(submap_layers)
+    P = np.ascontiguousarray(submap_poses, np.float32).reshape(n, 7)
+    arr = (C.c_void_p * n)(*[l._h for l in submap_layers])
+    st = capi.MergeStats()
+    capi.check(capi.load().cg_project_submaps(arr, _ptr(P), n, global_layer._h,
+                                              C.byref(st) if want_stats else None))
+    return st if want_stats else None
+
+
+def block_owner(block_idx, nranks):
+    return int(capi.load().cg_block_owner(int(block_idx[0]), int(block_idx[1]),
+                                          int(block_idx[2]), int(nranks)))

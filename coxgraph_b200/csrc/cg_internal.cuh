@@ -1,0 +1,209 @@
+// cg_internal.cuh — context / layer state and the GPU block hash shared by the .cu files.
+//
+// Layer<TsdfVoxel> replacement: an open-addressing hash
+// (packed int3 block index -> pool slot) plus a block pool laid out for coalesced access:
+// each 16^3 block is three 16 KB planes  [distance f32 x4096 | weight f32 x4096 | rgba u32 x4096]
+// (49,152 B, the same size as voxblox's AoS block; converted to AoS only at the boundary).
+// Unallocated pool slots are kept in the default-constructed state (d = 0, w = 0,
+// colour (0,0,0,255)) so that a freshly claimed block needs no initialisation pass.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/coxgraph_b200.h"
+#include "cg_math.cuh"
+
+namespace cg {
+
+constexpr uint64_t kEmptyKey = ~0ull;
+constexpr int kBlockIdxBits = 21;                    // per axis, offset 2^20
+constexpr int kBlockIdxOffset = 1 << 20;
+constexpr int kVoxIdxBits = 20;                      // per axis (bundle keys), offset 2^19
+constexpr int kVoxIdxOffset = 1 << 19;
+constexpr uint64_t kInvalidPointKey = ~0ull;         // sorts behind every valid key
+constexpr int kClearingBit = 60;
+
+enum ErrBits { kErrPoolFull = 1, kErrOutOfRange = 2 };
+
+// ------------------------------------------------------------------ key packing
+__host__ __device__ __forceinline__ uint64_t pack_block_key(int x, int y, int z) {
+  return (static_cast<uint64_t>(static_cast<uint32_t>(z + kBlockIdxOffset)) << 42) |
+         (static_cast<uint64_t>(static_cast<uint32_t>(y + kBlockIdxOffset)) << 21) |
+         static_cast<uint64_t>(static_cast<uint32_t>(x + kBlockIdxOffset));
+}
+__host__ __device__ __forceinline__ void unpack_block_key(uint64_t k, int& x, int& y, int& z) {
+  x = static_cast<int>(k & 0x1FFFFF) - kBlockIdxOffset;
+  y = static_cast<int>((k >> 21) & 0x1FFFFF) - kBlockIdxOffset;
+  z = static_cast<int>((k >> 42) & 0x1FFFFF) - kBlockIdxOffset;
+}
+__device__ __forceinline__ uint64_t pack_voxel_key(int x, int y, int z) {
+  return (static_cast<uint64_t>(static_cast<uint32_t>(z + kVoxIdxOffset)) << 40) |
+         (static_cast<uint64_t>(static_cast<uint32_t>(y + kVoxIdxOffset)) << 20) |
+         static_cast<uint64_t>(static_cast<uint32_t>(x + kVoxIdxOffset));
+}
+__device__ __forceinline__ bool voxel_index_in_range(int x, int y, int z) {
+  return x >= -kVoxIdxOffset && x < kVoxIdxOffset && y >= -kVoxIdxOffset && y < kVoxIdxOffset &&
+         z >= -kVoxIdxOffset && z < kVoxIdxOffset;
+}
+__host__ __device__ __forceinline__ uint32_t hash_key(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return static_cast<uint32_t>(k);
+}
+
+// ------------------------------------------------------------------ device view of a layer
+struct LayerView {
+  uint64_t* hash_keys;   // [hash_cap] packed block key or kEmptyKey
+  int32_t* hash_vals;    // [hash_cap] pool slot (-1: no slot, pool exhausted)
+  uint64_t* block_keys;  // [max_blocks] slot -> packed block key
+  uint8_t* has_data;     // [max_blocks]
+  uint8_t* updated;      // [max_blocks]
+  float* pool;           // [max_blocks * 3 * 4096] planes per block
+  int32_t* num_blocks;   // device counter of claimed slots
+  int32_t* err;          // device error bits
+  uint32_t hash_mask;
+  int32_t max_blocks;
+  float voxel_size, voxel_size_inv, block_size, block_size_inv;
+
+  __device__ __forceinline__ float* dist_plane(int slot) const {
+    return pool + static_cast<size_t>(slot) * (3 * kVoxelsPerBlock);
+  }
+  __device__ __forceinline__ float* weight_plane(int slot) const {
+    return dist_plane(slot) + kVoxelsPerBlock;
+  }
+  __device__ __forceinline__ uint32_t* color_plane(int slot) const {
+    return reinterpret_cast<uint32_t*>(dist_plane(slot) + 2 * kVoxelsPerBlock);
+  }
+
+  // hash entry of `key`, or -1
+  __device__ __forceinline__ int find_entry(uint64_t key) const {
+    uint32_t h = hash_key(key) & hash_mask;
+    for (;;) {
+      const uint64_t k = hash_keys[h];
+      if (k == key) return static_cast<int>(h);
+      if (k == kEmptyKey) return -1;
+      h = (h + 1) & hash_mask;
+    }
+  }
+  __device__ __forceinline__ int find_slot(uint64_t key) const {
+    const int e = find_entry(key);
+    return e < 0 ? -1 : hash_vals[e];
+  }
+  // insert-or-find; returns the hash entry.  The inserting thread claims a pool slot and
+  // publishes it in hash_vals[entry]; other kernels read it after this kernel completes.
+  __device__ __forceinline__ int insert_entry(uint64_t key) const {
+    uint32_t h = hash_key(key) & hash_mask;
+    for (;;) {
+      uint64_t k = hash_keys[h];
+      if (k == key) return static_cast<int>(h);
+      if (k == kEmptyKey) {
+        const unsigned long long old =
+            atomicCAS(reinterpret_cast<unsigned long long*>(&hash_keys[h]), kEmptyKey, key);
+        if (old == kEmptyKey) {
+          const int slot = atomicAdd(num_blocks, 1);
+          if (slot < max_blocks) {
+            hash_vals[h] = slot;
+            block_keys[slot] = key;
+          } else {
+            hash_vals[h] = -1;
+            atomicOr(err, kErrPoolFull);
+          }
+          return static_cast<int>(h);
+        }
+        if (old == key) return static_cast<int>(h);
+      }
+      h = (h + 1) & hash_mask;
+    }
+  }
+};
+
+// ------------------------------------------------------------------ host-side state
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      want = bytes;
+      e = cudaMalloc(&p, want);
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+// counters read back once per call (pinned host mirror)
+struct CallCounters {
+  unsigned long long rays;
+  unsigned long long pairs;
+  unsigned long long touched;
+  unsigned long long candidates;
+  unsigned long long blocks_out;
+  int err;
+  int num_blocks;
+};
+
+}  // namespace cg
+
+struct cg_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+  cg::CallCounters* h_counters = nullptr;  // pinned
+  cg::CallCounters* d_counters = nullptr;
+  // integration scratch
+  cg::DevBuf points, colors, poses, frame_base;
+  cg::DevBuf key_a, key_b, val_a, val_b, flags, scan, cub_tmp;
+  cg::DevBuf rays, ray_count, ray_offset;
+  cg::DevBuf pkey_a, pkey_b, pval_a, pval_b;
+  // merge / transfer scratch
+  cg::DevBuf cand_keys, cand_list, stage_a, stage_b, stage_c;
+};
+
+struct cg_layer {
+  cg_context* ctx = nullptr;
+  cg::LayerView v{};
+  size_t hash_cap = 0;
+  size_t max_blocks = 0;
+  int64_t num_blocks = 0;  // host mirror, refreshed at the end of every mutating call
+};
+
+namespace cg {
+
+void set_error(const char* fmt, ...);
+int32_t cuda_fail(cudaError_t e, const char* what);
+// pulls error bits + num_blocks back from the device; returns the status for the error bits
+int32_t finish_call(cg_layer* layer, CallCounters* out);
+
+#define CG_CUDA(expr)                                         \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return cg::cuda_fail(_e, #expr);   \
+  } while (0)
+
+inline unsigned grid_for(size_t n, unsigned block) {
+  return static_cast<unsigned>((n + block - 1) / block);
+}
+
+}  // namespace cg

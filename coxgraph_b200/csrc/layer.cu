@@ -1,0 +1,418 @@
+// layer.cu — context and Layer<TsdfVoxel> replacement: creation, clear, upload, download.
+// Boundary: include/coxgraph_b200.h.  Reference data contract: voxblox Layer / Block /
+// TsdfVoxel as consumed at coxgraph/include/coxgraph/utils/msg_converter.h:49-50,107-109.
+#include <cub/cub.cuh>
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "cg_internal.cuh"
+
+namespace cg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int32_t cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return CG_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ kernels
+__global__ void k_fill_default(float* pool, size_t first_block, size_t num_blocks) {
+  // one block plane triple = 3 * 4096 words; words [8192, 12288) are the colour plane
+  const size_t words = num_blocks * (3 * kVoxelsPerBlock);
+  uint32_t* p = reinterpret_cast<uint32_t*>(pool + first_block * (3 * kVoxelsPerBlock));
+  for (size_t i = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) * 4; i < words;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x * 4) {
+    const uint32_t in_block = static_cast<uint32_t>(i % (3 * kVoxelsPerBlock));
+    const uint32_t val = in_block >= 2 * kVoxelsPerBlock ? kDefaultColor : 0u;
+    *reinterpret_cast<uint4*>(p + i) = make_uint4(val, val, val, val);
+  }
+}
+
+__global__ void k_read_counters(LayerView L, CallCounters* c) {
+  int n = *L.num_blocks;
+  if (n > L.max_blocks) {
+    n = L.max_blocks;
+    *L.num_blocks = n;
+  }
+  c->num_blocks = n;
+  c->err = *L.err;
+  *L.err = 0;
+}
+
+__global__ void k_iota(uint32_t* v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+
+// planar pool block -> voxblox AoS (one CTA per output block)
+__global__ void k_gather_aos(LayerView L, const uint32_t* slots, int first, int count,
+                             uint32_t* out_words, int32_t* out_idx, uint8_t* out_flags,
+                             const uint64_t* sorted_keys) {
+  const int b = blockIdx.x;
+  if (b >= count) return;
+  const int slot = slots[first + b];
+  const float* d = L.dist_plane(slot);
+  const float* w = L.weight_plane(slot);
+  const uint32_t* c = L.color_plane(slot);
+  uint32_t* o = out_words + static_cast<size_t>(b) * (3 * kVoxelsPerBlock);
+  for (int i = threadIdx.x; i < kVoxelsPerBlock; i += blockDim.x) {
+    o[3 * i + 0] = __float_as_uint(d[i]);
+    o[3 * i + 1] = __float_as_uint(w[i]);
+    o[3 * i + 2] = c[i];
+  }
+  if (threadIdx.x == 0) {
+    int x, y, z;
+    unpack_block_key(sorted_keys[first + b], x, y, z);
+    if (out_idx) {
+      out_idx[3 * b + 0] = x;
+      out_idx[3 * b + 1] = y;
+      out_idx[3 * b + 2] = z;
+    }
+    if (out_flags) out_flags[b] = (L.has_data[slot] ? 1 : 0) | (L.updated[slot] ? 2 : 0);
+  }
+}
+
+__global__ void k_unpack_idx(const uint64_t* sorted_keys, int n, int32_t* out_idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x, y, z;
+  unpack_block_key(sorted_keys[i], x, y, z);
+  out_idx[3 * i] = x;
+  out_idx[3 * i + 1] = y;
+  out_idx[3 * i + 2] = z;
+}
+
+__global__ void k_upload_insert(LayerView L, const int32_t* idx, int n, int32_t* entries) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = idx[3 * i], y = idx[3 * i + 1], z = idx[3 * i + 2];
+  constexpr int lim = kVoxIdxOffset / kVps;  // keeps every voxel index inside +-2^19
+  if (x < -lim || x >= lim || y < -lim || y >= lim || z < -lim || z >= lim) {
+    atomicOr(L.err, kErrOutOfRange);
+    entries[i] = -1;
+    return;
+  }
+  entries[i] = L.insert_entry(pack_block_key(x, y, z));
+}
+
+__global__ void k_upload_write(LayerView L, const int32_t* entries, const uint32_t* in_words,
+                               const uint8_t* flags, int n) {
+  const int b = blockIdx.x;
+  if (b >= n) return;
+  const int e = entries[b];
+  if (e < 0) return;
+  const int slot = L.hash_vals[e];
+  if (slot < 0) return;
+  float* d = L.dist_plane(slot);
+  float* w = L.weight_plane(slot);
+  uint32_t* c = L.color_plane(slot);
+  const uint32_t* in = in_words + static_cast<size_t>(b) * (3 * kVoxelsPerBlock);
+  for (int i = threadIdx.x; i < kVoxelsPerBlock; i += blockDim.x) {
+    d[i] = __uint_as_float(in[3 * i + 0]);
+    w[i] = __uint_as_float(in[3 * i + 1]);
+    c[i] = in[3 * i + 2];
+  }
+  if (threadIdx.x == 0) {
+    const uint8_t f = flags ? flags[b] : 1;
+    L.has_data[slot] = f & 1;
+    L.updated[slot] = (f >> 1) & 1;
+  }
+}
+
+int32_t finish_call(cg_layer* layer, CallCounters* out) {
+  cg_context* ctx = layer->ctx;
+  k_read_counters<<<1, 1, 0, ctx->stream>>>(layer->v, ctx->d_counters);
+  CG_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(CallCounters),
+                          cudaMemcpyDeviceToHost, ctx->stream));
+  CG_CUDA(cudaStreamSynchronize(ctx->stream));
+  CG_CUDA(cudaGetLastError());
+  layer->num_blocks = ctx->h_counters->num_blocks;
+  if (out) *out = *ctx->h_counters;
+  const int err = ctx->h_counters->err;
+  if (err & kErrPoolFull) {
+    set_error("block pool exhausted (max_blocks = %zu)", layer->max_blocks);
+    return CG_ERR_POOL_FULL;
+  }
+  if (err & kErrOutOfRange) {
+    set_error("voxel / block index outside the addressable range");
+    return CG_ERR_OUT_OF_RANGE;
+  }
+  return CG_OK;
+}
+
+// sorted (z,y,x) view of the allocated blocks: keys in ctx->key_b, slots in ctx->val_b
+static int32_t sort_blocks(const cg_layer* layer, const uint64_t** keys, const uint32_t** slots) {
+  cg_context* ctx = layer->ctx;
+  const int n = static_cast<int>(layer->num_blocks);
+  CG_CUDA(ctx->key_b.reserve(sizeof(uint64_t) * n));
+  CG_CUDA(ctx->val_a.reserve(sizeof(uint32_t) * n));
+  CG_CUDA(ctx->val_b.reserve(sizeof(uint32_t) * n));
+  k_iota<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->val_a.as<uint32_t>(), n);
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, layer->v.block_keys, ctx->key_b.as<uint64_t>(),
+                                  ctx->val_a.as<uint32_t>(), ctx->val_b.as<uint32_t>(), n, 0, 63,
+                                  ctx->stream);
+  CG_CUDA(ctx->cub_tmp.reserve(tmp));
+  CG_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, layer->v.block_keys,
+                                          ctx->key_b.as<uint64_t>(), ctx->val_a.as<uint32_t>(),
+                                          ctx->val_b.as<uint32_t>(), n, 0, 63, ctx->stream));
+  *keys = ctx->key_b.as<uint64_t>();
+  *slots = ctx->val_b.as<uint32_t>();
+  return CG_OK;
+}
+
+}  // namespace cg
+
+using namespace cg;
+
+extern "C" {
+
+const char* cg_last_error(void) { return g_err; }
+const char* cg_version(void) { return "coxgraph_b200 0.1 (sm_100a)"; }
+
+int32_t cg_context_create(int32_t device, void* stream, cg_context** out) {
+  if (!out) return CG_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("no CUDA device available (%s); this library has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return CG_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    set_error("device %d out of range (%d devices)", device, count);
+    return CG_ERR_INVALID_ARG;
+  }
+  CG_CUDA(cudaSetDevice(device));
+  cg_context* ctx = new cg_context();
+  ctx->device = device;
+  if (stream) {
+    ctx->stream = static_cast<cudaStream_t>(stream);
+  } else {
+    CG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+  CG_CUDA(cudaMallocHost(&ctx->h_counters, sizeof(CallCounters)));
+  CG_CUDA(cudaMalloc(&ctx->d_counters, sizeof(CallCounters)));
+  CG_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(CallCounters), ctx->stream));
+  *out = ctx;
+  return CG_OK;
+}
+
+int32_t cg_context_destroy(cg_context* ctx) {
+  if (!ctx) return CG_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->points, &ctx->colors, &ctx->poses, &ctx->frame_base, &ctx->key_a,
+                    &ctx->key_b, &ctx->val_a, &ctx->val_b, &ctx->flags, &ctx->scan,
+                    &ctx->cub_tmp, &ctx->rays, &ctx->ray_count, &ctx->ray_offset, &ctx->pkey_a,
+                    &ctx->pkey_b, &ctx->pval_a, &ctx->pval_b, &ctx->cand_keys, &ctx->cand_list,
+                    &ctx->stage_a, &ctx->stage_b, &ctx->stage_c};
+  for (DevBuf* b : bufs) b->release();
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return CG_OK;
+}
+
+int32_t cg_context_synchronize(cg_context* ctx) {
+  if (!ctx) return CG_ERR_INVALID_ARG;
+  CG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CG_OK;
+}
+
+int32_t cg_layer_create(cg_context* ctx, float voxel_size, int32_t vps, size_t max_blocks,
+                        cg_layer** out) {
+  if (!ctx || !out || !(voxel_size > 0.0f) || max_blocks == 0 || max_blocks > (1u << 30)) {
+    set_error("cg_layer_create: invalid argument");
+    return CG_ERR_INVALID_ARG;
+  }
+  if (vps != kVps) {
+    set_error("voxels_per_side must be 16");
+    return CG_ERR_UNSUPPORTED;
+  }
+  *out = nullptr;
+  CG_CUDA(cudaSetDevice(ctx->device));
+  cg_layer* L = new cg_layer();
+  L->ctx = ctx;
+  L->max_blocks = max_blocks;
+  size_t cap = 1024;
+  while (cap < 2 * max_blocks) cap <<= 1;
+  L->hash_cap = cap;
+  LayerView& v = L->v;
+  v.hash_mask = static_cast<uint32_t>(cap - 1);
+  v.max_blocks = static_cast<int32_t>(max_blocks);
+  v.voxel_size = voxel_size;
+  v.voxel_size_inv = 1.0f / voxel_size;
+  v.block_size = voxel_size * static_cast<float>(kVps);
+  v.block_size_inv = 1.0f / v.block_size;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+  };
+  alloc(reinterpret_cast<void**>(&v.hash_keys), cap * sizeof(uint64_t));
+  alloc(reinterpret_cast<void**>(&v.hash_vals), cap * sizeof(int32_t));
+  alloc(reinterpret_cast<void**>(&v.block_keys), max_blocks * sizeof(uint64_t));
+  alloc(reinterpret_cast<void**>(&v.has_data), max_blocks);
+  alloc(reinterpret_cast<void**>(&v.updated), max_blocks);
+  alloc(reinterpret_cast<void**>(&v.pool), max_blocks * static_cast<size_t>(CG_BLOCK_BYTES));
+  alloc(reinterpret_cast<void**>(&v.num_blocks), sizeof(int32_t));
+  alloc(reinterpret_cast<void**>(&v.err), sizeof(int32_t));
+  if (e != cudaSuccess) {
+    cg_layer_destroy(L);
+    return cuda_fail(e, "cg_layer_create allocation");
+  }
+  cudaStream_t s = ctx->stream;
+  CG_CUDA(cudaMemsetAsync(v.hash_keys, 0xFF, cap * sizeof(uint64_t), s));
+  CG_CUDA(cudaMemsetAsync(v.hash_vals, 0xFF, cap * sizeof(int32_t), s));
+  CG_CUDA(cudaMemsetAsync(v.has_data, 0, max_blocks, s));
+  CG_CUDA(cudaMemsetAsync(v.updated, 0, max_blocks, s));
+  CG_CUDA(cudaMemsetAsync(v.num_blocks, 0, sizeof(int32_t), s));
+  CG_CUDA(cudaMemsetAsync(v.err, 0, sizeof(int32_t), s));
+  k_fill_default<<<ctx->num_sms * 8, 256, 0, s>>>(v.pool, 0, max_blocks);
+  CG_CUDA(cudaStreamSynchronize(s));
+  CG_CUDA(cudaGetLastError());
+  *out = L;
+  return CG_OK;
+}
+
+int32_t cg_layer_destroy(cg_layer* L) {
+  if (!L) return CG_ERR_INVALID_ARG;
+  cudaSetDevice(L->ctx->device);
+  cudaStreamSynchronize(L->ctx->stream);
+  LayerView& v = L->v;
+  cudaFree(v.hash_keys);
+  cudaFree(v.hash_vals);
+  cudaFree(v.block_keys);
+  cudaFree(v.has_data);
+  cudaFree(v.updated);
+  cudaFree(v.pool);
+  cudaFree(v.num_blocks);
+  cudaFree(v.err);
+  delete L;
+  return CG_OK;
+}
+
+int32_t cg_layer_clear(cg_layer* L) {
+  if (!L) return CG_ERR_INVALID_ARG;
+  cudaStream_t s = L->ctx->stream;
+  LayerView& v = L->v;
+  CG_CUDA(cudaMemsetAsync(v.hash_keys, 0xFF, L->hash_cap * sizeof(uint64_t), s));
+  CG_CUDA(cudaMemsetAsync(v.hash_vals, 0xFF, L->hash_cap * sizeof(int32_t), s));
+  if (L->num_blocks > 0) {
+    CG_CUDA(cudaMemsetAsync(v.has_data, 0, L->num_blocks, s));
+    CG_CUDA(cudaMemsetAsync(v.updated, 0, L->num_blocks, s));
+    k_fill_default<<<L->ctx->num_sms * 8, 256, 0, s>>>(v.pool, 0, L->num_blocks);
+  }
+  CG_CUDA(cudaMemsetAsync(v.num_blocks, 0, sizeof(int32_t), s));
+  L->num_blocks = 0;
+  CG_CUDA(cudaStreamSynchronize(s));
+  return CG_OK;
+}
+
+int64_t cg_layer_num_blocks(const cg_layer* L) { return L ? L->num_blocks : -1; }
+float cg_layer_voxel_size(const cg_layer* L) { return L ? L->v.voxel_size : 0.0f; }
+
+int32_t cg_layer_block_indices(const cg_layer* L, size_t capacity, int32_t* idx, size_t* n_out) {
+  if (!L) return CG_ERR_INVALID_ARG;
+  const size_t n = static_cast<size_t>(L->num_blocks);
+  if (n_out) *n_out = n;
+  if (!idx || n == 0) return CG_OK;
+  if (capacity < n) {
+    set_error("cg_layer_block_indices: capacity %zu < %zu blocks", capacity, n);
+    return CG_ERR_INVALID_ARG;
+  }
+  cg_context* ctx = L->ctx;
+  const uint64_t* keys;
+  const uint32_t* slots;
+  int32_t rc = sort_blocks(L, &keys, &slots);
+  if (rc) return rc;
+  CG_CUDA(ctx->stage_b.reserve(n * 3 * sizeof(int32_t)));
+  k_unpack_idx<<<grid_for(n, 256), 256, 0, ctx->stream>>>(keys, static_cast<int>(n),
+                                                          ctx->stage_b.as<int32_t>());
+  CG_CUDA(cudaMemcpyAsync(idx, ctx->stage_b.p, n * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                          ctx->stream));
+  CG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CG_OK;
+}
+
+int32_t cg_layer_download(const cg_layer* L, size_t capacity, int32_t* idx, cg_tsdf_voxel* voxels,
+                          uint8_t* flags, size_t* n_out) {
+  if (!L) return CG_ERR_INVALID_ARG;
+  const size_t n = static_cast<size_t>(L->num_blocks);
+  if (n_out) *n_out = n;
+  if (n == 0 || (!idx && !voxels && !flags)) return CG_OK;
+  if (capacity < n) {
+    set_error("cg_layer_download: capacity %zu < %zu blocks", capacity, n);
+    return CG_ERR_INVALID_ARG;
+  }
+  cg_context* ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  const uint64_t* keys;
+  const uint32_t* slots;
+  int32_t rc = sort_blocks(L, &keys, &slots);
+  if (rc) return rc;
+  const size_t chunk = 2048;  // 96 MB staging
+  CG_CUDA(ctx->stage_a.reserve(std::min(chunk, n) * CG_BLOCK_BYTES));
+  CG_CUDA(ctx->stage_b.reserve(std::min(chunk, n) * 3 * sizeof(int32_t)));
+  CG_CUDA(ctx->stage_c.reserve(std::min(chunk, n)));
+  for (size_t first = 0; first < n; first += chunk) {
+    const size_t cnt = std::min(chunk, n - first);
+    k_gather_aos<<<static_cast<unsigned>(cnt), 256, 0, s>>>(
+        L->v, slots, static_cast<int>(first), static_cast<int>(cnt), ctx->stage_a.as<uint32_t>(),
+        ctx->stage_b.as<int32_t>(), ctx->stage_c.as<uint8_t>(), keys);
+    if (voxels)
+      CG_CUDA(cudaMemcpyAsync(voxels + first * kVoxelsPerBlock, ctx->stage_a.p,
+                              cnt * CG_BLOCK_BYTES, cudaMemcpyDeviceToHost, s));
+    if (idx)
+      CG_CUDA(cudaMemcpyAsync(idx + first * 3, ctx->stage_b.p, cnt * 3 * sizeof(int32_t),
+                              cudaMemcpyDeviceToHost, s));
+    if (flags)
+      CG_CUDA(cudaMemcpyAsync(flags + first, ctx->stage_c.p, cnt, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(cudaStreamSynchronize(s));
+  }
+  CG_CUDA(cudaGetLastError());
+  return CG_OK;
+}
+
+int32_t cg_layer_upload(cg_layer* L, size_t n, const int32_t* idx, const cg_tsdf_voxel* voxels,
+                        const uint8_t* flags) {
+  if (!L || (n && (!idx || !voxels))) return CG_ERR_INVALID_ARG;
+  cg_context* ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  const size_t chunk = 2048;
+  CG_CUDA(ctx->stage_a.reserve(std::min(chunk, n) * CG_BLOCK_BYTES));
+  CG_CUDA(ctx->stage_b.reserve(std::min(chunk, n) * 4 * sizeof(int32_t)));
+  CG_CUDA(ctx->stage_c.reserve(std::min(chunk, n)));
+  for (size_t first = 0; first < n; first += chunk) {
+    const size_t cnt = std::min(chunk, n - first);
+    int32_t* d_idx = ctx->stage_b.as<int32_t>();
+    int32_t* d_entries = d_idx + 3 * cnt;
+    CG_CUDA(cudaMemcpyAsync(d_idx, idx + 3 * first, cnt * 3 * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, s));
+    CG_CUDA(cudaMemcpyAsync(ctx->stage_a.p, voxels + first * kVoxelsPerBlock, cnt * CG_BLOCK_BYTES,
+                            cudaMemcpyHostToDevice, s));
+    if (flags)
+      CG_CUDA(cudaMemcpyAsync(ctx->stage_c.p, flags + first, cnt, cudaMemcpyHostToDevice, s));
+    k_upload_insert<<<grid_for(cnt, 128), 128, 0, s>>>(L->v, d_idx, static_cast<int>(cnt),
+                                                       d_entries);
+    k_upload_write<<<static_cast<unsigned>(cnt), 256, 0, s>>>(
+        L->v, d_entries, ctx->stage_a.as<uint32_t>(), flags ? ctx->stage_c.as<uint8_t>() : nullptr,
+        static_cast<int>(cnt));
+    CG_CUDA(cudaStreamSynchronize(s));
+  }
+  return finish_call(L, nullptr);
+}
+
+}  // extern "C"

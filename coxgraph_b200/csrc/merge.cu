@@ -1,0 +1,394 @@
+// merge.cu — submap -> global TSDF resampling and merge.
+//
+// Replaces voxblox::mergeLayerAintoLayerB(layer_A, T_B_A, layer_B) = transformLayer +
+// Interpolator<TsdfVoxel> + Block::mergeBlock (R7-R10 of SURVEY.md §8a); reference call sites
+// coxgraph/src/client/map_server.cpp:67-69 and, through cblox getProjectedMap(),
+// coxgraph/src/server/visualizer/server_visualizer.cpp:123-126.
+//
+//   k_mark_candidates   forward pass: every source block marks the output blocks its bounding
+//                       sphere can reach (deduplicated in a scratch hash set)
+//   k_resample_merge    one CTA per candidate output block: inverse-transform each voxel centre,
+//                       8-tap trilinear gather (nearest fallback) from the source layer, and —
+//                       only if any voxel succeeded — claim / find the destination block and fold
+//                       the 4096 resampled voxels into it (mergeVoxelAIntoVoxelB).  The temporary
+//                       transformed layer of the reference never exists in memory.
+#include <string.h>
+
+#include <algorithm>
+
+#include "cg_internal.cuh"
+
+namespace cg {
+
+constexpr int kTab = 4;  // cached neighbourhood of source block slots: kTab^3
+
+__global__ void k_mark_candidates(LayerView A, int num_a, Xform T_B_A, float block_size_out,
+                                  uint64_t* set_keys, uint32_t set_mask, uint64_t* list,
+                                  CallCounters* counters, int32_t* err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_a) return;
+  int bx, by, bz;
+  unpack_block_key(A.block_keys[i], bx, by, bz);
+  const V3 c_in = V3{center_coord(bx, A.block_size), center_coord(by, A.block_size),
+                     center_coord(bz, A.block_size)};
+  const V3 c = apply(T_B_A, c_in);
+  const float kDiag = 1.7320508075688772f;  // kUnitCubeDiagonalLength
+  const float offset = kDiag * A.block_size * 0.5f;
+  const float inv_out = 1.0f / block_size_out;
+  constexpr int lim = kVoxIdxOffset / kVps;
+  for (float x = c.x - offset; x < c.x + offset; x += block_size_out)
+    for (float y = c.y - offset; y < c.y + offset; y += block_size_out)
+      for (float z = c.z - offset; z < c.z + offset; z += block_size_out) {
+        const int ix = grid_index(x, inv_out), iy = grid_index(y, inv_out),
+                  iz = grid_index(z, inv_out);
+        if (ix < -lim || ix >= lim || iy < -lim || iy >= lim || iz < -lim || iz >= lim) {
+          atomicOr(err, kErrOutOfRange);
+          continue;
+        }
+        const uint64_t key = pack_block_key(ix, iy, iz);
+        uint32_t h = hash_key(key) & set_mask;
+        for (;;) {
+          const uint64_t k = set_keys[h];
+          if (k == key) break;
+          if (k == kEmptyKey) {
+            const unsigned long long old = atomicCAS(
+                reinterpret_cast<unsigned long long*>(&set_keys[h]), kEmptyKey, key);
+            if (old == kEmptyKey) {
+              const unsigned long long pos = atomicAdd(&counters->candidates, 1ull);
+              list[pos] = key;
+              break;
+            }
+            if (old == key) break;
+          }
+          h = (h + 1) & set_mask;
+        }
+      }
+}
+
+struct SlotTable {
+  int ax, ay, az;          // anchor block index
+  int slot[kTab * kTab * kTab];
+};
+
+__device__ __forceinline__ int lookup_block(const LayerView& A, const SlotTable& tab, int bx, int by,
+                                            int bz) {
+  const unsigned dx = bx - tab.ax, dy = by - tab.ay, dz = bz - tab.az;
+  if (dx < kTab && dy < kTab && dz < kTab) return tab.slot[dx + kTab * (dy + kTab * dz)];
+  return A.find_slot(pack_block_key(bx, by, bz));
+}
+
+// 8x8 table of the SPIE PM159 trilinear formulation used by voxblox's Interpolator, applied as
+// q . (M . data) with rows and the dot product accumulated left to right.
+__device__ __forceinline__ float interp_member(const float q[8], const float d[8]) {
+  float acc = q[0] * d[0];
+  acc = acc + q[1] * (-d[0] + d[4]);
+  acc = acc + q[2] * (-d[0] + d[2]);
+  acc = acc + q[3] * (-d[0] + d[1]);
+  acc = acc + q[4] * (((d[0] + -d[2]) + -d[4]) + d[6]);
+  acc = acc + q[5] * (((d[0] + -d[1]) + -d[2]) + d[3]);
+  acc = acc + q[6] * (((d[0] + -d[1]) + -d[4]) + d[5]);
+  acc = acc + q[7] * (((((((-d[0] + d[1]) + d[2]) + -d[3]) + d[4]) + -d[5]) + -d[6]) + d[7]);
+  return acc;
+}
+__device__ __forceinline__ uint32_t trunc_u8(float v) {
+  if (!(v > 0.0f)) return 0u;
+  if (v >= 255.0f) return 255u;
+  return static_cast<uint32_t>(static_cast<int>(v));
+}
+
+// Interpolator<TsdfVoxel>::getVoxel(pos, voxel, true) then (.., false); returns success and
+// leaves in `out` what the reference's temporary voxel would hold.
+__device__ __forceinline__ bool resample_voxel(const LayerView& A, const SlotTable& tab, V3 p,
+                                               VoxelState& out) {
+  out.d = 0.0f;
+  out.w = 0.0f;
+  out.c = kDefaultColor;
+  int b[3] = {grid_index(p.x, A.block_size_inv), grid_index(p.y, A.block_size_inv),
+              grid_index(p.z, A.block_size_inv)};
+  const int slot0 = lookup_block(A, tab, b[0], b[1], b[2]);
+  if (slot0 < 0) return false;  // neither trilinear nor nearest can succeed
+  const V3 org = V3{static_cast<float>(b[0]) * A.block_size, static_cast<float>(b[1]) * A.block_size,
+                    static_cast<float>(b[2]) * A.block_size};
+  const V3 rel = p - org;
+  const int v0[3] = {grid_index(rel.x, A.voxel_size_inv), grid_index(rel.y, A.voxel_size_inv),
+                     grid_index(rel.z, A.voxel_size_inv)};
+  // ---- trilinear (R8)
+  bool ok = true;
+  {
+    int v[3] = {v0[0], v0[1], v0[2]};
+    const V3 vc = org + V3{center_coord(v[0], A.voxel_size), center_coord(v[1], A.voxel_size),
+                           center_coord(v[2], A.voxel_size)};
+    const float off[3] = {p.x - vc.x, p.y - vc.y, p.z - vc.z};
+    bool moved = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (off[a] < 0.0f) {
+        v[a]--;
+        if (v[a] < 0) {
+          b[a]--;
+          v[a] += kVps;
+          moved = true;
+        }
+      }
+    }
+    int base_slot = slot0;
+    if (moved) base_slot = lookup_block(A, tab, b[0], b[1], b[2]);
+    if (base_slot < 0) ok = false;
+    float q[8], dd[8], ww[8];
+    uint32_t cc[8];
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int nv[3] = {v[0] + ((i >> 2) & 1), v[1] + ((i >> 1) & 1), v[2] + (i & 1)};
+        int nb[3] = {b[0], b[1], b[2]};
+        int slot = base_slot;
+        if (nv[0] >= kVps || nv[1] >= kVps || nv[2] >= kVps) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+            if (nv[a] >= kVps) {
+              nb[a]++;
+              nv[a] -= kVps;
+            }
+          slot = lookup_block(A, tab, nb[0], nb[1], nb[2]);
+          if (slot < 0) {
+            ok = false;
+            break;
+          }
+        }
+        if (i == 0) {
+          const V3 no = V3{static_cast<float>(nb[0]) * A.block_size,
+                           static_cast<float>(nb[1]) * A.block_size,
+                           static_cast<float>(nb[2]) * A.block_size};
+          const V3 vpos = no + V3{center_coord(nv[0], A.voxel_size),
+                                  center_coord(nv[1], A.voxel_size),
+                                  center_coord(nv[2], A.voxel_size)};
+          const V3 o = (p - vpos) * A.voxel_size_inv;
+          q[0] = 1.0f;
+          q[1] = o.x;
+          q[2] = o.y;
+          q[3] = o.z;
+          q[4] = o.x * o.y;
+          q[5] = o.y * o.z;
+          q[6] = o.z * o.x;
+          q[7] = o.x * o.y * o.z;
+        }
+        const int lin = nv[0] + kVps * (nv[1] + kVps * nv[2]);
+        const float w = A.weight_plane(slot)[lin];
+        if (!(w > kEps)) {  // utils::isObservedVoxel
+          ok = false;
+          break;
+        }
+        ww[i] = w;
+        dd[i] = A.dist_plane(slot)[lin];
+        cc[i] = A.color_plane(slot)[lin];
+      }
+    }
+    if (ok) {
+      out.d = interp_member(q, dd);
+      out.w = interp_member(q, ww);
+      float ch[8];
+      uint32_t rgba = 0;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ch[i] = static_cast<float>((cc[i] >> (8 * s)) & 255u);
+        rgba |= trunc_u8(interp_member(q, ch)) << (8 * s);
+      }
+      out.c = rgba;
+      return true;
+    }
+  }
+  // ---- nearest (R9): clamped voxel index in the block containing p
+  const int nx = max(min(v0[0], kVps - 1), 0), ny = max(min(v0[1], kVps - 1), 0),
+            nz = max(min(v0[2], kVps - 1), 0);
+  const int lin = nx + kVps * (ny + kVps * nz);
+  out.d = A.dist_plane(slot0)[lin];
+  out.w = A.weight_plane(slot0)[lin];
+  out.c = A.color_plane(slot0)[lin];
+  return out.w > kEps;
+}
+
+constexpr int kMergeThreads = 256;
+constexpr int kVoxPerThread = kVoxelsPerBlock / kMergeThreads;
+
+__global__ void __launch_bounds__(kMergeThreads)
+k_resample_merge(LayerView A, LayerView B, Xform T_A_B, const uint64_t* __restrict__ cand,
+                 CallCounters* counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_d = reinterpret_cast<float*>(smem_raw);                 // resampled block, planar
+  float* s_w = s_d + kVoxelsPerBlock;
+  uint32_t* s_c = reinterpret_cast<uint32_t*>(s_w + kVoxelsPerBlock);
+  SlotTable& tab = *reinterpret_cast<SlotTable*>(s_c + kVoxelsPerBlock);
+  __shared__ int s_slot;
+  const unsigned long long num_cand = counters->candidates;
+  for (unsigned long long c = blockIdx.x; c < num_cand; c += gridDim.x) {
+    int bx, by, bz;
+    unpack_block_key(cand[c], bx, by, bz);
+    const V3 org_out = V3{static_cast<float>(bx) * B.block_size, static_cast<float>(by) * B.block_size,
+                          static_cast<float>(bz) * B.block_size};
+    __syncthreads();  // previous iteration done with tab / s_slot
+    if (threadIdx.x == 0) {
+      const V3 ctr = V3{center_coord(bx, B.block_size), center_coord(by, B.block_size),
+                        center_coord(bz, B.block_size)};
+      const V3 pc = apply(T_A_B, ctr);
+      const float reach = 0.8660254f * B.block_size + A.voxel_size;
+      tab.ax = __float2int_rd((pc.x - reach) * A.block_size_inv);
+      tab.ay = __float2int_rd((pc.y - reach) * A.block_size_inv);
+      tab.az = __float2int_rd((pc.z - reach) * A.block_size_inv);
+    }
+    __syncthreads();
+    if (threadIdx.x < kTab * kTab * kTab) {
+      const int t = threadIdx.x;
+      const int dx = t % kTab, dy = (t / kTab) % kTab, dz = t / (kTab * kTab);
+      tab.slot[t] = A.find_slot(pack_block_key(tab.ax + dx, tab.ay + dy, tab.az + dz));
+    }
+    __syncthreads();
+    bool any = false;
+#pragma unroll 1
+    for (int j = 0; j < kVoxPerThread; ++j) {
+      const int lin = threadIdx.x + j * kMergeThreads;
+      const int vx = lin & 15, vy = (lin >> 4) & 15, vz = lin >> 8;
+      const V3 center_out =
+          org_out + V3{center_coord(vx, B.voxel_size), center_coord(vy, B.voxel_size),
+                       center_coord(vz, B.voxel_size)};
+      const V3 p = apply(T_A_B, center_out);
+      VoxelState t;
+      any |= resample_voxel(A, tab, p, t);
+      s_d[lin] = t.d;
+      s_w[lin] = t.w;
+      s_c[lin] = t.c;
+    }
+    const int has_data = __syncthreads_or(any ? 1 : 0);
+    if (!has_data) continue;  // block dropped from the transformed layer: nothing merged
+    if (threadIdx.x == 0) {
+      const int e = B.insert_entry(cand[c]);
+      s_slot = B.hash_vals[e];  // written by this thread or by an earlier kernel
+      atomicAdd(&counters->blocks_out, 1ull);
+      if (s_slot >= 0) {
+        B.has_data[s_slot] = 1;
+        B.updated[s_slot] = 1;
+      }
+    }
+    __syncthreads();
+    const int slot = s_slot;
+    if (slot < 0) continue;
+    float* dp = B.dist_plane(slot);
+    float* wp = B.weight_plane(slot);
+    uint32_t* cp = B.color_plane(slot);
+#pragma unroll
+    for (int j = 0; j < kVoxPerThread; ++j) {
+      const int lin = threadIdx.x + j * kMergeThreads;
+      VoxelState b{dp[lin], wp[lin], cp[lin]};
+      merge_voxel(s_d[lin], s_w[lin], s_c[lin], b);
+      dp[lin] = b.d;
+      wp[lin] = b.w;
+      cp[lin] = b.c;
+    }
+  }
+}
+
+__global__ void k_reset_merge_counters(CallCounters* c) {
+  c->candidates = 0;
+  c->blocks_out = 0;
+}
+
+static int32_t enqueue_merge(const cg_layer* A, const float T_B_A[7], cg_layer* B) {
+  cg_context* ctx = B->ctx;
+  cudaStream_t s = ctx->stream;
+  const size_t nA = static_cast<size_t>(A->num_blocks);
+  if (nA == 0) return CG_OK;
+  size_t cap = 1024;
+  while (cap < 32 * nA) cap <<= 1;
+  CG_CUDA(ctx->cand_keys.reserve(cap * sizeof(uint64_t)));
+  CG_CUDA(ctx->cand_list.reserve(27 * nA * sizeof(uint64_t)));
+  CG_CUDA(cudaMemsetAsync(ctx->cand_keys.p, 0xFF, cap * sizeof(uint64_t), s));
+  k_reset_merge_counters<<<1, 1, 0, s>>>(ctx->d_counters);
+  const Xform T = make_xform(T_B_A);
+  k_mark_candidates<<<grid_for(nA, 128), 128, 0, s>>>(
+      A->v, static_cast<int>(nA), T, B->v.block_size, ctx->cand_keys.as<uint64_t>(),
+      static_cast<uint32_t>(cap - 1), ctx->cand_list.as<uint64_t>(), ctx->d_counters, B->v.err);
+  // inverse on the host with the same operation order as the device / reference
+  Xform Ti;
+  {
+    const float w = T.w;
+    const V3 cv = V3{-T.v.x, -T.v.y, -T.v.z};
+    // rotate(w, cv, t) spelled out (host code: no FMA contraction, see Makefile flags)
+    const V3 t = T.t;
+    V3 uv = V3{cv.y * t.z - cv.z * t.y, cv.z * t.x - cv.x * t.z, cv.x * t.y - cv.y * t.x};
+    uv = V3{uv.x + uv.x, uv.y + uv.y, uv.z + uv.z};
+    const V3 cr = V3{cv.y * uv.z - cv.z * uv.y, cv.z * uv.x - cv.x * uv.z, cv.x * uv.y - cv.y * uv.x};
+    const V3 r = V3{(t.x + w * uv.x) + cr.x, (t.y + w * uv.y) + cr.y, (t.z + w * uv.z) + cr.z};
+    Ti.w = w;
+    Ti.v = cv;
+    Ti.t = V3{-r.x, -r.y, -r.z};
+  }
+  const unsigned grid = static_cast<unsigned>(
+      std::min<size_t>(27 * nA, static_cast<size_t>(ctx->num_sms) * 4));
+  const size_t smem = 3 * kVoxelsPerBlock * sizeof(float) + sizeof(SlotTable);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CG_CUDA(cudaFuncSetAttribute(k_resample_merge, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+    attr_set = true;
+  }
+  k_resample_merge<<<grid, kMergeThreads, smem, s>>>(A->v, B->v, Ti, ctx->cand_list.as<uint64_t>(),
+                                                  ctx->d_counters);
+  CG_CUDA(cudaGetLastError());
+  return CG_OK;
+}
+
+}  // namespace cg
+
+using namespace cg;
+
+extern "C" {
+
+int32_t cg_merge_layer_into_layer(const cg_layer* A, const float T_B_A[7], cg_layer* B,
+                                  cg_merge_stats* stats) {
+  if (!A || !B || !T_B_A || A == B || A->ctx != B->ctx) {
+    set_error("cg_merge_layer_into_layer: invalid argument (layers must differ and share a context)");
+    return CG_ERR_INVALID_ARG;
+  }
+  CG_CUDA(cudaSetDevice(B->ctx->device));
+  int32_t rc = enqueue_merge(A, T_B_A, B);
+  if (rc) return rc;
+  CallCounters c;
+  rc = finish_call(B, &c);
+  if (stats) {
+    stats->blocks_in = static_cast<uint64_t>(A->num_blocks);
+    stats->blocks_candidate = A->num_blocks ? c.candidates : 0;
+    stats->blocks_out = A->num_blocks ? c.blocks_out : 0;
+  }
+  return rc;
+}
+
+int32_t cg_project_submaps(const cg_layer* const* submaps, const float* poses, size_t n,
+                           cg_layer* G, cg_merge_stats* stats) {
+  if (!G || (n && (!submaps || !poses))) return CG_ERR_INVALID_ARG;
+  CG_CUDA(cudaSetDevice(G->ctx->device));
+  cg_context* ctx = G->ctx;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  for (size_t i = 0; i < n; ++i) {
+    const cg_layer* A = submaps[i];
+    if (!A || A == G || A->ctx != ctx) {
+      set_error("cg_project_submaps: submap %zu invalid", i);
+      return CG_ERR_INVALID_ARG;
+    }
+    int32_t rc = enqueue_merge(A, poses + 7 * i, G);
+    if (rc) return rc;
+    if (stats) {
+      // per-submap counters are reset by the next merge: read them back (stats path only)
+      CG_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(CallCounters),
+                              cudaMemcpyDeviceToHost, ctx->stream));
+      CG_CUDA(cudaStreamSynchronize(ctx->stream));
+      stats->blocks_in += static_cast<uint64_t>(A->num_blocks);
+      if (A->num_blocks) {
+        stats->blocks_candidate += ctx->h_counters->candidates;
+        stats->blocks_out += ctx->h_counters->blocks_out;
+      }
+    }
+  }
+  return finish_call(G, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,187 @@
+/*
+ * coxgraph_b200.h — C ABI of the B200-native TSDF fusion engine for coxgraph's hot path.
+ *
+ * This is the drop-in boundary: a plain `extern "C"` shared library (libcoxgraph_b200.so),
+ * opaque handles, POD structs, plain pointers and sizes.  No torch, STL or exceptions cross
+ * it.  Every entry point names the reference interface it replaces (paths are relative to
+ * the reference checkout, mfkiwl/coxgraph).  The arithmetic itself lives in the reference's
+ * un-vendored dependency voxblox ([EXT]); the file:line given is the
+ * reference's own call site of that interface.
+ *
+ * Conventions
+ *  - status: 0 = CG_OK, negative = error; cg_last_error() returns a thread-local message.
+ *  - transforms: float[7] = {qw, qx, qy, qz, tx, ty, tz} (kindr::minimal::QuatTransformation,
+ *    unit quaternion); points: float xyz triples; colours: uint8 r,g,b,a quadruples.
+ *  - host pointers are caller-owned, may be pageable, and are only read during the call.
+ *    `*_device` variants take pointers to device memory on the context's GPU.
+ *  - calls return after the work has completed on the GPU unless stated otherwise.
+ *  - handles are thread-compatible, not thread-safe (the reference drives this path from a
+ *    single-threaded ros::spin(), coxgraph/src/tsdf_recover_node.cpp:23).
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *    CG_ERR_CUDA.
+ */
+#ifndef COXGRAPH_B200_H_
+#define COXGRAPH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CG_VOXELS_PER_SIDE 16
+#define CG_VOXELS_PER_BLOCK 4096
+#define CG_VOXEL_BYTES 12
+#define CG_BLOCK_BYTES (CG_VOXELS_PER_BLOCK * CG_VOXEL_BYTES) /* 49152 */
+
+enum cg_status {
+  CG_OK = 0,
+  CG_ERR_INVALID_ARG = -1,
+  CG_ERR_CUDA = -2,         /* CUDA runtime error (no device, OOM, launch failure) */
+  CG_ERR_POOL_FULL = -3,    /* block pool exhausted (max_blocks of cg_layer_create) */
+  CG_ERR_OUT_OF_RANGE = -4, /* a voxel index left the +-2^19 voxel addressable range */
+  CG_ERR_UNSUPPORTED = -5   /* e.g. method FAST (order-dependent) */
+};
+
+enum cg_method { CG_METHOD_SIMPLE = 0, CG_METHOD_MERGED = 1, CG_METHOD_FAST = 2 };
+enum cg_order_mode { CG_ORDER_MIXED = 0, CG_ORDER_NATURAL = 1 };
+
+/* The voxel record handed across the boundary: voxblox::TsdfVoxel
+ * (consumed by the reference at coxgraph/include/coxgraph/utils/msg_converter.h:49-50 and
+ * coxgraph/src/client/map_server.cpp:88-89 through serializeLayerAsMsg). */
+typedef struct cg_tsdf_voxel {
+  float distance;
+  float weight;
+  uint8_t r, g, b, a;
+} cg_tsdf_voxel;
+
+/* voxblox::TsdfIntegratorBase::Config — the parameter set the reference loads from
+ * coxgraph/config/tsdf_server_*.yaml and coxgraph/config/tsdf_recover.yaml:2-11.
+ * cg_integrator_config_default() fills the upstream defaults. */
+typedef struct cg_integrator_config {
+  float default_truncation_distance; /* truncation_distance */
+  float max_weight;
+  int32_t voxel_carving_enabled;
+  float min_ray_length_m;
+  float max_ray_length_m;
+  int32_t use_const_weight;
+  int32_t allow_clear;
+  int32_t use_weight_dropoff;
+  int32_t use_sparsity_compensation_factor;
+  float sparsity_compensation_factor;
+  int32_t enable_anti_grazing;
+  int32_t method;                 /* cg_method; `method:` in the yaml files */
+  int32_t integration_order_mode; /* cg_order_mode */
+  float start_voxel_subsampling_factor;   /* FAST only */
+  int32_t max_consecutive_ray_collisions; /* FAST only */
+} cg_integrator_config;
+
+typedef struct cg_context cg_context;
+typedef struct cg_layer cg_layer;
+
+/* Per-call statistics (the byte model of DESIGN.md / SURVEY.md §8d uses these). */
+typedef struct cg_integrate_stats {
+  uint64_t points_in;       /* N */
+  uint64_t rays;            /* rays cast (bundles for MERGED) */
+  uint64_t voxel_updates;   /* (ray, voxel) visits */
+  uint64_t blocks_touched;  /* distinct blocks visited by any ray of the call */
+  uint64_t blocks_allocated;/* new blocks */
+} cg_integrate_stats;
+
+typedef struct cg_merge_stats {
+  uint64_t blocks_in;        /* allocated blocks of the source layer(s) */
+  uint64_t blocks_candidate; /* output blocks marked by the forward pass */
+  uint64_t blocks_out;       /* output blocks that received data */
+} cg_merge_stats;
+
+const char* cg_last_error(void);
+const char* cg_version(void);
+
+/* --- context: one per GPU / per process rank --------------------------------------- */
+/* `stream` is a cudaStream_t passed as void* (NULL = a stream owned by the context). */
+int32_t cg_context_create(int32_t device, void* stream, cg_context** out);
+int32_t cg_context_destroy(cg_context* ctx);
+int32_t cg_context_synchronize(cg_context* ctx);
+
+/* --- layer: replaces voxblox::Layer<TsdfVoxel> (block hash map keyed by BlockIndex) --- */
+/* voxels_per_side must be 16 (the reference never overrides tsdf_voxels_per_side). */
+int32_t cg_layer_create(cg_context* ctx, float voxel_size, int32_t voxels_per_side,
+                        size_t max_blocks, cg_layer** out);
+int32_t cg_layer_destroy(cg_layer* layer);
+/* Layer::removeAllBlocks — coxgraph/include/coxgraph/map_comm/tsdf_recover.h:62,
+ * coxgraph/src/client/map_server.cpp:65 */
+int32_t cg_layer_clear(cg_layer* layer);
+/* Layer::getNumberOfAllocatedBlocks */
+int64_t cg_layer_num_blocks(const cg_layer* layer);
+float cg_layer_voxel_size(const cg_layer* layer);
+
+/* Copy the layer out in voxblox's own layout: blocks sorted by (z, y, x) block index,
+ * block_idx_xyz int32[B*3], voxels cg_tsdf_voxel[B*4096] (linear x + 16*(y + 16*z)),
+ * flags uint8[B] (bit0 has_data, bit1 updated).  Any output may be NULL.  `capacity_blocks`
+ * bounds B.  This is what serializeLayerAsMsg consumes
+ * (coxgraph/include/coxgraph/map_comm/tsdf_recover.h:95). */
+int32_t cg_layer_download(const cg_layer* layer, size_t capacity_blocks, int32_t* block_idx_xyz,
+                          cg_tsdf_voxel* voxels, uint8_t* flags, size_t* num_blocks_out);
+/* Insert / overwrite blocks (deserializeMsgToLayer hand-off,
+ * coxgraph/include/coxgraph/utils/msg_converter.h:107-109). flags may be NULL (has_data). */
+int32_t cg_layer_upload(cg_layer* layer, size_t num_blocks, const int32_t* block_idx_xyz,
+                        const cg_tsdf_voxel* voxels, const uint8_t* flags);
+/* Block indices only (sorted), e.g. to compare allocation sets. */
+int32_t cg_layer_block_indices(const cg_layer* layer, size_t capacity_blocks,
+                               int32_t* block_idx_xyz, size_t* num_blocks_out);
+
+/* --- integration: replaces voxblox::TsdfIntegratorBase::integratePointCloud(T_G_C,
+ * points_C, colors, freespace_points) — called by the reference at
+ * coxgraph/include/coxgraph/map_comm/tsdf_recover.h:75 and by voxblox_ros TsdfServer
+ * (coxgraph/launch/firefly/tsdf_client.launch:24). */
+void cg_integrator_config_default(cg_integrator_config* cfg);
+int32_t cg_integrate_pointcloud(cg_layer* layer, const cg_integrator_config* cfg,
+                                const float T_G_C[7], const float* points_xyz,
+                                const uint8_t* colors_rgba, size_t num_points,
+                                int32_t freespace_points, cg_integrate_stats* stats);
+int32_t cg_integrate_pointcloud_device(cg_layer* layer, const cg_integrator_config* cfg,
+                                       const float T_G_C[7], const float* d_points_xyz,
+                                       const uint8_t* d_colors_rgba, size_t num_points,
+                                       int32_t freespace_points, cg_integrate_stats* stats);
+/* F consecutive integratePointCloud calls (the loop of tsdf_recover.h:71-86) submitted as
+ * one job; identical result to F single calls in order.  frame_offsets has F+1 entries
+ * (points of frame f are [frame_offsets[f], frame_offsets[f+1])); poses is F*7 floats. */
+int32_t cg_integrate_batch(cg_layer* layer, const cg_integrator_config* cfg, size_t num_frames,
+                           const float* T_G_C_poses, const float* points_xyz,
+                           const uint8_t* colors_rgba, const uint64_t* frame_offsets,
+                           int32_t freespace_points, cg_integrate_stats* stats);
+int32_t cg_integrate_batch_device(cg_layer* layer, const cg_integrator_config* cfg,
+                                  size_t num_frames, const float* T_G_C_poses,
+                                  const float* d_points_xyz, const uint8_t* d_colors_rgba,
+                                  const uint64_t* frame_offsets, int32_t freespace_points,
+                                  cg_integrate_stats* stats);
+
+/* --- merge: replaces voxblox::mergeLayerAintoLayerB(layer_A, T_B_A, layer_B) — called at
+ * coxgraph/src/client/map_server.cpp:67-69 — and cblox SubmapCollection::getProjectedMap(),
+ * the server's submap-to-global entry reached from
+ * coxgraph/src/server/visualizer/server_visualizer.cpp:123-126. */
+int32_t cg_merge_layer_into_layer(const cg_layer* layer_a, const float T_B_A[7],
+                                  cg_layer* layer_b, cg_merge_stats* stats);
+/* for s in 0..n-1: mergeLayerAintoLayerB(submaps[s], T_M_S[s], global), in that order. */
+int32_t cg_project_submaps(const cg_layer* const* submaps, const float* T_M_S_poses,
+                           size_t num_submaps, cg_layer* global_layer, cg_merge_stats* stats);
+
+/* --- multi-GPU exchange of partial global layers (DESIGN.md "Multi-GPU") -------------
+ * Ownership of a global block is owner = cg_block_owner(idx, nranks).  Each rank packs the
+ * blocks of its partial layer destined to every peer into one device buffer of records
+ * {int32 x,y,z,flags; 3 x 4096 x 4 B planes} grouped by owner; the host exchanges them
+ * (NCCL all-to-all through torch.distributed or ncclSend/Recv) and the owner folds the
+ * received records in ascending source-rank order with mergeVoxelAIntoVoxelB. */
+#define CG_PACKED_BLOCK_BYTES (16 + CG_BLOCK_BYTES)
+int32_t cg_block_owner(int32_t bx, int32_t by, int32_t bz, int32_t nranks);
+/* counts_out[nranks]: number of blocks per owner; d_packed must hold num_blocks records. */
+int32_t cg_layer_pack_by_owner(const cg_layer* layer, int32_t nranks, void* d_packed,
+                               size_t capacity_blocks, uint64_t* counts_out);
+/* Fold `num_blocks` packed records (device memory) into `layer` in record order. */
+int32_t cg_layer_merge_packed(cg_layer* layer, const void* d_packed, size_t num_blocks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COXGRAPH_B200_H_ */

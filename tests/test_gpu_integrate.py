@@ -1,0 +1,157 @@
+"""GPU parity: cg_integrate_* against the CPU oracle on identical seeded inputs (through the
+C ABI).  Reference call site: coxgraph/include/coxgraph/map_comm/tsdf_recover.h:59-99."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(gpu_ctx, frames, voxel_size=0.05, batch=False, max_blocks=2048, **over):
+    from coxgraph_b200 import Layer, TsdfIntegrator
+    from oracle import oracle_py as orc
+    ocfg, gcfg = util.make_cfgs(**over)
+    ol = orc.Layer(voxel_size)
+    gl = Layer(gpu_ctx, voxel_size, max_blocks=max_blocks)
+    integ = TsdfIntegrator(gcfg, gl)
+    touched = []
+    for (T, p, c) in frames:
+        ol.integrate(ocfg, T, p, c)
+        touched.append(ol.last_blocks_touched)
+    if batch:
+        offs = np.cumsum([0] + [len(p) for (_, p, _) in frames]).astype(np.uint64)
+        integ.integrateBatch(np.stack([T for (T, _, _) in frames]),
+                             np.concatenate([p for (_, p, _) in frames]),
+                             np.concatenate([c for (_, _, c) in frames]), offs)
+    else:
+        for k, (T, p, c) in enumerate(frames):
+            st = integ.integratePointCloud(T, p, c)
+            assert st.blocks_touched == touched[k], "B_touched differs from the oracle"
+            assert st.points_in == len(p)
+    return gl.download(), ol.download(), gl
+
+
+@pytest.mark.parametrize("method", [1, 0])
+def test_single_frames_match_oracle(gpu_ctx, method):
+    frames = util.small_frames(3, stride=8 if method == 1 else 16)
+    got, ref, gl = _run_both(gpu_ctx, frames, method=method)
+    util.compare_layers(got, ref, f"method {method}")
+    assert util.exact_fraction(got, ref) > 0.999
+    gl.close()
+
+
+def test_batch_equals_sequential(gpu_ctx):
+    frames = util.small_frames(5, stride=8)
+    got, ref, gl = _run_both(gpu_ctx, frames, batch=True)
+    util.compare_layers(got, ref, "batch")
+    gl.close()
+
+
+def test_batch_split_path(gpu_ctx, monkeypatch):
+    monkeypatch.setenv("CG_MAX_PAIRS", "100000")
+    frames = util.small_frames(4, stride=8)
+    got, ref, gl = _run_both(gpu_ctx, frames, batch=True)
+    util.compare_layers(got, ref, "batch split")
+    gl.close()
+
+
+@pytest.mark.parametrize("over", [
+    dict(use_const_weight=0),
+    dict(voxel_carving_enabled=0),
+    dict(allow_clear=0),
+    dict(use_weight_dropoff=0, use_sparsity_compensation_factor=1,
+         sparsity_compensation_factor=20.0, max_weight=1000.0),
+    dict(integration_order_mode=1),
+    dict(default_truncation_distance=0.16),
+])
+def test_config_variants(gpu_ctx, over):
+    frames = util.small_frames(2, stride=8, robot=1)
+    got, ref, gl = _run_both(gpu_ctx, frames, **over)
+    util.compare_layers(got, ref, str(over))
+    gl.close()
+
+
+def test_fine_voxels_720p(gpu_ctx):
+    from coxgraph_b200 import synth
+    frames = util.small_frames(2, stride=8, cam=synth.CAM_1280x720)
+    got, ref, gl = _run_both(gpu_ctx, frames, voxel_size=0.02, max_blocks=8192,
+                             default_truncation_distance=0.06, max_ray_length_m=3.0)
+    util.compare_layers(got, ref, "2 cm")
+    gl.close()
+
+
+def test_freespace_and_edge_inputs(gpu_ctx):
+    from coxgraph_b200 import Layer, TsdfIntegrator
+    from oracle import oracle_py as orc
+    ocfg, gcfg = util.make_cfgs()
+    (T, p, c), = util.small_frames(1, stride=16)
+    p = p.copy()
+    p[5] = np.nan          # non-finite points are dropped
+    p[6] = [0, 0, 0.01]    # closer than min_ray
+    p[7] = [np.inf, 0, 1]
+    ol = orc.Layer(0.05)
+    gl = Layer(gpu_ctx, 0.05, max_blocks=1024)
+    integ = TsdfIntegrator(gcfg, gl)
+    ol.integrate(ocfg, T, p, c, freespace=True)
+    integ.integratePointCloud(T, p, c, freespace_points=True)
+    # empty cloud is a no-op
+    integ.integratePointCloud(T, np.zeros((0, 3), np.float32), np.zeros((0, 4), np.uint8))
+    util.compare_layers(gl.download(), ol.download(), "freespace")
+    gl.removeAllBlocks()
+    assert gl.num_blocks == 0 and len(gl.download()[0]) == 0
+    # after a clear the pool is back in its default state
+    integ.integratePointCloud(T, p, c)
+    ol.clear()
+    ol.integrate(ocfg, T, p, c)
+    util.compare_layers(gl.download(), ol.download(), "after clear")
+    gl.close()
+
+
+def test_pool_exhaustion_and_unsupported(gpu_ctx):
+    from coxgraph_b200 import Layer, TsdfIntegrator, capi
+    _, gcfg = util.make_cfgs()
+    (T, p, c), = util.small_frames(1, stride=16)
+    gl = Layer(gpu_ctx, 0.05, max_blocks=8)
+    with pytest.raises(capi.CgError) as e:
+        TsdfIntegrator(gcfg, gl).integratePointCloud(T, p, c)
+    assert e.value.status == capi.CG_ERR_POOL_FULL
+    assert gl.num_blocks == 8
+    gl.close()
+    _, fast = util.make_cfgs(method=2)
+    gl = Layer(gpu_ctx, 0.05, max_blocks=64)
+    with pytest.raises(capi.CgError) as e:
+        TsdfIntegrator(fast, gl).integratePointCloud(T, p, c)
+    assert e.value.status == capi.CG_ERR_UNSUPPORTED
+    gl.close()
+
+
+def test_device_pointer_inputs(gpu_ctx):
+    import torch
+    from coxgraph_b200 import Layer, TsdfIntegrator
+    _, gcfg = util.make_cfgs()
+    (T, p, c), = util.small_frames(1, stride=8)
+    a = Layer(gpu_ctx, 0.05, max_blocks=1024)
+    b = Layer(gpu_ctx, 0.05, max_blocks=1024)
+    TsdfIntegrator(gcfg, a).integratePointCloud(T, p, c)
+    TsdfIntegrator(gcfg, b).integratePointCloud(T, torch.from_numpy(p).cuda(),
+                                                torch.from_numpy(c).cuda())
+    util.compare_layers(b.download(), a.download(), "device inputs", exact=True)
+    a.close()
+    b.close()
+
+
+def test_upload_download_roundtrip(gpu_ctx):
+    from coxgraph_b200 import Layer
+    from oracle import oracle_py as orc
+    ocfg, _ = util.make_cfgs()
+    (T, p, c), = util.small_frames(1, stride=8)
+    ol = orc.Layer(0.05)
+    ol.integrate(ocfg, T, p, c)
+    idx, vox, fl = ol.download()
+    gl = Layer(gpu_ctx, 0.05, max_blocks=1024)
+    perm = np.random.default_rng(0).permutation(len(idx))
+    gl.upload(idx[perm], vox[perm], fl[perm])
+    util.compare_layers(gl.download(), (idx, vox, fl), "roundtrip", exact=True, check_flags=True)
+    assert np.array_equal(gl.block_indices(), idx)
+    gl.close()
