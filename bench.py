@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py — TSDF points integrated/s and submap-merge voxels/s (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1], "two-client CVG-experiment shape"): robots x submaps of 25
+synthetic 640x480 depth frames each, 5 cm voxels, 16 cm truncation, Merged integrator, every
+fused submap merged into the rank's global TSDF.  One STEP = clear the submap layer, fuse the 25
+frames of one submap (7.68 M points) into it, merge it into the global layer.
+
+  python bench.py --gpus N --steps K --warmup W              our arm (CUDA, C ABI)
+  python bench.py --impl reference --gpus N --steps K ...    the CPU oracle port, all host threads
+
+Multi-GPU (torchrun, one rank per GPU): robots shard over ranks, no data-path collective in the
+timed region (weak scaling); time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FRAMES_PER_SUBMAP = 25
+VOXEL_SIZE = 0.05
+CFG = dict(default_truncation_distance=0.16, max_ray_length_m=5.0, min_ray_length_m=0.1,
+           use_const_weight=1, method=1)
+WORKLOAD = ("C2 two-client CVG shape: per step one submap = 25 x 640x480 depth frames "
+            "(7.68 M points), 5 cm voxels, 16 cm truncation, merged integrator, voxel carving, "
+            "fused into a cleared submap layer then merged into the global TSDF")
+BLOCK_BYTES = 49152
+
+
+# ----------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nme in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def submap_of_step(step, rank, world):
+    """(robot, submap) fused at `step` on `rank`: robots shard over ranks."""
+    if world == 1:
+        return step % 2, step // 2
+    return rank, step
+
+
+def host_frames(robot, submap, frames, device):
+    from coxgraph_b200 import synth
+    fr = synth.submap_frames(robot, submap % 20, frames, device=device)
+    poses = np.stack([T for (T, _, _) in fr]).astype(np.float32)
+    return poses, [p for (_, p, _) in fr], [c for (_, _, c) in fr]
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path (restated: oracle/, kind 'port'), with all
+    host threads, on a bounded sample of every step."""
+    if rank != 0:
+        return
+    from coxgraph_b200 import synth
+    from oracle import oracle_py as orc
+    threads = os.cpu_count() or 1
+    ocfg = orc.default_config(**CFG)
+    sample_frames = args.ref_frames
+    og = orc.Layer(VOXEL_SIZE)
+    t_int = t_merge = 0.0
+    pts_total = vox_total = 0
+    t_region = 0.0
+    for step in range(args.warmup + args.steps):
+        robot, sm = submap_of_step(step, 0, 1)
+        poses, pts, cols = host_frames(robot, sm, sample_frames, "cpu")
+        pts = [p.numpy() for p in pts]
+        cols = [c.numpy() for c in cols]
+        ol = orc.Layer(VOXEL_SIZE)
+        t0 = time.perf_counter()
+        for f in range(sample_frames):
+            ol.integrate(ocfg, poses[f], pts[f], cols[f], threads=threads)
+        t1 = time.perf_counter()
+        og.merge_from(ol, synth.robot_map_offset(robot), threads=threads)
+        t2 = time.perf_counter()
+        if step >= args.warmup:
+            t_int += t1 - t0
+            t_merge += t2 - t1
+            t_region += t2 - t0
+            pts_total += sum(len(p) for p in pts)
+            vox_total += 4096 * ol.num_blocks
+    value = pts_total / t_region
+    sample = (f"{sample_frames} of {FRAMES_PER_SUBMAP} frames per step "
+              f"({sample_frames * 307200} points), then merge of that partial submap")
+    line = {
+        "impl": "reference", "metric": "tsdf_points_integrated_per_s", "value": value,
+        "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_region / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "integrate": {"value": pts_total / t_int, "unit": "points/s"},
+        "merge": {"value": vox_total / t_merge, "unit": "voxels/s"},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from coxgraph_b200 import (Context, Layer, TsdfIntegrator, TsdfIntegratorConfig,
+                               mergeLayerAintoLayerB, synth)
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = Context(local_rank, stream=stream.cuda_stream)
+    gcfg = TsdfIntegratorConfig(**CFG)
+    submap = Layer(ctx, VOXEL_SIZE, max_blocks=4096)
+    glob = Layer(ctx, VOXEL_SIZE, max_blocks=32768)
+    integ = TsdfIntegrator(gcfg, submap)
+
+    # ---- synthetic inputs (generated on the GPU with torch, outside every timed region)
+    total_steps = args.warmup + args.steps
+    pool_n = min(total_steps, args.pool)
+    pool = []
+    for s in range(pool_n):
+        robot, sm = submap_of_step(s, rank, world)
+        poses, pts, cols = host_frames(robot, sm, FRAMES_PER_SUBMAP, dev)
+        d_pts = torch.cat(pts).contiguous()
+        d_cols = torch.cat(cols).contiguous()
+        offs = np.cumsum([0] + [len(p) for p in pts]).astype(np.uint64)
+        h_pts = torch.empty(d_pts.shape, dtype=d_pts.dtype, pin_memory=True).copy_(d_pts)
+        h_cols = torch.empty(d_cols.shape, dtype=d_cols.dtype, pin_memory=True).copy_(d_cols)
+        pool.append(dict(robot=robot, poses=poses, d_pts=d_pts, d_cols=d_cols, offs=offs,
+                         h_pts=h_pts.numpy(), h_cols=h_cols.numpy(),
+                         T_M_S=synth.robot_map_offset(robot), n=int(offs[-1])))
+    torch.cuda.synchronize()
+
+    # ---- untimed accounting pass: per-frame B_touched (the byte model's definition) and the
+    # merge block counts, for every pool submap
+    for e in pool:
+        submap.clear()
+        touched = 0
+        for f in range(FRAMES_PER_SUBMAP):
+            a, b = int(e["offs"][f]), int(e["offs"][f + 1])
+            st = integ.integratePointCloud(e["poses"][f], e["d_pts"][a:b], e["d_cols"][a:b])
+            touched += st.blocks_touched
+        e["bytes_integrate"] = 16 * e["n"] + 2 * BLOCK_BYTES * touched
+        e["blocks_in"] = submap.num_blocks
+        glob.clear()
+        ms = mergeLayerAintoLayerB(submap, e["T_M_S"], glob)
+        e["bytes_merge"] = BLOCK_BYTES * (ms.blocks_in + 2 * ms.blocks_out)
+        e["voxels_in"] = 4096 * ms.blocks_in
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # pinned result buffers for the e2e leg (the fused submap layer, voxblox layout)
+    out_idx = torch.empty((4096, 3), dtype=torch.int32, pin_memory=True).numpy()
+    out_vox_t = torch.empty((4096, 4096 * 12), dtype=torch.uint8, pin_memory=True)
+    from coxgraph_b200 import VOXEL_DTYPE
+    out_vox = out_vox_t.numpy().view(VOXEL_DTYPE).reshape(4096, 4096)
+    out_flags = torch.empty((4096,), dtype=torch.uint8, pin_memory=True).numpy()
+
+    def step_device(e, ev=None):
+        submap.clear()
+        if ev:
+            ev[0].record(stream)
+        integ.integrateBatch(e["poses"], e["d_pts"], e["d_cols"], e["offs"])
+        if ev:
+            ev[1].record(stream)
+        mergeLayerAintoLayerB(submap, e["T_M_S"], glob)
+        if ev:
+            ev[2].record(stream)
+
+    def step_e2e(e):
+        submap.clear()
+        integ.integrateBatch(e["poses"], e["h_pts"], e["h_cols"], e["offs"])   # H2D inside
+        mergeLayerAintoLayerB(submap, e["T_M_S"], glob)
+        idx, vox, fl = submap.download(out=(out_idx, out_vox, out_flags))       # D2H result
+        return len(idx)
+
+    results = {}
+    for leg in ("device", "e2e"):
+        glob.clear()
+        for s in range(args.warmup):
+            (step_device if leg == "device" else step_e2e)(pool[s % pool_n])
+        sampler = ClockSampler(local_rank)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = ctx.kernel_launches
+        if leg == "device":
+            ctx.reset_profile()
+            ctx.set_profiling(True)
+        barrier()
+        sampler.start()
+        ev_a.record(stream)
+        d2h = 0
+        for k in range(args.steps):
+            e = pool[(args.warmup + k) % pool_n]
+            if leg == "device":
+                step_device(e, evs[k])
+            else:
+                d2h += step_e2e(e) * (BLOCK_BYTES + 13)
+        ev_b.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ctx.set_profiling(False)
+        total_ms = max_over_ranks(ev_a.elapsed_time(ev_b))
+        used = [pool[(args.warmup + k) % pool_n] for k in range(args.steps)]
+        res = dict(total_ms=total_ms, clocks=clocks, launches=ctx.kernel_launches - launches0,
+                   points=sum_over_ranks(sum(e["n"] for e in used)),
+                   h2d=sum(16 * e["n"] for e in used) / args.steps, d2h=d2h / args.steps)
+        if leg == "device":
+            res["int_ms"] = max_over_ranks(sum(a.elapsed_time(b) for (a, b, _) in evs))
+            res["merge_ms"] = max_over_ranks(sum(b.elapsed_time(c) for (_, b, c) in evs))
+            res["voxels"] = sum_over_ranks(sum(e["voxels_in"] for e in used))
+            res["bytes_int"] = sum(e["bytes_integrate"] for e in used)
+            res["bytes_merge"] = sum(e["bytes_merge"] for e in used)
+            res["profile"] = ctx.profile()
+        results[leg] = res
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle, all host threads, bounded
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle_py as orc
+        threads = os.cpu_count() or 1
+        ocfg = orc.default_config(**CFG)
+        e = pool[args.warmup % pool_n]
+        ol = orc.Layer(VOXEL_SIZE)
+        t0 = time.perf_counter()
+        done = 0
+        for f in range(FRAMES_PER_SUBMAP):
+            a, b = int(e["offs"][f]), int(e["offs"][f + 1])
+            ol.integrate(ocfg, e["poses"][f], e["h_pts"][a:b], e["h_cols"][a:b], threads=threads)
+            done += b - a
+            if time.perf_counter() - t0 > args.cpu_seconds:
+                break
+        t_cpu = time.perf_counter() - t0
+        og = orc.Layer(VOXEL_SIZE)
+        t1 = time.perf_counter()
+        og.merge_from(ol, e["T_M_S"])          # single thread, as the reference merges
+        t_m = time.perf_counter() - t1
+        cpu = {"value": done / t_cpu, "unit": "points/s", "cores": threads, "kind": "port",
+               "sample": f"first {done // 307200} frames ({done} points) of one submap, "
+                         f"{threads}-thread voxblox-style integrator (oracle port)",
+               "merge_voxels_per_s": 4096 * ol.num_blocks / t_m, "merge_threads": 1}
+
+    if rank == 0:
+        dv, ee = results["device"], results["e2e"]
+        peak, peak_src = measured_peak_gbs()
+        prof = dv["profile"]
+        per_frame = ("point_keys", "bundle_sort", "bundle_scan", "bundle_fold")
+        top = max((k for k in prof if k != "transfer"), key=lambda k: prof[k][0])
+        is_merge = top.startswith("merge")
+        calls_per_step = FRAMES_PER_SUBMAP if top in per_frame else 1
+        top_ms_per_launch = prof[top][0] / (args.steps * calls_per_step)
+        alg_bytes = (dv["bytes_merge"] if is_merge else dv["bytes_int"]) / (args.steps *
+                                                                            calls_per_step)
+        achieved = alg_bytes / (top_ms_per_launch * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(top)
+        except Exception:
+            pass
+        line = {
+            "metric": "tsdf_points_integrated_per_s",
+            "value": dv["points"] / (dv["total_ms"] * 1e-3),
+            "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dv["total_ms"] / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": f"robots sharded over {world} GPU(s)",
+                       "l2": "each step streams >300 MB of fresh points and update lists "
+                             "(> 126 MB L2); distinct submap per step",
+                       "pool_submaps": pool_n},
+            "integrate": {"value": dv["points"] / (dv["int_ms"] * 1e-3), "unit": "points/s",
+                          "ms_per_step": dv["int_ms"] / args.steps,
+                          "hbm_frac_phase": dv["bytes_int"] / (dv["int_ms"] * 1e-3) / 1e9 / peak},
+            "merge": {"value": dv["voxels"] / (dv["merge_ms"] * 1e-3), "unit": "voxels/s",
+                      "ms_per_step": dv["merge_ms"] / args.steps,
+                      "hbm_frac_phase": dv["bytes_merge"] / (dv["merge_ms"] * 1e-3) / 1e9 / peak},
+            "e2e": {"value": ee["points"] / (ee["total_ms"] * 1e-3), "unit": "points/s",
+                    "ms_per_step": ee["total_ms"] / args.steps,
+                    "h2d_bytes_per_step": ee["h2d"], "d2h_bytes_per_step": ee["d2h"]},
+            "gpu_launches": dv["launches"],
+            "roofline": {"bound": "hbm", "kernel": top,
+                         "library_kernel": prof[top][1] == 0, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "ms_per_launch": top_ms_per_launch},
+            "stages_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "clocks": dv["clocks"], "clocks_e2e": ee["clocks"],
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    submap.close()
+    glob.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pool", type=int, default=6, help="distinct submaps kept resident")
+    ap.add_argument("--ref-frames", type=int, default=2,
+                    help="frames per step the reference arm fuses (bounded sample)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,24 @@ class Context:
     def synchronize(self):
         capi.check(capi.load().cg_context_synchronize(self._h))
 
+    def set_profiling(self, enable=True):
+        """Bracket every pipeline stage with CUDA events (voxblox::timing::Timer counterpart)."""
+        capi.check(capi.load().cg_context_set_profiling(self._h, int(bool(enable))))
+
+    def reset_profile(self):
+        capi.check(capi.load().cg_context_reset_profile(self._h))
+
+    def profile(self):
+        """-> {stage: (accumulated ms, own kernel launches)}"""
+        arr = (capi.StageProfile * 32)()
+        n = C.c_size_t(0)
+        capi.check(capi.load().cg_context_get_profile(self._h, arr, 32, C.byref(n)))
+        return {arr[i].name.decode(): (arr[i].ms, int(arr[i].launches)) for i in range(n.value)}
+
+    @property
+    def kernel_launches(self):
+        return int(capi.load().cg_context_kernel_launches(self._h))
+
     def close(self):
         if getattr(self, "_h", None):
             capi.load().cg_context_destroy(self._h)
@@ -103,16 +121,24 @@ class Layer:
         capi.check(capi.load().cg_layer_block_indices(self._h, n, _ptr(idx), C.byref(out)))
         return idx
 
-    def download(self):
-        """-> (block_idx int32 [B,3] sorted (z,y,x), voxels [B,4096] VOXEL_DTYPE, flags u8 [B])."""
+    def download(self, out=None):
+        """-> (block_idx int32 [B,3] sorted (z,y,x), voxels [B,4096] VOXEL_DTYPE, flags u8 [B]).
+
+        `out` = (idx, voxels, flags) preallocated host arrays (e.g. views of pinned memory) with
+        room for at least num_blocks blocks; slices of them are returned."""
         n = self.num_blocks
-        idx = np.zeros((n, 3), np.int32)
-        vox = np.zeros((n, capi.VOXELS_PER_BLOCK), VOXEL_DTYPE)
-        flags = np.zeros((n,), np.uint8)
-        out = C.c_size_t(0)
-        capi.check(capi.load().cg_layer_download(self._h, n, _ptr(idx), _ptr(vox), _ptr(flags),
-                                                 C.byref(out)))
-        return idx, vox, flags
+        if out is None:
+            idx = np.zeros((n, 3), np.int32)
+            vox = np.zeros((n, capi.VOXELS_PER_BLOCK), VOXEL_DTYPE)
+            flags = np.zeros((n,), np.uint8)
+            cap = n
+        else:
+            idx, vox, flags = out
+            cap = min(len(idx), len(vox), len(flags))
+        cnt = C.c_size_t(0)
+        capi.check(capi.load().cg_layer_download(self._h, cap, _ptr(idx), _ptr(vox), _ptr(flags),
+                                                 C.byref(cnt)))
+        return idx[:n], vox[:n], flags[:n]
 
     def upload(self, block_idx, voxels, flags=None):
         idx = np.ascontiguousarray(block_idx, np.int32).reshape(-1, 3)

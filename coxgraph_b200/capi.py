@@ -52,6 +52,10 @@ class IntegrateStats(C.Structure):
                 ("blocks_touched", C.c_uint64), ("blocks_allocated", C.c_uint64)]
 
 
+class StageProfile(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("ms", C.c_double), ("launches", C.c_uint64)]
+
+
 class MergeStats(C.Structure):
     _fields_ = [("blocks_in", C.c_uint64), ("blocks_candidate", C.c_uint64),
                 ("blocks_out", C.c_uint64)]
@@ -65,6 +69,10 @@ SYMBOLS = {
     "cg_context_create": (C.c_int32, [C.c_int32, _P, C.POINTER(_P)]),
     "cg_context_destroy": (C.c_int32, [_P]),
     "cg_context_synchronize": (C.c_int32, [_P]),
+    "cg_context_set_profiling": (C.c_int32, [_P, C.c_int32]),
+    "cg_context_get_profile": (C.c_int32, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "cg_context_reset_profile": (C.c_int32, [_P]),
+    "cg_context_kernel_launches": (C.c_uint64, [_P]),
     "cg_layer_create": (C.c_int32, [_P, C.c_float, C.c_int32, C.c_size_t, C.POINTER(_P)]),
     "cg_layer_destroy": (C.c_int32, [_P]),
     "cg_layer_clear": (C.c_int32, [_P]),

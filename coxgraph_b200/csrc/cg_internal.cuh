@@ -12,6 +12,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/coxgraph_b200.h"
 #include "cg_math.cuh"
@@ -163,6 +164,29 @@ struct CallCounters {
   int num_blocks;
 };
 
+// named stages (the reference wraps the same path in voxblox::timing::Timer scopes,
+// coxgraph/include/coxgraph/map_comm/tsdf_recover.h:63,74-76)
+enum Stage {
+  kStagePointKeys = 0,
+  kStageBundleSort,
+  kStageBundleScan,
+  kStageFold,
+  kStageRayScan,
+  kStageRayWalk,
+  kStagePairSort,
+  kStageSegments,
+  kStageVoxelUpdate,
+  kStageMergeMark,
+  kStageMergeResample,
+  kStageTransfer,
+  kNumStages
+};
+const char* stage_name(int s);
+struct PendingEvent {
+  int stage;
+  cudaEvent_t start, stop;
+};
+
 }  // namespace cg
 
 struct cg_context {
@@ -176,9 +200,17 @@ struct cg_context {
   cg::DevBuf points, colors, poses, frame_base;
   cg::DevBuf key_a, key_b, val_a, val_b, flags, scan, cub_tmp;
   cg::DevBuf rays, ray_count, ray_offset;
-  cg::DevBuf pkey_a, pkey_b, pval_a, pval_b;
+  cg::DevBuf pkey_a, pkey_b, pval_a, pval_b, seg_start;
+  uint32_t* d_select_count = nullptr;  // output count of the stream compactions
   // merge / transfer scratch
   cg::DevBuf cand_keys, cand_list, stage_a, stage_b, stage_c;
+  // instrumentation
+  bool profiling = false;
+  uint64_t own_launches = 0;  // kernels of this library launched (library sorts/scans excluded)
+  double stage_ms[cg::kNumStages] = {};
+  uint64_t stage_launches[cg::kNumStages] = {};
+  std::vector<cg::PendingEvent> pending;
+  std::vector<cudaEvent_t> event_pool;
 };
 
 struct cg_layer {
@@ -201,6 +233,39 @@ int32_t finish_call(cg_layer* layer, CallCounters* out);
     cudaError_t _e = (expr);                                  \
     if (_e != cudaSuccess) return cg::cuda_fail(_e, #expr);   \
   } while (0)
+
+// RAII scope around one pipeline stage: counts the library's own kernel launches and, when
+// profiling is on, brackets the stage with CUDA events on the context's stream.
+struct StageScope {
+  cg_context* ctx;
+  int stage;
+  cudaEvent_t start = nullptr, stop = nullptr;
+  StageScope(cg_context* c, int st, int own_kernels) : ctx(c), stage(st) {
+    ctx->own_launches += own_kernels;
+    ctx->stage_launches[st] += own_kernels;
+    if (ctx->profiling) {
+      start = take();
+      stop = take();
+      cudaEventRecord(start, ctx->stream);
+    }
+  }
+  ~StageScope() {
+    if (start) {
+      cudaEventRecord(stop, ctx->stream);
+      ctx->pending.push_back(PendingEvent{stage, start, stop});
+    }
+  }
+  cudaEvent_t take() {
+    if (!ctx->event_pool.empty()) {
+      cudaEvent_t e = ctx->event_pool.back();
+      ctx->event_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
 
 inline unsigned grid_for(size_t n, unsigned block) {
   return static_cast<unsigned>((n + block - 1) / block);

@@ -3,19 +3,29 @@
 // Replaces voxblox::TsdfIntegratorBase::integratePointCloud (Simple / Merged semantics, R1-R6 of
 // SURVEY.md §8a); reference call site coxgraph/include/coxgraph/map_comm/tsdf_recover.h:75.
 //
-// Pipeline per submitted job (one frame, or a batch of frames into the same layer):
-//   per frame   k_point_keys      validity, T_G_C * p, bundle key (voxel of p_G), in index-getter order
-//               radix sort        stable sort-by-key  -> bundles, points inside a bundle in visit order
-//               k_mark_heads/scan bundle ids
-//               k_fold_bundles    sequential weighted mean / colour blend per bundle -> one ray
-//   per job     scan              pair offsets from the closed-form ray length (steps + 1)
-//               k_ray_walk        3-D DDA per ray; warp-independent hash insert of every block the
-//                                 ray visits; emits (hash entry, voxel) keys in ray order
-//               radix sort        stable sort-by-key -> per-voxel update lists in canonical order
-//               k_voxel_update    one owner per voxel replays its updates sequentially
-// The only value-dependent ordering is per voxel: (frame, non-clearing before clearing, bundle
-// key ascending) — exactly the oracle's canonical order, so results do not depend on scheduling.
+// One job = one frame, or a batch of frames fused into the same layer (the loop of
+// tsdf_recover.h:71-86).  All frames of a job go through every stage together:
+//   k_point_keys    validity, T_G_C * p, bundle key = (frame | clearing | voxel of p_G relative to
+//                   the sensor voxel), written in index-getter ("mixed") order
+//   radix sort      stable sort-by-key -> bundles in canonical order, points of a bundle in the
+//                   order the reference visits them
+//   select          bundle heads
+//   k_fold_bundles  one warp per bundle: cooperative gather, then the reference's *sequential*
+//                   weighted mean / colour blend (bit-exact: the merged point decides which voxels
+//                   and blocks the ray visits) -> one ray per bundle
+//   scan            pair offsets from the closed-form ray length (steps + 1)
+//   k_ray_walk      3-D DDA per ray (voxblox::RayCaster); inserts every visited block into the
+//                   GPU hash (allocation on first visit, R4); emits (hash entry, voxel) keys
+//   radix sort      stable sort-by-key -> per-voxel update lists in canonical order
+//   select          voxel segment heads
+//   k_voxel_update  one warp per voxel segment; 32 updates at a time: weights by prefix sum, the
+//                   clamped weighted average as an ordered composition of clamped affine maps
+//                   x -> clamp(a x + b) (associative, so it reduces in log steps), colours
+//                   replayed sequentially for the few updates inside the truncation band.
+// Per-voxel order is (frame, non-clearing before clearing, bundle key ascending) — the oracle's
+// canonical order — independent of scheduling.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -26,12 +36,20 @@
 
 namespace cg {
 
-struct Ray {          // 24 B
-  float px, py, pz;   // merged point, global frame
-  float weight;       // merged weight
-  uint32_t color;     // merged colour
-  uint32_t frame_clr; // frame index in job | clearing << 31
+struct Ray {           // 24 B
+  float px, py, pz;    // merged point, global frame
+  float weight;        // merged weight
+  uint32_t color;      // merged colour
+  uint32_t frame_clr;  // frame index in job | clearing << 31 ; 0xFFFFFFFF = no ray
 };
+constexpr uint32_t kNoRay = 0xFFFFFFFFu;
+
+// bundle key layout: [frame | clearing(1) | z(13) y(13) x(13)], voxel index relative to the
+// voxel holding the sensor origin
+constexpr int kRelBits = 13;
+constexpr int kRelOffset = 1 << (kRelBits - 1);
+constexpr int kBundleClearBit = 3 * kRelBits;
+constexpr int kBundleFrameShift = kBundleClearBit + 1;
 
 __device__ __forceinline__ int order_index(int k, int n, int mode) {
   // voxblox MixedThreadSafeIndex: groups of 1024 visited round-robin
@@ -41,130 +59,193 @@ __device__ __forceinline__ int order_index(int k, int n, int mode) {
   return (k % groups) * 1024 + (k / groups);
 }
 
-__device__ __forceinline__ V3 load_point(const float* pts, int i) {
+__device__ __forceinline__ V3 load_point(const float* pts, size_t i) {
   return V3{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
 }
 
-// ------------------------------------------------------------------ MERGED front half
-__global__ void k_point_keys(IntegratorParams P, Xform T, const float* __restrict__ pts, int n,
+// frame of global slot g (offs has F+1 entries)
+__device__ __forceinline__ int frame_of(const uint64_t* __restrict__ offs, int F, uint64_t g) {
+  int lo = 0, hi = F;  // offs[lo] <= g < offs[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (offs[mid] <= g) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------ front half
+// slot g enumerates (frame, visit rank k); vals = global point index
+__global__ void k_point_keys(IntegratorParams P, const float* __restrict__ poses,
+                             const uint64_t* __restrict__ offs, int F,
+                             const float* __restrict__ pts, uint64_t total,
                              uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
                              int32_t* err) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const int i = order_index(k, n, P.order_mode);
-  const V3 pc = load_point(pts, i);
+  const uint64_t g = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+  if (g >= total) return;
+  const int f = frame_of(offs, F, g);
+  const uint64_t base = offs[f];
+  const int n = static_cast<int>(offs[f + 1] - base);
+  const int i = order_index(static_cast<int>(g - base), n, P.order_mode);
+  const V3 pc = load_point(pts, base + i);
   bool clearing = false;
   uint64_t key = kInvalidPointKey;
   if (point_valid(P, pc, &clearing)) {
+    const Xform T = make_xform(poses + 7 * f);
     const V3 pg = apply(T, pc);
     const float lim = 524000.0f * P.voxel_size;
-    if (fabsf(pg.x) < lim && fabsf(pg.y) < lim && fabsf(pg.z) < lim) {
-      const int vx = grid_index(pg.x, P.voxel_size_inv);
-      const int vy = grid_index(pg.y, P.voxel_size_inv);
-      const int vz = grid_index(pg.z, P.voxel_size_inv);
-      key = pack_voxel_key(vx, vy, vz) | (static_cast<uint64_t>(clearing) << kClearingBit);
+    if (fabsf(pg.x) < lim && fabsf(pg.y) < lim && fabsf(pg.z) < lim && fabsf(T.t.x) < lim &&
+        fabsf(T.t.y) < lim && fabsf(T.t.z) < lim) {
+      const int rx = grid_index(pg.x, P.voxel_size_inv) - grid_index(T.t.x, P.voxel_size_inv);
+      const int ry = grid_index(pg.y, P.voxel_size_inv) - grid_index(T.t.y, P.voxel_size_inv);
+      const int rz = grid_index(pg.z, P.voxel_size_inv) - grid_index(T.t.z, P.voxel_size_inv);
+      if (abs(rx) < kRelOffset && abs(ry) < kRelOffset && abs(rz) < kRelOffset) {
+        key = (static_cast<uint64_t>(f) << kBundleFrameShift) |
+              (static_cast<uint64_t>(clearing) << kBundleClearBit) |
+              (static_cast<uint64_t>(rz + kRelOffset) << (2 * kRelBits)) |
+              (static_cast<uint64_t>(ry + kRelOffset) << kRelBits) |
+              static_cast<uint64_t>(rx + kRelOffset);
+      } else {
+        atomicOr(err, kErrOutOfRange);
+      }
     } else {
       atomicOr(err, kErrOutOfRange);
     }
   }
-  keys[k] = key;
-  vals[k] = static_cast<uint32_t>(i);
+  keys[g] = key;
+  vals[g] = static_cast<uint32_t>(base + i);
 }
 
-__global__ void k_mark_heads(const uint64_t* __restrict__ keys, int n, uint32_t* flags) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint64_t key = keys[k];
-  flags[k] = (key != kInvalidPointKey && (k == 0 || keys[k - 1] != key)) ? 1u : 0u;
-}
-
-// one thread per bundle head: MergedTsdfIntegrator::integrateVoxel, first half
-__global__ void k_fold_bundles(IntegratorParams P, Xform T, int frame,
-                               const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                               const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan,
-                               int n, const float* __restrict__ pts,
-                               const uint32_t* __restrict__ cols, uint32_t* frame_base, Ray* rays,
-                               uint32_t* ray_count) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t base = frame_base[frame];
-  if (k == n - 1) frame_base[frame + 1] = base + scan[k] + flags[k];
-  if (!flags[k]) return;
-  const uint64_t key = keys[k];
-  const bool clearing = (key >> kClearingBit) & 1;
-  uint32_t merged_color = kDefaultColor;
-  V3 merged = V3{0.0f, 0.0f, 0.0f};
-  float merged_weight = 0.0f;
-  for (int j = k; j < n && keys[j] == key; ++j) {
-    const int i = static_cast<int>(vals[j]);
-    const V3 pc = load_point(pts, i);
-    const float w = voxel_weight(P, pc.z);
-    if (w < kEps) continue;
-    merged = (merged * merged_weight + pc * w) / (merged_weight + w);
-    merged_color = blend_colors(merged_color, merged_weight, cols[i], w);
-    merged_weight += w;
-    if (clearing) break;  // only the first point of a clearing bundle is used
+struct BundleHead {
+  const uint64_t* keys;
+  __device__ __forceinline__ bool operator()(uint32_t i) const {
+    // the first invalid key is a head too: it terminates the last real bundle
+    return i == 0 || keys[i] != keys[i - 1];
   }
-  const V3 pg = apply(T, merged);
-  RayCaster rc;
-  rc.init(T.t, pg, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc);
-  const uint32_t r = base + scan[k];
-  Ray ray;
-  ray.px = pg.x;
-  ray.py = pg.y;
-  ray.pz = pg.z;
-  ray.weight = merged_weight;
-  ray.color = merged_color;
-  ray.frame_clr = static_cast<uint32_t>(frame) | (clearing ? 0x80000000u : 0u);
-  rays[r] = ray;
-  ray_count[r] = rc.valid ? rc.steps + 1u : 0u;
+};
+
+// One warp per bundle: MergedTsdfIntegrator::integrateVoxel, first half.  Loads are cooperative,
+// the arithmetic is the reference's sequential recurrence (all lanes compute it redundantly).
+__global__ void __launch_bounds__(256)
+k_fold_bundles(IntegratorParams P, const float* __restrict__ poses,
+               const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+               uint32_t total, const uint32_t* __restrict__ heads,
+               const uint32_t* __restrict__ num_heads, const float* __restrict__ pts,
+               const uint32_t* __restrict__ cols, Ray* __restrict__ rays,
+               uint32_t* __restrict__ ray_count) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t nb = *num_heads;
+  for (uint32_t b = warp; b < nb; b += num_warps) {
+    const uint32_t start = heads[b];
+    const uint32_t end = (b + 1 < nb) ? heads[b + 1] : total;
+    const uint64_t key = keys[start];
+    if (key == kInvalidPointKey) {  // sentinel bundle of dropped points
+      if (lane == 0) {
+        rays[b].frame_clr = kNoRay;
+        ray_count[b] = 0;
+      }
+      continue;
+    }
+    const uint32_t frame = static_cast<uint32_t>(key >> kBundleFrameShift);
+    const bool clearing = (key >> kBundleClearBit) & 1;
+    uint32_t merged_color = kDefaultColor;
+    V3 merged = V3{0.0f, 0.0f, 0.0f};
+    float merged_weight = 0.0f;
+    bool done = false;
+    for (uint32_t c0 = start; c0 < end && !done; c0 += 32) {
+      const uint32_t j = c0 + lane;
+      V3 pc = V3{0.0f, 0.0f, 0.0f};
+      uint32_t col = 0;
+      if (j < end) {
+        const uint32_t i = vals[j];
+        pc = load_point(pts, i);
+        col = cols[i];
+      }
+      const int cnt = static_cast<int>(min(32u, end - c0));
+      for (int t = 0; t < cnt; ++t) {
+        const V3 q = V3{__shfl_sync(0xFFFFFFFFu, pc.x, t), __shfl_sync(0xFFFFFFFFu, pc.y, t),
+                        __shfl_sync(0xFFFFFFFFu, pc.z, t)};
+        const uint32_t qc = __shfl_sync(0xFFFFFFFFu, col, t);
+        const float w = voxel_weight(P, q.z);
+        if (w < kEps) continue;
+        merged = (merged * merged_weight + q * w) / (merged_weight + w);
+        merged_color = blend_colors(merged_color, merged_weight, qc, w);
+        merged_weight += w;
+        if (clearing) {  // only the first point of a clearing bundle is used
+          done = true;
+          break;
+        }
+      }
+    }
+    if (lane == 0) {
+      const Xform T = make_xform(poses + 7 * frame);
+      const V3 pg = apply(T, merged);
+      RayCaster rc;
+      rc.init(T.t, pg, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc);
+      Ray ray;
+      ray.px = pg.x;
+      ray.py = pg.y;
+      ray.pz = pg.z;
+      ray.weight = merged_weight;
+      ray.color = merged_color;
+      ray.frame_clr = frame | (clearing ? 0x80000000u : 0u);
+      rays[b] = ray;
+      ray_count[b] = rc.valid ? rc.steps + 1u : 0u;
+    }
+  }
 }
 
-// ------------------------------------------------------------------ SIMPLE front half
-__global__ void k_simple_flags(IntegratorParams P, const float* __restrict__ pts, int n,
-                               uint32_t* flags) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  bool clearing;
-  flags[k] = point_valid(P, load_point(pts, order_index(k, n, P.order_mode)), &clearing) ? 1u : 0u;
-}
+// SIMPLE: one ray per valid point, in (frame, visit rank) order
+struct ValidSlot {
+  IntegratorParams P;
+  const uint64_t* offs;
+  int F;
+  const float* pts;
+  __device__ __forceinline__ bool operator()(uint32_t g) const {
+    const int f = frame_of(offs, F, g);
+    const uint64_t base = offs[f];
+    const int n = static_cast<int>(offs[f + 1] - base);
+    bool clearing;
+    return point_valid(P, load_point(pts, base + order_index(static_cast<int>(g - base), n,
+                                                             P.order_mode)), &clearing);
+  }
+};
 
-__global__ void k_simple_rays(IntegratorParams P, Xform T, int frame,
-                              const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan,
-                              int n, const float* __restrict__ pts,
-                              const uint32_t* __restrict__ cols, uint32_t* frame_base, Ray* rays,
-                              uint32_t* ray_count) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t base = frame_base[frame];
-  if (k == n - 1) frame_base[frame + 1] = base + scan[k] + flags[k];
-  if (!flags[k]) return;
-  const int i = order_index(k, n, P.order_mode);
+__global__ void k_simple_rays(IntegratorParams P, const float* __restrict__ poses,
+                              const uint64_t* __restrict__ offs, int F,
+                              const uint32_t* __restrict__ slots,
+                              const uint32_t* __restrict__ num_slots, const float* __restrict__ pts,
+                              const uint32_t* __restrict__ cols, Ray* __restrict__ rays,
+                              uint32_t* __restrict__ ray_count) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= *num_slots) return;
+  const uint32_t g = slots[r];
+  const int f = frame_of(offs, F, g);
+  const uint64_t base = offs[f];
+  const int n = static_cast<int>(offs[f + 1] - base);
+  const size_t i = base + order_index(static_cast<int>(g - base), n, P.order_mode);
   const V3 pc = load_point(pts, i);
   bool clearing = false;
   point_valid(P, pc, &clearing);
+  const Xform T = make_xform(poses + 7 * f);
   const V3 pg = apply(T, pc);
   RayCaster rc;
   rc.init(T.t, pg, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc);
-  const uint32_t r = base + scan[k];
   Ray ray;
   ray.px = pg.x;
   ray.py = pg.y;
   ray.pz = pg.z;
   ray.weight = voxel_weight(P, pc.z);
   ray.color = cols[i];
-  ray.frame_clr = static_cast<uint32_t>(frame) | (clearing ? 0x80000000u : 0u);
+  ray.frame_clr = static_cast<uint32_t>(f) | (clearing ? 0x80000000u : 0u);
   rays[r] = ray;
   ray_count[r] = rc.valid ? rc.steps + 1u : 0u;
 }
 
-__global__ void k_copy_base(uint32_t* frame_base, int frame) {
-  frame_base[frame + 1] = frame_base[frame];
-}
-
-__global__ void k_totals(const uint32_t* frame_base, int frames, const uint32_t* ray_count,
+__global__ void k_totals(const uint32_t* num_rays, const uint32_t* ray_count,
                          const uint32_t* ray_offset, size_t upper, CallCounters* c) {
-  c->rays = frame_base[frames];
+  c->rays = *num_rays;
   c->pairs = upper ? static_cast<unsigned long long>(ray_offset[upper - 1]) + ray_count[upper - 1]
                    : 0ull;
   c->touched = 0;
@@ -181,6 +262,7 @@ __global__ void k_ray_walk(IntegratorParams P, const float* __restrict__ poses,
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= num_rays) return;
   const Ray ray = rays[r];
+  if (ray.frame_clr == kNoRay) return;
   const uint32_t frame = ray.frame_clr & 0x7FFFFFFFu;
   const bool clearing = (ray.frame_clr >> 31) != 0;
   const float* T = poses + 7 * frame;
@@ -211,43 +293,130 @@ __global__ void k_ray_walk(IntegratorParams P, const float* __restrict__ poses,
   }
 }
 
-// One owner thread per voxel: replays the voxel's update list in order (R5).
 template <class K>
-__global__ void k_voxel_update(IntegratorParams P, const float* __restrict__ poses,
-                               const Ray* __restrict__ rays, const K* __restrict__ pkeys,
-                               const uint32_t* __restrict__ pvals, size_t num_pairs, LayerView L,
-                               CallCounters* counters) {
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (i >= num_pairs) return;
-  const K key = pkeys[i];
-  const K prev = i ? pkeys[i - 1] : ~key;
-  if (i && prev == key) return;  // not the head of its voxel segment
-  const uint32_t entry = static_cast<uint32_t>(key >> 12);
-  const int lin = static_cast<int>(key & 4095);
-  const int slot = L.hash_vals[entry];
-  if (slot < 0) return;  // pool exhausted; error already flagged
-  if (i == 0 || static_cast<uint32_t>(prev >> 12) != entry) {
-    atomicAdd(&counters->touched, 1ull);
-    L.updated[slot] = 1;
+struct SegmentHead {
+  const K* keys;
+  __device__ __forceinline__ bool operator()(uint32_t i) const {
+    return i == 0 || keys[i] != keys[i - 1];
   }
-  int bx, by, bz;
-  unpack_block_key(L.hash_keys[entry], bx, by, bz);
-  const int gx = bx * 16 + (lin & 15), gy = by * 16 + ((lin >> 4) & 15), gz = bz * 16 + (lin >> 8);
-  const V3 center = V3{center_coord(gx, P.voxel_size), center_coord(gy, P.voxel_size),
-                       center_coord(gz, P.voxel_size)};
-  float* dp = L.dist_plane(slot) + lin;
-  float* wp = L.weight_plane(slot) + lin;
-  uint32_t* cp = L.color_plane(slot) + lin;
-  VoxelState v{*dp, *wp, *cp};
-  for (size_t j = i; j < num_pairs && pkeys[j] == key; ++j) {
-    const Ray ray = rays[pvals[j]];
-    const float* T = poses + 7 * (ray.frame_clr & 0x7FFFFFFFu);
-    update_tsdf_voxel(P, V3{T[4], T[5], T[6]}, V3{ray.px, ray.py, ray.pz}, center, ray.color,
-                      ray.weight, v);
+};
+
+// x -> clamp(a x + b, lo, hi), a >= 0.  Closed under composition.
+struct ClampedAffine {
+  float a, b, lo, hi;
+};
+__device__ __forceinline__ ClampedAffine compose(const ClampedAffine& f, const ClampedAffine& g) {
+  // g after f
+  ClampedAffine r;
+  r.a = g.a * f.a;
+  r.b = g.a * f.b + g.b;
+  r.lo = fminf(fmaxf(g.a * f.lo + g.b, g.lo), g.hi);
+  r.hi = fminf(fmaxf(g.a * f.hi + g.b, g.lo), g.hi);
+  return r;
+}
+constexpr float kBig = 1.0e30f;
+
+// One warp per voxel segment (R5 updateTsdfVoxel replayed over the voxel's update list).
+template <class K>
+__global__ void __launch_bounds__(256)
+k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
+               const K* __restrict__ pkeys, const uint32_t* __restrict__ pvals, uint32_t num_pairs,
+               const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ num_segs,
+               LayerView L, CallCounters* counters) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t ns = *num_segs;
+  for (uint32_t s = warp; s < ns; s += num_warps) {
+    const uint32_t start = seg_start[s];
+    const uint32_t end = (s + 1 < ns) ? seg_start[s + 1] : num_pairs;
+    const K key = pkeys[start];
+    const uint32_t entry = static_cast<uint32_t>(key >> 12);
+    const int lin = static_cast<int>(key & 4095);
+    const int slot = L.hash_vals[entry];
+    if (slot < 0) continue;  // pool exhausted; error already flagged
+    if (lane == 0 && (start == 0 || static_cast<uint32_t>(pkeys[start - 1] >> 12) != entry)) {
+      atomicAdd(&counters->touched, 1ull);
+      L.updated[slot] = 1;
+    }
+    int bx, by, bz;
+    unpack_block_key(L.hash_keys[entry], bx, by, bz);
+    const V3 center = V3{center_coord(bx * 16 + (lin & 15), P.voxel_size),
+                         center_coord(by * 16 + ((lin >> 4) & 15), P.voxel_size),
+                         center_coord(bz * 16 + (lin >> 8), P.voxel_size)};
+    float* dp = L.dist_plane(slot) + lin;
+    float* wp = L.weight_plane(slot) + lin;
+    uint32_t* cp = L.color_plane(slot) + lin;
+    float D = *dp, W = *wp;
+    uint32_t C = *cp;
+    for (uint32_t c0 = start; c0 < end; c0 += 32) {
+      const uint32_t j = c0 + lane;
+      const bool act = j < end;
+      float sdf = 0.0f, w = 0.0f;
+      uint32_t col = 0;
+      if (act) {
+        const Ray ray = rays[pvals[j]];
+        const float* T = poses + 7 * (ray.frame_clr & 0x7FFFFFFFu);
+        const V3 origin = V3{T[4], T[5], T[6]};
+        const V3 pg = V3{ray.px, ray.py, ray.pz};
+        // computeDistance + weight drop-off / sparsity compensation (state independent)
+        const V3 v_voxel_origin = center - origin;
+        const V3 v_point_origin = pg - origin;
+        const float dist_G = norm3(v_point_origin);
+        const float dist_G_V = dot3(v_voxel_origin, v_point_origin) / dist_G;
+        sdf = dist_G - dist_G_V;
+        w = ray.weight;
+        if (P.weight_dropoff && sdf < -P.voxel_size) {
+          w = w * (P.trunc + sdf) / (P.trunc - P.voxel_size);
+          w = fmaxf(w, 0.0f);
+        }
+        if (P.use_sparsity && fabsf(sdf) < P.trunc) w *= P.sparsity_factor;
+        col = ray.color;
+      }
+      // weights: W_k = min(max_weight, W_{k-1} + w_k)  ==  min(max_weight, W_0 + sum w)
+      float pre = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float o = __shfl_up_sync(0xFFFFFFFFu, pre, d);
+        if (lane >= d) pre += o;
+      }
+      const float w_prev = fminf(P.max_weight, W + (pre - w));
+      const float w_new = w_prev + w;
+      const bool skip = !act || w_new < kEps;  // "new_weight < kFloatEpsilon -> return"
+      ClampedAffine f;
+      f.a = skip ? 1.0f : w_prev / w_new;
+      f.b = skip ? 0.0f : (sdf * w) / w_new;
+      f.lo = skip ? -kBig : -P.trunc;
+      f.hi = skip ? kBig : P.trunc;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {  // ordered tree reduction into lane 0
+        ClampedAffine g;
+        g.a = __shfl_down_sync(0xFFFFFFFFu, f.a, d);
+        g.b = __shfl_down_sync(0xFFFFFFFFu, f.b, d);
+        g.lo = __shfl_down_sync(0xFFFFFFFFu, f.lo, d);
+        g.hi = __shfl_down_sync(0xFFFFFFFFu, f.hi, d);
+        if ((lane & (2 * d - 1)) == 0) f = compose(f, g);
+      }
+      const float fa = __shfl_sync(0xFFFFFFFFu, f.a, 0), fb = __shfl_sync(0xFFFFFFFFu, f.b, 0);
+      const float flo = __shfl_sync(0xFFFFFFFFu, f.lo, 0), fhi = __shfl_sync(0xFFFFFFFFu, f.hi, 0);
+      D = fminf(fmaxf(fa * D + fb, flo), fhi);
+      // colours: sequential over the updates inside the truncation band (few per chunk)
+      unsigned band = __ballot_sync(0xFFFFFFFFu, !skip && fabsf(sdf) < P.trunc);
+      while (band) {
+        const int t = __ffs(band) - 1;
+        band &= band - 1;
+        C = blend_colors(C, __shfl_sync(0xFFFFFFFFu, w_prev, t), __shfl_sync(0xFFFFFFFFu, col, t),
+                         __shfl_sync(0xFFFFFFFFu, w, t));
+      }
+      const float w_after = skip ? w_prev : fminf(P.max_weight, w_new);
+      W = __shfl_sync(0xFFFFFFFFu, w_after, 31);
+    }
+    if (lane == 0) {
+      *dp = D;
+      *wp = W;
+      *cp = C;
+    }
   }
-  *dp = v.d;
-  *wp = v.w;
-  *cp = v.c;
 }
 
 // ------------------------------------------------------------------ host orchestration
@@ -284,18 +453,38 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
   CG_CUDA(ctx->pkey_b.reserve(num_pairs * sizeof(K)));
   CG_CUDA(ctx->pval_a.reserve(num_pairs * sizeof(uint32_t)));
   CG_CUDA(ctx->pval_b.reserve(num_pairs * sizeof(uint32_t)));
-  k_ray_walk<K><<<grid_for(num_rays, 128), 128, 0, s>>>(
-      P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), ctx->ray_offset.as<uint32_t>(), num_rays,
-      L->v, ctx->pkey_a.as<K>(), ctx->pval_a.as<uint32_t>());
+  CG_CUDA(ctx->seg_start.reserve(num_pairs * sizeof(uint32_t)));
+  uint32_t* d_num = ctx->d_select_count;
+  {
+    StageScope sc(ctx, kStageRayWalk, 1);
+    k_ray_walk<K><<<grid_for(num_rays, 128), 128, 0, s>>>(
+        P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), ctx->ray_offset.as<uint32_t>(), num_rays,
+        L->v, ctx->pkey_a.as<K>(), ctx->pval_a.as<uint32_t>());
+  }
   cub::DoubleBuffer<K> dk(ctx->pkey_a.as<K>(), ctx->pkey_b.as<K>());
   cub::DoubleBuffer<uint32_t> dv(ctx->pval_a.as<uint32_t>(), ctx->pval_b.as<uint32_t>());
-  size_t tmp = 0;
+  size_t tmp = 0, tmp2 = 0;
   CG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, num_pairs, 0, key_bits, s));
-  CG_CUDA(ctx->cub_tmp.reserve(tmp));
-  CG_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, dk, dv, num_pairs, 0, key_bits, s));
-  k_voxel_update<K><<<grid_for(num_pairs, 128), 128, 0, s>>>(
-      P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), dv.Current(), num_pairs, L->v,
-      ctx->d_counters);
+  thrust::counting_iterator<uint32_t> iota(0);
+  CG_CUDA(cub::DeviceSelect::If(nullptr, tmp2, iota, ctx->seg_start.as<uint32_t>(), d_num,
+                                static_cast<int>(num_pairs), SegmentHead<K>{nullptr}, s));
+  CG_CUDA(ctx->cub_tmp.reserve(std::max(tmp, tmp2)));
+  {
+    StageScope sc(ctx, kStagePairSort, 0);
+    CG_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, dk, dv, num_pairs, 0, key_bits, s));
+  }
+  {
+    StageScope sc(ctx, kStageSegments, 0);
+    CG_CUDA(cub::DeviceSelect::If(ctx->cub_tmp.p, tmp2, iota, ctx->seg_start.as<uint32_t>(), d_num,
+                                  static_cast<int>(num_pairs), SegmentHead<K>{dk.Current()}, s));
+  }
+  {
+    StageScope sc(ctx, kStageVoxelUpdate, 1);
+    k_voxel_update<K><<<ctx->num_sms * 8, 256, 0, s>>>(
+        P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), dv.Current(),
+        static_cast<uint32_t>(num_pairs), ctx->seg_start.as<uint32_t>(), d_num, L->v,
+        ctx->d_counters);
+  }
   CG_CUDA(cudaGetLastError());
   return CG_OK;
 }
@@ -309,79 +498,104 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   cg_context* ctx = L->ctx;
   cudaStream_t s = ctx->stream;
   const size_t F = f1 - f0;
-  const size_t upper = offs[f1] - offs[f0];  // upper bound on rays
-  if (upper == 0) return CG_OK;
-  size_t max_n = 0;
-  for (size_t f = f0; f < f1; ++f) max_n = std::max<size_t>(max_n, offs[f + 1] - offs[f]);
-  if (max_n > 0x7FFFFFFFull || upper > 0xFFFFFFF0ull) {
-    set_error("too many points in one frame / group");
+  const size_t total = offs[f1] - offs[f0];  // points of the group = upper bound on rays
+  if (total == 0) return CG_OK;
+  if (total > 0x7FFFFFF0ull || F > (1u << 20)) {
+    set_error("too many points / frames in one group");
     return CG_ERR_INVALID_ARG;
   }
+  const size_t upper = total + 1;  // + the sentinel bundle of dropped points
   CG_CUDA(ctx->rays.reserve(upper * sizeof(Ray)));
   CG_CUDA(ctx->ray_count.reserve(upper * sizeof(uint32_t)));
   CG_CUDA(ctx->ray_offset.reserve(upper * sizeof(uint32_t)));
   CG_CUDA(ctx->poses.reserve(F * 7 * sizeof(float)));
-  CG_CUDA(ctx->frame_base.reserve((F + 1) * sizeof(uint32_t)));
-  CG_CUDA(ctx->key_a.reserve(max_n * sizeof(uint64_t)));
-  CG_CUDA(ctx->key_b.reserve(max_n * sizeof(uint64_t)));
-  CG_CUDA(ctx->val_a.reserve(max_n * sizeof(uint32_t)));
-  CG_CUDA(ctx->val_b.reserve(max_n * sizeof(uint32_t)));
-  CG_CUDA(ctx->flags.reserve(max_n * sizeof(uint32_t)));
-  CG_CUDA(ctx->scan.reserve(max_n * sizeof(uint32_t)));
-  size_t tmp_sort = 0, tmp_scan = 0, tmp_scan2 = 0;
+  CG_CUDA(ctx->frame_base.reserve((F + 1) * sizeof(uint64_t)));
+  CG_CUDA(ctx->scan.reserve(upper * sizeof(uint32_t)));  // bundle heads / valid slots
+  const bool merged = cfg->method == CG_METHOD_MERGED;
+  if (merged) {
+    CG_CUDA(ctx->key_a.reserve(total * sizeof(uint64_t)));
+    CG_CUDA(ctx->key_b.reserve(total * sizeof(uint64_t)));
+    CG_CUDA(ctx->val_a.reserve(total * sizeof(uint32_t)));
+    CG_CUDA(ctx->val_b.reserve(total * sizeof(uint32_t)));
+  }
+  int frame_bits = 0;
+  while ((size_t(1) << frame_bits) < F) ++frame_bits;
+  const int bundle_bits = kBundleFrameShift + frame_bits;
+  cub::DoubleBuffer<uint64_t> dk(ctx->key_a.as<uint64_t>(), ctx->key_b.as<uint64_t>());
+  cub::DoubleBuffer<uint32_t> dv(ctx->val_a.as<uint32_t>(), ctx->val_b.as<uint32_t>());
+  thrust::counting_iterator<uint32_t> iota(0);
+  uint32_t* d_num = ctx->d_select_count;
+  // group-relative frame offsets on the device
+  std::vector<uint64_t> rel(F + 1);
+  for (size_t f = 0; f <= F; ++f) rel[f] = offs[f0 + f] - offs[f0];
+  const float* pts = d_points + 3 * offs[f0];
+  const uint32_t* cols = reinterpret_cast<const uint32_t*>(d_colors) + offs[f0];
+  const uint64_t* d_offs = ctx->frame_base.as<uint64_t>();
+  ValidSlot valid{P, d_offs, static_cast<int>(F), pts};
+  size_t tmp_sort = 0, tmp_sel = 0, tmp_scan = 0;
+  if (merged) {
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, dk, dv, total, 0, bundle_bits, s);
+    cub::DeviceSelect::If(nullptr, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
+                          static_cast<int>(total), BundleHead{nullptr}, s);
+  } else {
+    cub::DeviceSelect::If(nullptr, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
+                          static_cast<int>(total), valid, s);
+  }
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, ctx->ray_count.as<uint32_t>(),
+                                ctx->ray_offset.as<uint32_t>(), static_cast<int>(upper), s);
+  CG_CUDA(ctx->cub_tmp.reserve(std::max(tmp_sort, std::max(tmp_sel, tmp_scan))));
   {
-    cub::DoubleBuffer<uint64_t> dk(ctx->key_a.as<uint64_t>(), ctx->key_b.as<uint64_t>());
-    cub::DoubleBuffer<uint32_t> dv(ctx->val_a.as<uint32_t>(), ctx->val_b.as<uint32_t>());
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, dk, dv, static_cast<int>(max_n), 0, 61, s);
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, ctx->flags.as<uint32_t>(),
-                                  ctx->scan.as<uint32_t>(), static_cast<int>(max_n), s);
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan2, ctx->ray_count.as<uint32_t>(),
-                                  ctx->ray_offset.as<uint32_t>(), upper, s);
+    StageScope sc(ctx, kStageTransfer, 0);
+    CG_CUDA(cudaMemcpyAsync(ctx->poses.p, h_poses + 7 * f0, F * 7 * sizeof(float),
+                            cudaMemcpyHostToDevice, s));
+    CG_CUDA(cudaMemcpyAsync(ctx->frame_base.p, rel.data(), (F + 1) * sizeof(uint64_t),
+                            cudaMemcpyHostToDevice, s));
+    CG_CUDA(cudaMemsetAsync(ctx->ray_count.p, 0, upper * sizeof(uint32_t), s));
   }
-  CG_CUDA(ctx->cub_tmp.reserve(std::max(tmp_sort, std::max(tmp_scan, tmp_scan2))));
-  CG_CUDA(cudaMemcpyAsync(ctx->poses.p, h_poses + 7 * f0, F * 7 * sizeof(float),
-                          cudaMemcpyHostToDevice, s));
-  CG_CUDA(cudaMemsetAsync(ctx->frame_base.p, 0, sizeof(uint32_t), s));
-  CG_CUDA(cudaMemsetAsync(ctx->ray_count.p, 0, upper * sizeof(uint32_t), s));
-
-  for (size_t f = f0; f < f1; ++f) {
-    const int n = static_cast<int>(offs[f + 1] - offs[f]);
-    const int fi = static_cast<int>(f - f0);
-    if (n == 0) {
-      k_copy_base<<<1, 1, 0, s>>>(ctx->frame_base.as<uint32_t>(), fi);
-      continue;
+  if (merged) {
+    {
+      StageScope sc(ctx, kStagePointKeys, 1);
+      k_point_keys<<<grid_for(total, 256), 256, 0, s>>>(
+          P, ctx->poses.as<float>(), d_offs, static_cast<int>(F), pts, total,
+          ctx->key_a.as<uint64_t>(), ctx->val_a.as<uint32_t>(), L->v.err);
     }
-    const float* pts = d_points + 3 * offs[f];
-    const uint32_t* cols = reinterpret_cast<const uint32_t*>(d_colors) + offs[f];
-    const Xform T = make_xform(h_poses + 7 * f);
-    const unsigned g = grid_for(n, 256);
-    if (cfg->method == CG_METHOD_MERGED) {
-      k_point_keys<<<g, 256, 0, s>>>(P, T, pts, n, ctx->key_a.as<uint64_t>(),
-                                     ctx->val_a.as<uint32_t>(), L->v.err);
-      cub::DoubleBuffer<uint64_t> dk(ctx->key_a.as<uint64_t>(), ctx->key_b.as<uint64_t>());
-      cub::DoubleBuffer<uint32_t> dv(ctx->val_a.as<uint32_t>(), ctx->val_b.as<uint32_t>());
-      CG_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_sort, dk, dv, n, 0, 61, s));
-      k_mark_heads<<<g, 256, 0, s>>>(dk.Current(), n, ctx->flags.as<uint32_t>());
-      CG_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_scan, ctx->flags.as<uint32_t>(),
-                                            ctx->scan.as<uint32_t>(), n, s));
-      k_fold_bundles<<<g, 256, 0, s>>>(P, T, fi, dk.Current(), dv.Current(),
-                                       ctx->flags.as<uint32_t>(), ctx->scan.as<uint32_t>(), n, pts,
-                                       cols, ctx->frame_base.as<uint32_t>(), ctx->rays.as<Ray>(),
-                                       ctx->ray_count.as<uint32_t>());
-    } else {
-      k_simple_flags<<<g, 256, 0, s>>>(P, pts, n, ctx->flags.as<uint32_t>());
-      CG_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_scan, ctx->flags.as<uint32_t>(),
-                                            ctx->scan.as<uint32_t>(), n, s));
-      k_simple_rays<<<g, 256, 0, s>>>(P, T, fi, ctx->flags.as<uint32_t>(), ctx->scan.as<uint32_t>(),
-                                      n, pts, cols, ctx->frame_base.as<uint32_t>(),
-                                      ctx->rays.as<Ray>(), ctx->ray_count.as<uint32_t>());
+    {
+      StageScope sc(ctx, kStageBundleSort, 0);
+      CG_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_sort, dk, dv, total, 0,
+                                              bundle_bits, s));
     }
+    {
+      StageScope sc(ctx, kStageBundleScan, 0);
+      CG_CUDA(cub::DeviceSelect::If(ctx->cub_tmp.p, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
+                                    static_cast<int>(total), BundleHead{dk.Current()}, s));
+    }
+    {
+      StageScope sc(ctx, kStageFold, 1);
+      k_fold_bundles<<<ctx->num_sms * 8, 256, 0, s>>>(
+          P, ctx->poses.as<float>(), dk.Current(), dv.Current(), static_cast<uint32_t>(total),
+          ctx->scan.as<uint32_t>(), d_num, pts, cols, ctx->rays.as<Ray>(),
+          ctx->ray_count.as<uint32_t>());
+    }
+  } else {
+    {
+      StageScope sc(ctx, kStageBundleScan, 0);
+      CG_CUDA(cub::DeviceSelect::If(ctx->cub_tmp.p, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
+                                    static_cast<int>(total), valid, s));
+    }
+    StageScope sc(ctx, kStageFold, 1);
+    k_simple_rays<<<grid_for(total, 256), 256, 0, s>>>(
+        P, ctx->poses.as<float>(), d_offs, static_cast<int>(F), ctx->scan.as<uint32_t>(), d_num, pts,
+        cols, ctx->rays.as<Ray>(), ctx->ray_count.as<uint32_t>());
   }
-  CG_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_scan2, ctx->ray_count.as<uint32_t>(),
-                                        ctx->ray_offset.as<uint32_t>(), upper, s));
-  k_totals<<<1, 1, 0, s>>>(ctx->frame_base.as<uint32_t>(), static_cast<int>(F),
-                           ctx->ray_count.as<uint32_t>(), ctx->ray_offset.as<uint32_t>(), upper,
-                           ctx->d_counters);
+  {
+    StageScope sc(ctx, kStageRayScan, 1);
+    CG_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_scan, ctx->ray_count.as<uint32_t>(),
+                                          ctx->ray_offset.as<uint32_t>(), static_cast<int>(upper),
+                                          s));
+    k_totals<<<1, 1, 0, s>>>(d_num, ctx->ray_count.as<uint32_t>(), ctx->ray_offset.as<uint32_t>(),
+                             upper, ctx->d_counters);
+  }
+  // the staged host buffer (rel) must outlive its async copy: the sync below covers it
   CG_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(CallCounters),
                           cudaMemcpyDeviceToHost, s));
   CG_CUDA(cudaStreamSynchronize(s));
@@ -389,14 +603,14 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   const uint32_t num_rays = static_cast<uint32_t>(ctx->h_counters->rays);
   const size_t num_pairs = ctx->h_counters->pairs;
   const size_t max_pairs = env_size("CG_MAX_PAIRS", size_t(768) << 20);
-  if (num_pairs > max_pairs || num_pairs >= 0xFFFFFFF0ull) {
+  if (num_pairs > max_pairs || num_pairs >= 0x7FFFFFF0ull) {
     if (F > 1) {  // the front half never touches the layer: safe to redo in two halves
       const size_t mid = f0 + F / 2;
       int32_t rc = integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, mid, stats);
       if (rc) return rc;
       return integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, mid, f1, stats);
     }
-    if (num_pairs >= 0xFFFFFFF0ull) {
+    if (num_pairs >= 0x7FFFFFF0ull) {
       set_error("a single frame produces %zu voxel updates; split the point cloud", num_pairs);
       return CG_ERR_INVALID_ARG;
     }
@@ -462,6 +676,7 @@ static int32_t stage_inputs(cg_context* ctx, const float* pts, const uint8_t* co
   CG_CUDA(cudaSetDevice(ctx->device));
   CG_CUDA(ctx->points.reserve(n * 3 * sizeof(float)));
   CG_CUDA(ctx->colors.reserve(n * 4));
+  StageScope sc(ctx, kStageTransfer, 0);
   CG_CUDA(cudaMemcpyAsync(ctx->points.p, pts, n * 3 * sizeof(float), cudaMemcpyHostToDevice,
                           ctx->stream));
   CG_CUDA(cudaMemcpyAsync(ctx->colors.p, cols, n * 4, cudaMemcpyHostToDevice, ctx->stream));

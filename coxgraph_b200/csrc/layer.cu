@@ -23,6 +23,23 @@ int32_t cuda_fail(cudaError_t e, const char* what) {
   return CG_ERR_CUDA;
 }
 
+const char* stage_name(int s) {
+  static const char* names[kNumStages] = {"point_keys",  "bundle_sort", "bundle_scan", "bundle_fold",
+                                          "ray_scan",    "ray_walk",    "pair_sort",   "segments", "voxel_update",
+                                          "merge_mark",  "merge_resample", "transfer"};
+  return (s >= 0 && s < kNumStages) ? names[s] : "?";
+}
+
+static void drain_events(cg_context* ctx) {
+  for (const PendingEvent& pe : ctx->pending) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, pe.start, pe.stop) == cudaSuccess) ctx->stage_ms[pe.stage] += ms;
+    ctx->event_pool.push_back(pe.start);
+    ctx->event_pool.push_back(pe.stop);
+  }
+  ctx->pending.clear();
+}
+
 // ------------------------------------------------------------------ kernels
 __global__ void k_fill_default(float* pool, size_t first_block, size_t num_blocks) {
   // one block plane triple = 3 * 4096 words; words [8192, 12288) are the colour plane
@@ -205,6 +222,8 @@ int32_t cg_context_create(int32_t device, void* stream, cg_context** out) {
   CG_CUDA(cudaMallocHost(&ctx->h_counters, sizeof(CallCounters)));
   CG_CUDA(cudaMalloc(&ctx->d_counters, sizeof(CallCounters)));
   CG_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(CallCounters), ctx->stream));
+  CG_CUDA(cudaMalloc(&ctx->d_select_count, sizeof(uint32_t)));
+  CG_CUDA(cudaMemsetAsync(ctx->d_select_count, 0, sizeof(uint32_t), ctx->stream));
   *out = ctx;
   return CG_OK;
 }
@@ -216,15 +235,51 @@ int32_t cg_context_destroy(cg_context* ctx) {
   DevBuf* bufs[] = {&ctx->points, &ctx->colors, &ctx->poses, &ctx->frame_base, &ctx->key_a,
                     &ctx->key_b, &ctx->val_a, &ctx->val_b, &ctx->flags, &ctx->scan,
                     &ctx->cub_tmp, &ctx->rays, &ctx->ray_count, &ctx->ray_offset, &ctx->pkey_a,
-                    &ctx->pkey_b, &ctx->pval_a, &ctx->pval_b, &ctx->cand_keys, &ctx->cand_list,
+                    &ctx->pkey_b, &ctx->pval_a, &ctx->pval_b, &ctx->seg_start, &ctx->cand_keys, &ctx->cand_list,
                     &ctx->stage_a, &ctx->stage_b, &ctx->stage_c};
   for (DevBuf* b : bufs) b->release();
+  drain_events(ctx);
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->d_select_count) cudaFree(ctx->d_select_count);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return CG_OK;
 }
+
+int32_t cg_context_set_profiling(cg_context* ctx, int32_t enable) {
+  if (!ctx) return CG_ERR_INVALID_ARG;
+  ctx->profiling = enable != 0;
+  return CG_OK;
+}
+
+int32_t cg_context_reset_profile(cg_context* ctx) {
+  if (!ctx) return CG_ERR_INVALID_ARG;
+  CG_CUDA(cudaStreamSynchronize(ctx->stream));
+  drain_events(ctx);
+  for (int i = 0; i < kNumStages; ++i) {
+    ctx->stage_ms[i] = 0.0;
+    ctx->stage_launches[i] = 0;
+  }
+  return CG_OK;
+}
+
+int32_t cg_context_get_profile(cg_context* ctx, cg_stage_profile* out, size_t capacity,
+                               size_t* num_out) {
+  if (!ctx) return CG_ERR_INVALID_ARG;
+  CG_CUDA(cudaStreamSynchronize(ctx->stream));
+  drain_events(ctx);
+  if (num_out) *num_out = kNumStages;
+  for (size_t i = 0; out && i < capacity && i < kNumStages; ++i) {
+    snprintf(out[i].name, sizeof(out[i].name), "%s", stage_name(static_cast<int>(i)));
+    out[i].ms = ctx->stage_ms[i];
+    out[i].launches = ctx->stage_launches[i];
+  }
+  return CG_OK;
+}
+
+uint64_t cg_context_kernel_launches(const cg_context* ctx) { return ctx ? ctx->own_launches : 0; }
 
 int32_t cg_context_synchronize(cg_context* ctx) {
   if (!ctx) return CG_ERR_INVALID_ARG;

@@ -301,12 +301,15 @@ static int32_t enqueue_merge(const cg_layer* A, const float T_B_A[7], cg_layer* 
   while (cap < 32 * nA) cap <<= 1;
   CG_CUDA(ctx->cand_keys.reserve(cap * sizeof(uint64_t)));
   CG_CUDA(ctx->cand_list.reserve(27 * nA * sizeof(uint64_t)));
-  CG_CUDA(cudaMemsetAsync(ctx->cand_keys.p, 0xFF, cap * sizeof(uint64_t), s));
-  k_reset_merge_counters<<<1, 1, 0, s>>>(ctx->d_counters);
   const Xform T = make_xform(T_B_A);
-  k_mark_candidates<<<grid_for(nA, 128), 128, 0, s>>>(
-      A->v, static_cast<int>(nA), T, B->v.block_size, ctx->cand_keys.as<uint64_t>(),
-      static_cast<uint32_t>(cap - 1), ctx->cand_list.as<uint64_t>(), ctx->d_counters, B->v.err);
+  {
+    StageScope sc(ctx, kStageMergeMark, 2);
+    CG_CUDA(cudaMemsetAsync(ctx->cand_keys.p, 0xFF, cap * sizeof(uint64_t), s));
+    k_reset_merge_counters<<<1, 1, 0, s>>>(ctx->d_counters);
+    k_mark_candidates<<<grid_for(nA, 128), 128, 0, s>>>(
+        A->v, static_cast<int>(nA), T, B->v.block_size, ctx->cand_keys.as<uint64_t>(),
+        static_cast<uint32_t>(cap - 1), ctx->cand_list.as<uint64_t>(), ctx->d_counters, B->v.err);
+  }
   // inverse on the host with the same operation order as the device / reference
   Xform Ti;
   {
@@ -331,8 +334,12 @@ static int32_t enqueue_merge(const cg_layer* A, const float T_B_A[7], cg_layer* 
                                  static_cast<int>(smem)));
     attr_set = true;
   }
-  k_resample_merge<<<grid, kMergeThreads, smem, s>>>(A->v, B->v, Ti, ctx->cand_list.as<uint64_t>(),
-                                                  ctx->d_counters);
+  {
+    StageScope sc(ctx, kStageMergeResample, 1);
+    k_resample_merge<<<grid, kMergeThreads, smem, s>>>(A->v, B->v, Ti,
+                                                       ctx->cand_list.as<uint64_t>(),
+                                                       ctx->d_counters);
+  }
   CG_CUDA(cudaGetLastError());
   return CG_OK;
 }

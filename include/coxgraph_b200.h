@@ -104,6 +104,21 @@ int32_t cg_context_create(int32_t device, void* stream, cg_context** out);
 int32_t cg_context_destroy(cg_context* ctx);
 int32_t cg_context_synchronize(cg_context* ctx);
 
+/* Named stage timers (CUDA events on the context's stream) and launch counters — the
+ * counterpart of the voxblox::timing::Timer scopes the reference wraps around this path
+ * (coxgraph/include/coxgraph/map_comm/tsdf_recover.h:63,74-76,93). */
+typedef struct cg_stage_profile {
+  char name[32];
+  double ms;         /* accumulated device time of the stage while profiling was enabled */
+  uint64_t launches; /* kernels of this library launched in the stage (always counted) */
+} cg_stage_profile;
+int32_t cg_context_set_profiling(cg_context* ctx, int32_t enable);
+int32_t cg_context_get_profile(cg_context* ctx, cg_stage_profile* out, size_t capacity,
+                               size_t* num_out);
+int32_t cg_context_reset_profile(cg_context* ctx);
+/* Total number of this library's own kernels launched so far on the context. */
+uint64_t cg_context_kernel_launches(const cg_context* ctx);
+
 /* --- layer: replaces voxblox::Layer<TsdfVoxel> (block hash map keyed by BlockIndex) --- */
 /* voxels_per_side must be 16 (the reference never overrides tsdf_voxels_per_side). */
 int32_t cg_layer_create(cg_context* ctx, float voxel_size, int32_t voxels_per_side,
