@@ -200,6 +200,9 @@ def run_ours(args, rank, world, local_rank):
     # ---- untimed accounting pass: per-frame B_touched (the byte model's definition) and the
     # merge block counts, for every pool submap
     for e in pool:
+        if args.profile_mode:
+            e.update(bytes_integrate=0, blocks_in=0, bytes_merge=0, voxels_in=0, rays=0, pairs=0)
+            continue
         submap.clear()
         touched = 0
         for f in range(FRAMES_PER_SUBMAP):
@@ -207,6 +210,9 @@ def run_ours(args, rank, world, local_rank):
             st = integ.integratePointCloud(e["poses"][f], e["d_pts"][a:b], e["d_cols"][a:b])
             touched += st.blocks_touched
         e["bytes_integrate"] = 16 * e["n"] + 2 * BLOCK_BYTES * touched
+        submap.clear()
+        st = integ.integrateBatch(e["poses"], e["d_pts"], e["d_cols"], e["offs"])
+        e["rays"], e["pairs"] = int(st.rays), int(st.voxel_updates)
         e["blocks_in"] = submap.num_blocks
         glob.clear()
         ms = mergeLayerAintoLayerB(submap, e["T_M_S"], glob)
@@ -299,7 +305,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle, all host threads, bounded
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile_mode:
         from oracle import oracle_py as orc
         threads = os.cpu_count() or 1
         ocfg = orc.default_config(**CFG)
@@ -325,6 +331,7 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         dv, ee = results["device"], results["e2e"]
+        used_dev = [pool[(args.warmup + k) % pool_n] for k in range(args.steps)]
         peak, peak_src = measured_peak_gbs()
         prof = dv["profile"]
         per_frame = ("point_keys", "bundle_sort", "bundle_scan", "bundle_fold")
@@ -368,6 +375,9 @@ def run_ours(args, rank, world, local_rank):
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "ms_per_launch": top_ms_per_launch},
             "stages_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "per_step": {"rays": sum(e["rays"] for e in used_dev) / args.steps,
+                         "voxel_updates": sum(e["pairs"] for e in used_dev) / args.steps,
+                         "blocks_in": sum(e["blocks_in"] for e in used_dev) / args.steps},
             "clocks": dv["clocks"], "clocks_e2e": ee["clocks"],
             "cpu_baseline": cpu,
         }
@@ -390,6 +400,8 @@ def main():
                     help="frames per step the reference arm fuses (bounded sample)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="skip the accounting pass and the CPU baseline (for runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

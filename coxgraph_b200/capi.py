@@ -96,6 +96,7 @@ SYMBOLS = {
     "cg_block_owner": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "cg_layer_pack_by_owner": (C.c_int32, [_P, C.c_int32, _P, C.c_size_t, _P]),
     "cg_layer_merge_packed": (C.c_int32, [_P, _P, C.c_size_t]),
+    "cg_debug_selftest": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

@@ -199,9 +199,11 @@ struct cg_context {
   // integration scratch
   cg::DevBuf points, colors, poses, frame_base;
   cg::DevBuf key_a, key_b, val_a, val_b, flags, scan, cub_tmp;
-  cg::DevBuf rays, ray_count, ray_offset;
-  cg::DevBuf pkey_a, pkey_b, pval_a, pval_b, seg_start;
+  cg::DevBuf rays, ray_count, ray_offset, sorted_pts;
+  cg::DevBuf pkey_a, pkey_b, pval_a, pval_b, seg_start, long_list, long_partials;
+  unsigned long long* d_long_counter = nullptr;  // (#long segments << 32) | #sub-blocks
   uint32_t* d_select_count = nullptr;  // output count of the stream compactions
+  uint32_t* d_work_counter = nullptr;  // dynamic work distribution of the persistent kernels
   // merge / transfer scratch
   cg::DevBuf cand_keys, cand_list, stage_a, stage_b, stage_c;
   // instrumentation

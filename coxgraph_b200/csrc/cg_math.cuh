@@ -97,6 +97,55 @@ __device__ __forceinline__ uint32_t blend_colors(uint32_t c1, float w1, uint32_t
   return pack_rgba(round_u8(r), round_u8(g), round_u8(b), round_u8(a));
 }
 
+// --- helpers of the sequential bundle fold (MergedTsdfIntegrator::integrateVoxel): the same
+// IEEE results as the plain expressions, with a shorter dependent chain.
+// num / den with r = RN(1 / den) given: two FMA correction steps give the correctly rounded
+// quotient (Markstein's theorem; verified exhaustively-by-sampling in tests/test_gpu_math.py).
+__device__ __forceinline__ float div_with_rcp(float num, float den, float r) {
+  float q = num * r;
+  float e = __fmaf_rn(-den, q, num);
+  q = __fmaf_rn(e, r, q);
+  e = __fmaf_rn(-den, q, num);
+  q = __fmaf_rn(e, r, q);
+  return q;
+}
+// roundf() (half away from zero) for 0 <= v < 2^23, result kept as float
+__device__ __forceinline__ float round_half_away_pos(float v) {
+  const float t = truncf(v);
+  return (v - t >= 0.5f) ? t + 1.0f : t;
+}
+struct FoldState {
+  V3 m;                   // merged_point_C
+  float W;                // merged_weight
+  float cr, cg, cb, ca;   // merged_color, one integer-valued float per channel
+};
+__device__ __forceinline__ void fold_reset(FoldState& s) {
+  s.m = V3{0.0f, 0.0f, 0.0f};
+  s.W = 0.0f;
+  s.cr = s.cg = s.cb = 0.0f;
+  s.ca = 255.0f;
+}
+__device__ __forceinline__ uint32_t fold_color(const FoldState& s) {
+  return pack_rgba(static_cast<uint32_t>(s.cr), static_cast<uint32_t>(s.cg),
+                   static_cast<uint32_t>(s.cb), static_cast<uint32_t>(s.ca));
+}
+// one point: merged = (merged * W + p * w) / (W + w); colour = blendTwoColors(colour, W, c, w)
+__device__ __forceinline__ void fold_step(FoldState& s, float px, float py, float pz, uint32_t col,
+                                          float w) {
+  const float Wn = s.W + w;
+  const float r = 1.0f / Wn;
+  const float a = s.W / Wn;  // blendTwoColors: first_weight /= total
+  const float b = w / Wn;    //                 second_weight /= total
+  s.m.x = div_with_rcp(s.m.x * s.W + px * w, Wn, r);
+  s.m.y = div_with_rcp(s.m.y * s.W + py * w, Wn, r);
+  s.m.z = div_with_rcp(s.m.z * s.W + pz * w, Wn, r);
+  s.cr = round_half_away_pos(s.cr * a + static_cast<float>(col & 255u) * b);
+  s.cg = round_half_away_pos(s.cg * a + static_cast<float>((col >> 8) & 255u) * b);
+  s.cb = round_half_away_pos(s.cb * a + static_cast<float>((col >> 16) & 255u) * b);
+  s.ca = round_half_away_pos(s.ca * a + static_cast<float>(col >> 24) * b);
+  s.W = Wn;
+}
+
 // --- R3: voxblox::RayCaster (integrator_utils.cc), indices as int32 (range checked by caller)
 struct RayCaster {
   int cx, cy, cz;

@@ -123,77 +123,193 @@ struct BundleHead {
   }
 };
 
-// One warp per bundle: MergedTsdfIntegrator::integrateVoxel, first half.  Loads are cooperative,
-// the arithmetic is the reference's sequential recurrence (all lanes compute it redundantly).
-__global__ void __launch_bounds__(256)
-k_fold_bundles(IntegratorParams P, const float* __restrict__ poses,
-               const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-               uint32_t total, const uint32_t* __restrict__ heads,
-               const uint32_t* __restrict__ num_heads, const float* __restrict__ pts,
-               const uint32_t* __restrict__ cols, Ray* __restrict__ rays,
-               uint32_t* __restrict__ ray_count) {
+// Gather the sorted points next to each other: (x, y, z, rgba) per sorted slot, so that the
+// sequential fold streams contiguous memory.
+__global__ void k_gather_sorted(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                uint32_t total, const float* __restrict__ pts,
+                                const uint32_t* __restrict__ cols, float4* __restrict__ out) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= total) return;
+  if (keys[j] == kInvalidPointKey) return;
+  const uint32_t i = vals[j];
+  out[j] = make_float4(pts[3 * size_t(i)], pts[3 * size_t(i) + 1], pts[3 * size_t(i) + 2],
+                       __uint_as_float(cols[i]));
+}
+
+// MergedTsdfIntegrator::integrateVoxel, first half: the reference's *sequential* weighted mean and
+// colour blend over the points of a bundle (bit-exact: the merged point decides which voxels and
+// blocks the ray visits).
+//  * bundles shorter than kLongBundle: persistent lanes — every lane folds its own bundle and
+//    fetches the next one from a global counter, a warp advances 32 independent recurrences;
+//  * longer bundles: one warp per bundle — coalesced loads, the next 32 points in flight while the
+//    current 32 are folded (all lanes run the same recurrence from shuffled operands).
+constexpr int kFoldUnroll = 4;
+constexpr uint32_t kLongBundle = 192;
+
+__device__ __forceinline__ void store_folded(Ray* __restrict__ folded, uint32_t b,
+                                             const FoldState& st, uint32_t frame_clr) {
+  Ray r;
+  r.px = st.m.x;  // camera frame; k_bundle_rays moves it to the global frame
+  r.py = st.m.y;
+  r.pz = st.m.z;
+  r.weight = st.W;
+  r.color = fold_color(st);
+  r.frame_clr = frame_clr;
+  folded[b] = r;
+}
+
+__global__ void __launch_bounds__(128)
+k_fold_bundles(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t total,
+               const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
+               const float4* __restrict__ sorted, uint32_t* work_counter, Ray* __restrict__ folded) {
+  const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t nb = *num_heads;
-  for (uint32_t b = warp; b < nb; b += num_warps) {
-    const uint32_t start = heads[b];
-    const uint32_t end = (b + 1 < nb) ? heads[b + 1] : total;
-    const uint64_t key = keys[start];
-    if (key == kInvalidPointKey) {  // sentinel bundle of dropped points
-      if (lane == 0) {
-        rays[b].frame_clr = kNoRay;
-        ray_count[b] = 0;
-      }
-      continue;
-    }
-    const uint32_t frame = static_cast<uint32_t>(key >> kBundleFrameShift);
-    const bool clearing = (key >> kBundleClearBit) & 1;
-    uint32_t merged_color = kDefaultColor;
-    V3 merged = V3{0.0f, 0.0f, 0.0f};
-    float merged_weight = 0.0f;
-    bool done = false;
-    for (uint32_t c0 = start; c0 < end && !done; c0 += 32) {
-      const uint32_t j = c0 + lane;
-      V3 pc = V3{0.0f, 0.0f, 0.0f};
-      uint32_t col = 0;
-      if (j < end) {
-        const uint32_t i = vals[j];
-        pc = load_point(pts, i);
-        col = cols[i];
-      }
-      const int cnt = static_cast<int>(min(32u, end - c0));
-      for (int t = 0; t < cnt; ++t) {
-        const V3 q = V3{__shfl_sync(0xFFFFFFFFu, pc.x, t), __shfl_sync(0xFFFFFFFFu, pc.y, t),
-                        __shfl_sync(0xFFFFFFFFu, pc.z, t)};
-        const uint32_t qc = __shfl_sync(0xFFFFFFFFu, col, t);
-        const float w = voxel_weight(P, q.z);
-        if (w < kEps) continue;
-        merged = (merged * merged_weight + q * w) / (merged_weight + w);
-        merged_color = blend_colors(merged_color, merged_weight, qc, w);
-        merged_weight += w;
-        if (clearing) {  // only the first point of a clearing bundle is used
-          done = true;
-          break;
+  uint32_t cur = 0, end = 0, my_b = 0, frame_clr = 0;
+  bool finished = false, clearing = false;
+  FoldState st;
+  fold_reset(st);
+  for (;;) {
+    const bool need = !finished && cur >= end;
+    const unsigned m = __ballot_sync(full, need);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(work_counter, static_cast<uint32_t>(__popc(m)));
+      base = __shfl_sync(full, base, leader);
+      if (need) {
+        const uint32_t b = base + __popc(m & ((1u << lane) - 1u));
+        if (b < nb) {
+          const uint32_t start = heads[b];
+          const uint32_t stop = (b + 1 < nb) ? heads[b + 1] : total;
+          const uint64_t key = keys[start];
+          if (key == kInvalidPointKey) {  // sentinel bundle of dropped points
+            folded[b].frame_clr = kNoRay;
+            cur = end = 0;                // fetch again on the next round
+          } else if (stop - start >= kLongBundle) {
+            cur = end = 0;                // left to k_fold_long
+          } else {
+            cur = start;
+            end = stop;
+            my_b = b;
+            clearing = (key >> kBundleClearBit) & 1;
+            frame_clr = static_cast<uint32_t>(key >> kBundleFrameShift) |
+                        (clearing ? 0x80000000u : 0u);
+            fold_reset(st);
+          }
+        } else {
+          finished = true;
         }
       }
     }
-    if (lane == 0) {
-      const Xform T = make_xform(poses + 7 * frame);
-      const V3 pg = apply(T, merged);
-      RayCaster rc;
-      rc.init(T.t, pg, clearing, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc);
-      Ray ray;
-      ray.px = pg.x;
-      ray.py = pg.y;
-      ray.pz = pg.z;
-      ray.weight = merged_weight;
-      ray.color = merged_color;
-      ray.frame_clr = frame | (clearing ? 0x80000000u : 0u);
-      rays[b] = ray;
-      ray_count[b] = rc.valid ? rc.steps + 1u : 0u;
+    if (__all_sync(full, finished)) break;
+    if (!finished && cur < end) {
+      const int n = static_cast<int>(min(static_cast<uint32_t>(kFoldUnroll), end - cur));
+      float4 q[kFoldUnroll];
+#pragma unroll
+      for (int u = 0; u < kFoldUnroll; ++u)
+        if (u < n) q[u] = sorted[cur + u];
+      bool done = false;
+#pragma unroll
+      for (int u = 0; u < kFoldUnroll; ++u) {
+        if (u < n && !done) {
+          const float w = voxel_weight(P, q[u].z);
+          if (!(w < kEps)) {
+            fold_step(st, q[u].x, q[u].y, q[u].z, __float_as_uint(q[u].w), w);
+            done = clearing;  // only the first point of a clearing bundle is used
+          }
+        }
+      }
+      cur = done ? end : cur + n;
+      if (cur >= end) store_folded(folded, my_b, st, frame_clr);
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_fold_long(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t total,
+            const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
+            const float4* __restrict__ sorted, uint32_t* work_counter, Ray* __restrict__ folded) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nb = *num_heads;
+  constexpr uint32_t kBatch = 64;
+  for (;;) {
+    uint32_t b0 = 0;
+    if (lane == 0) b0 = atomicAdd(work_counter, kBatch);
+    b0 = __shfl_sync(full, b0, 0);
+    if (b0 >= nb) break;
+    // lanes look at two bundles of the batch each, the warp then folds the long ones in turn
+    uint32_t long_mask[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t b = b0 + h * 32 + lane;
+      bool is_long = false;
+      if (b < nb) {
+        const uint32_t start = heads[b];
+        const uint32_t stop = (b + 1 < nb) ? heads[b + 1] : total;
+        is_long = stop - start >= kLongBundle && keys[start] != kInvalidPointKey;
+      }
+      long_mask[h] = __ballot_sync(full, is_long);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t mask = long_mask[h];
+      while (mask) {
+        const uint32_t b = b0 + h * 32 + (__ffs(mask) - 1);
+        mask &= mask - 1;
+        const uint32_t start = heads[b];
+        const uint32_t end = (b + 1 < nb) ? heads[b + 1] : total;
+        const uint64_t key = keys[start];
+        const bool clearing = (key >> kBundleClearBit) & 1;
+        const uint32_t frame_clr =
+            static_cast<uint32_t>(key >> kBundleFrameShift) | (clearing ? 0x80000000u : 0u);
+        FoldState st;
+        fold_reset(st);
+        bool done = false;
+        float4 nxt = (start + lane < end) ? sorted[start + lane] : make_float4(0, 0, 0, 0);
+        for (uint32_t c0 = start; c0 < end && !done; c0 += 32) {
+          const float4 q = nxt;
+          if (c0 + 32 + lane < end) nxt = sorted[c0 + 32 + lane];
+          const int cnt = static_cast<int>(min(32u, end - c0));
+          for (int t = 0; t < cnt; ++t) {
+            const float px = __shfl_sync(full, q.x, t), py = __shfl_sync(full, q.y, t);
+            const float pz = __shfl_sync(full, q.z, t), pw = __shfl_sync(full, q.w, t);
+            const float w = voxel_weight(P, pz);
+            if (w < kEps) continue;
+            fold_step(st, px, py, pz, __float_as_uint(pw), w);
+            if (clearing) {
+              done = true;
+              break;
+            }
+          }
+        }
+        if (lane == 0) store_folded(folded, b, st, frame_clr);
+      }
+    }
+  }
+}
+
+// one thread per bundle: T_G_C * merged point, ray set-up, pair count
+__global__ void k_bundle_rays(IntegratorParams P, const float* __restrict__ poses,
+                              const uint32_t* __restrict__ num_heads, Ray* __restrict__ rays,
+                              uint32_t* __restrict__ ray_count) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= *num_heads) return;
+  Ray ray = rays[b];
+  if (ray.frame_clr == kNoRay) {
+    ray_count[b] = 0;
+    return;
+  }
+  const Xform T = make_xform(poses + 7 * (ray.frame_clr & 0x7FFFFFFFu));
+  const V3 pg = apply(T, V3{ray.px, ray.py, ray.pz});
+  RayCaster rc;
+  rc.init(T.t, pg, (ray.frame_clr >> 31) != 0, P.carving != 0, P.max_ray, P.voxel_size_inv,
+          P.trunc);
+  rays[b].px = pg.x;
+  rays[b].py = pg.y;
+  rays[b].pz = pg.z;
+  ray_count[b] = rc.valid ? rc.steps + 1u : 0u;
 }
 
 // SIMPLE: one ray per valid point, in (frame, visit rank) order
@@ -316,105 +432,278 @@ __device__ __forceinline__ ClampedAffine compose(const ClampedAffine& f, const C
 }
 constexpr float kBig = 1.0e30f;
 
-// One warp per voxel segment (R5 updateTsdfVoxel replayed over the voxel's update list).
+// state-independent part of updateTsdfVoxel for one (ray, voxel) visit
+struct Visit {
+  float sdf, w;
+  uint32_t col;
+};
+__device__ __forceinline__ Visit make_visit(const IntegratorParams& P, const float* __restrict__ poses,
+                                            const Ray& ray, V3 center) {
+  const float* T = poses + 7 * (ray.frame_clr & 0x7FFFFFFFu);
+  const V3 origin = V3{T[4], T[5], T[6]};
+  const V3 pg = V3{ray.px, ray.py, ray.pz};
+  // computeDistance + weight drop-off / sparsity compensation
+  const V3 v_voxel_origin = center - origin;
+  const V3 v_point_origin = pg - origin;
+  const float dist_G = norm3(v_point_origin);
+  const float dist_G_V = dot3(v_voxel_origin, v_point_origin) / dist_G;
+  Visit v;
+  v.sdf = dist_G - dist_G_V;
+  v.w = ray.weight;
+  if (P.weight_dropoff && v.sdf < -P.voxel_size) {
+    v.w = v.w * (P.trunc + v.sdf) / (P.trunc - P.voxel_size);
+    v.w = fmaxf(v.w, 0.0f);
+  }
+  if (P.use_sparsity && fabsf(v.sdf) < P.trunc) v.w *= P.sparsity_factor;
+  v.col = ray.color;
+  return v;
+}
+
+// voxel addressed by a pair key
+struct VoxelRef {
+  int slot;
+  uint32_t entry;
+  V3 center;
+  float* dp;
+  float* wp;
+  uint32_t* cp;
+};
+template <class K>
+__device__ __forceinline__ VoxelRef voxel_ref(const IntegratorParams& P, const LayerView& L, K key) {
+  VoxelRef r;
+  r.entry = static_cast<uint32_t>(key >> 12);
+  const int lin = static_cast<int>(key & 4095);
+  r.slot = L.hash_vals[r.entry];
+  int bx, by, bz;
+  unpack_block_key(L.hash_keys[r.entry], bx, by, bz);
+  r.center = V3{center_coord(bx * 16 + (lin & 15), P.voxel_size),
+                center_coord(by * 16 + ((lin >> 4) & 15), P.voxel_size),
+                center_coord(bz * 16 + (lin >> 8), P.voxel_size)};
+  const int s = r.slot < 0 ? 0 : r.slot;
+  r.dp = L.dist_plane(s) + lin;
+  r.wp = L.weight_plane(s) + lin;
+  r.cp = L.color_plane(s) + lin;
+  return r;
+}
+
+// Replays updates [start, end) of one voxel on (D, W, C), 32 at a time: weights by prefix sum,
+// the clamped weighted average as an ordered tree reduction of clamped affine maps, colours
+// sequentially for the updates inside the truncation band.  The ray records of chunk c+1 and the
+// ray ids of chunk c+2 are in flight while chunk c is reduced.
+__device__ __forceinline__ void replay_segment(const IntegratorParams& P,
+                                               const float* __restrict__ poses,
+                                               const Ray* __restrict__ rays,
+                                               const uint32_t* __restrict__ pvals, uint32_t start,
+                                               uint32_t end, V3 center, int lane, float& D, float& W,
+                                               uint32_t& C) {
+  const unsigned full = 0xFFFFFFFFu;
+  uint32_t id_next = (start + lane < end) ? pvals[start + lane] : 0u;
+  Ray ray_next = rays[id_next];
+  id_next = (start + 32 + lane < end) ? pvals[start + 32 + lane] : 0u;
+  for (uint32_t c0 = start; c0 < end; c0 += 32) {
+    const Ray ray = ray_next;
+    if (c0 + 32 < end) {
+      ray_next = rays[id_next];
+      id_next = (c0 + 64 + lane < end) ? pvals[c0 + 64 + lane] : 0u;
+    }
+    const bool act = c0 + lane < end;
+    Visit v = make_visit(P, poses, ray, center);
+    if (!act) v.w = 0.0f;
+    const float sdf = v.sdf, w = v.w;
+    // weights: W_k = min(max_weight, W_{k-1} + w_k)  ==  min(max_weight, W_0 + sum w)
+    float pre = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float o = __shfl_up_sync(full, pre, d);
+      if (lane >= d) pre += o;
+    }
+    const float w_prev = fminf(P.max_weight, W + (pre - w));
+    const float w_new = w_prev + w;
+    const bool skip = !act || w_new < kEps;  // "new_weight < kFloatEpsilon -> return"
+    const float inv = __fdividef(1.0f, w_new);
+    ClampedAffine f;
+    f.a = skip ? 1.0f : w_prev * inv;
+    f.b = skip ? 0.0f : (sdf * w) * inv;
+    f.lo = skip ? -kBig : -P.trunc;
+    f.hi = skip ? kBig : P.trunc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {  // ordered tree reduction into lane 0
+      ClampedAffine g;
+      g.a = __shfl_down_sync(full, f.a, d);
+      g.b = __shfl_down_sync(full, f.b, d);
+      g.lo = __shfl_down_sync(full, f.lo, d);
+      g.hi = __shfl_down_sync(full, f.hi, d);
+      if ((lane & (2 * d - 1)) == 0) f = compose(f, g);
+    }
+    const float fa = __shfl_sync(full, f.a, 0), fb = __shfl_sync(full, f.b, 0);
+    const float flo = __shfl_sync(full, f.lo, 0), fhi = __shfl_sync(full, f.hi, 0);
+    D = fminf(fmaxf(fa * D + fb, flo), fhi);
+    unsigned band = __ballot_sync(full, !skip && fabsf(sdf) < P.trunc);
+    while (band) {
+      const int t = __ffs(band) - 1;
+      band &= band - 1;
+      C = blend_colors(C, __shfl_sync(full, w_prev, t), __shfl_sync(full, v.col, t),
+                       __shfl_sync(full, w, t));
+    }
+    const float w_after = skip ? w_prev : fminf(P.max_weight, w_new);
+    W = __shfl_sync(full, w_after, 31);
+  }
+}
+
+// Long segments (>= kLongSegment updates: the voxels next to the sensor, crossed by every ray)
+// are split into sub-blocks that many warps reduce in parallel, see k_long_partials.
+constexpr uint32_t kLongSegment = 2048;
+constexpr uint32_t kLongSub = 1024;
+struct LongSeg {
+  uint32_t start, end;    // pair range
+  uint32_t item_base;     // first sub-block index
+  uint32_t pad;
+};
+struct LongPartial {
+  float sum_w;            // sum of the effective weights of the sub-block
+  uint32_t not_free;      // any update with sdf < trunc (not a pure free-space observation)
+};
+
+// One warp per voxel segment (R5 updateTsdfVoxel replayed over the voxel's update list);
+// segments are handed out dynamically, kSegBatch at a time.
+constexpr uint32_t kSegBatch = 8;
 template <class K>
 __global__ void __launch_bounds__(256)
 k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
                const K* __restrict__ pkeys, const uint32_t* __restrict__ pvals, uint32_t num_pairs,
                const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ num_segs,
-               LayerView L, CallCounters* counters) {
+               uint32_t* work_counter, unsigned long long* long_counter, LongSeg* long_list,
+               uint32_t long_cap, LayerView L, CallCounters* counters) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t ns = *num_segs;
+  for (;;) {
+    uint32_t s0 = 0;
+    if (lane == 0) s0 = atomicAdd(work_counter, kSegBatch);
+    s0 = __shfl_sync(full, s0, 0);
+    if (s0 >= ns) break;
+    const uint32_t s1 = min(ns, s0 + kSegBatch);
+    for (uint32_t s = s0; s < s1; ++s) {
+      const uint32_t start = seg_start[s];
+      const uint32_t end = (s + 1 < ns) ? seg_start[s + 1] : num_pairs;
+      const K key = pkeys[start];
+      const VoxelRef vr = voxel_ref(P, L, key);
+      if (vr.slot < 0) continue;  // pool exhausted; error already flagged
+      if (lane == 0 && (start == 0 || static_cast<uint32_t>(pkeys[start - 1] >> 12) != vr.entry)) {
+        atomicAdd(&counters->touched, 1ull);
+        L.updated[vr.slot] = 1;
+      }
+      if (end - start >= kLongSegment) {
+        if (lane == 0) {
+          const uint32_t nsub = (end - start + kLongSub - 1) / kLongSub;
+          // one 64-bit atomic hands out the list index (high word) and the sub-block range (low)
+          const unsigned long long old =
+              atomicAdd(long_counter, (1ull << 32) | static_cast<unsigned long long>(nsub));
+          const uint32_t idx = static_cast<uint32_t>(old >> 32);
+          if (idx < long_cap) long_list[idx] = LongSeg{start, end, static_cast<uint32_t>(old), 0u};
+        }
+        continue;
+      }
+      float D = *vr.dp, W = *vr.wp;
+      uint32_t C = *vr.cp;
+      replay_segment(P, poses, rays, pvals, start, end, vr.center, lane, D, W, C);
+      if (lane == 0) {
+        *vr.dp = D;
+        *vr.wp = W;
+        *vr.cp = C;
+      }
+    }
+  }
+}
+
+// sub-block t of the long segments: sum of weights + "all free space" flag (one warp each)
+template <class K>
+__global__ void __launch_bounds__(256)
+k_long_partials(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
+                const K* __restrict__ pkeys, const uint32_t* __restrict__ pvals,
+                const unsigned long long* __restrict__ long_counter,
+                const LongSeg* __restrict__ long_list, uint32_t long_cap, LayerView L,
+                LongPartial* __restrict__ partials) {
+  const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t ns = *num_segs;
-  for (uint32_t s = warp; s < ns; s += num_warps) {
-    const uint32_t start = seg_start[s];
-    const uint32_t end = (s + 1 < ns) ? seg_start[s + 1] : num_pairs;
-    const K key = pkeys[start];
-    const uint32_t entry = static_cast<uint32_t>(key >> 12);
-    const int lin = static_cast<int>(key & 4095);
-    const int slot = L.hash_vals[entry];
-    if (slot < 0) continue;  // pool exhausted; error already flagged
-    if (lane == 0 && (start == 0 || static_cast<uint32_t>(pkeys[start - 1] >> 12) != entry)) {
-      atomicAdd(&counters->touched, 1ull);
-      L.updated[slot] = 1;
+  const unsigned long long cnt = *long_counter;
+  const uint32_t nlong = min(static_cast<uint32_t>(cnt >> 32), long_cap);
+  const uint32_t nitems = static_cast<uint32_t>(cnt);
+  for (uint32_t t = warp; t < nitems; t += num_warps) {
+    // long_list is ordered by item_base (both come from the same atomic): binary search
+    uint32_t lo = 0, hi = nlong;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (long_list[mid].item_base <= t) lo = mid; else hi = mid;
     }
-    int bx, by, bz;
-    unpack_block_key(L.hash_keys[entry], bx, by, bz);
-    const V3 center = V3{center_coord(bx * 16 + (lin & 15), P.voxel_size),
-                         center_coord(by * 16 + ((lin >> 4) & 15), P.voxel_size),
-                         center_coord(bz * 16 + (lin >> 8), P.voxel_size)};
-    float* dp = L.dist_plane(slot) + lin;
-    float* wp = L.weight_plane(slot) + lin;
-    uint32_t* cp = L.color_plane(slot) + lin;
-    float D = *dp, W = *wp;
-    uint32_t C = *cp;
-    for (uint32_t c0 = start; c0 < end; c0 += 32) {
+    const LongSeg seg = long_list[lo];
+    if (t < seg.item_base) continue;  // list overflowed: handled by the slow path elsewhere
+    const uint32_t a = seg.start + (t - seg.item_base) * kLongSub;
+    const uint32_t b = min(seg.end, a + kLongSub);
+    const VoxelRef vr = voxel_ref(P, L, pkeys[seg.start]);
+    float sum = 0.0f;
+    bool not_free = false;
+    for (uint32_t c0 = a; c0 < b; c0 += 32) {
       const uint32_t j = c0 + lane;
-      const bool act = j < end;
-      float sdf = 0.0f, w = 0.0f;
-      uint32_t col = 0;
-      if (act) {
-        const Ray ray = rays[pvals[j]];
-        const float* T = poses + 7 * (ray.frame_clr & 0x7FFFFFFFu);
-        const V3 origin = V3{T[4], T[5], T[6]};
-        const V3 pg = V3{ray.px, ray.py, ray.pz};
-        // computeDistance + weight drop-off / sparsity compensation (state independent)
-        const V3 v_voxel_origin = center - origin;
-        const V3 v_point_origin = pg - origin;
-        const float dist_G = norm3(v_point_origin);
-        const float dist_G_V = dot3(v_voxel_origin, v_point_origin) / dist_G;
-        sdf = dist_G - dist_G_V;
-        w = ray.weight;
-        if (P.weight_dropoff && sdf < -P.voxel_size) {
-          w = w * (P.trunc + sdf) / (P.trunc - P.voxel_size);
-          w = fmaxf(w, 0.0f);
-        }
-        if (P.use_sparsity && fabsf(sdf) < P.trunc) w *= P.sparsity_factor;
-        col = ray.color;
+      float w = 0.0f;
+      if (j < b) {
+        const Visit v = make_visit(P, poses, rays[pvals[j]], vr.center);
+        w = v.w;
+        not_free = not_free || !(v.sdf >= P.trunc);
       }
-      // weights: W_k = min(max_weight, W_{k-1} + w_k)  ==  min(max_weight, W_0 + sum w)
-      float pre = w;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const float o = __shfl_up_sync(0xFFFFFFFFu, pre, d);
-        if (lane >= d) pre += o;
+      for (int d = 16; d >= 1; d >>= 1) w += __shfl_xor_sync(full, w, d);
+      sum += w;
+    }
+    const bool any_not_free = __any_sync(full, not_free);
+    if (lane == 0) partials[t] = LongPartial{sum, any_not_free ? 1u : 0u};
+  }
+}
+
+// one warp per long segment: closed form when every update is a free-space observation of a
+// voxel that is fresh or already at +truncation (then every step of the reference clamps to
+// +truncation again), otherwise the general replay.
+template <class K>
+__global__ void __launch_bounds__(256)
+k_long_finish(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
+              const K* __restrict__ pkeys, const uint32_t* __restrict__ pvals,
+              const unsigned long long* __restrict__ long_counter,
+              const LongSeg* __restrict__ long_list, uint32_t long_cap, LayerView L,
+              const LongPartial* __restrict__ partials) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned long long cnt = *long_counter;
+  const uint32_t nlong = min(static_cast<uint32_t>(cnt >> 32), long_cap);
+  for (uint32_t i = warp; i < nlong; i += num_warps) {
+    const LongSeg seg = long_list[i];
+    const VoxelRef vr = voxel_ref(P, L, pkeys[seg.start]);
+    float D = *vr.dp, W = *vr.wp;
+    uint32_t C = *vr.cp;
+    const uint32_t nsub = (seg.end - seg.start + kLongSub - 1) / kLongSub;
+    float sum = 0.0f;
+    bool not_free = false;
+    for (uint32_t t = 0; t < nsub; ++t) {  // fixed order: deterministic
+      const LongPartial p = partials[seg.item_base + t];
+      sum += p.sum_w;
+      not_free = not_free || p.not_free != 0;
+    }
+    const bool fresh_or_saturated = (W == 0.0f) || (D == P.trunc);
+    if (!not_free && fresh_or_saturated && P.trunc > 0.0f) {
+      const float w_total = W + sum;
+      if (!(w_total < kEps)) {
+        D = P.trunc;
+        W = fminf(P.max_weight, w_total);
       }
-      const float w_prev = fminf(P.max_weight, W + (pre - w));
-      const float w_new = w_prev + w;
-      const bool skip = !act || w_new < kEps;  // "new_weight < kFloatEpsilon -> return"
-      ClampedAffine f;
-      f.a = skip ? 1.0f : w_prev / w_new;
-      f.b = skip ? 0.0f : (sdf * w) / w_new;
-      f.lo = skip ? -kBig : -P.trunc;
-      f.hi = skip ? kBig : P.trunc;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {  // ordered tree reduction into lane 0
-        ClampedAffine g;
-        g.a = __shfl_down_sync(0xFFFFFFFFu, f.a, d);
-        g.b = __shfl_down_sync(0xFFFFFFFFu, f.b, d);
-        g.lo = __shfl_down_sync(0xFFFFFFFFu, f.lo, d);
-        g.hi = __shfl_down_sync(0xFFFFFFFFu, f.hi, d);
-        if ((lane & (2 * d - 1)) == 0) f = compose(f, g);
-      }
-      const float fa = __shfl_sync(0xFFFFFFFFu, f.a, 0), fb = __shfl_sync(0xFFFFFFFFu, f.b, 0);
-      const float flo = __shfl_sync(0xFFFFFFFFu, f.lo, 0), fhi = __shfl_sync(0xFFFFFFFFu, f.hi, 0);
-      D = fminf(fmaxf(fa * D + fb, flo), fhi);
-      // colours: sequential over the updates inside the truncation band (few per chunk)
-      unsigned band = __ballot_sync(0xFFFFFFFFu, !skip && fabsf(sdf) < P.trunc);
-      while (band) {
-        const int t = __ffs(band) - 1;
-        band &= band - 1;
-        C = blend_colors(C, __shfl_sync(0xFFFFFFFFu, w_prev, t), __shfl_sync(0xFFFFFFFFu, col, t),
-                         __shfl_sync(0xFFFFFFFFu, w, t));
-      }
-      const float w_after = skip ? w_prev : fminf(P.max_weight, w_new);
-      W = __shfl_sync(0xFFFFFFFFu, w_after, 31);
+    } else {
+      replay_segment(P, poses, rays, pvals, seg.start, seg.end, vr.center, lane, D, W, C);
     }
     if (lane == 0) {
-      *dp = D;
-      *wp = W;
-      *cp = C;
+      *vr.dp = D;
+      *vr.wp = W;
+      *vr.cp = C;
     }
   }
 }
@@ -479,11 +768,26 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
                                   static_cast<int>(num_pairs), SegmentHead<K>{dk.Current()}, s));
   }
   {
-    StageScope sc(ctx, kStageVoxelUpdate, 1);
+    StageScope sc(ctx, kStageVoxelUpdate, 3);
+    const uint32_t long_cap = static_cast<uint32_t>(num_pairs / kLongSegment + 1);
+    const size_t max_items = num_pairs / kLongSub + long_cap + 1;
+    CG_CUDA(ctx->long_list.reserve(long_cap * sizeof(LongSeg)));
+    CG_CUDA(ctx->long_partials.reserve(max_items * sizeof(LongPartial)));
+    CG_CUDA(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(uint32_t), s));
+    CG_CUDA(cudaMemsetAsync(ctx->d_long_counter, 0, sizeof(unsigned long long), s));
     k_voxel_update<K><<<ctx->num_sms * 8, 256, 0, s>>>(
         P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), dv.Current(),
-        static_cast<uint32_t>(num_pairs), ctx->seg_start.as<uint32_t>(), d_num, L->v,
+        static_cast<uint32_t>(num_pairs), ctx->seg_start.as<uint32_t>(), d_num,
+        ctx->d_work_counter, ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v,
         ctx->d_counters);
+    k_long_partials<K><<<ctx->num_sms * 8, 256, 0, s>>>(
+        P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), dv.Current(),
+        ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v,
+        ctx->long_partials.as<LongPartial>());
+    k_long_finish<K><<<ctx->num_sms, 256, 0, s>>>(
+        P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), dv.Current(),
+        ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v,
+        ctx->long_partials.as<LongPartial>());
   }
   CG_CUDA(cudaGetLastError());
   return CG_OK;
@@ -517,6 +821,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
     CG_CUDA(ctx->key_b.reserve(total * sizeof(uint64_t)));
     CG_CUDA(ctx->val_a.reserve(total * sizeof(uint32_t)));
     CG_CUDA(ctx->val_b.reserve(total * sizeof(uint32_t)));
+    CG_CUDA(ctx->sorted_pts.reserve(total * sizeof(float4)));
   }
   int frame_bits = 0;
   while ((size_t(1) << frame_bits) < F) ++frame_bits;
@@ -570,11 +875,21 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
                                     static_cast<int>(total), BundleHead{dk.Current()}, s));
     }
     {
-      StageScope sc(ctx, kStageFold, 1);
-      k_fold_bundles<<<ctx->num_sms * 8, 256, 0, s>>>(
-          P, ctx->poses.as<float>(), dk.Current(), dv.Current(), static_cast<uint32_t>(total),
-          ctx->scan.as<uint32_t>(), d_num, pts, cols, ctx->rays.as<Ray>(),
-          ctx->ray_count.as<uint32_t>());
+      StageScope sc(ctx, kStageFold, 4);
+      CG_CUDA(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(uint32_t), s));
+      k_gather_sorted<<<grid_for(total, 256), 256, 0, s>>>(
+          dk.Current(), dv.Current(), static_cast<uint32_t>(total), pts, cols,
+          ctx->sorted_pts.as<float4>());
+      k_fold_bundles<<<ctx->num_sms * 16, 128, 0, s>>>(
+          P, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
+          ctx->sorted_pts.as<float4>(), ctx->d_work_counter, ctx->rays.as<Ray>());
+      CG_CUDA(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(uint32_t), s));
+      k_fold_long<<<ctx->num_sms * 8, 256, 0, s>>>(
+          P, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
+          ctx->sorted_pts.as<float4>(), ctx->d_work_counter, ctx->rays.as<Ray>());
+      k_bundle_rays<<<grid_for(upper, 256), 256, 0, s>>>(P, ctx->poses.as<float>(), d_num,
+                                                         ctx->rays.as<Ray>(),
+                                                         ctx->ray_count.as<uint32_t>());
     }
   } else {
     {

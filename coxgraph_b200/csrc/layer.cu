@@ -222,6 +222,8 @@ int32_t cg_context_create(int32_t device, void* stream, cg_context** out) {
   CG_CUDA(cudaMallocHost(&ctx->h_counters, sizeof(CallCounters)));
   CG_CUDA(cudaMalloc(&ctx->d_counters, sizeof(CallCounters)));
   CG_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(CallCounters), ctx->stream));
+  CG_CUDA(cudaMalloc(&ctx->d_work_counter, sizeof(uint32_t)));
+  CG_CUDA(cudaMalloc(&ctx->d_long_counter, sizeof(unsigned long long)));
   CG_CUDA(cudaMalloc(&ctx->d_select_count, sizeof(uint32_t)));
   CG_CUDA(cudaMemsetAsync(ctx->d_select_count, 0, sizeof(uint32_t), ctx->stream));
   *out = ctx;
@@ -234,8 +236,8 @@ int32_t cg_context_destroy(cg_context* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->points, &ctx->colors, &ctx->poses, &ctx->frame_base, &ctx->key_a,
                     &ctx->key_b, &ctx->val_a, &ctx->val_b, &ctx->flags, &ctx->scan,
-                    &ctx->cub_tmp, &ctx->rays, &ctx->ray_count, &ctx->ray_offset, &ctx->pkey_a,
-                    &ctx->pkey_b, &ctx->pval_a, &ctx->pval_b, &ctx->seg_start, &ctx->cand_keys, &ctx->cand_list,
+                    &ctx->cub_tmp, &ctx->rays, &ctx->ray_count, &ctx->ray_offset, &ctx->sorted_pts, &ctx->pkey_a,
+                    &ctx->pkey_b, &ctx->pval_a, &ctx->pval_b, &ctx->seg_start, &ctx->long_list, &ctx->long_partials, &ctx->cand_keys, &ctx->cand_list,
                     &ctx->stage_a, &ctx->stage_b, &ctx->stage_c};
   for (DevBuf* b : bufs) b->release();
   drain_events(ctx);
@@ -243,6 +245,8 @@ int32_t cg_context_destroy(cg_context* ctx) {
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_select_count) cudaFree(ctx->d_select_count);
+  if (ctx->d_work_counter) cudaFree(ctx->d_work_counter);
+  if (ctx->d_long_counter) cudaFree(ctx->d_long_counter);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return CG_OK;

@@ -19,12 +19,14 @@ CAM_640x480 = dict(width=640, height=480, fx=611.16, fy=609.64, cx=323.45, cy=24
 CAM_1280x720 = dict(width=1280, height=720, fx=920.0, fy=920.0, cx=640.0, cy=360.0)
 
 ROOM = (12.0, 8.0, 3.0)
+# Objects stand along the two long walls and on the centre line, leaving two clear corridors
+# (y = 2.8 and y = 5.2) for the robots: every camera keeps >= 0.9 m from every surface.
 # (cx, cy, cz, r)
-SPHERES = [(3.0, 2.0, 0.8, 0.8), (6.5, 5.5, 0.5, 0.5), (9.0, 2.5, 1.2, 0.6),
-           (4.5, 6.5, 0.3, 0.3), (10.0, 6.0, 0.7, 0.7), (7.5, 1.5, 1.8, 0.4)]
+SPHERES = [(3.0, 1.0, 0.8, 0.8), (6.5, 0.9, 0.5, 0.5), (9.0, 1.1, 1.2, 0.6),
+           (4.5, 7.0, 0.6, 0.6), (10.0, 6.9, 0.7, 0.7), (7.5, 7.2, 1.8, 0.4)]
 # (xmin, ymin, zmin, xmax, ymax, zmax)
-BOXES = [(1.0, 5.0, 0.0, 2.0, 7.0, 1.5), (5.0, 3.0, 0.0, 6.0, 4.0, 0.9),
-         (8.0, 4.0, 0.0, 8.6, 7.5, 2.2), (10.5, 0.5, 0.0, 11.5, 1.5, 1.0)]
+BOXES = [(1.0, 6.2, 0.0, 2.0, 7.6, 1.5), (5.0, 3.6, 0.0, 6.0, 4.4, 0.9),
+         (8.0, 6.3, 0.0, 8.6, 7.7, 2.2), (10.5, 0.4, 0.0, 11.5, 1.4, 1.0)]
 
 
 def quat_from_matrix(R):
@@ -87,20 +89,24 @@ def invert(T):
 
 
 def trajectory(num_frames, robot=0, submap=0, frames_per_submap=None):
-    """Smooth arc inside the room: 3 cm steps, slowly turning, never axis-aligned."""
+    """Smooth drive along one of the two corridors: ~1.5 cm per frame, the camera sweeping
+    left-right across the wall and the objects in front of it (never axis-aligned)."""
     if frames_per_submap is None:
         frames_per_submap = num_frames
     poses = []
+    lane = robot // 2
     for f in range(num_frames):
         k = submap * frames_per_submap + f
+        u = (k % 500) / 500.0
         s = 0.03 * k
-        if robot % 2 == 0:
-            pos = (2.2 + 0.55 * s, 3.6 + 0.9 * math.sin(0.35 * s), 1.35 + 0.1 * math.sin(0.8 * s))
-            yaw = 0.23 + 0.11 * s + 0.5 * (robot // 2)
-        else:
-            pos = (9.7 - 0.5 * s, 4.3 + 0.8 * math.cos(0.3 * s), 1.25 + 0.12 * math.cos(0.7 * s))
-            yaw = 2.9 - 0.13 * s + 0.5 * (robot // 2)
-        pos = (min(max(pos[0], 0.6), ROOM[0] - 0.6), min(max(pos[1], 0.6), ROOM[1] - 0.6), pos[2])
+        if robot % 2 == 0:   # corridor A, driving +x, looking towards the y = 0 wall
+            pos = (2.0 + 7.5 * u + 0.13 * lane, 2.8 + 0.15 * math.sin(0.35 * s + lane),
+                   1.35 + 0.1 * math.sin(0.8 * s) - 0.07 * lane)
+            yaw = -math.pi / 2 + 0.62 + 0.6 * math.sin(0.21 * s + 0.9 * lane)
+        else:                # corridor B, driving -x, looking towards the y = 8 wall
+            pos = (10.0 - 7.5 * u - 0.13 * lane, 5.2 + 0.15 * math.cos(0.3 * s + lane),
+                   1.25 + 0.12 * math.cos(0.7 * s) + 0.07 * lane)
+            yaw = math.pi / 2 - 0.58 + 0.6 * math.sin(0.17 * s + 0.7 * lane + 0.4)
         pitch = 0.07 * math.sin(0.5 * s + robot)
         roll = 0.03 * math.cos(0.4 * s)
         poses.append(camera_pose(pos, yaw, pitch, roll))
@@ -151,12 +157,13 @@ def render_frame(T_G_C, cam=CAM_640x480, device="cpu", near_box=False, stride=1)
         t_hit = torch.where((disc > 0) & (t0 > 1e-6), t0, inf)
         t_best = torch.minimum(t_best, t_hit)
     boxes = list(BOXES)
-    if near_box:  # a thin plate 8 cm in front of the camera: exercises the min_ray rejection
+    if near_box:  # a small object 5 cm in front of the lens: every point on it is closer than
+        # min_ray_length_m and must be rejected (about a third of the frame)
         fwd = R[:, 2].cpu().numpy()
         oc_ = o.cpu().numpy()
-        ctr = oc_ + 0.08 * fwd
-        boxes.append((ctr[0] - 0.02, ctr[1] - 0.02, ctr[2] - 0.02,
-                      ctr[0] + 0.02, ctr[1] + 0.02, ctr[2] + 0.02))
+        ctr = oc_ + 0.05 * fwd
+        boxes.append((ctr[0] - 0.012, ctr[1] - 0.012, ctr[2] - 0.012,
+                      ctr[0] + 0.012, ctr[1] + 0.012, ctr[2] + 0.012))
     for (x0, y0, z0, x1, y1, z1) in boxes:
         lo = torch.tensor([x0, y0, z0], device=dev, dtype=torch.float64)
         hi = torch.tensor([x1, y1, z1], device=dev, dtype=torch.float64)

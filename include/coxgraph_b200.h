@@ -196,6 +196,10 @@ int32_t cg_layer_pack_by_owner(const cg_layer* layer, int32_t nranks, void* d_pa
 /* Fold `num_blocks` packed records (device memory) into `layer` in record order. */
 int32_t cg_layer_merge_packed(cg_layer* layer, const void* d_packed, size_t num_blocks);
 
+/* --- self checks of device arithmetic shortcuts (which: 0 = exact division through a
+ * precomputed reciprocal, 1 = round-half-away); *mismatches must come back 0. */
+int32_t cg_debug_selftest(cg_context* ctx, int32_t which, uint64_t samples, uint64_t* mismatches);
+
 #ifdef __cplusplus
 }
 #endif
