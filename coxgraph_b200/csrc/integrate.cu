@@ -138,25 +138,11 @@ __global__ void k_gather_sorted(const uint64_t* __restrict__ keys, const uint32_
 
 // MergedTsdfIntegrator::integrateVoxel, first half: the reference's *sequential* weighted mean and
 // colour blend over the points of a bundle (bit-exact: the merged point decides which voxels and
-// blocks the ray visits).
-//  * bundles shorter than kLongBundle: persistent lanes — every lane folds its own bundle and
-//    fetches the next one from a global counter, a warp advances 32 independent recurrences;
-//  * longer bundles: one warp per bundle — coalesced loads, the next 32 points in flight while the
-//    current 32 are folded (all lanes run the same recurrence from shuffled operands).
-constexpr int kFoldUnroll = 4;
-constexpr uint32_t kLongBundle = 192;
-
-__device__ __forceinline__ void store_folded(Ray* __restrict__ folded, uint32_t b,
-                                             const FoldState& st, uint32_t frame_clr) {
-  Ray r;
-  r.px = st.m.x;  // camera frame; k_bundle_rays moves it to the global frame
-  r.py = st.m.y;
-  r.pz = st.m.z;
-  r.weight = st.W;
-  r.color = fold_color(st);
-  r.frame_clr = frame_clr;
-  folded[b] = r;
-}
+// blocks the ray visits).  Persistent groups of 4 lanes: a group owns one bundle at a time
+// (fetched from a global counter), loads 32 points with 8 coalesced 64-byte reads, then runs the
+// recurrence over them from shuffled operands; a warp advances 8 independent recurrences.
+constexpr int kFoldGroup = 4;
+constexpr int kFoldChunk = 32;  // points per group per round (8 per lane)
 
 __global__ void __launch_bounds__(128)
 k_fold_bundles(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t total,
@@ -164,33 +150,32 @@ k_fold_bundles(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t t
                const float4* __restrict__ sorted, uint32_t* work_counter, Ray* __restrict__ folded) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
+  const int sub = lane & (kFoldGroup - 1);
+  const int gbase = lane & ~(kFoldGroup - 1);
   const uint32_t nb = *num_heads;
   uint32_t cur = 0, end = 0, my_b = 0, frame_clr = 0;
   bool finished = false, clearing = false;
   FoldState st;
   fold_reset(st);
   for (;;) {
-    const bool need = !finished && cur >= end;
-    const unsigned m = __ballot_sync(full, need);
+    const bool need = !finished && cur >= end;  // uniform within a group
+    const unsigned m = __ballot_sync(full, need && sub == 0);
     if (m) {
       const int leader = __ffs(m) - 1;
       uint32_t base = 0;
       if (lane == leader) base = atomicAdd(work_counter, static_cast<uint32_t>(__popc(m)));
       base = __shfl_sync(full, base, leader);
       if (need) {
-        const uint32_t b = base + __popc(m & ((1u << lane) - 1u));
+        const uint32_t b = base + __popc(m & ((1u << gbase) - 1u));
         if (b < nb) {
           const uint32_t start = heads[b];
-          const uint32_t stop = (b + 1 < nb) ? heads[b + 1] : total;
           const uint64_t key = keys[start];
           if (key == kInvalidPointKey) {  // sentinel bundle of dropped points
-            folded[b].frame_clr = kNoRay;
+            if (sub == 0) folded[b].frame_clr = kNoRay;
             cur = end = 0;                // fetch again on the next round
-          } else if (stop - start >= kLongBundle) {
-            cur = end = 0;                // left to k_fold_long
           } else {
             cur = start;
-            end = stop;
+            end = (b + 1 < nb) ? heads[b + 1] : total;
             my_b = b;
             clearing = (key >> kBundleClearBit) & 1;
             frame_clr = static_cast<uint32_t>(key >> kBundleFrameShift) |
@@ -203,88 +188,46 @@ k_fold_bundles(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t t
       }
     }
     if (__all_sync(full, finished)) break;
-    if (!finished && cur < end) {
-      const int n = static_cast<int>(min(static_cast<uint32_t>(kFoldUnroll), end - cur));
-      float4 q[kFoldUnroll];
+    const bool work = !finished && cur < end;
+    // a clearing bundle only uses its first point: do not stream the rest
+    const uint32_t n = work ? min(static_cast<uint32_t>(clearing ? kFoldGroup : kFoldChunk),
+                                  end - cur)
+                            : 0u;
+    float4 q[kFoldChunk / kFoldGroup];
 #pragma unroll
-      for (int u = 0; u < kFoldUnroll; ++u)
-        if (u < n) q[u] = sorted[cur + u];
-      bool done = false;
+    for (int u = 0; u < kFoldChunk / kFoldGroup; ++u) {
+      const uint32_t o = u * kFoldGroup + sub;
+      q[u] = (o < n) ? sorted[cur + o] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    const uint32_t n_max = __reduce_max_sync(full, n);
+    bool done = false;
 #pragma unroll
-      for (int u = 0; u < kFoldUnroll; ++u) {
-        if (u < n && !done) {
-          const float w = voxel_weight(P, q[u].z);
+    for (int t = 0; t < kFoldChunk; ++t) {
+      if (t < static_cast<int>(n_max)) {  // warp-uniform: shuffles are executed by all lanes
+        const int src = gbase + (t & (kFoldGroup - 1));
+        const float4 v = q[t / kFoldGroup];
+        const float px = __shfl_sync(full, v.x, src), py = __shfl_sync(full, v.y, src);
+        const float pz = __shfl_sync(full, v.z, src), pw = __shfl_sync(full, v.w, src);
+        if (t < static_cast<int>(n) && !done) {
+          const float w = voxel_weight(P, pz);
           if (!(w < kEps)) {
-            fold_step(st, q[u].x, q[u].y, q[u].z, __float_as_uint(q[u].w), w);
+            fold_step(st, px, py, pz, __float_as_uint(pw), w);
             done = clearing;  // only the first point of a clearing bundle is used
           }
         }
       }
+    }
+    if (work) {
       cur = done ? end : cur + n;
-      if (cur >= end) store_folded(folded, my_b, st, frame_clr);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-k_fold_long(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t total,
-            const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
-            const float4* __restrict__ sorted, uint32_t* work_counter, Ray* __restrict__ folded) {
-  const unsigned full = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31;
-  const uint32_t nb = *num_heads;
-  constexpr uint32_t kBatch = 64;
-  for (;;) {
-    uint32_t b0 = 0;
-    if (lane == 0) b0 = atomicAdd(work_counter, kBatch);
-    b0 = __shfl_sync(full, b0, 0);
-    if (b0 >= nb) break;
-    // lanes look at two bundles of the batch each, the warp then folds the long ones in turn
-    uint32_t long_mask[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint32_t b = b0 + h * 32 + lane;
-      bool is_long = false;
-      if (b < nb) {
-        const uint32_t start = heads[b];
-        const uint32_t stop = (b + 1 < nb) ? heads[b + 1] : total;
-        is_long = stop - start >= kLongBundle && keys[start] != kInvalidPointKey;
-      }
-      long_mask[h] = __ballot_sync(full, is_long);
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint32_t mask = long_mask[h];
-      while (mask) {
-        const uint32_t b = b0 + h * 32 + (__ffs(mask) - 1);
-        mask &= mask - 1;
-        const uint32_t start = heads[b];
-        const uint32_t end = (b + 1 < nb) ? heads[b + 1] : total;
-        const uint64_t key = keys[start];
-        const bool clearing = (key >> kBundleClearBit) & 1;
-        const uint32_t frame_clr =
-            static_cast<uint32_t>(key >> kBundleFrameShift) | (clearing ? 0x80000000u : 0u);
-        FoldState st;
-        fold_reset(st);
-        bool done = false;
-        float4 nxt = (start + lane < end) ? sorted[start + lane] : make_float4(0, 0, 0, 0);
-        for (uint32_t c0 = start; c0 < end && !done; c0 += 32) {
-          const float4 q = nxt;
-          if (c0 + 32 + lane < end) nxt = sorted[c0 + 32 + lane];
-          const int cnt = static_cast<int>(min(32u, end - c0));
-          for (int t = 0; t < cnt; ++t) {
-            const float px = __shfl_sync(full, q.x, t), py = __shfl_sync(full, q.y, t);
-            const float pz = __shfl_sync(full, q.z, t), pw = __shfl_sync(full, q.w, t);
-            const float w = voxel_weight(P, pz);
-            if (w < kEps) continue;
-            fold_step(st, px, py, pz, __float_as_uint(pw), w);
-            if (clearing) {
-              done = true;
-              break;
-            }
-          }
-        }
-        if (lane == 0) store_folded(folded, b, st, frame_clr);
+      if (cur >= end && sub == 0) {
+        Ray r;
+        r.px = st.m.x;  // camera frame; k_bundle_rays moves it to the global frame
+        r.py = st.m.y;
+        r.pz = st.m.z;
+        r.weight = st.W;
+        r.color = fold_color(st);
+        r.frame_clr = frame_clr;
+        folded[my_b] = r;
       }
     }
   }
@@ -370,42 +313,67 @@ __global__ void k_totals(const uint32_t* num_rays, const uint32_t* ray_count,
 // ------------------------------------------------------------------ back half
 // Walk every ray (Amanatides-Woo DDA exactly as voxblox::RayCaster), allocate every block it
 // visits (R4: allocation on first visit), emit one (hash entry << 12 | voxel) key per visit.
+// One lane per ray; every kWalkRound steps the warp flushes the keys staged in shared memory so
+// that each ray's run goes out as contiguous 128-byte rows instead of 32 scattered words.
+constexpr int kWalkRound = 32;
+constexpr int kWalkWarps = 4;
 template <class K>
-__global__ void k_ray_walk(IntegratorParams P, const float* __restrict__ poses,
-                           const Ray* __restrict__ rays, const uint32_t* __restrict__ ray_offset,
-                           uint32_t num_rays, LayerView L, K* __restrict__ pkeys,
-                           uint32_t* __restrict__ pvals) {
+__global__ void __launch_bounds__(kWalkWarps * 32)
+k_ray_walk(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
+           const uint32_t* __restrict__ ray_offset, uint32_t num_rays, LayerView L,
+           K* __restrict__ pkeys, uint32_t* __restrict__ pvals) {
+  __shared__ K stage[kWalkWarps][32][kWalkRound + 1];
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= num_rays) return;
-  const Ray ray = rays[r];
-  if (ray.frame_clr == kNoRay) return;
-  const uint32_t frame = ray.frame_clr & 0x7FFFFFFFu;
-  const bool clearing = (ray.frame_clr >> 31) != 0;
-  const float* T = poses + 7 * frame;
-  const V3 origin = V3{T[4], T[5], T[6]};
   RayCaster rc;
-  rc.init(origin, V3{ray.px, ray.py, ray.pz}, clearing, P.carving != 0, P.max_ray,
-          P.voxel_size_inv, P.trunc);
-  if (!rc.valid) {
-    if (!rc.in_range) atomicOr(L.err, kErrOutOfRange);
-    return;
+  rc.valid = false;
+  rc.steps = 0;
+  uint32_t out = 0;
+  if (r < num_rays) {
+    const Ray ray = rays[r];
+    if (ray.frame_clr != kNoRay) {
+      const uint32_t frame = ray.frame_clr & 0x7FFFFFFFu;
+      const float* T = poses + 7 * frame;
+      rc.init(V3{T[4], T[5], T[6]}, V3{ray.px, ray.py, ray.pz}, (ray.frame_clr >> 31) != 0,
+              P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc);
+      if (!rc.valid && !rc.in_range) atomicOr(L.err, kErrOutOfRange);
+      out = ray_offset[r];
+    }
   }
-  size_t out = ray_offset[r];
+  uint32_t remaining = rc.valid ? rc.steps + 1u : 0u;
   int lbx = 0x7FFFFFFF, lby = 0, lbz = 0;
   K entry_bits = 0;
-  for (unsigned s = 0; s <= rc.steps; ++s) {
-    const int bx = rc.cx >> 4, by = rc.cy >> 4, bz = rc.cz >> 4;
-    if (bx != lbx || by != lby || bz != lbz) {
-      lbx = bx;
-      lby = by;
-      lbz = bz;
-      entry_bits = static_cast<K>(L.insert_entry(pack_block_key(bx, by, bz))) << 12;
+  while (__any_sync(full, remaining > 0)) {
+    const uint32_t n = min(remaining, static_cast<uint32_t>(kWalkRound));
+    for (uint32_t s = 0; s < n; ++s) {
+      const int bx = rc.cx >> 4, by = rc.cy >> 4, bz = rc.cz >> 4;
+      if (bx != lbx || by != lby || bz != lbz) {
+        lbx = bx;
+        lby = by;
+        lbz = bz;
+        entry_bits = static_cast<K>(L.insert_entry(pack_block_key(bx, by, bz))) << 12;
+      }
+      const int lin = (rc.cx & 15) + 16 * ((rc.cy & 15) + 16 * (rc.cz & 15));
+      stage[wib][lane][s] = entry_bits | static_cast<K>(lin);
+      rc.step();
     }
-    const int lin = (rc.cx & 15) + 16 * ((rc.cy & 15) + 16 * (rc.cz & 15));
-    pkeys[out] = entry_bits | static_cast<K>(lin);
-    pvals[out] = r;
-    ++out;
-    rc.step();
+    __syncwarp();
+    // flush: row l = the n_l keys of lane l's ray, contiguous at out_l
+    for (int l = 0; l < 32; ++l) {
+      const uint32_t n_l = __shfl_sync(full, n, l);
+      if (n_l == 0) continue;
+      const uint32_t out_l = __shfl_sync(full, out, l);
+      const uint32_t r_l = __shfl_sync(full, r, l);
+      if (static_cast<uint32_t>(lane) < n_l) {
+        pkeys[out_l + lane] = stage[wib][l][lane];
+        pvals[out_l + lane] = r_l;
+      }
+    }
+    __syncwarp();
+    out += n;
+    remaining -= n;
   }
 }
 
@@ -875,16 +843,12 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
                                     static_cast<int>(total), BundleHead{dk.Current()}, s));
     }
     {
-      StageScope sc(ctx, kStageFold, 4);
+      StageScope sc(ctx, kStageFold, 3);
       CG_CUDA(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(uint32_t), s));
       k_gather_sorted<<<grid_for(total, 256), 256, 0, s>>>(
           dk.Current(), dv.Current(), static_cast<uint32_t>(total), pts, cols,
           ctx->sorted_pts.as<float4>());
       k_fold_bundles<<<ctx->num_sms * 16, 128, 0, s>>>(
-          P, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
-          ctx->sorted_pts.as<float4>(), ctx->d_work_counter, ctx->rays.as<Ray>());
-      CG_CUDA(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(uint32_t), s));
-      k_fold_long<<<ctx->num_sms * 8, 256, 0, s>>>(
           P, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
           ctx->sorted_pts.as<float4>(), ctx->d_work_counter, ctx->rays.as<Ray>());
       k_bundle_rays<<<grid_for(upper, 256), 256, 0, s>>>(P, ctx->poses.as<float>(), d_num,
