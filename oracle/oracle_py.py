@@ -78,6 +78,8 @@ def lib():
         L.orc_merge_layer_into_layer_mt.restype = C.c_int32
         L.orc_merge_layer_into_layer_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                                     C.POINTER(C.c_uint64)]
+        L.orc_merge_layer_aligned.restype = C.c_int32
+        L.orc_merge_layer_aligned.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_transform_point.argtypes = [C.c_void_p] * 3
         L.orc_inverse_transform.argtypes = [C.c_void_p] * 2
         L.orc_cast_ray.restype = C.c_size_t
@@ -162,6 +164,11 @@ class Layer:
         self.last_blocks_out = out.value
         if rc != 0:
             raise RuntimeError(f"oracle merge failed rc={rc}")
+
+    def merge_aligned_from(self, layer_a):
+        """2-argument mergeLayerAintoLayerB(layer_a, self) (same grid, voxel-wise)."""
+        if lib().orc_merge_layer_aligned(layer_a._h, self._h) != 0:
+            raise RuntimeError("oracle aligned merge failed")
 
     def download(self):
         """-> (block_idx int32 [B,3] sorted (z,y,x), voxels [B,4096] VOXEL_DTYPE, flags u8 [B])."""

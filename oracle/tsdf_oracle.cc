@@ -1002,6 +1002,22 @@ int32_t orc_merge_layer_into_layer_mt(const orc_layer* a, const float T[7], orc_
   return merge_layers(a, load_xform(T), b, threads, blocks_out);
 }
 
+int32_t orc_merge_layer_aligned(const orc_layer* a, orc_layer* b) {
+  if (!a || !b || a->voxel_size != b->voxel_size) return -1;
+  std::vector<I3> keys;
+  for (const auto& kv : a->blocks) keys.push_back(kv.first);
+  std::sort(keys.begin(), keys.end(), zyx_less_i);
+  for (const I3& k : keys) {
+    const Block* src = a->find(k);
+    Block* dst = b->get_or_create(k);  // allocated even when the source carries no data
+    if (!src->has_data) continue;      // Block::mergeBlock
+    dst->has_data = true;
+    dst->updated = true;
+    for (int lin = 0; lin < kVoxelsPerBlock; ++lin) merge_voxel(src->voxels[lin], &dst->voxels[lin]);
+  }
+  return 0;
+}
+
 void orc_transform_point(const float T[7], const float p[3], float out[3]) {
   const V3 r = apply(load_xform(T), V3{p[0], p[1], p[2]});
   out[0] = r.x;

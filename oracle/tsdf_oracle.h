@@ -88,6 +88,11 @@ int32_t orc_merge_layer_into_layer_mt(const orc_layer* layer_a, const float T_B_
                                       orc_layer* layer_b, int32_t threads,
                                       uint64_t* blocks_out);
 
+/* 2-argument voxblox::mergeLayerAintoLayerB(layer_A, layer_B) for layers on the same grid
+ * (call site coxgraph/src/server/submap_collection.cpp:31-33): Block::mergeBlock per block,
+ * blocks of A without data are skipped. */
+int32_t orc_merge_layer_aligned(const orc_layer* layer_a, orc_layer* layer_b);
+
 /* Small pieces exposed for known-answer tests. */
 void orc_transform_point(const float T[7], const float p[3], float out[3]);
 void orc_inverse_transform(const float T[7], float Tinv[7]);
