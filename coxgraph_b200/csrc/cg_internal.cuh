@@ -27,7 +27,7 @@ constexpr int kVoxIdxOffset = 1 << 19;
 constexpr uint64_t kInvalidPointKey = ~0ull;         // sorts behind every valid key
 constexpr int kClearingBit = 60;
 
-enum ErrBits { kErrPoolFull = 1, kErrOutOfRange = 2 };
+enum ErrBits { kErrPoolFull = 1, kErrOutOfRange = 2, kErrTouchFull = 4 };
 
 // ------------------------------------------------------------------ key packing
 __host__ __device__ __forceinline__ uint64_t pack_block_key(int x, int y, int z) {
@@ -158,6 +158,7 @@ struct CallCounters {
   unsigned long long rays;
   unsigned long long pairs;
   unsigned long long touched;
+  unsigned long long general_pairs;
   unsigned long long candidates;
   unsigned long long blocks_out;
   int err;
@@ -172,10 +173,12 @@ enum Stage {
   kStageBundleScan,
   kStageFold,
   kStageRayScan,
-  kStageRayWalk,
+  kStageWalkAccumulate,
+  kStageWalkEmit,
   kStagePairSort,
   kStageSegments,
   kStageVoxelUpdate,
+  kStageFinalize,
   kStageMergeMark,
   kStageMergeResample,
   kStageTransfer,
@@ -200,7 +203,12 @@ struct cg_context {
   cg::DevBuf points, colors, poses, frame_base;
   cg::DevBuf key_a, key_b, val_a, val_b, flags, scan, cub_tmp;
   cg::DevBuf rays, ray_count, ray_offset, sorted_pts;
-  cg::DevBuf pkey_a, pkey_b, pval_a, pval_b, seg_start, long_list, long_partials;
+  cg::DevBuf pkey_a, pkey_b, seg_start, long_list, long_partials;
+  // per-call touch set (integrate.cu "back half"): kept all-clear between calls
+  cg::DevBuf touch_ord, touch_entry, touch_acc, touch_bits;
+  uint32_t* d_touch_count = nullptr;  // [0] blocks touched, [1] general (voxel, ray) keys emitted
+  size_t touch_cap = 0;               // blocks the scratch holds
+  bool touch_clean = false;
   unsigned long long* d_long_counter = nullptr;  // (#long segments << 32) | #sub-blocks
   uint32_t* d_select_count = nullptr;  // output count of the stream compactions
   uint32_t* d_work_counter = nullptr;  // dynamic work distribution of the persistent kernels

@@ -311,94 +311,82 @@ __global__ void k_totals(const uint32_t* num_rays, const uint32_t* ray_count,
 }
 
 // ------------------------------------------------------------------ back half
-// Walk every ray (Amanatides-Woo DDA exactly as voxblox::RayCaster), allocate every block it
-// visits (R4: allocation on first visit), emit one (hash entry << 12 | voxel) key per visit.
-// One lane per ray; every kWalkRound steps the warp flushes the keys staged in shared memory so
-// that each ray's run goes out as contiguous 128-byte rows instead of 32 scattered words.
-constexpr int kWalkRound = 32;
-constexpr int kWalkWarps = 4;
-template <class K>
-__global__ void __launch_bounds__(kWalkWarps * 32)
-k_ray_walk(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
-           const uint32_t* __restrict__ ray_offset, uint32_t num_rays, LayerView L,
-           K* __restrict__ pkeys, uint32_t* __restrict__ pvals) {
-  __shared__ K stage[kWalkWarps][32][kWalkRound + 1];
-  const unsigned full = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+// The voxels a job visits fall in two classes.  Nearly all of them (the carved free space) only
+// ever see observations with sdf >= truncation while being fresh or already saturated at
+// +truncation: for those updateTsdfVoxel degenerates to "D = trunc, W = min(max_weight, W + sum
+// of the ray weights)", which needs no ordering — a fixed-point sum per voxel (deterministic, the
+// adds commute exactly).  The rest ("general" voxels: any observation inside the truncation band
+// or behind the surface, or a previous state that is not saturated) replay their updates in the
+// reference's order.  Two walks over the rays:
+//   k_walk_accumulate  DDA (voxblox::RayCaster), block allocation on first visit (R4), weight
+//                      accumulation for every visit, "general" bit for every visit whose sdf is
+//                      below the truncation distance (only the tail of a ray can be)
+//   k_mark_existing    voxels of previously existing blocks whose state is not saturated
+//   k_walk_emit        DDA again; visits of general voxels are appended as (voxel, ray) keys
+//   radix sort         keys only: per-voxel update lists in ray (= canonical) order
+//   k_voxel_update     ordered replay of the general voxels
+//   k_finalize_blocks  one CTA per touched block: coalesced read-modify-write of the remaining
+//                      voxels from the accumulators; resets the per-call scratch.
+
+// Per-call "touch set": a block gets an ordinal when the first ray of the job visits it; the
+// per-call scratch is indexed by ordinal.
+struct TouchView {
+  int32_t* ord;             // [hash_cap]   hash entry -> ordinal; -1 untouched, -2 being claimed
+  uint32_t* entry;          // [cap]        ordinal -> hash entry
+  unsigned long long* acc;  // [cap * 4096] fixed-point sum of the ray weights of all visits
+  uint32_t* general;        // [cap * 128]  bit per voxel: replay its updates in order
+  uint32_t* count;          // ordinals claimed (exceeds cap on overflow: the job is redone)
+  uint32_t cap;
+};
+
+__device__ __forceinline__ uint32_t touch_ordinal(const TouchView& Tv, int entry, int32_t* err) {
+  volatile int32_t* p = Tv.ord + entry;
+  for (;;) {
+    const int32_t o = *p;
+    if (o >= 0) return static_cast<uint32_t>(o);
+    if (o == -1 && atomicCAS(Tv.ord + entry, -1, -2) == -1) {
+      uint32_t n = atomicAdd(Tv.count, 1u);
+      if (n < Tv.cap) {
+        Tv.entry[n] = static_cast<uint32_t>(entry);
+      } else {
+        atomicOr(err, kErrTouchFull);
+        n = n % Tv.cap;  // stays addressable; the host grows the scratch and redoes the walks
+      }
+      __threadfence();
+      *p = static_cast<int32_t>(n);
+      return n;
+    }
+  }
+}
+
+constexpr int kWalkThreads = 128;
+
+struct WalkRay {
   RayCaster rc;
-  rc.valid = false;
-  rc.steps = 0;
-  uint32_t out = 0;
+  Ray ray;
+  uint32_t remaining;
+};
+__device__ __forceinline__ WalkRay load_walk_ray(const IntegratorParams& P,
+                                                 const float* __restrict__ poses,
+                                                 const Ray* __restrict__ rays, uint32_t r,
+                                                 uint32_t num_rays, int32_t* err) {
+  WalkRay w;
+  w.rc.valid = false;
+  w.rc.steps = 0;
+  w.ray.frame_clr = kNoRay;
+  w.ray.weight = 0.0f;
   if (r < num_rays) {
-    const Ray ray = rays[r];
-    if (ray.frame_clr != kNoRay) {
-      const uint32_t frame = ray.frame_clr & 0x7FFFFFFFu;
-      const float* T = poses + 7 * frame;
-      rc.init(V3{T[4], T[5], T[6]}, V3{ray.px, ray.py, ray.pz}, (ray.frame_clr >> 31) != 0,
-              P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc);
-      if (!rc.valid && !rc.in_range) atomicOr(L.err, kErrOutOfRange);
-      out = ray_offset[r];
+    w.ray = rays[r];
+    if (w.ray.frame_clr != kNoRay) {
+      const float* T = poses + 7 * (w.ray.frame_clr & 0x7FFFFFFFu);
+      w.rc.init(V3{T[4], T[5], T[6]}, V3{w.ray.px, w.ray.py, w.ray.pz},
+                (w.ray.frame_clr >> 31) != 0, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc);
+      if (!w.rc.valid && !w.rc.in_range && err) atomicOr(err, kErrOutOfRange);
     }
   }
-  uint32_t remaining = rc.valid ? rc.steps + 1u : 0u;
-  int lbx = 0x7FFFFFFF, lby = 0, lbz = 0;
-  K entry_bits = 0;
-  while (__any_sync(full, remaining > 0)) {
-    const uint32_t n = min(remaining, static_cast<uint32_t>(kWalkRound));
-    for (uint32_t s = 0; s < n; ++s) {
-      const int bx = rc.cx >> 4, by = rc.cy >> 4, bz = rc.cz >> 4;
-      if (bx != lbx || by != lby || bz != lbz) {
-        lbx = bx;
-        lby = by;
-        lbz = bz;
-        entry_bits = static_cast<K>(L.insert_entry(pack_block_key(bx, by, bz))) << 12;
-      }
-      const int lin = (rc.cx & 15) + 16 * ((rc.cy & 15) + 16 * (rc.cz & 15));
-      stage[wib][lane][s] = entry_bits | static_cast<K>(lin);
-      rc.step();
-    }
-    __syncwarp();
-    // flush: row l = the n_l keys of lane l's ray, contiguous at out_l
-    for (int l = 0; l < 32; ++l) {
-      const uint32_t n_l = __shfl_sync(full, n, l);
-      if (n_l == 0) continue;
-      const uint32_t out_l = __shfl_sync(full, out, l);
-      const uint32_t r_l = __shfl_sync(full, r, l);
-      if (static_cast<uint32_t>(lane) < n_l) {
-        pkeys[out_l + lane] = stage[wib][l][lane];
-        pvals[out_l + lane] = r_l;
-      }
-    }
-    __syncwarp();
-    out += n;
-    remaining -= n;
-  }
+  w.remaining = w.rc.valid ? w.rc.steps + 1u : 0u;
+  return w;
 }
-
-template <class K>
-struct SegmentHead {
-  const K* keys;
-  __device__ __forceinline__ bool operator()(uint32_t i) const {
-    return i == 0 || keys[i] != keys[i - 1];
-  }
-};
-
-// x -> clamp(a x + b, lo, hi), a >= 0.  Closed under composition.
-struct ClampedAffine {
-  float a, b, lo, hi;
-};
-__device__ __forceinline__ ClampedAffine compose(const ClampedAffine& f, const ClampedAffine& g) {
-  // g after f
-  ClampedAffine r;
-  r.a = g.a * f.a;
-  r.b = g.a * f.b + g.b;
-  r.lo = fminf(fmaxf(g.a * f.lo + g.b, g.lo), g.hi);
-  r.hi = fminf(fmaxf(g.a * f.hi + g.b, g.lo), g.hi);
-  return r;
-}
-constexpr float kBig = 1.0e30f;
 
 // state-independent part of updateTsdfVoxel for one (ray, voxel) visit
 struct Visit {
@@ -427,23 +415,186 @@ __device__ __forceinline__ Visit make_visit(const IntegratorParams& P, const flo
   return v;
 }
 
+// Walk 1.  One lane per ray, the warp advances in lock step.  `tail_visits`: only the last
+// tail_visits visits of a ray can have sdf < truncation (host: walk_tail_visits()).
+__global__ void __launch_bounds__(kWalkThreads)
+k_walk_accumulate(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
+                  uint32_t num_rays, LayerView L, TouchView Tv, float acc_scale,
+                  uint32_t tail_visits) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  for (uint32_t r0 = blockIdx.x * blockDim.x; r0 < num_rays; r0 += gridDim.x * blockDim.x) {
+    WalkRay w = load_walk_ray(P, poses, rays, r0 + threadIdx.x, num_rays, L.err);
+    RayCaster& rc = w.rc;
+    const unsigned long long wq =
+        __float2ull_rn(fminf(fmaxf(w.ray.weight, 0.0f), P.max_weight) * acc_scale);
+    int lbx = 0x7FFFFFFF, lby = 0, lbz = 0;
+    uint32_t vbase = 0;
+    for (;;) {
+      const bool active = w.remaining > 0;
+      const unsigned am = __ballot_sync(full, active);
+      if (!am) break;
+      uint32_t vid = 0xFFFFFFFFu;
+      if (active) {
+        const int bx = rc.cx >> 4, by = rc.cy >> 4, bz = rc.cz >> 4;
+        if (bx != lbx || by != lby || bz != lbz) {
+          lbx = bx;
+          lby = by;
+          lbz = bz;
+          const int entry = L.insert_entry(pack_block_key(bx, by, bz));
+          vbase = touch_ordinal(Tv, entry, L.err) << 12;
+        }
+        vid = vbase | static_cast<uint32_t>((rc.cx & 15) + 16 * ((rc.cy & 15) + 16 * (rc.cz & 15)));
+        if (w.remaining <= tail_visits) {
+          const V3 center = V3{center_coord(rc.cx, P.voxel_size), center_coord(rc.cy, P.voxel_size),
+                               center_coord(rc.cz, P.voxel_size)};
+          const float sdf = make_visit(P, poses, w.ray, center).sdf;
+          if (!(sdf >= P.trunc)) atomicOr(Tv.general + (vid >> 5), 1u << (vid & 31));
+        }
+      }
+      // next to the sensor every ray of the warp crosses the same voxel: one add for the warp
+      const int first = __ffs(am) - 1;
+      const uint32_t v0 = __shfl_sync(full, vid, first);
+      if (__all_sync(full, !active || vid == v0)) {
+        unsigned long long s = active ? wq : 0ull;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(full, s, d);
+        if (lane == first) atomicAdd(Tv.acc + v0, s);
+      } else if (active) {
+        atomicAdd(Tv.acc + vid, wq);
+      }
+      if (active) {
+        rc.step();
+        --w.remaining;
+      }
+    }
+  }
+}
+
+// Voxels of blocks that existed before the job and whose state is neither fresh nor saturated
+// at +truncation need the ordered replay even if the job only observes them as free space.
+__global__ void __launch_bounds__(128)
+k_mark_existing(IntegratorParams P, LayerView L, TouchView Tv, int32_t blocks_before) {
+  const unsigned full = 0xFFFFFFFFu;
+  const uint32_t n = min(*Tv.count, Tv.cap);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t o = blockIdx.x; o < n; o += gridDim.x) {
+    const int slot = L.hash_vals[Tv.entry[o]];
+    if (slot < 0 || slot >= blocks_before) continue;
+    const float* dp = L.dist_plane(slot);
+    const float* wp = L.weight_plane(slot);
+    for (int word = warp; word < kVoxelsPerBlock / 32; word += 4) {
+      const int lin = word * 32 + lane;
+      const bool g = wp[lin] > 0.0f && dp[lin] != P.trunc;
+      const unsigned m = __ballot_sync(full, g);
+      if (lane == 0 && m) atomicOr(Tv.general + o * (kVoxelsPerBlock / 32) + word, m);
+    }
+  }
+}
+
+// Walk 2: same rays, same voxels; visits of general voxels go out as (voxel << ray_bits | ray).
+// Each warp stages its keys in shared memory and appends them with one atomic per flush; the
+// append order is irrelevant because the sort key contains the ray rank.
+constexpr int kEmitBuf = 256;
+__global__ void __launch_bounds__(kWalkThreads)
+k_walk_emit(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
+            uint32_t num_rays, LayerView L, TouchView Tv, uint32_t ray_bits,
+            unsigned long long* __restrict__ out, uint32_t* out_count, uint32_t out_cap) {
+  __shared__ unsigned long long buf[kWalkThreads / 32][kEmitBuf];
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t cnt = 0;
+  auto flush = [&]() {
+    __syncwarp();
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(out_count, cnt);
+    base = __shfl_sync(full, base, 0);
+    for (uint32_t i = lane; i < cnt; i += 32)
+      if (base + i < out_cap) out[base + i] = buf[wib][i];
+    __syncwarp();
+    cnt = 0;
+  };
+  for (uint32_t r0 = blockIdx.x * blockDim.x; r0 < num_rays; r0 += gridDim.x * blockDim.x) {
+    const uint32_t r = r0 + threadIdx.x;
+    WalkRay w = load_walk_ray(P, poses, rays, r, num_rays, nullptr);
+    RayCaster& rc = w.rc;
+    int lbx = 0x7FFFFFFF, lby = 0, lbz = 0;
+    uint32_t vbase = 0;
+    bool known = false;
+    for (;;) {
+      const bool active = w.remaining > 0;
+      if (!__any_sync(full, active)) break;
+      bool g = false;
+      uint32_t vid = 0;
+      if (active) {
+        const int bx = rc.cx >> 4, by = rc.cy >> 4, bz = rc.cz >> 4;
+        if (bx != lbx || by != lby || bz != lbz) {
+          lbx = bx;
+          lby = by;
+          lbz = bz;
+          const int entry = L.find_entry(pack_block_key(bx, by, bz));
+          known = entry >= 0;
+          vbase = known ? static_cast<uint32_t>(Tv.ord[entry]) << 12 : 0u;
+        }
+        vid = vbase | static_cast<uint32_t>((rc.cx & 15) + 16 * ((rc.cy & 15) + 16 * (rc.cz & 15)));
+        g = known && ((Tv.general[vid >> 5] >> (vid & 31)) & 1u);
+      }
+      const unsigned gm = __ballot_sync(full, g);
+      if (gm) {
+        if (g) buf[wib][cnt + __popc(gm & lt)] =
+            (static_cast<unsigned long long>(vid) << ray_bits) | r;
+        cnt += __popc(gm);
+        if (cnt > kEmitBuf - 32) flush();
+      }
+      if (active) {
+        rc.step();
+        --w.remaining;
+      }
+    }
+  }
+  if (cnt) flush();
+}
+
+struct SegmentHead {
+  const unsigned long long* keys;
+  uint32_t ray_bits;
+  __device__ __forceinline__ bool operator()(uint32_t i) const {
+    return i == 0 || (keys[i] >> ray_bits) != (keys[i - 1] >> ray_bits);
+  }
+};
+
+// x -> clamp(a x + b, lo, hi), a >= 0.  Closed under composition.
+struct ClampedAffine {
+  float a, b, lo, hi;
+};
+__device__ __forceinline__ ClampedAffine compose(const ClampedAffine& f, const ClampedAffine& g) {
+  // g after f
+  ClampedAffine r;
+  r.a = g.a * f.a;
+  r.b = g.a * f.b + g.b;
+  r.lo = fminf(fmaxf(g.a * f.lo + g.b, g.lo), g.hi);
+  r.hi = fminf(fmaxf(g.a * f.hi + g.b, g.lo), g.hi);
+  return r;
+}
+constexpr float kBig = 1.0e30f;
+
 // voxel addressed by a pair key
 struct VoxelRef {
   int slot;
-  uint32_t entry;
   V3 center;
   float* dp;
   float* wp;
   uint32_t* cp;
 };
-template <class K>
-__device__ __forceinline__ VoxelRef voxel_ref(const IntegratorParams& P, const LayerView& L, K key) {
+__device__ __forceinline__ VoxelRef voxel_ref(const IntegratorParams& P, const LayerView& L,
+                                              const TouchView& Tv, uint32_t vid) {
   VoxelRef r;
-  r.entry = static_cast<uint32_t>(key >> 12);
-  const int lin = static_cast<int>(key & 4095);
-  r.slot = L.hash_vals[r.entry];
+  const uint32_t entry = Tv.entry[vid >> 12];
+  const int lin = static_cast<int>(vid & 4095u);
+  r.slot = L.hash_vals[entry];
   int bx, by, bz;
-  unpack_block_key(L.hash_keys[r.entry], bx, by, bz);
+  unpack_block_key(L.hash_keys[entry], bx, by, bz);
   r.center = V3{center_coord(bx * 16 + (lin & 15), P.voxel_size),
                 center_coord(by * 16 + ((lin >> 4) & 15), P.voxel_size),
                 center_coord(bz * 16 + (lin >> 8), P.voxel_size)};
@@ -461,18 +612,22 @@ __device__ __forceinline__ VoxelRef voxel_ref(const IntegratorParams& P, const L
 __device__ __forceinline__ void replay_segment(const IntegratorParams& P,
                                                const float* __restrict__ poses,
                                                const Ray* __restrict__ rays,
-                                               const uint32_t* __restrict__ pvals, uint32_t start,
-                                               uint32_t end, V3 center, int lane, float& D, float& W,
+                                               const unsigned long long* __restrict__ keys,
+                                               uint32_t ray_mask, uint32_t start, uint32_t end,
+                                               V3 center, int lane, float& D, float& W,
                                                uint32_t& C) {
   const unsigned full = 0xFFFFFFFFu;
-  uint32_t id_next = (start + lane < end) ? pvals[start + lane] : 0u;
+  auto ray_id = [&](uint32_t j) -> uint32_t {
+    return (j < end) ? static_cast<uint32_t>(keys[j]) & ray_mask : 0u;
+  };
+  uint32_t id_next = ray_id(start + lane);
   Ray ray_next = rays[id_next];
-  id_next = (start + 32 + lane < end) ? pvals[start + 32 + lane] : 0u;
+  id_next = ray_id(start + 32 + lane);
   for (uint32_t c0 = start; c0 < end; c0 += 32) {
     const Ray ray = ray_next;
     if (c0 + 32 < end) {
       ray_next = rays[id_next];
-      id_next = (c0 + 64 + lane < end) ? pvals[c0 + 64 + lane] : 0u;
+      id_next = ray_id(c0 + 64 + lane);
     }
     const bool act = c0 + lane < end;
     Visit v = make_visit(P, poses, ray, center);
@@ -518,8 +673,8 @@ __device__ __forceinline__ void replay_segment(const IntegratorParams& P,
   }
 }
 
-// Long segments (>= kLongSegment updates: the voxels next to the sensor, crossed by every ray)
-// are split into sub-blocks that many warps reduce in parallel, see k_long_partials.
+// Long segments (>= kLongSegment updates) are split into sub-blocks that many warps reduce in
+// parallel, see k_long_partials.
 constexpr uint32_t kLongSegment = 2048;
 constexpr uint32_t kLongSub = 1024;
 struct LongSeg {
@@ -532,19 +687,19 @@ struct LongPartial {
   uint32_t not_free;      // any update with sdf < trunc (not a pure free-space observation)
 };
 
-// One warp per voxel segment (R5 updateTsdfVoxel replayed over the voxel's update list);
+// One warp per general voxel (R5 updateTsdfVoxel replayed over the voxel's update list);
 // segments are handed out dynamically, kSegBatch at a time.
 constexpr uint32_t kSegBatch = 8;
-template <class K>
 __global__ void __launch_bounds__(256)
 k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
-               const K* __restrict__ pkeys, const uint32_t* __restrict__ pvals, uint32_t num_pairs,
+               const unsigned long long* __restrict__ keys, uint32_t ray_bits, uint32_t num_pairs,
                const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ num_segs,
                uint32_t* work_counter, unsigned long long* long_counter, LongSeg* long_list,
-               uint32_t long_cap, LayerView L, CallCounters* counters) {
+               uint32_t long_cap, LayerView L, TouchView Tv) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const uint32_t ns = *num_segs;
+  const uint32_t ray_mask = (1u << ray_bits) - 1u;
   for (;;) {
     uint32_t s0 = 0;
     if (lane == 0) s0 = atomicAdd(work_counter, kSegBatch);
@@ -554,13 +709,8 @@ k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* _
     for (uint32_t s = s0; s < s1; ++s) {
       const uint32_t start = seg_start[s];
       const uint32_t end = (s + 1 < ns) ? seg_start[s + 1] : num_pairs;
-      const K key = pkeys[start];
-      const VoxelRef vr = voxel_ref(P, L, key);
+      const VoxelRef vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[start] >> ray_bits));
       if (vr.slot < 0) continue;  // pool exhausted; error already flagged
-      if (lane == 0 && (start == 0 || static_cast<uint32_t>(pkeys[start - 1] >> 12) != vr.entry)) {
-        atomicAdd(&counters->touched, 1ull);
-        L.updated[vr.slot] = 1;
-      }
       if (end - start >= kLongSegment) {
         if (lane == 0) {
           const uint32_t nsub = (end - start + kLongSub - 1) / kLongSub;
@@ -574,7 +724,7 @@ k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* _
       }
       float D = *vr.dp, W = *vr.wp;
       uint32_t C = *vr.cp;
-      replay_segment(P, poses, rays, pvals, start, end, vr.center, lane, D, W, C);
+      replay_segment(P, poses, rays, keys, ray_mask, start, end, vr.center, lane, D, W, C);
       if (lane == 0) {
         *vr.dp = D;
         *vr.wp = W;
@@ -585,12 +735,11 @@ k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* _
 }
 
 // sub-block t of the long segments: sum of weights + "all free space" flag (one warp each)
-template <class K>
 __global__ void __launch_bounds__(256)
 k_long_partials(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
-                const K* __restrict__ pkeys, const uint32_t* __restrict__ pvals,
+                const unsigned long long* __restrict__ keys, uint32_t ray_bits,
                 const unsigned long long* __restrict__ long_counter,
-                const LongSeg* __restrict__ long_list, uint32_t long_cap, LayerView L,
+                const LongSeg* __restrict__ long_list, uint32_t long_cap, LayerView L, TouchView Tv,
                 LongPartial* __restrict__ partials) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
@@ -599,6 +748,7 @@ k_long_partials(IntegratorParams P, const float* __restrict__ poses, const Ray* 
   const unsigned long long cnt = *long_counter;
   const uint32_t nlong = min(static_cast<uint32_t>(cnt >> 32), long_cap);
   const uint32_t nitems = static_cast<uint32_t>(cnt);
+  const uint32_t ray_mask = (1u << ray_bits) - 1u;
   for (uint32_t t = warp; t < nitems; t += num_warps) {
     // long_list is ordered by item_base (both come from the same atomic): binary search
     uint32_t lo = 0, hi = nlong;
@@ -607,17 +757,18 @@ k_long_partials(IntegratorParams P, const float* __restrict__ poses, const Ray* 
       if (long_list[mid].item_base <= t) lo = mid; else hi = mid;
     }
     const LongSeg seg = long_list[lo];
-    if (t < seg.item_base) continue;  // list overflowed: handled by the slow path elsewhere
+    if (t < seg.item_base) continue;
     const uint32_t a = seg.start + (t - seg.item_base) * kLongSub;
     const uint32_t b = min(seg.end, a + kLongSub);
-    const VoxelRef vr = voxel_ref(P, L, pkeys[seg.start]);
+    const VoxelRef vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[seg.start] >> ray_bits));
     float sum = 0.0f;
     bool not_free = false;
     for (uint32_t c0 = a; c0 < b; c0 += 32) {
       const uint32_t j = c0 + lane;
       float w = 0.0f;
       if (j < b) {
-        const Visit v = make_visit(P, poses, rays[pvals[j]], vr.center);
+        const Visit v =
+            make_visit(P, poses, rays[static_cast<uint32_t>(keys[j]) & ray_mask], vr.center);
         w = v.w;
         not_free = not_free || !(v.sdf >= P.trunc);
       }
@@ -631,23 +782,22 @@ k_long_partials(IntegratorParams P, const float* __restrict__ poses, const Ray* 
 }
 
 // one warp per long segment: closed form when every update is a free-space observation of a
-// voxel that is fresh or already at +truncation (then every step of the reference clamps to
-// +truncation again), otherwise the general replay.
-template <class K>
+// voxel that is fresh or already at +truncation, otherwise the general replay.
 __global__ void __launch_bounds__(256)
 k_long_finish(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
-              const K* __restrict__ pkeys, const uint32_t* __restrict__ pvals,
+              const unsigned long long* __restrict__ keys, uint32_t ray_bits,
               const unsigned long long* __restrict__ long_counter,
-              const LongSeg* __restrict__ long_list, uint32_t long_cap, LayerView L,
+              const LongSeg* __restrict__ long_list, uint32_t long_cap, LayerView L, TouchView Tv,
               const LongPartial* __restrict__ partials) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
   const unsigned long long cnt = *long_counter;
   const uint32_t nlong = min(static_cast<uint32_t>(cnt >> 32), long_cap);
+  const uint32_t ray_mask = (1u << ray_bits) - 1u;
   for (uint32_t i = warp; i < nlong; i += num_warps) {
     const LongSeg seg = long_list[i];
-    const VoxelRef vr = voxel_ref(P, L, pkeys[seg.start]);
+    const VoxelRef vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[seg.start] >> ray_bits));
     float D = *vr.dp, W = *vr.wp;
     uint32_t C = *vr.cp;
     const uint32_t nsub = (seg.end - seg.start + kLongSub - 1) / kLongSub;
@@ -666,13 +816,47 @@ k_long_finish(IntegratorParams P, const float* __restrict__ poses, const Ray* __
         W = fminf(P.max_weight, w_total);
       }
     } else {
-      replay_segment(P, poses, rays, pvals, seg.start, seg.end, vr.center, lane, D, W, C);
+      replay_segment(P, poses, rays, keys, ray_mask, seg.start, seg.end, vr.center, lane, D, W, C);
     }
     if (lane == 0) {
       *vr.dp = D;
       *vr.wp = W;
       *vr.cp = C;
     }
+  }
+}
+
+// One CTA per touched block: every voxel that is not general and was visited becomes
+// (D = trunc, W = min(max_weight, W + sum of ray weights)) — coalesced read-modify-write of the
+// weight and distance planes — and the per-call scratch of the block goes back to zero.
+__global__ void __launch_bounds__(256)
+k_finalize_blocks(IntegratorParams P, LayerView L, TouchView Tv, float acc_inv_scale) {
+  const uint32_t o = blockIdx.x;
+  const uint32_t entry = Tv.entry[o];
+  const int slot = L.hash_vals[entry];
+  unsigned long long* acc = Tv.acc + static_cast<size_t>(o) * kVoxelsPerBlock;
+  uint32_t* bits = Tv.general + static_cast<size_t>(o) * (kVoxelsPerBlock / 32);
+  float* dp = slot >= 0 ? L.dist_plane(slot) : nullptr;
+  float* wp = slot >= 0 ? L.weight_plane(slot) : nullptr;
+  for (int lin = threadIdx.x; lin < kVoxelsPerBlock; lin += blockDim.x) {
+    const unsigned long long a = acc[lin];
+    if (a != 0ull) {
+      acc[lin] = 0ull;
+      const bool general = (bits[lin >> 5] >> (lin & 31)) & 1u;
+      if (!general && slot >= 0) {
+        const float w_total = wp[lin] + static_cast<float>(a) * acc_inv_scale;
+        if (!(w_total < kEps)) {
+          dp[lin] = P.trunc;
+          wp[lin] = fminf(P.max_weight, w_total);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kVoxelsPerBlock / 32) bits[threadIdx.x] = 0u;
+  if (threadIdx.x == 0) {
+    Tv.ord[entry] = -1;
+    if (slot >= 0) L.updated[slot] = 1;
   }
 }
 
@@ -702,62 +886,179 @@ static size_t env_size(const char* name, size_t dflt) {
   return static_cast<size_t>(strtoull(s, nullptr, 10));
 }
 
-template <class K>
-static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParams& P,
-                             uint32_t num_rays, size_t num_pairs, int key_bits) {
+// number of trailing visits of a ray that can have sdf < truncation.  A visit with k DDA steps
+// left lies at L1 voxel distance k from the end voxel, hence at Euclidean distance >=
+// (k - 1.5) / sqrt(3) voxels from the ray end; the voxel centre is within sqrt(3)/2 voxels of
+// the ray, and the end lies trunc behind the surface point, so sdf >= trunc is guaranteed once
+// ((k - 1.5) / sqrt(3))^2 - 3/4 >= (2 trunc / voxel + 1/2)^2.  (Clearing rays end before the
+// point: the same bound holds with more slack.)
+static uint32_t walk_tail_visits(const IntegratorParams& P) {
+  const float m = 2.0f * P.trunc * P.voxel_size_inv;
+  const float k = 1.5f + 1.7321f * (m + 0.5f + 0.87f);
+  return static_cast<uint32_t>(std::min(1.0e6f, ceilf(k))) + 2u;
+}
+
+static int ceil_log2(uint64_t v) {
+  int b = 0;
+  while ((uint64_t(1) << b) < v) ++b;
+  return b;
+}
+
+// per-call touch scratch for at least `cap` blocks, all clear
+static int32_t ensure_touch(cg_context* ctx, const cg_layer* L, size_t cap) {
   cudaStream_t s = ctx->stream;
-  CG_CUDA(ctx->pkey_a.reserve(num_pairs * sizeof(K)));
-  CG_CUDA(ctx->pkey_b.reserve(num_pairs * sizeof(K)));
-  CG_CUDA(ctx->pval_a.reserve(num_pairs * sizeof(uint32_t)));
-  CG_CUDA(ctx->pval_b.reserve(num_pairs * sizeof(uint32_t)));
-  CG_CUDA(ctx->seg_start.reserve(num_pairs * sizeof(uint32_t)));
-  uint32_t* d_num = ctx->d_select_count;
-  {
-    StageScope sc(ctx, kStageRayWalk, 1);
-    k_ray_walk<K><<<grid_for(num_rays, 128), 128, 0, s>>>(
-        P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), ctx->ray_offset.as<uint32_t>(), num_rays,
-        L->v, ctx->pkey_a.as<K>(), ctx->pval_a.as<uint32_t>());
+  bool wipe = !ctx->touch_clean;
+  const size_t ord_bytes = L->hash_cap * sizeof(int32_t);
+  if (ctx->touch_ord.cap < ord_bytes) {
+    CG_CUDA(ctx->touch_ord.reserve(ord_bytes));
+    wipe = true;
   }
-  cub::DoubleBuffer<K> dk(ctx->pkey_a.as<K>(), ctx->pkey_b.as<K>());
-  cub::DoubleBuffer<uint32_t> dv(ctx->pval_a.as<uint32_t>(), ctx->pval_b.as<uint32_t>());
-  size_t tmp = 0, tmp2 = 0;
-  CG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, num_pairs, 0, key_bits, s));
-  thrust::counting_iterator<uint32_t> iota(0);
-  CG_CUDA(cub::DeviceSelect::If(nullptr, tmp2, iota, ctx->seg_start.as<uint32_t>(), d_num,
-                                static_cast<int>(num_pairs), SegmentHead<K>{nullptr}, s));
-  CG_CUDA(ctx->cub_tmp.reserve(std::max(tmp, tmp2)));
-  {
-    StageScope sc(ctx, kStagePairSort, 0);
-    CG_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, dk, dv, num_pairs, 0, key_bits, s));
+  if (cap > ctx->touch_cap) {
+    CG_CUDA(ctx->touch_entry.reserve(cap * sizeof(uint32_t)));
+    CG_CUDA(ctx->touch_acc.reserve(cap * kVoxelsPerBlock * sizeof(unsigned long long)));
+    CG_CUDA(ctx->touch_bits.reserve(cap * (kVoxelsPerBlock / 32) * sizeof(uint32_t)));
+    ctx->touch_cap = cap;
+    wipe = true;
   }
-  {
-    StageScope sc(ctx, kStageSegments, 0);
-    CG_CUDA(cub::DeviceSelect::If(ctx->cub_tmp.p, tmp2, iota, ctx->seg_start.as<uint32_t>(), d_num,
-                                  static_cast<int>(num_pairs), SegmentHead<K>{dk.Current()}, s));
+  if (wipe) {
+    CG_CUDA(cudaMemsetAsync(ctx->touch_ord.p, 0xFF, ctx->touch_ord.cap, s));
+    CG_CUDA(cudaMemsetAsync(ctx->touch_acc.p, 0, ctx->touch_acc.cap, s));
+    CG_CUDA(cudaMemsetAsync(ctx->touch_bits.p, 0, ctx->touch_bits.cap, s));
   }
-  {
-    StageScope sc(ctx, kStageVoxelUpdate, 3);
-    const uint32_t long_cap = static_cast<uint32_t>(num_pairs / kLongSegment + 1);
-    const size_t max_items = num_pairs / kLongSub + long_cap + 1;
-    CG_CUDA(ctx->long_list.reserve(long_cap * sizeof(LongSeg)));
-    CG_CUDA(ctx->long_partials.reserve(max_items * sizeof(LongPartial)));
-    CG_CUDA(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(uint32_t), s));
-    CG_CUDA(cudaMemsetAsync(ctx->d_long_counter, 0, sizeof(unsigned long long), s));
-    k_voxel_update<K><<<ctx->num_sms * 8, 256, 0, s>>>(
-        P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), dv.Current(),
-        static_cast<uint32_t>(num_pairs), ctx->seg_start.as<uint32_t>(), d_num,
-        ctx->d_work_counter, ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v,
-        ctx->d_counters);
-    k_long_partials<K><<<ctx->num_sms * 8, 256, 0, s>>>(
-        P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), dv.Current(),
-        ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v,
-        ctx->long_partials.as<LongPartial>());
-    k_long_finish<K><<<ctx->num_sms, 256, 0, s>>>(
-        P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), dv.Current(),
-        ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v,
-        ctx->long_partials.as<LongPartial>());
+  CG_CUDA(cudaMemsetAsync(ctx->d_touch_count, 0, 2 * sizeof(uint32_t), s));  // + pair count
+  ctx->touch_clean = true;
+  return CG_OK;
+}
+
+__global__ void k_collect_walk(LayerView L, const uint32_t* touch_count, CallCounters* c) {
+  c->touched = touch_count[0];
+  c->general_pairs = touch_count[1];
+  c->num_blocks = min(*L.num_blocks, L.max_blocks);
+  const int e = *L.err;
+  c->err = e;
+  if (e & kErrTouchFull) *L.err = e & ~kErrTouchFull;
+}
+
+static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParams& P,
+                             uint32_t num_rays, size_t num_pairs, cg_integrate_stats* stats) {
+  cudaStream_t s = ctx->stream;
+  if (num_pairs >= 0xFFFFFFF0ull) {
+    set_error("too many voxel visits in one group");
+    return CG_ERR_INVALID_ARG;
+  }
+  CG_CUDA(ctx->pkey_a.reserve(num_pairs * sizeof(unsigned long long)));
+  CG_CUDA(ctx->pkey_b.reserve(num_pairs * sizeof(unsigned long long)));
+  const uint32_t ray_bits = static_cast<uint32_t>(std::max(1, ceil_log2(num_rays)));
+  const int weight_bits = ceil_log2(static_cast<uint64_t>(std::min(std::max(P.max_weight, 1.0f), 1.0e9f)) + 1);
+  const int shift = std::max(0, std::min(40, 62 - weight_bits - ceil_log2(uint64_t(num_rays) + 1)));
+  const float acc_scale = ldexpf(1.0f, shift), acc_inv_scale = ldexpf(1.0f, -shift);
+  const uint32_t tail_visits = walk_tail_visits(P);
+  const unsigned walk_grid = std::min<unsigned>(grid_for(num_rays, kWalkThreads),
+                                                static_cast<unsigned>(ctx->num_sms) * 16u);
+  size_t cap = std::max<size_t>(ctx->touch_cap, std::min<size_t>(L->max_blocks, env_size("CG_TOUCH_CAP", 1024)));
+  uint32_t n_touched = 0, n_general = 0;
+  int64_t blocks_after = L->num_blocks;
+  for (;;) {
+    int32_t rc = ensure_touch(ctx, L, cap);
+    if (rc) return rc;
+    ctx->touch_clean = false;
+    TouchView tv{ctx->touch_ord.as<int32_t>(), ctx->touch_entry.as<uint32_t>(),
+                 ctx->touch_acc.as<unsigned long long>(), ctx->touch_bits.as<uint32_t>(),
+                 ctx->d_touch_count, static_cast<uint32_t>(ctx->touch_cap)};
+    {
+      StageScope sc(ctx, kStageWalkAccumulate, 2);
+      k_walk_accumulate<<<walk_grid, kWalkThreads, 0, s>>>(P, ctx->poses.as<float>(),
+                                                           ctx->rays.as<Ray>(), num_rays, L->v, tv,
+                                                           acc_scale, tail_visits);
+      if (L->num_blocks > 0)
+        k_mark_existing<<<ctx->num_sms * 4, 128, 0, s>>>(P, L->v, tv,
+                                                         static_cast<int32_t>(L->num_blocks));
+    }
+    {
+      StageScope sc(ctx, kStageWalkEmit, 2);
+      k_walk_emit<<<walk_grid, kWalkThreads, 0, s>>>(
+          P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), num_rays, L->v, tv, ray_bits,
+          ctx->pkey_a.as<unsigned long long>(), ctx->d_touch_count + 1,
+          static_cast<uint32_t>(num_pairs));
+      k_collect_walk<<<1, 1, 0, s>>>(L->v, ctx->d_touch_count, ctx->d_counters);
+    }
+    CG_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(CallCounters),
+                            cudaMemcpyDeviceToHost, s));
+    CG_CUDA(cudaStreamSynchronize(s));
+    CG_CUDA(cudaGetLastError());
+    n_touched = static_cast<uint32_t>(ctx->h_counters->touched);
+    n_general = static_cast<uint32_t>(ctx->h_counters->general_pairs);
+    blocks_after = ctx->h_counters->num_blocks;
+    if (!(ctx->h_counters->err & kErrTouchFull)) break;
+    // more blocks touched than the scratch holds: grow it (wiped by ensure_touch) and redo
+    cap = 1024;
+    while (cap < n_touched + n_touched / 4) cap <<= 1;
+    if (cap > (size_t(1) << 19)) {
+      set_error("a single job touches %u blocks; split the point cloud", n_touched);
+      return CG_ERR_INVALID_ARG;
+    }
+  }
+  TouchView tv{ctx->touch_ord.as<int32_t>(), ctx->touch_entry.as<uint32_t>(),
+               ctx->touch_acc.as<unsigned long long>(), ctx->touch_bits.as<uint32_t>(),
+               ctx->d_touch_count, static_cast<uint32_t>(ctx->touch_cap)};
+  if (n_general > num_pairs) n_general = static_cast<uint32_t>(num_pairs);  // cannot happen
+  if (n_general > 0) {
+    CG_CUDA(ctx->seg_start.reserve(size_t(n_general) * sizeof(uint32_t)));
+    uint32_t* d_num = ctx->d_select_count;
+    cub::DoubleBuffer<unsigned long long> dk(ctx->pkey_a.as<unsigned long long>(),
+                                             ctx->pkey_b.as<unsigned long long>());
+    const int key_bits = static_cast<int>(ray_bits) + 12 + std::max(1, ceil_log2(n_touched));
+    size_t tmp = 0, tmp2 = 0;
+    CG_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, dk, static_cast<int>(n_general), 0,
+                                           key_bits, s));
+    thrust::counting_iterator<uint32_t> iota(0);
+    CG_CUDA(cub::DeviceSelect::If(nullptr, tmp2, iota, ctx->seg_start.as<uint32_t>(), d_num,
+                                  static_cast<int>(n_general), SegmentHead{nullptr, ray_bits}, s));
+    CG_CUDA(ctx->cub_tmp.reserve(std::max(tmp, tmp2)));
+    {
+      StageScope sc(ctx, kStagePairSort, 0);
+      CG_CUDA(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tmp, dk, static_cast<int>(n_general), 0,
+                                             key_bits, s));
+    }
+    {
+      StageScope sc(ctx, kStageSegments, 0);
+      CG_CUDA(cub::DeviceSelect::If(ctx->cub_tmp.p, tmp2, iota, ctx->seg_start.as<uint32_t>(), d_num,
+                                    static_cast<int>(n_general),
+                                    SegmentHead{dk.Current(), ray_bits}, s));
+    }
+    {
+      StageScope sc(ctx, kStageVoxelUpdate, 3);
+      const uint32_t long_cap = static_cast<uint32_t>(n_general / kLongSegment + 1);
+      const size_t max_items = n_general / kLongSub + long_cap + 1;
+      CG_CUDA(ctx->long_list.reserve(long_cap * sizeof(LongSeg)));
+      CG_CUDA(ctx->long_partials.reserve(max_items * sizeof(LongPartial)));
+      CG_CUDA(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(uint32_t), s));
+      CG_CUDA(cudaMemsetAsync(ctx->d_long_counter, 0, sizeof(unsigned long long), s));
+      k_voxel_update<<<ctx->num_sms * 8, 256, 0, s>>>(
+          P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), ray_bits, n_general,
+          ctx->seg_start.as<uint32_t>(), d_num, ctx->d_work_counter, ctx->d_long_counter,
+          ctx->long_list.as<LongSeg>(), long_cap, L->v, tv);
+      k_long_partials<<<ctx->num_sms * 8, 256, 0, s>>>(
+          P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), ray_bits,
+          ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv,
+          ctx->long_partials.as<LongPartial>());
+      k_long_finish<<<ctx->num_sms, 256, 0, s>>>(
+          P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), ray_bits,
+          ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv,
+          ctx->long_partials.as<LongPartial>());
+    }
+  }
+  if (n_touched > 0) {
+    StageScope sc(ctx, kStageFinalize, 1);
+    k_finalize_blocks<<<n_touched, 256, 0, s>>>(P, L->v, tv, acc_inv_scale);
   }
   CG_CUDA(cudaGetLastError());
+  ctx->touch_clean = true;
+  L->num_blocks = blocks_after;  // the next group of the job must see these blocks as existing
+  if (stats) {
+    stats->blocks_touched += n_touched;
+    stats->general_updates += n_general;
+  }
   return CG_OK;
 }
 
@@ -895,22 +1196,11 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
     }
   }
   if (num_rays == 0 || num_pairs == 0) return CG_OK;
-  int hash_bits = 0;
-  while ((size_t(1) << hash_bits) < L->hash_cap) ++hash_bits;
-  const int key_bits = hash_bits + 12;
-  int32_t rc = key_bits <= 32 ? run_back_half<uint32_t>(ctx, L, P, num_rays, num_pairs, key_bits)
-                              : run_back_half<uint64_t>(ctx, L, P, num_rays, num_pairs, key_bits);
-  if (rc) return rc;
   if (stats) {
     stats->rays += num_rays;
     stats->voxel_updates += num_pairs;
-    // blocks_touched is accumulated on the device (counters->touched) per group
-    CG_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(CallCounters),
-                            cudaMemcpyDeviceToHost, s));
-    CG_CUDA(cudaStreamSynchronize(s));
-    stats->blocks_touched += ctx->h_counters->touched;
   }
-  return CG_OK;
+  return run_back_half(ctx, L, P, num_rays, num_pairs, stats);
 }
 
 static int32_t integrate_job(cg_layer* L, const cg_integrator_config* cfg, size_t F,

@@ -24,9 +24,10 @@ int32_t cuda_fail(cudaError_t e, const char* what) {
 }
 
 const char* stage_name(int s) {
-  static const char* names[kNumStages] = {"point_keys",  "bundle_sort", "bundle_scan", "bundle_fold",
-                                          "ray_scan",    "ray_walk",    "pair_sort",   "segments", "voxel_update",
-                                          "merge_mark",  "merge_resample", "transfer"};
+  static const char* names[kNumStages] = {
+      "point_keys", "bundle_sort",  "bundle_scan", "bundle_fold",  "ray_scan",   "walk_accumulate",
+      "walk_emit",  "pair_sort",    "segments",    "voxel_update", "finalize",   "merge_mark",
+      "merge_resample", "transfer"};
   return (s >= 0 && s < kNumStages) ? names[s] : "?";
 }
 
@@ -225,6 +226,7 @@ int32_t cg_context_create(int32_t device, void* stream, cg_context** out) {
   CG_CUDA(cudaMalloc(&ctx->d_work_counter, sizeof(uint32_t)));
   CG_CUDA(cudaMalloc(&ctx->d_long_counter, sizeof(unsigned long long)));
   CG_CUDA(cudaMalloc(&ctx->d_select_count, sizeof(uint32_t)));
+  CG_CUDA(cudaMalloc(&ctx->d_touch_count, 2 * sizeof(uint32_t)));
   CG_CUDA(cudaMemsetAsync(ctx->d_select_count, 0, sizeof(uint32_t), ctx->stream));
   *out = ctx;
   return CG_OK;
@@ -237,7 +239,7 @@ int32_t cg_context_destroy(cg_context* ctx) {
   DevBuf* bufs[] = {&ctx->points, &ctx->colors, &ctx->poses, &ctx->frame_base, &ctx->key_a,
                     &ctx->key_b, &ctx->val_a, &ctx->val_b, &ctx->flags, &ctx->scan,
                     &ctx->cub_tmp, &ctx->rays, &ctx->ray_count, &ctx->ray_offset, &ctx->sorted_pts, &ctx->pkey_a,
-                    &ctx->pkey_b, &ctx->pval_a, &ctx->pval_b, &ctx->seg_start, &ctx->long_list, &ctx->long_partials, &ctx->cand_keys, &ctx->cand_list,
+                    &ctx->pkey_b, &ctx->touch_ord, &ctx->touch_entry, &ctx->touch_acc, &ctx->touch_bits, &ctx->seg_start, &ctx->long_list, &ctx->long_partials, &ctx->cand_keys, &ctx->cand_list,
                     &ctx->stage_a, &ctx->stage_b, &ctx->stage_c};
   for (DevBuf* b : bufs) b->release();
   drain_events(ctx);
@@ -245,6 +247,7 @@ int32_t cg_context_destroy(cg_context* ctx) {
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_select_count) cudaFree(ctx->d_select_count);
+  if (ctx->d_touch_count) cudaFree(ctx->d_touch_count);
   if (ctx->d_work_counter) cudaFree(ctx->d_work_counter);
   if (ctx->d_long_counter) cudaFree(ctx->d_long_counter);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

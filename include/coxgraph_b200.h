@@ -85,6 +85,7 @@ typedef struct cg_integrate_stats {
   uint64_t points_in;       /* N */
   uint64_t rays;            /* rays cast (bundles for MERGED) */
   uint64_t voxel_updates;   /* (ray, voxel) visits */
+  uint64_t general_updates; /* visits replayed in order (voxels inside the truncation band) */
   uint64_t blocks_touched;  /* distinct blocks visited by any ray of the call */
   uint64_t blocks_allocated;/* new blocks */
 } cg_integrate_stats;

@@ -58,6 +58,18 @@ def test_batch_split_path(gpu_ctx, monkeypatch):
     gl.close()
 
 
+def test_touch_scratch_growth(monkeypatch):
+    """The per-call touch scratch starts too small, overflows, grows and the walks are redone."""
+    from coxgraph_b200 import Context
+    monkeypatch.setenv("CG_TOUCH_CAP", "8")
+    ctx = Context(0)          # fresh context: its scratch starts at the tiny capacity
+    frames = util.small_frames(2, stride=8)
+    got, ref, gl = _run_both(ctx, frames)
+    util.compare_layers(got, ref, "touch growth")
+    gl.close()
+    ctx.close()
+
+
 @pytest.mark.parametrize("over", [
     dict(use_const_weight=0),
     dict(voxel_carving_enabled=0),
