@@ -138,11 +138,10 @@ __global__ void k_gather_sorted(const uint64_t* __restrict__ keys, const uint32_
 
 // MergedTsdfIntegrator::integrateVoxel, first half: the reference's *sequential* weighted mean and
 // colour blend over the points of a bundle (bit-exact: the merged point decides which voxels and
-// blocks the ray visits).  Persistent groups of 4 lanes: a group owns one bundle at a time
-// (fetched from a global counter), loads 32 points with 8 coalesced 64-byte reads, then runs the
-// recurrence over them from shuffled operands; a warp advances 8 independent recurrences.
-constexpr int kFoldGroup = 4;
-constexpr int kFoldChunk = 32;  // points per group per round (8 per lane)
+// blocks the ray visits).  Persistent lanes: every lane owns one bundle at a time (handed out
+// through a warp-aggregated atomic) and runs the recurrence over its points, which lie next to
+// each other in `sorted`; the next point is in flight while the current one is folded.
+constexpr int kFoldInner = 8;  // points per lane between two work-fetch rounds
 
 __global__ void __launch_bounds__(128)
 k_fold_bundles(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t total,
@@ -150,28 +149,28 @@ k_fold_bundles(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t t
                const float4* __restrict__ sorted, uint32_t* work_counter, Ray* __restrict__ folded) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
-  const int sub = lane & (kFoldGroup - 1);
-  const int gbase = lane & ~(kFoldGroup - 1);
+  const unsigned lt = (1u << lane) - 1u;
   const uint32_t nb = *num_heads;
   uint32_t cur = 0, end = 0, my_b = 0, frame_clr = 0;
   bool finished = false, clearing = false;
+  float4 q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   FoldState st;
   fold_reset(st);
   for (;;) {
-    const bool need = !finished && cur >= end;  // uniform within a group
-    const unsigned m = __ballot_sync(full, need && sub == 0);
+    const bool need = !finished && cur >= end;
+    const unsigned m = __ballot_sync(full, need);
     if (m) {
       const int leader = __ffs(m) - 1;
       uint32_t base = 0;
       if (lane == leader) base = atomicAdd(work_counter, static_cast<uint32_t>(__popc(m)));
       base = __shfl_sync(full, base, leader);
       if (need) {
-        const uint32_t b = base + __popc(m & ((1u << gbase) - 1u));
+        const uint32_t b = base + __popc(m & lt);
         if (b < nb) {
           const uint32_t start = heads[b];
           const uint64_t key = keys[start];
           if (key == kInvalidPointKey) {  // sentinel bundle of dropped points
-            if (sub == 0) folded[b].frame_clr = kNoRay;
+            folded[b].frame_clr = kNoRay;
             cur = end = 0;                // fetch again on the next round
           } else {
             cur = start;
@@ -181,6 +180,7 @@ k_fold_bundles(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t t
             frame_clr = static_cast<uint32_t>(key >> kBundleFrameShift) |
                         (clearing ? 0x80000000u : 0u);
             fold_reset(st);
+            q = sorted[cur];
           }
         } else {
           finished = true;
@@ -188,46 +188,27 @@ k_fold_bundles(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t t
       }
     }
     if (__all_sync(full, finished)) break;
-    const bool work = !finished && cur < end;
-    // a clearing bundle only uses its first point: do not stream the rest
-    const uint32_t n = work ? min(static_cast<uint32_t>(clearing ? kFoldGroup : kFoldChunk),
-                                  end - cur)
-                            : 0u;
-    float4 q[kFoldChunk / kFoldGroup];
-#pragma unroll
-    for (int u = 0; u < kFoldChunk / kFoldGroup; ++u) {
-      const uint32_t o = u * kFoldGroup + sub;
-      q[u] = (o < n) ? sorted[cur + o] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    }
-    const uint32_t n_max = __reduce_max_sync(full, n);
-    bool done = false;
-#pragma unroll
-    for (int t = 0; t < kFoldChunk; ++t) {
-      if (t < static_cast<int>(n_max)) {  // warp-uniform: shuffles are executed by all lanes
-        const int src = gbase + (t & (kFoldGroup - 1));
-        const float4 v = q[t / kFoldGroup];
-        const float px = __shfl_sync(full, v.x, src), py = __shfl_sync(full, v.y, src);
-        const float pz = __shfl_sync(full, v.z, src), pw = __shfl_sync(full, v.w, src);
-        if (t < static_cast<int>(n) && !done) {
-          const float w = voxel_weight(P, pz);
-          if (!(w < kEps)) {
-            fold_step(st, px, py, pz, __float_as_uint(pw), w);
-            done = clearing;  // only the first point of a clearing bundle is used
-          }
+#pragma unroll 1
+    for (int t = 0; t < kFoldInner; ++t) {
+      if (cur < end) {
+        const float4 p = q;
+        if (cur + 1 < end) q = sorted[cur + 1];
+        ++cur;
+        const float w = voxel_weight(P, p.z);
+        if (!(w < kEps)) {
+          fold_step(st, p.x, p.y, p.z, __float_as_uint(p.w), w);
+          if (clearing) cur = end;  // only the first point of a clearing bundle is used
         }
-      }
-    }
-    if (work) {
-      cur = done ? end : cur + n;
-      if (cur >= end && sub == 0) {
-        Ray r;
-        r.px = st.m.x;  // camera frame; k_bundle_rays moves it to the global frame
-        r.py = st.m.y;
-        r.pz = st.m.z;
-        r.weight = st.W;
-        r.color = fold_color(st);
-        r.frame_clr = frame_clr;
-        folded[my_b] = r;
+        if (cur >= end) {
+          Ray r;
+          r.px = st.m.x;  // camera frame; k_bundle_rays moves it to the global frame
+          r.py = st.m.y;
+          r.pz = st.m.z;
+          r.weight = st.W;
+          r.color = fold_color(st);
+          r.frame_clr = frame_clr;
+          folded[my_b] = r;
+        }
       }
     }
   }
@@ -361,6 +342,29 @@ __device__ __forceinline__ uint32_t touch_ordinal(const TouchView& Tv, int entry
 
 constexpr int kWalkThreads = 128;
 
+// Per-CTA direct-mapped cache block index -> ordinal in shared memory.  The rays of a CTA are
+// neighbours (bundles are sorted by voxel), so they cross the same few blocks; a hit replaces the
+// two dependent L2 round trips of the hash probe and the ordinal lookup.  One 64-bit word per
+// entry (tag << 20 | ordinal), written with a single store, so a reader never sees a torn pair.
+// Ordinals are immutable for the duration of the job.
+constexpr int kBlockCacheSize = 512;
+__device__ __forceinline__ bool block_cache_tag(int bx, int by, int bz, unsigned long long& tag,
+                                                uint32_t& idx) {
+  const uint32_t ux = static_cast<uint32_t>(bx + 8192), uy = static_cast<uint32_t>(by + 8192),
+                 uz = static_cast<uint32_t>(bz + 8192);
+  if ((ux | uy | uz) >> 14) return false;  // far from the origin: not cached
+  tag = ((static_cast<unsigned long long>(uz) << 28) | (static_cast<unsigned long long>(uy) << 14) |
+         ux) + 1ull;
+  idx = (ux + 7u * uy + 61u * uz) & (kBlockCacheSize - 1);
+  return true;
+}
+// dynamic work distribution: each warp takes the next batch of 32 consecutive rays
+__device__ __forceinline__ uint32_t next_ray_batch(uint32_t* work_counter, int lane) {
+  uint32_t b = 0;
+  if (lane == 0) b = atomicAdd(work_counter, 1u);
+  return __shfl_sync(0xFFFFFFFFu, b, 0);
+}
+
 struct WalkRay {
   RayCaster rc;
   Ray ray;
@@ -420,11 +424,16 @@ __device__ __forceinline__ Visit make_visit(const IntegratorParams& P, const flo
 __global__ void __launch_bounds__(kWalkThreads)
 k_walk_accumulate(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
                   uint32_t num_rays, LayerView L, TouchView Tv, float acc_scale,
-                  uint32_t tail_visits) {
+                  uint32_t tail_visits, uint32_t* work_counter) {
+  __shared__ unsigned long long cache[kBlockCacheSize];
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
-  for (uint32_t r0 = blockIdx.x * blockDim.x; r0 < num_rays; r0 += gridDim.x * blockDim.x) {
-    WalkRay w = load_walk_ray(P, poses, rays, r0 + threadIdx.x, num_rays, L.err);
+  for (int i = threadIdx.x; i < kBlockCacheSize; i += blockDim.x) cache[i] = 0ull;
+  __syncthreads();
+  for (;;) {
+    const uint32_t r0 = next_ray_batch(work_counter, lane) * 32u;
+    if (r0 >= num_rays) break;
+    WalkRay w = load_walk_ray(P, poses, rays, r0 + lane, num_rays, L.err);
     RayCaster& rc = w.rc;
     const unsigned long long wq =
         __float2ull_rn(fminf(fmaxf(w.ray.weight, 0.0f), P.max_weight) * acc_scale);
@@ -441,8 +450,18 @@ k_walk_accumulate(IntegratorParams P, const float* __restrict__ poses, const Ray
           lbx = bx;
           lby = by;
           lbz = bz;
-          const int entry = L.insert_entry(pack_block_key(bx, by, bz));
-          vbase = touch_ordinal(Tv, entry, L.err) << 12;
+          unsigned long long tag = 0ull;
+          uint32_t ci = 0;
+          const bool cacheable = block_cache_tag(bx, by, bz, tag, ci);
+          const unsigned long long cw = cacheable ? cache[ci] : 0ull;
+          if (cacheable && (cw >> 20) == tag) {
+            vbase = static_cast<uint32_t>(cw & 0xFFFFFu) << 12;
+          } else {
+            const int entry = L.insert_entry(pack_block_key(bx, by, bz));
+            const uint32_t ord = touch_ordinal(Tv, entry, L.err);
+            vbase = ord << 12;
+            if (cacheable) cache[ci] = (tag << 20) | ord;
+          }
         }
         vid = vbase | static_cast<uint32_t>((rc.cx & 15) + 16 * ((rc.cy & 15) + 16 * (rc.cz & 15)));
         if (w.remaining <= tail_visits) {
@@ -499,8 +518,12 @@ constexpr int kEmitBuf = 256;
 __global__ void __launch_bounds__(kWalkThreads)
 k_walk_emit(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
             uint32_t num_rays, LayerView L, TouchView Tv, uint32_t ray_bits,
-            unsigned long long* __restrict__ out, uint32_t* out_count, uint32_t out_cap) {
+            unsigned long long* __restrict__ out, uint32_t* out_count, uint32_t out_cap,
+            uint32_t* work_counter) {
   __shared__ unsigned long long buf[kWalkThreads / 32][kEmitBuf];
+  __shared__ unsigned long long cache[kBlockCacheSize];
+  for (int i = threadIdx.x; i < kBlockCacheSize; i += blockDim.x) cache[i] = 0ull;
+  __syncthreads();
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
@@ -515,8 +538,10 @@ k_walk_emit(IntegratorParams P, const float* __restrict__ poses, const Ray* __re
     __syncwarp();
     cnt = 0;
   };
-  for (uint32_t r0 = blockIdx.x * blockDim.x; r0 < num_rays; r0 += gridDim.x * blockDim.x) {
-    const uint32_t r = r0 + threadIdx.x;
+  for (;;) {
+    const uint32_t r0 = next_ray_batch(work_counter, lane) * 32u;
+    if (r0 >= num_rays) break;
+    const uint32_t r = r0 + lane;
     WalkRay w = load_walk_ray(P, poses, rays, r, num_rays, nullptr);
     RayCaster& rc = w.rc;
     int lbx = 0x7FFFFFFF, lby = 0, lbz = 0;
@@ -533,9 +558,20 @@ k_walk_emit(IntegratorParams P, const float* __restrict__ poses, const Ray* __re
           lbx = bx;
           lby = by;
           lbz = bz;
-          const int entry = L.find_entry(pack_block_key(bx, by, bz));
-          known = entry >= 0;
-          vbase = known ? static_cast<uint32_t>(Tv.ord[entry]) << 12 : 0u;
+          unsigned long long tag = 0ull;
+          uint32_t ci = 0;
+          const bool cacheable = block_cache_tag(bx, by, bz, tag, ci);
+          const unsigned long long cw = cacheable ? cache[ci] : 0ull;
+          if (cacheable && (cw >> 20) == tag) {
+            known = true;
+            vbase = static_cast<uint32_t>(cw & 0xFFFFFu) << 12;
+          } else {
+            const int entry = L.find_entry(pack_block_key(bx, by, bz));
+            known = entry >= 0;
+            const uint32_t ord = known ? static_cast<uint32_t>(Tv.ord[entry]) : 0u;
+            vbase = ord << 12;
+            if (cacheable && known) cache[ci] = (tag << 20) | ord;
+          }
         }
         vid = vbase | static_cast<uint32_t>((rc.cx & 15) + 16 * ((rc.cy & 15) + 16 * (rc.cz & 15)));
         g = known && ((Tv.general[vid >> 5] >> (vid & 31)) & 1u);
@@ -687,10 +723,13 @@ struct LongPartial {
   uint32_t not_free;      // any update with sdf < trunc (not a pure free-space observation)
 };
 
-// One warp per general voxel (R5 updateTsdfVoxel replayed over the voxel's update list);
-// segments are handed out dynamically, kSegBatch at a time.
-constexpr uint32_t kSegBatch = 8;
-__global__ void __launch_bounds__(256)
+// General voxels, short update lists: persistent lanes, one voxel per lane at a time, the
+// reference's updateTsdfVoxel applied update by update (R5; bit-identical to the sequential
+// oracle).  Lists of kWideSegment updates or more go to a list for the warp-cooperative kernels
+// below (k_long_partials / k_long_finish).
+constexpr uint32_t kWideSegment = 96;
+constexpr int kUpdateInner = 4;
+__global__ void __launch_bounds__(128)
 k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
                const unsigned long long* __restrict__ keys, uint32_t ray_bits, uint32_t num_pairs,
                const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ num_segs,
@@ -698,37 +737,67 @@ k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* _
                uint32_t long_cap, LayerView L, TouchView Tv) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
   const uint32_t ns = *num_segs;
   const uint32_t ray_mask = (1u << ray_bits) - 1u;
+  uint32_t cur = 0, end = 0;
+  bool finished = false;
+  VoxelRef vr;
+  vr.dp = vr.wp = nullptr;
+  vr.cp = nullptr;
+  vr.center = V3{0.0f, 0.0f, 0.0f};
+  VoxelState st{0.0f, 0.0f, 0u};
   for (;;) {
-    uint32_t s0 = 0;
-    if (lane == 0) s0 = atomicAdd(work_counter, kSegBatch);
-    s0 = __shfl_sync(full, s0, 0);
-    if (s0 >= ns) break;
-    const uint32_t s1 = min(ns, s0 + kSegBatch);
-    for (uint32_t s = s0; s < s1; ++s) {
-      const uint32_t start = seg_start[s];
-      const uint32_t end = (s + 1 < ns) ? seg_start[s + 1] : num_pairs;
-      const VoxelRef vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[start] >> ray_bits));
-      if (vr.slot < 0) continue;  // pool exhausted; error already flagged
-      if (end - start >= kLongSegment) {
-        if (lane == 0) {
-          const uint32_t nsub = (end - start + kLongSub - 1) / kLongSub;
-          // one 64-bit atomic hands out the list index (high word) and the sub-block range (low)
-          const unsigned long long old =
-              atomicAdd(long_counter, (1ull << 32) | static_cast<unsigned long long>(nsub));
-          const uint32_t idx = static_cast<uint32_t>(old >> 32);
-          if (idx < long_cap) long_list[idx] = LongSeg{start, end, static_cast<uint32_t>(old), 0u};
+    const bool need = !finished && cur >= end;
+    const unsigned m = __ballot_sync(full, need);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(work_counter, static_cast<uint32_t>(__popc(m)));
+      base = __shfl_sync(full, base, leader);
+      if (need) {
+        const uint32_t sidx = base + __popc(m & lt);
+        if (sidx < ns) {
+          const uint32_t start = seg_start[sidx];
+          const uint32_t stop = (sidx + 1 < ns) ? seg_start[sidx + 1] : num_pairs;
+          vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[start] >> ray_bits));
+          cur = end = 0;
+          if (vr.slot >= 0) {  // else: pool exhausted, error already flagged
+            if (stop - start >= kWideSegment) {
+              const uint32_t nsub =
+                  stop - start >= kLongSegment ? (stop - start + kLongSub - 1) / kLongSub : 0u;
+              // one 64-bit atomic hands out the list index (high word) and the sub-block range
+              const unsigned long long old =
+                  atomicAdd(long_counter, (1ull << 32) | static_cast<unsigned long long>(nsub));
+              const uint32_t idx = static_cast<uint32_t>(old >> 32);
+              if (idx < long_cap)
+                long_list[idx] = LongSeg{start, stop, static_cast<uint32_t>(old), 0u};
+            } else {
+              cur = start;
+              end = stop;
+              st.d = *vr.dp;
+              st.w = *vr.wp;
+              st.c = *vr.cp;
+            }
+          }
+        } else {
+          finished = true;
         }
-        continue;
       }
-      float D = *vr.dp, W = *vr.wp;
-      uint32_t C = *vr.cp;
-      replay_segment(P, poses, rays, keys, ray_mask, start, end, vr.center, lane, D, W, C);
-      if (lane == 0) {
-        *vr.dp = D;
-        *vr.wp = W;
-        *vr.cp = C;
+    }
+    if (__all_sync(full, finished)) break;
+#pragma unroll 1
+    for (int t = 0; t < kUpdateInner; ++t) {
+      if (cur < end) {
+        const Ray ray = rays[static_cast<uint32_t>(keys[cur]) & ray_mask];
+        const float* T = poses + 7 * (ray.frame_clr & 0x7FFFFFFFu);
+        update_tsdf_voxel(P, V3{T[4], T[5], T[6]}, V3{ray.px, ray.py, ray.pz}, vr.center, ray.color,
+                          ray.weight, st);
+        if (++cur >= end) {
+          *vr.dp = st.d;
+          *vr.wp = st.w;
+          *vr.cp = st.c;
+        }
       }
     }
   }
@@ -800,9 +869,10 @@ k_long_finish(IntegratorParams P, const float* __restrict__ poses, const Ray* __
     const VoxelRef vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[seg.start] >> ray_bits));
     float D = *vr.dp, W = *vr.wp;
     uint32_t C = *vr.cp;
-    const uint32_t nsub = (seg.end - seg.start + kLongSub - 1) / kLongSub;
+    const bool is_long = seg.end - seg.start >= kLongSegment;
+    const uint32_t nsub = is_long ? (seg.end - seg.start + kLongSub - 1) / kLongSub : 0u;
     float sum = 0.0f;
-    bool not_free = false;
+    bool not_free = !is_long;
     for (uint32_t t = 0; t < nsub; ++t) {  // fixed order: deterministic
       const LongPartial p = partials[seg.item_base + t];
       sum += p.sum_w;
@@ -954,7 +1024,7 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
   const float acc_scale = ldexpf(1.0f, shift), acc_inv_scale = ldexpf(1.0f, -shift);
   const uint32_t tail_visits = walk_tail_visits(P);
   const unsigned walk_grid = std::min<unsigned>(grid_for(num_rays, kWalkThreads),
-                                                static_cast<unsigned>(ctx->num_sms) * 16u);
+                                                static_cast<unsigned>(ctx->num_sms) * 10u);
   size_t cap = std::max<size_t>(ctx->touch_cap, std::min<size_t>(L->max_blocks, env_size("CG_TOUCH_CAP", 1024)));
   uint32_t n_touched = 0, n_general = 0;
   int64_t blocks_after = L->num_blocks;
@@ -965,11 +1035,12 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
     TouchView tv{ctx->touch_ord.as<int32_t>(), ctx->touch_entry.as<uint32_t>(),
                  ctx->touch_acc.as<unsigned long long>(), ctx->touch_bits.as<uint32_t>(),
                  ctx->d_touch_count, static_cast<uint32_t>(ctx->touch_cap)};
+    CG_CUDA(cudaMemsetAsync(ctx->d_walk_counters, 0, 2 * sizeof(uint32_t), s));
     {
       StageScope sc(ctx, kStageWalkAccumulate, 2);
-      k_walk_accumulate<<<walk_grid, kWalkThreads, 0, s>>>(P, ctx->poses.as<float>(),
-                                                           ctx->rays.as<Ray>(), num_rays, L->v, tv,
-                                                           acc_scale, tail_visits);
+      k_walk_accumulate<<<walk_grid, kWalkThreads, 0, s>>>(
+          P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), num_rays, L->v, tv, acc_scale,
+          tail_visits, ctx->d_walk_counters);
       if (L->num_blocks > 0)
         k_mark_existing<<<ctx->num_sms * 4, 128, 0, s>>>(P, L->v, tv,
                                                          static_cast<int32_t>(L->num_blocks));
@@ -979,7 +1050,7 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
       k_walk_emit<<<walk_grid, kWalkThreads, 0, s>>>(
           P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), num_rays, L->v, tv, ray_bits,
           ctx->pkey_a.as<unsigned long long>(), ctx->d_touch_count + 1,
-          static_cast<uint32_t>(num_pairs));
+          static_cast<uint32_t>(num_pairs), ctx->d_walk_counters + 1);
       k_collect_walk<<<1, 1, 0, s>>>(L->v, ctx->d_touch_count, ctx->d_counters);
     }
     CG_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(CallCounters),
@@ -1028,13 +1099,13 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
     }
     {
       StageScope sc(ctx, kStageVoxelUpdate, 3);
-      const uint32_t long_cap = static_cast<uint32_t>(n_general / kLongSegment + 1);
+      const uint32_t long_cap = static_cast<uint32_t>(n_general / kWideSegment + 1);
       const size_t max_items = n_general / kLongSub + long_cap + 1;
       CG_CUDA(ctx->long_list.reserve(long_cap * sizeof(LongSeg)));
       CG_CUDA(ctx->long_partials.reserve(max_items * sizeof(LongPartial)));
       CG_CUDA(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(uint32_t), s));
       CG_CUDA(cudaMemsetAsync(ctx->d_long_counter, 0, sizeof(unsigned long long), s));
-      k_voxel_update<<<ctx->num_sms * 8, 256, 0, s>>>(
+      k_voxel_update<<<ctx->num_sms * 8, 128, 0, s>>>(
           P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), ray_bits, n_general,
           ctx->seg_start.as<uint32_t>(), d_num, ctx->d_work_counter, ctx->d_long_counter,
           ctx->long_list.as<LongSeg>(), long_cap, L->v, tv);
@@ -1042,7 +1113,7 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
           P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), ray_bits,
           ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv,
           ctx->long_partials.as<LongPartial>());
-      k_long_finish<<<ctx->num_sms, 256, 0, s>>>(
+      k_long_finish<<<ctx->num_sms * 4, 256, 0, s>>>(
           P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), ray_bits,
           ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv,
           ctx->long_partials.as<LongPartial>());
@@ -1149,7 +1220,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
       k_gather_sorted<<<grid_for(total, 256), 256, 0, s>>>(
           dk.Current(), dv.Current(), static_cast<uint32_t>(total), pts, cols,
           ctx->sorted_pts.as<float4>());
-      k_fold_bundles<<<ctx->num_sms * 16, 128, 0, s>>>(
+      k_fold_bundles<<<ctx->num_sms * 12, 128, 0, s>>>(
           P, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
           ctx->sorted_pts.as<float4>(), ctx->d_work_counter, ctx->rays.as<Ray>());
       k_bundle_rays<<<grid_for(upper, 256), 256, 0, s>>>(P, ctx->poses.as<float>(), d_num,
