@@ -207,6 +207,7 @@ struct cg_context {
   // per-call touch set (integrate.cu "back half"): kept all-clear between calls
   cg::DevBuf touch_ord, touch_entry, touch_acc, touch_bits;
   uint32_t* d_touch_count = nullptr;  // [0] blocks touched, [1] general (voxel, ray) keys emitted
+  uint32_t* d_class_count = nullptr;    // bundle size-class histogram + scatter cursors
   uint32_t* d_walk_counters = nullptr;  // dynamic ray-batch counters of the two walks
   size_t touch_cap = 0;               // blocks the scratch holds
   bool touch_clean = false;

@@ -228,6 +228,7 @@ int32_t cg_context_create(int32_t device, void* stream, cg_context** out) {
   CG_CUDA(cudaMalloc(&ctx->d_select_count, sizeof(uint32_t)));
   CG_CUDA(cudaMalloc(&ctx->d_touch_count, 2 * sizeof(uint32_t)));
   CG_CUDA(cudaMalloc(&ctx->d_walk_counters, 2 * sizeof(uint32_t)));
+  CG_CUDA(cudaMalloc(&ctx->d_class_count, 128 * sizeof(uint32_t)));
   CG_CUDA(cudaMemsetAsync(ctx->d_select_count, 0, sizeof(uint32_t), ctx->stream));
   *out = ctx;
   return CG_OK;
@@ -250,6 +251,7 @@ int32_t cg_context_destroy(cg_context* ctx) {
   if (ctx->d_select_count) cudaFree(ctx->d_select_count);
   if (ctx->d_touch_count) cudaFree(ctx->d_touch_count);
   if (ctx->d_walk_counters) cudaFree(ctx->d_walk_counters);
+  if (ctx->d_class_count) cudaFree(ctx->d_class_count);
   if (ctx->d_work_counter) cudaFree(ctx->d_work_counter);
   if (ctx->d_long_counter) cudaFree(ctx->d_long_counter);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
