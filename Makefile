@@ -11,7 +11,9 @@ LIB  = coxgraph_b200/lib/libcoxgraph_b200.so
 HDRS = $(SRC)/cg_math.cuh $(SRC)/cg_internal.cuh include/coxgraph_b200.h
 OBJS = $(OBJ)/layer.o $(OBJ)/integrate.o $(OBJ)/merge.o $(OBJ)/exchange.o $(OBJ)/selftest.o
 
-all: $(LIB) oracle
+HOSTCHK = build/host_api_check
+
+all: $(LIB) oracle $(HOSTCHK)
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -23,6 +25,11 @@ $(LIB): $(OBJS)
 
 oracle:
 	$(MAKE) -C oracle -s
+
+# C++ host API driver (tests/test_host_cpp.py): plain g++, links only the C ABI
+$(HOSTCHK): tests/host/host_api_check.cc coxgraph_b200/host/coxgraph_b200.hpp include/coxgraph_b200.h $(LIB)
+	g++ -std=c++17 -O1 -Wall -Wextra tests/host/host_api_check.cc -o $@ -Lcoxgraph_b200/lib \
+	    -lcoxgraph_b200 -Wl,-rpath,'$$ORIGIN/../coxgraph_b200/lib'
 
 clean:
 	rm -rf build coxgraph_b200/lib oracle/_build

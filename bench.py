@@ -38,53 +38,51 @@ BLOCK_BYTES = 49152
 
 # ----------------------------------------------------------------------------- helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread
+    every 2 ms (the timed region is tens of ms, too short for `nvidia-smi -lms`)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while True:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                bits = int(get_reasons(h))
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+                if self._stop.wait(0.002):
+                    break
+        except Exception as e:  # noqa: BLE001 - reported in the JSON line
+            self.err = f"nvml unavailable: {e}"
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.gpu)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for k, nme in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
-                        reasons.add(nme)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(np.max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self.thread:
+            self.thread.join(timeout=2)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+               "sm_max_mhz": self.max_mhz, "samples": len(self.sm),
+               "reasons": sorted(self.reasons)}
+        if self.err:
+            out["reasons"] = out["reasons"] + [self.err]
+        return out
 
 
 def measured_peak_gbs():
@@ -201,7 +199,8 @@ def run_ours(args, rank, world, local_rank):
     # merge block counts, for every pool submap
     for e in pool:
         if args.profile_mode:
-            e.update(bytes_integrate=0, blocks_in=0, bytes_merge=0, voxels_in=0, rays=0, pairs=0)
+            e.update(bytes_integrate=0, blocks_in=0, bytes_merge=0, voxels_in=0, rays=0, pairs=0,
+                     general=0)
             continue
         submap.clear()
         touched = 0
@@ -213,6 +212,7 @@ def run_ours(args, rank, world, local_rank):
         submap.clear()
         st = integ.integrateBatch(e["poses"], e["d_pts"], e["d_cols"], e["offs"])
         e["rays"], e["pairs"] = int(st.rays), int(st.voxel_updates)
+        e["general"] = int(st.general_updates)
         e["blocks_in"] = submap.num_blocks
         glob.clear()
         ms = mergeLayerAintoLayerB(submap, e["T_M_S"], glob)
@@ -256,18 +256,32 @@ def run_ours(args, rank, world, local_rank):
         if ev:
             ev[2].record(stream)
 
-    def step_e2e(e):
-        submap.clear()
-        integ.integrateBatch(e["poses"], e["h_pts"], e["h_cols"], e["offs"])   # H2D inside
-        mergeLayerAintoLayerB(submap, e["T_M_S"], glob)
-        idx, vox, fl = submap.download(out=(out_idx, out_vox, out_flags))       # D2H result
-        return len(idx)
+    def run_e2e(entries):
+        """Every step: H2D of its inputs from pinned host memory (cg_stage_batch_async, double
+        buffered: the copy of step k+1 is queued before step k is fused), fuse, merge, D2H of the
+        fused submap in voxblox layout.  Returns the D2H bytes."""
+        d2h = 0
+        if entries:
+            integ.stageBatch(0, entries[0]["h_pts"], entries[0]["h_cols"])
+        for k, e in enumerate(entries):
+            if k + 1 < len(entries):
+                nxt = entries[k + 1]
+                integ.stageBatch((k + 1) % 2, nxt["h_pts"], nxt["h_cols"])
+            submap.clear()
+            integ.integrateStaged(k % 2, e["poses"], e["offs"])
+            mergeLayerAintoLayerB(submap, e["T_M_S"], glob)
+            idx, vox, fl = submap.download(out=(out_idx, out_vox, out_flags))
+            d2h += len(idx) * (BLOCK_BYTES + 13)
+        return d2h
 
     results = {}
     for leg in ("device", "e2e"):
         glob.clear()
-        for s in range(args.warmup):
-            (step_device if leg == "device" else step_e2e)(pool[s % pool_n])
+        if leg == "device":
+            for s in range(args.warmup):
+                step_device(pool[s % pool_n])
+        else:
+            run_e2e([pool[s % pool_n] for s in range(args.warmup)])
         sampler = ClockSampler(local_rank)
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -279,12 +293,11 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
         ev_a.record(stream)
         d2h = 0
-        for k in range(args.steps):
-            e = pool[(args.warmup + k) % pool_n]
-            if leg == "device":
-                step_device(e, evs[k])
-            else:
-                d2h += step_e2e(e) * (BLOCK_BYTES + 13)
+        if leg == "device":
+            for k in range(args.steps):
+                step_device(pool[(args.warmup + k) % pool_n], evs[k])
+        else:
+            d2h = run_e2e([pool[(args.warmup + k) % pool_n] for k in range(args.steps)])
         ev_b.record(stream)
         barrier()
         clocks = sampler.stop()
@@ -334,13 +347,12 @@ def run_ours(args, rank, world, local_rank):
         used_dev = [pool[(args.warmup + k) % pool_n] for k in range(args.steps)]
         peak, peak_src = measured_peak_gbs()
         prof = dv["profile"]
-        per_frame = ("point_keys", "bundle_sort", "bundle_scan", "bundle_fold")
-        top = max((k for k in prof if k != "transfer"), key=lambda k: prof[k][0])
+        # dominant stage among the library's OWN kernels; every stage runs once per step (all
+        # 25 frames of the submap go through each kernel together)
+        top = max((k for k in prof if k != "transfer" and prof[k][1] > 0), key=lambda k: prof[k][0])
         is_merge = top.startswith("merge")
-        calls_per_step = FRAMES_PER_SUBMAP if top in per_frame else 1
-        top_ms_per_launch = prof[top][0] / (args.steps * calls_per_step)
-        alg_bytes = (dv["bytes_merge"] if is_merge else dv["bytes_int"]) / (args.steps *
-                                                                            calls_per_step)
+        top_ms_per_launch = prof[top][0] / args.steps
+        alg_bytes = (dv["bytes_merge"] if is_merge else dv["bytes_int"]) / args.steps
         achieved = alg_bytes / (top_ms_per_launch * 1e-3) / 1e9
         traffic = None
         try:
@@ -377,6 +389,7 @@ def run_ours(args, rank, world, local_rank):
             "stages_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "per_step": {"rays": sum(e["rays"] for e in used_dev) / args.steps,
                          "voxel_updates": sum(e["pairs"] for e in used_dev) / args.steps,
+                         "ordered_updates": sum(e["general"] for e in used_dev) / args.steps,
                          "blocks_in": sum(e["blocks_in"] for e in used_dev) / args.steps},
             "clocks": dv["clocks"], "clocks_e2e": ee["clocks"],
             "cpu_baseline": cpu,
@@ -392,7 +405,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pool", type=int, default=6, help="distinct submaps kept resident")

@@ -200,6 +200,36 @@ class TsdfIntegrator:
         return self.last_stats
 
 
+def _stage_batch(self, slot, points_C, colors):
+    """Queue the host->device copy of a later integrateStaged(slot, ...) job (pinned numpy arrays;
+    returns at once).  Keep the arrays alive until that job has returned."""
+    pts = np.ascontiguousarray(points_C, np.float32).reshape(-1, 3)
+    cols = np.ascontiguousarray(colors, np.uint8).reshape(-1, 4)
+    if len(pts) != len(cols):
+        raise ValueError("points_C and colors differ in length")
+    capi.check(capi.load().cg_stage_batch_async(self.layer.ctx._h, int(slot), _ptr(pts), _ptr(cols),
+                                                len(pts)))
+    self._staged = getattr(self, "_staged", {})
+    self._staged[int(slot)] = (pts, cols)
+
+
+def _integrate_staged(self, slot, poses, frame_offsets, freespace_points=False):
+    """integrateBatch on the inputs staged in `slot`."""
+    P = np.ascontiguousarray(poses, np.float32).reshape(-1, 7)
+    offs = np.ascontiguousarray(frame_offsets, np.uint64).reshape(-1)
+    if len(offs) != len(P) + 1:
+        raise ValueError("frame_offsets must have F+1 entries")
+    capi.check(capi.load().cg_integrate_batch_staged(
+        self.layer._h, C.byref(self.config), len(P), _ptr(P), int(slot), _ptr(offs),
+        int(freespace_points), C.byref(self.last_stats)))
+    getattr(self, "_staged", {}).pop(int(slot), None)
+    return self.last_stats
+
+
+TsdfIntegrator.stageBatch = _stage_batch
+TsdfIntegrator.integrateStaged = _integrate_staged
+
+
 def mergeLayerAintoLayerB(layer_A, T_B_A, layer_B):
     """voxblox::mergeLayerAintoLayerB(layer_A, T_B_A, &layer_B); returns MergeStats."""
     T = np.ascontiguousarray(T_B_A, np.float32).reshape(7)

@@ -91,6 +91,9 @@ SYMBOLS = {
                                        C.c_int32, C.POINTER(IntegrateStats)]),
     "cg_integrate_batch_device": (C.c_int32, [_P, C.POINTER(IntegratorConfig), C.c_size_t, _P, _P,
                                               _P, _P, C.c_int32, C.POINTER(IntegrateStats)]),
+    "cg_stage_batch_async": (C.c_int32, [_P, C.c_int32, _P, _P, C.c_size_t]),
+    "cg_integrate_batch_staged": (C.c_int32, [_P, C.POINTER(IntegratorConfig), C.c_size_t, _P,
+                                              C.c_int32, _P, C.c_int32, C.POINTER(IntegrateStats)]),
     "cg_merge_layer_into_layer": (C.c_int32, [_P, _P, _P, C.POINTER(MergeStats)]),
     "cg_project_submaps": (C.c_int32, [_P, _P, C.c_size_t, _P, C.POINTER(MergeStats)]),
     "cg_block_owner": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

@@ -196,6 +196,14 @@ struct cg_context {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t copy_stream = nullptr;       // pipelined host->device transfers (lazy)
+  std::vector<cudaEvent_t> copy_events;
+  void* h_tables = nullptr;                 // pinned + mapped: poses / frame offsets of the job
+  size_t h_tables_cap = 0;
+  cg::DevBuf stage_pts[2], stage_cols[2];   // cg_stage_batch_async double buffer
+  cudaEvent_t stage_ready[2] = {nullptr, nullptr};
+  size_t stage_points[2] = {0, 0};
+  const float* group_poses = nullptr;       // device poses of the group being fused
   int num_sms = 148;
   cg::CallCounters* h_counters = nullptr;  // pinned
   cg::CallCounters* d_counters = nullptr;

@@ -36,6 +36,27 @@
 
 namespace cg {
 
+// Device-side fill used instead of cudaMemsetAsync on the compute stream: a memset may be
+// executed by a copy engine, where it would queue behind the (large) host->device transfers of
+// the pipelined batch path and stall the kernels that follow it.
+__global__ void k_fill_words(uint32_t* __restrict__ p, uint32_t v, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    p[i] = v;
+}
+__global__ void k_copy_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+static inline cudaError_t fill_bytes(void* p, int byte, size_t bytes, cudaStream_t s) {
+  const size_t n = bytes / 4;
+  if (n == 0) return cudaSuccess;
+  const uint32_t v = 0x01010101u * static_cast<uint32_t>(byte & 0xFF);
+  const unsigned grid = static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 148 * 8));
+  k_fill_words<<<grid, 256, 0, s>>>(static_cast<uint32_t*>(p), v, n);
+  return cudaGetLastError();
+}
+
 struct Ray {           // 24 B
   float px, py, pz;    // merged point, global frame
   float weight;        // merged weight
@@ -63,28 +84,34 @@ __device__ __forceinline__ V3 load_point(const float* pts, size_t i) {
   return V3{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
 }
 
-// frame of global slot g (offs has F+1 entries)
-__device__ __forceinline__ int frame_of(const uint64_t* __restrict__ offs, int F, uint64_t g) {
-  int lo = 0, hi = F;  // offs[lo] <= g < offs[hi]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (offs[mid] <= g) lo = mid; else hi = mid;
+// Frames of one group: offs points at the group's first entry of the job's offset table (F + 1
+// entries are read), base = offs[0]; slots and point indices are relative to the group.
+struct FrameTable {
+  const uint64_t* offs;
+  uint64_t base;
+  int F;
+  __device__ __forceinline__ uint64_t start(int f) const { return offs[f] - base; }
+  __device__ __forceinline__ int frame_of(uint64_t g) const {
+    int lo = 0, hi = F;  // start(lo) <= g < start(hi)
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (start(mid) <= g) lo = mid; else hi = mid;
+    }
+    return lo;
   }
-  return lo;
-}
+};
 
 // ------------------------------------------------------------------ front half
 // slot g enumerates (frame, visit rank k); vals = global point index
-__global__ void k_point_keys(IntegratorParams P, const float* __restrict__ poses,
-                             const uint64_t* __restrict__ offs, int F,
+__global__ void k_point_keys(IntegratorParams P, const float* __restrict__ poses, FrameTable ft,
                              const float* __restrict__ pts, uint64_t total,
                              uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
                              int32_t* err) {
   const uint64_t g = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
   if (g >= total) return;
-  const int f = frame_of(offs, F, g);
-  const uint64_t base = offs[f];
-  const int n = static_cast<int>(offs[f + 1] - base);
+  const int f = ft.frame_of(g);
+  const uint64_t base = ft.start(f);
+  const int n = static_cast<int>(ft.start(f + 1) - base);
   const int i = order_index(static_cast<int>(g - base), n, P.order_mode);
   const V3 pc = load_point(pts, base + i);
   bool clearing = false;
@@ -433,21 +460,19 @@ __global__ void k_bundle_rays(IntegratorParams P, const float* __restrict__ pose
 // SIMPLE: one ray per valid point, in (frame, visit rank) order
 struct ValidSlot {
   IntegratorParams P;
-  const uint64_t* offs;
-  int F;
+  FrameTable ft;
   const float* pts;
   __device__ __forceinline__ bool operator()(uint32_t g) const {
-    const int f = frame_of(offs, F, g);
-    const uint64_t base = offs[f];
-    const int n = static_cast<int>(offs[f + 1] - base);
+    const int f = ft.frame_of(g);
+    const uint64_t base = ft.start(f);
+    const int n = static_cast<int>(ft.start(f + 1) - base);
     bool clearing;
     return point_valid(P, load_point(pts, base + order_index(static_cast<int>(g - base), n,
                                                              P.order_mode)), &clearing);
   }
 };
 
-__global__ void k_simple_rays(IntegratorParams P, const float* __restrict__ poses,
-                              const uint64_t* __restrict__ offs, int F,
+__global__ void k_simple_rays(IntegratorParams P, const float* __restrict__ poses, FrameTable ft,
                               const uint32_t* __restrict__ slots,
                               const uint32_t* __restrict__ num_slots, const float* __restrict__ pts,
                               const uint32_t* __restrict__ cols, Ray* __restrict__ rays,
@@ -455,9 +480,9 @@ __global__ void k_simple_rays(IntegratorParams P, const float* __restrict__ pose
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= *num_slots) return;
   const uint32_t g = slots[r];
-  const int f = frame_of(offs, F, g);
-  const uint64_t base = offs[f];
-  const int n = static_cast<int>(offs[f + 1] - base);
+  const int f = ft.frame_of(g);
+  const uint64_t base = ft.start(f);
+  const int n = static_cast<int>(ft.start(f + 1) - base);
   const size_t i = base + order_index(static_cast<int>(g - base), n, P.order_mode);
   const V3 pc = load_point(pts, i);
   bool clearing = false;
@@ -919,8 +944,8 @@ struct LongPartial {
 };
 
 // General voxels, short update lists: persistent lanes, one voxel per lane at a time, the
-// reference's updateTsdfVoxel applied update by update (R5; bit-identical to the sequential
-// oracle).  Lists of kWideSegment updates or more go to a list for the warp-cooperative kernels
+// reference's updateTsdfVoxel applied update by update (R5, in the reference's own operation
+// order).  Lists of kWideSegment updates or more go to a list for the warp-cooperative kernels
 // below (k_long_partials / k_long_finish).
 constexpr uint32_t kWideSegment = 96;
 constexpr int kUpdateInner = 4;
@@ -1186,11 +1211,11 @@ static int32_t ensure_touch(cg_context* ctx, const cg_layer* L, size_t cap) {
     wipe = true;
   }
   if (wipe) {
-    CG_CUDA(cudaMemsetAsync(ctx->touch_ord.p, 0xFF, ctx->touch_ord.cap, s));
-    CG_CUDA(cudaMemsetAsync(ctx->touch_acc.p, 0, ctx->touch_acc.cap, s));
-    CG_CUDA(cudaMemsetAsync(ctx->touch_bits.p, 0, ctx->touch_bits.cap, s));
+    CG_CUDA(fill_bytes(ctx->touch_ord.p, 0xFF, ctx->touch_ord.cap, s));
+    CG_CUDA(fill_bytes(ctx->touch_acc.p, 0, ctx->touch_acc.cap, s));
+    CG_CUDA(fill_bytes(ctx->touch_bits.p, 0, ctx->touch_bits.cap, s));
   }
-  CG_CUDA(cudaMemsetAsync(ctx->d_touch_count, 0, 2 * sizeof(uint32_t), s));  // + pair count
+  CG_CUDA(fill_bytes(ctx->d_touch_count, 0, 2 * sizeof(uint32_t), s));  // + pair count
   ctx->touch_clean = true;
   return CG_OK;
 }
@@ -1230,11 +1255,11 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
     TouchView tv{ctx->touch_ord.as<int32_t>(), ctx->touch_entry.as<uint32_t>(),
                  ctx->touch_acc.as<unsigned long long>(), ctx->touch_bits.as<uint32_t>(),
                  ctx->d_touch_count, static_cast<uint32_t>(ctx->touch_cap)};
-    CG_CUDA(cudaMemsetAsync(ctx->d_walk_counters, 0, 2 * sizeof(uint32_t), s));
+    CG_CUDA(fill_bytes(ctx->d_walk_counters, 0, 2 * sizeof(uint32_t), s));
     {
       StageScope sc(ctx, kStageWalkAccumulate, 2);
       k_walk_accumulate<<<walk_grid, kWalkThreads, 0, s>>>(
-          P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), num_rays, L->v, tv, acc_scale,
+          P, ctx->group_poses, ctx->rays.as<Ray>(), num_rays, L->v, tv, acc_scale,
           tail_visits, ctx->d_walk_counters);
       if (L->num_blocks > 0)
         k_mark_existing<<<ctx->num_sms * 4, 128, 0, s>>>(P, L->v, tv,
@@ -1243,7 +1268,7 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
     {
       StageScope sc(ctx, kStageWalkEmit, 2);
       k_walk_emit<<<walk_grid, kWalkThreads, 0, s>>>(
-          P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), num_rays, L->v, tv, ray_bits,
+          P, ctx->group_poses, ctx->rays.as<Ray>(), num_rays, L->v, tv, ray_bits,
           ctx->pkey_a.as<unsigned long long>(), ctx->d_touch_count + 1,
           static_cast<uint32_t>(num_pairs), ctx->d_walk_counters + 1);
       k_collect_walk<<<1, 1, 0, s>>>(L->v, ctx->d_touch_count, ctx->d_counters);
@@ -1298,18 +1323,18 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
       const size_t max_items = n_general / kLongSub + long_cap + 1;
       CG_CUDA(ctx->long_list.reserve(long_cap * sizeof(LongSeg)));
       CG_CUDA(ctx->long_partials.reserve(max_items * sizeof(LongPartial)));
-      CG_CUDA(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(uint32_t), s));
-      CG_CUDA(cudaMemsetAsync(ctx->d_long_counter, 0, sizeof(unsigned long long), s));
+      CG_CUDA(fill_bytes(ctx->d_work_counter, 0, sizeof(uint32_t), s));
+      CG_CUDA(fill_bytes(ctx->d_long_counter, 0, sizeof(unsigned long long), s));
       k_voxel_update<<<ctx->num_sms * 8, 128, 0, s>>>(
-          P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), ray_bits, n_general,
+          P, ctx->group_poses, ctx->rays.as<Ray>(), dk.Current(), ray_bits, n_general,
           ctx->seg_start.as<uint32_t>(), d_num, ctx->d_work_counter, ctx->d_long_counter,
           ctx->long_list.as<LongSeg>(), long_cap, L->v, tv);
       k_long_partials<<<ctx->num_sms * 8, 256, 0, s>>>(
-          P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), ray_bits,
+          P, ctx->group_poses, ctx->rays.as<Ray>(), dk.Current(), ray_bits,
           ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv,
           ctx->long_partials.as<LongPartial>());
       k_long_finish<<<ctx->num_sms * 4, 256, 0, s>>>(
-          P, ctx->poses.as<float>(), ctx->rays.as<Ray>(), dk.Current(), ray_bits,
+          P, ctx->group_poses, ctx->rays.as<Ray>(), dk.Current(), ray_bits,
           ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv,
           ctx->long_partials.as<LongPartial>());
     }
@@ -1347,8 +1372,6 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   CG_CUDA(ctx->rays.reserve(upper * sizeof(Ray)));
   CG_CUDA(ctx->ray_count.reserve(upper * sizeof(uint32_t)));
   CG_CUDA(ctx->ray_offset.reserve(upper * sizeof(uint32_t)));
-  CG_CUDA(ctx->poses.reserve(F * 7 * sizeof(float)));
-  CG_CUDA(ctx->frame_base.reserve((F + 1) * sizeof(uint64_t)));
   CG_CUDA(ctx->scan.reserve(upper * sizeof(uint32_t)));  // bundle heads / valid slots
   const bool merged = cfg->method == CG_METHOD_MERGED;
   if (merged) {
@@ -1365,13 +1388,12 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   cub::DoubleBuffer<uint32_t> dv(ctx->val_a.as<uint32_t>(), ctx->val_b.as<uint32_t>());
   thrust::counting_iterator<uint32_t> iota(0);
   uint32_t* d_num = ctx->d_select_count;
-  // group-relative frame offsets on the device
-  std::vector<uint64_t> rel(F + 1);
-  for (size_t f = 0; f <= F; ++f) rel[f] = offs[f0 + f] - offs[f0];
+  // the job's poses and frame offsets were uploaded once by integrate_job
   const float* pts = d_points + 3 * offs[f0];
   const uint32_t* cols = reinterpret_cast<const uint32_t*>(d_colors) + offs[f0];
-  const uint64_t* d_offs = ctx->frame_base.as<uint64_t>();
-  ValidSlot valid{P, d_offs, static_cast<int>(F), pts};
+  const FrameTable ft{ctx->frame_base.as<uint64_t>() + f0, offs[f0] - offs[0], static_cast<int>(F)};
+  ctx->group_poses = ctx->poses.as<float>() + 7 * f0;
+  ValidSlot valid{P, ft, pts};
   size_t tmp_sort = 0, tmp_sel = 0, tmp_scan = 0;
   if (merged) {
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, dk, dv, total, 0, bundle_bits, s);
@@ -1386,17 +1408,13 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   CG_CUDA(ctx->cub_tmp.reserve(std::max(tmp_sort, std::max(tmp_sel, tmp_scan))));
   {
     StageScope sc(ctx, kStageTransfer, 0);
-    CG_CUDA(cudaMemcpyAsync(ctx->poses.p, h_poses + 7 * f0, F * 7 * sizeof(float),
-                            cudaMemcpyHostToDevice, s));
-    CG_CUDA(cudaMemcpyAsync(ctx->frame_base.p, rel.data(), (F + 1) * sizeof(uint64_t),
-                            cudaMemcpyHostToDevice, s));
-    CG_CUDA(cudaMemsetAsync(ctx->ray_count.p, 0, upper * sizeof(uint32_t), s));
+    CG_CUDA(fill_bytes(ctx->ray_count.p, 0, upper * sizeof(uint32_t), s));
   }
   if (merged) {
     {
       StageScope sc(ctx, kStagePointKeys, 1);
       k_point_keys<<<grid_for(total, 256), 256, 0, s>>>(
-          P, ctx->poses.as<float>(), d_offs, static_cast<int>(F), pts, total,
+          P, ctx->group_poses, ft, pts, total,
           ctx->key_a.as<uint64_t>(), ctx->val_a.as<uint32_t>(), L->v.err);
     }
     {
@@ -1411,7 +1429,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
     }
     {
       StageScope sc(ctx, kStageFold, 6);
-      CG_CUDA(cudaMemsetAsync(ctx->d_class_count, 0, 2 * kSizeClasses * sizeof(uint32_t), s));
+      CG_CUDA(fill_bytes(ctx->d_class_count, 0, 2 * kSizeClasses * sizeof(uint32_t), s));
       k_gather_sorted<<<grid_for(total, 256), 256, 0, s>>>(
           dk.Current(), dv.Current(), static_cast<uint32_t>(total), pts, cols,
           ctx->sorted_pts.as<float4>());
@@ -1431,7 +1449,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
           P, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
           ctx->sorted_pts.as<float4>(), ctx->d_class_count, ctx->ray_offset.as<uint32_t>(),
           ctx->rays.as<Ray>());
-      k_bundle_rays<<<grid_for(upper, 256), 256, 0, s>>>(P, ctx->poses.as<float>(), d_num,
+      k_bundle_rays<<<grid_for(upper, 256), 256, 0, s>>>(P, ctx->group_poses, d_num,
                                                          ctx->rays.as<Ray>(),
                                                          ctx->ray_count.as<uint32_t>());
     }
@@ -1443,7 +1461,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
     }
     StageScope sc(ctx, kStageFold, 1);
     k_simple_rays<<<grid_for(total, 256), 256, 0, s>>>(
-        P, ctx->poses.as<float>(), d_offs, static_cast<int>(F), ctx->scan.as<uint32_t>(), d_num, pts,
+        P, ctx->group_poses, ft, ctx->scan.as<uint32_t>(), d_num, pts,
         cols, ctx->rays.as<Ray>(), ctx->ray_count.as<uint32_t>());
   }
   {
@@ -1482,9 +1500,48 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   return run_back_half(ctx, L, P, num_rays, num_pairs, stats);
 }
 
+// The job's poses and frame offsets (relative to its first point) go up once per job, through a
+// pinned, device-mapped host buffer and a copy KERNEL: an H2D memcpy would be queued on the copy
+// engine behind the point data that the staging / pipelined paths have in flight.
+static int32_t upload_frame_tables(cg_context* ctx, size_t F, const float* h_poses,
+                                   const uint64_t* offs, cudaStream_t stream) {
+  const size_t pose_words = F * 7, off_words = (F + 1) * 2;
+  const size_t bytes = (pose_words + off_words) * sizeof(uint32_t);
+  if (bytes > ctx->h_tables_cap) {
+    if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
+    ctx->h_tables = nullptr;
+    ctx->h_tables_cap = 0;
+    CG_CUDA(cudaHostAlloc(&ctx->h_tables, bytes * 2, cudaHostAllocMapped));
+    ctx->h_tables_cap = bytes * 2;
+  }
+  CG_CUDA(ctx->poses.reserve(pose_words * sizeof(float)));
+  CG_CUDA(ctx->frame_base.reserve((F + 1) * sizeof(uint64_t)));
+  uint32_t* h = static_cast<uint32_t*>(ctx->h_tables);
+  memcpy(h, h_poses, pose_words * sizeof(float));
+  uint64_t* ho = reinterpret_cast<uint64_t*>(h + pose_words + (pose_words & 1));
+  for (size_t f = 0; f <= F; ++f) ho[f] = offs[f] - offs[0];
+  void* d_alias = nullptr;
+  CG_CUDA(cudaHostGetDevicePointer(&d_alias, ctx->h_tables, 0));
+  const uint32_t* src = static_cast<const uint32_t*>(d_alias);
+  k_copy_words<<<grid_for(pose_words, 256), 256, 0, stream>>>(ctx->poses.as<uint32_t>(), src,
+                                                              pose_words);
+  k_copy_words<<<grid_for(off_words, 256), 256, 0, stream>>>(
+      ctx->frame_base.as<uint32_t>(), src + pose_words + (pose_words & 1), off_words);
+  CG_CUDA(cudaGetLastError());
+  return CG_OK;
+}
+
+// Frames grouped for a pipelined host->device transfer: group g covers frames
+// [bounds[g], bounds[g+1]) and may start once ready[g] has fired on the copy stream.
+struct TransferPlan {
+  std::vector<size_t> bounds;
+  std::vector<cudaEvent_t> ready;
+};
+
 static int32_t integrate_job(cg_layer* L, const cg_integrator_config* cfg, size_t F,
                              const float* h_poses, const float* d_points, const uint8_t* d_colors,
-                             const uint64_t* offs, int freespace, cg_integrate_stats* stats) {
+                             const uint64_t* offs, int freespace, cg_integrate_stats* stats,
+                             const TransferPlan* plan = nullptr) {
   if (cfg->method == CG_METHOD_FAST) {
     set_error("method FAST is order- and wall-clock-dependent in the reference and has no "
               "deterministic device form; use MERGED or SIMPLE");
@@ -1507,13 +1564,28 @@ static int32_t integrate_job(cg_layer* L, const cg_integrator_config* cfg, size_
     stats->points_in = offs[F] - offs[0];
   }
   const size_t max_group_points = env_size("CG_MAX_GROUP_POINTS", size_t(48) << 20);
+  // poses and frame offsets (relative to the job's first point) go up once per job; with a
+  // transfer plan the caller already queued them on the copy stream ahead of the point data
+  if (!plan) {
+    int32_t urc = upload_frame_tables(L->ctx, F, h_poses, offs, L->ctx->stream);
+    if (urc) return urc;
+  }
   int32_t rc = CG_OK;
-  size_t f0 = 0;
-  while (f0 < F && rc == CG_OK) {
-    size_t f1 = f0 + 1;
-    while (f1 < F && offs[f1 + 1] - offs[f0] <= max_group_points) ++f1;
-    rc = integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, f1, stats);
-    f0 = f1;
+  if (plan) {
+    // the copies of group g+1.. proceed on the copy stream while group g is fused
+    for (size_t g = 0; g + 1 < plan->bounds.size() && rc == CG_OK; ++g) {
+      CG_CUDA(cudaStreamWaitEvent(L->ctx->stream, plan->ready[g], 0));
+      rc = integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, plan->bounds[g],
+                           plan->bounds[g + 1], stats);
+    }
+  } else {
+    size_t f0 = 0;
+    while (f0 < F && rc == CG_OK) {
+      size_t f1 = f0 + 1;
+      while (f1 < F && offs[f1 + 1] - offs[f0] <= max_group_points) ++f1;
+      rc = integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, f1, stats);
+      f0 = f1;
+    }
   }
   const int32_t rc2 = finish_call(L, nullptr);
   if (stats) stats->blocks_allocated = L->num_blocks - blocks_before;
@@ -1584,12 +1656,100 @@ int32_t cg_integrate_batch(cg_layer* L, const cg_integrator_config* cfg, size_t 
     set_error("cg_integrate: null argument");
     return CG_ERR_INVALID_ARG;
   }
-  int32_t rc = stage_inputs(L->ctx, pts + 3 * first, cols + 4 * first, total);
-  if (rc) return rc;
   std::vector<uint64_t> rel(F + 1);
   for (size_t f = 0; f <= F; ++f) rel[f] = offs[f] - first;
-  return cg_integrate_batch_device(L, cfg, F, poses, L->ctx->points.as<float>(),
-                                   L->ctx->colors.as<uint8_t>(), rel.data(), freespace, stats);
+  cg_context* ctx = L->ctx;
+  // Optional (CG_H2D_CHUNK_POINTS > 0): the host->device copy is cut into groups of frames on a
+  // second stream so that fusing group g overlaps the copy of group g+1.  Off by default: at the
+  // C2 size every group costs ~0.5 ms of latency-bound kernel tails, more than the overlap wins
+  // (measured); overlapping across jobs (cg_stage_batch_async) is what pays.
+  const size_t chunk_points = env_size("CG_H2D_CHUNK_POINTS", 0);
+  if (F > 1 && total > 2 * chunk_points && chunk_points > 0) {
+    for (size_t f = 0; f < F; ++f)
+      if (offs[f + 1] < offs[f]) {
+        set_error("frame_offsets must be non-decreasing");
+        return CG_ERR_INVALID_ARG;
+      }
+    CG_CUDA(cudaSetDevice(ctx->device));
+    CG_CUDA(ctx->points.reserve(total * 3 * sizeof(float)));
+    CG_CUDA(ctx->colors.reserve(total * 4));
+    if (!ctx->copy_stream)
+      CG_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    TransferPlan plan;
+    plan.bounds.push_back(0);
+    for (size_t f = 1; f <= F; ++f)
+      if (f == F || rel[f] - rel[plan.bounds.back()] >= chunk_points) plan.bounds.push_back(f);
+    const size_t G = plan.bounds.size() - 1;
+    int32_t urc = upload_frame_tables(ctx, F, poses, rel.data(), ctx->stream);
+    if (urc) return urc;
+    while (ctx->copy_events.size() < G) {
+      cudaEvent_t e;
+      CG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->copy_events.push_back(e);
+    }
+    for (size_t g = 0; g < G; ++g) {
+      const size_t a = rel[plan.bounds[g]], b = rel[plan.bounds[g + 1]];
+      CG_CUDA(cudaMemcpyAsync(ctx->points.as<float>() + 3 * a, pts + 3 * (first + a),
+                              (b - a) * 3 * sizeof(float), cudaMemcpyHostToDevice,
+                              ctx->copy_stream));
+      CG_CUDA(cudaMemcpyAsync(ctx->colors.as<uint8_t>() + 4 * a, cols + 4 * (first + a),
+                              (b - a) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CG_CUDA(cudaEventRecord(ctx->copy_events[g], ctx->copy_stream));
+      plan.ready.push_back(ctx->copy_events[g]);
+    }
+    const int32_t rc = integrate_job(L, cfg, F, poses, ctx->points.as<float>(),
+                                     ctx->colors.as<uint8_t>(), rel.data(), freespace, stats, &plan);
+    // the staging buffers are reused by the next call: the copies must have drained even if the
+    // job failed early
+    cudaStreamSynchronize(ctx->copy_stream);
+    return rc;
+  }
+  int32_t rc = stage_inputs(ctx, pts + 3 * first, cols + 4 * first, total);
+  if (rc) return rc;
+  return cg_integrate_batch_device(L, cfg, F, poses, ctx->points.as<float>(),
+                                   ctx->colors.as<uint8_t>(), rel.data(), freespace, stats);
+}
+
+int32_t cg_stage_batch_async(cg_context* ctx, int32_t slot, const float* pts, const uint8_t* cols,
+                             size_t n) {
+  if (!ctx || slot < 0 || slot > 1 || (n && (!pts || !cols))) {
+    set_error("cg_stage_batch_async: invalid argument");
+    return CG_ERR_INVALID_ARG;
+  }
+  CG_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream)
+    CG_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (!ctx->stage_ready[slot])
+    CG_CUDA(cudaEventCreateWithFlags(&ctx->stage_ready[slot], cudaEventDisableTiming));
+  CG_CUDA(ctx->stage_pts[slot].reserve(n * 3 * sizeof(float)));
+  CG_CUDA(ctx->stage_cols[slot].reserve(n * 4));
+  if (n) {
+    CG_CUDA(cudaMemcpyAsync(ctx->stage_pts[slot].p, pts, n * 3 * sizeof(float),
+                            cudaMemcpyHostToDevice, ctx->copy_stream));
+    CG_CUDA(cudaMemcpyAsync(ctx->stage_cols[slot].p, cols, n * 4, cudaMemcpyHostToDevice,
+                            ctx->copy_stream));
+  }
+  CG_CUDA(cudaEventRecord(ctx->stage_ready[slot], ctx->copy_stream));
+  ctx->stage_points[slot] = n;
+  return CG_OK;
+}
+
+int32_t cg_integrate_batch_staged(cg_layer* L, const cg_integrator_config* cfg, size_t F,
+                                  const float* poses, int32_t slot, const uint64_t* offs,
+                                  int32_t freespace, cg_integrate_stats* stats) {
+  if (!L || !cfg || !poses || !offs || slot < 0 || slot > 1 || !L->ctx->stage_ready[slot]) {
+    set_error("cg_integrate_batch_staged: invalid argument (nothing staged in this slot?)");
+    return CG_ERR_INVALID_ARG;
+  }
+  cg_context* ctx = L->ctx;
+  if (offs[0] != 0 || offs[F] != ctx->stage_points[slot]) {
+    set_error("cg_integrate_batch_staged: frame_offsets must cover exactly the %zu staged points",
+              ctx->stage_points[slot]);
+    return CG_ERR_INVALID_ARG;
+  }
+  CG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->stage_ready[slot], 0));
+  return cg_integrate_batch_device(L, cfg, F, poses, ctx->stage_pts[slot].as<float>(),
+                                   ctx->stage_cols[slot].as<uint8_t>(), offs, freespace, stats);
 }
 
 int32_t cg_integrate_pointcloud_device(cg_layer* L, const cg_integrator_config* cfg,

@@ -254,6 +254,14 @@ int32_t cg_context_destroy(cg_context* ctx) {
   if (ctx->d_class_count) cudaFree(ctx->d_class_count);
   if (ctx->d_work_counter) cudaFree(ctx->d_work_counter);
   if (ctx->d_long_counter) cudaFree(ctx->d_long_counter);
+  for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    ctx->stage_pts[i].release();
+    ctx->stage_cols[i].release();
+    if (ctx->stage_ready[i]) cudaEventDestroy(ctx->stage_ready[i]);
+  }
+  if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return CG_OK;

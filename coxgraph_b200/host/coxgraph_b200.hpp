@@ -1,0 +1,270 @@
+// coxgraph_b200.hpp — C++ host-side mirror of the reference-facing interface of the hot path,
+// header-only, on top of the C ABI (include/coxgraph_b200.h, libcoxgraph_b200.so).
+//
+// The reference (mfkiwl/coxgraph) is C++ and reaches this path through voxblox's classes; this
+// header keeps their names, argument order and meaning so that the call sites read the same:
+//   tsdf_integrator_->integratePointCloud(T_G_C, *points_C, *colors, false)
+//       coxgraph/include/coxgraph/map_comm/tsdf_recover.h:75
+//   tsdf_map_->getTsdfLayerPtr()->removeAllBlocks()                    tsdf_recover.h:62
+//   voxblox::mergeLayerAintoLayerB(layer, submap->getPose(), combined) coxgraph/src/client/map_server.cpp:67-69
+//   SubmapCollection::getProjectedMap()   via coxgraph/src/server/visualizer/server_visualizer.cpp:123-126
+// Types are layout-compatible with the ones the reference passes (Eigen::Vector3f = 3 floats,
+// voxblox::Color = 4 x uint8, kindr QuatTransformation = unit quaternion w,x,y,z + translation),
+// so an adapter inside a voxblox build is a reinterpret of the containers' data pointers
+// (INTEGRATION.md shows it).
+//
+// Error behaviour: the reference aborts through glog CHECK / LOG(FATAL) on this path
+// (e.g. coxgraph/include/coxgraph/utils/msg_converter.h:110-111).  Here every failed C-ABI call
+// goes through fatal(), which prints cg_last_error() and aborts; set_fatal_handler() lets a host
+// turn that into an exception instead.  There is no CPU fallback anywhere.
+#ifndef COXGRAPH_B200_HPP_
+#define COXGRAPH_B200_HPP_
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/coxgraph_b200.h"
+
+namespace coxgraph_b200 {
+
+using FloatingPoint = float;
+struct Point {  // Eigen::Matrix<float, 3, 1>
+  FloatingPoint x, y, z;
+};
+struct Color {  // voxblox::Color
+  uint8_t r = 0, g = 0, b = 0, a = 255;
+};
+using Pointcloud = std::vector<Point>;  // voxblox::AlignedVector<Point>
+using Colors = std::vector<Color>;
+struct BlockIndex {  // voxblox::BlockIndex (Eigen::Vector3i)
+  int32_t x, y, z;
+};
+using BlockIndexList = std::vector<BlockIndex>;
+using TsdfVoxel = cg_tsdf_voxel;  // {float distance; float weight; Color color}
+static_assert(sizeof(Point) == 12 && sizeof(Color) == 4 && sizeof(TsdfVoxel) == 12 &&
+                  sizeof(BlockIndex) == 12,
+              "layouts must match the reference's types");
+
+// kindr::minimal::QuatTransformationTemplate<float>: p_G = q * p_C + t
+struct Transformation {
+  FloatingPoint qw = 1, qx = 0, qy = 0, qz = 0, tx = 0, ty = 0, tz = 0;
+  const float* data() const { return &qw; }
+};
+
+// ---- error handling -------------------------------------------------------------------
+using FatalHandler = std::function<void(int32_t status, const char* message)>;
+inline FatalHandler& fatal_handler() {
+  static FatalHandler h = [](int32_t status, const char* message) {
+    std::fprintf(stderr, "coxgraph_b200: fatal error %d: %s\n", static_cast<int>(status), message);
+    std::abort();  // what glog CHECK does in the reference
+  };
+  return h;
+}
+inline void set_fatal_handler(FatalHandler h) { fatal_handler() = std::move(h); }
+struct Error : std::runtime_error {
+  int32_t status;
+  Error(int32_t s, const char* m) : std::runtime_error(m), status(s) {}
+};
+inline void throw_on_error() {
+  set_fatal_handler([](int32_t s, const char* m) { throw Error(s, m); });
+}
+inline void check(int32_t status) {
+  if (status != CG_OK) fatal_handler()(status, cg_last_error());
+}
+
+// ---- context: one per GPU / process rank ----------------------------------------------
+class Context {
+ public:
+  explicit Context(int device = 0, void* cuda_stream = nullptr) {
+    check(cg_context_create(device, cuda_stream, &ctx_));
+  }
+  ~Context() {
+    if (ctx_) cg_context_destroy(ctx_);
+  }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  cg_context* handle() const { return ctx_; }
+  void synchronize() const { check(cg_context_synchronize(ctx_)); }
+  uint64_t kernelLaunches() const { return cg_context_kernel_launches(ctx_); }
+
+ private:
+  cg_context* ctx_ = nullptr;
+};
+
+// ---- voxblox::Block<TsdfVoxel> as handed across the boundary ---------------------------
+struct TsdfBlock {
+  BlockIndex block_index;
+  bool has_data = false, updated = false;
+  std::vector<TsdfVoxel> voxels;  // 4096, linear index x + 16 (y + 16 z)
+};
+
+// ---- voxblox::Layer<TsdfVoxel> ----------------------------------------------------------
+class TsdfLayer {
+ public:
+  // Layer(voxel_size, voxels_per_side); max_blocks sizes the block pool in HBM
+  TsdfLayer(const Context& ctx, FloatingPoint voxel_size, size_t voxels_per_side = 16,
+            size_t max_blocks = 4096) {
+    check(cg_layer_create(ctx.handle(), voxel_size, static_cast<int32_t>(voxels_per_side),
+                          max_blocks, &layer_));
+  }
+  ~TsdfLayer() {
+    if (layer_) cg_layer_destroy(layer_);
+  }
+  TsdfLayer(const TsdfLayer&) = delete;
+  TsdfLayer& operator=(const TsdfLayer&) = delete;
+
+  cg_layer* handle() const { return layer_; }
+  FloatingPoint voxel_size() const { return cg_layer_voxel_size(layer_); }
+  size_t voxels_per_side() const { return CG_VOXELS_PER_SIDE; }
+  FloatingPoint block_size() const { return voxel_size() * CG_VOXELS_PER_SIDE; }
+  size_t getNumberOfAllocatedBlocks() const {
+    return static_cast<size_t>(cg_layer_num_blocks(layer_));
+  }
+  size_t getMemorySize() const { return getNumberOfAllocatedBlocks() * CG_BLOCK_BYTES; }
+  void removeAllBlocks() { check(cg_layer_clear(layer_)); }
+  void getAllAllocatedBlocks(BlockIndexList* blocks) const {
+    const size_t n = getNumberOfAllocatedBlocks();
+    blocks->resize(n);
+    size_t got = 0;
+    check(cg_layer_block_indices(layer_, n, n ? &(*blocks)[0].x : nullptr, &got));
+  }
+  // copy the layer out in voxblox's own block layout (what serializeLayerAsMsg walks,
+  // coxgraph/include/coxgraph/map_comm/tsdf_recover.h:95)
+  void download(BlockIndexList* indices, std::vector<TsdfVoxel>* voxels,
+                std::vector<uint8_t>* flags = nullptr) const {
+    const size_t n = getNumberOfAllocatedBlocks();
+    indices->resize(n);
+    voxels->resize(n * CG_VOXELS_PER_BLOCK);
+    if (flags) flags->resize(n);
+    size_t got = 0;
+    check(cg_layer_download(layer_, n, n ? &(*indices)[0].x : nullptr, voxels->data(),
+                            flags ? flags->data() : nullptr, &got));
+  }
+  // insert / overwrite blocks (deserializeMsgToLayer hand-off,
+  // coxgraph/include/coxgraph/utils/msg_converter.h:107-109)
+  void upload(const BlockIndexList& indices, const std::vector<TsdfVoxel>& voxels,
+              const std::vector<uint8_t>* flags = nullptr) {
+    if (voxels.size() != indices.size() * CG_VOXELS_PER_BLOCK)
+      fatal_handler()(CG_ERR_INVALID_ARG, "TsdfLayer::upload: voxel count does not match");
+    check(cg_layer_upload(layer_, indices.size(), indices.empty() ? nullptr : &indices[0].x,
+                          voxels.data(), flags ? flags->data() : nullptr));
+  }
+
+ private:
+  cg_layer* layer_ = nullptr;
+};
+
+// ---- voxblox::TsdfIntegratorBase and its concrete integrators ---------------------------
+class TsdfIntegratorBase {
+ public:
+  using Ptr = std::shared_ptr<TsdfIntegratorBase>;
+  struct Config : cg_integrator_config {
+    Config() { cg_integrator_config_default(this); }
+  };
+  TsdfIntegratorBase(const Config& config, TsdfLayer* layer) : config_(config), layer_(layer) {}
+  virtual ~TsdfIntegratorBase() = default;
+
+  // Integrates the point cloud into the TSDF layer (same contract as voxblox: points in the
+  // sensor frame C, T_G_C the sensor pose, one colour per point).
+  virtual void integratePointCloud(const Transformation& T_G_C, const Pointcloud& points_C,
+                                   const Colors& colors, const bool freespace_points = false) {
+    if (points_C.size() != colors.size())
+      fatal_handler()(CG_ERR_INVALID_ARG, "integratePointCloud: points_C.size() != colors.size()");
+    check(cg_integrate_pointcloud(layer_->handle(), &config_, T_G_C.data(),
+                                  points_C.empty() ? nullptr : &points_C[0].x,
+                                  colors.empty() ? nullptr : &colors[0].r, points_C.size(),
+                                  freespace_points ? 1 : 0, &stats_));
+  }
+  // The frame loop of TsdfRecover::processMesh (tsdf_recover.h:71-86) as one job: identical
+  // result to calling integratePointCloud once per frame, in order.
+  void integratePointClouds(const std::vector<Transformation>& T_G_C,
+                            const std::vector<const Pointcloud*>& points_C,
+                            const std::vector<const Colors*>& colors,
+                            const bool freespace_points = false) {
+    const size_t F = T_G_C.size();
+    if (points_C.size() != F || colors.size() != F)
+      fatal_handler()(CG_ERR_INVALID_ARG, "integratePointClouds: one cloud per pose expected");
+    std::vector<uint64_t> offs(F + 1, 0);
+    for (size_t f = 0; f < F; ++f) offs[f + 1] = offs[f] + points_C[f]->size();
+    std::vector<Point> pts(offs[F]);
+    std::vector<Color> cols(offs[F]);
+    std::vector<float> poses(7 * F);
+    for (size_t f = 0; f < F; ++f) {
+      std::copy(points_C[f]->begin(), points_C[f]->end(), pts.begin() + offs[f]);
+      std::copy(colors[f]->begin(), colors[f]->end(), cols.begin() + offs[f]);
+      std::copy(T_G_C[f].data(), T_G_C[f].data() + 7, poses.begin() + 7 * f);
+    }
+    check(cg_integrate_batch(layer_->handle(), &config_, F, poses.data(),
+                             pts.empty() ? nullptr : &pts[0].x, cols.empty() ? nullptr : &cols[0].r,
+                             offs.data(), freespace_points ? 1 : 0, &stats_));
+  }
+  void setLayer(TsdfLayer* layer) { layer_ = layer; }
+  const Config& getConfig() const { return config_; }
+  const cg_integrate_stats& lastStats() const { return stats_; }
+
+ protected:
+  Config config_;
+  TsdfLayer* layer_;
+  cg_integrate_stats stats_{};
+};
+
+class SimpleTsdfIntegrator : public TsdfIntegratorBase {
+ public:
+  SimpleTsdfIntegrator(const Config& config, TsdfLayer* layer) : TsdfIntegratorBase(config, layer) {
+    config_.method = CG_METHOD_SIMPLE;
+  }
+};
+class MergedTsdfIntegrator : public TsdfIntegratorBase {
+ public:
+  MergedTsdfIntegrator(const Config& config, TsdfLayer* layer) : TsdfIntegratorBase(config, layer) {
+    config_.method = CG_METHOD_MERGED;
+  }
+};
+
+// voxblox::TsdfIntegratorFactory::create(integrator_type_name, config, layer).  The reference's
+// yaml files ask for "fast" (tsdf_server_euroc.yaml:6, tsdf_recover.yaml:6): FastTsdfIntegrator
+// is an approximation of the merged integrator whose result depends on thread timing, so "fast"
+// maps to the deterministic merged integrator here (DESIGN.md "Integrator methods").
+struct TsdfIntegratorFactory {
+  static TsdfIntegratorBase::Ptr create(const std::string& integrator_type_name,
+                                        const TsdfIntegratorBase::Config& config, TsdfLayer* layer) {
+    if (integrator_type_name == "simple")
+      return std::make_shared<SimpleTsdfIntegrator>(config, layer);
+    if (integrator_type_name == "merged" || integrator_type_name == "fast")
+      return std::make_shared<MergedTsdfIntegrator>(config, layer);
+    fatal_handler()(CG_ERR_UNSUPPORTED, ("unknown TSDF integrator type: " + integrator_type_name).c_str());
+    return nullptr;
+  }
+};
+
+// ---- voxblox::mergeLayerAintoLayerB(layer_A, T_B_A, layer_B) ---------------------------
+inline void mergeLayerAintoLayerB(const TsdfLayer& layer_A, const Transformation& T_B_A,
+                                  TsdfLayer* layer_B, cg_merge_stats* stats = nullptr) {
+  check(cg_merge_layer_into_layer(layer_A.handle(), T_B_A.data(), layer_B->handle(), stats));
+}
+
+// ---- cblox::SubmapCollection::getProjectedMap(): every submap merged into one layer, in
+// order, with its pose T_M_S (the server's submap-to-global entry point) ---------------------
+inline void getProjectedMap(const std::vector<const TsdfLayer*>& submap_layers,
+                            const std::vector<Transformation>& T_M_S, TsdfLayer* projected_layer,
+                            cg_merge_stats* stats = nullptr) {
+  if (submap_layers.size() != T_M_S.size())
+    fatal_handler()(CG_ERR_INVALID_ARG, "getProjectedMap: one pose per submap expected");
+  std::vector<const cg_layer*> handles(submap_layers.size());
+  std::vector<float> poses(7 * T_M_S.size());
+  for (size_t i = 0; i < submap_layers.size(); ++i) {
+    handles[i] = submap_layers[i]->handle();
+    std::copy(T_M_S[i].data(), T_M_S[i].data() + 7, poses.begin() + 7 * i);
+  }
+  check(cg_project_submaps(handles.data(), poses.data(), handles.size(), projected_layer->handle(),
+                           stats));
+}
+
+}  // namespace coxgraph_b200
+#endif  // COXGRAPH_B200_HPP_

@@ -173,6 +173,20 @@ int32_t cg_integrate_batch_device(cg_layer* layer, const cg_integrator_config* c
                                   const uint64_t* frame_offsets, int32_t freespace_points,
                                   cg_integrate_stats* stats);
 
+/* Double-buffered input staging (slot 0 or 1): cg_stage_batch_async queues the host->device copy
+ * of a later job's points / colours on the context's copy stream and returns at once (pinned host
+ * memory; it must stay valid until the matching cg_integrate_batch_staged returns), so the
+ * transfer of job k+1 overlaps the fusion of job k — the counterpart of the ROS subscriber queue
+ * that holds the next PointCloud2 while the current one is integrated
+ * (coxgraph/launch/firefly/tsdf_client.launch:24, voxblox_ros TsdfServer).  frame_offsets must
+ * start at 0 and end at the staged point count. */
+int32_t cg_stage_batch_async(cg_context* ctx, int32_t slot, const float* points_xyz,
+                             const uint8_t* colors_rgba, size_t num_points);
+int32_t cg_integrate_batch_staged(cg_layer* layer, const cg_integrator_config* cfg,
+                                  size_t num_frames, const float* T_G_C_poses, int32_t slot,
+                                  const uint64_t* frame_offsets, int32_t freespace_points,
+                                  cg_integrate_stats* stats);
+
 /* --- merge: replaces voxblox::mergeLayerAintoLayerB(layer_A, T_B_A, layer_B) — called at
  * coxgraph/src/client/map_server.cpp:67-69 — and cblox SubmapCollection::getProjectedMap(),
  * the server's submap-to-global entry reached from

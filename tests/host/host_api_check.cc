@@ -1,0 +1,80 @@
+// host_api_check — drives the C++ host API (coxgraph_b200/host/coxgraph_b200.hpp) the way the
+// reference's call sites do (tsdf_recover.h:59-99, map_server.cpp:59-73).  tests/test_host_cpp.py
+// writes the input frames, runs this program on the GPU box and compares the layers it writes
+// with the CPU oracle.
+//   host_api_check nogpu                       -> exit 0 iff creating a context fails loudly
+//   host_api_check run <in.bin> <out.bin>      -> integrate frames, merge, dump both layers
+// in.bin : u32 F, f32 voxel_size, f32 trunc, f32 T_M_S[7], then per frame: f32 T[7], u32 n,
+//          n * 3 f32 points, n * 4 u8 colours
+// out.bin: per layer (submap, global): u32 B, B * 3 i32, B * 4096 * 12 B voxels
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../coxgraph_b200/host/coxgraph_b200.hpp"
+
+namespace cg = coxgraph_b200;
+
+template <class T>
+static bool rd(FILE* f, T* p, size_t n = 1) { return fread(p, sizeof(T), n, f) == n; }
+
+static void dump(FILE* f, const cg::TsdfLayer& layer) {
+  cg::BlockIndexList idx;
+  std::vector<cg::TsdfVoxel> vox;
+  layer.download(&idx, &vox);
+  const uint32_t B = static_cast<uint32_t>(idx.size());
+  fwrite(&B, 4, 1, f);
+  if (B) {
+    fwrite(idx.data(), sizeof(cg::BlockIndex), B, f);
+    fwrite(vox.data(), sizeof(cg::TsdfVoxel), vox.size(), f);
+  }
+}
+
+int main(int argc, char** argv) {
+  cg::throw_on_error();
+  if (argc >= 2 && std::string(argv[1]) == "nogpu") {
+    try {
+      cg::Context ctx(0);
+    } catch (const cg::Error& e) {
+      std::printf("no device: status %d (%s)\n", e.status, e.what());
+      return e.status == CG_ERR_CUDA ? 0 : 2;
+    }
+    std::printf("a CUDA device is present\n");
+    return 3;
+  }
+  if (argc < 4 || std::string(argv[1]) != "run") return 64;
+  FILE* in = fopen(argv[2], "rb");
+  if (!in) return 65;
+  uint32_t F = 0;
+  float voxel_size = 0, trunc = 0;
+  cg::Transformation T_M_S;
+  if (!rd(in, &F) || !rd(in, &voxel_size) || !rd(in, &trunc) || !rd(in, &T_M_S.qw, 7)) return 66;
+  cg::Context ctx(0);
+  cg::TsdfLayer submap(ctx, voxel_size, 16, 2048), combined(ctx, voxel_size, 16, 4096);
+  cg::TsdfIntegratorBase::Config config;
+  config.default_truncation_distance = trunc;
+  config.use_const_weight = 1;
+  auto integrator = cg::TsdfIntegratorFactory::create("fast", config, &submap);
+  submap.removeAllBlocks();  // tsdf_recover.h:62
+  for (uint32_t f = 0; f < F; ++f) {
+    cg::Transformation T_G_C;
+    uint32_t n = 0;
+    if (!rd(in, &T_G_C.qw, 7) || !rd(in, &n)) return 67;
+    cg::Pointcloud points_C(n);
+    cg::Colors colors(n);
+    if (n && (!rd(in, points_C.data(), n) || !rd(in, colors.data(), n))) return 68;
+    integrator->integratePointCloud(T_G_C, points_C, colors, false);  // tsdf_recover.h:75
+  }
+  fclose(in);
+  combined.removeAllBlocks();                            // map_server.cpp:65
+  cg::mergeLayerAintoLayerB(submap, T_M_S, &combined);   // map_server.cpp:67-69
+  FILE* out = fopen(argv[3], "wb");
+  if (!out) return 69;
+  dump(out, submap);
+  dump(out, combined);
+  fclose(out);
+  std::printf("ok: submap %zu blocks, combined %zu blocks, %llu kernel launches\n",
+              submap.getNumberOfAllocatedBlocks(), combined.getNumberOfAllocatedBlocks(),
+              static_cast<unsigned long long>(ctx.kernelLaunches()));
+  return 0;
+}

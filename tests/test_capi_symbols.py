@@ -31,7 +31,7 @@ def test_struct_layouts_match_the_header():
     from oracle import oracle_py as orc
     assert C.sizeof(capi.IntegratorConfig) == 15 * 4
     assert [f[0] for f in capi.IntegratorConfig._fields_] == [f[0] for f in orc.IntegratorConfig._fields_]
-    assert C.sizeof(capi.IntegrateStats) == 40 and C.sizeof(capi.MergeStats) == 24
+    assert C.sizeof(capi.IntegrateStats) == 48 and C.sizeof(capi.MergeStats) == 24
     assert C.sizeof(capi.StageProfile) == 48
     assert capi.PACKED_BLOCK_BYTES == 16 + 4096 * 12
 
@@ -73,7 +73,6 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
-                assert "oracle" not in src.replace("oracle's", "").replace("the oracle", "") \
-                    or f in ("sharding.py",), f"{f} mentions the oracle package"
-                assert "import oracle" not in src and "from oracle" not in src
-                assert "tsdf_oracle" not in src
+                for needle in ("import oracle", "from oracle", "tsdf_oracle", "oracle_py",
+                               "oracle/", "liboracle", "orc_"):
+                    assert needle not in src, f"{f} references the oracle ({needle})"

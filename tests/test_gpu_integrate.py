@@ -58,6 +58,47 @@ def test_batch_split_path(gpu_ctx, monkeypatch):
     gl.close()
 
 
+def test_batch_pipelined_transfer(gpu_ctx, monkeypatch):
+    """Host-pointer batches are copied group by group on a second stream while earlier groups
+    are fused; the result is the one of the plain sequence."""
+    monkeypatch.setenv("CG_H2D_CHUNK_POINTS", "3000")
+    frames = util.small_frames(6, stride=8)
+    got, ref, gl = _run_both(gpu_ctx, frames, batch=True)
+    util.compare_layers(got, ref, "pipelined batch")
+    gl.close()
+
+
+def test_staged_double_buffer(gpu_ctx):
+    """cg_stage_batch_async + cg_integrate_batch_staged: inputs of job k+1 are copied while job k
+    is fused; results equal the plain calls."""
+    import torch
+    from coxgraph_b200 import Layer, TsdfIntegrator
+    from oracle import oracle_py as orc
+    ocfg, gcfg = util.make_cfgs()
+    jobs = [util.small_frames(2, stride=8, submap=s) for s in range(3)]
+    gl = Layer(gpu_ctx, 0.05, max_blocks=2048)
+    integ = TsdfIntegrator(gcfg, gl)
+    host = []
+    for frames in jobs:
+        p = torch.from_numpy(np.concatenate([p for (_, p, _) in frames])).pin_memory().numpy()
+        c = torch.from_numpy(np.concatenate([c for (_, _, c) in frames])).pin_memory().numpy()
+        offs = np.cumsum([0] + [len(p_) for (_, p_, _) in frames]).astype(np.uint64)
+        host.append((np.stack([T for (T, _, _) in frames]), p, c, offs))
+    integ.stageBatch(0, host[0][1], host[0][2])
+    for k, (poses, p, c, offs) in enumerate(host):
+        if k + 1 < len(host):
+            integ.stageBatch((k + 1) % 2, host[k + 1][1], host[k + 1][2])
+        gl.clear()
+        integ.integrateStaged(k % 2, poses, offs)
+        ol = orc.Layer(0.05)
+        for (T, pp, cc) in jobs[k]:
+            ol.integrate(ocfg, T, pp, cc)
+        util.compare_layers(gl.download(), ol.download(), f"staged job {k}")
+    with pytest.raises(Exception):
+        integ.integrateStaged(0, host[0][0], host[0][3][:-1])
+    gl.close()
+
+
 def test_touch_scratch_growth(monkeypatch):
     """The per-call touch scratch starts too small, overflows, grows and the walks are redone."""
     from coxgraph_b200 import Context
