@@ -27,7 +27,7 @@ constexpr int kVoxIdxOffset = 1 << 19;
 constexpr uint64_t kInvalidPointKey = ~0ull;         // sorts behind every valid key
 constexpr int kClearingBit = 60;
 
-enum ErrBits { kErrPoolFull = 1, kErrOutOfRange = 2, kErrTouchFull = 4 };
+enum ErrBits { kErrPoolFull = 1, kErrOutOfRange = 2, kErrTouchFull = 4, kErrSegmentFull = 8 };
 
 // ------------------------------------------------------------------ key packing
 __host__ __device__ __forceinline__ uint64_t pack_block_key(int x, int y, int z) {
@@ -159,6 +159,7 @@ struct CallCounters {
   unsigned long long pairs;
   unsigned long long touched;
   unsigned long long general_pairs;
+  unsigned long long segments;
   unsigned long long candidates;
   unsigned long long blocks_out;
   int err;
@@ -173,8 +174,9 @@ enum Stage {
   kStageBundleScan,
   kStageFold,
   kStageRayScan,
-  kStageWalkAccumulate,
-  kStageWalkEmit,
+  kStageWalkSegments,
+  kStageSegmentSort,
+  kStageBlockAccumulate,
   kStagePairSort,
   kStageSegments,
   kStageVoxelUpdate,
@@ -212,6 +214,7 @@ struct cg_context {
   cg::DevBuf key_a, key_b, val_a, val_b, flags, scan, cub_tmp;
   cg::DevBuf rays, ray_count, ray_offset, sorted_pts;
   cg::DevBuf pkey_a, pkey_b, seg_start, long_list, long_partials;
+  cg::DevBuf seg_keys_a, seg_keys_b, seg_idx_a, seg_idx_b, seg_recs;  // (ray, block) segments
   // per-call touch set (integrate.cu "back half"): kept all-clear between calls
   cg::DevBuf touch_ord, touch_entry, touch_acc, touch_bits;
   uint32_t* d_touch_count = nullptr;  // [0] blocks touched, [1] general (voxel, ray) keys emitted

@@ -153,6 +153,7 @@ struct RayCaster {
   float tnx, tny, tnz;
   float tsx, tsy, tsz;
   unsigned steps;  // ray_length_in_steps; steps + 1 indices are produced
+  int ex, ey, ez;  // voxel holding the ray end
   bool valid;
   bool in_range;  // all indices the walk can reach stay inside +-2^19
 
@@ -183,6 +184,7 @@ struct RayCaster {
       steps = 0;
       valid = false;
       cx = cy = cz = 0;
+      ex = ey = ez = 0;
       sx = sy = sz = 0;
       tnx = tny = tnz = tsx = tsy = tsz = 0.0f;
       return;
@@ -190,7 +192,9 @@ struct RayCaster {
     cx = grid_index_scaled(s.x);
     cy = grid_index_scaled(s.y);
     cz = grid_index_scaled(s.z);
-    const int ex = grid_index_scaled(e.x), ey = grid_index_scaled(e.y), ez = grid_index_scaled(e.z);
+    ex = grid_index_scaled(e.x);
+    ey = grid_index_scaled(e.y);
+    ez = grid_index_scaled(e.z);
     steps = static_cast<unsigned>(abs(ex - cx) + abs(ey - cy) + abs(ez - cz));
     const float rx = e.x - s.x, ry = e.y - s.y, rz = e.z - s.z;
     sx = signum(rx);
@@ -206,6 +210,15 @@ struct RayCaster {
     tsx = static_cast<float>(sx) / rx;
     tsy = static_cast<float>(sy) / ry;
     tsz = static_cast<float>(sz) / rz;
+  }
+
+  // (number of 16^3 blocks the walk crosses) << 32 | number of voxels it visits.  The walk is
+  // monotone per axis, so it crosses |delta block index|_1 + 1 blocks when it ends in the end
+  // voxel; rounding can make it end one step off (callers allow slack).
+  __device__ __forceinline__ unsigned long long packed_counts() const {
+    const unsigned nb = static_cast<unsigned>(abs((ex >> 4) - (cx >> 4)) + abs((ey >> 4) - (cy >> 4)) +
+                                              abs((ez >> 4) - (cz >> 4))) + 1u;
+    return (static_cast<unsigned long long>(nb) << 32) | (steps + 1u);
   }
 
   // advance to the next voxel (Eigen minCoeff: first coefficient wins ties, NaN in x sticks)

@@ -438,7 +438,7 @@ k_fold_bundles(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t t
 // one thread per bundle: T_G_C * merged point, ray set-up, pair count
 __global__ void k_bundle_rays(IntegratorParams P, const float* __restrict__ poses,
                               const uint32_t* __restrict__ num_heads, Ray* __restrict__ rays,
-                              uint32_t* __restrict__ ray_count) {
+                              unsigned long long* __restrict__ ray_count) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= *num_heads) return;
   Ray ray = rays[b];
@@ -454,7 +454,7 @@ __global__ void k_bundle_rays(IntegratorParams P, const float* __restrict__ pose
   rays[b].px = pg.x;
   rays[b].py = pg.y;
   rays[b].pz = pg.z;
-  ray_count[b] = rc.valid ? rc.steps + 1u : 0u;
+  ray_count[b] = rc.valid ? rc.packed_counts() : 0ull;
 }
 
 // SIMPLE: one ray per valid point, in (frame, visit rank) order
@@ -476,7 +476,7 @@ __global__ void k_simple_rays(IntegratorParams P, const float* __restrict__ pose
                               const uint32_t* __restrict__ slots,
                               const uint32_t* __restrict__ num_slots, const float* __restrict__ pts,
                               const uint32_t* __restrict__ cols, Ray* __restrict__ rays,
-                              uint32_t* __restrict__ ray_count) {
+                              unsigned long long* __restrict__ ray_count) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= *num_slots) return;
   const uint32_t g = slots[r];
@@ -499,14 +499,15 @@ __global__ void k_simple_rays(IntegratorParams P, const float* __restrict__ pose
   ray.color = cols[i];
   ray.frame_clr = static_cast<uint32_t>(f) | (clearing ? 0x80000000u : 0u);
   rays[r] = ray;
-  ray_count[r] = rc.valid ? rc.steps + 1u : 0u;
+  ray_count[r] = rc.valid ? rc.packed_counts() : 0ull;
 }
 
-__global__ void k_totals(const uint32_t* num_rays, const uint32_t* ray_count,
-                         const uint32_t* ray_offset, size_t upper, CallCounters* c) {
+__global__ void k_totals(const uint32_t* num_rays, const unsigned long long* ray_count,
+                         const unsigned long long* ray_offset, size_t upper, CallCounters* c) {
   c->rays = *num_rays;
-  c->pairs = upper ? static_cast<unsigned long long>(ray_offset[upper - 1]) + ray_count[upper - 1]
-                   : 0ull;
+  const unsigned long long tot = upper ? ray_offset[upper - 1] + ray_count[upper - 1] : 0ull;
+  c->pairs = tot & 0xFFFFFFFFull;   // voxel visits (the host splits jobs that reach 2^32)
+  c->segments = tot >> 32;          // (ray, block) segments
   c->touched = 0;
 }
 
@@ -638,12 +639,28 @@ __device__ __forceinline__ Visit make_visit(const IntegratorParams& P, const flo
   return v;
 }
 
-// Walk 1.  One lane per ray, the warp advances in lock step.  `tail_visits`: only the last
-// tail_visits visits of a ray can have sdf < truncation (host: walk_tail_visits()).
+// (ray, block) segment: the part of a ray's walk that lies inside one 16^3 block, with the
+// RayCaster state at its first voxel so that the block pass can replay it on its own.
+struct SegRecord {      // 32 B
+  uint32_t ray;
+  uint32_t packed;      // lx | ly << 4 | lz << 8 | (sx+1) << 12 | (sy+1) << 14 | (sz+1) << 16 | visits << 18
+  float tnx, tny, tnz;  // t_to_next_boundary at the first voxel
+  float tsx, tsy, tsz;  // t_step_size
+};
+static_assert(sizeof(SegRecord) == 32, "SegRecord is written as two 16-byte stores");
+
+// Walk.  One lane per ray, the warp advances in lock step: DDA exactly as voxblox::RayCaster,
+// block allocation on first visit (R4), one SegRecord per (ray, block), "general" bit for every
+// visit with sdf < truncation (only the last `tail_visits` visits of a ray can be such,
+// walk_tail_visits()).  Ray r owns the record slots [seg_first(r), seg_first(r) + its closed-form
+// block count + slack); unused slots get the null key.
 __global__ void __launch_bounds__(kWalkThreads)
-k_walk_accumulate(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
-                  uint32_t num_rays, LayerView L, TouchView Tv, float acc_scale,
-                  uint32_t tail_visits, uint32_t* work_counter) {
+k_walk_segments(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
+                uint32_t num_rays, const unsigned long long* __restrict__ ray_count,
+                const unsigned long long* __restrict__ ray_offset, uint32_t slack, LayerView L,
+                TouchView Tv, uint32_t tail_visits, uint32_t null_key, uint32_t* work_counter,
+                uint32_t* __restrict__ seg_keys, uint32_t* __restrict__ seg_idx,
+                uint4* __restrict__ seg_recs) {
   __shared__ unsigned long long cache[kBlockCacheSize];
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
@@ -652,20 +669,40 @@ k_walk_accumulate(IntegratorParams P, const float* __restrict__ poses, const Ray
   for (;;) {
     const uint32_t r0 = next_ray_batch(work_counter, lane) * 32u;
     if (r0 >= num_rays) break;
-    WalkRay w = load_walk_ray(P, poses, rays, r0 + lane, num_rays, L.err);
+    const uint32_t r = r0 + lane;
+    WalkRay w = load_walk_ray(P, poses, rays, r, num_rays, L.err);
     RayCaster& rc = w.rc;
-    const unsigned long long wq =
-        __float2ull_rn(fminf(fmaxf(w.ray.weight, 0.0f), P.max_weight) * acc_scale);
+    uint32_t seg_pos = 0, seg_end = 0;
+    if (r < num_rays) {
+      seg_pos = static_cast<uint32_t>(ray_offset[r] >> 32) + r * slack;
+      seg_end = seg_pos + static_cast<uint32_t>(ray_count[r] >> 32) + slack;
+    }
     int lbx = 0x7FFFFFFF, lby = 0, lbz = 0;
-    uint32_t vbase = 0;
-    for (;;) {
-      const bool active = w.remaining > 0;
-      const unsigned am = __ballot_sync(full, active);
-      if (!am) break;
-      uint32_t vid = 0xFFFFFFFFu;
-      if (active) {
+    uint32_t ord = 0, s_entry = 0, s_visits = 0;
+    float s_tnx = 0.0f, s_tny = 0.0f, s_tnz = 0.0f;
+    const uint32_t sign_bits = (static_cast<uint32_t>(rc.sx + 1) << 12) |
+                               (static_cast<uint32_t>(rc.sy + 1) << 14) |
+                               (static_cast<uint32_t>(rc.sz + 1) << 16);
+    auto emit = [&]() {
+      if (seg_pos < seg_end) {
+        seg_keys[seg_pos] = ord;
+        seg_idx[seg_pos] = seg_pos;
+        seg_recs[2 * size_t(seg_pos)] =
+            make_uint4(r, s_entry | sign_bits | (s_visits << 18), __float_as_uint(s_tnx),
+                       __float_as_uint(s_tny));
+        seg_recs[2 * size_t(seg_pos) + 1] =
+            make_uint4(__float_as_uint(s_tnz), __float_as_uint(rc.tsx), __float_as_uint(rc.tsy),
+                       __float_as_uint(rc.tsz));
+      } else {
+        atomicOr(L.err, kErrSegmentFull);  // the host redoes the job with more slack
+      }
+      ++seg_pos;
+    };
+    while (__any_sync(full, w.remaining > 0)) {
+      if (w.remaining > 0) {
         const int bx = rc.cx >> 4, by = rc.cy >> 4, bz = rc.cz >> 4;
         if (bx != lbx || by != lby || bz != lbz) {
+          if (s_visits) emit();
           lbx = bx;
           lby = by;
           lbz = bz;
@@ -674,38 +711,36 @@ k_walk_accumulate(IntegratorParams P, const float* __restrict__ poses, const Ray
           const bool cacheable = block_cache_tag(bx, by, bz, tag, ci);
           const unsigned long long cw = cacheable ? cache[ci] : 0ull;
           if (cacheable && (cw >> 20) == tag) {
-            vbase = static_cast<uint32_t>(cw & 0xFFFFFu) << 12;
+            ord = static_cast<uint32_t>(cw & 0xFFFFFu);
           } else {
             const int entry = L.insert_entry(pack_block_key(bx, by, bz));
-            const uint32_t ord = touch_ordinal(Tv, entry, L.err);
-            vbase = ord << 12;
+            ord = touch_ordinal(Tv, entry, L.err);
             if (cacheable) cache[ci] = (tag << 20) | ord;
           }
+          s_entry = static_cast<uint32_t>((rc.cx & 15) | ((rc.cy & 15) << 4) | ((rc.cz & 15) << 8));
+          s_tnx = rc.tnx;
+          s_tny = rc.tny;
+          s_tnz = rc.tnz;
+          s_visits = 0;
         }
-        vid = vbase | static_cast<uint32_t>((rc.cx & 15) + 16 * ((rc.cy & 15) + 16 * (rc.cz & 15)));
+        ++s_visits;
         if (w.remaining <= tail_visits) {
           const V3 center = V3{center_coord(rc.cx, P.voxel_size), center_coord(rc.cy, P.voxel_size),
                                center_coord(rc.cz, P.voxel_size)};
           const float sdf = make_visit(P, poses, w.ray, center).sdf;
-          if (!(sdf >= P.trunc)) atomicOr(Tv.general + (vid >> 5), 1u << (vid & 31));
+          if (!(sdf >= P.trunc)) {
+            const uint32_t vid = (ord << 12) | static_cast<uint32_t>((rc.cx & 15) + 16 * ((rc.cy & 15) +
+                                                                     16 * (rc.cz & 15)));
+            atomicOr(Tv.general + (vid >> 5), 1u << (vid & 31));
+          }
         }
-      }
-      // next to the sensor every ray of the warp crosses the same voxel: one add for the warp
-      // (same-address atomics serialise in L2; measured 0.97 -> 0.63 ms on the C2 step)
-      const int first = __ffs(am) - 1;
-      const uint32_t v0 = __shfl_sync(full, vid, first);
-      if (__all_sync(full, !active || vid == v0)) {
-        unsigned long long s = active ? wq : 0ull;
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(full, s, d);
-        if (lane == first) atomicAdd(Tv.acc + v0, s);
-      } else if (active) {
-        atomicAdd(Tv.acc + vid, wq);
-      }
-      if (active) {
         rc.step();
-        --w.remaining;
+        if (--w.remaining == 0) emit();
       }
+    }
+    for (; seg_pos < seg_end; ++seg_pos) {  // unused slots sort behind every real segment
+      seg_keys[seg_pos] = null_key;
+      seg_idx[seg_pos] = seg_pos;
     }
   }
 }
@@ -731,19 +766,32 @@ k_mark_existing(IntegratorParams P, LayerView L, TouchView Tv, int32_t blocks_be
   }
 }
 
-// Walk 2: same rays, same voxels; visits of general voxels go out as (voxel << ray_bits | ray).
-// Each warp stages its keys in shared memory and appends them with one atomic per flush; the
-// append order is irrelevant because the sort key contains the ray rank.
-constexpr int kEmitBuf = 256;
-__global__ void __launch_bounds__(kWalkThreads)
-k_walk_emit(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
-            uint32_t num_rays, LayerView L, TouchView Tv, uint32_t ray_bits,
-            unsigned long long* __restrict__ out, uint32_t* out_count, uint32_t out_cap,
-            uint32_t* work_counter) {
-  __shared__ unsigned long long buf[kWalkThreads / 32][kEmitBuf];
-  __shared__ unsigned long long cache[kBlockCacheSize];
-  for (int i = threadIdx.x; i < kBlockCacheSize; i += blockDim.x) cache[i] = 0ull;
-  __syncthreads();
+// Block pass.  The segments are sorted by block; a CTA takes a chunk of the sorted list and, per
+// block run inside it, replays the segments against a shared-memory tile of the block:
+// fixed-point weight accumulation with shared-memory atomics (deterministic: integer adds
+// commute), "general" test from the block's bit tile, general visits appended as
+// (voxel << ray_bits | ray) keys (warp-staged, one global atomic per flush; the append order is
+// irrelevant because the sort key contains the ray rank).  The tile is then added to the
+// per-job accumulators in global memory — one add per touched voxel and chunk instead of one
+// per visit (measured: per-visit global atomics cost 0.4 ms of a 0.6 ms walk on the C2 step).
+constexpr int kAccThreads = 256;
+constexpr uint32_t kSegChunk = 2048;   // segments per work item
+constexpr uint32_t kTileMinRun = 64;   // shorter block runs add straight to global memory
+constexpr int kEmitBuf = 128;
+__global__ void __launch_bounds__(kAccThreads)
+k_block_accumulate(IntegratorParams P, const Ray* __restrict__ rays,
+                   const uint32_t* __restrict__ seg_keys, const uint32_t* __restrict__ seg_idx,
+                   const uint4* __restrict__ seg_recs, uint32_t num_slots, uint32_t null_key,
+                   TouchView Tv, float acc_scale, uint32_t ray_bits,
+                   unsigned long long* __restrict__ out, uint32_t* out_count, uint32_t out_cap,
+                   uint32_t* work_counter) {
+  // 64-bit accumulators as (lo, hi) words: shared memory has native 32-bit atomic adds only (a
+  // 64-bit add is a compare-and-swap loop); the carry out of lo is recovered from the returned
+  // old value, so the sum is exact whatever the order of the adds
+  __shared__ uint32_t tile_lo[kVoxelsPerBlock], tile_hi[kVoxelsPerBlock];
+  __shared__ uint32_t bits[kVoxelsPerBlock / 32];
+  __shared__ unsigned long long buf[kAccThreads / 32][kEmitBuf];
+  __shared__ uint32_t s_chunk;
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
@@ -759,54 +807,105 @@ k_walk_emit(IntegratorParams P, const float* __restrict__ poses, const Ray* __re
     cnt = 0;
   };
   for (;;) {
-    const uint32_t r0 = next_ray_batch(work_counter, lane) * 32u;
-    if (r0 >= num_rays) break;
-    const uint32_t r = r0 + lane;
-    WalkRay w = load_walk_ray(P, poses, rays, r, num_rays, nullptr);
-    RayCaster& rc = w.rc;
-    int lbx = 0x7FFFFFFF, lby = 0, lbz = 0;
-    uint32_t vbase = 0;
-    bool known = false;
-    for (;;) {
-      const bool active = w.remaining > 0;
-      if (!__any_sync(full, active)) break;
-      bool g = false;
-      uint32_t vid = 0;
-      if (active) {
-        const int bx = rc.cx >> 4, by = rc.cy >> 4, bz = rc.cz >> 4;
-        if (bx != lbx || by != lby || bz != lbz) {
-          lbx = bx;
-          lby = by;
-          lbz = bz;
-          unsigned long long tag = 0ull;
-          uint32_t ci = 0;
-          const bool cacheable = block_cache_tag(bx, by, bz, tag, ci);
-          const unsigned long long cw = cacheable ? cache[ci] : 0ull;
-          if (cacheable && (cw >> 20) == tag) {
-            known = true;
-            vbase = static_cast<uint32_t>(cw & 0xFFFFFu) << 12;
-          } else {
-            const int entry = L.find_entry(pack_block_key(bx, by, bz));
-            known = entry >= 0;
-            const uint32_t ord = known ? static_cast<uint32_t>(Tv.ord[entry]) : 0u;
-            vbase = ord << 12;
-            if (cacheable && known) cache[ci] = (tag << 20) | ord;
+    __syncthreads();
+    if (threadIdx.x == 0) s_chunk = atomicAdd(work_counter, 1u);
+    __syncthreads();
+    const uint32_t c_lo = s_chunk * kSegChunk;
+    if (c_lo >= num_slots) break;
+    const uint32_t c_hi = min(num_slots, c_lo + kSegChunk);
+    uint32_t pos = c_lo;
+    while (pos < c_hi) {
+      const uint32_t o = seg_keys[pos];
+      if (o >= null_key) break;  // unused slots are sorted last
+      uint32_t lo = pos, hi = c_hi;  // end of this block's run inside the chunk
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (seg_keys[mid] == o) lo = mid; else hi = mid;
+      }
+      const bool use_tile = hi - pos >= kTileMinRun;
+      if (use_tile)
+        for (int i = threadIdx.x; i < kVoxelsPerBlock; i += kAccThreads) tile_lo[i] = tile_hi[i] = 0u;
+      if (threadIdx.x < kVoxelsPerBlock / 32)
+        bits[threadIdx.x] = Tv.general[size_t(o) * (kVoxelsPerBlock / 32) + threadIdx.x];
+      __syncthreads();
+      unsigned long long* acc = Tv.acc + size_t(o) * kVoxelsPerBlock;
+      for (uint32_t i0 = pos + wib * 32; i0 < hi; i0 += kAccThreads) {
+        const uint32_t i = i0 + lane;
+        uint32_t visits = 0, ray = 0;
+        int lx = 0, ly = 0, lz = 0, sx = 0, sy = 0, sz = 0;
+        float tnx = 0.0f, tny = 0.0f, tnz = 0.0f, tsx = 0.0f, tsy = 0.0f, tsz = 0.0f;
+        unsigned long long wq = 0ull;
+        if (i < hi) {
+          const uint32_t slot = seg_idx[i];
+          const uint4 ra = seg_recs[2 * size_t(slot)], rb = seg_recs[2 * size_t(slot) + 1];
+          ray = ra.x;
+          lx = ra.y & 15;
+          ly = (ra.y >> 4) & 15;
+          lz = (ra.y >> 8) & 15;
+          sx = static_cast<int>((ra.y >> 12) & 3) - 1;
+          sy = static_cast<int>((ra.y >> 14) & 3) - 1;
+          sz = static_cast<int>((ra.y >> 16) & 3) - 1;
+          visits = ra.y >> 18;
+          tnx = __uint_as_float(ra.z);
+          tny = __uint_as_float(ra.w);
+          tnz = __uint_as_float(rb.x);
+          tsx = __uint_as_float(rb.y);
+          tsy = __uint_as_float(rb.z);
+          tsz = __uint_as_float(rb.w);
+          wq = __float2ull_rn(fminf(fmaxf(rays[ray].weight, 0.0f), P.max_weight) * acc_scale);
+        }
+        const uint32_t vmax = __reduce_max_sync(full, visits);
+        for (uint32_t v = 0; v < vmax; ++v) {
+          bool g = false;
+          uint32_t lin = 0;
+          if (v < visits) {
+            lin = static_cast<uint32_t>(lx + 16 * (ly + 16 * lz));
+            if (use_tile) {
+              const uint32_t wlo = static_cast<uint32_t>(wq), whi = static_cast<uint32_t>(wq >> 32);
+              const uint32_t old = atomicAdd(&tile_lo[lin], wlo);
+              const uint32_t up = whi + ((old + wlo < old) ? 1u : 0u);
+              if (up) atomicAdd(&tile_hi[lin], up);
+            } else {
+              atomicAdd(acc + lin, wq);
+            }
+            g = (bits[lin >> 5] >> (lin & 31)) & 1u;
+            // RayCaster::step (first minimum wins ties)
+            int m = 0;
+            float best = tnx;
+            if (tny < best) {
+              best = tny;
+              m = 1;
+            }
+            if (tnz < best) m = 2;
+            if (m == 0) {
+              lx += sx;
+              tnx += tsx;
+            } else if (m == 1) {
+              ly += sy;
+              tny += tsy;
+            } else {
+              lz += sz;
+              tnz += tsz;
+            }
+          }
+          const unsigned gm = __ballot_sync(full, g);
+          if (gm) {
+            if (g) buf[wib][cnt + __popc(gm & lt)] =
+                (static_cast<unsigned long long>((o << 12) | lin) << ray_bits) | ray;
+            cnt += __popc(gm);
+            if (cnt > kEmitBuf - 32) flush();
           }
         }
-        vid = vbase | static_cast<uint32_t>((rc.cx & 15) + 16 * ((rc.cy & 15) + 16 * (rc.cz & 15)));
-        g = known && ((Tv.general[vid >> 5] >> (vid & 31)) & 1u);
       }
-      const unsigned gm = __ballot_sync(full, g);
-      if (gm) {
-        if (g) buf[wib][cnt + __popc(gm & lt)] =
-            (static_cast<unsigned long long>(vid) << ray_bits) | r;
-        cnt += __popc(gm);
-        if (cnt > kEmitBuf - 32) flush();
-      }
-      if (active) {
-        rc.step();
-        --w.remaining;
-      }
+      __syncthreads();
+      if (use_tile)
+        for (int i = threadIdx.x; i < kVoxelsPerBlock; i += kAccThreads) {
+          const unsigned long long a =
+              (static_cast<unsigned long long>(tile_hi[i]) << 32) | tile_lo[i];
+          if (a) atomicAdd(acc + i, a);
+        }
+      __syncthreads();
+      pos = hi;
     }
   }
   if (cnt) flush();
@@ -917,12 +1016,32 @@ __device__ __forceinline__ void replay_segment(const IntegratorParams& P,
     const float fa = __shfl_sync(full, f.a, 0), fb = __shfl_sync(full, f.b, 0);
     const float flo = __shfl_sync(full, f.lo, 0), fhi = __shfl_sync(full, f.hi, 0);
     D = fminf(fmaxf(fa * D + fb, flo), fhi);
+    // Colours (Color::blendTwoColors, rounded to uint8 after every blend) stay sequential over the
+    // updates inside the truncation band, but only the 3-operation chain per channel: the blend
+    // factors and products are computed by the update's own lane, the 4 channels run on 4 lanes.
     unsigned band = __ballot_sync(full, !skip && fabsf(sdf) < P.trunc);
-    while (band) {
-      const int t = __ffs(band) - 1;
-      band &= band - 1;
-      C = blend_colors(C, __shfl_sync(full, w_prev, t), __shfl_sync(full, v.col, t),
-                       __shfl_sync(full, w, t));
+    if (band) {
+      const float total = w_prev + w;
+      const float w1n = w_prev / total, w2n = w / total;
+      const float pr0 = static_cast<float>(v.col & 255u) * w2n;
+      const float pr1 = static_cast<float>((v.col >> 8) & 255u) * w2n;
+      const float pr2 = static_cast<float>((v.col >> 16) & 255u) * w2n;
+      const float pr3 = static_cast<float>(v.col >> 24) * w2n;
+      float ch = static_cast<float>((C >> (8 * (lane & 3))) & 255u);
+      while (band) {
+        const int t = __ffs(band) - 1;
+        band &= band - 1;
+        const float a = __shfl_sync(full, w1n, t);
+        const float q0 = __shfl_sync(full, pr0, t), q1 = __shfl_sync(full, pr1, t);
+        const float q2 = __shfl_sync(full, pr2, t), q3 = __shfl_sync(full, pr3, t);
+        const float mine = (lane & 2) ? ((lane & 1) ? q3 : q2) : ((lane & 1) ? q1 : q0);
+        ch = round_half_away_pos(ch * a + mine);
+      }
+      const uint32_t k0 = static_cast<uint32_t>(__shfl_sync(full, ch, 0));
+      const uint32_t k1 = static_cast<uint32_t>(__shfl_sync(full, ch, 1));
+      const uint32_t k2 = static_cast<uint32_t>(__shfl_sync(full, ch, 2));
+      const uint32_t k3 = static_cast<uint32_t>(__shfl_sync(full, ch, 3));
+      C = pack_rgba(k0 & 255u, k1 & 255u, k2 & 255u, k3 & 255u);
     }
     const float w_after = skip ? w_prev : fminf(P.max_weight, w_new);
     W = __shfl_sync(full, w_after, 31);
@@ -967,6 +1086,8 @@ k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* _
   vr.cp = nullptr;
   vr.center = V3{0.0f, 0.0f, 0.0f};
   VoxelState st{0.0f, 0.0f, 0u};
+  Ray ray_next = rays[0];
+  uint32_t id_next = 0;
   for (;;) {
     const bool need = !finished && cur >= end;
     const unsigned m = __ballot_sync(full, need);
@@ -998,6 +1119,8 @@ k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* _
               st.d = *vr.dp;
               st.w = *vr.wp;
               st.c = *vr.cp;
+              ray_next = rays[static_cast<uint32_t>(keys[start]) & ray_mask];
+              id_next = (start + 1 < stop) ? static_cast<uint32_t>(keys[start + 1]) & ray_mask : 0u;
             }
           }
         } else {
@@ -1009,7 +1132,11 @@ k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* _
 #pragma unroll 1
     for (int t = 0; t < kUpdateInner; ++t) {
       if (cur < end) {
-        const Ray ray = rays[static_cast<uint32_t>(keys[cur]) & ray_mask];
+        // two-stage software pipeline: key of update cur+2 and ray record of update cur+1 are in
+        // flight while update cur is applied
+        const Ray ray = ray_next;
+        ray_next = rays[id_next];
+        id_next = (cur + 2 < end) ? static_cast<uint32_t>(keys[cur + 2]) & ray_mask : 0u;
         const float* T = poses + 7 * (ray.frame_clr & 0x7FFFFFFFu);
         update_tsdf_voxel(P, V3{T[4], T[5], T[6]}, V3{ray.px, ray.py, ray.pz}, vr.center, ray.color,
                           ray.weight, st);
@@ -1226,11 +1353,12 @@ __global__ void k_collect_walk(LayerView L, const uint32_t* touch_count, CallCou
   c->num_blocks = min(*L.num_blocks, L.max_blocks);
   const int e = *L.err;
   c->err = e;
-  if (e & kErrTouchFull) *L.err = e & ~kErrTouchFull;
+  if (e & (kErrTouchFull | kErrSegmentFull)) *L.err = e & ~(kErrTouchFull | kErrSegmentFull);
 }
 
 static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParams& P,
-                             uint32_t num_rays, size_t num_pairs, cg_integrate_stats* stats) {
+                             uint32_t num_rays, size_t num_pairs, size_t num_segments,
+                             cg_integrate_stats* stats) {
   cudaStream_t s = ctx->stream;
   if (num_pairs >= 0xFFFFFFF0ull) {
     set_error("too many voxel visits in one group");
@@ -1246,6 +1374,7 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
   const unsigned walk_grid = std::min<unsigned>(grid_for(num_rays, kWalkThreads),
                                                 static_cast<unsigned>(ctx->num_sms) * 10u);
   size_t cap = std::max<size_t>(ctx->touch_cap, std::min<size_t>(L->max_blocks, env_size("CG_TOUCH_CAP", 1024)));
+  uint32_t slack = static_cast<uint32_t>(env_size("CG_SEGMENT_SLACK", 1));
   uint32_t n_touched = 0, n_general = 0;
   int64_t blocks_after = L->num_blocks;
   for (;;) {
@@ -1255,20 +1384,47 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
     TouchView tv{ctx->touch_ord.as<int32_t>(), ctx->touch_entry.as<uint32_t>(),
                  ctx->touch_acc.as<unsigned long long>(), ctx->touch_bits.as<uint32_t>(),
                  ctx->d_touch_count, static_cast<uint32_t>(ctx->touch_cap)};
+    // record slots: the closed-form block count of every ray + `slack` spare slots per ray
+    const size_t num_slots = num_segments + size_t(num_rays) * slack;
+    if (num_slots >= 0xFFFFFFF0ull) {
+      set_error("too many (ray, block) segments in one group");
+      return CG_ERR_INVALID_ARG;
+    }
+    CG_CUDA(ctx->seg_keys_a.reserve(num_slots * sizeof(uint32_t)));
+    CG_CUDA(ctx->seg_keys_b.reserve(num_slots * sizeof(uint32_t)));
+    CG_CUDA(ctx->seg_idx_a.reserve(num_slots * sizeof(uint32_t)));
+    CG_CUDA(ctx->seg_idx_b.reserve(num_slots * sizeof(uint32_t)));
+    CG_CUDA(ctx->seg_recs.reserve(num_slots * sizeof(SegRecord)));
+    const int ord_bits = std::max(1, ceil_log2(ctx->touch_cap));
+    const uint32_t null_key = 1u << ord_bits;  // above every ordinal
+    cub::DoubleBuffer<uint32_t> sk(ctx->seg_keys_a.as<uint32_t>(), ctx->seg_keys_b.as<uint32_t>());
+    cub::DoubleBuffer<uint32_t> sv(ctx->seg_idx_a.as<uint32_t>(), ctx->seg_idx_b.as<uint32_t>());
+    size_t tmp_seg = 0;
+    CG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_seg, sk, sv, static_cast<int>(num_slots), 0,
+                                            ord_bits + 1, s));
+    CG_CUDA(ctx->cub_tmp.reserve(tmp_seg));
     CG_CUDA(fill_bytes(ctx->d_walk_counters, 0, 2 * sizeof(uint32_t), s));
     {
-      StageScope sc(ctx, kStageWalkAccumulate, 2);
-      k_walk_accumulate<<<walk_grid, kWalkThreads, 0, s>>>(
-          P, ctx->group_poses, ctx->rays.as<Ray>(), num_rays, L->v, tv, acc_scale,
-          tail_visits, ctx->d_walk_counters);
+      StageScope sc(ctx, kStageWalkSegments, 2);
+      k_walk_segments<<<walk_grid, kWalkThreads, 0, s>>>(
+          P, ctx->group_poses, ctx->rays.as<Ray>(), num_rays,
+          ctx->ray_count.as<unsigned long long>(), ctx->ray_offset.as<unsigned long long>(), slack,
+          L->v, tv, tail_visits, null_key, ctx->d_walk_counters, sk.Current(), sv.Current(),
+          ctx->seg_recs.as<uint4>());
       if (L->num_blocks > 0)
         k_mark_existing<<<ctx->num_sms * 4, 128, 0, s>>>(P, L->v, tv,
                                                          static_cast<int32_t>(L->num_blocks));
     }
     {
-      StageScope sc(ctx, kStageWalkEmit, 2);
-      k_walk_emit<<<walk_grid, kWalkThreads, 0, s>>>(
-          P, ctx->group_poses, ctx->rays.as<Ray>(), num_rays, L->v, tv, ray_bits,
+      StageScope sc(ctx, kStageSegmentSort, 0);
+      CG_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_seg, sk, sv,
+                                              static_cast<int>(num_slots), 0, ord_bits + 1, s));
+    }
+    {
+      StageScope sc(ctx, kStageBlockAccumulate, 2);
+      k_block_accumulate<<<ctx->num_sms * 5, kAccThreads, 0, s>>>(
+          P, ctx->rays.as<Ray>(), sk.Current(), sv.Current(), ctx->seg_recs.as<uint4>(),
+          static_cast<uint32_t>(num_slots), null_key, tv, acc_scale, ray_bits,
           ctx->pkey_a.as<unsigned long long>(), ctx->d_touch_count + 1,
           static_cast<uint32_t>(num_pairs), ctx->d_walk_counters + 1);
       k_collect_walk<<<1, 1, 0, s>>>(L->v, ctx->d_touch_count, ctx->d_counters);
@@ -1280,13 +1436,24 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
     n_touched = static_cast<uint32_t>(ctx->h_counters->touched);
     n_general = static_cast<uint32_t>(ctx->h_counters->general_pairs);
     blocks_after = ctx->h_counters->num_blocks;
-    if (!(ctx->h_counters->err & kErrTouchFull)) break;
-    // more blocks touched than the scratch holds: grow it (wiped by ensure_touch) and redo
-    cap = 1024;
-    while (cap < n_touched + n_touched / 4) cap <<= 1;
-    if (cap > (size_t(1) << 19)) {
-      set_error("a single job touches %u blocks; split the point cloud", n_touched);
-      return CG_ERR_INVALID_ARG;
+    const int err = ctx->h_counters->err;
+    if (!(err & (kErrTouchFull | kErrSegmentFull))) break;
+    if (err & kErrTouchFull) {
+      // more blocks touched than the scratch holds: grow it (wiped by ensure_touch) and redo
+      cap = 1024;
+      while (cap < n_touched + n_touched / 4) cap <<= 1;
+      if (cap > (size_t(1) << 19)) {
+        set_error("a single job touches %u blocks; split the point cloud", n_touched);
+        return CG_ERR_INVALID_ARG;
+      }
+    }
+    if (err & kErrSegmentFull) {
+      // a walk ended off its closed-form end voxel by more steps than the slack allows
+      if (slack >= 4) {
+        set_error("ray walk crossed more blocks than its closed-form bound + 4");
+        return CG_ERR_INVALID_ARG;
+      }
+      slack = 4;
     }
   }
   TouchView tv{ctx->touch_ord.as<int32_t>(), ctx->touch_entry.as<uint32_t>(),
@@ -1370,8 +1537,8 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   }
   const size_t upper = total + 1;  // + the sentinel bundle of dropped points
   CG_CUDA(ctx->rays.reserve(upper * sizeof(Ray)));
-  CG_CUDA(ctx->ray_count.reserve(upper * sizeof(uint32_t)));
-  CG_CUDA(ctx->ray_offset.reserve(upper * sizeof(uint32_t)));
+  CG_CUDA(ctx->ray_count.reserve(upper * sizeof(unsigned long long)));
+  CG_CUDA(ctx->ray_offset.reserve(upper * sizeof(unsigned long long)));
   CG_CUDA(ctx->scan.reserve(upper * sizeof(uint32_t)));  // bundle heads / valid slots
   const bool merged = cfg->method == CG_METHOD_MERGED;
   if (merged) {
@@ -1403,12 +1570,12 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
     cub::DeviceSelect::If(nullptr, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
                           static_cast<int>(total), valid, s);
   }
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, ctx->ray_count.as<uint32_t>(),
-                                ctx->ray_offset.as<uint32_t>(), static_cast<int>(upper), s);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, ctx->ray_count.as<unsigned long long>(),
+                                ctx->ray_offset.as<unsigned long long>(), static_cast<int>(upper), s);
   CG_CUDA(ctx->cub_tmp.reserve(std::max(tmp_sort, std::max(tmp_sel, tmp_scan))));
   {
     StageScope sc(ctx, kStageTransfer, 0);
-    CG_CUDA(fill_bytes(ctx->ray_count.p, 0, upper * sizeof(uint32_t), s));
+    CG_CUDA(fill_bytes(ctx->ray_count.p, 0, upper * sizeof(unsigned long long), s));
   }
   if (merged) {
     {
@@ -1451,7 +1618,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
           ctx->rays.as<Ray>());
       k_bundle_rays<<<grid_for(upper, 256), 256, 0, s>>>(P, ctx->group_poses, d_num,
                                                          ctx->rays.as<Ray>(),
-                                                         ctx->ray_count.as<uint32_t>());
+                                                         ctx->ray_count.as<unsigned long long>());
     }
   } else {
     {
@@ -1462,14 +1629,16 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
     StageScope sc(ctx, kStageFold, 1);
     k_simple_rays<<<grid_for(total, 256), 256, 0, s>>>(
         P, ctx->group_poses, ft, ctx->scan.as<uint32_t>(), d_num, pts,
-        cols, ctx->rays.as<Ray>(), ctx->ray_count.as<uint32_t>());
+        cols, ctx->rays.as<Ray>(), ctx->ray_count.as<unsigned long long>());
   }
   {
     StageScope sc(ctx, kStageRayScan, 1);
-    CG_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_scan, ctx->ray_count.as<uint32_t>(),
-                                          ctx->ray_offset.as<uint32_t>(), static_cast<int>(upper),
-                                          s));
-    k_totals<<<1, 1, 0, s>>>(d_num, ctx->ray_count.as<uint32_t>(), ctx->ray_offset.as<uint32_t>(),
+    CG_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_scan,
+                                          ctx->ray_count.as<unsigned long long>(),
+                                          ctx->ray_offset.as<unsigned long long>(),
+                                          static_cast<int>(upper), s));
+    k_totals<<<1, 1, 0, s>>>(d_num, ctx->ray_count.as<unsigned long long>(),
+                             ctx->ray_offset.as<unsigned long long>(),
                              upper, ctx->d_counters);
   }
   // the staged host buffer (rel) must outlive its async copy: the sync below covers it
@@ -1497,7 +1666,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
     stats->rays += num_rays;
     stats->voxel_updates += num_pairs;
   }
-  return run_back_half(ctx, L, P, num_rays, num_pairs, stats);
+  return run_back_half(ctx, L, P, num_rays, num_pairs, ctx->h_counters->segments, stats);
 }
 
 // The job's poses and frame offsets (relative to its first point) go up once per job, through a

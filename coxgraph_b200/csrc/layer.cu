@@ -25,8 +25,8 @@ int32_t cuda_fail(cudaError_t e, const char* what) {
 
 const char* stage_name(int s) {
   static const char* names[kNumStages] = {
-      "point_keys", "bundle_sort",  "bundle_scan", "bundle_fold",  "ray_scan",   "walk_accumulate",
-      "walk_emit",  "pair_sort",    "segments",    "voxel_update", "finalize",   "merge_mark",
+      "point_keys", "bundle_sort",  "bundle_scan", "bundle_fold",  "ray_scan",   "walk_segments",
+      "segment_sort", "block_accumulate", "pair_sort",    "segments",    "voxel_update", "finalize",   "merge_mark",
       "merge_resample", "transfer"};
   return (s >= 0 && s < kNumStages) ? names[s] : "?";
 }
@@ -241,7 +241,7 @@ int32_t cg_context_destroy(cg_context* ctx) {
   DevBuf* bufs[] = {&ctx->points, &ctx->colors, &ctx->poses, &ctx->frame_base, &ctx->key_a,
                     &ctx->key_b, &ctx->val_a, &ctx->val_b, &ctx->flags, &ctx->scan,
                     &ctx->cub_tmp, &ctx->rays, &ctx->ray_count, &ctx->ray_offset, &ctx->sorted_pts, &ctx->pkey_a,
-                    &ctx->pkey_b, &ctx->touch_ord, &ctx->touch_entry, &ctx->touch_acc, &ctx->touch_bits, &ctx->seg_start, &ctx->long_list, &ctx->long_partials, &ctx->cand_keys, &ctx->cand_list,
+                    &ctx->pkey_b, &ctx->seg_keys_a, &ctx->seg_keys_b, &ctx->seg_idx_a, &ctx->seg_idx_b, &ctx->seg_recs, &ctx->touch_ord, &ctx->touch_entry, &ctx->touch_acc, &ctx->touch_bits, &ctx->seg_start, &ctx->long_list, &ctx->long_partials, &ctx->cand_keys, &ctx->cand_list,
                     &ctx->stage_a, &ctx->stage_b, &ctx->stage_c};
   for (DevBuf* b : bufs) b->release();
   drain_events(ctx);
