@@ -207,8 +207,7 @@ __global__ void k_bundle_histogram(const uint64_t* __restrict__ keys, uint32_t t
   if (threadIdx.x < kSizeClasses) hist[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t nb = *num_heads;
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < nb) {
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
     const BundleInfo bi = bundle_info(keys, total, heads, nb, b);
     if (bi.key == kInvalidPointKey)
       folded[b].frame_clr = kNoRay;  // sentinel bundle of dropped points
@@ -227,7 +226,6 @@ __global__ void k_bundle_order(const uint64_t* __restrict__ keys, uint32_t total
   __shared__ uint32_t base[kSizeClasses];
   __shared__ uint32_t hist[kSizeClasses];
   __shared__ uint32_t offs[kSizeClasses];
-  if (threadIdx.x < kSizeClasses) hist[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     uint32_t acc = 0;
     for (int c = 0; c < kSizeClasses; ++c) {
@@ -235,23 +233,27 @@ __global__ void k_bundle_order(const uint64_t* __restrict__ keys, uint32_t total
       acc += class_count[c];
     }
   }
-  __syncthreads();
   const uint32_t nb = *num_heads;
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  int c = -1;
-  uint32_t rank = 0;
-  if (b < nb) {
-    const BundleInfo bi = bundle_info(keys, total, heads, nb, b);
-    if (bi.key != kInvalidPointKey) {
-      c = size_class(fold_length(bi));
-      rank = atomicAdd(&hist[c], 1u);
+  for (uint32_t b0 = blockIdx.x * blockDim.x; b0 < nb; b0 += gridDim.x * blockDim.x) {
+    __syncthreads();
+    if (threadIdx.x < kSizeClasses) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t b = b0 + threadIdx.x;
+    int c = -1;
+    uint32_t rank = 0;
+    if (b < nb) {
+      const BundleInfo bi = bundle_info(keys, total, heads, nb, b);
+      if (bi.key != kInvalidPointKey) {
+        c = size_class(fold_length(bi));
+        rank = atomicAdd(&hist[c], 1u);
+      }
     }
+    __syncthreads();
+    if (threadIdx.x < kSizeClasses && hist[threadIdx.x])
+      offs[threadIdx.x] = atomicAdd(&class_count[kSizeClasses + threadIdx.x], hist[threadIdx.x]);
+    __syncthreads();
+    if (c >= 0) order[base[c] + offs[c] + rank] = b;
   }
-  __syncthreads();
-  if (threadIdx.x < kSizeClasses && hist[threadIdx.x])
-    offs[threadIdx.x] = atomicAdd(&class_count[kSizeClasses + threadIdx.x], hist[threadIdx.x]);
-  __syncthreads();
-  if (c >= 0) order[base[c] + offs[c] + rank] = b;
 }
 
 // bundles of 64 points or more are the first n_wide entries of `order`
@@ -439,22 +441,23 @@ k_fold_bundles(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t t
 __global__ void k_bundle_rays(IntegratorParams P, const float* __restrict__ poses,
                               const uint32_t* __restrict__ num_heads, Ray* __restrict__ rays,
                               unsigned long long* __restrict__ ray_count) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= *num_heads) return;
-  Ray ray = rays[b];
-  if (ray.frame_clr == kNoRay) {
-    ray_count[b] = 0;
-    return;
+  const uint32_t nb = *num_heads;
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+    Ray ray = rays[b];
+    if (ray.frame_clr == kNoRay) {
+      ray_count[b] = 0;
+      continue;
+    }
+    const Xform T = make_xform(poses + 7 * (ray.frame_clr & 0x7FFFFFFFu));
+    const V3 pg = apply(T, V3{ray.px, ray.py, ray.pz});
+    RayCaster rc;
+    rc.init(T.t, pg, (ray.frame_clr >> 31) != 0, P.carving != 0, P.max_ray, P.voxel_size_inv,
+            P.trunc);
+    rays[b].px = pg.x;
+    rays[b].py = pg.y;
+    rays[b].pz = pg.z;
+    ray_count[b] = rc.valid ? rc.packed_counts() : 0ull;
   }
-  const Xform T = make_xform(poses + 7 * (ray.frame_clr & 0x7FFFFFFFu));
-  const V3 pg = apply(T, V3{ray.px, ray.py, ray.pz});
-  RayCaster rc;
-  rc.init(T.t, pg, (ray.frame_clr >> 31) != 0, P.carving != 0, P.max_ray, P.voxel_size_inv,
-          P.trunc);
-  rays[b].px = pg.x;
-  rays[b].py = pg.y;
-  rays[b].pz = pg.z;
-  ray_count[b] = rc.valid ? rc.packed_counts() : 0ull;
 }
 
 // SIMPLE: one ray per valid point, in (frame, visit rank) order
@@ -1601,7 +1604,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
           dk.Current(), dv.Current(), static_cast<uint32_t>(total), pts, cols,
           ctx->sorted_pts.as<float4>());
       // upper bound on the number of bundles: one per point + the sentinel
-      const unsigned bgrid = grid_for(upper, 256);
+      const unsigned bgrid = std::min<unsigned>(grid_for(upper, 256), ctx->num_sms * 8u);
       k_bundle_histogram<<<bgrid, 256, 0, s>>>(dk.Current(), static_cast<uint32_t>(total),
                                                ctx->scan.as<uint32_t>(), d_num, ctx->d_class_count,
                                                ctx->rays.as<Ray>());
@@ -1616,7 +1619,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
           P, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
           ctx->sorted_pts.as<float4>(), ctx->d_class_count, ctx->ray_offset.as<uint32_t>(),
           ctx->rays.as<Ray>());
-      k_bundle_rays<<<grid_for(upper, 256), 256, 0, s>>>(P, ctx->group_poses, d_num,
+      k_bundle_rays<<<bgrid, 256, 0, s>>>(P, ctx->group_poses, d_num,
                                                          ctx->rays.as<Ray>(),
                                                          ctx->ray_count.as<unsigned long long>());
     }
