@@ -172,7 +172,11 @@ enum Stage {
   kStagePointKeys = 0,
   kStageBundleSort,
   kStageBundleScan,
+  kStageGather,
+  kStageBundleOrder,
+  kStageFoldWide,
   kStageFold,
+  kStageBundleRays,
   kStageRayScan,
   kStageWalkSegments,
   kStageSegmentSort,
@@ -180,6 +184,7 @@ enum Stage {
   kStagePairSort,
   kStageSegments,
   kStageVoxelUpdate,
+  kStageReplayWide,
   kStageFinalize,
   kStageMergeMark,
   kStageMergeResample,

@@ -265,53 +265,60 @@ __device__ __forceinline__ uint32_t wide_count(const uint32_t* __restrict__ clas
   return n;
 }
 
-// Long bundles: one warp per bundle.  The recurrence itself stays sequential, but everything
-// that does not depend on the running mean is taken off its critical path: per chunk of 32
-// points the lanes compute, in parallel, the point weights, then (one short sequential pass)
-// the running weight W_k, then the per-point reciprocal and blend factors and the products
-// p_k w_k, c_k b_k; what remains per point is the 7-operation chain
+// Long bundles: 8 lanes per bundle, 4 bundles per warp.  The recurrence itself stays sequential,
+// but everything that does not depend on the running mean is taken off its critical path: per
+// chunk of 8 points the lanes compute, in parallel, the point weights, then (one short
+// sequential pass) the running weight W_k, then the per-point reciprocal and blend factors and
+// the products p_k w_k, c_k b_k; what remains per point is the 7-operation chain
 //   m <- (m W_{k-1} + p_k w_k) / W_k          (div_with_rcp: exact IEEE quotient)
-// and the colour blend, run as 7 independent chains (x, y, z, r, g, b, a) on 7 lanes.
+// and the colour blend, run as 7 independent chains (x, y, z, r, g, b, a) on 7 of the 8 lanes.
 constexpr int kWideWarps = 4;
+constexpr int kWideGroup = 8;  // lanes per bundle = points per chunk
 __global__ void __launch_bounds__(kWideWarps * 32)
 k_fold_wide(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t total,
             const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
             const float4* __restrict__ sorted, const uint32_t* __restrict__ class_count,
             const uint32_t* __restrict__ order, Ray* __restrict__ folded) {
-  // per point of the chunk: W_{k-1}, W_k, 1/W_k, a = W_{k-1}/W_k, skip, and the 7 chain operands
+  // per point of the chunk: W_{k-1}, W_k, 1/W_k, a = W_{k-1}/W_k, and the 7 chain operands
   __shared__ float s_wprev[kWideWarps][32], s_w[kWideWarps][32], s_r[kWideWarps][32],
       s_a[kWideWarps][32], s_op[kWideWarps][8][32];
-  __shared__ uint32_t s_skip[kWideWarps];
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int sub = lane >> 3, l8 = lane & 7, gbase = lane & ~7;
   const uint32_t nb = *num_heads;
   const uint32_t n_wide = wide_count(class_count, lane);
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
-  const int chain = lane < 7 ? lane : 7;  // 0..2 mean, 3..6 colour, 7 idle
-  for (uint32_t g = warp; g < n_wide; g += num_warps) {
-    const uint32_t b = order[g];
-    const BundleInfo bi = bundle_info(keys, total, heads, nb, b);
-    const uint32_t end = bi.start + bi.n;
-    float W = 0.0f;                               // running weight (same in every lane)
-    float val = (chain == 6) ? 255.0f : 0.0f;     // this lane's chain state (alpha starts at 255)
-    float4 pt = (bi.start + lane < end) ? sorted[bi.start + lane]
-                                        : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    for (uint32_t c0 = bi.start; c0 < end; c0 += 32) {
-      const uint32_t cnt = min(32u, end - c0);
+  const int chain = l8;  // 0..2 mean, 3..6 colour, 7 idle
+  for (uint32_t g = warp * 4u; g < n_wide; g += num_warps * 4u) {
+    const bool have = g + sub < n_wide;
+    uint32_t b = 0, start = 0, end = 0;
+    uint64_t key = 0;
+    if (have) {
+      b = order[g + sub];
+      const BundleInfo bi = bundle_info(keys, total, heads, nb, b);
+      start = bi.start;
+      end = bi.start + bi.n;
+      key = bi.key;
+    }
+    float W = 0.0f;                            // running weight (same in the 8 lanes of a group)
+    float val = (chain == 6) ? 255.0f : 0.0f;  // this lane's chain state (alpha starts at 255)
+    float4 pt = (start + l8 < end) ? sorted[start + l8] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (uint32_t c0 = start; __any_sync(full, c0 < end); c0 += kWideGroup) {
+      const uint32_t cnt = c0 < end ? min(static_cast<uint32_t>(kWideGroup), end - c0) : 0u;
       const float4 p = pt;
-      if (c0 + 32 + lane < end) pt = sorted[c0 + 32 + lane];  // next chunk, in flight
-      const bool valid = static_cast<uint32_t>(lane) < cnt;
+      if (c0 + kWideGroup + l8 < end) pt = sorted[c0 + kWideGroup + l8];  // next chunk, in flight
+      const bool valid = static_cast<uint32_t>(l8) < cnt;
       const float w = valid ? voxel_weight(P, p.z) : 0.0f;
-      const bool skip = !valid || w < kEps;       // reference: "if (w < kEps) continue"
+      const bool skip = !valid || w < kEps;  // reference: "if (w < kEps) continue"
       const float w_eff = skip ? 0.0f : w;
       // running weight: the reference's sequential float sum
       float w_prev_mine = 0.0f, w_mine = 0.0f;
 #pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        const float wt = __shfl_sync(full, w_eff, t);
+      for (int t = 0; t < kWideGroup; ++t) {
+        const float wt = __shfl_sync(full, w_eff, gbase + t);
         const float Wn = W + wt;
-        if (lane == t) {
+        if (l8 == t) {
           w_prev_mine = W;
           w_mine = Wn;
         }
@@ -335,27 +342,26 @@ k_fold_wide(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t tota
       s_op[wib][5][lane] = static_cast<float>((col >> 16) & 255u) * bb;
       s_op[wib][6][lane] = static_cast<float>(col >> 24) * bb;
       s_op[wib][7][lane] = 0.0f;
-      const unsigned skip_mask = __ballot_sync(full, skip);
-      if (lane == 0) s_skip[wib] = skip_mask;
+      const unsigned skip_bits = (__ballot_sync(full, skip) >> gbase) & 0xFFu;
       __syncwarp();
-      // the sequential chains
-      const unsigned sm = s_skip[wib];
-      const float* op = s_op[wib][chain];
-#pragma unroll 4
-      for (uint32_t t = 0; t < cnt; ++t) {
-        const float wp = s_wprev[wib][t], wn = s_w[wib][t], rr = s_r[wib][t], aa = s_a[wib][t];
+      // the sequential chains of the 4 bundles side by side
+      const float* op = s_op[wib][chain] + gbase;
+#pragma unroll
+      for (int t = 0; t < kWideGroup; ++t) {
+        const float wp = s_wprev[wib][gbase + t], wn = s_w[wib][gbase + t];
+        const float rr = s_r[wib][gbase + t], aa = s_a[wib][gbase + t];
         const float o = op[t];
         const float mean = div_with_rcp(val * wp + o, wn, rr);
         const float colr = round_half_away_pos(val * aa + o);
         const float nv = chain < 3 ? mean : colr;
-        if (!((sm >> t) & 1u)) val = nv;
+        if (!((skip_bits >> t) & 1u)) val = nv;
       }
     }
-    const float mx = __shfl_sync(full, val, 0), my = __shfl_sync(full, val, 1);
-    const float mz = __shfl_sync(full, val, 2);
-    const float cr = __shfl_sync(full, val, 3), cg = __shfl_sync(full, val, 4);
-    const float cb = __shfl_sync(full, val, 5), ca = __shfl_sync(full, val, 6);
-    if (lane == 0) {
+    const float mx = __shfl_sync(full, val, gbase + 0), my = __shfl_sync(full, val, gbase + 1);
+    const float mz = __shfl_sync(full, val, gbase + 2);
+    const float cr = __shfl_sync(full, val, gbase + 3), cg = __shfl_sync(full, val, gbase + 4);
+    const float cb = __shfl_sync(full, val, gbase + 5), ca = __shfl_sync(full, val, gbase + 6);
+    if (have && l8 == 0) {
       Ray ray;
       ray.px = mx;  // camera frame; k_bundle_rays moves it to the global frame
       ray.py = my;
@@ -363,7 +369,7 @@ k_fold_wide(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t tota
       ray.weight = W;
       ray.color = pack_rgba(static_cast<uint32_t>(cr), static_cast<uint32_t>(cg),
                             static_cast<uint32_t>(cb), static_cast<uint32_t>(ca));
-      ray.frame_clr = static_cast<uint32_t>(bi.key >> kBundleFrameShift);
+      ray.frame_clr = static_cast<uint32_t>(key >> kBundleFrameShift);
       folded[b] = ray;
     }
   }
@@ -1487,18 +1493,21 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
                                     static_cast<int>(n_general),
                                     SegmentHead{dk.Current(), ray_bits}, s));
     }
+    const uint32_t long_cap = static_cast<uint32_t>(n_general / kWideSegment + 1);
+    const size_t max_items = n_general / kLongSub + long_cap + 1;
+    CG_CUDA(ctx->long_list.reserve(long_cap * sizeof(LongSeg)));
+    CG_CUDA(ctx->long_partials.reserve(max_items * sizeof(LongPartial)));
     {
-      StageScope sc(ctx, kStageVoxelUpdate, 3);
-      const uint32_t long_cap = static_cast<uint32_t>(n_general / kWideSegment + 1);
-      const size_t max_items = n_general / kLongSub + long_cap + 1;
-      CG_CUDA(ctx->long_list.reserve(long_cap * sizeof(LongSeg)));
-      CG_CUDA(ctx->long_partials.reserve(max_items * sizeof(LongPartial)));
+      StageScope sc(ctx, kStageVoxelUpdate, 1);
       CG_CUDA(fill_bytes(ctx->d_work_counter, 0, sizeof(uint32_t), s));
       CG_CUDA(fill_bytes(ctx->d_long_counter, 0, sizeof(unsigned long long), s));
       k_voxel_update<<<ctx->num_sms * 8, 128, 0, s>>>(
           P, ctx->group_poses, ctx->rays.as<Ray>(), dk.Current(), ray_bits, n_general,
           ctx->seg_start.as<uint32_t>(), d_num, ctx->d_work_counter, ctx->d_long_counter,
           ctx->long_list.as<LongSeg>(), long_cap, L->v, tv);
+    }
+    {
+      StageScope sc(ctx, kStageReplayWide, 2);
       k_long_partials<<<ctx->num_sms * 8, 256, 0, s>>>(
           P, ctx->group_poses, ctx->rays.as<Ray>(), dk.Current(), ray_bits,
           ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv,
@@ -1597,31 +1606,42 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
       CG_CUDA(cub::DeviceSelect::If(ctx->cub_tmp.p, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
                                     static_cast<int>(total), BundleHead{dk.Current()}, s));
     }
+    // upper bound on the number of bundles: one per point + the sentinel
+    const unsigned bgrid = std::min<unsigned>(grid_for(upper, 256), ctx->num_sms * 8u);
     {
-      StageScope sc(ctx, kStageFold, 6);
-      CG_CUDA(fill_bytes(ctx->d_class_count, 0, 2 * kSizeClasses * sizeof(uint32_t), s));
+      StageScope sc(ctx, kStageGather, 1);
       k_gather_sorted<<<grid_for(total, 256), 256, 0, s>>>(
           dk.Current(), dv.Current(), static_cast<uint32_t>(total), pts, cols,
           ctx->sorted_pts.as<float4>());
-      // upper bound on the number of bundles: one per point + the sentinel
-      const unsigned bgrid = std::min<unsigned>(grid_for(upper, 256), ctx->num_sms * 8u);
+    }
+    {
+      StageScope sc(ctx, kStageBundleOrder, 3);
+      CG_CUDA(fill_bytes(ctx->d_class_count, 0, 2 * kSizeClasses * sizeof(uint32_t), s));
       k_bundle_histogram<<<bgrid, 256, 0, s>>>(dk.Current(), static_cast<uint32_t>(total),
                                                ctx->scan.as<uint32_t>(), d_num, ctx->d_class_count,
                                                ctx->rays.as<Ray>());
       k_bundle_order<<<bgrid, 256, 0, s>>>(dk.Current(), static_cast<uint32_t>(total),
                                            ctx->scan.as<uint32_t>(), d_num, ctx->d_class_count,
                                            ctx->ray_offset.as<uint32_t>());
+    }
+    {
+      StageScope sc(ctx, kStageFoldWide, 1);
       k_fold_wide<<<ctx->num_sms * 12, kWideWarps * 32, 0, s>>>(
           P, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
           ctx->sorted_pts.as<float4>(), ctx->d_class_count, ctx->ray_offset.as<uint32_t>(),
           ctx->rays.as<Ray>());
+    }
+    {
+      StageScope sc(ctx, kStageFold, 1);
       k_fold_bundles<<<ctx->num_sms * 12, 128, 0, s>>>(
           P, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
           ctx->sorted_pts.as<float4>(), ctx->d_class_count, ctx->ray_offset.as<uint32_t>(),
           ctx->rays.as<Ray>());
-      k_bundle_rays<<<bgrid, 256, 0, s>>>(P, ctx->group_poses, d_num,
-                                                         ctx->rays.as<Ray>(),
-                                                         ctx->ray_count.as<unsigned long long>());
+    }
+    {
+      StageScope sc(ctx, kStageBundleRays, 1);
+      k_bundle_rays<<<bgrid, 256, 0, s>>>(P, ctx->group_poses, d_num, ctx->rays.as<Ray>(),
+                                          ctx->ray_count.as<unsigned long long>());
     }
   } else {
     {
@@ -1629,7 +1649,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
       CG_CUDA(cub::DeviceSelect::If(ctx->cub_tmp.p, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
                                     static_cast<int>(total), valid, s));
     }
-    StageScope sc(ctx, kStageFold, 1);
+    StageScope sc(ctx, kStageBundleRays, 1);
     k_simple_rays<<<grid_for(total, 256), 256, 0, s>>>(
         P, ctx->group_poses, ft, ctx->scan.as<uint32_t>(), d_num, pts,
         cols, ctx->rays.as<Ray>(), ctx->ray_count.as<unsigned long long>());

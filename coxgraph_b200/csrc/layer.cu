@@ -25,9 +25,10 @@ int32_t cuda_fail(cudaError_t e, const char* what) {
 
 const char* stage_name(int s) {
   static const char* names[kNumStages] = {
-      "point_keys", "bundle_sort",  "bundle_scan", "bundle_fold",  "ray_scan",   "walk_segments",
-      "segment_sort", "block_accumulate", "pair_sort",    "segments",    "voxel_update", "finalize",   "merge_mark",
-      "merge_resample", "transfer"};
+      "point_keys",    "bundle_sort",  "bundle_scan",      "gather_sorted", "bundle_order",
+      "fold_wide",     "fold_bundles", "bundle_rays",      "ray_scan",      "walk_segments",
+      "segment_sort",  "block_accumulate", "pair_sort",    "segments",      "voxel_update",
+      "replay_wide",   "finalize",     "merge_mark",       "merge_resample", "transfer"};
   return (s >= 0 && s < kNumStages) ? names[s] : "?";
 }
 
