@@ -27,7 +27,7 @@ constexpr int kVoxIdxOffset = 1 << 19;
 constexpr uint64_t kInvalidPointKey = ~0ull;         // sorts behind every valid key
 constexpr int kClearingBit = 60;
 
-enum ErrBits { kErrPoolFull = 1, kErrOutOfRange = 2, kErrTouchFull = 4, kErrSegmentFull = 8 };
+enum ErrBits { kErrPoolFull = 1, kErrOutOfRange = 2, kErrTouchFull = 4, kErrSegmentFull = 8, kErrKeyRange = 16 };
 
 // ------------------------------------------------------------------ key packing
 __host__ __device__ __forceinline__ uint64_t pack_block_key(int x, int y, int z) {
@@ -160,6 +160,7 @@ struct CallCounters {
   unsigned long long touched;
   unsigned long long general_pairs;
   unsigned long long segments;
+  uint32_t key_reach;  // farthest voxel offset of a point that did not fit the bundle key layout
   unsigned long long candidates;
   unsigned long long blocks_out;
   int err;
@@ -224,7 +225,8 @@ struct cg_context {
   cg::DevBuf touch_ord, touch_entry, touch_acc, touch_bits;
   uint32_t* d_touch_count = nullptr;  // [0] blocks touched, [1] general (voxel, ray) keys emitted
   uint32_t* d_class_count = nullptr;    // bundle size-class histogram + scatter cursors
-  uint32_t* d_walk_counters = nullptr;  // dynamic ray-batch counters of the two walks
+  uint32_t* d_walk_counters = nullptr;  // [0],[1] dynamic work counters, [2] bundle key reach
+  int rel_bits_hint = 0;                // voxel field width of the bundle keys (adaptive)
   size_t touch_cap = 0;               // blocks the scratch holds
   bool touch_clean = false;
   unsigned long long* d_long_counter = nullptr;  // (#long segments << 32) | #sub-blocks

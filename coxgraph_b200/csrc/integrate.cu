@@ -65,12 +65,27 @@ struct Ray {           // 24 B
 };
 constexpr uint32_t kNoRay = 0xFFFFFFFFu;
 
-// bundle key layout: [frame | clearing(1) | z(13) y(13) x(13)], voxel index relative to the
-// voxel holding the sensor origin
-constexpr int kRelBits = 13;
-constexpr int kRelOffset = 1 << (kRelBits - 1);
-constexpr int kBundleClearBit = 3 * kRelBits;
-constexpr int kBundleFrameShift = kBundleClearBit + 1;
+// Bundle key (u64): [frame | clearing(1) | z y x (rel_bits each) | visit rank (rank_bits)].
+// z, y, x: voxel index of the point relative to the voxel holding the sensor origin; visit rank:
+// position of the point in the reference's visiting order of its frame.  The keys are sorted on
+// the bits above the rank only (keys-only radix sort, begin_bit = rank_bits): a stable sort keeps
+// equal bundles in visiting order, and the point index is recovered from (frame, rank), so no
+// value array travels through the sort.  The widths are chosen per group by the host
+// (make_key_layout): they must fit 63 bits together with the frame field.
+struct KeyLayout {
+  int rank_bits, rel_bits;
+  __host__ __device__ __forceinline__ int clear_bit() const { return rank_bits + 3 * rel_bits; }
+  __host__ __device__ __forceinline__ int frame_shift() const { return clear_bit() + 1; }
+  __host__ __device__ __forceinline__ int rel_offset() const { return 1 << (rel_bits - 1); }
+  __device__ __forceinline__ bool clearing(uint64_t key) const { return (key >> clear_bit()) & 1; }
+  __device__ __forceinline__ uint32_t frame(uint64_t key) const {
+    return static_cast<uint32_t>(key >> frame_shift());
+  }
+  __device__ __forceinline__ uint32_t rank(uint64_t key) const {
+    return static_cast<uint32_t>(key & ((1ull << rank_bits) - 1ull));
+  }
+};
+constexpr int kMaxRelBits = 13;
 
 __device__ __forceinline__ int order_index(int k, int n, int mode) {
   // voxblox MixedThreadSafeIndex: groups of 1024 visited round-robin
@@ -102,17 +117,17 @@ struct FrameTable {
 };
 
 // ------------------------------------------------------------------ front half
-// slot g enumerates (frame, visit rank k); vals = global point index
-__global__ void k_point_keys(IntegratorParams P, const float* __restrict__ poses, FrameTable ft,
-                             const float* __restrict__ pts, uint64_t total,
-                             uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                             int32_t* err) {
+// slot g enumerates (frame, visit rank k)
+__global__ void k_point_keys(IntegratorParams P, KeyLayout kl, const float* __restrict__ poses,
+                             FrameTable ft, const float* __restrict__ pts, uint64_t total,
+                             uint64_t* __restrict__ keys, int32_t* err, uint32_t* key_reach) {
   const uint64_t g = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
   if (g >= total) return;
   const int f = ft.frame_of(g);
   const uint64_t base = ft.start(f);
   const int n = static_cast<int>(ft.start(f + 1) - base);
-  const int i = order_index(static_cast<int>(g - base), n, P.order_mode);
+  const uint32_t k = static_cast<uint32_t>(g - base);
+  const int i = order_index(static_cast<int>(k), n, P.order_mode);
   const V3 pc = load_point(pts, base + i);
   bool clearing = false;
   uint64_t key = kInvalidPointKey;
@@ -125,42 +140,49 @@ __global__ void k_point_keys(IntegratorParams P, const float* __restrict__ poses
       const int rx = grid_index(pg.x, P.voxel_size_inv) - grid_index(T.t.x, P.voxel_size_inv);
       const int ry = grid_index(pg.y, P.voxel_size_inv) - grid_index(T.t.y, P.voxel_size_inv);
       const int rz = grid_index(pg.z, P.voxel_size_inv) - grid_index(T.t.z, P.voxel_size_inv);
-      if (abs(rx) < kRelOffset && abs(ry) < kRelOffset && abs(rz) < kRelOffset) {
-        key = (static_cast<uint64_t>(f) << kBundleFrameShift) |
-              (static_cast<uint64_t>(clearing) << kBundleClearBit) |
-              (static_cast<uint64_t>(rz + kRelOffset) << (2 * kRelBits)) |
-              (static_cast<uint64_t>(ry + kRelOffset) << kRelBits) |
-              static_cast<uint64_t>(rx + kRelOffset);
+      const int ro = kl.rel_offset();
+      if (abs(rx) < ro && abs(ry) < ro && abs(rz) < ro) {
+        key = (static_cast<uint64_t>(f) << kl.frame_shift()) |
+              (static_cast<uint64_t>(clearing) << kl.clear_bit()) |
+              (static_cast<uint64_t>(rz + ro) << (kl.rank_bits + 2 * kl.rel_bits)) |
+              (static_cast<uint64_t>(ry + ro) << (kl.rank_bits + kl.rel_bits)) |
+              (static_cast<uint64_t>(rx + ro) << kl.rank_bits) | k;
       } else {
-        atomicOr(err, kErrOutOfRange);
+        // farther from the sensor than this group's key layout reaches: the host retries with
+        // wider voxel fields (fewer frames per group if need be); key_reach tells how wide
+        atomicOr(err, kErrKeyRange);
+        atomicMax(key_reach, static_cast<uint32_t>(max(abs(rx), max(abs(ry), abs(rz)))));
       }
     } else {
       atomicOr(err, kErrOutOfRange);
     }
   }
   keys[g] = key;
-  vals[g] = static_cast<uint32_t>(base + i);
 }
 
 struct BundleHead {
   const uint64_t* keys;
+  int rank_bits;
   __device__ __forceinline__ bool operator()(uint32_t i) const {
     // the first invalid key is a head too: it terminates the last real bundle
-    return i == 0 || keys[i] != keys[i - 1];
+    return i == 0 || (keys[i] >> rank_bits) != (keys[i - 1] >> rank_bits);
   }
 };
 
 // Gather the sorted points next to each other: (x, y, z, rgba) per sorted slot, so that the
-// sequential fold streams contiguous memory.
-__global__ void k_gather_sorted(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                uint32_t total, const float* __restrict__ pts,
+// sequential fold streams contiguous memory.  The point index comes from the key's (frame, rank).
+__global__ void k_gather_sorted(KeyLayout kl, int order_mode, const uint64_t* __restrict__ keys,
+                                uint32_t total, FrameTable ft, const float* __restrict__ pts,
                                 const uint32_t* __restrict__ cols, float4* __restrict__ out) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= total) return;
-  if (keys[j] == kInvalidPointKey) return;
-  const uint32_t i = vals[j];
-  out[j] = make_float4(pts[3 * size_t(i)], pts[3 * size_t(i) + 1], pts[3 * size_t(i) + 2],
-                       __uint_as_float(cols[i]));
+  const uint64_t key = keys[j];
+  if (key == kInvalidPointKey) return;
+  const int f = static_cast<int>(kl.frame(key));
+  const uint64_t base = ft.start(f);
+  const int n = static_cast<int>(ft.start(f + 1) - base);
+  const size_t i = base + order_index(static_cast<int>(kl.rank(key)), n, order_mode);
+  out[j] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], __uint_as_float(cols[i]));
 }
 
 // MergedTsdfIntegrator::integrateVoxel, first half: the reference's *sequential* weighted mean and
@@ -194,12 +216,12 @@ __device__ __forceinline__ BundleInfo bundle_info(const uint64_t* __restrict__ k
   return bi;
 }
 // a clearing bundle only uses its first point with a valid weight: it is short whatever its size
-__device__ __forceinline__ uint32_t fold_length(const BundleInfo& bi) {
-  return ((bi.key >> kBundleClearBit) & 1) ? 1u : bi.n;
+__device__ __forceinline__ uint32_t fold_length(const KeyLayout& kl, const BundleInfo& bi) {
+  return kl.clearing(bi.key) ? 1u : bi.n;
 }
 
 // class_count[0 .. kSizeClasses): histogram; [kSizeClasses .. 2 kSizeClasses): scatter cursors
-__global__ void k_bundle_histogram(const uint64_t* __restrict__ keys, uint32_t total,
+__global__ void k_bundle_histogram(KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
                                    const uint32_t* __restrict__ heads,
                                    const uint32_t* __restrict__ num_heads, uint32_t* class_count,
                                    Ray* __restrict__ folded) {
@@ -212,14 +234,14 @@ __global__ void k_bundle_histogram(const uint64_t* __restrict__ keys, uint32_t t
     if (bi.key == kInvalidPointKey)
       folded[b].frame_clr = kNoRay;  // sentinel bundle of dropped points
     else
-      atomicAdd(&hist[size_class(fold_length(bi))], 1u);
+      atomicAdd(&hist[size_class(fold_length(kl, bi))], 1u);
   }
   __syncthreads();
   if (threadIdx.x < kSizeClasses && hist[threadIdx.x])
     atomicAdd(&class_count[threadIdx.x], hist[threadIdx.x]);
 }
 
-__global__ void k_bundle_order(const uint64_t* __restrict__ keys, uint32_t total,
+__global__ void k_bundle_order(KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
                                const uint32_t* __restrict__ heads,
                                const uint32_t* __restrict__ num_heads, uint32_t* class_count,
                                uint32_t* __restrict__ order) {
@@ -244,7 +266,7 @@ __global__ void k_bundle_order(const uint64_t* __restrict__ keys, uint32_t total
     if (b < nb) {
       const BundleInfo bi = bundle_info(keys, total, heads, nb, b);
       if (bi.key != kInvalidPointKey) {
-        c = size_class(fold_length(bi));
+        c = size_class(fold_length(kl, bi));
         rank = atomicAdd(&hist[c], 1u);
       }
     }
@@ -275,7 +297,7 @@ __device__ __forceinline__ uint32_t wide_count(const uint32_t* __restrict__ clas
 constexpr int kWideWarps = 4;
 constexpr int kWideGroup = 8;  // lanes per bundle = points per chunk
 __global__ void __launch_bounds__(kWideWarps * 32)
-k_fold_wide(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t total,
+k_fold_wide(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
             const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
             const float4* __restrict__ sorted, const uint32_t* __restrict__ class_count,
             const uint32_t* __restrict__ order, Ray* __restrict__ folded) {
@@ -369,7 +391,7 @@ k_fold_wide(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t tota
       ray.weight = W;
       ray.color = pack_rgba(static_cast<uint32_t>(cr), static_cast<uint32_t>(cg),
                             static_cast<uint32_t>(cb), static_cast<uint32_t>(ca));
-      ray.frame_clr = static_cast<uint32_t>(key >> kBundleFrameShift);
+      ray.frame_clr = kl.frame(key);
       folded[b] = ray;
     }
   }
@@ -378,7 +400,7 @@ k_fold_wide(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t tota
 constexpr int kFoldDepth = 4;  // points in flight per lane
 
 __global__ void __launch_bounds__(128)
-k_fold_bundles(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t total,
+k_fold_bundles(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
                const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
                const float4* __restrict__ sorted, const uint32_t* __restrict__ class_count,
                const uint32_t* __restrict__ order, Ray* __restrict__ folded) {
@@ -402,8 +424,8 @@ k_fold_bundles(IntegratorParams P, const uint64_t* __restrict__ keys, uint32_t t
       const BundleInfo bi = bundle_info(keys, total, heads, nb, b);
       cur = bi.start;
       n = bi.n;
-      clearing = (bi.key >> kBundleClearBit) & 1;
-      frame_clr = static_cast<uint32_t>(bi.key >> kBundleFrameShift) | (clearing ? 0x80000000u : 0u);
+      clearing = kl.clearing(bi.key);
+      frame_clr = kl.frame(bi.key) | (clearing ? 0x80000000u : 0u);
     }
     const uint32_t end = cur + n;
     float4 q[kFoldDepth];
@@ -512,7 +534,13 @@ __global__ void k_simple_rays(IntegratorParams P, const float* __restrict__ pose
 }
 
 __global__ void k_totals(const uint32_t* num_rays, const unsigned long long* ray_count,
-                         const unsigned long long* ray_offset, size_t upper, CallCounters* c) {
+                         const unsigned long long* ray_offset, size_t upper, CallCounters* c,
+                         int32_t* err, uint32_t* key_reach) {
+  const int e = *err;  // a point outside the group's key layout: the host widens it / regroups
+  c->err = e & kErrKeyRange;
+  if (e & kErrKeyRange) *err = e & ~kErrKeyRange;
+  c->key_reach = *key_reach;
+  *key_reach = 0;
   c->rays = *num_rays;
   const unsigned long long tot = upper ? ray_offset[upper - 1] + ray_count[upper - 1] : 0ull;
   c->pairs = tot & 0xFFFFFFFFull;   // voxel visits (the host splits jobs that reach 2^32)
@@ -1537,7 +1565,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
                                const IntegratorParams& P, const float* h_poses,
                                const float* d_points, const uint8_t* d_colors,
                                const uint64_t* offs, size_t f0, size_t f1,
-                               cg_integrate_stats* stats) {
+                               cg_integrate_stats* stats, int rel_bits_floor = 0) {
   cg_context* ctx = L->ctx;
   cudaStream_t s = ctx->stream;
   const size_t F = f1 - f0;
@@ -1556,15 +1584,36 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   if (merged) {
     CG_CUDA(ctx->key_a.reserve(total * sizeof(uint64_t)));
     CG_CUDA(ctx->key_b.reserve(total * sizeof(uint64_t)));
-    CG_CUDA(ctx->val_a.reserve(total * sizeof(uint32_t)));
-    CG_CUDA(ctx->val_b.reserve(total * sizeof(uint32_t)));
     CG_CUDA(ctx->sorted_pts.reserve(total * sizeof(float4)));
   }
+  // bundle key layout of this group: as many bits per voxel axis as fit beside the frame field
+  // and the visit rank (at most 13: +-4096 voxels around the sensor)
   int frame_bits = 0;
   while ((size_t(1) << frame_bits) < F) ++frame_bits;
-  const int bundle_bits = kBundleFrameShift + frame_bits;
+  size_t max_frame_points = 1;
+  for (size_t f = f0; f < f1; ++f) max_frame_points = std::max<size_t>(max_frame_points, offs[f + 1] - offs[f]);
+  KeyLayout kl;
+  kl.rank_bits = std::max(1, ceil_log2(max_frame_points));
+  // voxel field width: what the sensor range needs (x4 head room for clearing points beyond
+  // max_ray), or what an earlier job on this context turned out to need; fewer bits = fewer
+  // radix passes.  A point beyond the reach flags kErrKeyRange and the group is redone wider.
+  const int avail_bits = std::min(kMaxRelBits, (63 - frame_bits - kl.rank_bits - 1) / 3);
+  if (ctx->rel_bits_hint == 0)
+    ctx->rel_bits_hint = std::min(
+        kMaxRelBits, ceil_log2(static_cast<uint64_t>(P.max_ray * P.voxel_size_inv) + 4) + 3);
+  kl.rel_bits = std::min(avail_bits, std::max(ctx->rel_bits_hint, rel_bits_floor));
+  if (merged && kl.rel_bits < 8) {
+    if (F > 1) {  // fewer frames per group leave more bits for the voxel fields
+      const size_t mid = f0 + F / 2;
+      int32_t rc = integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, mid, stats);
+      if (rc) return rc;
+      return integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, mid, f1, stats);
+    }
+    set_error("a single frame of %zu points is too large; split the point cloud", total);
+    return CG_ERR_INVALID_ARG;
+  }
+  const int bundle_end_bit = kl.frame_shift() + frame_bits;
   cub::DoubleBuffer<uint64_t> dk(ctx->key_a.as<uint64_t>(), ctx->key_b.as<uint64_t>());
-  cub::DoubleBuffer<uint32_t> dv(ctx->val_a.as<uint32_t>(), ctx->val_b.as<uint32_t>());
   thrust::counting_iterator<uint32_t> iota(0);
   uint32_t* d_num = ctx->d_select_count;
   // the job's poses and frame offsets were uploaded once by integrate_job
@@ -1575,9 +1624,10 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   ValidSlot valid{P, ft, pts};
   size_t tmp_sort = 0, tmp_sel = 0, tmp_scan = 0;
   if (merged) {
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, dk, dv, total, 0, bundle_bits, s);
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, dk, static_cast<int>(total), kl.rank_bits,
+                                   bundle_end_bit, s);
     cub::DeviceSelect::If(nullptr, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
-                          static_cast<int>(total), BundleHead{nullptr}, s);
+                          static_cast<int>(total), BundleHead{nullptr, 0}, s);
   } else {
     cub::DeviceSelect::If(nullptr, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
                           static_cast<int>(total), valid, s);
@@ -1592,49 +1642,49 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   if (merged) {
     {
       StageScope sc(ctx, kStagePointKeys, 1);
-      k_point_keys<<<grid_for(total, 256), 256, 0, s>>>(
-          P, ctx->group_poses, ft, pts, total,
-          ctx->key_a.as<uint64_t>(), ctx->val_a.as<uint32_t>(), L->v.err);
+      k_point_keys<<<grid_for(total, 256), 256, 0, s>>>(P, kl, ctx->group_poses, ft, pts, total,
+                                                        ctx->key_a.as<uint64_t>(), L->v.err,
+                                                        ctx->d_walk_counters + 2);
     }
     {
       StageScope sc(ctx, kStageBundleSort, 0);
-      CG_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_sort, dk, dv, total, 0,
-                                              bundle_bits, s));
+      CG_CUDA(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tmp_sort, dk, static_cast<int>(total),
+                                             kl.rank_bits, bundle_end_bit, s));
     }
     {
       StageScope sc(ctx, kStageBundleScan, 0);
       CG_CUDA(cub::DeviceSelect::If(ctx->cub_tmp.p, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
-                                    static_cast<int>(total), BundleHead{dk.Current()}, s));
+                                    static_cast<int>(total), BundleHead{dk.Current(), kl.rank_bits}, s));
     }
     // upper bound on the number of bundles: one per point + the sentinel
     const unsigned bgrid = std::min<unsigned>(grid_for(upper, 256), ctx->num_sms * 8u);
     {
       StageScope sc(ctx, kStageGather, 1);
       k_gather_sorted<<<grid_for(total, 256), 256, 0, s>>>(
-          dk.Current(), dv.Current(), static_cast<uint32_t>(total), pts, cols,
+          kl, P.order_mode, dk.Current(), static_cast<uint32_t>(total), ft, pts, cols,
           ctx->sorted_pts.as<float4>());
     }
     {
       StageScope sc(ctx, kStageBundleOrder, 3);
       CG_CUDA(fill_bytes(ctx->d_class_count, 0, 2 * kSizeClasses * sizeof(uint32_t), s));
-      k_bundle_histogram<<<bgrid, 256, 0, s>>>(dk.Current(), static_cast<uint32_t>(total),
+      k_bundle_histogram<<<bgrid, 256, 0, s>>>(kl, dk.Current(), static_cast<uint32_t>(total),
                                                ctx->scan.as<uint32_t>(), d_num, ctx->d_class_count,
                                                ctx->rays.as<Ray>());
-      k_bundle_order<<<bgrid, 256, 0, s>>>(dk.Current(), static_cast<uint32_t>(total),
+      k_bundle_order<<<bgrid, 256, 0, s>>>(kl, dk.Current(), static_cast<uint32_t>(total),
                                            ctx->scan.as<uint32_t>(), d_num, ctx->d_class_count,
                                            ctx->ray_offset.as<uint32_t>());
     }
     {
       StageScope sc(ctx, kStageFoldWide, 1);
       k_fold_wide<<<ctx->num_sms * 12, kWideWarps * 32, 0, s>>>(
-          P, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
+          P, kl, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
           ctx->sorted_pts.as<float4>(), ctx->d_class_count, ctx->ray_offset.as<uint32_t>(),
           ctx->rays.as<Ray>());
     }
     {
       StageScope sc(ctx, kStageFold, 1);
       k_fold_bundles<<<ctx->num_sms * 12, 128, 0, s>>>(
-          P, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
+          P, kl, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
           ctx->sorted_pts.as<float4>(), ctx->d_class_count, ctx->ray_offset.as<uint32_t>(),
           ctx->rays.as<Ray>());
     }
@@ -1661,10 +1711,9 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
                                           ctx->ray_offset.as<unsigned long long>(),
                                           static_cast<int>(upper), s));
     k_totals<<<1, 1, 0, s>>>(d_num, ctx->ray_count.as<unsigned long long>(),
-                             ctx->ray_offset.as<unsigned long long>(),
-                             upper, ctx->d_counters);
+                             ctx->ray_offset.as<unsigned long long>(), upper, ctx->d_counters,
+                             L->v.err, ctx->d_walk_counters + 2);
   }
-  // the staged host buffer (rel) must outlive its async copy: the sync below covers it
   CG_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(CallCounters),
                           cudaMemcpyDeviceToHost, s));
   CG_CUDA(cudaStreamSynchronize(s));
@@ -1672,7 +1721,20 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   const uint32_t num_rays = static_cast<uint32_t>(ctx->h_counters->rays);
   const size_t num_pairs = ctx->h_counters->pairs;
   const size_t max_pairs = env_size("CG_MAX_PAIRS", size_t(768) << 20);
-  if (num_pairs > max_pairs || num_pairs >= 0x7FFFFFF0ull) {
+  const bool key_range = (ctx->h_counters->err & kErrKeyRange) != 0;
+  if (key_range) {
+    // voxel field width that reaches the farthest point: |rel| < 2^(bits - 1)
+    const int needed = ceil_log2(uint64_t(ctx->h_counters->key_reach) + 1) + 1;
+    if (needed <= avail_bits && needed > kl.rel_bits) {
+      ctx->rel_bits_hint = std::max(ctx->rel_bits_hint, needed);  // remembered for later jobs
+      return integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, f1, stats, needed);
+    }
+    if (F == 1) {
+      set_error("a point lies more than %d voxels from the sensor", 1 << (kl.rel_bits - 1));
+      return CG_ERR_OUT_OF_RANGE;
+    }
+  }
+  if (key_range || num_pairs > max_pairs || num_pairs >= 0x7FFFFFF0ull) {
     if (F > 1) {  // the front half never touches the layer: safe to redo in two halves
       const size_t mid = f0 + F / 2;
       int32_t rc = integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, mid, stats);

@@ -228,7 +228,8 @@ int32_t cg_context_create(int32_t device, void* stream, cg_context** out) {
   CG_CUDA(cudaMalloc(&ctx->d_long_counter, sizeof(unsigned long long)));
   CG_CUDA(cudaMalloc(&ctx->d_select_count, sizeof(uint32_t)));
   CG_CUDA(cudaMalloc(&ctx->d_touch_count, 2 * sizeof(uint32_t)));
-  CG_CUDA(cudaMalloc(&ctx->d_walk_counters, 2 * sizeof(uint32_t)));
+  CG_CUDA(cudaMalloc(&ctx->d_walk_counters, 4 * sizeof(uint32_t)));
+  CG_CUDA(cudaMemsetAsync(ctx->d_walk_counters, 0, 4 * sizeof(uint32_t), ctx->stream));
   CG_CUDA(cudaMalloc(&ctx->d_class_count, 128 * sizeof(uint32_t)));
   CG_CUDA(cudaMemsetAsync(ctx->d_select_count, 0, sizeof(uint32_t), ctx->stream));
   *out = ctx;

@@ -68,6 +68,29 @@ def test_batch_pipelined_transfer(gpu_ctx, monkeypatch):
     gl.close()
 
 
+def test_far_points_regroup_then_out_of_range(gpu_ctx):
+    """A batch packs fewer bits per voxel axis into its bundle keys than a single frame; a point
+    beyond that reach makes the library regroup (fewer frames per group) instead of failing, and
+    only a point beyond the single-frame reach (4096 voxels) is an error."""
+    from coxgraph_b200 import Layer, TsdfIntegrator, capi
+    frames = util.small_frames(5, stride=8)
+    T, p, c = frames[2]
+    p = p.copy()
+    p[7] = (0.5, -0.3, 150.0)          # 3000 voxels away: a clearing ray (beyond max_ray)
+    frames[2] = (T, p, c)
+    got, ref, gl = _run_both(gpu_ctx, frames, batch=True)
+    util.compare_layers(got, ref, "far clearing point in a batch")
+    gl.close()
+    _, gcfg = util.make_cfgs()
+    gl = Layer(gpu_ctx, 0.05, max_blocks=2048)
+    p2 = p.copy()
+    p2[7] = (0.0, 0.0, 300.0)
+    with pytest.raises(capi.CgError) as e:
+        TsdfIntegrator(gcfg, gl).integratePointCloud(T, p2, c)
+    assert e.value.status == capi.CG_ERR_OUT_OF_RANGE
+    gl.close()
+
+
 def test_staged_double_buffer(gpu_ctx):
     """cg_stage_batch_async + cg_integrate_batch_staged: inputs of job k+1 are copied while job k
     is fused; results equal the plain calls."""
