@@ -234,6 +234,7 @@ struct cg_context {
   uint32_t* d_work_counter = nullptr;  // dynamic work distribution of the persistent kernels
   // merge / transfer scratch
   cg::DevBuf cand_keys, cand_list, stage_a, stage_b, stage_c;
+  cg::DevBuf batch_desc, merge_temp, merge_flags;  // batched projection (merge.cu)
   // instrumentation
   bool profiling = false;
   uint64_t own_launches = 0;  // kernels of this library launched (library sorts/scans excluded)

@@ -12,13 +12,23 @@
 //                       only if any voxel succeeded — claim / find the destination block and fold
 //                       the 4096 resampled voxels into it (mergeVoxelAIntoVoxelB).  The temporary
 //                       transformed layer of the reference never exists in memory.
+#include <cub/cub.cuh>
+#include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include <algorithm>
 
 #include "cg_internal.cuh"
 
 namespace cg {
+
+static size_t env_size_merge(const char* name, size_t dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return static_cast<size_t>(strtoull(v, nullptr, 10));
+}
 
 constexpr int kTab = 4;  // cached neighbourhood of source block slots: kTab^3
 
@@ -112,8 +122,9 @@ __device__ __forceinline__ bool resample_voxel(const LayerView& A, const SlotTab
   const V3 rel = p - org;
   const int v0[3] = {grid_index(rel.x, A.voxel_size_inv), grid_index(rel.y, A.voxel_size_inv),
                      grid_index(rel.z, A.voxel_size_inv)};
-  // ---- trilinear (R8)
-  bool ok = true;
+  // ---- trilinear (R8).  All eight taps are addressed first and their loads issued together
+  // (weights, then distances and colours): two memory round trips per voxel instead of one per
+  // tap — the gather is latency-bound, not bandwidth-bound.
   {
     int v[3] = {v0[0], v0[1], v0[2]};
     const V3 vc = org + V3{center_coord(v[0], A.voxel_size), center_coord(v[1], A.voxel_size),
@@ -133,9 +144,8 @@ __device__ __forceinline__ bool resample_voxel(const LayerView& A, const SlotTab
     }
     int base_slot = slot0;
     if (moved) base_slot = lookup_block(A, tab, b[0], b[1], b[2]);
-    if (base_slot < 0) ok = false;
-    float q[8], dd[8], ww[8];
-    uint32_t cc[8];
+    bool ok = base_slot >= 0;
+    const float* tap[8];  // distance plane address of every tap (weight / colour at fixed offsets)
     if (ok) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -150,52 +160,46 @@ __device__ __forceinline__ bool resample_voxel(const LayerView& A, const SlotTab
               nv[a] -= kVps;
             }
           slot = lookup_block(A, tab, nb[0], nb[1], nb[2]);
-          if (slot < 0) {
-            ok = false;
-            break;
-          }
+          if (slot < 0) ok = false;
         }
-        if (i == 0) {
-          const V3 no = V3{static_cast<float>(nb[0]) * A.block_size,
-                           static_cast<float>(nb[1]) * A.block_size,
-                           static_cast<float>(nb[2]) * A.block_size};
-          const V3 vpos = no + V3{center_coord(nv[0], A.voxel_size),
-                                  center_coord(nv[1], A.voxel_size),
-                                  center_coord(nv[2], A.voxel_size)};
-          const V3 o = (p - vpos) * A.voxel_size_inv;
-          q[0] = 1.0f;
-          q[1] = o.x;
-          q[2] = o.y;
-          q[3] = o.z;
-          q[4] = o.x * o.y;
-          q[5] = o.y * o.z;
-          q[6] = o.z * o.x;
-          q[7] = o.x * o.y * o.z;
-        }
-        const int lin = nv[0] + kVps * (nv[1] + kVps * nv[2]);
-        const float w = A.weight_plane(slot)[lin];
-        if (!(w > kEps)) {  // utils::isObservedVoxel
-          ok = false;
-          break;
-        }
-        ww[i] = w;
-        dd[i] = A.dist_plane(slot)[lin];
-        cc[i] = A.color_plane(slot)[lin];
+        tap[i] = A.dist_plane(slot < 0 ? 0 : slot) + (nv[0] + kVps * (nv[1] + kVps * nv[2]));
       }
     }
     if (ok) {
-      out.d = interp_member(q, dd);
-      out.w = interp_member(q, ww);
-      float ch[8];
-      uint32_t rgba = 0;
+      float ww[8];
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
+      for (int i = 0; i < 8; ++i) ww[i] = tap[i][kVoxelsPerBlock];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ch[i] = static_cast<float>((cc[i] >> (8 * s)) & 255u);
-        rgba |= trunc_u8(interp_member(q, ch)) << (8 * s);
+      for (int i = 0; i < 8; ++i) ok = ok && (ww[i] > kEps);  // utils::isObservedVoxel
+      if (ok) {
+        float dd[8];
+        uint32_t cc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          dd[i] = tap[i][0];
+          cc[i] = __float_as_uint(tap[i][2 * kVoxelsPerBlock]);
+        }
+        // offset inside the cell of tap 0 (always inside base block b / voxel v)
+        const V3 no = V3{static_cast<float>(b[0]) * A.block_size,
+                         static_cast<float>(b[1]) * A.block_size,
+                         static_cast<float>(b[2]) * A.block_size};
+        const V3 vpos = no + V3{center_coord(v[0], A.voxel_size), center_coord(v[1], A.voxel_size),
+                                center_coord(v[2], A.voxel_size)};
+        const V3 o = (p - vpos) * A.voxel_size_inv;
+        const float q[8] = {1.0f, o.x, o.y, o.z, o.x * o.y, o.y * o.z, o.z * o.x, o.x * o.y * o.z};
+        out.d = interp_member(q, dd);
+        out.w = interp_member(q, ww);
+        float ch[8];
+        uint32_t rgba = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ch[i] = static_cast<float>((cc[i] >> (8 * s)) & 255u);
+          rgba |= trunc_u8(interp_member(q, ch)) << (8 * s);
+        }
+        out.c = rgba;
+        return true;
       }
-      out.c = rgba;
-      return true;
     }
   }
   // ---- nearest (R9): clamped voxel index in the block containing p
@@ -344,6 +348,323 @@ static int32_t enqueue_merge(const cg_layer* A, const float T_B_A[7], cg_layer* 
   return CG_OK;
 }
 
+// ------------------------------------------------------------------ batched projection
+// cblox getProjectedMap() merges every submap into one layer.  Doing that submap by submap leaves
+// the GPU idle (a 5 cm submap has ~100 blocks), so up to 64 submaps go through the three kernels
+// below together:
+//   k_mark_batch      transformLayer's forward pass for all source blocks of the batch; a scratch
+//                     hash map destination block -> 64-bit mask of the submaps that may reach it
+//   (scan)            candidate (block, submap) pairs numbered by a prefix sum of the mask
+//                     population counts
+//   k_resample_batch  one CTA per candidate: the resampled block (R8 / R9) goes to a temporary
+//                     planar block, with a "has data" flag
+//   k_fold_batch      one CTA per destination block: claims the block iff a candidate carries
+//                     data (bit-exact block set) and folds its candidates in ascending submap
+//                     order (R10) — the order of the reference's loop, so the result is
+//                     bit-identical to merging the submaps one after the other.
+struct BatchSubmap {
+  LayerView A;
+  Xform T_B_A, T_A_B;
+  uint32_t first_block;  // prefix sum of the source block counts
+  uint32_t num_blocks;
+};
+constexpr int kBatchMax = 64;
+
+__global__ void k_mark_batch(const BatchSubmap* __restrict__ desc, int n, uint32_t total_blocks,
+                             float block_size_out, uint64_t* map_keys, unsigned long long* map_mask,
+                             uint32_t map_cap_mask, int32_t* err) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_blocks) return;
+  int lo = 0, hi = n;  // desc[lo].first_block <= g
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (desc[mid].first_block <= g) lo = mid; else hi = mid;
+  }
+  const BatchSubmap& d = desc[lo];
+  int bx, by, bz;
+  unpack_block_key(d.A.block_keys[g - d.first_block], bx, by, bz);
+  const V3 c_in = V3{center_coord(bx, d.A.block_size), center_coord(by, d.A.block_size),
+                     center_coord(bz, d.A.block_size)};
+  const V3 c = apply(d.T_B_A, c_in);
+  const float kDiag = 1.7320508075688772f;  // kUnitCubeDiagonalLength
+  const float offset = kDiag * d.A.block_size * 0.5f;
+  const float inv_out = 1.0f / block_size_out;
+  constexpr int lim = kVoxIdxOffset / kVps;
+  for (float x = c.x - offset; x < c.x + offset; x += block_size_out)
+    for (float y = c.y - offset; y < c.y + offset; y += block_size_out)
+      for (float z = c.z - offset; z < c.z + offset; z += block_size_out) {
+        const int ix = grid_index(x, inv_out), iy = grid_index(y, inv_out),
+                  iz = grid_index(z, inv_out);
+        if (ix < -lim || ix >= lim || iy < -lim || iy >= lim || iz < -lim || iz >= lim) {
+          atomicOr(err, kErrOutOfRange);
+          continue;
+        }
+        const uint64_t key = pack_block_key(ix, iy, iz);
+        uint32_t h = hash_key(key) & map_cap_mask;
+        for (;;) {
+          const uint64_t k = map_keys[h];
+          if (k == key) break;
+          if (k == kEmptyKey) {
+            const unsigned long long old = atomicCAS(
+                reinterpret_cast<unsigned long long*>(&map_keys[h]), kEmptyKey, key);
+            if (old == kEmptyKey || old == key) break;
+          }
+          h = (h + 1) & map_cap_mask;
+        }
+        atomicOr(&map_mask[h], 1ull << lo);
+      }
+}
+
+__global__ void k_mask_counts(const unsigned long long* __restrict__ map_mask, uint32_t cap,
+                              uint32_t* __restrict__ counts) {
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < cap) counts[h] = __popcll(map_mask[h]);
+}
+
+// number of candidates = cand_base[cap]; the candidate list is implicit:
+// candidate c belongs to the map entry h with cand_base[h] <= c < cand_base[h + 1] and to the
+// (c - cand_base[h])-th set bit of its mask
+__global__ void __launch_bounds__(kMergeThreads)
+k_resample_batch(const BatchSubmap* __restrict__ desc, LayerView B,
+                 const uint64_t* __restrict__ map_keys,
+                 const unsigned long long* __restrict__ map_mask,
+                 const uint32_t* __restrict__ cand_base, uint32_t cap, float* __restrict__ temp,
+                 uint8_t* __restrict__ has_flag, uint32_t temp_cap) {
+  __shared__ SlotTable tab;
+  __shared__ uint32_t s_h;
+  __shared__ int s_sub;
+  const uint32_t num_cand = cand_base[cap];
+  if (num_cand > temp_cap) return;  // the host sees the count and retries with a smaller batch
+  for (uint32_t c = blockIdx.x; c < num_cand; c += gridDim.x) {
+    __syncthreads();  // previous iteration done with tab / s_h / s_sub
+    if (threadIdx.x == 0) {
+      uint32_t lo = 0, hi = cap;  // last h with cand_base[h] <= c
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (cand_base[mid] <= c) lo = mid; else hi = mid;
+      }
+      unsigned long long m = map_mask[lo];
+      for (uint32_t k = c - cand_base[lo]; k > 0; --k) m &= m - 1;  // drop the k lowest set bits
+      s_h = lo;
+      s_sub = __ffsll(static_cast<long long>(m)) - 1;
+    }
+    __syncthreads();
+    const BatchSubmap& d = desc[s_sub];
+    const LayerView& A = d.A;
+    int bx, by, bz;
+    unpack_block_key(map_keys[s_h], bx, by, bz);
+    const V3 org_out = V3{static_cast<float>(bx) * B.block_size, static_cast<float>(by) * B.block_size,
+                          static_cast<float>(bz) * B.block_size};
+    if (threadIdx.x == 0) {
+      const V3 ctr = V3{center_coord(bx, B.block_size), center_coord(by, B.block_size),
+                        center_coord(bz, B.block_size)};
+      const V3 pc = apply(d.T_A_B, ctr);
+      const float reach = 0.8660254f * B.block_size + A.voxel_size;
+      tab.ax = __float2int_rd((pc.x - reach) * A.block_size_inv);
+      tab.ay = __float2int_rd((pc.y - reach) * A.block_size_inv);
+      tab.az = __float2int_rd((pc.z - reach) * A.block_size_inv);
+    }
+    __syncthreads();
+    if (threadIdx.x < kTab * kTab * kTab) {
+      const int t = threadIdx.x;
+      const int dx = t % kTab, dy = (t / kTab) % kTab, dz = t / (kTab * kTab);
+      tab.slot[t] = A.find_slot(pack_block_key(tab.ax + dx, tab.ay + dy, tab.az + dz));
+    }
+    __syncthreads();
+    float* t_d = temp + static_cast<size_t>(c) * (3 * kVoxelsPerBlock);
+    float* t_w = t_d + kVoxelsPerBlock;
+    uint32_t* t_c = reinterpret_cast<uint32_t*>(t_w + kVoxelsPerBlock);
+    bool any = false;
+#pragma unroll 1
+    for (int j = 0; j < kVoxPerThread; ++j) {
+      const int lin = threadIdx.x + j * kMergeThreads;
+      const int vx = lin & 15, vy = (lin >> 4) & 15, vz = lin >> 8;
+      const V3 center_out =
+          org_out + V3{center_coord(vx, B.voxel_size), center_coord(vy, B.voxel_size),
+                       center_coord(vz, B.voxel_size)};
+      const V3 p = apply(d.T_A_B, center_out);
+      VoxelState t;
+      any |= resample_voxel(A, tab, p, t);
+      t_d[lin] = t.d;
+      t_w[lin] = t.w;
+      t_c[lin] = t.c;
+    }
+    const int has_data = __syncthreads_or(any ? 1 : 0);
+    if (threadIdx.x == 0) has_flag[c] = has_data ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(kMergeThreads)
+k_fold_batch(LayerView B, const uint64_t* __restrict__ map_keys,
+             const unsigned long long* __restrict__ map_mask,
+             const uint32_t* __restrict__ cand_base, uint32_t cap, const float* __restrict__ temp,
+             const uint8_t* __restrict__ has_flag, uint32_t temp_cap, CallCounters* counters) {
+  __shared__ int s_slot;
+  const uint32_t num_cand = cand_base[cap];
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->candidates, 1ull * num_cand);
+  if (num_cand > temp_cap) return;
+  for (uint32_t h = blockIdx.x; h < cap; h += gridDim.x) {
+    const uint32_t c0 = cand_base[h], c1 = cand_base[h + 1];
+    if (c0 == c1) continue;
+    uint32_t with_data = 0;
+    for (uint32_t c = c0; c < c1; ++c) with_data += has_flag[c];
+    if (!with_data) continue;  // every candidate was dropped from its transformed layer
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int e = B.insert_entry(map_keys[h]);
+      s_slot = B.hash_vals[e];  // written by this thread or by an earlier kernel
+      atomicAdd(&counters->blocks_out, 1ull * with_data);
+      if (s_slot >= 0) {
+        B.has_data[s_slot] = 1;
+        B.updated[s_slot] = 1;
+      }
+    }
+    __syncthreads();
+    const int slot = s_slot;
+    if (slot < 0) continue;
+    float* dp = B.dist_plane(slot);
+    float* wp = B.weight_plane(slot);
+    uint32_t* cp = B.color_plane(slot);
+    VoxelState st[kVoxPerThread];
+#pragma unroll
+    for (int j = 0; j < kVoxPerThread; ++j) {
+      const int lin = threadIdx.x + j * kMergeThreads;
+      st[j] = VoxelState{dp[lin], wp[lin], cp[lin]};
+    }
+    for (uint32_t c = c0; c < c1; ++c) {  // ascending submap order
+      if (!has_flag[c]) continue;
+      const float* t_d = temp + static_cast<size_t>(c) * (3 * kVoxelsPerBlock);
+      const float* t_w = t_d + kVoxelsPerBlock;
+      const uint32_t* t_c = reinterpret_cast<const uint32_t*>(t_w + kVoxelsPerBlock);
+#pragma unroll
+      for (int j = 0; j < kVoxPerThread; ++j) {
+        const int lin = threadIdx.x + j * kMergeThreads;
+        merge_voxel(t_d[lin], t_w[lin], t_c[lin], st[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kVoxPerThread; ++j) {
+      const int lin = threadIdx.x + j * kMergeThreads;
+      dp[lin] = st[j].d;
+      wp[lin] = st[j].w;
+      cp[lin] = st[j].c;
+    }
+  }
+}
+
+__global__ void k_copy_desc(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+static Xform inverse_host(const Xform& T) {
+  // rotate(w, conj(v), t) spelled out (host code: no FMA contraction, see Makefile flags), the
+  // same operation order as the device / reference
+  const float w = T.w;
+  const V3 cv = V3{-T.v.x, -T.v.y, -T.v.z};
+  const V3 t = T.t;
+  V3 uv = V3{cv.y * t.z - cv.z * t.y, cv.z * t.x - cv.x * t.z, cv.x * t.y - cv.y * t.x};
+  uv = V3{uv.x + uv.x, uv.y + uv.y, uv.z + uv.z};
+  const V3 cr = V3{cv.y * uv.z - cv.z * uv.y, cv.z * uv.x - cv.x * uv.z, cv.x * uv.y - cv.y * uv.x};
+  const V3 r = V3{(t.x + w * uv.x) + cr.x, (t.y + w * uv.y) + cr.y, (t.z + w * uv.z) + cr.z};
+  Xform Ti;
+  Ti.w = w;
+  Ti.v = cv;
+  Ti.t = V3{-r.x, -r.y, -r.z};
+  return Ti;
+}
+
+// submaps [i0, i1) as one batch; returns CG_OK with *overflow = true when the batch has more
+// candidates than temp_cap (nothing was merged then)
+static int32_t project_batch(const cg_layer* const* submaps, const float* poses, size_t i0, size_t i1,
+                             cg_layer* G, size_t temp_cap, bool* overflow, cg_merge_stats* stats) {
+  cg_context* ctx = G->ctx;
+  cudaStream_t s = ctx->stream;
+  const int n = static_cast<int>(i1 - i0);
+  std::vector<BatchSubmap> h(n);
+  uint32_t total = 0;
+  for (int k = 0; k < n; ++k) {
+    const cg_layer* A = submaps[i0 + k];
+    h[k].A = A->v;
+    h[k].T_B_A = make_xform(poses + 7 * (i0 + k));
+    h[k].T_A_B = inverse_host(h[k].T_B_A);
+    h[k].first_block = total;
+    h[k].num_blocks = static_cast<uint32_t>(A->num_blocks);
+    total += h[k].num_blocks;
+  }
+  *overflow = false;
+  if (total == 0) return CG_OK;
+  size_t cap = 4096;
+  while (cap < 32 * static_cast<size_t>(total)) cap <<= 1;
+  const size_t desc_bytes = n * sizeof(BatchSubmap);
+  if (desc_bytes > ctx->h_tables_cap) {
+    if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
+    ctx->h_tables = nullptr;
+    ctx->h_tables_cap = 0;
+    CG_CUDA(cudaHostAlloc(&ctx->h_tables, desc_bytes * 2, cudaHostAllocMapped));
+    ctx->h_tables_cap = desc_bytes * 2;
+  }
+  memcpy(ctx->h_tables, h.data(), desc_bytes);
+  void* d_alias = nullptr;
+  CG_CUDA(cudaHostGetDevicePointer(&d_alias, ctx->h_tables, 0));
+  CG_CUDA(ctx->batch_desc.reserve(desc_bytes));
+  CG_CUDA(ctx->cand_keys.reserve(cap * sizeof(uint64_t)));
+  CG_CUDA(ctx->cand_list.reserve(cap * sizeof(unsigned long long)));      // masks
+  CG_CUDA(ctx->stage_b.reserve((cap + 1) * sizeof(uint32_t)));            // counts
+  CG_CUDA(ctx->stage_c.reserve((cap + 1) * sizeof(uint32_t)));            // cand_base
+  CG_CUDA(ctx->merge_temp.reserve(temp_cap * static_cast<size_t>(CG_BLOCK_BYTES)));
+  CG_CUDA(ctx->merge_flags.reserve(temp_cap));
+  size_t tmp_scan = 0;
+  CG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, ctx->stage_b.as<uint32_t>(),
+                                        ctx->stage_c.as<uint32_t>(), static_cast<int>(cap + 1), s));
+  CG_CUDA(ctx->cub_tmp.reserve(tmp_scan));
+  const BatchSubmap* desc = ctx->batch_desc.as<BatchSubmap>();
+  {
+    StageScope sc(ctx, kStageMergeMark, 4);
+    k_copy_desc<<<grid_for(desc_bytes / 4, 256), 256, 0, s>>>(
+        ctx->batch_desc.as<uint32_t>(), static_cast<const uint32_t*>(d_alias), desc_bytes / 4);
+    CG_CUDA(cudaMemsetAsync(ctx->cand_keys.p, 0xFF, cap * sizeof(uint64_t), s));
+    CG_CUDA(cudaMemsetAsync(ctx->cand_list.p, 0, cap * sizeof(unsigned long long), s));
+    CG_CUDA(cudaMemsetAsync(ctx->stage_b.p, 0, (cap + 1) * sizeof(uint32_t), s));
+    k_reset_merge_counters<<<1, 1, 0, s>>>(ctx->d_counters);
+    k_mark_batch<<<grid_for(total, 128), 128, 0, s>>>(
+        desc, n, total, G->v.block_size, ctx->cand_keys.as<uint64_t>(),
+        ctx->cand_list.as<unsigned long long>(), static_cast<uint32_t>(cap - 1), G->v.err);
+    k_mask_counts<<<grid_for(cap, 256), 256, 0, s>>>(ctx->cand_list.as<unsigned long long>(),
+                                                     static_cast<uint32_t>(cap),
+                                                     ctx->stage_b.as<uint32_t>());
+    CG_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_scan, ctx->stage_b.as<uint32_t>(),
+                                          ctx->stage_c.as<uint32_t>(), static_cast<int>(cap + 1),
+                                          s));
+  }
+  {
+    StageScope sc(ctx, kStageMergeResample, 2);
+    k_resample_batch<<<ctx->num_sms * 6, kMergeThreads, 0, s>>>(
+        desc, G->v, ctx->cand_keys.as<uint64_t>(), ctx->cand_list.as<unsigned long long>(),
+        ctx->stage_c.as<uint32_t>(), static_cast<uint32_t>(cap), ctx->merge_temp.as<float>(),
+        ctx->merge_flags.as<uint8_t>(), static_cast<uint32_t>(temp_cap));
+    k_fold_batch<<<ctx->num_sms * 6, kMergeThreads, 0, s>>>(
+        G->v, ctx->cand_keys.as<uint64_t>(), ctx->cand_list.as<unsigned long long>(),
+        ctx->stage_c.as<uint32_t>(), static_cast<uint32_t>(cap), ctx->merge_temp.as<float>(),
+        ctx->merge_flags.as<uint8_t>(), static_cast<uint32_t>(temp_cap), ctx->d_counters);
+  }
+  CG_CUDA(cudaGetLastError());
+  // the descriptor staging buffer is reused by the next batch: wait for this one
+  CG_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(CallCounters),
+                          cudaMemcpyDeviceToHost, s));
+  CG_CUDA(cudaStreamSynchronize(s));
+  if (ctx->h_counters->candidates > temp_cap) {
+    *overflow = true;
+    return CG_OK;
+  }
+  if (stats) {
+    stats->blocks_in += total;
+    stats->blocks_candidate += ctx->h_counters->candidates;
+    stats->blocks_out += ctx->h_counters->blocks_out;
+  }
+  return CG_OK;
+}
+
 }  // namespace cg
 
 using namespace cg;
@@ -381,19 +702,37 @@ int32_t cg_project_submaps(const cg_layer* const* submaps, const float* poses, s
       set_error("cg_project_submaps: submap %zu invalid", i);
       return CG_ERR_INVALID_ARG;
     }
-    int32_t rc = enqueue_merge(A, poses + 7 * i, G);
-    if (rc) return rc;
-    if (stats) {
-      // per-submap counters are reset by the next merge: read them back (stats path only)
-      CG_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(CallCounters),
-                              cudaMemcpyDeviceToHost, ctx->stream));
-      CG_CUDA(cudaStreamSynchronize(ctx->stream));
-      stats->blocks_in += static_cast<uint64_t>(A->num_blocks);
-      if (A->num_blocks) {
-        stats->blocks_candidate += ctx->h_counters->candidates;
-        stats->blocks_out += ctx->h_counters->blocks_out;
-      }
+  }
+  // temporary resampled blocks per batch (48 KB each)
+  size_t temp_cap = env_size_merge("CG_MERGE_TEMP_BLOCKS", 8192);
+  size_t i0 = 0;
+  size_t want = kBatchMax;
+  while (i0 < n) {
+    // a batch: up to 64 submaps whose candidate count is expected to fit (about 2 destination
+    // blocks per source block under rotation; the exact count comes back from the device)
+    size_t i1 = i0, blocks = 0;
+    while (i1 < n && i1 - i0 < want &&
+           (i1 == i0 || 2 * (blocks + submaps[i1]->num_blocks) <= temp_cap)) {
+      blocks += static_cast<size_t>(submaps[i1]->num_blocks);
+      ++i1;
     }
+    bool overflow = false;
+    int32_t rc = project_batch(submaps, poses, i0, i1, G, temp_cap, &overflow, stats);
+    if (rc) return rc;
+    if (overflow) {
+      if (i1 - i0 > 1) {
+        want = (i1 - i0) / 2;  // retry with half the submaps
+      } else {
+        temp_cap *= 2;         // a single submap with many candidates: more temporary blocks
+        if (temp_cap > (size_t(1) << 21)) {
+          set_error("cg_project_submaps: submap %zu needs more than 2^21 temporary blocks", i0);
+          return CG_ERR_INVALID_ARG;
+        }
+      }
+      continue;
+    }
+    want = kBatchMax;
+    i0 = i1;
   }
   return finish_call(G, nullptr);
 }
