@@ -173,6 +173,12 @@ def run_ours(args, rank, world, local_rank):
     from coxgraph_b200 import (Context, Layer, TsdfIntegrator, TsdfIntegratorConfig,
                                mergeLayerAintoLayerB, synth)
 
+    try:  # run (and first-touch the pinned buffers) on the CPUs next to this rank's GPU
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:  # noqa: BLE001 - affinity is an optimisation only
+        pass
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
