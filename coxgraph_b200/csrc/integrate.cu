@@ -735,8 +735,11 @@ k_walk_segments(IntegratorParams P, const float* __restrict__ poses, const Ray* 
       }
       ++seg_pos;
     };
-    while (__any_sync(full, w.remaining > 0)) {
-      if (w.remaining > 0) {
+    // The lanes are aligned at the END of their rays: a lane joins when the countdown reaches
+    // its own length, so all rays of the warp finish together and the costly tail (sdf of the
+    // last visits, closing the last segment) runs converged instead of a few lanes at a time.
+    for (uint32_t left = __reduce_max_sync(full, w.remaining); left > 0; --left) {
+      if (w.remaining >= left) {
         const int bx = rc.cx >> 4, by = rc.cy >> 4, bz = rc.cz >> 4;
         if (bx != lbx || by != lby || bz != lbz) {
           if (s_visits) emit();
@@ -822,9 +825,11 @@ k_block_accumulate(IntegratorParams P, const Ray* __restrict__ rays,
                    TouchView Tv, float acc_scale, uint32_t ray_bits,
                    unsigned long long* __restrict__ out, uint32_t* out_count, uint32_t out_cap,
                    uint32_t* work_counter) {
-  // 64-bit accumulators as (lo, hi) words: shared memory has native 32-bit atomic adds only (a
-  // 64-bit add is a compare-and-swap loop); the carry out of lo is recovered from the returned
-  // old value, so the sum is exact whatever the order of the adds
+  // Accumulators as two 20-bit limbs in 32-bit words: shared memory has native 32-bit atomic adds
+  // only (a 64-bit add is a compare-and-swap loop).  A segment visits a voxel at most once (the
+  // walk is monotone), so a tile sees at most kSegChunk = 2^11 adds per voxel before it is
+  // flushed and neither limb sum can overflow; the fixed-point weights are below 2^40 (host).
+  // No carry, no returned value to wait for, and the result is exact whatever the order.
   __shared__ uint32_t tile_lo[kVoxelsPerBlock], tile_hi[kVoxelsPerBlock];
   __shared__ uint32_t bits[kVoxelsPerBlock / 32];
   __shared__ unsigned long long buf[kAccThreads / 32][kEmitBuf];
@@ -898,10 +903,8 @@ k_block_accumulate(IntegratorParams P, const Ray* __restrict__ rays,
           if (v < visits) {
             lin = static_cast<uint32_t>(lx + 16 * (ly + 16 * lz));
             if (use_tile) {
-              const uint32_t wlo = static_cast<uint32_t>(wq), whi = static_cast<uint32_t>(wq >> 32);
-              const uint32_t old = atomicAdd(&tile_lo[lin], wlo);
-              const uint32_t up = whi + ((old + wlo < old) ? 1u : 0u);
-              if (up) atomicAdd(&tile_hi[lin], up);
+              atomicAdd(&tile_lo[lin], static_cast<uint32_t>(wq) & 0xFFFFFu);
+              atomicAdd(&tile_hi[lin], static_cast<uint32_t>(wq >> 20));
             } else {
               atomicAdd(acc + lin, wq);
             }
@@ -938,7 +941,7 @@ k_block_accumulate(IntegratorParams P, const Ray* __restrict__ rays,
       if (use_tile)
         for (int i = threadIdx.x; i < kVoxelsPerBlock; i += kAccThreads) {
           const unsigned long long a =
-              (static_cast<unsigned long long>(tile_hi[i]) << 32) | tile_lo[i];
+              (static_cast<unsigned long long>(tile_hi[i]) << 20) + tile_lo[i];
           if (a) atomicAdd(acc + i, a);
         }
       __syncthreads();
@@ -1405,7 +1408,7 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
   CG_CUDA(ctx->pkey_b.reserve(num_pairs * sizeof(unsigned long long)));
   const uint32_t ray_bits = static_cast<uint32_t>(std::max(1, ceil_log2(num_rays)));
   const int weight_bits = ceil_log2(static_cast<uint64_t>(std::min(std::max(P.max_weight, 1.0f), 1.0e9f)) + 1);
-  const int shift = std::max(0, std::min(std::min(40, 48 - weight_bits), 62 - weight_bits - ceil_log2(uint64_t(num_rays) + 1)));
+  const int shift = std::max(0, std::min(40 - weight_bits, 62 - weight_bits - ceil_log2(uint64_t(num_rays) + 1)));
   const float acc_scale = ldexpf(1.0f, shift), acc_inv_scale = ldexpf(1.0f, -shift);
   const uint32_t tail_visits = walk_tail_visits(P);
   const unsigned walk_grid = std::min<unsigned>(grid_for(num_rays, kWalkThreads),
