@@ -212,6 +212,7 @@ struct cg_context {
   cudaEvent_t stage_ready[2] = {nullptr, nullptr};
   size_t stage_points[2] = {0, 0};
   const float* group_poses = nullptr;       // device poses of the group being fused
+  int group_frames = 0;
   int num_sms = 148;
   cg::CallCounters* h_counters = nullptr;  // pinned
   cg::CallCounters* d_counters = nullptr;
@@ -221,6 +222,7 @@ struct cg_context {
   cg::DevBuf rays, ray_count, ray_offset, sorted_pts;
   cg::DevBuf pkey_a, pkey_b, seg_start, long_list, long_partials;
   cg::DevBuf seg_keys_a, seg_keys_b, seg_idx_a, seg_idx_b, seg_recs;  // (ray, block) segments
+  cg::DevBuf seg_order;  // update lists in size-class order
   // per-call touch set (integrate.cu "back half"): kept all-clear between calls
   cg::DevBuf touch_ord, touch_entry, touch_acc, touch_bits;
   uint32_t* d_touch_count = nullptr;  // [0] blocks touched, [1] general (voxel, ray) keys emitted

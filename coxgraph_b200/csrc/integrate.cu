@@ -1102,6 +1102,59 @@ struct LongPartial {
   uint32_t not_free;      // any update with sdf < trunc (not a pure free-space observation)
 };
 
+// Update lists ordered by size class (largest first), as the bundles are: the lanes of a warp
+// then hold lists of nearly the same length, so they finish — and fetch their next list, a chain
+// of dependent global loads — together instead of stalling one another every few updates.
+__device__ __forceinline__ uint32_t segment_length(const uint32_t* __restrict__ seg_start, uint32_t ns,
+                                                   uint32_t num_pairs, uint32_t sidx) {
+  return ((sidx + 1 < ns) ? seg_start[sidx + 1] : num_pairs) - seg_start[sidx];
+}
+__global__ void k_segment_histogram(const uint32_t* __restrict__ seg_start,
+                                    const uint32_t* __restrict__ num_segs, uint32_t num_pairs,
+                                    uint32_t* class_count) {
+  __shared__ uint32_t hist[kSizeClasses];
+  if (threadIdx.x < kSizeClasses) hist[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t ns = *num_segs;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x)
+    atomicAdd(&hist[size_class(segment_length(seg_start, ns, num_pairs, i))], 1u);
+  __syncthreads();
+  if (threadIdx.x < kSizeClasses && hist[threadIdx.x])
+    atomicAdd(&class_count[threadIdx.x], hist[threadIdx.x]);
+}
+__global__ void k_segment_order(const uint32_t* __restrict__ seg_start,
+                                const uint32_t* __restrict__ num_segs, uint32_t num_pairs,
+                                uint32_t* class_count, uint32_t* __restrict__ order) {
+  __shared__ uint32_t base[kSizeClasses];
+  __shared__ uint32_t hist[kSizeClasses];
+  __shared__ uint32_t offs[kSizeClasses];
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int c = 0; c < kSizeClasses; ++c) {
+      base[c] = acc;
+      acc += class_count[c];
+    }
+  }
+  const uint32_t ns = *num_segs;
+  for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < ns; i0 += gridDim.x * blockDim.x) {
+    __syncthreads();
+    if (threadIdx.x < kSizeClasses) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i = i0 + threadIdx.x;
+    int c = -1;
+    uint32_t rank = 0;
+    if (i < ns) {
+      c = size_class(segment_length(seg_start, ns, num_pairs, i));
+      rank = atomicAdd(&hist[c], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < kSizeClasses && hist[threadIdx.x])
+      offs[threadIdx.x] = atomicAdd(&class_count[kSizeClasses + threadIdx.x], hist[threadIdx.x]);
+    __syncthreads();
+    if (c >= 0) order[base[c] + offs[c] + rank] = i;
+  }
+}
+
 // General voxels, short update lists: persistent lanes, one voxel per lane at a time, the
 // reference's updateTsdfVoxel applied update by update (R5, in the reference's own operation
 // order).  Lists of kWideSegment updates or more go to a list for the warp-cooperative kernels
@@ -1112,8 +1165,18 @@ __global__ void __launch_bounds__(128)
 k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
                const unsigned long long* __restrict__ keys, uint32_t ray_bits, uint32_t num_pairs,
                const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ num_segs,
-               uint32_t* work_counter, unsigned long long* long_counter, LongSeg* long_list,
-               uint32_t long_cap, LayerView L, TouchView Tv) {
+               const uint32_t* __restrict__ order, uint32_t* work_counter,
+               unsigned long long* long_counter, LongSeg* long_list, uint32_t long_cap, LayerView L,
+               TouchView Tv, int num_frames) {
+  // sensor origins of the group's frames in shared memory: the per-update chain key -> ray ->
+  // pose would otherwise end in a global load that nothing hides (few lists, few warps)
+  constexpr int kOriginFrames = 256;
+  __shared__ float s_origin[3 * kOriginFrames];
+  const bool origins_staged = num_frames <= kOriginFrames;
+  if (origins_staged)
+    for (int i = threadIdx.x; i < 3 * num_frames; i += blockDim.x)
+      s_origin[i] = poses[7 * (i / 3) + 4 + (i % 3)];
+  __syncthreads();
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -1126,7 +1189,7 @@ k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* _
   vr.cp = nullptr;
   vr.center = V3{0.0f, 0.0f, 0.0f};
   VoxelState st{0.0f, 0.0f, 0u};
-  Ray ray_next = rays[0];
+  Ray ray_next = rays[0], ray_next2 = ray_next;
   uint32_t id_next = 0;
   for (;;) {
     const bool need = !finished && cur >= end;
@@ -1137,8 +1200,9 @@ k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* _
       if (lane == leader) base = atomicAdd(work_counter, static_cast<uint32_t>(__popc(m)));
       base = __shfl_sync(full, base, leader);
       if (need) {
-        const uint32_t sidx = base + __popc(m & lt);
-        if (sidx < ns) {
+        const uint32_t oidx = base + __popc(m & lt);
+        if (oidx < ns) {
+          const uint32_t sidx = order[oidx];  // lists in size-class order
           const uint32_t start = seg_start[sidx];
           const uint32_t stop = (sidx + 1 < ns) ? seg_start[sidx + 1] : num_pairs;
           vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[start] >> ray_bits));
@@ -1160,7 +1224,8 @@ k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* _
               st.w = *vr.wp;
               st.c = *vr.cp;
               ray_next = rays[static_cast<uint32_t>(keys[start]) & ray_mask];
-              id_next = (start + 1 < stop) ? static_cast<uint32_t>(keys[start + 1]) & ray_mask : 0u;
+              ray_next2 = rays[(start + 1 < stop) ? static_cast<uint32_t>(keys[start + 1]) & ray_mask : 0u];
+              id_next = (start + 2 < stop) ? static_cast<uint32_t>(keys[start + 2]) & ray_mask : 0u;
             }
           }
         } else {
@@ -1172,13 +1237,16 @@ k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* _
 #pragma unroll 1
     for (int t = 0; t < kUpdateInner; ++t) {
       if (cur < end) {
-        // two-stage software pipeline: key of update cur+2 and ray record of update cur+1 are in
-        // flight while update cur is applied
+        // software pipeline: the key of update cur+3 and the ray records of updates cur+1 and
+        // cur+2 are in flight while update cur is applied (a ray record is a dependent, random
+        // load: one update of head start does not cover its latency)
         const Ray ray = ray_next;
-        ray_next = rays[id_next];
-        id_next = (cur + 2 < end) ? static_cast<uint32_t>(keys[cur + 2]) & ray_mask : 0u;
-        const float* T = poses + 7 * (ray.frame_clr & 0x7FFFFFFFu);
-        update_tsdf_voxel(P, V3{T[4], T[5], T[6]}, V3{ray.px, ray.py, ray.pz}, vr.center, ray.color,
+        ray_next = ray_next2;
+        ray_next2 = rays[id_next];
+        id_next = (cur + 3 < end) ? static_cast<uint32_t>(keys[cur + 3]) & ray_mask : 0u;
+        const uint32_t fr = ray.frame_clr & 0x7FFFFFFFu;
+        const float* T = origins_staged ? s_origin + 3 * fr : poses + 7 * fr + 4;
+        update_tsdf_voxel(P, V3{T[0], T[1], T[2]}, V3{ray.px, ray.py, ray.pz}, vr.center, ray.color,
                           ray.weight, st);
         if (++cur >= end) {
           *vr.dp = st.d;
@@ -1528,14 +1596,21 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
     const size_t max_items = n_general / kLongSub + long_cap + 1;
     CG_CUDA(ctx->long_list.reserve(long_cap * sizeof(LongSeg)));
     CG_CUDA(ctx->long_partials.reserve(max_items * sizeof(LongPartial)));
+    CG_CUDA(ctx->seg_order.reserve(size_t(n_general) * sizeof(uint32_t)));
     {
-      StageScope sc(ctx, kStageVoxelUpdate, 1);
+      StageScope sc(ctx, kStageVoxelUpdate, 3);
       CG_CUDA(fill_bytes(ctx->d_work_counter, 0, sizeof(uint32_t), s));
       CG_CUDA(fill_bytes(ctx->d_long_counter, 0, sizeof(unsigned long long), s));
+      CG_CUDA(fill_bytes(ctx->d_class_count, 0, 2 * kSizeClasses * sizeof(uint32_t), s));
+      const unsigned ogrid = std::min<unsigned>(grid_for(n_general, 256), ctx->num_sms * 4u);
+      k_segment_histogram<<<ogrid, 256, 0, s>>>(ctx->seg_start.as<uint32_t>(), d_num, n_general,
+                                                ctx->d_class_count);
+      k_segment_order<<<ogrid, 256, 0, s>>>(ctx->seg_start.as<uint32_t>(), d_num, n_general,
+                                            ctx->d_class_count, ctx->seg_order.as<uint32_t>());
       k_voxel_update<<<ctx->num_sms * 8, 128, 0, s>>>(
           P, ctx->group_poses, ctx->rays.as<Ray>(), dk.Current(), ray_bits, n_general,
-          ctx->seg_start.as<uint32_t>(), d_num, ctx->d_work_counter, ctx->d_long_counter,
-          ctx->long_list.as<LongSeg>(), long_cap, L->v, tv);
+          ctx->seg_start.as<uint32_t>(), d_num, ctx->seg_order.as<uint32_t>(), ctx->d_work_counter,
+          ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv, ctx->group_frames);
     }
     {
       StageScope sc(ctx, kStageReplayWide, 2);
@@ -1624,6 +1699,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   const uint32_t* cols = reinterpret_cast<const uint32_t*>(d_colors) + offs[f0];
   const FrameTable ft{ctx->frame_base.as<uint64_t>() + f0, offs[f0] - offs[0], static_cast<int>(F)};
   ctx->group_poses = ctx->poses.as<float>() + 7 * f0;
+  ctx->group_frames = static_cast<int>(F);
   ValidSlot valid{P, ft, pts};
   size_t tmp_sort = 0, tmp_sel = 0, tmp_scan = 0;
   if (merged) {
