@@ -815,7 +815,7 @@ k_mark_existing(IntegratorParams P, LayerView L, TouchView Tv, int32_t blocks_be
 // per-job accumulators in global memory — one add per touched voxel and chunk instead of one
 // per visit (measured: per-visit global atomics cost 0.4 ms of a 0.6 ms walk on the C2 step).
 constexpr int kAccThreads = 256;
-constexpr uint32_t kSegChunk = 2048;   // segments per work item
+constexpr uint32_t kSegChunk = 1024;  // segments per work item
 constexpr uint32_t kTileMinRun = 64;   // shorter block runs add straight to global memory
 constexpr int kEmitBuf = 128;
 __global__ void __launch_bounds__(kAccThreads)
@@ -827,7 +827,7 @@ k_block_accumulate(IntegratorParams P, const Ray* __restrict__ rays,
                    uint32_t* work_counter) {
   // Accumulators as two 20-bit limbs in 32-bit words: shared memory has native 32-bit atomic adds
   // only (a 64-bit add is a compare-and-swap loop).  A segment visits a voxel at most once (the
-  // walk is monotone), so a tile sees at most kSegChunk = 2^11 adds per voxel before it is
+  // walk is monotone), so a tile sees at most kSegChunk <= 2^11 adds per voxel before it is
   // flushed and neither limb sum can overflow; the fixed-point weights are below 2^40 (host).
   // No carry, no returned value to wait for, and the result is exact whatever the order.
   __shared__ uint32_t tile_lo[kVoxelsPerBlock], tile_hi[kVoxelsPerBlock];
