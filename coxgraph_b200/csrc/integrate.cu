@@ -95,6 +95,14 @@ __device__ __forceinline__ int order_index(int k, int n, int mode) {
   return (k % groups) * 1024 + (k / groups);
 }
 
+// inverse of order_index: the visiting rank of point i
+__device__ __forceinline__ int visit_rank(int i, int n, int mode) {
+  if (mode != 0) return i;
+  const int groups = n / 1024;
+  if (groups * 1024 <= i) return i;
+  return (i % 1024) * groups + (i / 1024);
+}
+
 __device__ __forceinline__ V3 load_point(const float* pts, size_t i) {
   return V3{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
 }
@@ -117,7 +125,8 @@ struct FrameTable {
 };
 
 // ------------------------------------------------------------------ front half
-// slot g enumerates (frame, visit rank k)
+// One thread per point in input order (coalesced reads); its key goes to the slot of its visiting
+// rank k (the scattered 8-byte writes of a wave merge in L2).
 __global__ void k_point_keys(IntegratorParams P, KeyLayout kl, const float* __restrict__ poses,
                              FrameTable ft, const float* __restrict__ pts, uint64_t total,
                              uint64_t* __restrict__ keys, int32_t* err, uint32_t* key_reach) {
@@ -126,9 +135,9 @@ __global__ void k_point_keys(IntegratorParams P, KeyLayout kl, const float* __re
   const int f = ft.frame_of(g);
   const uint64_t base = ft.start(f);
   const int n = static_cast<int>(ft.start(f + 1) - base);
-  const uint32_t k = static_cast<uint32_t>(g - base);
-  const int i = order_index(static_cast<int>(k), n, P.order_mode);
-  const V3 pc = load_point(pts, base + i);
+  const int i = static_cast<int>(g - base);
+  const uint32_t k = static_cast<uint32_t>(visit_rank(i, n, P.order_mode));
+  const V3 pc = load_point(pts, g);
   bool clearing = false;
   uint64_t key = kInvalidPointKey;
   if (point_valid(P, pc, &clearing)) {
@@ -157,7 +166,7 @@ __global__ void k_point_keys(IntegratorParams P, KeyLayout kl, const float* __re
       atomicOr(err, kErrOutOfRange);
     }
   }
-  keys[g] = key;
+  keys[base + k] = key;
 }
 
 struct BundleHead {
