@@ -542,19 +542,66 @@ __global__ void k_simple_rays(IntegratorParams P, const float* __restrict__ pose
   ray_count[r] = rc.valid ? rc.packed_counts() : 0ull;
 }
 
-__global__ void k_totals(const uint32_t* num_rays, const unsigned long long* ray_count,
-                         const unsigned long long* ray_offset, size_t upper, CallCounters* c,
-                         int32_t* err, uint32_t* key_reach) {
-  const int e = *err;  // a point outside the group's key layout: the host widens it / regroups
-  c->err = e & kErrKeyRange;
-  if (e & kErrKeyRange) *err = e & ~kErrKeyRange;
-  c->key_reach = *key_reach;
-  *key_reach = 0;
-  c->rays = *num_rays;
-  const unsigned long long tot = upper ? ray_offset[upper - 1] + ray_count[upper - 1] : 0ull;
-  c->pairs = tot & 0xFFFFFFFFull;   // voxel visits (the host splits jobs that reach 2^32)
-  c->segments = tot >> 32;          // (ray, block) segments
-  c->touched = 0;
+// Exclusive scan of the packed per-ray counts over the first *num_rays entries only (the host
+// knows just the upper bound "one ray per point", 25x larger at the C2 shape): per-CTA partial
+// sums over contiguous ranges, a one-CTA scan of the partials, then a block scan per range.
+constexpr int kScanThreads = 256;
+__device__ __forceinline__ void scan_range(uint32_t n, uint32_t& lo, uint32_t& hi) {
+  const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+  lo = min(n, blockIdx.x * per);
+  hi = min(n, lo + per);
+}
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_partials(const uint32_t* __restrict__ num_rays, const unsigned long long* __restrict__ in,
+                unsigned long long* __restrict__ partials) {
+  typedef cub::BlockReduce<unsigned long long, kScanThreads> Reduce;
+  __shared__ typename Reduce::TempStorage tmp;
+  uint32_t lo, hi;
+  scan_range(*num_rays, lo, hi);
+  unsigned long long sum = 0;
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += kScanThreads) sum += in[i];
+  sum = Reduce(tmp).Sum(sum);
+  if (threadIdx.x == 0) partials[blockIdx.x] = sum;
+}
+// one CTA: exclusive scan of the partials in place; totals -> counters
+__global__ void __launch_bounds__(1024)
+k_scan_totals(const uint32_t* __restrict__ num_rays, unsigned long long* __restrict__ partials,
+              int num_partials, CallCounters* c, int32_t* err, uint32_t* key_reach) {
+  typedef cub::BlockScan<unsigned long long, 1024> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  unsigned long long v = static_cast<int>(threadIdx.x) < num_partials ? partials[threadIdx.x] : 0ull;
+  unsigned long long total = 0;
+  Scan(tmp).ExclusiveSum(v, v, total);
+  if (static_cast<int>(threadIdx.x) < num_partials) partials[threadIdx.x] = v;
+  if (threadIdx.x == 0) {
+    const int e = *err;  // a point outside the group's key layout: the host widens it / regroups
+    c->err = e & kErrKeyRange;
+    if (e & kErrKeyRange) *err = e & ~kErrKeyRange;
+    c->key_reach = *key_reach;
+    *key_reach = 0;
+    c->rays = *num_rays;
+    c->pairs = total & 0xFFFFFFFFull;  // voxel visits (the host splits jobs that reach 2^32)
+    c->segments = total >> 32;         // (ray, block) segments
+    c->touched = 0;
+  }
+}
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_apply(const uint32_t* __restrict__ num_rays, const unsigned long long* __restrict__ in,
+             const unsigned long long* __restrict__ partials, unsigned long long* __restrict__ out) {
+  typedef cub::BlockScan<unsigned long long, kScanThreads> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  uint32_t lo, hi;
+  scan_range(*num_rays, lo, hi);
+  unsigned long long running = partials[blockIdx.x];
+  for (uint32_t i0 = lo; i0 < hi; i0 += kScanThreads) {
+    const uint32_t i = i0 + threadIdx.x;
+    const unsigned long long v = i < hi ? in[i] : 0ull;
+    unsigned long long ex, agg;
+    Scan(tmp).ExclusiveSum(v, ex, agg);
+    if (i < hi) out[i] = running + ex;
+    running += agg;
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------ back half
@@ -1710,7 +1757,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   ctx->group_poses = ctx->poses.as<float>() + 7 * f0;
   ctx->group_frames = static_cast<int>(F);
   ValidSlot valid{P, ft, pts};
-  size_t tmp_sort = 0, tmp_sel = 0, tmp_scan = 0;
+  size_t tmp_sort = 0, tmp_sel = 0;
   if (merged) {
     cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, dk, static_cast<int>(total), kl.rank_bits,
                                    bundle_end_bit, s);
@@ -1720,13 +1767,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
     cub::DeviceSelect::If(nullptr, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
                           static_cast<int>(total), valid, s);
   }
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, ctx->ray_count.as<unsigned long long>(),
-                                ctx->ray_offset.as<unsigned long long>(), static_cast<int>(upper), s);
-  CG_CUDA(ctx->cub_tmp.reserve(std::max(tmp_sort, std::max(tmp_sel, tmp_scan))));
-  {
-    StageScope sc(ctx, kStageTransfer, 0);
-    CG_CUDA(fill_bytes(ctx->ray_count.p, 0, upper * sizeof(unsigned long long), s));
-  }
+  CG_CUDA(ctx->cub_tmp.reserve(std::max(tmp_sort, tmp_sel)));
   if (merged) {
     {
       StageScope sc(ctx, kStagePointKeys, 1);
@@ -1793,14 +1834,16 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
         cols, ctx->rays.as<Ray>(), ctx->ray_count.as<unsigned long long>());
   }
   {
-    StageScope sc(ctx, kStageRayScan, 1);
-    CG_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_scan,
-                                          ctx->ray_count.as<unsigned long long>(),
-                                          ctx->ray_offset.as<unsigned long long>(),
-                                          static_cast<int>(upper), s));
-    k_totals<<<1, 1, 0, s>>>(d_num, ctx->ray_count.as<unsigned long long>(),
-                             ctx->ray_offset.as<unsigned long long>(), upper, ctx->d_counters,
-                             L->v.err, ctx->d_walk_counters + 2);
+    StageScope sc(ctx, kStageRayScan, 3);
+    const int sgrid = std::min(1024, ctx->num_sms * 4);
+    CG_CUDA(ctx->scan_partials.reserve(1024 * sizeof(unsigned long long)));
+    k_scan_partials<<<sgrid, kScanThreads, 0, s>>>(d_num, ctx->ray_count.as<unsigned long long>(),
+                                                   ctx->scan_partials.as<unsigned long long>());
+    k_scan_totals<<<1, 1024, 0, s>>>(d_num, ctx->scan_partials.as<unsigned long long>(), sgrid,
+                                     ctx->d_counters, L->v.err, ctx->d_walk_counters + 2);
+    k_scan_apply<<<sgrid, kScanThreads, 0, s>>>(d_num, ctx->ray_count.as<unsigned long long>(),
+                                                ctx->scan_partials.as<unsigned long long>(),
+                                                ctx->ray_offset.as<unsigned long long>());
   }
   CG_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(CallCounters),
                           cudaMemcpyDeviceToHost, s));
