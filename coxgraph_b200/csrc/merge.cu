@@ -212,7 +212,7 @@ __device__ __forceinline__ bool resample_voxel(const LayerView& A, const SlotTab
   return out.w > kEps;
 }
 
-constexpr int kMergeThreads = 256;
+constexpr int kMergeThreads = 512;
 constexpr int kVoxPerThread = kVoxelsPerBlock / kMergeThreads;
 
 __global__ void __launch_bounds__(kMergeThreads)
