@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Turn the artefacts of scripts/profile_round.sh (gpurun_out/) into the committed summaries under
+profiles/: the launch list, the ncu --set full summary of the top kernels, and traffic.json (DRAM
+bytes per launch per pipeline stage, read by bench.py for roofline.traffic).
+Usage: make_profiles.py <tag> [<round-label>]"""
+import csv
+import io
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+label = sys.argv[2] if len(sys.argv) > 2 else tag
+out_dir = os.path.join(ROOT, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+go = os.path.join(ROOT, "gpurun_out")
+
+# kernel -> bench.py stage name
+STAGE = {"k_point_keys": "point_keys", "k_gather_sorted": "gather_sorted", "k_fold_wide": "fold_wide",
+         "k_fold_bundles": "fold_bundles", "k_walk_segments": "walk_segments",
+         "k_block_accumulate": "block_accumulate", "k_voxel_update": "voxel_update",
+         "k_long_finish": "replay_wide", "k_finalize_blocks": "finalize",
+         "k_resample_merge": "merge_resample"}
+
+head = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True,
+                      text=True).stdout.strip()
+ls = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "launch_summary.py"),
+                     os.path.join(go, f"launches_{tag}.csv")], capture_output=True, text=True).stdout
+with open(os.path.join(out_dir, f"{label}_launches.md"), "w") as f:
+    f.write(f"# {label}: launch list of C2 steps (commit {head})\n\n"
+            "`ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^k_|^Device' "
+            "-s 190 -c 70 python bench.py --steps 2 --warmup 3 --profile-mode`\n\n"
+            "Per-launch times under ncu are cold-cache and serialised: compare the SHARES with "
+            "`stages_ms_per_step` of the bench line, not the absolutes.\n\n" + ls)
+
+rep = os.path.join(go, f"prof_{tag}.ncu-rep")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
+                     text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+ix = {h: i for i, h in enumerate(hdr)}
+want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "sm__inst_executed.avg.per_cycle_active",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "lts__t_bytes.sum"]
+
+
+def to_bytes(val, unit):
+    v = float(val.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
+traffic, lines = {}, []
+for r in rows[2:]:
+    name = r[ix["Kernel Name"]].split("(")[0]
+    lines.append(f"## {name}\n")
+    lines.append("| metric | value |\n|---|---|")
+    for w in want:
+        if w in ix:
+            lines.append(f"| {w} | {r[ix[w]]} {units[ix[w]]} |")
+    stalls = []
+    for h in hdr:
+        if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio"):
+            try:
+                stalls.append((float(r[ix[h]]), h.replace("smsp__average_warps_issue_stalled_", "")
+                               .replace("_per_issue_active.ratio", "")))
+            except ValueError:
+                pass
+    top = ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)[:4])
+    lines.append(f"| top stalls (warps per issue) | {top} |\n")
+    if name in STAGE and STAGE[name] not in traffic:
+        traffic[STAGE[name]] = to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + \
+            to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
+with open(os.path.join(out_dir, f"{label}_ncu_top_kernels.md"), "w") as f:
+    f.write(f"# {label}: ncu --set full of the library's own kernels (commit {head})\n\n"
+            "`ncu --set full --clock-control none --import-source on -k regex:<kernels> -s 27 -c 10 "
+            "python bench.py --steps 2 --warmup 3 --profile-mode` — one launch per kernel, one C2 "
+            "step (25 x 640x480 frames).\n\n" + "\n".join(lines))
+with open(os.path.join(out_dir, "traffic.json"), "w") as f:
+    json.dump({"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch, from "
+                           f"profiles/{label}_ncu_top_kernels.md", **traffic}, f, indent=1)
+print("wrote", sorted(os.listdir(out_dir)))

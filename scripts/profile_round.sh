@@ -1,0 +1,15 @@
+#!/bin/bash
+# Runs ON THE GPU BOX (through gpurun): plain bench, ncu launch list of one step, ncu --set full
+# of the library's own top kernels.  Outputs land in gpurun_out/ with the tag given as $1.
+#   gpurun --timeout 1200 -- 'bash scripts/profile_round.sh r1'
+tag=${1:-r1}
+mkdir -p gpurun_out
+ARGS="--steps 2 --warmup 3 --profile-mode"
+python bench.py $ARGS > gpurun_out/plain_$tag.log 2>&1 || { echo "plain run failed"; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:^k_|^Device" -s 190 -c 70 --csv \
+    --log-file gpurun_out/launches_$tag.csv python bench.py $ARGS > gpurun_out/ncu_launches_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on \
+    -k "regex:k_block_accumulate|k_walk_segments|k_fold_wide|k_point_keys|k_voxel_update|k_long_finish|k_gather_sorted|k_resample_merge|k_fold_bundles|k_finalize_blocks" \
+    -s 27 -c 10 -o gpurun_out/prof_$tag -f python bench.py $ARGS > gpurun_out/ncu_full_$tag.log 2>&1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/smi_$tag.csv
+echo profile_round done
