@@ -862,6 +862,61 @@ k_mark_existing(IntegratorParams P, LayerView L, TouchView Tv, int32_t blocks_be
   }
 }
 
+// Counting sort of the segment slots by block ordinal (a few hundred distinct values, no order
+// needed inside a block): per-CTA histograms in shared memory, a scan of the global histogram,
+// then each CTA reserves one range per ordinal and scatters its tile.  Replaces two library radix
+// passes; unused (null) slots are dropped on the way.
+constexpr int kSortBins = 4096;      // ordinals handled in shared memory
+constexpr uint32_t kSortTile = 4096;  // slots per CTA round
+__global__ void __launch_bounds__(256)
+k_segment_hist(const uint32_t* __restrict__ keys, uint32_t num_slots, uint32_t null_key,
+               uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_hist[kSortBins];
+  for (int i = threadIdx.x; i < kSortBins; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  for (uint32_t t0 = blockIdx.x * kSortTile; t0 < num_slots; t0 += gridDim.x * kSortTile) {
+    const uint32_t t1 = min(num_slots, t0 + kSortTile);
+    for (uint32_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) {
+      const uint32_t k = keys[i];
+      if (k < null_key) atomicAdd(&s_hist[k], 1u);
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < null_key; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+__global__ void __launch_bounds__(256)
+k_segment_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ idx,
+                  uint32_t num_slots, uint32_t null_key, const uint32_t* __restrict__ bin_base,
+                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ keys_out,
+                  uint32_t* __restrict__ idx_out) {
+  __shared__ uint32_t s_cnt[kSortBins];   // per tile: count, then running position
+  for (uint32_t t0 = blockIdx.x * kSortTile; t0 < num_slots; t0 += gridDim.x * kSortTile) {
+    const uint32_t t1 = min(num_slots, t0 + kSortTile);
+    for (uint32_t i = threadIdx.x; i < null_key; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    for (uint32_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) {
+      const uint32_t k = keys[i];
+      if (k < null_key) atomicAdd(&s_cnt[k], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < null_key; i += blockDim.x) {
+      const uint32_t c = s_cnt[i];
+      s_cnt[i] = c ? bin_base[i] + atomicAdd(&cursor[i], c) : 0u;  // start of this tile's range
+    }
+    __syncthreads();
+    for (uint32_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) {
+      const uint32_t k = keys[i];
+      if (k < null_key) {
+        const uint32_t pos = atomicAdd(&s_cnt[k], 1u);
+        keys_out[pos] = k;
+        idx_out[pos] = idx[i];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Block pass.  The segments are sorted by block; a CTA takes a chunk of the sorted list and, per
 // block run inside it, replays the segments against a shared-memory tile of the block:
 // fixed-point weight accumulation with shared-memory atomics (deterministic: integer adds
@@ -877,8 +932,9 @@ constexpr int kEmitBuf = 128;
 __global__ void __launch_bounds__(kAccThreads)
 k_block_accumulate(IntegratorParams P, const Ray* __restrict__ rays,
                    const uint32_t* __restrict__ seg_keys, const uint32_t* __restrict__ seg_idx,
-                   const uint4* __restrict__ seg_recs, uint32_t num_slots, uint32_t null_key,
-                   TouchView Tv, float acc_scale, uint32_t ray_bits,
+                   const uint4* __restrict__ seg_recs, uint32_t num_slots_host,
+                   const uint32_t* __restrict__ num_slots_dev, uint32_t null_key, TouchView Tv,
+                   float acc_scale, uint32_t ray_bits,
                    unsigned long long* __restrict__ out, uint32_t* out_count, uint32_t out_cap,
                    uint32_t* work_counter) {
   // Accumulators as two 20-bit limbs in 32-bit words: shared memory has native 32-bit atomic adds
@@ -893,6 +949,8 @@ k_block_accumulate(IntegratorParams P, const Ray* __restrict__ rays,
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
+  // counting-sort path: the number of real segments is only known on the device
+  const uint32_t num_slots = num_slots_dev ? *num_slots_dev : num_slots_host;
   uint32_t cnt = 0;
   auto flush = [&]() {
     __syncwarp();
@@ -1579,16 +1637,45 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
         k_mark_existing<<<ctx->num_sms * 4, 128, 0, s>>>(P, L->v, tv,
                                                          static_cast<int32_t>(L->num_blocks));
     }
-    {
+    const uint32_t* sorted_keys = nullptr;
+    const uint32_t* sorted_idx = nullptr;
+    const uint32_t* num_real = nullptr;
+    if (null_key <= static_cast<uint32_t>(kSortBins)) {
+      StageScope sc(ctx, kStageSegmentSort, 3);
+      // hist[null_key + 1] | bin_base[null_key + 1] | cursor[null_key]
+      const size_t words = 3 * (size_t(null_key) + 1);
+      CG_CUDA(ctx->seg_bins.reserve(words * sizeof(uint32_t)));
+      uint32_t* hist = ctx->seg_bins.as<uint32_t>();
+      uint32_t* bin_base = hist + null_key + 1;
+      uint32_t* cursor = bin_base + null_key + 1;
+      CG_CUDA(fill_bytes(hist, 0, words * sizeof(uint32_t), s));
+      const unsigned sgrid = std::min<unsigned>(grid_for(num_slots, kSortTile), ctx->num_sms * 4u);
+      k_segment_hist<<<sgrid, 256, 0, s>>>(sk.Current(), static_cast<uint32_t>(num_slots), null_key,
+                                           hist);
+      size_t tmp_bins = 0;
+      CG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bins, hist, bin_base,
+                                            static_cast<int>(null_key + 1), s));
+      if (tmp_bins > ctx->cub_tmp.cap) CG_CUDA(ctx->cub_tmp.reserve(tmp_bins));
+      CG_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_bins, hist, bin_base,
+                                            static_cast<int>(null_key + 1), s));
+      k_segment_scatter<<<sgrid, 256, 0, s>>>(sk.Current(), sv.Current(),
+                                              static_cast<uint32_t>(num_slots), null_key, bin_base,
+                                              cursor, sk.Alternate(), sv.Alternate());
+      sorted_keys = sk.Alternate();
+      sorted_idx = sv.Alternate();
+      num_real = bin_base + null_key;  // total number of real segments
+    } else {
       StageScope sc(ctx, kStageSegmentSort, 0);
       CG_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_seg, sk, sv,
                                               static_cast<int>(num_slots), 0, ord_bits + 1, s));
+      sorted_keys = sk.Current();
+      sorted_idx = sv.Current();
     }
     {
       StageScope sc(ctx, kStageBlockAccumulate, 2);
       k_block_accumulate<<<ctx->num_sms * 5, kAccThreads, 0, s>>>(
-          P, ctx->rays.as<Ray>(), sk.Current(), sv.Current(), ctx->seg_recs.as<uint4>(),
-          static_cast<uint32_t>(num_slots), null_key, tv, acc_scale, ray_bits,
+          P, ctx->rays.as<Ray>(), sorted_keys, sorted_idx, ctx->seg_recs.as<uint4>(),
+          static_cast<uint32_t>(num_slots), num_real, null_key, tv, acc_scale, ray_bits,
           ctx->pkey_a.as<unsigned long long>(), ctx->d_touch_count + 1,
           static_cast<uint32_t>(num_pairs), ctx->d_walk_counters + 1);
       k_collect_walk<<<1, 1, 0, s>>>(L->v, ctx->d_touch_count, ctx->d_counters);
