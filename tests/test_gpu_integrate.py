@@ -150,6 +150,21 @@ def test_config_variants(gpu_ctx, over):
     gl.close()
 
 
+def test_full_resolution_frames_match_oracle(gpu_ctx):
+    """Dense 640x480 frames (bundles of up to ~1000 points, update lists of hundreds): the paths
+    the sub-sampled cases never reach — warp-cooperative bundle fold, warp replay of long update
+    lists, block tiles with many segments — against the oracle, voxel by voxel."""
+    frames = util.small_frames(3, stride=1, robot=1, submap=2)
+    assert len(frames[0][1]) == 640 * 480
+    got, ref, gl = _run_both(gpu_ctx, frames, batch=True, max_blocks=4096,
+                             default_truncation_distance=0.16)
+    util.compare_layers(got, ref, "full resolution, batch of 3")
+    gl.close()
+    got, ref, gl = _run_both(gpu_ctx, frames[:2], max_blocks=4096, use_const_weight=0)
+    util.compare_layers(got, ref, "full resolution, per frame, 1/z^2 weights")
+    gl.close()
+
+
 def test_fine_voxels_720p(gpu_ctx):
     from coxgraph_b200 import synth
     frames = util.small_frames(2, stride=8, cam=synth.CAM_1280x720)

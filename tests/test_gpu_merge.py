@@ -57,6 +57,30 @@ def test_merge_matches_oracle(gpu_ctx, pose_id):
     gb.close()
 
 
+def test_dense_submaps_project_matches_oracle(gpu_ctx):
+    """Submaps fused from full 640x480 frames (dense truncation bands, ~100 blocks each) projected
+    into one global layer under oblique poses, batched on the device, against the oracle's
+    sequential mergeLayerAintoLayerB."""
+    from coxgraph_b200 import Layer, getProjectedMap
+    from oracle import oracle_py as orc
+    ocfg, _ = util.make_cfgs(default_truncation_distance=0.16)
+    subs_o = [_submap(orc, ocfg, r, s, frames=2, stride=1) for (r, s) in ((0, 0), (1, 3), (0, 5))]
+    subs_g = [_to_gpu(gpu_ctx, ol) for ol in subs_o]
+    poses = [POSES[2].copy(), synth.robot_map_offset(1), POSES[4].copy()]
+    for T in poses:
+        T[:4] /= np.linalg.norm(T[:4])
+    og = orc.Layer(0.05)
+    for ol, T in zip(subs_o, poses):
+        og.merge_from(ol, T, threads=8)
+    gg = Layer(gpu_ctx, 0.05, max_blocks=8192)
+    st = getProjectedMap(subs_g, np.stack(poses), gg, want_stats=True)
+    assert st.blocks_in == sum(ol.num_blocks for ol in subs_o)
+    util.compare_layers(gg.download(), og.download(), "dense projection", check_flags=True)
+    assert util.exact_fraction(gg.download(), og.download()) > 0.999
+    for g in subs_g + [gg]:
+        g.close()
+
+
 def test_project_submaps_matches_sequential_oracle(gpu_ctx):
     from coxgraph_b200 import Layer, getProjectedMap
     from oracle import oracle_py as orc
