@@ -224,6 +224,8 @@ struct cg_context {
   cg::DevBuf seg_keys_a, seg_keys_b, seg_idx_a, seg_idx_b, seg_recs;  // (ray, block) segments
   cg::DevBuf seg_order;  // update lists in size-class order
   cg::DevBuf scan_partials, seg_bins;
+  cg::DevBuf grazing_keys, grazing_ray_key;  // anti-grazing: the scan's bundle voxels
+  uint32_t grazing_mask = 0;
   // per-call touch set (integrate.cu "back half"): kept all-clear between calls
   cg::DevBuf touch_ord, touch_entry, touch_acc, touch_bits;
   uint32_t* d_touch_count = nullptr;  // [0] blocks touched, [1] general (voxel, ray) keys emitted

@@ -261,6 +261,7 @@ struct IntegratorParams {
   int use_sparsity;
   int order_mode;
   int freespace;
+  int anti_grazing;
 };
 
 __device__ __forceinline__ float voxel_weight(const IntegratorParams& p, float z_C) {

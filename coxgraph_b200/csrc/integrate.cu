@@ -732,6 +732,60 @@ __device__ __forceinline__ Visit make_visit(const IntegratorParams& P, const flo
   return v;
 }
 
+// MergedTsdfIntegrator's optional anti-grazing (R6): a ray skips every voxel that holds points
+// of the same scan (i.e. that is the key of a non-clearing bundle of its frame) except, for a
+// non-clearing ray, its own bundle voxel.  The set of bundle voxels is a scratch hash set keyed by
+// (frame, voxel relative to the frame's sensor voxel).
+struct GrazingSet {
+  const unsigned long long* keys;      // open addressing, kEmptyKey = free
+  uint32_t mask;
+  const unsigned long long* ray_key;   // per ray (= bundle): its own packed bundle voxel
+};
+__device__ __forceinline__ unsigned long long grazing_key(uint32_t frame, int rx, int ry, int rz) {
+  return (static_cast<unsigned long long>(frame) << 42) |
+         (static_cast<unsigned long long>(rz & 0x3FFF) << 28) |
+         (static_cast<unsigned long long>(ry & 0x3FFF) << 14) |
+         static_cast<unsigned long long>(rx & 0x3FFF);
+}
+__device__ __forceinline__ bool grazing_contains(const GrazingSet& G, unsigned long long key) {
+  uint32_t h = hash_key(key) & G.mask;
+  for (;;) {
+    const unsigned long long k = G.keys[h];
+    if (k == key) return true;
+    if (k == kEmptyKey) return false;
+    h = (h + 1) & G.mask;
+  }
+}
+__global__ void k_grazing_build(KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
+                                const uint32_t* __restrict__ heads,
+                                const uint32_t* __restrict__ num_heads,
+                                unsigned long long* set_keys, uint32_t set_mask,
+                                unsigned long long* __restrict__ ray_key) {
+  const uint32_t nb = *num_heads;
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+    const BundleInfo bi = bundle_info(keys, total, heads, nb, b);
+    if (bi.key == kInvalidPointKey) continue;
+    const uint32_t fm = (1u << kl.rel_bits) - 1u;
+    const int ro = kl.rel_offset();
+    const int rx = static_cast<int>((bi.key >> kl.rank_bits) & fm) - ro;
+    const int ry = static_cast<int>((bi.key >> (kl.rank_bits + kl.rel_bits)) & fm) - ro;
+    const int rz = static_cast<int>((bi.key >> (kl.rank_bits + 2 * kl.rel_bits)) & fm) - ro;
+    const unsigned long long gk = grazing_key(kl.frame(bi.key), rx, ry, rz);
+    ray_key[b] = gk;
+    if (kl.clearing(bi.key)) continue;  // only non-clearing bundles are in the set
+    uint32_t h = hash_key(gk) & set_mask;
+    for (;;) {
+      const unsigned long long k = set_keys[h];
+      if (k == gk) break;
+      if (k == kEmptyKey) {
+        const unsigned long long old = atomicCAS(&set_keys[h], kEmptyKey, gk);
+        if (old == kEmptyKey || old == gk) break;
+      }
+      h = (h + 1) & set_mask;
+    }
+  }
+}
+
 // (ray, block) segment: the part of a ray's walk that lies inside one 16^3 block, with the
 // RayCaster state at its first voxel so that the block pass can replay it on its own.
 struct SegRecord {      // 32 B
@@ -747,13 +801,14 @@ static_assert(sizeof(SegRecord) == 32, "SegRecord is written as two 16-byte stor
 // visit with sdf < truncation (only the last `tail_visits` visits of a ray can be such,
 // walk_tail_visits()).  Ray r owns the record slots [seg_first(r), seg_first(r) + its closed-form
 // block count + slack); unused slots get the null key.
+template <bool kGrazing>
 __global__ void __launch_bounds__(kWalkThreads)
 k_walk_segments(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
                 uint32_t num_rays, const unsigned long long* __restrict__ ray_count,
                 const unsigned long long* __restrict__ ray_offset, uint32_t slack, LayerView L,
                 TouchView Tv, uint32_t tail_visits, uint32_t null_key, uint32_t* work_counter,
                 uint32_t* __restrict__ seg_keys, uint32_t* __restrict__ seg_idx,
-                uint4* __restrict__ seg_recs) {
+                uint4* __restrict__ seg_recs, GrazingSet G) {
   __shared__ unsigned long long cache[kBlockCacheSize];
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
@@ -773,6 +828,18 @@ k_walk_segments(IntegratorParams P, const float* __restrict__ poses, const Ray* 
     int lbx = 0x7FFFFFFF, lby = 0, lbz = 0;
     uint32_t ord = 0, s_entry = 0, s_visits = 0;
     float s_tnx = 0.0f, s_tny = 0.0f, s_tnz = 0.0f;
+    // anti-grazing: sensor voxel of the ray's frame and the ray's own bundle voxel
+    int svx = 0, svy = 0, svz = 0;
+    unsigned long long own_key = kEmptyKey;
+    uint32_t g_frame = 0;
+    if (kGrazing && w.remaining > 0) {
+      g_frame = w.ray.frame_clr & 0x7FFFFFFFu;
+      const float* T = poses + 7 * g_frame;
+      svx = grid_index(T[4], P.voxel_size_inv);
+      svy = grid_index(T[5], P.voxel_size_inv);
+      svz = grid_index(T[6], P.voxel_size_inv);
+      if (!(w.ray.frame_clr >> 31)) own_key = G.ray_key[r];
+    }
     const uint32_t sign_bits = (static_cast<uint32_t>(rc.sx + 1) << 12) |
                                (static_cast<uint32_t>(rc.sy + 1) << 14) |
                                (static_cast<uint32_t>(rc.sz + 1) << 16);
@@ -796,6 +863,23 @@ k_walk_segments(IntegratorParams P, const float* __restrict__ poses, const Ray* 
     // last visits, closing the last segment) runs converged instead of a few lanes at a time.
     for (uint32_t left = __reduce_max_sync(full, w.remaining); left > 0; --left) {
       if (w.remaining >= left) {
+        bool skip = false;
+        if (kGrazing) {
+          const int rx = rc.cx - svx, ry = rc.cy - svy, rz = rc.cz - svz;
+          if (abs(rx) < 8192 && abs(ry) < 8192 && abs(rz) < 8192) {
+            const unsigned long long gk = grazing_key(g_frame, rx, ry, rz);
+            skip = gk != own_key && grazing_contains(G, gk);
+          }
+        }
+        if (skip) {
+          // the reference "continue"s before it even looks the voxel up: no allocation, no
+          // update; the segment ends here and a new one starts at the next voxel that counts
+          if (s_visits) emit();
+          s_visits = 0;
+          rc.step();
+          --w.remaining;
+          continue;
+        }
         const int bx = rc.cx >> 4, by = rc.cy >> 4, bz = rc.cz >> 4;
         if (bx != lbx || by != lby || bz != lbz) {
           if (s_visits) emit();
@@ -813,11 +897,13 @@ k_walk_segments(IntegratorParams P, const float* __restrict__ poses, const Ray* 
             ord = touch_ordinal(Tv, entry, L.err);
             if (cacheable) cache[ci] = (tag << 20) | ord;
           }
+          s_visits = 0;
+        }
+        if (s_visits == 0) {  // first voxel of a segment (new block, or right after a skipped voxel)
           s_entry = static_cast<uint32_t>((rc.cx & 15) | ((rc.cy & 15) << 4) | ((rc.cz & 15) << 8));
           s_tnx = rc.tnx;
           s_tny = rc.tny;
           s_tnz = rc.tnz;
-          s_visits = 0;
         }
         ++s_visits;
         if (w.remaining <= tail_visits) {
@@ -1516,6 +1602,8 @@ static IntegratorParams make_params(const cg_layer* L, const cg_integrator_confi
   P.use_sparsity = c->use_sparsity_compensation_factor;
   P.order_mode = c->integration_order_mode;
   P.freespace = freespace;
+  // anti-grazing belongs to the merged integrator only (the simple one never looks at it)
+  P.anti_grazing = (c->enable_anti_grazing && c->method == CG_METHOD_MERGED) ? 1 : 0;
   return P;
 }
 
@@ -1596,7 +1684,9 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
   const unsigned walk_grid = std::min<unsigned>(grid_for(num_rays, kWalkThreads),
                                                 static_cast<unsigned>(ctx->num_sms) * 10u);
   size_t cap = std::max<size_t>(ctx->touch_cap, std::min<size_t>(L->max_blocks, env_size("CG_TOUCH_CAP", 1024)));
-  uint32_t slack = static_cast<uint32_t>(env_size("CG_SEGMENT_SLACK", 1));
+  // spare record slots per ray: a walk can end one step off its closed-form end voxel; with
+  // anti-grazing every skipped voxel also splits a segment
+  uint32_t slack = static_cast<uint32_t>(env_size("CG_SEGMENT_SLACK", P.anti_grazing ? 8 : 1));
   uint32_t n_touched = 0, n_general = 0;
   int64_t blocks_after = L->num_blocks;
   for (;;) {
@@ -1628,11 +1718,20 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
     CG_CUDA(fill_bytes(ctx->d_walk_counters, 0, 2 * sizeof(uint32_t), s));
     {
       StageScope sc(ctx, kStageWalkSegments, 2);
-      k_walk_segments<<<walk_grid, kWalkThreads, 0, s>>>(
-          P, ctx->group_poses, ctx->rays.as<Ray>(), num_rays,
-          ctx->ray_count.as<unsigned long long>(), ctx->ray_offset.as<unsigned long long>(), slack,
-          L->v, tv, tail_visits, null_key, ctx->d_walk_counters, sk.Current(), sv.Current(),
-          ctx->seg_recs.as<uint4>());
+      const GrazingSet gz{ctx->grazing_keys.as<unsigned long long>(), ctx->grazing_mask,
+                          ctx->grazing_ray_key.as<unsigned long long>()};
+      if (P.anti_grazing)
+        k_walk_segments<true><<<walk_grid, kWalkThreads, 0, s>>>(
+            P, ctx->group_poses, ctx->rays.as<Ray>(), num_rays,
+            ctx->ray_count.as<unsigned long long>(), ctx->ray_offset.as<unsigned long long>(),
+            slack, L->v, tv, tail_visits, null_key, ctx->d_walk_counters, sk.Current(),
+            sv.Current(), ctx->seg_recs.as<uint4>(), gz);
+      else
+        k_walk_segments<false><<<walk_grid, kWalkThreads, 0, s>>>(
+            P, ctx->group_poses, ctx->rays.as<Ray>(), num_rays,
+            ctx->ray_count.as<unsigned long long>(), ctx->ray_offset.as<unsigned long long>(),
+            slack, L->v, tv, tail_visits, null_key, ctx->d_walk_counters, sk.Current(),
+            sv.Current(), ctx->seg_recs.as<uint4>(), gz);
       if (L->num_blocks > 0)
         k_mark_existing<<<ctx->num_sms * 4, 128, 0, s>>>(P, L->v, tv,
                                                          static_cast<int32_t>(L->num_blocks));
@@ -1700,11 +1799,11 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
     }
     if (err & kErrSegmentFull) {
       // a walk ended off its closed-form end voxel by more steps than the slack allows
-      if (slack >= 4) {
-        set_error("ray walk crossed more blocks than its closed-form bound + 4");
+      if (slack >= 256) {
+        set_error("ray walk needs more than its closed-form block count + 256 segment records");
         return CG_ERR_INVALID_ARG;
       }
-      slack = 4;
+      slack *= 4;
     }
   }
   TouchView tv{ctx->touch_ord.as<int32_t>(), ctx->touch_entry.as<uint32_t>(),
@@ -1909,6 +2008,19 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
       k_bundle_rays<<<bgrid, 256, 0, s>>>(P, ctx->group_poses, d_num, ctx->rays.as<Ray>(),
                                           ctx->ray_count.as<unsigned long long>());
     }
+    if (P.anti_grazing) {  // set of the scan's bundle voxels (at most one per point)
+      size_t gcap = 1024;
+      while (gcap < 2 * total) gcap <<= 1;
+      CG_CUDA(ctx->grazing_keys.reserve(gcap * sizeof(unsigned long long)));
+      CG_CUDA(ctx->grazing_ray_key.reserve(upper * sizeof(unsigned long long)));
+      ctx->grazing_mask = static_cast<uint32_t>(gcap - 1);
+      CG_CUDA(fill_bytes(ctx->grazing_keys.p, 0xFF, gcap * sizeof(unsigned long long), s));
+      k_grazing_build<<<bgrid, 256, 0, s>>>(kl, dk.Current(), static_cast<uint32_t>(total),
+                                            ctx->scan.as<uint32_t>(), d_num,
+                                            ctx->grazing_keys.as<unsigned long long>(),
+                                            ctx->grazing_mask,
+                                            ctx->grazing_ray_key.as<unsigned long long>());
+    }
   } else {
     {
       StageScope sc(ctx, kStageBundleScan, 0);
@@ -2020,10 +2132,6 @@ static int32_t integrate_job(cg_layer* L, const cg_integrator_config* cfg, size_
     return CG_ERR_UNSUPPORTED;
   }
   if (cfg->method != CG_METHOD_MERGED && cfg->method != CG_METHOD_SIMPLE) return CG_ERR_INVALID_ARG;
-  if (cfg->enable_anti_grazing) {
-    set_error("enable_anti_grazing is not supported yet");
-    return CG_ERR_UNSUPPORTED;
-  }
   if (!(cfg->default_truncation_distance > 0.0f) || !(cfg->max_ray_length_m > 0.0f)) {
     set_error("invalid integrator config");
     return CG_ERR_INVALID_ARG;

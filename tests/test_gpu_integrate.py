@@ -142,6 +142,8 @@ def test_touch_scratch_growth(monkeypatch):
          sparsity_compensation_factor=20.0, max_weight=1000.0),
     dict(integration_order_mode=1),
     dict(default_truncation_distance=0.16),
+    dict(enable_anti_grazing=1),
+    dict(enable_anti_grazing=1, voxel_carving_enabled=0, use_const_weight=0),
 ])
 def test_config_variants(gpu_ctx, over):
     frames = util.small_frames(2, stride=8, robot=1)
@@ -162,6 +164,14 @@ def test_full_resolution_frames_match_oracle(gpu_ctx):
     gl.close()
     got, ref, gl = _run_both(gpu_ctx, frames[:2], max_blocks=4096, use_const_weight=0)
     util.compare_layers(got, ref, "full resolution, per frame, 1/z^2 weights")
+    gl.close()
+    # anti-grazing at full density: many voxels are skipped (the result must differ from the
+    # plain one) and segments are split at every skipped voxel
+    plain = got
+    got, ref, gl = _run_both(gpu_ctx, frames[:2], batch=True, max_blocks=4096,
+                             use_const_weight=0, enable_anti_grazing=1)
+    util.compare_layers(got, ref, "full resolution, anti-grazing")
+    assert got[0].shape != plain[0].shape or not np.array_equal(got[1]["weight"], plain[1]["weight"])
     gl.close()
 
 
