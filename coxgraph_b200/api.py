@@ -140,6 +140,28 @@ class Layer:
                                                  C.byref(cnt)))
         return idx[:n], vox[:n], flags[:n]
 
+    def serializeLayerAsMsg(self, only_updated=False):
+        """voxblox::serializeLayerAsMsg block payload: (block_idx int32 [B,3], data uint32
+        [B, 12288]) — three words per voxel, colour packed a | b<<8 | g<<16 | r<<24."""
+        lib = capi.load()
+        n = C.c_size_t(0)
+        capi.check(lib.cg_layer_serialize(self._h, int(bool(only_updated)), 0, None, None,
+                                          C.byref(n)))
+        idx = np.zeros((n.value, 3), np.int32)
+        data = np.zeros((n.value, 3 * capi.VOXELS_PER_BLOCK), np.uint32)
+        if n.value:
+            capi.check(lib.cg_layer_serialize(self._h, int(bool(only_updated)), n.value, _ptr(idx),
+                                              _ptr(data), C.byref(n)))
+        return idx[:n.value], data[:n.value]
+
+    def resetUpdated(self):
+        capi.check(capi.load().cg_layer_reset_updated(self._h))
+
+    def deserializeMsgToLayer(self, block_idx, data):
+        idx = np.ascontiguousarray(block_idx, np.int32).reshape(-1, 3)
+        words = np.ascontiguousarray(data, np.uint32).reshape(len(idx), 3 * capi.VOXELS_PER_BLOCK)
+        capi.check(capi.load().cg_layer_deserialize(self._h, len(idx), _ptr(idx), _ptr(words)))
+
     def upload(self, block_idx, voxels, flags=None):
         idx = np.ascontiguousarray(block_idx, np.int32).reshape(-1, 3)
         vox = np.ascontiguousarray(voxels, VOXEL_DTYPE).reshape(len(idx), capi.VOXELS_PER_BLOCK)

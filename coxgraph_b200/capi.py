@@ -80,6 +80,9 @@ SYMBOLS = {
     "cg_layer_voxel_size": (C.c_float, [_P]),
     "cg_layer_download": (C.c_int32, [_P, C.c_size_t, _P, _P, _P, C.POINTER(C.c_size_t)]),
     "cg_layer_upload": (C.c_int32, [_P, C.c_size_t, _P, _P, _P]),
+    "cg_layer_serialize": (C.c_int32, [_P, C.c_int32, C.c_size_t, _P, _P, C.POINTER(C.c_size_t)]),
+    "cg_layer_reset_updated": (C.c_int32, [_P]),
+    "cg_layer_deserialize": (C.c_int32, [_P, C.c_size_t, _P, _P]),
     "cg_layer_block_indices": (C.c_int32, [_P, C.c_size_t, _P, C.POINTER(C.c_size_t)]),
     "cg_integrator_config_default": (None, [C.POINTER(IntegratorConfig)]),
     "cg_integrate_pointcloud": (C.c_int32, [_P, C.POINTER(IntegratorConfig), _P, _P, _P,

@@ -99,6 +99,86 @@ __global__ void k_gather_aos(LayerView L, const uint32_t* slots, int first, int 
   }
 }
 
+// voxblox::Block<TsdfVoxel>::serializeToIntegers: three words per voxel — float bits of the
+// distance, float bits of the weight, colour packed a | b << 8 | g << 16 | r << 24
+__device__ __forceinline__ uint32_t msg_color(uint32_t rgba) {  // rgba: r | g << 8 | b << 16 | a << 24
+  return __byte_perm(rgba, 0, 0x0123);
+}
+__global__ void k_serialize_blocks(LayerView L, const uint32_t* slots, int count,
+                                   uint32_t* out_words, int32_t* out_idx,
+                                   const uint64_t* sorted_keys, const uint32_t* order) {
+  const int b = blockIdx.x;
+  if (b >= count) return;
+  const int src = order ? static_cast<int>(order[b]) : b;
+  const int slot = slots[src];
+  const float* d = L.dist_plane(slot);
+  const float* w = L.weight_plane(slot);
+  const uint32_t* c = L.color_plane(slot);
+  uint32_t* o = out_words + static_cast<size_t>(b) * (3 * kVoxelsPerBlock);
+  for (int i = threadIdx.x; i < kVoxelsPerBlock; i += blockDim.x) {
+    o[3 * i + 0] = __float_as_uint(d[i]);
+    o[3 * i + 1] = __float_as_uint(w[i]);
+    o[3 * i + 2] = msg_color(c[i]);
+  }
+  if (threadIdx.x == 0) {
+    int x, y, z;
+    unpack_block_key(sorted_keys[src], x, y, z);
+    out_idx[3 * b + 0] = x;
+    out_idx[3 * b + 1] = y;
+    out_idx[3 * b + 2] = z;
+  }
+}
+__global__ void k_select_updated(LayerView L, const uint32_t* slots, int n, uint32_t* order,
+                                 uint32_t* count) {
+  // sorted position i -> kept, in order (single CTA, n is a few thousand blocks at most per call)
+  __shared__ uint32_t s_run;
+  if (threadIdx.x == 0) s_run = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const bool keep = i < n && L.updated[slots[i]];
+    // ordered compaction: ballot within warps, warp offsets through shared memory
+    __shared__ uint32_t s_warp[32];
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s_warp[wid] = __popc(m);
+    __syncthreads();
+    uint32_t before = 0;
+    for (int k = 0; k < wid; ++k) before += s_warp[k];
+    if (keep) order[s_run + before + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tot = 0;
+      for (int k = 0; k < static_cast<int>(blockDim.x >> 5); ++k) tot += s_warp[k];
+      s_run += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = s_run;
+}
+__global__ void k_deserialize_write(LayerView L, const int32_t* entries, const uint32_t* in_words,
+                                    int n) {
+  const int b = blockIdx.x;
+  if (b >= n) return;
+  const int e = entries[b];
+  if (e < 0) return;
+  const int slot = L.hash_vals[e];
+  if (slot < 0) return;
+  float* d = L.dist_plane(slot);
+  float* w = L.weight_plane(slot);
+  uint32_t* c = L.color_plane(slot);
+  const uint32_t* in = in_words + static_cast<size_t>(b) * (3 * kVoxelsPerBlock);
+  for (int i = threadIdx.x; i < kVoxelsPerBlock; i += blockDim.x) {
+    d[i] = __uint_as_float(in[3 * i + 0]);
+    w[i] = __uint_as_float(in[3 * i + 1]);
+    c[i] = msg_color(in[3 * i + 2]);  // the byte reversal is its own inverse
+  }
+  if (threadIdx.x == 0) {
+    L.has_data[slot] = 1;  // Block::deserializeFromIntegers
+    L.updated[slot] = 1;
+  }
+}
+
 __global__ void k_unpack_idx(const uint64_t* sorted_keys, int n, int32_t* out_idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -460,6 +540,87 @@ int32_t cg_layer_download(const cg_layer* L, size_t capacity, int32_t* idx, cg_t
   }
   CG_CUDA(cudaGetLastError());
   return CG_OK;
+}
+
+int32_t cg_layer_serialize(const cg_layer* L, int32_t only_updated, size_t capacity, int32_t* idx,
+                           uint32_t* data, size_t* n_out) {
+  if (!L) return CG_ERR_INVALID_ARG;
+  cg_context* ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  const size_t n_all = static_cast<size_t>(L->num_blocks);
+  if (n_out) *n_out = 0;
+  if (n_all == 0) return CG_OK;
+  const uint64_t* keys;
+  const uint32_t* slots;
+  int32_t rc = sort_blocks(L, &keys, &slots);
+  if (rc) return rc;
+  size_t n = n_all;
+  const uint32_t* order = nullptr;
+  if (only_updated) {  // Layer::getAllUpdatedBlocks
+    CG_CUDA(ctx->val_a.reserve(sizeof(uint32_t) * (n_all + 1)));  // val_a is free after the sort
+    uint32_t* d_order = ctx->val_a.as<uint32_t>();
+    k_select_updated<<<1, 1024, 0, s>>>(L->v, slots, static_cast<int>(n_all), d_order,
+                                        d_order + n_all);
+    uint32_t cnt = 0;
+    CG_CUDA(cudaMemcpyAsync(&cnt, d_order + n_all, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CG_CUDA(cudaStreamSynchronize(s));
+    n = cnt;
+    order = d_order;
+  }
+  if (n_out) *n_out = n;
+  if (n == 0 || (!idx && !data)) return CG_OK;
+  if (capacity < n || !idx || !data) {
+    set_error("cg_layer_serialize: capacity %zu < %zu blocks (or null output)", capacity, n);
+    return CG_ERR_INVALID_ARG;
+  }
+  const size_t chunk = 2048;  // 96 MB staging
+  CG_CUDA(ctx->stage_a.reserve(std::min(chunk, n) * CG_BLOCK_BYTES));
+  CG_CUDA(ctx->stage_b.reserve(std::min(chunk, n) * 3 * sizeof(int32_t)));
+  for (size_t first = 0; first < n; first += chunk) {
+    const size_t cnt = std::min(chunk, n - first);
+    k_serialize_blocks<<<static_cast<unsigned>(cnt), 256, 0, s>>>(
+        L->v, order ? slots : slots + first, static_cast<int>(cnt), ctx->stage_a.as<uint32_t>(),
+        ctx->stage_b.as<int32_t>(), order ? keys : keys + first, order ? order + first : nullptr);
+    CG_CUDA(cudaMemcpyAsync(data + first * 3 * kVoxelsPerBlock, ctx->stage_a.p, cnt * CG_BLOCK_BYTES,
+                            cudaMemcpyDeviceToHost, s));
+    CG_CUDA(cudaMemcpyAsync(idx + first * 3, ctx->stage_b.p, cnt * 3 * sizeof(int32_t),
+                            cudaMemcpyDeviceToHost, s));
+    CG_CUDA(cudaStreamSynchronize(s));
+  }
+  CG_CUDA(cudaGetLastError());
+  return CG_OK;
+}
+
+int32_t cg_layer_reset_updated(cg_layer* L) {
+  if (!L) return CG_ERR_INVALID_ARG;
+  if (L->num_blocks > 0)
+    CG_CUDA(cudaMemsetAsync(L->v.updated, 0, static_cast<size_t>(L->num_blocks), L->ctx->stream));
+  CG_CUDA(cudaStreamSynchronize(L->ctx->stream));
+  return CG_OK;
+}
+
+int32_t cg_layer_deserialize(cg_layer* L, size_t n, const int32_t* idx, const uint32_t* data) {
+  if (!L || (n && (!idx || !data))) return CG_ERR_INVALID_ARG;
+  cg_context* ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  const size_t chunk = 2048;
+  CG_CUDA(ctx->stage_a.reserve(std::min(chunk, n) * CG_BLOCK_BYTES));
+  CG_CUDA(ctx->stage_b.reserve(std::min(chunk, n) * 4 * sizeof(int32_t)));
+  for (size_t first = 0; first < n; first += chunk) {
+    const size_t cnt = std::min(chunk, n - first);
+    int32_t* d_idx = ctx->stage_b.as<int32_t>();
+    int32_t* d_entries = d_idx + 3 * cnt;
+    CG_CUDA(cudaMemcpyAsync(d_idx, idx + 3 * first, cnt * 3 * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, s));
+    CG_CUDA(cudaMemcpyAsync(ctx->stage_a.p, data + first * 3 * kVoxelsPerBlock, cnt * CG_BLOCK_BYTES,
+                            cudaMemcpyHostToDevice, s));
+    k_upload_insert<<<grid_for(cnt, 128), 128, 0, s>>>(L->v, d_idx, static_cast<int>(cnt),
+                                                       d_entries);
+    k_deserialize_write<<<static_cast<unsigned>(cnt), 256, 0, s>>>(
+        L->v, d_entries, ctx->stage_a.as<uint32_t>(), static_cast<int>(cnt));
+    CG_CUDA(cudaStreamSynchronize(s));
+  }
+  return finish_call(L, nullptr);
 }
 
 int32_t cg_layer_upload(cg_layer* L, size_t n, const int32_t* idx, const cg_tsdf_voxel* voxels,

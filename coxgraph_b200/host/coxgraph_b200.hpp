@@ -146,6 +146,23 @@ class TsdfLayer {
     check(cg_layer_download(layer_, n, n ? &(*indices)[0].x : nullptr, voxels->data(),
                             flags ? flags->data() : nullptr, &got));
   }
+  // voxblox::serializeLayerAsMsg block payload (Block::serializeToIntegers per block: 3 words per
+  // voxel, colour a | b<<8 | g<<16 | r<<24), produced on the device
+  void serializeLayerAsMsg(bool only_updated, BlockIndexList* indices,
+                           std::vector<uint32_t>* data) const {
+    size_t n = 0;
+    check(cg_layer_serialize(layer_, only_updated ? 1 : 0, 0, nullptr, nullptr, &n));
+    indices->resize(n);
+    data->resize(n * 3 * CG_VOXELS_PER_BLOCK);
+    if (n)
+      check(cg_layer_serialize(layer_, only_updated ? 1 : 0, n, &(*indices)[0].x, data->data(), &n));
+  }
+  void deserializeMsgToLayer(const BlockIndexList& indices, const std::vector<uint32_t>& data) {
+    if (data.size() != indices.size() * 3 * CG_VOXELS_PER_BLOCK)
+      fatal_handler()(CG_ERR_INVALID_ARG, "deserializeMsgToLayer: data size does not match");
+    check(cg_layer_deserialize(layer_, indices.size(), indices.empty() ? nullptr : &indices[0].x,
+                               data.data()));
+  }
   // insert / overwrite blocks (deserializeMsgToLayer hand-off,
   // coxgraph/include/coxgraph/utils/msg_converter.h:107-109)
   void upload(const BlockIndexList& indices, const std::vector<TsdfVoxel>& voxels,

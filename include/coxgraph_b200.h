@@ -143,6 +143,23 @@ int32_t cg_layer_download(const cg_layer* layer, size_t capacity_blocks, int32_t
  * coxgraph/include/coxgraph/utils/msg_converter.h:107-109). flags may be NULL (has_data). */
 int32_t cg_layer_upload(cg_layer* layer, size_t num_blocks, const int32_t* block_idx_xyz,
                         const cg_tsdf_voxel* voxels, const uint8_t* flags);
+/* The block payload of voxblox_msgs/Layer, produced / consumed on the device
+ * (voxblox::serializeLayerAsMsg / deserializeMsgToLayer = Block::serializeToIntegers per block;
+ * reference call sites coxgraph/include/coxgraph/utils/msg_converter.h:49-50 and :107-109,
+ * coxgraph/src/client/map_server.cpp:88-89, coxgraph/include/coxgraph/map_comm/tsdf_recover.h:95).
+ * Per block: x/y/z index (block_idx_xyz, int32[3]) and data = 4096 x 3 uint32 words {float bits
+ * of distance, float bits of weight, colour a | b<<8 | g<<16 | r<<24}, blocks in (z, y, x) order.
+ * only_updated != 0 keeps the blocks whose `updated` flag is set (serializeLayerAsMsg's
+ * only_updated / getAllUpdatedBlocks).  Call with data == NULL to get the block count. */
+int32_t cg_layer_serialize(const cg_layer* layer, int32_t only_updated, size_t capacity_blocks,
+                           int32_t* block_idx_xyz, uint32_t* data, size_t* num_blocks_out);
+/* Block::updated().reset() for every block (what a publisher does after sending the updated
+ * blocks). */
+int32_t cg_layer_reset_updated(cg_layer* layer);
+/* Blocks are created or overwritten and marked has_data + updated (deserializeMsgToLayer with
+ * action kUpdate; call cg_layer_clear first for kReset). */
+int32_t cg_layer_deserialize(cg_layer* layer, size_t num_blocks, const int32_t* block_idx_xyz,
+                             const uint32_t* data);
 /* Block indices only (sorted), e.g. to compare allocation sets. */
 int32_t cg_layer_block_indices(const cg_layer* layer, size_t capacity_blocks,
                                int32_t* block_idx_xyz, size_t* num_blocks_out);
