@@ -130,3 +130,48 @@ def test_merge_algebra_at_full_size(gpu_ctx):
     assert 0.5 * q.num_blocks < p.num_blocks < 2 * q.num_blocks
     for L in subs + [g, h, p, q]:
         L.close()
+
+
+def test_block_pool_beyond_4_gib(gpu_ctx):
+    """C4 needs ~2 M blocks (98 GB): voxel offsets must be 64-bit.  Fill a layer with > 87 k far-away
+    blocks (4.9 GB of pool) so that every block the frames touch lies beyond the 4 GiB mark, then
+    fuse, merge and read back against the oracle."""
+    from coxgraph_b200 import Layer, TsdfIntegrator, mergeLayerAintoLayerB, VOXEL_DTYPE
+    from oracle import oracle_py as orc
+    ocfg, gcfg = util.make_cfgs()
+    gl = Layer(gpu_ctx, 0.05, max_blocks=100_000)
+    chunk = 2048
+    filler = np.zeros((chunk, 4096), VOXEL_DTYPE)
+    filler["distance"], filler["weight"] = 0.03, 2.0
+    filler["rgba"] = (9, 8, 7, 255)
+    n_fill = 0
+    for k in range(44):                     # 44 x 2048 = 90,112 blocks = 4.43 GB
+        idx = np.stack([np.arange(chunk, dtype=np.int32) - 1024, np.full(chunk, 5000 + k, np.int32),
+                        np.full(chunk, -3000, np.int32)], axis=1)
+        gl.upload(idx, filler)
+        n_fill += chunk
+    assert gl.num_blocks == n_fill and n_fill * 49152 > 4 * 2**30
+    frames = util.small_frames(2, stride=8)
+    ol = orc.Layer(0.05)
+    integ = TsdfIntegrator(gcfg, gl)
+    for (T, p, c) in frames:
+        ol.integrate(ocfg, T, p, c)
+        integ.integratePointCloud(T, p, c)
+    oi, ov, of = ol.download()
+    assert gl.num_blocks == n_fill + len(oi)
+    gi, gv, gf = gl.download()
+    mine = gi[:, 1] < 4000                  # the filler blocks sit at y >= 5000
+    util.compare_layers((gi[mine], gv[mine], gf[mine]), (oi, ov, of), "blocks beyond 4 GiB")
+    far = gv[~mine]                           # the filler blocks are untouched
+    assert (far["distance"] == np.float32(0.03)).all() and (far["weight"] == 2.0).all()
+    assert (far["rgba"] == np.array([9, 8, 7, 255], np.uint8)).all()
+    # merge out of the big layer (source blocks beyond 4 GiB) into a fresh one
+    og, gg = orc.Layer(0.05), Layer(gpu_ctx, 0.05, max_blocks=4096)
+    small = Layer(gpu_ctx, 0.05, max_blocks=2048)
+    small.upload(gi[mine], gv[mine])
+    T = np.array([np.cos(0.2), 0, 0, np.sin(0.2), 0.3, 0.1, 0.0], np.float32)
+    og.merge_from(ol, T)
+    mergeLayerAintoLayerB(small, T, gg)
+    util.compare_layers(gg.download(), og.download(), "merge after the big layer")
+    for L in (gl, gg, small):
+        L.close()
