@@ -4,24 +4,30 @@
 // SURVEY.md §8a); reference call site coxgraph/include/coxgraph/map_comm/tsdf_recover.h:75.
 //
 // One job = one frame, or a batch of frames fused into the same layer (the loop of
-// tsdf_recover.h:71-86).  All frames of a job go through every stage together:
-//   k_point_keys    validity, T_G_C * p, bundle key = (frame | clearing | voxel of p_G relative to
-//                   the sensor voxel), written in index-getter ("mixed") order
-//   radix sort      stable sort-by-key -> bundles in canonical order, points of a bundle in the
-//                   order the reference visits them
-//   select          bundle heads
-//   k_fold_bundles  one warp per bundle: cooperative gather, then the reference's *sequential*
-//                   weighted mean / colour blend (bit-exact: the merged point decides which voxels
-//                   and blocks the ray visits) -> one ray per bundle
-//   scan            pair offsets from the closed-form ray length (steps + 1)
-//   k_ray_walk      3-D DDA per ray (voxblox::RayCaster); inserts every visited block into the
-//                   GPU hash (allocation on first visit, R4); emits (hash entry, voxel) keys
-//   radix sort      stable sort-by-key -> per-voxel update lists in canonical order
-//   select          voxel segment heads
-//   k_voxel_update  one warp per voxel segment; 32 updates at a time: weights by prefix sum, the
-//                   clamped weighted average as an ordered composition of clamped affine maps
-//                   x -> clamp(a x + b) (associative, so it reduces in log steps), colours
-//                   replayed sequentially for the few updates inside the truncation band.
+// tsdf_recover.h:71-86).  All frames of a job go through every stage together (DESIGN.md §4):
+//  front half — points to one ray per bundle (R1, R2, R6)
+//   k_point_keys        validity, T_G_C * p, bundle key [frame | clearing | voxel of p_G relative
+//                       to the sensor voxel | visit rank]
+//   radix sort (keys)   on the bits above the rank: bundles in canonical order, their points in the
+//                       order the reference visits them
+//   select              bundle heads
+//   k_gather_sorted     the sorted points next to each other
+//   k_bundle_histogram / k_bundle_order   bundles by size class, longest first
+//   k_fold_wide / k_fold_bundles          the reference's *sequential* weighted mean and colour
+//                       blend per bundle (bit-exact: the merged point decides which voxels and
+//                       blocks the ray visits) -> one ray per bundle
+//   k_grazing_build     (anti-grazing only) set of the scan's bundle voxels
+//   k_bundle_rays       T_G_C * merged point, closed-form visit / block counts; k_scan_* offsets
+//  back half — rays to voxels (R3, R4, R5)
+//   k_walk_segments     3-D DDA per ray (voxblox::RayCaster); every visited block enters the GPU
+//                       hash (allocation on first visit); one record per (ray, block); voxels
+//                       whose update order matters are flagged "general"
+//   k_segment_hist / k_segment_scatter    segments grouped by block
+//   k_block_accumulate  per block, in shared memory: commutative weight sums of the free-space
+//                       visits; visits of general voxels go out as (voxel, ray) keys
+//   radix sort (keys)   per-voxel update lists in canonical order
+//   k_voxel_update / k_long_partials / k_long_finish   ordered replay of the general voxels
+//   k_finalize_blocks   coalesced read-modify-write of the free-space voxels of every touched block
 // Per-voxel order is (frame, non-clearing before clearing, bundle key ascending) — the oracle's
 // canonical order — independent of scheduling.
 #include <cub/cub.cuh>
