@@ -687,6 +687,7 @@ __device__ __forceinline__ uint32_t next_ray_batch(uint32_t* work_counter, int l
 struct WalkRay {
   RayCaster rc;
   Ray ray;
+  V3 origin;  // sensor origin of the ray's frame
   uint32_t remaining;
 };
 __device__ __forceinline__ WalkRay load_walk_ray(const IntegratorParams& P,
@@ -698,11 +699,13 @@ __device__ __forceinline__ WalkRay load_walk_ray(const IntegratorParams& P,
   w.rc.steps = 0;
   w.ray.frame_clr = kNoRay;
   w.ray.weight = 0.0f;
+  w.origin = V3{0.0f, 0.0f, 0.0f};
   if (r < num_rays) {
     w.ray = rays[r];
     if (w.ray.frame_clr != kNoRay) {
       const float* T = poses + 7 * (w.ray.frame_clr & 0x7FFFFFFFu);
-      w.rc.init(V3{T[4], T[5], T[6]}, V3{w.ray.px, w.ray.py, w.ray.pz},
+      w.origin = V3{T[4], T[5], T[6]};
+      w.rc.init(w.origin, V3{w.ray.px, w.ray.py, w.ray.pz},
                 (w.ray.frame_clr >> 31) != 0, P.carving != 0, P.max_ray, P.voxel_size_inv, P.trunc);
       if (!w.rc.valid && !w.rc.in_range && err) atomicOr(err, kErrOutOfRange);
     }
@@ -716,10 +719,8 @@ struct Visit {
   float sdf, w;
   uint32_t col;
 };
-__device__ __forceinline__ Visit make_visit(const IntegratorParams& P, const float* __restrict__ poses,
-                                            const Ray& ray, V3 center) {
-  const float* T = poses + 7 * (ray.frame_clr & 0x7FFFFFFFu);
-  const V3 origin = V3{T[4], T[5], T[6]};
+__device__ __forceinline__ Visit make_visit(const IntegratorParams& P, V3 origin, const Ray& ray,
+                                            V3 center) {
   const V3 pg = V3{ray.px, ray.py, ray.pz};
   // computeDistance + weight drop-off / sparsity compensation
   const V3 v_voxel_origin = center - origin;
@@ -736,6 +737,11 @@ __device__ __forceinline__ Visit make_visit(const IntegratorParams& P, const flo
   if (P.use_sparsity && fabsf(v.sdf) < P.trunc) v.w *= P.sparsity_factor;
   v.col = ray.color;
   return v;
+}
+__device__ __forceinline__ Visit make_visit(const IntegratorParams& P, const float* __restrict__ poses,
+                                            const Ray& ray, V3 center) {
+  const float* T = poses + 7 * (ray.frame_clr & 0x7FFFFFFFu);
+  return make_visit(P, V3{T[4], T[5], T[6]}, ray, center);
 }
 
 // MergedTsdfIntegrator's optional anti-grazing (R6): a ray skips every voxel that holds points
@@ -915,7 +921,7 @@ k_walk_segments(IntegratorParams P, const float* __restrict__ poses, const Ray* 
         if (w.remaining <= tail_visits) {
           const V3 center = V3{center_coord(rc.cx, P.voxel_size), center_coord(rc.cy, P.voxel_size),
                                center_coord(rc.cz, P.voxel_size)};
-          const float sdf = make_visit(P, poses, w.ray, center).sdf;
+          const float sdf = make_visit(P, w.origin, w.ray, center).sdf;
           if (!(sdf >= P.trunc)) {
             const uint32_t vid = (ord << 12) | static_cast<uint32_t>((rc.cx & 15) + 16 * ((rc.cy & 15) +
                                                                      16 * (rc.cz & 15)));
