@@ -32,5 +32,9 @@ for it in range(3):
     getProjectedMap(subs, poses, glob)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    if it == 2:
+        ctx.reset_profile(); ctx.set_profiling(True)
+        glob.removeAllBlocks(); getProjectedMap(subs, poses, glob); ctx.set_profiling(False)
+        print({k: round(v[0], 3) for k, v in ctx.profile().items() if v[0] > 0})
     print(f"project {nsub} submaps ({blocks_in} blocks in, {glob.num_blocks} global): {dt*1e3:.2f} ms, "
           f"{4096*blocks_in/dt/1e9:.2f} G voxels/s, {dt*1e3/nsub:.3f} ms/submap")
