@@ -56,7 +56,7 @@ def to_bytes(val, unit):
 
 traffic, lines = {}, []
 for r in rows[2:]:
-    name = r[ix["Kernel Name"]].split("(")[0]
+    name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0].strip()
     lines.append(f"## {name}\n")
     lines.append("| metric | value |\n|---|---|")
     for w in want:
