@@ -390,7 +390,17 @@ def run_ours(args, rank, world, local_rank):
         t1 = time.perf_counter()
         og.merge_from(ol, e["T_M_S"])          # single thread, as the reference merges
         t_m = time.perf_counter() - t1
+        # the reference's own setting is integrator_threads: 8 (tsdf_server_euroc.yaml:10)
+        ol8 = orc.Layer(VOXEL_SIZE)
+        t8 = time.perf_counter()
+        done8 = 0
+        for f in range(min(5, FRAMES_PER_SUBMAP)):
+            a, b = int(e["offs"][f]), int(e["offs"][f + 1])
+            ol8.integrate(ocfg, e["poses"][f], e["h_pts"][a:b], e["h_cols"][a:b], threads=8)
+            done8 += b - a
+        t8 = time.perf_counter() - t8
         cpu = {"value": done / t_cpu, "unit": "points/s", "cores": threads, "kind": "port",
+               "value_8_threads": done8 / t8,
                "sample": f"first {done // 307200} frames ({done} points) of one submap, "
                          f"{threads}-thread voxblox-style integrator (oracle port)",
                "merge_voxels_per_s": 4096 * ol.num_blocks / t_m, "merge_threads": 1}
@@ -471,8 +481,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pool", type=int, default=6, help="distinct submaps kept resident")
-    ap.add_argument("--ref-frames", type=int, default=2,
-                    help="frames per step the reference arm fuses (bounded sample)")
+    ap.add_argument("--ref-frames", type=int, default=FRAMES_PER_SUBMAP,
+                    help="frames per step the reference arm fuses (25 = the whole step; fewer = a "
+                         "bounded sample)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--project-submaps", type=int, default=40,
                     help="submaps of the separate getProjectedMap timing (0 = skip)")
