@@ -1,0 +1,99 @@
+"""Edge-case parity of the CUDA integration path against the oracle on hand-built clouds (not
+depth images): one giant bundle, thousands of updates on the same voxels (the long-list replay
+and its closed form), points exactly on voxel faces, duplicates, non-finite and zero points,
+rays along the axes, random poses.  Reference call site: tsdf_recover.h:75."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _pose(rng=None):
+    if rng is None:
+        return np.array([1, 0, 0, 0, 0.01, 0.02, 0.03], np.float32)
+    q = rng.standard_normal(4)
+    q /= np.linalg.norm(q)
+    return np.concatenate([q, rng.uniform(-2, 2, 3)]).astype(np.float32)
+
+
+def _colors(n, rng):
+    c = rng.integers(0, 256, (n, 4), dtype=np.uint8)
+    c[:, 3] = 255
+    return c
+
+
+def _compare(gpu_ctx, frames, batch, max_blocks=4096, **cfg):
+    from coxgraph_b200 import Layer, TsdfIntegrator
+    from oracle import oracle_py as orc
+    ocfg, gcfg = util.make_cfgs(**cfg)
+    ol, gl = orc.Layer(0.05), Layer(gpu_ctx, 0.05, max_blocks=max_blocks)
+    for (T, p, c) in frames:
+        ol.integrate(ocfg, T, p, c)
+    integ = TsdfIntegrator(gcfg, gl)
+    if batch:
+        offs = np.cumsum([0] + [len(p) for (_, p, _) in frames]).astype(np.uint64)
+        st = integ.integrateBatch(np.stack([T for (T, _, _) in frames]),
+                                  np.concatenate([p for (_, p, _) in frames]),
+                                  np.concatenate([c for (_, _, c) in frames]), offs)
+    else:
+        for (T, p, c) in frames:
+            st = integ.integratePointCloud(T, p, c)
+    util.compare_layers(gl.download(), ol.download(), "edge case")
+    gl.close()
+    return st
+
+
+def test_one_giant_bundle(gpu_ctx):
+    """6000 points inside one voxel: a single sequential fold of 6000 steps."""
+    rng = np.random.default_rng(3)
+    p = (np.array([0.52, 0.27, 1.51]) + rng.uniform(0, 0.045, (6000, 3))).astype(np.float32)
+    st = _compare(gpu_ctx, [(_pose(), p, _colors(len(p), rng))], batch=False, use_const_weight=0)
+    assert st.rays <= 8
+
+
+@pytest.mark.parametrize("carving", [1, 0])
+def test_thousands_of_updates_per_voxel(gpu_ctx, carving):
+    """300 frames of the same small cluster from the same pose: every voxel on the way gets
+    > 2048 updates (free-space ones near the sensor: the closed form; band ones: ordered replay
+    across sub-blocks), all in one job."""
+    rng = np.random.default_rng(5)
+    base = np.array([0.3, -0.2, 1.4])
+    frames = []
+    for f in range(300):
+        p = (base + rng.uniform(-0.08, 0.08, (40, 3))).astype(np.float32)
+        frames.append((_pose(), p, _colors(len(p), rng)))
+    st = _compare(gpu_ctx, frames, batch=True, voxel_carving_enabled=carving,
+                  default_truncation_distance=0.16)
+    assert st.voxel_updates > (100_000 if carving else 20_000)
+
+
+def test_degenerate_points_and_exact_faces(gpu_ctx):
+    rng = np.random.default_rng(7)
+    grid = np.stack(np.meshgrid(np.arange(-6, 7), np.arange(-6, 7), [20, 30, 40]), -1).reshape(-1, 3)
+    on_faces = (grid * 0.05).astype(np.float32)                  # coordinates exactly k * 0.05
+    axis = np.array([[0, 0, 2.0], [0, 1.5, 0], [1.25, 0, 0], [0, 0, -1.0], [-0.75, 0, 0]], np.float32)
+    dup = np.repeat(np.array([[0.4, 0.4, 2.2]], np.float32), 300, axis=0)
+    junk = np.array([[np.nan, 0, 1], [0, np.inf, 1], [0, 0, 0], [0.01, 0.0, 0.02],
+                     [0, 0, 7.5], [3, 4, 50.0], [1e-4, 0, 5.0001]], np.float32)
+    p = np.concatenate([on_faces, axis, dup, junk, rng.normal(0, 1.2, (500, 3)).astype(np.float32)])
+    c = _colors(len(p), rng)
+    T = np.array([1, 0, 0, 0, 0, 0, 0], np.float32)              # origin exactly on a voxel corner
+    for over in (dict(), dict(use_const_weight=0, allow_clear=0), dict(voxel_carving_enabled=0),
+                 dict(method=0)):
+        _compare(gpu_ctx, [(T, p, c)], batch=False, **over)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_clouds_random_poses(gpu_ctx, seed):
+    rng = np.random.default_rng(seed)
+    frames = []
+    for f in range(4):
+        n = int(rng.integers(200, 3000))
+        d = rng.standard_normal((n, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        p = (d * rng.uniform(0.05, 7.0, (n, 1))).astype(np.float32)   # below min_ray .. beyond max_ray
+        frames.append((_pose(rng), p, _colors(n, rng)))
+    _compare(gpu_ctx, frames, batch=bool(seed & 1), use_const_weight=int(seed % 3 == 0),
+             max_weight=50.0 if seed == 13 else 10000.0)
