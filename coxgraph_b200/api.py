@@ -252,6 +252,38 @@ TsdfIntegrator.stageBatch = _stage_batch
 TsdfIntegrator.integrateStaged = _integrate_staged
 
 
+def meshToFrames(ctx, mesh, interpolate_voxel_size, poses, stamps_sec):
+    """voxblox::MeshConverter (coxgraph/include/coxgraph/map_comm/mesh_converter.h):
+    convertToPointCloud + getNextPointcloud for every trajectory pose.
+    -> (frame_offsets u64 [F+1], points_C f32 [N,3], colors u8 [N,4])."""
+    lib = capi.load()
+    m, keep = capi.make_mesh(mesh)
+    P = np.ascontiguousarray(poses, np.float32).reshape(-1, 7)
+    st = np.ascontiguousarray(stamps_sec, np.float64).reshape(-1)
+    offs = np.zeros(len(P) + 1, np.uint64)
+    capi.check(lib.cg_mesh_to_frames(ctx._h, C.byref(m), float(interpolate_voxel_size), len(P),
+                                     _ptr(P), _ptr(st), _ptr(offs), None, None, 0))
+    n = int(offs[-1])
+    pts, cols = np.zeros((n, 3), np.float32), np.zeros((n, 4), np.uint8)
+    if n:
+        capi.check(lib.cg_mesh_to_frames(ctx._h, C.byref(m), float(interpolate_voxel_size), len(P),
+                                         _ptr(P), _ptr(st), _ptr(offs), _ptr(pts), _ptr(cols), n))
+    return offs, pts, cols
+
+
+def recoverMesh(layer, config, mesh, interpolate_voxel_size, poses, stamps_sec):
+    """TsdfRecover::processMesh (coxgraph/include/coxgraph/map_comm/tsdf_recover.h:59-99) on the
+    device: clear the layer, mesh -> per-pose clouds, integrate them.  Returns IntegrateStats."""
+    m, keep = capi.make_mesh(mesh)
+    P = np.ascontiguousarray(poses, np.float32).reshape(-1, 7)
+    st = np.ascontiguousarray(stamps_sec, np.float64).reshape(-1)
+    stats = capi.IntegrateStats()
+    capi.check(capi.load().cg_recover_mesh(layer._h, C.byref(config), C.byref(m),
+                                           float(interpolate_voxel_size), len(P), _ptr(P), _ptr(st),
+                                           C.byref(stats)))
+    return stats
+
+
 def mergeLayerAintoLayerB(layer_A, T_B_A, layer_B):
     """voxblox::mergeLayerAintoLayerB(layer_A, T_B_A, &layer_B); returns MergeStats."""
     T = np.ascontiguousarray(T_B_A, np.float32).reshape(7)

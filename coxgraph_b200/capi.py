@@ -52,6 +52,35 @@ class IntegrateStats(C.Structure):
                 ("general_updates", C.c_uint64), ("blocks_touched", C.c_uint64), ("blocks_allocated", C.c_uint64)]
 
 
+class Mesh(C.Structure):
+    """cg_mesh: voxblox_msgs/Mesh (with observation history) flattened into plain arrays."""
+
+    _fields_ = [("num_blocks", C.c_size_t), ("block_index", C.c_void_p),
+                ("block_has_history", C.c_void_p), ("vertex_begin", C.c_void_p),
+                ("x", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p),
+                ("r", C.c_void_p), ("g", C.c_void_p), ("b", C.c_void_p),
+                ("hist_begin", C.c_void_p), ("hist", C.c_void_p),
+                ("block_edge_length", C.c_float)]
+
+
+def make_mesh(mesh):
+    """dict of numpy arrays -> (Mesh struct, keep-alive list).  Keys: block_index [B,3] i32,
+    block_has_history [B] u8, vertex_begin [B+1] u32, x/y/z [V] u16, r/g/b [V] u8,
+    hist_begin [V/3+1] u32, hist [H] u32, block_edge_length."""
+    import numpy as np
+    spec = [("block_index", np.int32), ("block_has_history", np.uint8), ("vertex_begin", np.uint32),
+            ("x", np.uint16), ("y", np.uint16), ("z", np.uint16), ("r", np.uint8), ("g", np.uint8),
+            ("b", np.uint8), ("hist_begin", np.uint32), ("hist", np.uint32)]
+    keep, m = [], Mesh()
+    for name, dt in spec:
+        a = np.ascontiguousarray(mesh[name], dt)
+        keep.append(a)
+        setattr(m, name, a.ctypes.data)
+    m.num_blocks = len(keep[1])
+    m.block_edge_length = float(mesh["block_edge_length"])
+    return m, keep
+
+
 class StageProfile(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("ms", C.c_double), ("launches", C.c_uint64)]
 
@@ -97,6 +126,10 @@ SYMBOLS = {
     "cg_stage_batch_async": (C.c_int32, [_P, C.c_int32, _P, _P, C.c_size_t]),
     "cg_integrate_batch_staged": (C.c_int32, [_P, C.POINTER(IntegratorConfig), C.c_size_t, _P,
                                               C.c_int32, _P, C.c_int32, C.POINTER(IntegrateStats)]),
+    "cg_mesh_to_frames": (C.c_int32, [_P, C.POINTER(Mesh), C.c_float, C.c_size_t, _P, _P, _P, _P, _P,
+                                      C.c_size_t]),
+    "cg_recover_mesh": (C.c_int32, [_P, C.POINTER(IntegratorConfig), C.POINTER(Mesh), C.c_float,
+                                    C.c_size_t, _P, _P, C.POINTER(IntegrateStats)]),
     "cg_merge_layer_into_layer": (C.c_int32, [_P, _P, _P, C.POINTER(MergeStats)]),
     "cg_project_submaps": (C.c_int32, [_P, _P, C.c_size_t, _P, C.POINTER(MergeStats)]),
     "cg_block_owner": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

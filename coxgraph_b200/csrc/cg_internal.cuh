@@ -240,6 +240,9 @@ struct cg_context {
   // merge / transfer scratch
   cg::DevBuf cand_keys, cand_list, stage_a, stage_b, stage_c;
   cg::DevBuf batch_desc, merge_temp, merge_flags;  // batched projection (merge.cu)
+  // mesh recovery (mesh_recover.cu)
+  cg::DevBuf mesh_in, mesh_tri, mesh_pairs, mesh_pts_g, mesh_cols_g, mesh_pts_c, mesh_cols_c,
+      mesh_frames;
   // instrumentation
   bool profiling = false;
   uint64_t own_launches = 0;  // kernels of this library launched (library sorts/scans excluded)

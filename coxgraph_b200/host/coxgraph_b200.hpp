@@ -260,6 +260,21 @@ struct TsdfIntegratorFactory {
   }
 };
 
+// ---- TsdfRecover::processMesh (coxgraph/include/coxgraph/map_comm/tsdf_recover.h:59-99): mesh
+// with observation history -> per-pose clouds (voxblox::MeshConverter) -> fused layer ----------
+inline void recoverMesh(TsdfLayer* layer, const TsdfIntegratorBase::Config& config,
+                        const cg_mesh& mesh, FloatingPoint interpolate_voxel_size,
+                        const std::vector<Transformation>& T_G_C, const std::vector<double>& stamps_sec,
+                        cg_integrate_stats* stats = nullptr) {
+  if (T_G_C.size() != stamps_sec.size())
+    fatal_handler()(CG_ERR_INVALID_ARG, "recoverMesh: one time stamp per pose expected");
+  std::vector<float> poses(7 * T_G_C.size());
+  for (size_t i = 0; i < T_G_C.size(); ++i)
+    std::copy(T_G_C[i].data(), T_G_C[i].data() + 7, poses.begin() + 7 * i);
+  check(cg_recover_mesh(layer->handle(), &config, &mesh, interpolate_voxel_size, T_G_C.size(),
+                        poses.data(), stamps_sec.data(), stats));
+}
+
 // ---- voxblox::mergeLayerAintoLayerB(layer_A, T_B_A, layer_B) ---------------------------
 inline void mergeLayerAintoLayerB(const TsdfLayer& layer_A, const Transformation& T_B_A,
                                   TsdfLayer* layer_B, cg_merge_stats* stats = nullptr) {

@@ -204,6 +204,41 @@ int32_t cg_integrate_batch_staged(cg_layer* layer, const cg_integrator_config* c
                                   const uint64_t* frame_offsets, int32_t freespace_points,
                                   cg_integrate_stats* stats);
 
+/* --- mesh recovery: the recover node's front end ----------------------
+ * voxblox_msgs/Mesh (the fork's "mesh with observation history") flattened into plain arrays:
+ * block b owns vertices [vertex_begin[b], vertex_begin[b+1]) (triangles: multiples of 3), x/y/z
+ * are the uint16 vertex offsets inside the block, r/g/b the vertex colours; triangle t (= vertex
+ * index / 3) owns the entries [hist_begin[t], hist_begin[t+1]) of `hist`, read as (first stamp,
+ * last stamp) pairs (voxblox_msgs/ObsHistory); block_has_history[b] = 0 means MeshBlock.history
+ * was empty (the block is skipped, mesh_converter.h:87).  All pointers are host pointers. */
+typedef struct cg_mesh {
+  size_t num_blocks;
+  const int32_t* block_index;        /* [B*3]  MeshBlock.index */
+  const uint8_t* block_has_history;  /* [B] */
+  const uint32_t* vertex_begin;      /* [B+1] */
+  const uint16_t *x, *y, *z;         /* [V]    MeshBlock.x / y / z */
+  const uint8_t *r, *g, *b;          /* [V]    MeshBlock.r / g / b */
+  const uint32_t* hist_begin;        /* [V/3 + 1] */
+  const uint32_t* hist;              /* (first, last) stamp pairs */
+  float block_edge_length;           /* Mesh.block_edge_length */
+} cg_mesh;
+/* voxblox::MeshConverter::convertToPointCloud followed by getNextPointcloud for every trajectory
+ * pose (coxgraph/include/coxgraph/map_comm/mesh_converter.h:74-172, :186-209, :211-265): the
+ * point clouds, in the sensor frame, that TsdfRecover::processMesh integrates.  poses: F x 7,
+ * stamps_sec: the trajectory's time stamps.  frame_offsets (F + 1) is always filled; points and
+ * colours only when non-NULL and capacity_points suffices. */
+int32_t cg_mesh_to_frames(cg_context* ctx, const cg_mesh* mesh, float interpolate_voxel_size,
+                          size_t num_poses, const float* T_G_C_poses, const double* stamps_sec,
+                          uint64_t* frame_offsets, float* points_xyz, uint8_t* colors_rgba,
+                          size_t capacity_points);
+/* TsdfRecover::processMesh without the ROS plumbing (coxgraph/include/coxgraph/map_comm/
+ * tsdf_recover.h:59-99): removeAllBlocks, mesh -> per-pose clouds, integratePointCloud for every
+ * pose with a non-empty cloud — all on the device; serialise the result with cg_layer_serialize
+ * (:95). */
+int32_t cg_recover_mesh(cg_layer* layer, const cg_integrator_config* cfg, const cg_mesh* mesh,
+                        float interpolate_voxel_size, size_t num_poses, const float* T_G_C_poses,
+                        const double* stamps_sec, cg_integrate_stats* stats);
+
 /* --- merge: replaces voxblox::mergeLayerAintoLayerB(layer_A, T_B_A, layer_B) — called at
  * coxgraph/src/client/map_server.cpp:67-69 — and cblox SubmapCollection::getProjectedMap(),
  * the server's submap-to-global entry reached from

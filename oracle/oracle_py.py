@@ -80,6 +80,9 @@ def lib():
                                                     C.POINTER(C.c_uint64)]
         L.orc_merge_layer_aligned.restype = C.c_int32
         L.orc_merge_layer_aligned.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_mesh_to_frames.restype = C.c_size_t
+        L.orc_mesh_to_frames.argtypes = [C.c_void_p, C.c_float, C.c_size_t, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_transform_point.argtypes = [C.c_void_p] * 3
         L.orc_inverse_transform.argtypes = [C.c_void_p] * 2
         L.orc_cast_ray.restype = C.c_size_t
@@ -215,3 +218,38 @@ def cast_ray(origin, point_G, clearing, carving, max_ray, voxel_size_inv, trunc,
                            int(carving), float(max_ray), float(voxel_size_inv), float(trunc),
                            int(cast_from_origin), _ptr(out), cap)
     return out[: min(n, cap)].copy()
+
+
+class _Mesh(C.Structure):  # orc_mesh
+    _fields_ = [("num_blocks", C.c_size_t), ("block_index", C.c_void_p),
+                ("block_has_history", C.c_void_p), ("vertex_begin", C.c_void_p),
+                ("x", C.c_void_p), ("y", C.c_void_p), ("z", C.c_void_p),
+                ("r", C.c_void_p), ("g", C.c_void_p), ("b", C.c_void_p),
+                ("hist_begin", C.c_void_p), ("hist", C.c_void_p),
+                ("block_edge_length", C.c_float)]
+
+
+def mesh_to_frames(mesh, interpolate_voxel_size, poses, stamps_sec):
+    """MeshConverter::convertToPointCloud + getNextPointcloud per pose (mesh_converter.h:74-209).
+    mesh: dict of numpy arrays (see coxgraph_b200.capi.make_mesh for the keys).
+    -> (frame_offsets u64 [F+1], points_C f32 [N,3], colors u8 [N,4])."""
+    spec = [("block_index", np.int32), ("block_has_history", np.uint8), ("vertex_begin", np.uint32),
+            ("x", np.uint16), ("y", np.uint16), ("z", np.uint16), ("r", np.uint8), ("g", np.uint8),
+            ("b", np.uint8), ("hist_begin", np.uint32), ("hist", np.uint32)]
+    keep, m = [], _Mesh()
+    for name, dt in spec:
+        a = np.ascontiguousarray(mesh[name], dt)
+        keep.append(a)
+        setattr(m, name, a.ctypes.data)
+    m.num_blocks = len(keep[1])
+    m.block_edge_length = float(mesh["block_edge_length"])
+    P = np.ascontiguousarray(poses, np.float32).reshape(-1, 7)
+    st = np.ascontiguousarray(stamps_sec, np.float64).reshape(-1)
+    offs = np.zeros(len(P) + 1, np.uint64)
+    n = lib().orc_mesh_to_frames(C.byref(m), float(interpolate_voxel_size), len(P), P.ctypes.data,
+                                 st.ctypes.data, offs.ctypes.data, None, None, 0)
+    pts, cols = np.zeros((n, 3), np.float32), np.zeros((n, 4), np.uint8)
+    if n:
+        lib().orc_mesh_to_frames(C.byref(m), float(interpolate_voxel_size), len(P), P.ctypes.data,
+                                 st.ctypes.data, offs.ctypes.data, pts.ctypes.data, cols.ctypes.data, n)
+    return offs, pts, cols

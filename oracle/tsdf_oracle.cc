@@ -22,6 +22,7 @@
 #include <thread>
 #include <unordered_map>
 #include <unordered_set>
+#include <limits>
 #include <vector>
 
 namespace {
@@ -1065,6 +1066,121 @@ int32_t orc_interp_voxel(const orc_layer* l, const float pos[3], int32_t interpo
     rgba[3] = v.color.a;
   }
   return ok ? 1 : 0;
+}
+
+}  // extern "C"
+
+// ================================================================== MeshConverter (in-repo code)
+// Unlike the voxblox arithmetic above, this part of the path IS in the reference tree:
+// coxgraph/include/coxgraph/map_comm/mesh_converter.h.  The restatement follows it line by line,
+// including its quirks (edge p0-p2 blends colors[0] with colors[1], :235-236; the observation
+// map is keyed by uint8_t, :274).
+namespace {
+
+// MeshConverter::interpolateTriangle — mesh_converter.h:211-265
+void interpolate_triangle(const V3 tri[3], const Color col[3], float voxel_size,
+                          std::vector<V3>* out_pts, std::vector<Color>* out_cols) {
+  const V3 p0 = tri[0], p1 = tri[1], p2 = tri[2];
+  const V3 t01 = p1 - p0, t02 = p2 - p0, t12 = p2 - p1;
+  std::vector<V3> e01, e02, e12;
+  std::vector<Color> c01, c02, c12;
+  for (float dist = voxel_size; dist < norm(t01); dist += voxel_size) {  // :224-230
+    e01.push_back(p0 + (t01 / norm(t01)) * dist);
+    c01.push_back(blend(col[0], 1 - dist / norm(t01), col[1], dist / norm(t01)));
+  }
+  for (float dist = voxel_size; dist < norm(t02); dist += voxel_size) {  // :231-237 (colors[1]: sic)
+    e02.push_back(p0 + (t02 / norm(t02)) * dist);
+    c02.push_back(blend(col[0], 1 - dist / norm(t02), col[1], dist / norm(t02)));
+  }
+  for (float dist = voxel_size; dist < norm(t12); dist += voxel_size) {  // :238-244
+    e12.push_back(p1 + (t12 / norm(t12)) * dist);
+    c12.push_back(blend(col[1], 1 - dist / norm(t12), col[2], dist / norm(t12)));
+  }
+  e01.push_back(((p0 + p1) + p2) / 3.0f);  // :246
+  c01.push_back(blend(col[2], static_cast<float>(1 / 3.0), blend(col[0], 0.5f, col[1], 0.5f),
+                      static_cast<float>(2 / 3.0)));  // :247-249
+  out_pts->clear();
+  out_cols->clear();
+  for (const auto* v : {&e01, &e02, &e12}) out_pts->insert(out_pts->end(), v->begin(), v->end());
+  for (const auto* v : {&c01, &c02, &c12}) out_cols->insert(out_cols->end(), v->begin(), v->end());
+}
+
+}  // namespace
+
+extern "C" {
+
+// MeshConverter::convertToPointCloud (mesh_converter.h:74-172) followed, for every trajectory
+// pose, by getNextPointcloud (:186-209): the per-frame clouds TsdfRecover::processMesh
+// (tsdf_recover.h:59-99) hands to integratePointCloud.  Returns the total number of points;
+// points / colours are written only if capacity_points is large enough.
+size_t orc_mesh_to_frames(const orc_mesh* m, float interp_voxel_size, size_t F, const float* poses,
+                          const double* stamps, uint64_t* frame_offsets, float* pts_out,
+                          uint8_t* cols_out, size_t capacity_points) {
+  std::vector<std::vector<V3>> bucket_pts(256);
+  std::vector<std::vector<Color>> bucket_cols(256);
+  for (size_t b = 0; b < m->num_blocks; ++b) {
+    if (!m->block_has_history[b]) continue;  // :87
+    const int32_t* index = m->block_index + 3 * b;
+    V3 tri[3];
+    Color col[3];
+    int nt = 0;
+    for (uint32_t i = m->vertex_begin[b]; i < m->vertex_begin[b + 1]; ++i) {
+      constexpr float point_conv_factor = 2.0f / std::numeric_limits<uint16_t>::max();  // :97-98
+      const float mx = (static_cast<float>(m->x[i]) * point_conv_factor +
+                        static_cast<float>(index[0])) * m->block_edge_length;
+      const float my = (static_cast<float>(m->y[i]) * point_conv_factor +
+                        static_cast<float>(index[1])) * m->block_edge_length;
+      const float mz = (static_cast<float>(m->z[i]) * point_conv_factor +
+                        static_cast<float>(index[2])) * m->block_edge_length;
+      tri[nt] = V3{mx, my, mz};
+      col[nt] = Color{m->r[i], m->g[i], m->b[i], 255};  // Color(r, g, b): alpha 255
+      if (++nt < 3) continue;
+      nt = 0;
+      std::vector<V3> ipts;
+      std::vector<Color> icols;
+      interpolate_triangle(tri, col, interp_voxel_size, &ipts, &icols);  // :133-135
+      const uint32_t t = i / 3;  // history of the triangle: the one of its last vertex (:112)
+      for (uint32_t h = m->hist_begin[t]; h + 1 < m->hist_begin[t + 1]; h += 2)  // :138-142
+        for (size_t j = m->hist[h]; j <= m->hist[h + 1]; ++j) {
+          const uint8_t key = static_cast<uint8_t>(j);  // std::map<uint8_t, ...>, :274
+          auto& bp = bucket_pts[key];
+          auto& bc = bucket_cols[key];
+          bp.insert(bp.end(), tri, tri + 3);  // :148-160
+          bp.insert(bp.end(), ipts.begin(), ipts.end());
+          bc.insert(bc.end(), col, col + 3);
+          bc.insert(bc.end(), icols.begin(), icols.end());
+        }
+    }
+  }
+  size_t total = 0;
+  std::vector<int> frame_bucket(F);
+  for (size_t i = 0; i < F; ++i) {  // getNextPointcloud, :195-200
+    const double id = stamps[i] == stamps[0] ? 0 : std::round((stamps[i] - stamps[0]) / 0.05);
+    frame_bucket[i] = static_cast<uint8_t>(static_cast<long long>(id));
+    if (frame_offsets) frame_offsets[i] = total;
+    total += bucket_pts[frame_bucket[i]].size();
+  }
+  if (frame_offsets) frame_offsets[F] = total;
+  if (!pts_out || !cols_out || capacity_points < total) return total;
+  size_t o = 0;
+  for (size_t i = 0; i < F; ++i) {
+    // T_Submap_C = T_odom_submap_.inverse() * T_G_C with T_odom_submap_ = identity (:50,:202),
+    // exact; the cloud is moved into the sensor frame with its inverse (:203-204)
+    const Xform Ti = inverse(load_xform(poses + 7 * i));
+    const auto& bp = bucket_pts[frame_bucket[i]];
+    const auto& bc = bucket_cols[frame_bucket[i]];
+    for (size_t k = 0; k < bp.size(); ++k, ++o) {
+      const V3 pc = apply(Ti, bp[k]);
+      pts_out[3 * o] = pc.x;
+      pts_out[3 * o + 1] = pc.y;
+      pts_out[3 * o + 2] = pc.z;
+      cols_out[4 * o] = bc[k].r;
+      cols_out[4 * o + 1] = bc[k].g;
+      cols_out[4 * o + 2] = bc[k].b;
+      cols_out[4 * o + 3] = bc[k].a;
+    }
+  }
+  return total;
 }
 
 }  // extern "C"

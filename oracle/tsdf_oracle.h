@@ -104,6 +104,28 @@ size_t orc_cast_ray(const float origin[3], const float point_G[3], int32_t clear
 int32_t orc_interp_voxel(const orc_layer* layer, const float pos[3], int32_t interpolate,
                          float* distance, float* weight, uint8_t rgba[4]);
 
+/* ---- MeshConverter (coxgraph/include/coxgraph/map_comm/mesh_converter.h, IN the reference tree:
+ * this part of the oracle is pinned to the reference's own source lines).
+ * voxblox_msgs/Mesh flattened: block b owns vertices [vertex_begin[b], vertex_begin[b+1]) (a
+ * multiple of 3 each: triangles), x/y/z are the uint16 offsets inside the block, r/g/b the vertex
+ * colours; triangle t (= vertex index / 3) owns the history entries [hist_begin[t],
+ * hist_begin[t+1]) of `hist`, read as (first stamp, last stamp) pairs; block_has_history[b] = 0
+ * means MeshBlock.history was empty (the block is skipped, mesh_converter.h:87). */
+typedef struct orc_mesh {
+  size_t num_blocks;
+  const int32_t* block_index;
+  const uint8_t* block_has_history;
+  const uint32_t* vertex_begin;
+  const uint16_t *x, *y, *z;
+  const uint8_t *r, *g, *b;
+  const uint32_t* hist_begin;
+  const uint32_t* hist;
+  float block_edge_length;
+} orc_mesh;
+size_t orc_mesh_to_frames(const orc_mesh* mesh, float interpolate_voxel_size, size_t num_poses,
+                          const float* poses, const double* stamps_sec, uint64_t* frame_offsets,
+                          float* points_xyz, uint8_t* colors_rgba, size_t capacity_points);
+
 #ifdef __cplusplus
 }
 #endif
