@@ -17,6 +17,9 @@
  *   coxgraph/src/server/visualizer/server_visualizer.cpp:123-126 (getProjectedMap)
  * It is pinned by analytic / algebraic known-answer tests (tests/test_oracle_*.py)
  * and by frozen digests under tests/golden/.
+ * One part IS pinned to reference source: the MeshConverter section (orc_mesh_to_frames) restates
+ * coxgraph/include/coxgraph/map_comm/mesh_converter.h, which is in the reference tree, line by
+ * line (tests/test_mesh_recover.py checks it against hand-evaluated values of those formulas).
  */
 #ifndef TSDF_ORACLE_H_
 #define TSDF_ORACLE_H_
