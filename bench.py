@@ -370,6 +370,30 @@ def run_ours(args, rank, world, local_rank):
                    "global_blocks": big.num_blocks,
                    "hbm_frac": BLOCK_BYTES * (st.blocks_in + 2 * st.blocks_out) / (ms * 1e-3) / 1e9 /
                    measured_peak_gbs()[0]}
+        if world > 1:
+            # the server's global merge over all ranks: every rank projects its submaps into a
+            # partial layer, one NCCL all-to-all moves the partial blocks to their owners, the
+            # owners fold them (coxgraph_b200/sharding.py); timed on the device, max over ranks
+            from coxgraph_b200 import sharding
+            partial = Layer(ctx, VOXEL_SIZE, max_blocks=65536)
+            owned = Layer(ctx, VOXEL_SIZE, max_blocks=65536)
+            times = []
+            for it in range(4):
+                owned.clear()
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                sent, got = sharding.project_sharded(subs, T_all, partial, owned)
+                b.record(stream)
+                barrier()
+                times.append(max_over_ranks(a.elapsed_time(b)))
+            ms_sh = min(times[1:])
+            project["sharded"] = {"value": vox / (ms_sh * 1e-3), "unit": "voxels/s", "ms": ms_sh,
+                                  "submaps_total": args.project_submaps * world,
+                                  "blocks_sent": int(sum_over_ranks(float(sum(sent)))),
+                                  "collective": "nccl all_to_all_single"}
+            partial.close()
+            owned.close()
         for L in subs:
             L.close()
         big.close()
