@@ -1031,7 +1031,7 @@ __global__ void __launch_bounds__(kAccThreads)
 k_block_accumulate(IntegratorParams P, const Ray* __restrict__ rays,
                    const uint32_t* __restrict__ seg_keys, const uint32_t* __restrict__ seg_idx,
                    const uint4* __restrict__ seg_recs, uint32_t num_slots_host,
-                   const uint32_t* __restrict__ num_slots_dev, uint32_t null_key, TouchView Tv,
+                   const uint32_t* __restrict__ bin_base, uint32_t null_key, TouchView Tv,
                    float acc_scale, uint32_t ray_bits,
                    unsigned long long* __restrict__ out, uint32_t* out_count, uint32_t out_cap,
                    uint32_t* work_counter) {
@@ -1047,8 +1047,9 @@ k_block_accumulate(IntegratorParams P, const Ray* __restrict__ rays,
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  // counting-sort path: the number of real segments is only known on the device
-  const uint32_t num_slots = num_slots_dev ? *num_slots_dev : num_slots_host;
+  // counting-sort path: bin_base[o] = first sorted segment of block ordinal o, bin_base[null_key]
+  // = number of real segments (only known on the device)
+  const uint32_t num_slots = bin_base ? bin_base[null_key] : num_slots_host;
   uint32_t cnt = 0;
   auto flush = [&]() {
     __syncwarp();
@@ -1072,9 +1073,13 @@ k_block_accumulate(IntegratorParams P, const Ray* __restrict__ rays,
       const uint32_t o = seg_keys[pos];
       if (o >= null_key) break;  // unused slots are sorted last
       uint32_t lo = pos, hi = c_hi;  // end of this block's run inside the chunk
-      while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (seg_keys[mid] == o) lo = mid; else hi = mid;
+      if (bin_base) {
+        hi = min(c_hi, bin_base[o + 1]);
+      } else {
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (seg_keys[mid] == o) lo = mid; else hi = mid;
+        }
       }
       const bool use_tile = hi - pos >= kTileMinRun;
       if (use_tile)
@@ -1774,7 +1779,7 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
                                               cursor, sk.Alternate(), sv.Alternate());
       sorted_keys = sk.Alternate();
       sorted_idx = sv.Alternate();
-      num_real = bin_base + null_key;  // total number of real segments
+      num_real = bin_base;  // run boundaries; [null_key] = total number of real segments
     } else {
       StageScope sc(ctx, kStageSegmentSort, 0);
       CG_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp_seg, sk, sv,
