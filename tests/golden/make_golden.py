@@ -79,9 +79,21 @@ def build_case(name, spec):
     return meta
 
 
+def build_mesh_case():
+    """MeshConverter fixture: the synthetic mesh / trajectory of tests/test_mesh_recover.py (seeded
+    numpy generators) and the digest of the per-pose clouds the oracle recovers from it."""
+    from tests.test_mesh_recover import make_mesh, make_trajectory
+    mesh = make_mesh(seed=0, blocks=9, tris_per_block=60)
+    poses, stamps = make_trajectory(12, 0)
+    offs, pts, cols = orc.mesh_to_frames(mesh, 0.05, poses, stamps)
+    return dict(num_points=int(len(pts)), offsets_sha256=digest(offs), points_sha256=digest(pts),
+                colors_sha256=digest(cols))
+
+
 if __name__ == "__main__":
     metas = {name: build_case(name, spec) for name, spec in CASES.items()}
+    metas["mesh_frames"] = build_mesh_case()
     with open(os.path.join(HERE, "digests.json"), "w") as f:
         json.dump(metas, f, indent=1, sort_keys=True)
     for k, v in metas.items():
-        print(k, v["num_blocks"], v["sha256"][:16])
+        print(k, v.get("num_blocks", v.get("num_points")), v.get("sha256", v.get("points_sha256"))[:16])

@@ -175,3 +175,30 @@ def test_block_pool_beyond_4_gib(gpu_ctx):
     util.compare_layers(gg.download(), og.download(), "merge after the big layer")
     for L in (gl, gg, small):
         L.close()
+
+
+def test_results_are_run_to_run_deterministic(gpu_ctx):
+    """north_star: "updates stay deterministic".  The same job twice (full frames, 1/z^2 weights so
+    that the weight sums are not integers) gives bit-identical layers, and so does the batched
+    projection: the free-space sums are integer (fixed point), the ordered lists are sorted on
+    their full key, the folds run in submap order."""
+    import torch
+    from coxgraph_b200 import (Layer, TsdfIntegrator, TsdfIntegratorConfig, getProjectedMap, synth)
+    dev = torch.device("cuda", 0)
+    cfg = TsdfIntegratorConfig(use_const_weight=0, method=1, default_truncation_distance=0.16)
+    poses, pts, cols, offs = _device_frames(0, 3, 5, synth.CAM_640x480, dev)
+    layers = []
+    for rep in range(2):
+        L = Layer(gpu_ctx, 0.05, max_blocks=8192)
+        TsdfIntegrator(cfg, L).integrateBatch(poses, pts, cols, offs)
+        layers.append(L)
+    util.compare_layers(layers[0].download(), layers[1].download(), "same job twice", exact=True)
+    T = np.stack([synth.robot_map_offset(1), synth.robot_map_offset(0)])
+    globs = []
+    for rep in range(2):
+        G = Layer(gpu_ctx, 0.05, max_blocks=16384)
+        getProjectedMap(layers, T, G)
+        globs.append(G)
+    util.compare_layers(globs[0].download(), globs[1].download(), "same projection twice", exact=True)
+    for L in layers + globs:
+        L.close()

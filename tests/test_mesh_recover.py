@@ -95,6 +95,37 @@ def test_oracle_buckets_by_uint8_stamp_and_pose_time():
     assert (sizes > 0).all()
 
 
+def _frozen():
+    import hashlib
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "digests.json")
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()  # noqa: E731
+    return json.load(open(here))["mesh_frames"], sha
+
+
+def test_oracle_reproduces_frozen_mesh_frames():
+    from oracle import oracle_py as orc
+    want, sha = _frozen()
+    poses, stamps = make_trajectory(12, 0)
+    offs, pts, cols = orc.mesh_to_frames(make_mesh(seed=0, blocks=9, tris_per_block=60), 0.05, poses,
+                                         stamps)
+    assert len(pts) == want["num_points"]
+    assert (sha(offs), sha(pts), sha(cols)) == (want["offsets_sha256"], want["points_sha256"],
+                                               want["colors_sha256"])
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_frozen_mesh_frames(gpu_ctx):
+    from coxgraph_b200 import meshToFrames
+    want, sha = _frozen()
+    poses, stamps = make_trajectory(12, 0)
+    offs, pts, cols = meshToFrames(gpu_ctx, make_mesh(seed=0, blocks=9, tris_per_block=60), 0.05,
+                                   poses, stamps)
+    assert (sha(offs), sha(pts), sha(cols)) == (want["offsets_sha256"], want["points_sha256"],
+                                               want["colors_sha256"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed,vs", [(0, 0.05), (3, 0.02), (5, 0.2)])
 def test_cuda_mesh_to_frames_is_bit_exact(gpu_ctx, seed, vs):
