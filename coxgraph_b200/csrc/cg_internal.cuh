@@ -239,7 +239,7 @@ struct cg_context {
   uint32_t* d_work_counter = nullptr;  // dynamic work distribution of the persistent kernels
   // merge / transfer scratch
   cg::DevBuf cand_keys, cand_list, stage_a, stage_b, stage_c;
-  cg::DevBuf batch_desc, merge_temp, merge_flags;  // batched projection (merge.cu)
+  cg::DevBuf batch_desc, merge_cands;  // batched projection (merge.cu)
   // mesh recovery (mesh_recover.cu)
   cg::DevBuf mesh_in, mesh_tri, mesh_pairs, mesh_pts_g, mesh_cols_g, mesh_pts_c, mesh_cols_c,
       mesh_frames;

@@ -324,7 +324,7 @@ int32_t cg_context_destroy(cg_context* ctx) {
                     &ctx->key_b, &ctx->val_a, &ctx->val_b, &ctx->flags, &ctx->scan,
                     &ctx->cub_tmp, &ctx->rays, &ctx->ray_count, &ctx->ray_offset, &ctx->sorted_pts, &ctx->pkey_a,
                     &ctx->pkey_b, &ctx->seg_keys_a, &ctx->seg_keys_b, &ctx->seg_idx_a, &ctx->seg_idx_b, &ctx->seg_recs, &ctx->seg_order, &ctx->scan_partials, &ctx->seg_bins, &ctx->grazing_keys, &ctx->grazing_ray_key, &ctx->touch_ord, &ctx->touch_entry, &ctx->touch_acc, &ctx->touch_bits, &ctx->seg_start, &ctx->long_list, &ctx->long_partials, &ctx->cand_keys, &ctx->cand_list,
-                    &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->batch_desc, &ctx->merge_temp, &ctx->merge_flags, &ctx->mesh_in, &ctx->mesh_tri,
+                    &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->batch_desc, &ctx->merge_cands, &ctx->mesh_in, &ctx->mesh_tri,
                     &ctx->mesh_pairs, &ctx->mesh_pts_g, &ctx->mesh_cols_g, &ctx->mesh_pts_c,
                     &ctx->mesh_cols_c, &ctx->mesh_frames};
   for (DevBuf* b : bufs) b->release();

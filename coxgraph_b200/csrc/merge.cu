@@ -19,16 +19,11 @@
 #include <vector>
 
 #include <algorithm>
+#include <cmath>
 
 #include "cg_internal.cuh"
 
 namespace cg {
-
-static size_t env_size_merge(const char* name, size_t dflt) {
-  const char* v = getenv(name);
-  if (!v || !*v) return dflt;
-  return static_cast<size_t>(strtoull(v, nullptr, 10));
-}
 
 constexpr int kTab = 4;  // cached neighbourhood of source block slots: kTab^3
 
@@ -356,12 +351,12 @@ static int32_t enqueue_merge(const cg_layer* A, const float T_B_A[7], cg_layer* 
 //                     hash map destination block -> 64-bit mask of the submaps that may reach it
 //   (scan)            candidate (block, submap) pairs numbered by a prefix sum of the mask
 //                     population counts
-//   k_resample_batch  one CTA per candidate: the resampled block (R8 / R9) goes to a temporary
-//                     planar block, with a "has data" flag
-//   k_fold_batch      one CTA per destination block: claims the block iff a candidate carries
-//                     data (bit-exact block set) and folds its candidates in ascending submap
-//                     order (R10) — the order of the reference's loop, so the result is
-//                     bit-identical to merging the submaps one after the other.
+//   k_list_candidates the explicit (destination block, submap, rank) list
+//   k_project_batch   one CTA per candidate: resamples the block (R8 / R9) into shared memory and,
+//                     if it carries data, claims the destination block (bit-exact block set) and
+//                     folds it in (R10) when its turn comes — candidates of one destination block
+//                     fold in ascending submap order, the order of the reference's loop, so the
+//                     result is bit-identical to merging the submaps one after the other.
 struct BatchSubmap {
   LayerView A;
   Xform T_B_A, T_A_B;
@@ -421,59 +416,78 @@ __global__ void k_mask_counts(const unsigned long long* __restrict__ map_mask, u
   if (h < cap) counts[h] = __popcll(map_mask[h]);
 }
 
-// number of candidates = cand_base[cap]; the candidate list is implicit:
-// candidate c belongs to the map entry h with cand_base[h] <= c < cand_base[h + 1] and to the
-// (c - cand_base[h])-th set bit of its mask
+// Explicit candidate list: candidate c = (map entry, submap of the batch, rank among the entry's
+// candidates); c runs over [cand_base[h], cand_base[h + 1]) in ascending submap order.
+struct BatchCand {
+  uint32_t entry;
+  uint32_t sub_rank;  // submap | rank << 8
+};
+__global__ void k_list_candidates(const unsigned long long* __restrict__ map_mask,
+                                  const uint32_t* __restrict__ cand_base, uint32_t cap,
+                                  BatchCand* __restrict__ list, CallCounters* counters) {
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h == 0) atomicAdd(&counters->candidates, 1ull * cand_base[cap]);
+  if (h >= cap) return;
+  unsigned long long m = map_mask[h];
+  uint32_t c = cand_base[h];
+  for (uint32_t k = 0; m; ++k, ++c, m &= m - 1)
+    list[c] = BatchCand{h, static_cast<uint32_t>(__ffsll(static_cast<long long>(m)) - 1) | (k << 8)};
+}
+
+// One CTA per candidate, handed out in ascending order by an atomic counter.  The resampled block
+// (R8 / R9) stays in shared memory; if it carries data the CTA waits until the lower-ranked
+// candidates of the same destination block are done, claims the block (bit-exact block set: only
+// candidates with data claim) and folds its 4096 voxels in (R10).  Ranks follow the submap order,
+// so the result is bit-identical to merging the submaps one after the other, and nothing but the
+// destination block itself (L2-resident) is written.  A waiting CTA only waits on candidates with
+// a smaller number; those were handed out earlier to CTAs that are running, so the smallest
+// unfinished candidate never waits: no deadlock whatever the grid size or residency.
 __global__ void __launch_bounds__(kMergeThreads)
-k_resample_batch(const BatchSubmap* __restrict__ desc, LayerView B,
-                 const uint64_t* __restrict__ map_keys,
-                 const unsigned long long* __restrict__ map_mask,
-                 const uint32_t* __restrict__ cand_base, uint32_t cap, float* __restrict__ temp,
-                 uint8_t* __restrict__ has_flag, uint32_t temp_cap) {
-  __shared__ SlotTable tab;
-  __shared__ uint32_t s_h;
-  __shared__ int s_sub;
+k_project_batch(const BatchSubmap* __restrict__ desc, LayerView B,
+                const uint64_t* __restrict__ map_keys, const BatchCand* __restrict__ list,
+                const uint32_t* __restrict__ cand_base, uint32_t cap, unsigned long long* done,
+                uint32_t* work_counter, CallCounters* counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_d = reinterpret_cast<float*>(smem_raw);  // resampled block, planar
+  float* s_w = s_d + kVoxelsPerBlock;
+  uint32_t* s_c = reinterpret_cast<uint32_t*>(s_w + kVoxelsPerBlock);
+  SlotTable& tab = *reinterpret_cast<SlotTable*>(s_c + kVoxelsPerBlock);
+  __shared__ uint32_t s_cand;
+  __shared__ int s_slot;
   const uint32_t num_cand = cand_base[cap];
-  if (num_cand > temp_cap) return;  // the host sees the count and retries with a smaller batch
-  for (uint32_t c = blockIdx.x; c < num_cand; c += gridDim.x) {
-    __syncthreads();  // previous iteration done with tab / s_h / s_sub
-    if (threadIdx.x == 0) {
-      uint32_t lo = 0, hi = cap;  // last h with cand_base[h] <= c
-      while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (cand_base[mid] <= c) lo = mid; else hi = mid;
-      }
-      unsigned long long m = map_mask[lo];
-      for (uint32_t k = c - cand_base[lo]; k > 0; --k) m &= m - 1;  // drop the k lowest set bits
-      s_h = lo;
-      s_sub = __ffsll(static_cast<long long>(m)) - 1;
-    }
+  for (;;) {
+    __syncthreads();  // previous iteration done with the shared state
+    if (threadIdx.x == 0) s_cand = atomicAdd(work_counter, 1u);
     __syncthreads();
-    const BatchSubmap& d = desc[s_sub];
+    const uint32_t c = s_cand;
+    if (c >= num_cand) break;
+    const BatchCand cd = list[c];
+    const uint32_t rank = cd.sub_rank >> 8;
+    const BatchSubmap& d = desc[cd.sub_rank & 0xFFu];
     const LayerView& A = d.A;
+    const uint64_t key = map_keys[cd.entry];
     int bx, by, bz;
-    unpack_block_key(map_keys[s_h], bx, by, bz);
+    unpack_block_key(key, bx, by, bz);
     const V3 org_out = V3{static_cast<float>(bx) * B.block_size, static_cast<float>(by) * B.block_size,
                           static_cast<float>(bz) * B.block_size};
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < kTab * kTab * kTab) {
       const V3 ctr = V3{center_coord(bx, B.block_size), center_coord(by, B.block_size),
                         center_coord(bz, B.block_size)};
       const V3 pc = apply(d.T_A_B, ctr);
       const float reach = 0.8660254f * B.block_size + A.voxel_size;
-      tab.ax = __float2int_rd((pc.x - reach) * A.block_size_inv);
-      tab.ay = __float2int_rd((pc.y - reach) * A.block_size_inv);
-      tab.az = __float2int_rd((pc.z - reach) * A.block_size_inv);
-    }
-    __syncthreads();
-    if (threadIdx.x < kTab * kTab * kTab) {
+      const int ax = __float2int_rd((pc.x - reach) * A.block_size_inv);
+      const int ay = __float2int_rd((pc.y - reach) * A.block_size_inv);
+      const int az = __float2int_rd((pc.z - reach) * A.block_size_inv);
       const int t = threadIdx.x;
       const int dx = t % kTab, dy = (t / kTab) % kTab, dz = t / (kTab * kTab);
-      tab.slot[t] = A.find_slot(pack_block_key(tab.ax + dx, tab.ay + dy, tab.az + dz));
+      tab.slot[t] = A.find_slot(pack_block_key(ax + dx, ay + dy, az + dz));
+      if (t == 0) {
+        tab.ax = ax;
+        tab.ay = ay;
+        tab.az = az;
+      }
     }
     __syncthreads();
-    float* t_d = temp + static_cast<size_t>(c) * (3 * kVoxelsPerBlock);
-    float* t_w = t_d + kVoxelsPerBlock;
-    uint32_t* t_c = reinterpret_cast<uint32_t*>(t_w + kVoxelsPerBlock);
     bool any = false;
 #pragma unroll 1
     for (int j = 0; j < kVoxPerThread; ++j) {
@@ -485,70 +499,54 @@ k_resample_batch(const BatchSubmap* __restrict__ desc, LayerView B,
       const V3 p = apply(d.T_A_B, center_out);
       VoxelState t;
       any |= resample_voxel(A, tab, p, t);
-      t_d[lin] = t.d;
-      t_w[lin] = t.w;
-      t_c[lin] = t.c;
+      s_d[lin] = t.d;
+      s_w[lin] = t.w;
+      s_c[lin] = t.c;
     }
     const int has_data = __syncthreads_or(any ? 1 : 0);
-    if (threadIdx.x == 0) has_flag[c] = has_data ? 1 : 0;
-  }
-}
-
-__global__ void __launch_bounds__(kMergeThreads)
-k_fold_batch(LayerView B, const uint64_t* __restrict__ map_keys,
-             const unsigned long long* __restrict__ map_mask,
-             const uint32_t* __restrict__ cand_base, uint32_t cap, const float* __restrict__ temp,
-             const uint8_t* __restrict__ has_flag, uint32_t temp_cap, CallCounters* counters) {
-  __shared__ int s_slot;
-  const uint32_t num_cand = cand_base[cap];
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters->candidates, 1ull * num_cand);
-  if (num_cand > temp_cap) return;
-  for (uint32_t h = blockIdx.x; h < cap; h += gridDim.x) {
-    const uint32_t c0 = cand_base[h], c1 = cand_base[h + 1];
-    if (c0 == c1) continue;
-    uint32_t with_data = 0;
-    for (uint32_t c = c0; c < c1; ++c) with_data += has_flag[c];
-    if (!with_data) continue;  // every candidate was dropped from its transformed layer
-    __syncthreads();
+    unsigned long long* turn = done + cd.entry;
+    if (!has_data) {  // dropped from its transformed layer: nothing merged, nobody waits for it
+      if (threadIdx.x == 0) atomicOr(turn, 1ull << rank);
+      continue;
+    }
     if (threadIdx.x == 0) {
-      const int e = B.insert_entry(map_keys[h]);
-      s_slot = B.hash_vals[e];  // written by this thread or by an earlier kernel
-      atomicAdd(&counters->blocks_out, 1ull * with_data);
-      if (s_slot >= 0) {
-        B.has_data[s_slot] = 1;
-        B.updated[s_slot] = 1;
+      const unsigned long long need = (1ull << rank) - 1ull;
+      while ((*reinterpret_cast<volatile unsigned long long*>(turn) & need) != need) __nanosleep(64);
+      __threadfence();  // acquire: the earlier folds (and the block claim) are visible
+      const int e = B.insert_entry(key);
+      const int slot = *reinterpret_cast<volatile int32_t*>(B.hash_vals + e);
+      s_slot = slot;
+      atomicAdd(&counters->blocks_out, 1ull);
+      if (slot >= 0) {
+        B.has_data[slot] = 1;
+        B.updated[slot] = 1;
       }
     }
     __syncthreads();
     const int slot = s_slot;
-    if (slot < 0) continue;
-    float* dp = B.dist_plane(slot);
-    float* wp = B.weight_plane(slot);
-    uint32_t* cp = B.color_plane(slot);
-    VoxelState st[kVoxPerThread];
-#pragma unroll
-    for (int j = 0; j < kVoxPerThread; ++j) {
-      const int lin = threadIdx.x + j * kMergeThreads;
-      st[j] = VoxelState{dp[lin], wp[lin], cp[lin]};
-    }
-    for (uint32_t c = c0; c < c1; ++c) {  // ascending submap order
-      if (!has_flag[c]) continue;
-      const float* t_d = temp + static_cast<size_t>(c) * (3 * kVoxelsPerBlock);
-      const float* t_w = t_d + kVoxelsPerBlock;
-      const uint32_t* t_c = reinterpret_cast<const uint32_t*>(t_w + kVoxelsPerBlock);
+    if (slot >= 0) {
+      // the block may have been written by another SM a moment ago: bypass L1 both ways
+      float* dp = B.dist_plane(slot);
+      float* wp = B.weight_plane(slot);
+      uint32_t* cp = B.color_plane(slot);
+      VoxelState st[kVoxPerThread];
 #pragma unroll
       for (int j = 0; j < kVoxPerThread; ++j) {
         const int lin = threadIdx.x + j * kMergeThreads;
-        merge_voxel(t_d[lin], t_w[lin], t_c[lin], st[j]);
+        st[j] = VoxelState{__ldcg(dp + lin), __ldcg(wp + lin), __ldcg(cp + lin)};
       }
-    }
 #pragma unroll
-    for (int j = 0; j < kVoxPerThread; ++j) {
-      const int lin = threadIdx.x + j * kMergeThreads;
-      dp[lin] = st[j].d;
-      wp[lin] = st[j].w;
-      cp[lin] = st[j].c;
+      for (int j = 0; j < kVoxPerThread; ++j) {
+        const int lin = threadIdx.x + j * kMergeThreads;
+        merge_voxel(s_d[lin], s_w[lin], s_c[lin], st[j]);
+        __stcg(dp + lin, st[j].d);
+        __stcg(wp + lin, st[j].w);
+        __stcg(cp + lin, st[j].c);
+      }
+      __threadfence();  // release: every thread's stores before the turn is passed on
     }
+    __syncthreads();
+    if (threadIdx.x == 0) atomicOr(turn, 1ull << rank);
   }
 }
 
@@ -574,94 +572,70 @@ static Xform inverse_host(const Xform& T) {
   return Ti;
 }
 
-// submaps [i0, i1) as one batch; returns CG_OK with *overflow = true when the batch has more
-// candidates than temp_cap (nothing was merged then)
-static int32_t project_batch(const cg_layer* const* submaps, const float* poses, size_t i0, size_t i1,
-                             cg_layer* G, size_t temp_cap, bool* overflow, cg_merge_stats* stats) {
+// submaps [i0, i1) as one batch (descriptors already on the device); everything is enqueued on the
+// context's stream, nothing is read back
+static int32_t project_batch(const cg_layer* const* submaps, const BatchSubmap* h_desc,
+                             const BatchSubmap* d_desc, size_t i0, size_t i1, cg_layer* G) {
   cg_context* ctx = G->ctx;
   cudaStream_t s = ctx->stream;
   const int n = static_cast<int>(i1 - i0);
-  std::vector<BatchSubmap> h(n);
   uint32_t total = 0;
+  size_t cand_bound = 0;  // transformLayer marks at most this many destination blocks
   for (int k = 0; k < n; ++k) {
     const cg_layer* A = submaps[i0 + k];
-    h[k].A = A->v;
-    h[k].T_B_A = make_xform(poses + 7 * (i0 + k));
-    h[k].T_A_B = inverse_host(h[k].T_B_A);
-    h[k].first_block = total;
-    h[k].num_blocks = static_cast<uint32_t>(A->num_blocks);
-    total += h[k].num_blocks;
+    total += h_desc[i0 + k].num_blocks;
+    const double per_axis = std::floor(1.7320508075688772 * A->v.block_size / G->v.block_size) + 2.0;
+    cand_bound += static_cast<size_t>(h_desc[i0 + k].num_blocks) *
+                  static_cast<size_t>(per_axis * per_axis * per_axis);
   }
-  *overflow = false;
   if (total == 0) return CG_OK;
   size_t cap = 4096;
-  while (cap < 32 * static_cast<size_t>(total)) cap <<= 1;
-  const size_t desc_bytes = n * sizeof(BatchSubmap);
-  if (desc_bytes > ctx->h_tables_cap) {
-    if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
-    ctx->h_tables = nullptr;
-    ctx->h_tables_cap = 0;
-    CG_CUDA(cudaHostAlloc(&ctx->h_tables, desc_bytes * 2, cudaHostAllocMapped));
-    ctx->h_tables_cap = desc_bytes * 2;
-  }
-  memcpy(ctx->h_tables, h.data(), desc_bytes);
-  void* d_alias = nullptr;
-  CG_CUDA(cudaHostGetDevicePointer(&d_alias, ctx->h_tables, 0));
-  CG_CUDA(ctx->batch_desc.reserve(desc_bytes));
+  while (cap < 2 * cand_bound) cap <<= 1;
   CG_CUDA(ctx->cand_keys.reserve(cap * sizeof(uint64_t)));
-  CG_CUDA(ctx->cand_list.reserve(cap * sizeof(unsigned long long)));      // masks
-  CG_CUDA(ctx->stage_b.reserve((cap + 1) * sizeof(uint32_t)));            // counts
+  // masks, then the per-entry "done" masks of the fused fold, then the counts (one memset clears all)
+  CG_CUDA(ctx->cand_list.reserve(2 * cap * sizeof(unsigned long long) + (cap + 1) * sizeof(uint32_t)));
   CG_CUDA(ctx->stage_c.reserve((cap + 1) * sizeof(uint32_t)));            // cand_base
-  CG_CUDA(ctx->merge_temp.reserve(temp_cap * static_cast<size_t>(CG_BLOCK_BYTES)));
-  CG_CUDA(ctx->merge_flags.reserve(temp_cap));
+  CG_CUDA(ctx->merge_cands.reserve(cand_bound * sizeof(BatchCand)));
+  unsigned long long* masks = ctx->cand_list.as<unsigned long long>();
+  unsigned long long* done = masks + cap;
+  uint32_t* counts = reinterpret_cast<uint32_t*>(done + cap);
   size_t tmp_scan = 0;
-  CG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, ctx->stage_b.as<uint32_t>(),
-                                        ctx->stage_c.as<uint32_t>(), static_cast<int>(cap + 1), s));
+  CG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, counts, ctx->stage_c.as<uint32_t>(),
+                                        static_cast<int>(cap + 1), s));
   CG_CUDA(ctx->cub_tmp.reserve(tmp_scan));
-  const BatchSubmap* desc = ctx->batch_desc.as<BatchSubmap>();
   {
-    StageScope sc(ctx, kStageMergeMark, 4);
-    k_copy_desc<<<grid_for(desc_bytes / 4, 256), 256, 0, s>>>(
-        ctx->batch_desc.as<uint32_t>(), static_cast<const uint32_t*>(d_alias), desc_bytes / 4);
+    StageScope sc(ctx, kStageMergeMark, 3);
     CG_CUDA(cudaMemsetAsync(ctx->cand_keys.p, 0xFF, cap * sizeof(uint64_t), s));
-    CG_CUDA(cudaMemsetAsync(ctx->cand_list.p, 0, cap * sizeof(unsigned long long), s));
-    CG_CUDA(cudaMemsetAsync(ctx->stage_b.p, 0, (cap + 1) * sizeof(uint32_t), s));
-    k_reset_merge_counters<<<1, 1, 0, s>>>(ctx->d_counters);
+    CG_CUDA(cudaMemsetAsync(masks, 0, 2 * cap * sizeof(unsigned long long) + (cap + 1) * sizeof(uint32_t), s));
+    CG_CUDA(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(uint32_t), s));
     k_mark_batch<<<grid_for(total, 128), 128, 0, s>>>(
-        desc, n, total, G->v.block_size, ctx->cand_keys.as<uint64_t>(),
-        ctx->cand_list.as<unsigned long long>(), static_cast<uint32_t>(cap - 1), G->v.err);
-    k_mask_counts<<<grid_for(cap, 256), 256, 0, s>>>(ctx->cand_list.as<unsigned long long>(),
-                                                     static_cast<uint32_t>(cap),
-                                                     ctx->stage_b.as<uint32_t>());
-    CG_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_scan, ctx->stage_b.as<uint32_t>(),
-                                          ctx->stage_c.as<uint32_t>(), static_cast<int>(cap + 1),
-                                          s));
+        d_desc + i0, n, total, G->v.block_size, ctx->cand_keys.as<uint64_t>(), masks,
+        static_cast<uint32_t>(cap - 1), G->v.err);
+    k_mask_counts<<<grid_for(cap, 256), 256, 0, s>>>(masks, static_cast<uint32_t>(cap), counts);
+    CG_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_scan, counts,
+                                          ctx->stage_c.as<uint32_t>(), static_cast<int>(cap + 1), s));
+    k_list_candidates<<<grid_for(cap, 256), 256, 0, s>>>(masks, ctx->stage_c.as<uint32_t>(),
+                                                         static_cast<uint32_t>(cap),
+                                                         ctx->merge_cands.as<BatchCand>(),
+                                                         ctx->d_counters);
+  }
+  const size_t smem = 3 * kVoxelsPerBlock * sizeof(float) + sizeof(SlotTable);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CG_CUDA(cudaFuncSetAttribute(k_project_batch, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+    attr_set = true;
   }
   {
-    StageScope sc(ctx, kStageMergeResample, 2);
-    k_resample_batch<<<ctx->num_sms * 6, kMergeThreads, 0, s>>>(
-        desc, G->v, ctx->cand_keys.as<uint64_t>(), ctx->cand_list.as<unsigned long long>(),
-        ctx->stage_c.as<uint32_t>(), static_cast<uint32_t>(cap), ctx->merge_temp.as<float>(),
-        ctx->merge_flags.as<uint8_t>(), static_cast<uint32_t>(temp_cap));
-    k_fold_batch<<<ctx->num_sms * 6, kMergeThreads, 0, s>>>(
-        G->v, ctx->cand_keys.as<uint64_t>(), ctx->cand_list.as<unsigned long long>(),
-        ctx->stage_c.as<uint32_t>(), static_cast<uint32_t>(cap), ctx->merge_temp.as<float>(),
-        ctx->merge_flags.as<uint8_t>(), static_cast<uint32_t>(temp_cap), ctx->d_counters);
+    StageScope sc(ctx, kStageMergeResample, 1);
+    const unsigned grid = static_cast<unsigned>(
+        std::min<size_t>(cand_bound, static_cast<size_t>(ctx->num_sms) * 2));
+    k_project_batch<<<grid, kMergeThreads, smem, s>>>(
+        d_desc + i0, G->v, ctx->cand_keys.as<uint64_t>(), ctx->merge_cands.as<BatchCand>(),
+        ctx->stage_c.as<uint32_t>(), static_cast<uint32_t>(cap), done, ctx->d_work_counter,
+        ctx->d_counters);
   }
   CG_CUDA(cudaGetLastError());
-  // the descriptor staging buffer is reused by the next batch: wait for this one
-  CG_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(CallCounters),
-                          cudaMemcpyDeviceToHost, s));
-  CG_CUDA(cudaStreamSynchronize(s));
-  if (ctx->h_counters->candidates > temp_cap) {
-    *overflow = true;
-    return CG_OK;
-  }
-  if (stats) {
-    stats->blocks_in += total;
-    stats->blocks_candidate += ctx->h_counters->candidates;
-    stats->blocks_out += ctx->h_counters->blocks_out;
-  }
   return CG_OK;
 }
 
@@ -703,38 +677,52 @@ int32_t cg_project_submaps(const cg_layer* const* submaps, const float* poses, s
       return CG_ERR_INVALID_ARG;
     }
   }
-  // temporary resampled blocks per batch (48 KB each)
-  size_t temp_cap = env_size_merge("CG_MERGE_TEMP_BLOCKS", 8192);
-  size_t i0 = 0;
-  size_t want = kBatchMax;
-  while (i0 < n) {
-    // a batch: up to 64 submaps whose candidate count is expected to fit (about 2 destination
-    // blocks per source block under rotation; the exact count comes back from the device)
-    size_t i1 = i0, blocks = 0;
-    while (i1 < n && i1 - i0 < want &&
-           (i1 == i0 || 2 * (blocks + submaps[i1]->num_blocks) <= temp_cap)) {
-      blocks += static_cast<size_t>(submaps[i1]->num_blocks);
-      ++i1;
-    }
-    bool overflow = false;
-    int32_t rc = project_batch(submaps, poses, i0, i1, G, temp_cap, &overflow, stats);
-    if (rc) return rc;
-    if (overflow) {
-      if (i1 - i0 > 1) {
-        want = (i1 - i0) / 2;  // retry with half the submaps
-      } else {
-        temp_cap *= 2;         // a single submap with many candidates: more temporary blocks
-        if (temp_cap > (size_t(1) << 21)) {
-          set_error("cg_project_submaps: submap %zu needs more than 2^21 temporary blocks", i0);
-          return CG_ERR_INVALID_ARG;
-        }
-      }
-      continue;
-    }
-    want = kBatchMax;
-    i0 = i1;
+  if (n == 0) return finish_call(G, nullptr);
+  // descriptors of all submaps go up once (pinned, device-mapped staging + a copy kernel)
+  const size_t desc_bytes = n * sizeof(BatchSubmap);
+  if (desc_bytes > ctx->h_tables_cap) {
+    if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
+    ctx->h_tables = nullptr;
+    ctx->h_tables_cap = 0;
+    CG_CUDA(cudaHostAlloc(&ctx->h_tables, desc_bytes * 2, cudaHostAllocMapped));
+    ctx->h_tables_cap = desc_bytes * 2;
   }
-  return finish_call(G, nullptr);
+  BatchSubmap* h = static_cast<BatchSubmap*>(ctx->h_tables);
+  uint64_t blocks_in = 0;
+  for (size_t i0 = 0; i0 < n; i0 += kBatchMax) {
+    uint32_t total = 0;
+    for (size_t i = i0; i < std::min(n, i0 + static_cast<size_t>(kBatchMax)); ++i) {
+      h[i].A = submaps[i]->v;
+      h[i].T_B_A = make_xform(poses + 7 * i);
+      h[i].T_A_B = inverse_host(h[i].T_B_A);
+      h[i].first_block = total;  // prefix sum inside the submap's batch
+      h[i].num_blocks = static_cast<uint32_t>(submaps[i]->num_blocks);
+      total += h[i].num_blocks;
+    }
+    blocks_in += total;
+  }
+  void* d_alias = nullptr;
+  CG_CUDA(cudaHostGetDevicePointer(&d_alias, ctx->h_tables, 0));
+  CG_CUDA(ctx->batch_desc.reserve(desc_bytes));
+  ctx->own_launches += 2;
+  k_copy_desc<<<grid_for(desc_bytes / 4, 256), 256, 0, ctx->stream>>>(
+      ctx->batch_desc.as<uint32_t>(), static_cast<const uint32_t*>(d_alias), desc_bytes / 4);
+  k_reset_merge_counters<<<1, 1, 0, ctx->stream>>>(ctx->d_counters);
+  // batches of up to 64 submaps, in submap order (the mask of a destination block has one bit per
+  // submap of the batch)
+  for (size_t i0 = 0; i0 < n; i0 += kBatchMax) {
+    int32_t rc = project_batch(submaps, h, ctx->batch_desc.as<BatchSubmap>(), i0,
+                               std::min(n, i0 + static_cast<size_t>(kBatchMax)), G);
+    if (rc) return rc;
+  }
+  CallCounters c;
+  const int32_t rc = finish_call(G, &c);
+  if (stats) {
+    stats->blocks_in = blocks_in;
+    stats->blocks_candidate = c.candidates;
+    stats->blocks_out = c.blocks_out;
+  }
+  return rc;
 }
 
 }  // extern "C"

@@ -132,6 +132,44 @@ def test_merge_algebra_at_full_size(gpu_ctx):
         L.close()
 
 
+def test_projection_in_several_batches_is_sequential_and_repeatable(gpu_ctx):
+    """More submaps than one batch holds (64): destination blocks reached by submaps of different
+    batches and by many submaps of one batch (the in-kernel turn order of k_project_batch).  The
+    projection must equal the single merges in submap order bit for bit, every time it runs."""
+    import torch
+    from coxgraph_b200 import (Layer, TsdfIntegrator, TsdfIntegratorConfig, getProjectedMap,
+                               mergeLayerAintoLayerB, synth)
+    dev = torch.device("cuda", 0)
+    cfg = TsdfIntegratorConfig(use_const_weight=1, method=1, default_truncation_distance=0.16)
+    rng = np.random.default_rng(11)
+    base, T_M_S = [], []
+    for k in range(6):  # six distinct submaps, reused under 150 different poses
+        fr = synth.submap_frames(k % 2, k, 2, device=dev, stride=4)
+        L = Layer(gpu_ctx, 0.05, max_blocks=2048)
+        integ = TsdfIntegrator(cfg, L)
+        for (T, pts, cols) in fr:
+            integ.integratePointCloud(T, pts, cols)
+        base.append(L)
+    subs = [base[k % 6] for k in range(150)]
+    for k in range(150):
+        T_M_S.append(synth.perturb_pose(synth.robot_map_offset(k % 2), rng, sigma_t=0.3,
+                                        sigma_yaw_deg=20.0))
+    poses = np.stack(T_M_S)
+    q = Layer(gpu_ctx, 0.05, max_blocks=16384)
+    for L, T in zip(subs, T_M_S):
+        mergeLayerAintoLayerB(L, T, q)
+    want = q.download()
+    p = Layer(gpu_ctx, 0.05, max_blocks=16384)
+    for rep in range(3):
+        p.removeAllBlocks()
+        st = getProjectedMap(subs, poses, p, want_stats=True)
+        util.compare_layers(p.download(), want, f"150-submap projection, run {rep}", exact=True)
+        assert st.blocks_in == sum(L.num_blocks for L in subs)
+        assert st.blocks_out >= p.num_blocks and st.blocks_candidate >= st.blocks_out
+    for L in base + [p, q]:
+        L.close()
+
+
 def test_block_pool_beyond_4_gib(gpu_ctx):
     """C4 needs ~2 M blocks (98 GB): voxel offsets must be 64-bit.  Fill a layer with > 87 k far-away
     blocks (4.9 GB of pool) so that every block the frames touch lies beyond the 4 GiB mark, then
