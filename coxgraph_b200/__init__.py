@@ -6,4 +6,5 @@ generates the synthetic depth streams of the benchmark.  Nothing here falls back
 """
 from . import capi  # noqa: F401
 from .api import (Context, Layer, TsdfIntegrator, TsdfIntegratorConfig,  # noqa: F401
-                  getProjectedMap, mergeLayerAintoLayerB, meshToFrames, recoverMesh, VOXEL_DTYPE)
+                  getProjectedMap, mergeLayerAintoLayerB, meshToFrames, recoverMesh,
+                  reprojectSubmaps, VOXEL_DTYPE)

@@ -109,6 +109,17 @@ class Layer:
 
     clear = removeAllBlocks
 
+    def removeBlocks(self, block_indices):
+        """Layer::removeBlock for every listed (x, y, z) block index; returns how many existed."""
+        idx = np.ascontiguousarray(block_indices, np.int32).reshape(-1, 3)
+        removed = C.c_uint64(0)
+        capi.check(capi.load().cg_layer_remove_blocks(self._h, len(idx), _ptr(idx),
+                                                      C.byref(removed)))
+        return int(removed.value)
+
+    def removeBlock(self, block_index):
+        return self.removeBlocks([block_index])
+
     def getNumberOfAllocatedBlocks(self):
         return int(capi.load().cg_layer_num_blocks(self._h))
 
@@ -302,6 +313,23 @@ def getProjectedMap(submap_layers, submap_poses, global_layer, want_stats=False)
     capi.check(capi.load().cg_project_submaps(arr, _ptr(P), n, global_layer._h,
                                               C.byref(st) if want_stats else None))
     return st if want_stats else None
+
+
+def reprojectSubmaps(submap_layers, poses_old, poses_new, global_layer, eps_translation=0.0,
+                     eps_rotation=0.0):
+    """Incremental getProjectedMap() after a pose-graph update: global_layer must
+    hold the projection under poses_old; afterwards it is bit-identical to a fresh projection with
+    the moved submaps at poses_new.  Returns (changed mask, ReprojectStats)."""
+    n = len(submap_layers)
+    Po = np.ascontiguousarray(poses_old, np.float32).reshape(n, 7)
+    Pn = np.ascontiguousarray(poses_new, np.float32).reshape(n, 7)
+    arr = (C.c_void_p * n)(*[l._h for l in submap_layers])
+    changed = np.zeros(n, np.uint8)
+    st = capi.ReprojectStats()
+    capi.check(capi.load().cg_reproject_submaps(arr, _ptr(Po), _ptr(Pn), n, float(eps_translation),
+                                                float(eps_rotation), global_layer._h, _ptr(changed),
+                                                C.byref(st)))
+    return changed.astype(bool), st
 
 
 def block_owner(block_idx, nranks):

@@ -90,6 +90,12 @@ class MergeStats(C.Structure):
                 ("blocks_out", C.c_uint64)]
 
 
+class ReprojectStats(C.Structure):
+    _fields_ = [("submaps_moved", C.c_uint64), ("blocks_dirty", C.c_uint64),
+                ("candidates", C.c_uint64), ("blocks_folded", C.c_uint64),
+                ("blocks_removed", C.c_uint64)]
+
+
 # every symbol include/coxgraph_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -105,6 +111,7 @@ SYMBOLS = {
     "cg_layer_create": (C.c_int32, [_P, C.c_float, C.c_int32, C.c_size_t, C.POINTER(_P)]),
     "cg_layer_destroy": (C.c_int32, [_P]),
     "cg_layer_clear": (C.c_int32, [_P]),
+    "cg_layer_remove_blocks": (C.c_int32, [_P, C.c_size_t, _P, C.POINTER(C.c_uint64)]),
     "cg_layer_num_blocks": (C.c_int64, [_P]),
     "cg_layer_voxel_size": (C.c_float, [_P]),
     "cg_layer_download": (C.c_int32, [_P, C.c_size_t, _P, _P, _P, C.POINTER(C.c_size_t)]),
@@ -132,6 +139,8 @@ SYMBOLS = {
                                     C.c_size_t, _P, _P, C.POINTER(IntegrateStats)]),
     "cg_merge_layer_into_layer": (C.c_int32, [_P, _P, _P, C.POINTER(MergeStats)]),
     "cg_project_submaps": (C.c_int32, [_P, _P, C.c_size_t, _P, C.POINTER(MergeStats)]),
+    "cg_reproject_submaps": (C.c_int32, [_P, _P, _P, C.c_size_t, C.c_float, C.c_float, _P, _P,
+                                         C.POINTER(ReprojectStats)]),
     "cg_block_owner": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "cg_layer_pack_by_owner": (C.c_int32, [_P, C.c_int32, _P, C.c_size_t, _P]),
     "cg_layer_merge_packed": (C.c_int32, [_P, _P, C.c_size_t]),

@@ -266,6 +266,9 @@ void set_error(const char* fmt, ...);
 int32_t cuda_fail(cudaError_t e, const char* what);
 // pulls error bits + num_blocks back from the device; returns the status for the error bits
 int32_t finish_call(cg_layer* layer, CallCounters* out);
+// Layer::removeBlock for every slot with d_remove[slot] != 0 (device flags, one per claimed slot):
+// compacts the pool, rebuilds the hash; enqueued on the context's stream, host mirror updated
+int32_t remove_flagged_blocks(cg_layer* layer, const uint8_t* d_remove, uint64_t* removed_out);
 
 #define CG_CUDA(expr)                                         \
   do {                                                        \

@@ -3,6 +3,7 @@
 // TsdfVoxel as consumed at coxgraph/include/coxgraph/utils/msg_converter.h:49-50,107-109.
 #include <cub/cub.cuh>
 #include <stdarg.h>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
 
@@ -224,6 +225,125 @@ __global__ void k_upload_write(LayerView L, const int32_t* entries, const uint32
     L.has_data[slot] = f & 1;
     L.updated[slot] = (f >> 1) & 1;
   }
+}
+
+// ------------------------------------------------------------------ block removal
+// Layer::removeBlock for a set of blocks: the pool stays dense (claimed slots are [0, num_blocks)),
+// so the survivors of the tail fill the holes, the freed tail returns to the default-constructed
+// state and the hash is rebuilt from block_keys.
+struct HoleSlot {
+  const uint8_t* remove;
+  uint32_t keep;  // blocks that survive
+  __device__ __forceinline__ bool operator()(uint32_t slot) const {
+    return slot < keep && remove[slot] != 0;
+  }
+};
+struct FillerSlot {
+  const uint8_t* remove;
+  uint32_t keep;
+  __device__ __forceinline__ bool operator()(uint32_t slot) const {
+    return slot >= keep && remove[slot] == 0;
+  }
+};
+__global__ void k_count_flags(const uint8_t* __restrict__ flags, uint32_t n, uint32_t* count) {
+  uint32_t c = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    c += flags[i] != 0;
+  c = __reduce_add_sync(0xFFFFFFFFu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+__global__ void __launch_bounds__(256)
+k_move_blocks(LayerView L, const uint32_t* __restrict__ holes, const uint32_t* __restrict__ fillers,
+              uint32_t m) {
+  for (uint32_t i = blockIdx.x; i < m; i += gridDim.x) {
+    const uint32_t dst = holes[i], src = fillers[i];
+    const uint4* from = reinterpret_cast<const uint4*>(L.dist_plane(src));
+    uint4* to = reinterpret_cast<uint4*>(L.dist_plane(dst));
+    for (int w = threadIdx.x; w < 3 * kVoxelsPerBlock / 4; w += blockDim.x) to[w] = from[w];
+    if (threadIdx.x == 0) {
+      L.block_keys[dst] = L.block_keys[src];
+      L.has_data[dst] = L.has_data[src];
+      L.updated[dst] = L.updated[src];
+    }
+  }
+}
+__global__ void k_rehash(LayerView L, uint32_t n) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n) return;
+  const uint64_t key = L.block_keys[slot];
+  uint32_t h = hash_key(key) & L.hash_mask;
+  for (;;) {
+    if (L.hash_keys[h] == kEmptyKey &&
+        atomicCAS(reinterpret_cast<unsigned long long*>(&L.hash_keys[h]), kEmptyKey, key) == kEmptyKey) {
+      L.hash_vals[h] = static_cast<int32_t>(slot);
+      return;
+    }
+    h = (h + 1) & L.hash_mask;
+  }
+}
+__global__ void k_set_num_blocks(LayerView L, int32_t n) { *L.num_blocks = n; }
+
+int32_t remove_flagged_blocks(cg_layer* L, const uint8_t* d_remove, uint64_t* removed_out) {
+  cg_context* ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  const uint32_t n = static_cast<uint32_t>(L->num_blocks);
+  if (removed_out) *removed_out = 0;
+  if (n == 0) return CG_OK;
+  uint32_t* d_cnt = ctx->d_select_count;
+  CG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t), s));
+  ctx->own_launches += 1;
+  k_count_flags<<<std::min<unsigned>(grid_for(n, 256), ctx->num_sms * 8u), 256, 0, s>>>(d_remove, n,
+                                                                                         d_cnt);
+  uint32_t r = 0;
+  CG_CUDA(cudaMemcpyAsync(&r, d_cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CG_CUDA(cudaStreamSynchronize(s));
+  if (r == 0) return CG_OK;
+  const uint32_t keep = n - r;
+  LayerView& v = L->v;
+  if (keep > 0) {
+    CG_CUDA(ctx->val_a.reserve(sizeof(uint32_t) * r));
+    CG_CUDA(ctx->val_b.reserve(sizeof(uint32_t) * r));
+    thrust::counting_iterator<uint32_t> iota(0);
+    size_t tmp = 0;
+    CG_CUDA(cub::DeviceSelect::If(nullptr, tmp, iota, ctx->val_a.as<uint32_t>(), d_cnt,
+                                  static_cast<int>(n), HoleSlot{d_remove, keep}, s));
+    CG_CUDA(ctx->cub_tmp.reserve(tmp));
+    CG_CUDA(cub::DeviceSelect::If(ctx->cub_tmp.p, tmp, iota, ctx->val_a.as<uint32_t>(), d_cnt,
+                                  static_cast<int>(n), HoleSlot{d_remove, keep}, s));
+    CG_CUDA(cub::DeviceSelect::If(ctx->cub_tmp.p, tmp, iota, ctx->val_b.as<uint32_t>(), d_cnt,
+                                  static_cast<int>(n), FillerSlot{d_remove, keep}, s));
+    uint32_t m = 0;  // holes below `keep` == survivors at or above it
+    CG_CUDA(cudaMemcpyAsync(&m, d_cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CG_CUDA(cudaStreamSynchronize(s));
+    if (m > 0) {
+      ctx->own_launches += 1;
+      k_move_blocks<<<std::min<unsigned>(m, ctx->num_sms * 8u), 256, 0, s>>>(
+          v, ctx->val_a.as<uint32_t>(), ctx->val_b.as<uint32_t>(), m);
+    }
+  }
+  ctx->own_launches += 3;
+  k_fill_default<<<ctx->num_sms * 8, 256, 0, s>>>(v.pool, keep, r);
+  CG_CUDA(cudaMemsetAsync(v.has_data + keep, 0, r, s));
+  CG_CUDA(cudaMemsetAsync(v.updated + keep, 0, r, s));
+  CG_CUDA(cudaMemsetAsync(v.hash_keys, 0xFF, L->hash_cap * sizeof(uint64_t), s));
+  CG_CUDA(cudaMemsetAsync(v.hash_vals, 0xFF, L->hash_cap * sizeof(int32_t), s));
+  if (keep > 0) k_rehash<<<grid_for(keep, 256), 256, 0, s>>>(v, keep);
+  k_set_num_blocks<<<1, 1, 0, s>>>(v, static_cast<int32_t>(keep));
+  CG_CUDA(cudaGetLastError());
+  L->num_blocks = keep;
+  if (removed_out) *removed_out = r;
+  return CG_OK;
+}
+
+__global__ void k_flag_listed(LayerView L, const int32_t* __restrict__ idx, int n,
+                              uint8_t* __restrict__ remove) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = idx[3 * i], y = idx[3 * i + 1], z = idx[3 * i + 2];
+  constexpr int lim = kVoxIdxOffset / kVps;
+  if (x < -lim || x >= lim || y < -lim || y >= lim || z < -lim || z >= lim) return;
+  const int slot = L.find_slot(pack_block_key(x, y, z));
+  if (slot >= 0) remove[slot] = 1;
 }
 
 int32_t finish_call(cg_layer* layer, CallCounters* out) {
@@ -477,6 +597,25 @@ int32_t cg_layer_clear(cg_layer* L) {
   L->num_blocks = 0;
   CG_CUDA(cudaStreamSynchronize(s));
   return CG_OK;
+}
+
+int32_t cg_layer_remove_blocks(cg_layer* L, size_t n, const int32_t* idx, uint64_t* removed_out) {
+  if (!L || (n && !idx)) return CG_ERR_INVALID_ARG;
+  if (removed_out) *removed_out = 0;
+  if (n == 0 || L->num_blocks == 0) return CG_OK;
+  cg_context* ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  CG_CUDA(cudaSetDevice(ctx->device));
+  CG_CUDA(ctx->stage_b.reserve(n * 3 * sizeof(int32_t)));
+  CG_CUDA(ctx->stage_c.reserve(static_cast<size_t>(L->num_blocks)));
+  CG_CUDA(cudaMemcpyAsync(ctx->stage_b.p, idx, n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  CG_CUDA(cudaMemsetAsync(ctx->stage_c.p, 0, static_cast<size_t>(L->num_blocks), s));
+  ctx->own_launches += 1;
+  k_flag_listed<<<grid_for(n, 128), 128, 0, s>>>(L->v, ctx->stage_b.as<int32_t>(),
+                                                 static_cast<int>(n), ctx->stage_c.as<uint8_t>());
+  int32_t rc = remove_flagged_blocks(L, ctx->stage_c.as<uint8_t>(), removed_out);
+  if (rc) return rc;
+  return finish_call(L, nullptr);
 }
 
 int64_t cg_layer_num_blocks(const cg_layer* L) { return L ? L->num_blocks : -1; }

@@ -365,9 +365,21 @@ struct BatchSubmap {
 };
 constexpr int kBatchMax = 64;
 
+// `filter_keys` (optional): a hash set of destination blocks; blocks outside it are not marked
+// (incremental re-projection).  `map_mask` may be null: plain set insertion.
+__device__ __forceinline__ bool key_set_contains(const uint64_t* keys, uint32_t mask, uint64_t key) {
+  uint32_t h = hash_key(key) & mask;
+  for (;;) {
+    const uint64_t k = keys[h];
+    if (k == key) return true;
+    if (k == kEmptyKey) return false;
+    h = (h + 1) & mask;
+  }
+}
 __global__ void k_mark_batch(const BatchSubmap* __restrict__ desc, int n, uint32_t total_blocks,
                              float block_size_out, uint64_t* map_keys, unsigned long long* map_mask,
-                             uint32_t map_cap_mask, int32_t* err) {
+                             uint32_t map_cap_mask, int32_t* err,
+                             const uint64_t* __restrict__ filter_keys, uint32_t filter_mask) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total_blocks) return;
   int lo = 0, hi = n;  // desc[lo].first_block <= g
@@ -395,6 +407,7 @@ __global__ void k_mark_batch(const BatchSubmap* __restrict__ desc, int n, uint32
           continue;
         }
         const uint64_t key = pack_block_key(ix, iy, iz);
+        if (filter_keys && !key_set_contains(filter_keys, filter_mask, key)) continue;
         uint32_t h = hash_key(key) & map_cap_mask;
         for (;;) {
           const uint64_t k = map_keys[h];
@@ -406,7 +419,7 @@ __global__ void k_mark_batch(const BatchSubmap* __restrict__ desc, int n, uint32
           }
           h = (h + 1) & map_cap_mask;
         }
-        atomicOr(&map_mask[h], 1ull << lo);
+        if (map_mask) atomicOr(&map_mask[h], 1ull << lo);
       }
 }
 
@@ -574,8 +587,14 @@ static Xform inverse_host(const Xform& T) {
 
 // submaps [i0, i1) as one batch (descriptors already on the device); everything is enqueued on the
 // context's stream, nothing is read back
+static size_t mark_bound(const cg_layer* A, const cg_layer* G, size_t blocks) {
+  const double per_axis = std::floor(1.7320508075688772 * A->v.block_size / G->v.block_size) + 2.0;
+  return blocks * static_cast<size_t>(per_axis * per_axis * per_axis);
+}
+
 static int32_t project_batch(const cg_layer* const* submaps, const BatchSubmap* h_desc,
-                             const BatchSubmap* d_desc, size_t i0, size_t i1, cg_layer* G) {
+                             const BatchSubmap* d_desc, size_t i0, size_t i1, cg_layer* G,
+                             const uint64_t* filter_keys = nullptr, uint32_t filter_mask = 0) {
   cg_context* ctx = G->ctx;
   cudaStream_t s = ctx->stream;
   const int n = static_cast<int>(i1 - i0);
@@ -584,9 +603,7 @@ static int32_t project_batch(const cg_layer* const* submaps, const BatchSubmap* 
   for (int k = 0; k < n; ++k) {
     const cg_layer* A = submaps[i0 + k];
     total += h_desc[i0 + k].num_blocks;
-    const double per_axis = std::floor(1.7320508075688772 * A->v.block_size / G->v.block_size) + 2.0;
-    cand_bound += static_cast<size_t>(h_desc[i0 + k].num_blocks) *
-                  static_cast<size_t>(per_axis * per_axis * per_axis);
+    cand_bound += mark_bound(A, G, h_desc[i0 + k].num_blocks);
   }
   if (total == 0) return CG_OK;
   size_t cap = 4096;
@@ -610,7 +627,7 @@ static int32_t project_batch(const cg_layer* const* submaps, const BatchSubmap* 
     CG_CUDA(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(uint32_t), s));
     k_mark_batch<<<grid_for(total, 128), 128, 0, s>>>(
         d_desc + i0, n, total, G->v.block_size, ctx->cand_keys.as<uint64_t>(), masks,
-        static_cast<uint32_t>(cap - 1), G->v.err);
+        static_cast<uint32_t>(cap - 1), G->v.err, filter_keys, filter_mask);
     k_mask_counts<<<grid_for(cap, 256), 256, 0, s>>>(masks, static_cast<uint32_t>(cap), counts);
     CG_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_scan, counts,
                                           ctx->stage_c.as<uint32_t>(), static_cast<int>(cap + 1), s));
@@ -637,6 +654,65 @@ static int32_t project_batch(const cg_layer* const* submaps, const BatchSubmap* 
   }
   CG_CUDA(cudaGetLastError());
   return CG_OK;
+}
+
+// ------------------------------------------------------------------ incremental re-projection
+//   The server rebuilds the whole global map whenever poses change
+// (coxgraph/include/coxgraph/server/coxgraph_server.h:275-283 -> server_visualizer.cpp:123-126).
+// Here only the destination blocks a moved submap can reach — under its old or its new pose — are
+// rebuilt: they are reset, every submap (moved or not) whose forward pass marks them is resampled
+// and folded into them in submap order, and those left without data are removed.  Every other
+// block holds exactly what a full rebuild would produce, so the result is bit-identical to
+// clearing the layer and projecting all submaps again.
+__global__ void k_dirty_slots(LayerView G, const uint64_t* __restrict__ dirty_keys, uint32_t cap,
+                              uint32_t* __restrict__ slots, uint32_t* __restrict__ counts) {
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= cap) return;
+  const uint64_t key = dirty_keys[h];
+  if (key == kEmptyKey) return;
+  atomicAdd(&counts[1], 1u);  // dirty destination blocks
+  const int slot = G.find_slot(key);
+  if (slot >= 0) slots[atomicAdd(&counts[0], 1u)] = static_cast<uint32_t>(slot);
+}
+__global__ void __launch_bounds__(256)
+k_reset_blocks(LayerView G, const uint32_t* __restrict__ slots, const uint32_t* __restrict__ counts) {
+  const uint32_t n = counts[0];
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint32_t slot = slots[i];
+    uint4* p = reinterpret_cast<uint4*>(G.dist_plane(slot));
+    for (int w = threadIdx.x; w < 3 * kVoxelsPerBlock / 4; w += blockDim.x) {
+      const uint32_t v = w >= 2 * kVoxelsPerBlock / 4 ? kDefaultColor : 0u;
+      p[w] = make_uint4(v, v, v, v);
+    }
+    if (threadIdx.x == 0) G.has_data[slot] = 0;
+  }
+}
+__global__ void k_flag_dead(LayerView G, const uint32_t* __restrict__ slots,
+                            const uint32_t* __restrict__ counts, uint8_t* __restrict__ remove) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < counts[0] && !G.has_data[slots[i]]) remove[slots[i]] = 1;
+}
+
+static void fill_desc(BatchSubmap& d, const cg_layer* A, const float* pose, uint32_t first) {
+  d.A = A->v;
+  d.T_B_A = make_xform(pose);
+  d.T_A_B = inverse_host(d.T_B_A);
+  d.first_block = first;
+  d.num_blocks = static_cast<uint32_t>(A->num_blocks);
+}
+
+static bool pose_changed(const float* a, const float* b, float eps_t, float eps_rot) {
+  if (memcmp(a, b, 7 * sizeof(float)) == 0) return false;
+  const double dx = double(a[4]) - b[4], dy = double(a[5]) - b[5], dz = double(a[6]) - b[6];
+  if (std::sqrt(dx * dx + dy * dy + dz * dz) > eps_t) return true;
+  double dot = std::fabs(double(a[0]) * b[0] + double(a[1]) * b[1] + double(a[2]) * b[2] +
+                         double(a[3]) * b[3]);
+  const double na = std::sqrt(double(a[0]) * a[0] + double(a[1]) * a[1] + double(a[2]) * a[2] +
+                              double(a[3]) * a[3]);
+  const double nb = std::sqrt(double(b[0]) * b[0] + double(b[1]) * b[1] + double(b[2]) * b[2] +
+                              double(b[3]) * b[3]);
+  if (na > 0 && nb > 0) dot /= na * nb;
+  return 2.0 * std::acos(std::min(1.0, dot)) > eps_rot;
 }
 
 }  // namespace cg
@@ -723,6 +799,142 @@ int32_t cg_project_submaps(const cg_layer* const* submaps, const float* poses, s
     stats->blocks_out = c.blocks_out;
   }
   return rc;
+}
+
+int32_t cg_reproject_submaps(const cg_layer* const* submaps, const float* poses_old,
+                             const float* poses_new, size_t n, float eps_translation,
+                             float eps_rotation, cg_layer* G, uint8_t* changed_out,
+                             cg_reproject_stats* stats) {
+  if (!G || (n && (!submaps || !poses_old || !poses_new))) return CG_ERR_INVALID_ARG;
+  CG_CUDA(cudaSetDevice(G->ctx->device));
+  cg_context* ctx = G->ctx;
+  cudaStream_t s = ctx->stream;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  std::vector<size_t> moved;
+  for (size_t i = 0; i < n; ++i) {
+    const cg_layer* A = submaps[i];
+    if (!A || A == G || A->ctx != ctx) {
+      set_error("cg_reproject_submaps: submap %zu invalid", i);
+      return CG_ERR_INVALID_ARG;
+    }
+    const bool ch = pose_changed(poses_old + 7 * i, poses_new + 7 * i, eps_translation, eps_rotation);
+    if (changed_out) changed_out[i] = ch ? 1 : 0;
+    if (ch) moved.push_back(i);
+  }
+  if (stats) stats->submaps_moved = moved.size();
+  if (moved.empty()) return CG_OK;
+  // descriptor table: [0, n) all submaps under their effective pose (batch-relative block prefix),
+  // then every moved submap under its old and under its new pose (one prefix over the list)
+  const size_t nd = n + 2 * moved.size();
+  const size_t desc_bytes = nd * sizeof(BatchSubmap);
+  if (desc_bytes > ctx->h_tables_cap) {
+    if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
+    ctx->h_tables = nullptr;
+    ctx->h_tables_cap = 0;
+    CG_CUDA(cudaHostAlloc(&ctx->h_tables, desc_bytes * 2, cudaHostAllocMapped));
+    ctx->h_tables_cap = desc_bytes * 2;
+  }
+  BatchSubmap* h = static_cast<BatchSubmap*>(ctx->h_tables);
+  {
+    size_t mi = 0;
+    for (size_t i0 = 0; i0 < n; i0 += kBatchMax) {
+      uint32_t total = 0;
+      for (size_t i = i0; i < std::min(n, i0 + static_cast<size_t>(kBatchMax)); ++i) {
+        const bool ch = mi < moved.size() && moved[mi] == i;
+        if (ch) ++mi;
+        fill_desc(h[i], submaps[i], (ch ? poses_new : poses_old) + 7 * i, total);
+        total += h[i].num_blocks;
+      }
+    }
+  }
+  uint32_t dirty_src = 0;
+  size_t dirty_bound = 0;
+  for (size_t k = 0; k < moved.size(); ++k) {
+    const size_t i = moved[k];
+    fill_desc(h[n + 2 * k], submaps[i], poses_old + 7 * i, dirty_src);
+    dirty_src += h[n + 2 * k].num_blocks;
+    fill_desc(h[n + 2 * k + 1], submaps[i], poses_new + 7 * i, dirty_src);
+    dirty_src += h[n + 2 * k + 1].num_blocks;
+    dirty_bound += 2 * mark_bound(submaps[i], G, h[n + 2 * k].num_blocks);
+  }
+  void* d_alias = nullptr;
+  CG_CUDA(cudaHostGetDevicePointer(&d_alias, ctx->h_tables, 0));
+  CG_CUDA(ctx->batch_desc.reserve(desc_bytes));
+  ctx->own_launches += 2;
+  k_copy_desc<<<grid_for(desc_bytes / 4, 256), 256, 0, s>>>(
+      ctx->batch_desc.as<uint32_t>(), static_cast<const uint32_t*>(d_alias), desc_bytes / 4);
+  k_reset_merge_counters<<<1, 1, 0, s>>>(ctx->d_counters);
+  const BatchSubmap* d_desc = ctx->batch_desc.as<BatchSubmap>();
+  uint32_t dirty_total = 0, dirty_existing = 0;
+  uint64_t removed = 0;
+  if (dirty_src > 0) {
+    // the dirty set: destination blocks a moved submap marks under either pose
+    size_t cap = 4096;
+    while (cap < 2 * dirty_bound) cap <<= 1;
+    const size_t g_blocks = static_cast<size_t>(G->num_blocks);
+    CG_CUDA(ctx->stage_a.reserve(cap * sizeof(uint64_t)));
+    CG_CUDA(ctx->stage_b.reserve((g_blocks + 2) * sizeof(uint32_t)));
+    uint32_t* counts = ctx->stage_b.as<uint32_t>();  // [0] dirty blocks present in G, [1] dirty blocks
+    uint32_t* slots = counts + 2;
+    {
+      StageScope sc(ctx, kStageMergeMark, 3);
+      CG_CUDA(cudaMemsetAsync(ctx->stage_a.p, 0xFF, cap * sizeof(uint64_t), s));
+      CG_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(uint32_t), s));
+      k_mark_batch<<<grid_for(dirty_src, 128), 128, 0, s>>>(
+          d_desc + n, static_cast<int>(2 * moved.size()), dirty_src, G->v.block_size,
+          ctx->stage_a.as<uint64_t>(), nullptr, static_cast<uint32_t>(cap - 1), G->v.err, nullptr, 0);
+      k_dirty_slots<<<grid_for(cap, 256), 256, 0, s>>>(G->v, ctx->stage_a.as<uint64_t>(),
+                                                       static_cast<uint32_t>(cap), slots, counts);
+      k_reset_blocks<<<ctx->num_sms * 8, 256, 0, s>>>(G->v, slots, counts);
+    }
+    // every submap that reaches a dirty block is folded into it again, in submap order
+    for (size_t i0 = 0; i0 < n; i0 += kBatchMax) {
+      int32_t rc = project_batch(submaps, h, d_desc, i0, std::min(n, i0 + static_cast<size_t>(kBatchMax)),
+                                 G, ctx->stage_a.as<uint64_t>(), static_cast<uint32_t>(cap - 1));
+      if (rc) return rc;
+    }
+    // dirty blocks that ended up without data leave the layer (a fresh projection would not
+    // have allocated them)
+    uint32_t h_counts[2] = {0, 0};
+    CG_CUDA(cudaMemcpyAsync(h_counts, counts, sizeof(h_counts), cudaMemcpyDeviceToHost, s));
+    CG_CUDA(cudaStreamSynchronize(s));
+    dirty_existing = h_counts[0];
+    dirty_total = h_counts[1];
+    if (dirty_existing > 0) {
+      // new blocks were claimed behind the old ones: flags cover the current block count
+      CallCounters c0;
+      int32_t rc = finish_call(G, &c0);
+      if (rc) return rc;
+      const CallCounters keep = c0;
+      CG_CUDA(ctx->flags.reserve(static_cast<size_t>(G->num_blocks) + 1));
+      CG_CUDA(cudaMemsetAsync(ctx->flags.p, 0, static_cast<size_t>(G->num_blocks), s));
+      ctx->own_launches += 1;
+      k_flag_dead<<<grid_for(dirty_existing, 256), 256, 0, s>>>(G->v, slots, counts,
+                                                                ctx->flags.as<uint8_t>());
+      rc = remove_flagged_blocks(G, ctx->flags.as<uint8_t>(), &removed);
+      if (rc) return rc;
+      rc = finish_call(G, nullptr);
+      if (rc) return rc;
+      if (stats) {
+        stats->candidates = keep.candidates;
+        stats->blocks_folded = keep.blocks_out;
+      }
+    }
+  }
+  if (dirty_existing == 0) {
+    CallCounters c;
+    const int32_t rc = finish_call(G, &c);
+    if (rc) return rc;
+    if (stats) {
+      stats->candidates = c.candidates;
+      stats->blocks_folded = c.blocks_out;
+    }
+  }
+  if (stats) {
+    stats->blocks_dirty = dirty_total;
+    stats->blocks_removed = removed;
+  }
+  return CG_OK;
 }
 
 }  // extern "C"

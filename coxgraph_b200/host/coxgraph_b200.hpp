@@ -128,6 +128,12 @@ class TsdfLayer {
   }
   size_t getMemorySize() const { return getNumberOfAllocatedBlocks() * CG_BLOCK_BYTES; }
   void removeAllBlocks() { check(cg_layer_clear(layer_)); }
+  // Layer::removeBlock(index); returns whether the block existed
+  bool removeBlock(const BlockIndex& index) {
+    uint64_t removed = 0;
+    check(cg_layer_remove_blocks(layer_, 1, &index.x, &removed));
+    return removed != 0;
+  }
   void getAllAllocatedBlocks(BlockIndexList* blocks) const {
     const size_t n = getNumberOfAllocatedBlocks();
     blocks->resize(n);
@@ -296,6 +302,32 @@ inline void getProjectedMap(const std::vector<const TsdfLayer*>& submap_layers,
   }
   check(cg_project_submaps(handles.data(), poses.data(), handles.size(), projected_layer->handle(),
                            stats));
+}
+
+// ---- the same map after a pose-graph update, rebuilt only where a moved submap reaches
+// (the reference re-projects everything, coxgraph_server.h:275-283).  The layer must
+// hold getProjectedMap(submap_layers, T_M_S_old); afterwards it is bit-identical to
+// getProjectedMap with the moved submaps at T_M_S_new.  Returns which submaps counted as moved.
+inline std::vector<uint8_t> reprojectSubmaps(const std::vector<const TsdfLayer*>& submap_layers,
+                                             const std::vector<Transformation>& T_M_S_old,
+                                             const std::vector<Transformation>& T_M_S_new,
+                                             TsdfLayer* projected_layer, float eps_translation = 0.0f,
+                                             float eps_rotation = 0.0f,
+                                             cg_reproject_stats* stats = nullptr) {
+  const size_t n = submap_layers.size();
+  if (T_M_S_old.size() != n || T_M_S_new.size() != n)
+    fatal_handler()(CG_ERR_INVALID_ARG, "reprojectSubmaps: one old and one new pose per submap expected");
+  std::vector<const cg_layer*> handles(n);
+  std::vector<float> po(7 * n), pn(7 * n);
+  for (size_t i = 0; i < n; ++i) {
+    handles[i] = submap_layers[i]->handle();
+    std::copy(T_M_S_old[i].data(), T_M_S_old[i].data() + 7, po.begin() + 7 * i);
+    std::copy(T_M_S_new[i].data(), T_M_S_new[i].data() + 7, pn.begin() + 7 * i);
+  }
+  std::vector<uint8_t> changed(n, 0);
+  check(cg_reproject_submaps(handles.data(), po.data(), pn.data(), n, eps_translation, eps_rotation,
+                             projected_layer->handle(), changed.data(), stats));
+  return changed;
 }
 
 }  // namespace coxgraph_b200

@@ -128,6 +128,10 @@ int32_t cg_layer_destroy(cg_layer* layer);
 /* Layer::removeAllBlocks — coxgraph/include/coxgraph/map_comm/tsdf_recover.h:62,
  * coxgraph/src/client/map_server.cpp:65 */
 int32_t cg_layer_clear(cg_layer* layer);
+/* Layer::removeBlock for each listed block index (absent ones are ignored); *removed_out
+ * (optional) = blocks actually removed.  The pool is compacted and the hash rebuilt. */
+int32_t cg_layer_remove_blocks(cg_layer* layer, size_t num_blocks, const int32_t* block_idx_xyz,
+                               uint64_t* removed_out);
 /* Layer::getNumberOfAllocatedBlocks */
 int64_t cg_layer_num_blocks(const cg_layer* layer);
 float cg_layer_voxel_size(const cg_layer* layer);
@@ -248,6 +252,28 @@ int32_t cg_merge_layer_into_layer(const cg_layer* layer_a, const float T_B_A[7],
 /* for s in 0..n-1: mergeLayerAintoLayerB(submaps[s], T_M_S[s], global), in that order. */
 int32_t cg_project_submaps(const cg_layer* const* submaps, const float* T_M_S_poses,
                            size_t num_submaps, cg_layer* global_layer, cg_merge_stats* stats);
+
+/* --- incremental re-projection.  The reference rebuilds the whole global map
+ * on every trigger (coxgraph/include/coxgraph/server/coxgraph_server.h:275-283 ->
+ * coxgraph/src/server/visualizer/server_visualizer.cpp:123-126) although it knows which submap
+ * poses the optimisation moved (coxgraph/src/client/coxgraph_client.cpp:135-153,
+ * coxgraph/src/server/client_handler.cpp:106-129).  Precondition: `global_layer` holds the
+ * projection of `submaps` under `poses_old` (cg_project_submaps into an empty layer, or an earlier
+ * cg_reproject_submaps).  Submap i counts as moved when its translation changed by more than
+ * eps_translation [m] or its rotation by more than eps_rotation [rad] (bit-identical poses never
+ * count).  On return the layer is bit-identical to clearing it and projecting every submap with
+ * pose_eff[i] = moved ? poses_new[i] : poses_old[i]; changed_out[i] (optional) tells which. */
+typedef struct cg_reproject_stats {
+  uint64_t submaps_moved;
+  uint64_t blocks_dirty;    /* destination blocks a moved submap reaches under either pose */
+  uint64_t candidates;      /* (dirty block, submap) pairs resampled */
+  uint64_t blocks_folded;   /* pairs that carried data */
+  uint64_t blocks_removed;  /* dirty blocks left without data: removed from the layer */
+} cg_reproject_stats;
+int32_t cg_reproject_submaps(const cg_layer* const* submaps, const float* poses_old,
+                             const float* poses_new, size_t num_submaps, float eps_translation,
+                             float eps_rotation, cg_layer* global_layer, uint8_t* changed_out,
+                             cg_reproject_stats* stats);
 
 /* --- multi-GPU exchange of partial global layers (DESIGN.md "Multi-GPU") -------------
  * Ownership of a global block is owner = cg_block_owner(idx, nranks).  Each rank packs the

@@ -3,7 +3,8 @@ import sys, os, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from coxgraph_b200 import Context, Layer, TsdfIntegrator, TsdfIntegratorConfig, getProjectedMap, synth
+from coxgraph_b200 import (Context, Layer, TsdfIntegrator, TsdfIntegratorConfig, getProjectedMap,
+                           reprojectSubmaps, synth)
 
 dev = torch.device("cuda", 0)
 ctx = Context(0)
@@ -38,3 +39,23 @@ for it in range(3):
         print({k: round(v[0], 3) for k, v in ctx.profile().items() if v[0] > 0})
     print(f"project {nsub} submaps ({blocks_in} blocks in, {glob.num_blocks} global): {dt*1e3:.2f} ms, "
           f"{4096*blocks_in/dt/1e9:.2f} G voxels/s, {dt*1e3/nsub:.3f} ms/submap")
+
+# incremental re-projection after a pose-graph update that moved a fraction of the submaps
+rng = np.random.default_rng(1)
+for frac in (0.05, 0.25, 1.0):
+    best = None
+    for it in range(3):
+        glob.removeAllBlocks()
+        getProjectedMap(subs, poses, glob)
+        new = poses.copy()
+        moved = rng.choice(nsub, max(1, int(frac * nsub)), replace=False)
+        for k in moved:
+            new[k] = synth.perturb_pose(poses[k], rng)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        changed, st = reprojectSubmaps(subs, poses, new, glob)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    print(f"reproject {len(moved)}/{nsub} moved: {best*1e3:.2f} ms (dirty {st.blocks_dirty} blocks, "
+          f"{st.candidates} candidates, {st.blocks_folded} folds, {st.blocks_removed} removed)")
