@@ -88,6 +88,11 @@ def lib():
         L.orc_cast_ray.restype = C.c_size_t
         L.orc_cast_ray.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                                    C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_size_t]
+        L.orc_layer_mesh.restype = C.c_size_t
+        L.orc_layer_mesh.argtypes = [C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_triangle_table.restype = C.POINTER(C.c_int)
+        L.orc_triangle_table.argtypes = []
         L.orc_interp_voxel.restype = C.c_int32
         L.orc_interp_voxel.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_float),
                                        C.POINTER(C.c_float), C.c_void_p]
@@ -190,6 +195,21 @@ class Layer:
         lib().orc_layer_upload(self._h, _ptr(idx), _ptr(vox), None if fl is None else _ptr(fl),
                                len(idx))
 
+    def mesh(self, min_weight=1e-4, use_color=True, only_updated=False):
+        """MeshIntegrator::generateMesh -> (vertex_begin u32 [B+1], vertices f32 [V,3],
+        normals f32 [V,3], colors u8 [V,4]); blocks in (z,y,x) order."""
+        nb = self.num_blocks
+        begin = np.zeros(nb + 1, np.uint32)
+        n = lib().orc_layer_mesh(self._h, min_weight, int(use_color), int(only_updated),
+                                 _ptr(begin), None, None, None, 0)
+        v = np.zeros((n, 3), np.float32)
+        nr = np.zeros((n, 3), np.float32)
+        c = np.zeros((n, 4), np.uint8)
+        if n:
+            lib().orc_layer_mesh(self._h, min_weight, int(use_color), int(only_updated),
+                                 _ptr(begin), _ptr(v), _ptr(nr), _ptr(c), n)
+        return begin, v, nr, c
+
     def interp(self, pos, interpolate=True):
         p = _f32(pos, (3,))
         d, w = C.c_float(0), C.c_float(0)
@@ -197,6 +217,11 @@ class Layer:
         ok = lib().orc_interp_voxel(self._h, _ptr(p), int(interpolate), C.byref(d), C.byref(w),
                                     _ptr(rgba))
         return bool(ok), d.value, w.value, rgba
+
+
+def triangle_table():
+    """kTriangleTable as an int array [256, 16]."""
+    return np.ctypeslib.as_array(lib().orc_triangle_table(), shape=(256, 16)).copy()
 
 
 def transform_point(T, p):

@@ -129,6 +129,19 @@ size_t orc_mesh_to_frames(const orc_mesh* mesh, float interpolate_voxel_size, si
                           const float* poses, const double* stamps_sec, uint64_t* frame_offsets,
                           float* points_xyz, uint8_t* colors_rgba, size_t capacity_points);
 
+/* ---- MeshIntegrator<TsdfVoxel>::generateMesh (marching cubes per block, [EXT] voxblox
+ * mesh/mesh_integrator.h + mesh/marching_cubes.h; parity unpinned).  Blocks in (z, y, x) order;
+ * block b owns vertices [vertex_begin[b], vertex_begin[b+1]) (B + 1 entries), in the reference's
+ * voxel loop order; three consecutive vertices = one triangle (indices are 0..n-1 per block);
+ * normals per vertex (the triangle's), colours nearest-voxel.  With only_updated, blocks whose
+ * `updated` flag is clear produce nothing.  Returns the vertex count; arrays are filled only if
+ * capacity_vertices suffices.  Any pointer may be NULL. */
+size_t orc_layer_mesh(const orc_layer* layer, float min_weight, int32_t use_color,
+                      int32_t only_updated, uint32_t* vertex_begin, float* vertices, float* normals,
+                      uint8_t* colors, size_t capacity_vertices);
+/* kTriangleTable[256][16] */
+const int* orc_triangle_table(void);
+
 #ifdef __cplusplus
 }
 #endif
