@@ -9,7 +9,7 @@ SRC  = coxgraph_b200/csrc
 OBJ  = build/obj
 LIB  = coxgraph_b200/lib/libcoxgraph_b200.so
 HDRS = $(SRC)/cg_math.cuh $(SRC)/cg_internal.cuh include/coxgraph_b200.h
-OBJS = $(OBJ)/layer.o $(OBJ)/integrate.o $(OBJ)/merge.o $(OBJ)/exchange.o $(OBJ)/mesh_recover.o $(OBJ)/selftest.o
+OBJS = $(OBJ)/layer.o $(OBJ)/integrate.o $(OBJ)/merge.o $(OBJ)/exchange.o $(OBJ)/mesh_recover.o $(OBJ)/mesh.o $(OBJ)/selftest.o
 
 HOSTCHK = build/host_api_check
 

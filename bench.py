@@ -370,6 +370,36 @@ def run_ours(args, rank, world, local_rank):
                    "global_blocks": big.num_blocks,
                    "hbm_frac": BLOCK_BYTES * (st.blocks_in + 2 * st.blocks_out) / (ms * 1e-3) / 1e9 /
                    measured_peak_gbs()[0]}
+        # after a pose-graph update that moved a tenth of the submaps: incremental re-projection
+        # (bit-identical to the full rebuild), then the mesh of the device-resident map — what
+        # saveAndPubCombinedMesh does next (server_visualizer.cpp:123-126)
+        from coxgraph_b200 import reprojectSubmaps
+        rng = np.random.default_rng(7)
+        rep_ms = []
+        for it in range(3):
+            big.clear()
+            getProjectedMap(subs, T_all, big)
+            T_new = T_all.copy()
+            for k in rng.choice(len(subs), max(1, len(subs) // 10), replace=False):
+                T_new[k] = synth.perturb_pose(T_all[k], rng)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            _, rst = reprojectSubmaps(subs, T_all, T_new, big)
+            b.record(stream)
+            torch.cuda.synchronize()
+            rep_ms.append(a.elapsed_time(b))
+        project["reproject_10pct_moved"] = {
+            "ms": max_over_ranks(min(rep_ms[1:])), "submaps_moved": int(rst.submaps_moved),
+            "blocks_dirty": int(rst.blocks_dirty), "candidates": int(rst.candidates)}
+        mesh_ms = []
+        for it in range(3):
+            t0 = time.perf_counter()
+            mesh = big.generateMesh()
+            mesh_ms.append((time.perf_counter() - t0) * 1e3)
+        project["mesh"] = {"ms_with_d2h": max_over_ranks(min(mesh_ms[1:])),
+                           "triangles": int(len(mesh[2]) // 3), "blocks": big.num_blocks,
+                           "d2h_bytes": int(len(mesh[2]) * 28),
+                           "layer_bytes_not_downloaded": int(big.num_blocks * BLOCK_BYTES)}
         if world > 1:
             # the server's global merge over all ranks: every rank projects its submaps into a
             # partial layer, one NCCL all-to-all moves the partial blocks to their owners, the

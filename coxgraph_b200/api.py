@@ -173,6 +173,26 @@ class Layer:
         words = np.ascontiguousarray(data, np.uint32).reshape(len(idx), 3 * capi.VOXELS_PER_BLOCK)
         capi.check(capi.load().cg_layer_deserialize(self._h, len(idx), _ptr(idx), _ptr(words)))
 
+    def generateMesh(self, min_weight=1e-4, use_color=True, only_updated=False):
+        """voxblox::MeshIntegrator<TsdfVoxel>::generateMesh on the device (marching cubes per
+        block) -> (block_idx int32 [B,3] in (z,y,x) order, vertex_begin u32 [B+1], vertices f32
+        [V,3], normals f32 [V,3], colors u8 [V,4]); three consecutive vertices = one triangle."""
+        lib = capi.load()
+        nb, nv = C.c_size_t(0), C.c_size_t(0)
+        capi.check(lib.cg_layer_mesh(self._h, min_weight, int(use_color), int(only_updated), 0, 0,
+                                     None, None, None, None, None, C.byref(nb), C.byref(nv)))
+        B, V = nb.value, nv.value
+        idx = np.zeros((B, 3), np.int32)
+        begin = np.zeros(B + 1, np.uint32)
+        v = np.zeros((V, 3), np.float32)
+        n = np.zeros((V, 3), np.float32)
+        c = np.zeros((V, 4), np.uint8)
+        if B:
+            capi.check(lib.cg_mesh_fetch(self.ctx._h, B, V, _ptr(idx), _ptr(begin),
+                                         _ptr(v) if V else None, _ptr(n) if V else None,
+                                         _ptr(c) if V else None))
+        return idx, begin, v, n, c
+
     def upload(self, block_idx, voxels, flags=None):
         idx = np.ascontiguousarray(block_idx, np.int32).reshape(-1, 3)
         vox = np.ascontiguousarray(voxels, VOXEL_DTYPE).reshape(len(idx), capi.VOXELS_PER_BLOCK)

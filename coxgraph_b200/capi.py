@@ -139,6 +139,9 @@ SYMBOLS = {
                                     C.c_size_t, _P, _P, C.POINTER(IntegrateStats)]),
     "cg_merge_layer_into_layer": (C.c_int32, [_P, _P, _P, C.POINTER(MergeStats)]),
     "cg_project_submaps": (C.c_int32, [_P, _P, C.c_size_t, _P, C.POINTER(MergeStats)]),
+    "cg_layer_mesh": (C.c_int32, [_P, C.c_float, C.c_int32, C.c_int32, C.c_size_t, C.c_size_t, _P, _P,
+                                  _P, _P, _P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "cg_mesh_fetch": (C.c_int32, [_P, C.c_size_t, C.c_size_t, _P, _P, _P, _P, _P]),
     "cg_reproject_submaps": (C.c_int32, [_P, _P, _P, C.c_size_t, C.c_float, C.c_float, _P, _P,
                                          C.POINTER(ReprojectStats)]),
     "cg_block_owner": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

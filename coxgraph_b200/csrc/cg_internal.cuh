@@ -243,6 +243,9 @@ struct cg_context {
   // mesh recovery (mesh_recover.cu)
   cg::DevBuf mesh_in, mesh_tri, mesh_pairs, mesh_pts_g, mesh_cols_g, mesh_pts_c, mesh_cols_c,
       mesh_frames;
+  // marching cubes (mesh.cu)
+  cg::DevBuf mc_counts, mc_index, mc_vertices, mc_normals, mc_colors;
+  size_t mc_blocks = 0, mc_total = 0;  // size of the retained result (cg_mesh_fetch)
   // instrumentation
   bool profiling = false;
   uint64_t own_launches = 0;  // kernels of this library launched (library sorts/scans excluded)
@@ -266,6 +269,8 @@ void set_error(const char* fmt, ...);
 int32_t cuda_fail(cudaError_t e, const char* what);
 // pulls error bits + num_blocks back from the device; returns the status for the error bits
 int32_t finish_call(cg_layer* layer, CallCounters* out);
+// sorted (z,y,x) view of the allocated blocks: keys in ctx->key_b, slots in ctx->val_b
+int32_t sort_blocks(const cg_layer* layer, const uint64_t** keys, const uint32_t** slots);
 // Layer::removeBlock for every slot with d_remove[slot] != 0 (device flags, one per claimed slot):
 // compacts the pool, rebuilds the hash; enqueued on the context's stream, host mirror updated
 int32_t remove_flagged_blocks(cg_layer* layer, const uint8_t* d_remove, uint64_t* removed_out);

@@ -368,7 +368,7 @@ int32_t finish_call(cg_layer* layer, CallCounters* out) {
 }
 
 // sorted (z,y,x) view of the allocated blocks: keys in ctx->key_b, slots in ctx->val_b
-static int32_t sort_blocks(const cg_layer* layer, const uint64_t** keys, const uint32_t** slots) {
+int32_t sort_blocks(const cg_layer* layer, const uint64_t** keys, const uint32_t** slots) {
   cg_context* ctx = layer->ctx;
   const int n = static_cast<int>(layer->num_blocks);
   CG_CUDA(ctx->key_b.reserve(sizeof(uint64_t) * n));
@@ -444,7 +444,7 @@ int32_t cg_context_destroy(cg_context* ctx) {
                     &ctx->key_b, &ctx->val_a, &ctx->val_b, &ctx->flags, &ctx->scan,
                     &ctx->cub_tmp, &ctx->rays, &ctx->ray_count, &ctx->ray_offset, &ctx->sorted_pts, &ctx->pkey_a,
                     &ctx->pkey_b, &ctx->seg_keys_a, &ctx->seg_keys_b, &ctx->seg_idx_a, &ctx->seg_idx_b, &ctx->seg_recs, &ctx->seg_order, &ctx->scan_partials, &ctx->seg_bins, &ctx->grazing_keys, &ctx->grazing_ray_key, &ctx->touch_ord, &ctx->touch_entry, &ctx->touch_acc, &ctx->touch_bits, &ctx->seg_start, &ctx->long_list, &ctx->long_partials, &ctx->cand_keys, &ctx->cand_list,
-                    &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->batch_desc, &ctx->merge_cands, &ctx->mesh_in, &ctx->mesh_tri,
+                    &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->batch_desc, &ctx->merge_cands, &ctx->mc_counts, &ctx->mc_index, &ctx->mc_vertices, &ctx->mc_normals, &ctx->mc_colors, &ctx->mesh_in, &ctx->mesh_tri,
                     &ctx->mesh_pairs, &ctx->mesh_pts_g, &ctx->mesh_cols_g, &ctx->mesh_pts_c,
                     &ctx->mesh_cols_c, &ctx->mesh_frames};
   for (DevBuf* b : bufs) b->release();

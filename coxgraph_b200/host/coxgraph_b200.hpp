@@ -112,6 +112,7 @@ class TsdfLayer {
             size_t max_blocks = 4096) {
     check(cg_layer_create(ctx.handle(), voxel_size, static_cast<int32_t>(voxels_per_side),
                           max_blocks, &layer_));
+    ctx_ = ctx.handle();
   }
   ~TsdfLayer() {
     if (layer_) cg_layer_destroy(layer_);
@@ -120,6 +121,7 @@ class TsdfLayer {
   TsdfLayer& operator=(const TsdfLayer&) = delete;
 
   cg_layer* handle() const { return layer_; }
+  cg_context* context() const { return ctx_; }
   FloatingPoint voxel_size() const { return cg_layer_voxel_size(layer_); }
   size_t voxels_per_side() const { return CG_VOXELS_PER_SIDE; }
   FloatingPoint block_size() const { return voxel_size() * CG_VOXELS_PER_SIDE; }
@@ -181,6 +183,7 @@ class TsdfLayer {
 
  private:
   cg_layer* layer_ = nullptr;
+  cg_context* ctx_ = nullptr;
 };
 
 // ---- voxblox::TsdfIntegratorBase and its concrete integrators ---------------------------
@@ -302,6 +305,37 @@ inline void getProjectedMap(const std::vector<const TsdfLayer*>& submap_layers,
   }
   check(cg_project_submaps(handles.data(), poses.data(), handles.size(), projected_layer->handle(),
                            stats));
+}
+
+// ---- voxblox::MeshIntegrator<TsdfVoxel>::generateMesh over a device-resident layer (what
+// saveAndPubCombinedMesh runs on the projected map, server_visualizer.cpp:123-126): per-block
+// marching cubes; block b owns vertices [vertex_begin[b], vertex_begin[b + 1]), three per triangle
+struct MeshIntegratorConfig {  // voxblox::MeshIntegratorConfig
+  bool use_color = true;
+  float min_weight = 1e-4f;
+};
+struct LayerMesh {
+  BlockIndexList block_indices;        // (z, y, x) order
+  std::vector<uint32_t> vertex_begin;  // block_indices.size() + 1
+  std::vector<Point> vertices, normals;
+  std::vector<Color> colors;
+};
+inline void generateMesh(const TsdfLayer& layer, LayerMesh* mesh,
+                         const MeshIntegratorConfig& config = MeshIntegratorConfig(),
+                         bool only_mesh_updated_blocks = false) {
+  size_t nb = 0, nv = 0;
+  check(cg_layer_mesh(layer.handle(), config.min_weight, config.use_color ? 1 : 0,
+                      only_mesh_updated_blocks ? 1 : 0, 0, 0, nullptr, nullptr, nullptr, nullptr,
+                      nullptr, &nb, &nv));
+  mesh->block_indices.resize(nb);
+  mesh->vertex_begin.assign(nb + 1, 0);
+  mesh->vertices.resize(nv);
+  mesh->normals.resize(nv);
+  mesh->colors.resize(nv);
+  if (nb == 0) return;
+  check(cg_mesh_fetch(layer.context(), nb, nv, &mesh->block_indices[0].x, mesh->vertex_begin.data(),
+                      nv ? &mesh->vertices[0].x : nullptr, nv ? &mesh->normals[0].x : nullptr,
+                      nv ? &mesh->colors[0].r : nullptr));
 }
 
 // ---- the same map after a pose-graph update, rebuilt only where a moved submap reaches

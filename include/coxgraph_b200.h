@@ -253,6 +253,29 @@ int32_t cg_merge_layer_into_layer(const cg_layer* layer_a, const float T_B_A[7],
 int32_t cg_project_submaps(const cg_layer* const* submaps, const float* T_M_S_poses,
                            size_t num_submaps, cg_layer* global_layer, cg_merge_stats* stats);
 
+/* --- meshing on the device-resident layer: replaces
+ * voxblox::MeshIntegrator<TsdfVoxel>::generateMesh as run by
+ * voxgraph::SubmapVisuals::saveAndPubCombinedMesh right after the merge
+ * (coxgraph/src/server/visualizer/server_visualizer.cpp:123-126) and by generateSubmapMesh on the
+ * client (coxgraph/src/client/map_server.cpp:126-130), so only triangles leave the GPU.
+ * Blocks come in (z, y, x) order; block b owns vertices [vertex_begin[b], vertex_begin[b+1])
+ * (num_blocks + 1 entries), in the reference's voxel loop order; three consecutive vertices are
+ * one triangle (voxblox's per-block `indices` are 0..n-1), normals are per vertex, colours the
+ * nearest voxel's (MeshIntegratorConfig: use_color, min_weight, default 1e-4).  With
+ * only_updated, blocks whose `updated` flag is clear produce no vertices (clear the flags with
+ * cg_layer_reset_updated).  Counts are always reported; host arrays (any may be NULL) are filled
+ * when the capacities suffice, otherwise CG_ERR_INVALID_ARG.  The result also stays on the device
+ * until the next cg_layer_mesh on the same context: call with NULL arrays to get the counts, then
+ * cg_mesh_fetch to copy it out without meshing again. */
+int32_t cg_layer_mesh(const cg_layer* layer, float min_weight, int32_t use_color,
+                      int32_t only_updated, size_t capacity_blocks, size_t capacity_vertices,
+                      int32_t* block_idx_xyz, uint32_t* vertex_begin, float* vertices_xyz,
+                      float* normals_xyz, uint8_t* colors_rgba, size_t* num_blocks_out,
+                      size_t* num_vertices_out);
+int32_t cg_mesh_fetch(cg_context* ctx, size_t capacity_blocks, size_t capacity_vertices,
+                      int32_t* block_idx_xyz, uint32_t* vertex_begin, float* vertices_xyz,
+                      float* normals_xyz, uint8_t* colors_rgba);
+
 /* --- incremental re-projection.  The reference rebuilds the whole global map
  * on every trigger (coxgraph/include/coxgraph/server/coxgraph_server.h:275-283 ->
  * coxgraph/src/server/visualizer/server_visualizer.cpp:123-126) although it knows which submap

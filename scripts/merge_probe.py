@@ -59,3 +59,18 @@ for frac in (0.05, 0.25, 1.0):
         best = dt if best is None else min(best, dt)
     print(f"reproject {len(moved)}/{nsub} moved: {best*1e3:.2f} ms (dirty {st.blocks_dirty} blocks, "
           f"{st.candidates} candidates, {st.blocks_folded} folds, {st.blocks_removed} removed)")
+
+# meshing the device-resident global map (N4) against downloading it
+glob.removeAllBlocks()
+getProjectedMap(subs, poses, glob)
+for it in range(3):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    mi, mb, mv, mn, mc = glob.generateMesh()
+    dt = time.perf_counter() - t0
+t0 = time.perf_counter()
+glob.download()
+dl = time.perf_counter() - t0
+print(f"generateMesh: {glob.num_blocks} blocks -> {len(mv)//3} triangles in {dt*1e3:.2f} ms "
+      f"({(len(mv) * 28) / 1e6:.1f} MB out); downloading the layer instead: {dl*1e3:.2f} ms "
+      f"({glob.num_blocks * 49152 / 1e6:.1f} MB)")

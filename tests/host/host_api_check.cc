@@ -73,6 +73,19 @@ int main(int argc, char** argv) {
   dump(out, submap);
   dump(out, combined);
   fclose(out);
+  // what the server does next (server_visualizer.cpp:123-126): mesh the merged map; and a pose
+  // update that moves nothing must leave it alone
+  cg::LayerMesh mesh;
+  cg::generateMesh(combined, &mesh);
+  if (mesh.vertices.size() % 3 != 0 || mesh.vertex_begin.size() != mesh.block_indices.size() + 1 ||
+      mesh.vertex_begin.back() != mesh.vertices.size())
+    return 70;
+  const size_t before = combined.getNumberOfAllocatedBlocks();
+  const std::vector<uint8_t> moved =
+      cg::reprojectSubmaps({&submap}, {T_M_S}, {T_M_S}, &combined);
+  if (moved[0] != 0 || combined.getNumberOfAllocatedBlocks() != before) return 71;
+  std::printf("mesh: %zu triangles over %zu blocks\n", mesh.vertices.size() / 3,
+              mesh.block_indices.size());
   std::printf("ok: submap %zu blocks, combined %zu blocks, %llu kernel launches\n",
               submap.getNumberOfAllocatedBlocks(), combined.getNumberOfAllocatedBlocks(),
               static_cast<unsigned long long>(ctx.kernelLaunches()));
