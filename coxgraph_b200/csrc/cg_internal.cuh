@@ -160,7 +160,7 @@ struct CallCounters {
   unsigned long long touched;
   unsigned long long general_pairs;
   unsigned long long segments;
-  uint32_t key_reach;  // farthest voxel offset of a point that did not fit the bundle key layout
+  int key_lo[3], key_hi[3];  // extent of the job's points (voxel indices relative to the sensor voxel)
   unsigned long long candidates;
   unsigned long long blocks_out;
   int err;
@@ -231,7 +231,12 @@ struct cg_context {
   uint32_t* d_touch_count = nullptr;  // [0] blocks touched, [1] general (voxel, ray) keys emitted
   uint32_t* d_class_count = nullptr;    // bundle size-class histogram + scatter cursors
   uint32_t* d_walk_counters = nullptr;  // [0],[1] dynamic work counters, [2] bundle key reach
-  int rel_bits_hint = 0;                // voxel field width of the bundle keys (adaptive)
+  int* d_key_bounds = nullptr;          // [6] running min / max of the bundle voxel fields
+  bool key_box_valid = false;           // bundle key layout (adaptive): union of the extents
+  int key_lo[3] = {0, 0, 0}, key_hi[3] = {0, 0, 0};  // measured by the jobs of this context
+  int key_win_lo[3] = {0, 0, 0}, key_win_hi[3] = {0, 0, 0}, key_win_jobs = 0;  // last <= 8 measured jobs
+  unsigned key_jobs = 0;
+  bool key_retry_measured = false;      // the pass that asked for a retry had measured the extent
   size_t touch_cap = 0;               // blocks the scratch holds
   bool touch_clean = false;
   unsigned long long* d_long_counter = nullptr;  // (#long segments << 32) | #sub-blocks

@@ -71,24 +71,37 @@ struct Ray {           // 24 B
 };
 constexpr uint32_t kNoRay = 0xFFFFFFFFu;
 
-// Bundle key (u64): [frame | clearing(1) | z y x (rel_bits each) | visit rank (rank_bits)].
-// z, y, x: voxel index of the point relative to the voxel holding the sensor origin; visit rank:
-// position of the point in the reference's visiting order of its frame.  The keys are sorted on
-// the bits above the rank only (keys-only radix sort, begin_bit = rank_bits): a stable sort keeps
-// equal bundles in visiting order, and the point index is recovered from (frame, rank), so no
-// value array travels through the sort.  The widths are chosen per group by the host
-// (make_key_layout): they must fit 63 bits together with the frame field.
+// Bundle key (u64): [frame | clearing(1) | z | y | x | visit rank (rank_bits)].
+// z, y, x: voxel index of the point relative to the voxel holding the sensor origin, minus the
+// lower corner `lo` of the box the layout covers, bits[a] wide; visit rank: position of the point in
+// the reference's visiting order of its frame.  The keys are sorted on the bits above the rank
+// only (keys-only radix sort, begin_bit = rank_bits): a stable sort keeps equal bundles in
+// visiting order, and the point index is recovered from (frame, rank), so no value array travels
+// through the sort.  The box is chosen per group by the host (make_key_layout) from the extent
+// earlier jobs on the context measured — a room-sized scene needs 9 + 8 + 6 bits where a cube
+// around the sensor wide enough for clearing points needs 3 x 10, one radix pass less; a point
+// outside the box is detected on the device and the group is redone with the measured extent.
 struct KeyLayout {
-  int rank_bits, rel_bits;
-  __host__ __device__ __forceinline__ int clear_bit() const { return rank_bits + 3 * rel_bits; }
+  int rank_bits;
+  int bits[3];  // x, y, z
+  int lo[3];
+  __host__ __device__ __forceinline__ int shift(int a) const {
+    return rank_bits + (a > 0 ? bits[0] : 0) + (a > 1 ? bits[1] : 0);
+  }
+  __host__ __device__ __forceinline__ int clear_bit() const {
+    return rank_bits + bits[0] + bits[1] + bits[2];
+  }
   __host__ __device__ __forceinline__ int frame_shift() const { return clear_bit() + 1; }
-  __host__ __device__ __forceinline__ int rel_offset() const { return 1 << (rel_bits - 1); }
   __device__ __forceinline__ bool clearing(uint64_t key) const { return (key >> clear_bit()) & 1; }
   __device__ __forceinline__ uint32_t frame(uint64_t key) const {
     return static_cast<uint32_t>(key >> frame_shift());
   }
   __device__ __forceinline__ uint32_t rank(uint64_t key) const {
     return static_cast<uint32_t>(key & ((1ull << rank_bits) - 1ull));
+  }
+  // voxel of the bundle relative to its frame's sensor voxel
+  __device__ __forceinline__ int rel(uint64_t key, int a) const {
+    return static_cast<int>((key >> shift(a)) & ((1ull << bits[a]) - 1ull)) + lo[a];
   }
 };
 constexpr int kMaxRelBits = 13;
@@ -135,44 +148,73 @@ struct FrameTable {
 // rank k (the scattered 8-byte writes of a wave merge in L2).
 __global__ void k_point_keys(IntegratorParams P, KeyLayout kl, const float* __restrict__ poses,
                              FrameTable ft, const float* __restrict__ pts, uint64_t total,
-                             uint64_t* __restrict__ keys, int32_t* err, uint32_t* key_reach) {
+                             uint64_t* __restrict__ keys, int32_t* err, int* key_bounds) {
+  // key_bounds != nullptr: also measure the extent of the job's points (see below)
+  __shared__ int s_bounds[6];
+  if (key_bounds && threadIdx.x < 6) s_bounds[threadIdx.x] = threadIdx.x < 3 ? 0x3FFFFFFF : -0x3FFFFFFF;
+  if (key_bounds) __syncthreads();
   const uint64_t g = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-  if (g >= total) return;
-  const int f = ft.frame_of(g);
-  const uint64_t base = ft.start(f);
-  const int n = static_cast<int>(ft.start(f + 1) - base);
-  const int i = static_cast<int>(g - base);
-  const uint32_t k = static_cast<uint32_t>(visit_rank(i, n, P.order_mode));
-  const V3 pc = load_point(pts, g);
-  bool clearing = false;
-  uint64_t key = kInvalidPointKey;
-  if (point_valid(P, pc, &clearing)) {
-    const Xform T = make_xform(poses + 7 * f);
-    const V3 pg = apply(T, pc);
-    const float lim = 524000.0f * P.voxel_size;
-    if (fabsf(pg.x) < lim && fabsf(pg.y) < lim && fabsf(pg.z) < lim && fabsf(T.t.x) < lim &&
-        fabsf(T.t.y) < lim && fabsf(T.t.z) < lim) {
-      const int rx = grid_index(pg.x, P.voxel_size_inv) - grid_index(T.t.x, P.voxel_size_inv);
-      const int ry = grid_index(pg.y, P.voxel_size_inv) - grid_index(T.t.y, P.voxel_size_inv);
-      const int rz = grid_index(pg.z, P.voxel_size_inv) - grid_index(T.t.z, P.voxel_size_inv);
-      const int ro = kl.rel_offset();
-      if (abs(rx) < ro && abs(ry) < ro && abs(rz) < ro) {
-        key = (static_cast<uint64_t>(f) << kl.frame_shift()) |
-              (static_cast<uint64_t>(clearing) << kl.clear_bit()) |
-              (static_cast<uint64_t>(rz + ro) << (kl.rank_bits + 2 * kl.rel_bits)) |
-              (static_cast<uint64_t>(ry + ro) << (kl.rank_bits + kl.rel_bits)) |
-              (static_cast<uint64_t>(rx + ro) << kl.rank_bits) | k;
+  int rx = 0, ry = 0, rz = 0;
+  bool have = false;
+  if (g < total) {
+    const int f = ft.frame_of(g);
+    const uint64_t base = ft.start(f);
+    const int n = static_cast<int>(ft.start(f + 1) - base);
+    const int i = static_cast<int>(g - base);
+    const uint32_t k = static_cast<uint32_t>(visit_rank(i, n, P.order_mode));
+    const V3 pc = load_point(pts, g);
+    bool clearing = false;
+    uint64_t key = kInvalidPointKey;
+    if (point_valid(P, pc, &clearing)) {
+      const Xform T = make_xform(poses + 7 * f);
+      const V3 pg = apply(T, pc);
+      const float lim = 524000.0f * P.voxel_size;
+      if (fabsf(pg.x) < lim && fabsf(pg.y) < lim && fabsf(pg.z) < lim && fabsf(T.t.x) < lim &&
+          fabsf(T.t.y) < lim && fabsf(T.t.z) < lim) {
+        rx = grid_index(pg.x, P.voxel_size_inv) - grid_index(T.t.x, P.voxel_size_inv);
+        ry = grid_index(pg.y, P.voxel_size_inv) - grid_index(T.t.y, P.voxel_size_inv);
+        rz = grid_index(pg.z, P.voxel_size_inv) - grid_index(T.t.z, P.voxel_size_inv);
+        have = true;
+        const uint32_t ux = static_cast<uint32_t>(rx - kl.lo[0]), uy = static_cast<uint32_t>(ry - kl.lo[1]),
+                       uz = static_cast<uint32_t>(rz - kl.lo[2]);
+        if ((ux >> kl.bits[0]) == 0 && (uy >> kl.bits[1]) == 0 && (uz >> kl.bits[2]) == 0) {
+          key = (static_cast<uint64_t>(f) << kl.frame_shift()) |
+                (static_cast<uint64_t>(clearing) << kl.clear_bit()) |
+                (static_cast<uint64_t>(uz) << kl.shift(2)) | (static_cast<uint64_t>(uy) << kl.shift(1)) |
+                (static_cast<uint64_t>(ux) << kl.shift(0)) | k;
+        } else {
+          // outside the box this group's key layout covers: the host redoes the group with the
+          // extent measured below (fewer frames per group if the bits run out)
+          atomicOr(err, kErrKeyRange);
+        }
       } else {
-        // farther from the sensor than this group's key layout reaches: the host retries with
-        // wider voxel fields (fewer frames per group if need be); key_reach tells how wide
-        atomicOr(err, kErrKeyRange);
-        atomicMax(key_reach, static_cast<uint32_t>(max(abs(rx), max(abs(ry), abs(rz)))));
+        atomicOr(err, kErrOutOfRange);
       }
-    } else {
-      atomicOr(err, kErrOutOfRange);
     }
+    keys[base + k] = key;
   }
-  keys[base + k] = key;
+  // Extent of the job's points (relative voxel indices): it sizes the key layout of later jobs.
+  // Only measured when the host asks (first job of a context, the retry after a point fell outside
+  // the box, and now and then to let the box shrink): warp minimum / maximum, then shared memory,
+  // then six atomics per CTA.
+  if (!key_bounds) return;
+  const unsigned full = 0xFFFFFFFFu;
+  const int big = 0x3FFFFFFF;
+  const int mnx = __reduce_min_sync(full, have ? rx : big), mxx = __reduce_max_sync(full, have ? rx : -big);
+  const int mny = __reduce_min_sync(full, have ? ry : big), mxy = __reduce_max_sync(full, have ? ry : -big);
+  const int mnz = __reduce_min_sync(full, have ? rz : big), mxz = __reduce_max_sync(full, have ? rz : -big);
+  if ((threadIdx.x & 31) == 0 && mnx != big) {
+    atomicMin(&s_bounds[0], mnx);
+    atomicMin(&s_bounds[1], mny);
+    atomicMin(&s_bounds[2], mnz);
+    atomicMax(&s_bounds[3], mxx);
+    atomicMax(&s_bounds[4], mxy);
+    atomicMax(&s_bounds[5], mxz);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 && s_bounds[threadIdx.x] != big) atomicMin(key_bounds + threadIdx.x, s_bounds[threadIdx.x]);
+  if (threadIdx.x >= 3 && threadIdx.x < 6 && s_bounds[threadIdx.x] != -big)
+    atomicMax(key_bounds + threadIdx.x, s_bounds[threadIdx.x]);
 }
 
 struct BundleHead {
@@ -572,7 +614,7 @@ k_scan_partials(const uint32_t* __restrict__ num_rays, const unsigned long long*
 // one CTA: exclusive scan of the partials in place; totals -> counters
 __global__ void __launch_bounds__(1024)
 k_scan_totals(const uint32_t* __restrict__ num_rays, unsigned long long* __restrict__ partials,
-              int num_partials, CallCounters* c, int32_t* err, uint32_t* key_reach) {
+              int num_partials, CallCounters* c, int32_t* err, int* key_bounds) {
   typedef cub::BlockScan<unsigned long long, 1024> Scan;
   __shared__ typename Scan::TempStorage tmp;
   unsigned long long v = static_cast<int>(threadIdx.x) < num_partials ? partials[threadIdx.x] : 0ull;
@@ -583,8 +625,12 @@ k_scan_totals(const uint32_t* __restrict__ num_rays, unsigned long long* __restr
     const int e = *err;  // a point outside the group's key layout: the host widens it / regroups
     c->err = e & kErrKeyRange;
     if (e & kErrKeyRange) *err = e & ~kErrKeyRange;
-    c->key_reach = *key_reach;
-    *key_reach = 0;
+    for (int a = 0; a < 3; ++a) {
+      c->key_lo[a] = key_bounds[a];
+      c->key_hi[a] = key_bounds[3 + a];
+      key_bounds[a] = 0x3FFFFFFF;
+      key_bounds[3 + a] = -0x3FFFFFFF;
+    }
     c->rays = *num_rays;
     c->pairs = total & 0xFFFFFFFFull;  // voxel visits (the host splits jobs that reach 2^32)
     c->segments = total >> 32;         // (ray, block) segments
@@ -777,11 +823,7 @@ __global__ void k_grazing_build(KeyLayout kl, const uint64_t* __restrict__ keys,
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
     const BundleInfo bi = bundle_info(keys, total, heads, nb, b);
     if (bi.key == kInvalidPointKey) continue;
-    const uint32_t fm = (1u << kl.rel_bits) - 1u;
-    const int ro = kl.rel_offset();
-    const int rx = static_cast<int>((bi.key >> kl.rank_bits) & fm) - ro;
-    const int ry = static_cast<int>((bi.key >> (kl.rank_bits + kl.rel_bits)) & fm) - ro;
-    const int rz = static_cast<int>((bi.key >> (kl.rank_bits + 2 * kl.rel_bits)) & fm) - ro;
+    const int rx = kl.rel(bi.key, 0), ry = kl.rel(bi.key, 1), rz = kl.rel(bi.key, 2);
     const unsigned long long gk = grazing_key(kl.frame(bi.key), rx, ry, rz);
     ray_key[b] = gk;
     if (kl.clearing(bi.key)) continue;  // only non-clearing bundles are in the set
@@ -1902,7 +1944,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
                                const IntegratorParams& P, const float* h_poses,
                                const float* d_points, const uint8_t* d_colors,
                                const uint64_t* offs, size_t f0, size_t f1,
-                               cg_integrate_stats* stats, int rel_bits_floor = 0) {
+                               cg_integrate_stats* stats, int attempt = 0) {
   cg_context* ctx = L->ctx;
   cudaStream_t s = ctx->stream;
   const size_t F = f1 - f0;
@@ -1931,15 +1973,29 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   for (size_t f = f0; f < f1; ++f) max_frame_points = std::max<size_t>(max_frame_points, offs[f + 1] - offs[f]);
   KeyLayout kl;
   kl.rank_bits = std::max(1, ceil_log2(max_frame_points));
-  // voxel field width: what the sensor range needs (x4 head room for clearing points beyond
-  // max_ray), or what an earlier job on this context turned out to need; fewer bits = fewer
-  // radix passes.  A point beyond the reach flags kErrKeyRange and the group is redone wider.
-  const int avail_bits = std::min(kMaxRelBits, (63 - frame_bits - kl.rank_bits - 1) / 3);
-  if (ctx->rel_bits_hint == 0)
-    ctx->rel_bits_hint = std::min(
-        kMaxRelBits, ceil_log2(static_cast<uint64_t>(P.max_ray * P.voxel_size_inv) + 4) + 3);
-  kl.rel_bits = std::min(avail_bits, std::max(ctx->rel_bits_hint, rel_bits_floor));
-  if (merged && kl.rel_bits < 8) {
+  // voxel fields: the box earlier jobs on this context measured (kept as a running union, with
+  // some slack around it), or — first job — a cube around the sensor sized for the sensor range
+  // with x4 head room for clearing points beyond max_ray.  Fewer bits = fewer radix passes.  A
+  // point outside the box flags kErrKeyRange and the group is redone with the measured extent.
+  constexpr int kKeySlack = 16, kKeyLimit = 8191;  // |rel| <= 8191: the anti-grazing set packs 14 bits
+  // measuring the extent costs a few hundred thousand atomics: first job, retries, every 64th job
+  const bool measure = !ctx->key_box_valid || attempt > 0 || (ctx->key_jobs++ % 64) == 63;
+  const int avail_total = 63 - frame_bits - kl.rank_bits - 1;
+  // attempt 1 follows a point outside a box that was not being measured: the wide cube again
+  if (!ctx->key_box_valid || (attempt == 1 && !ctx->key_retry_measured)) {
+    const int half = 1 << (std::min(kMaxRelBits, ceil_log2(static_cast<uint64_t>(P.max_ray * P.voxel_size_inv) + 4) + 3) - 1);
+    for (int a = 0; a < 3; ++a) {
+      kl.lo[a] = -half;
+      kl.bits[a] = ceil_log2(2 * static_cast<uint64_t>(half));
+    }
+  } else {
+    for (int a = 0; a < 3; ++a) {
+      kl.lo[a] = std::max(-kKeyLimit, ctx->key_lo[a] - kKeySlack);
+      const int hi = std::min(kKeyLimit, ctx->key_hi[a] + kKeySlack);
+      kl.bits[a] = std::max(1, ceil_log2(static_cast<uint64_t>(hi - kl.lo[a]) + 1));
+    }
+  }
+  if (merged && kl.bits[0] + kl.bits[1] + kl.bits[2] > avail_total) {
     if (F > 1) {  // fewer frames per group leave more bits for the voxel fields
       const size_t mid = f0 + F / 2;
       int32_t rc = integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, mid, stats);
@@ -1976,7 +2032,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
       StageScope sc(ctx, kStagePointKeys, 1);
       k_point_keys<<<grid_for(total, 256), 256, 0, s>>>(P, kl, ctx->group_poses, ft, pts, total,
                                                         ctx->key_a.as<uint64_t>(), L->v.err,
-                                                        ctx->d_walk_counters + 2);
+                                                        measure ? ctx->d_key_bounds : nullptr);
     }
     {
       StageScope sc(ctx, kStageBundleSort, 0);
@@ -2056,7 +2112,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
     k_scan_partials<<<sgrid, kScanThreads, 0, s>>>(d_num, ctx->ray_count.as<unsigned long long>(),
                                                    ctx->scan_partials.as<unsigned long long>());
     k_scan_totals<<<1, 1024, 0, s>>>(d_num, ctx->scan_partials.as<unsigned long long>(), sgrid,
-                                     ctx->d_counters, L->v.err, ctx->d_walk_counters + 2);
+                                     ctx->d_counters, L->v.err, ctx->d_key_bounds);
     k_scan_apply<<<sgrid, kScanThreads, 0, s>>>(d_num, ctx->ray_count.as<unsigned long long>(),
                                                 ctx->scan_partials.as<unsigned long long>(),
                                                 ctx->ray_offset.as<unsigned long long>());
@@ -2069,15 +2125,48 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   const size_t num_pairs = ctx->h_counters->pairs;
   const size_t max_pairs = env_size("CG_MAX_PAIRS", size_t(768) << 20);
   const bool key_range = (ctx->h_counters->err & kErrKeyRange) != 0;
+  // The box = union of the extents measured by the jobs of this context (relative voxel indices
+  // of every valid point).  A second union over a window of 8 jobs replaces it when it needs
+  // fewer bits, so that one outlier (a stray far return) does not widen the keys for good.
+  if (merged && ctx->h_counters->key_lo[0] <= ctx->h_counters->key_hi[0]) {
+    int lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = std::max(-kKeyLimit, ctx->h_counters->key_lo[a]);
+      hi[a] = std::min(kKeyLimit, ctx->h_counters->key_hi[a]);
+      ctx->key_lo[a] = ctx->key_box_valid ? std::min(ctx->key_lo[a], lo[a]) : lo[a];
+      ctx->key_hi[a] = ctx->key_box_valid ? std::max(ctx->key_hi[a], hi[a]) : hi[a];
+      ctx->key_win_lo[a] = ctx->key_win_jobs ? std::min(ctx->key_win_lo[a], lo[a]) : lo[a];
+      ctx->key_win_hi[a] = ctx->key_win_jobs ? std::max(ctx->key_win_hi[a], hi[a]) : hi[a];
+    }
+    ctx->key_box_valid = true;
+    if (++ctx->key_win_jobs == 8) {
+      int box_bits = 0, win_bits = 0;
+      for (int a = 0; a < 3; ++a) {
+        box_bits += ceil_log2(static_cast<uint64_t>(ctx->key_hi[a] - ctx->key_lo[a] + 2 * kKeySlack) + 1);
+        win_bits += ceil_log2(static_cast<uint64_t>(ctx->key_win_hi[a] - ctx->key_win_lo[a] + 2 * kKeySlack) + 1);
+      }
+      if (win_bits < box_bits)
+        for (int a = 0; a < 3; ++a) {
+          ctx->key_lo[a] = ctx->key_win_lo[a];
+          ctx->key_hi[a] = ctx->key_win_hi[a];
+        }
+      ctx->key_win_jobs = 0;
+    }
+  }
   if (key_range) {
-    // voxel field width that reaches the farthest point: |rel| < 2^(bits - 1)
-    const int needed = ceil_log2(uint64_t(ctx->h_counters->key_reach) + 1) + 1;
-    if (needed <= avail_bits && needed > kl.rel_bits) {
-      ctx->rel_bits_hint = std::max(ctx->rel_bits_hint, needed);  // remembered for later jobs
-      return integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, f1, stats, needed);
+    const bool measured = ctx->h_counters->key_lo[0] <= ctx->h_counters->key_hi[0];
+    bool reachable = attempt < 3;
+    for (int a = 0; a < 3 && measured; ++a)
+      reachable = reachable && ctx->h_counters->key_lo[a] >= -kKeyLimit &&
+                  ctx->h_counters->key_hi[a] <= kKeyLimit;
+    // redo the group: with the extent just measured the box covers its points; if this pass did
+    // not measure, the next one does (and may have to be redone once more)
+    if (reachable) {
+      ctx->key_retry_measured = measured;
+      return integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, f1, stats, attempt + 1);
     }
     if (F == 1) {
-      set_error("a point lies more than %d voxels from the sensor", 1 << (kl.rel_bits - 1));
+      set_error("a point lies more than %d voxels from the sensor", kKeyLimit);
       return CG_ERR_OUT_OF_RANGE;
     }
   }

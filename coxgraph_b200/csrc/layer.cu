@@ -428,6 +428,11 @@ int32_t cg_context_create(int32_t device, void* stream, cg_context** out) {
   CG_CUDA(cudaMalloc(&ctx->d_long_counter, sizeof(unsigned long long)));
   CG_CUDA(cudaMalloc(&ctx->d_select_count, sizeof(uint32_t)));
   CG_CUDA(cudaMalloc(&ctx->d_touch_count, 2 * sizeof(uint32_t)));
+  CG_CUDA(cudaMalloc(&ctx->d_key_bounds, 6 * sizeof(int)));
+  {
+    const int init[6] = {0x3FFFFFFF, 0x3FFFFFFF, 0x3FFFFFFF, -0x3FFFFFFF, -0x3FFFFFFF, -0x3FFFFFFF};
+    CG_CUDA(cudaMemcpy(ctx->d_key_bounds, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
   CG_CUDA(cudaMalloc(&ctx->d_walk_counters, 4 * sizeof(uint32_t)));
   CG_CUDA(cudaMemsetAsync(ctx->d_walk_counters, 0, 4 * sizeof(uint32_t), ctx->stream));
   CG_CUDA(cudaMalloc(&ctx->d_class_count, 128 * sizeof(uint32_t)));
@@ -455,6 +460,7 @@ int32_t cg_context_destroy(cg_context* ctx) {
   if (ctx->d_select_count) cudaFree(ctx->d_select_count);
   if (ctx->d_touch_count) cudaFree(ctx->d_touch_count);
   if (ctx->d_walk_counters) cudaFree(ctx->d_walk_counters);
+  if (ctx->d_key_bounds) cudaFree(ctx->d_key_bounds);
   if (ctx->d_class_count) cudaFree(ctx->d_class_count);
   if (ctx->d_work_counter) cudaFree(ctx->d_work_counter);
   if (ctx->d_long_counter) cudaFree(ctx->d_long_counter);

@@ -95,6 +95,17 @@ __device__ __forceinline__ float interp_member(const float q[8], const float d[8
   acc = acc + q[7] * (((((((-d[0] + d[1]) + d[2]) + -d[3]) + d[4]) + -d[5]) + -d[6]) + d[7]);
   return acc;
 }
+// Same value, fewer instructions where the eight taps agree (carved free space: every distance is
+// +truncation, every colour the default): all differences of the table are then exactly 0, so
+// q . (M . data) = 1 * d0 + q1 * 0 + ... = d0 bit for bit.  (A zero d0 takes the long way: the sign
+// of a zero result depends on the signs of q.)
+__device__ __forceinline__ float interp_member_fast(const float q[8], const float d[8]) {
+  bool same = true;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) same = same && (d[i] == d[0]);
+  if (same && d[0] != 0.0f) return d[0];
+  return interp_member(q, d);
+}
 __device__ __forceinline__ uint32_t trunc_u8(float v) {
   if (!(v > 0.0f)) return 0u;
   if (v >= 255.0f) return 255u;
@@ -182,15 +193,21 @@ __device__ __forceinline__ bool resample_voxel(const LayerView& A, const SlotTab
                                 center_coord(v[2], A.voxel_size)};
         const V3 o = (p - vpos) * A.voxel_size_inv;
         const float q[8] = {1.0f, o.x, o.y, o.z, o.x * o.y, o.y * o.z, o.z * o.x, o.x * o.y * o.z};
-        out.d = interp_member(q, dd);
-        out.w = interp_member(q, ww);
-        float ch[8];
-        uint32_t rgba = 0;
+        out.d = interp_member_fast(q, dd);
+        out.w = interp_member_fast(q, ww);
+        bool same_colour = true;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
+        for (int i = 1; i < 8; ++i) same_colour = same_colour && (cc[i] == cc[0]);
+        uint32_t rgba = cc[0];  // eight equal colours interpolate to themselves, channel by channel
+        if (!same_colour) {
+          float ch[8];
+          rgba = 0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) ch[i] = static_cast<float>((cc[i] >> (8 * s)) & 255u);
-          rgba |= trunc_u8(interp_member(q, ch)) << (8 * s);
+          for (int s = 0; s < 4; ++s) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ch[i] = static_cast<float>((cc[i] >> (8 * s)) & 255u);
+            rgba |= trunc_u8(interp_member(q, ch)) << (8 * s);
+          }
         }
         out.c = rgba;
         return true;

@@ -54,27 +54,52 @@ def to_bytes(val, unit):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
 
 
-traffic, lines = {}, []
-for r in rows[2:]:
-    name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0].strip()
-    lines.append(f"## {name}\n")
-    lines.append("| metric | value |\n|---|---|")
-    for w in want:
-        if w in ix:
-            lines.append(f"| {w} | {r[ix[w]]} {units[ix[w]]} |")
-    stalls = []
-    for h in hdr:
-        if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio"):
-            try:
-                stalls.append((float(r[ix[h]]), h.replace("smsp__average_warps_issue_stalled_", "")
-                               .replace("_per_issue_active.ratio", "")))
-            except ValueError:
-                pass
-    top = ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)[:4])
-    lines.append(f"| top stalls (warps per issue) | {top} |\n")
-    if name in STAGE and STAGE[name] not in traffic:
-        traffic[STAGE[name]] = to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + \
-            to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
+def summarise(rows, hdr, units, traffic):
+    ix = {h: i for i, h in enumerate(hdr)}
+    lines = []
+    for r in rows:
+        name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").strip()
+        lines.append(f"## {name}\n")
+        name = name.split("<")[0]
+        lines.append("| metric | value |\n|---|---|")
+        for w in want:
+            if w in ix:
+                lines.append(f"| {w} | {r[ix[w]]} {units[ix[w]]} |")
+        stalls = []
+        for h in hdr:
+            if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio"):
+                try:
+                    stalls.append((float(r[ix[h]]), h.replace("smsp__average_warps_issue_stalled_", "")
+                                   .replace("_per_issue_active.ratio", "")))
+                except ValueError:
+                    pass
+        top = ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)[:4])
+        lines.append(f"| top stalls (warps per issue) | {top} |\n")
+        if traffic is not None and name in STAGE and STAGE[name] not in traffic:
+            traffic[STAGE[name]] = \
+                to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + \
+                to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
+    return lines
+
+
+traffic = {}
+lines = summarise(rows[2:], hdr, units, traffic)
+# second capture: the server-side kernels (40-submap projection, re-projection, meshing)
+server = [os.path.join(go, f"prof_{k}_{tag}.ncu-rep") for k in ("merge", "mesh")]
+if all(os.path.exists(r) for r in server):
+    lines.append("# server side: `ncu --set full ... python scripts/merge_probe.py 40` — the first "
+                 "projection of 40 C2 submaps (`-k regex:k_project_batch|k_mark_batch|"
+                 "k_list_candidates -c 3`) and the meshing of the projected map (`-k k_mesh_blocks "
+                 "-c 2`: count pass, write pass)\n")
+    for rep2 in server:
+        raw2 = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True,
+                              text=True).stdout
+        rows2 = list(csv.reader(io.StringIO(raw2)))
+        lines += summarise(rows2[2:], rows2[0], rows2[1], None)
+    plain = os.path.join(go, f"merge_plain_{tag}.log")
+    if os.path.exists(plain):
+        lines.append("Un-instrumented run of the same script:\n\n```\n" + open(plain).read().strip() +
+                     "\n```\n")
 with open(os.path.join(out_dir, f"{label}_ncu_top_kernels.md"), "w") as f:
     f.write(f"# {label}: ncu --set full of the library's own kernels (commit {head})\n\n"
             "`ncu --set full --clock-control none --import-source on -k regex:<kernels> -s 27 -c 10 "

@@ -11,5 +11,12 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:^k_|^Device"
 ncu --set full --clock-control none --import-source on \
     -k "regex:k_block_accumulate|k_walk_segments|k_fold_wide|k_point_keys|k_voxel_update|k_long_finish|k_gather_sorted|k_resample_merge|k_fold_bundles|k_finalize_blocks" \
     -s 27 -c 10 -o gpurun_out/prof_$tag -f python bench.py $ARGS > gpurun_out/ncu_full_$tag.log 2>&1
+# server side: projection of 40 submaps, incremental re-projection, meshing (scripts/merge_probe.py)
+python scripts/merge_probe.py 40 > gpurun_out/merge_plain_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on \
+    -k "regex:k_project_batch|k_mark_batch|k_list_candidates" \
+    -c 3 -o gpurun_out/prof_merge_$tag -f python scripts/merge_probe.py 40 > gpurun_out/ncu_merge_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:k_mesh_blocks" \
+    -c 2 -o gpurun_out/prof_mesh_$tag -f python scripts/merge_probe.py 40 > gpurun_out/ncu_mesh_$tag.log 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/smi_$tag.csv
 echo profile_round done

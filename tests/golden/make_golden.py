@@ -90,9 +90,37 @@ def build_mesh_case():
                 colors_sha256=digest(cols))
 
 
+def fused_golden_layer(name="merged_5cm"):
+    """The oracle layer of a layer fixture, re-fused from the stored inputs."""
+    g = np.load(os.path.join(HERE, f"{name}.npz"))
+    spec = CASES[name]
+    cfg = orc.default_config(**spec["cfg"])
+    L = orc.Layer(spec["voxel_size"])
+    offs = g["offsets"].astype(int)
+    for f in range(len(g["poses"])):
+        L.integrate(cfg, g["poses"][f], g["points"][offs[f]:offs[f + 1]], g["colors"][offs[f]:offs[f + 1]])
+    return L
+
+
+def build_layer_mesh_case():
+    """MeshIntegrator fixture: marching cubes over the fused merged_5cm layer (oracle)."""
+    begin, v, n, c = fused_golden_layer().mesh()
+    return dict(num_vertices=int(len(v)), begin_sha256=digest(begin), vertices_sha256=digest(v),
+                normals_sha256=digest(n), colors_sha256=digest(c))
+
+
 if __name__ == "__main__":
+    if "--only-layer-mesh" in sys.argv:  # add the newest fixture without touching the others
+        with open(os.path.join(HERE, "digests.json")) as f:
+            metas = json.load(f)
+        metas["layer_mesh"] = build_layer_mesh_case()
+        with open(os.path.join(HERE, "digests.json"), "w") as f:
+            json.dump(metas, f, indent=1, sort_keys=True)
+        print("layer_mesh", metas["layer_mesh"])
+        sys.exit(0)
     metas = {name: build_case(name, spec) for name, spec in CASES.items()}
     metas["mesh_frames"] = build_mesh_case()
+    metas["layer_mesh"] = build_layer_mesh_case()
     with open(os.path.join(HERE, "digests.json"), "w") as f:
         json.dump(metas, f, indent=1, sort_keys=True)
     for k, v in metas.items():

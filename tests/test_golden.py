@@ -88,3 +88,28 @@ def test_cuda_reproduces_golden(gpu_ctx, name, batch):
         _check_sample(gv, g["merge_sample_pos"], g["merge_sample_vox"], name + " merge")
         G.close()
     L.close()
+
+
+def _mesh_digests(begin, v, n, c):
+    return dict(num_vertices=int(len(v)), begin_sha256=_sha(begin), vertices_sha256=_sha(v),
+                normals_sha256=_sha(n), colors_sha256=_sha(c))
+
+
+def test_oracle_reproduces_golden_layer_mesh():
+    """Marching cubes over the fused merged_5cm layer: frozen digests of the oracle's output."""
+    from tests.golden.make_golden import fused_golden_layer
+    assert _mesh_digests(*fused_golden_layer().mesh()) == META["layer_mesh"]
+    assert META["layer_mesh"]["num_vertices"] > 1000
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_layer_mesh(gpu_ctx):
+    from coxgraph_b200 import Layer
+    from tests.golden.make_golden import fused_golden_layer
+    idx, vox, flags = fused_golden_layer().download()
+    L = Layer(gpu_ctx, 0.05, max_blocks=4096)
+    L.upload(idx, vox, flags)
+    gi, begin, v, n, c = L.generateMesh()
+    assert np.array_equal(gi, idx)
+    assert _mesh_digests(begin, v, n, c) == META["layer_mesh"]
+    L.close()

@@ -69,9 +69,9 @@ def test_batch_pipelined_transfer(gpu_ctx, monkeypatch):
 
 
 def test_far_points_regroup_then_out_of_range(gpu_ctx):
-    """A batch packs fewer bits per voxel axis into its bundle keys than a single frame; a point
-    beyond that reach makes the library regroup (fewer frames per group) instead of failing, and
-    only a point beyond the single-frame reach (4096 voxels) is an error."""
+    """The bundle keys cover the box of voxels (relative to the sensor) that earlier jobs measured;
+    a point outside it makes the library redo the group with the measured extent instead of
+    failing, and only a point more than 8191 voxels from the sensor is an error."""
     from coxgraph_b200 import Layer, TsdfIntegrator, capi
     frames = util.small_frames(5, stride=8)
     T, p, c = frames[2]
@@ -84,7 +84,7 @@ def test_far_points_regroup_then_out_of_range(gpu_ctx):
     _, gcfg = util.make_cfgs()
     gl = Layer(gpu_ctx, 0.05, max_blocks=2048)
     p2 = p.copy()
-    p2[7] = (0.0, 0.0, 300.0)
+    p2[7] = (0.0, 0.0, 1000.0)         # 20000 voxels: some axis is beyond 8191 whatever the pose
     with pytest.raises(capi.CgError) as e:
         TsdfIntegrator(gcfg, gl).integratePointCloud(T, p2, c)
     assert e.value.status == capi.CG_ERR_OUT_OF_RANGE
