@@ -440,28 +440,56 @@ __global__ void k_mark_batch(const BatchSubmap* __restrict__ desc, int n, uint32
       }
 }
 
-__global__ void k_mask_counts(const unsigned long long* __restrict__ map_mask, uint32_t cap,
-                              uint32_t* __restrict__ counts) {
-  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h < cap) counts[h] = __popcll(map_mask[h]);
-}
-
-// Explicit candidate list: candidate c = (map entry, submap of the batch, rank among the entry's
-// candidates); c runs over [cand_base[h], cand_base[h + 1]) in ascending submap order.
+// Candidates are listed rank-major: first the lowest-numbered submap of every destination block,
+// then the second, ... so that the candidates of one block are handed out far apart in time and a
+// candidate rarely has to wait for its predecessor (block-major order made ~12 CTAs resample the
+// same block side by side and then queue up for the fold).  rank_count[k] = number of blocks with
+// more than k candidates; the position inside a rank comes from an atomic cursor — the list order
+// inside a rank is arbitrary, the result is not: the fold order per block is fixed by the ranks.
 struct BatchCand {
-  uint32_t entry;
+  uint32_t entry;     // scratch map entry = destination block
   uint32_t sub_rank;  // submap | rank << 8
 };
-__global__ void k_list_candidates(const unsigned long long* __restrict__ map_mask,
-                                  const uint32_t* __restrict__ cand_base, uint32_t cap,
-                                  BatchCand* __restrict__ list, CallCounters* counters) {
+struct RankTable {
+  uint32_t count[kBatchMax];
+  uint32_t cursor[kBatchMax];
+  uint32_t total;
+};
+__global__ void k_rank_hist(const unsigned long long* __restrict__ map_mask, uint32_t cap,
+                            RankTable* table) {
+  __shared__ uint32_t s_cnt[kBatchMax];
+  if (threadIdx.x < kBatchMax) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
   const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h == 0) atomicAdd(&counters->candidates, 1ull * cand_base[cap]);
+  const int p = h < cap ? __popcll(map_mask[h]) : 0;
+  for (int k = 0; k < p; ++k) atomicAdd(&s_cnt[k], 1u);
+  __syncthreads();
+  if (threadIdx.x < kBatchMax && s_cnt[threadIdx.x]) atomicAdd(&table->count[threadIdx.x], s_cnt[threadIdx.x]);
+}
+__global__ void k_list_candidates(const unsigned long long* __restrict__ map_mask, uint32_t cap,
+                                  RankTable* table, BatchCand* __restrict__ list,
+                                  CallCounters* counters) {
+  __shared__ uint32_t s_base[kBatchMax + 1];
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int k = 0; k < kBatchMax; ++k) {
+      s_base[k] = run;
+      run += table->count[k];
+    }
+    s_base[kBatchMax] = run;
+    if (blockIdx.x == 0) {
+      table->total = run;
+      atomicAdd(&counters->candidates, 1ull * run);
+    }
+  }
+  __syncthreads();
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= cap) return;
   unsigned long long m = map_mask[h];
-  uint32_t c = cand_base[h];
-  for (uint32_t k = 0; m; ++k, ++c, m &= m - 1)
-    list[c] = BatchCand{h, static_cast<uint32_t>(__ffsll(static_cast<long long>(m)) - 1) | (k << 8)};
+  for (uint32_t k = 0; m; ++k, m &= m - 1) {
+    const uint32_t pos = s_base[k] + atomicAdd(&table->cursor[k], 1u);
+    list[pos] = BatchCand{h, static_cast<uint32_t>(__ffsll(static_cast<long long>(m)) - 1) | (k << 8)};
+  }
 }
 
 // One CTA per candidate, handed out in ascending order by an atomic counter.  The resampled block
@@ -475,7 +503,7 @@ __global__ void k_list_candidates(const unsigned long long* __restrict__ map_mas
 __global__ void __launch_bounds__(kMergeThreads)
 k_project_batch(const BatchSubmap* __restrict__ desc, LayerView B,
                 const uint64_t* __restrict__ map_keys, const BatchCand* __restrict__ list,
-                const uint32_t* __restrict__ cand_base, uint32_t cap, unsigned long long* done,
+                const RankTable* __restrict__ table, unsigned long long* done,
                 uint32_t* work_counter, CallCounters* counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_d = reinterpret_cast<float*>(smem_raw);  // resampled block, planar
@@ -484,7 +512,7 @@ k_project_batch(const BatchSubmap* __restrict__ desc, LayerView B,
   SlotTable& tab = *reinterpret_cast<SlotTable*>(s_c + kVoxelsPerBlock);
   __shared__ uint32_t s_cand;
   __shared__ int s_slot;
-  const uint32_t num_cand = cand_base[cap];
+  const uint32_t num_cand = table->total;
   for (;;) {
     __syncthreads();  // previous iteration done with the shared state
     if (threadIdx.x == 0) s_cand = atomicAdd(work_counter, 1u);
@@ -626,30 +654,24 @@ static int32_t project_batch(const cg_layer* const* submaps, const BatchSubmap* 
   size_t cap = 4096;
   while (cap < 2 * cand_bound) cap <<= 1;
   CG_CUDA(ctx->cand_keys.reserve(cap * sizeof(uint64_t)));
-  // masks, then the per-entry "done" masks of the fused fold, then the counts (one memset clears all)
-  CG_CUDA(ctx->cand_list.reserve(2 * cap * sizeof(unsigned long long) + (cap + 1) * sizeof(uint32_t)));
-  CG_CUDA(ctx->stage_c.reserve((cap + 1) * sizeof(uint32_t)));            // cand_base
+  // masks, then the per-entry "done" masks of the fused fold, then the rank table (one memset
+  // clears all)
+  const size_t scratch_bytes = 2 * cap * sizeof(unsigned long long) + sizeof(RankTable);
+  CG_CUDA(ctx->cand_list.reserve(scratch_bytes));
   CG_CUDA(ctx->merge_cands.reserve(cand_bound * sizeof(BatchCand)));
   unsigned long long* masks = ctx->cand_list.as<unsigned long long>();
   unsigned long long* done = masks + cap;
-  uint32_t* counts = reinterpret_cast<uint32_t*>(done + cap);
-  size_t tmp_scan = 0;
-  CG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, counts, ctx->stage_c.as<uint32_t>(),
-                                        static_cast<int>(cap + 1), s));
-  CG_CUDA(ctx->cub_tmp.reserve(tmp_scan));
+  RankTable* table = reinterpret_cast<RankTable*>(done + cap);
   {
     StageScope sc(ctx, kStageMergeMark, 3);
     CG_CUDA(cudaMemsetAsync(ctx->cand_keys.p, 0xFF, cap * sizeof(uint64_t), s));
-    CG_CUDA(cudaMemsetAsync(masks, 0, 2 * cap * sizeof(unsigned long long) + (cap + 1) * sizeof(uint32_t), s));
+    CG_CUDA(cudaMemsetAsync(masks, 0, scratch_bytes, s));
     CG_CUDA(cudaMemsetAsync(ctx->d_work_counter, 0, sizeof(uint32_t), s));
     k_mark_batch<<<grid_for(total, 128), 128, 0, s>>>(
         d_desc + i0, n, total, G->v.block_size, ctx->cand_keys.as<uint64_t>(), masks,
         static_cast<uint32_t>(cap - 1), G->v.err, filter_keys, filter_mask);
-    k_mask_counts<<<grid_for(cap, 256), 256, 0, s>>>(masks, static_cast<uint32_t>(cap), counts);
-    CG_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp_scan, counts,
-                                          ctx->stage_c.as<uint32_t>(), static_cast<int>(cap + 1), s));
-    k_list_candidates<<<grid_for(cap, 256), 256, 0, s>>>(masks, ctx->stage_c.as<uint32_t>(),
-                                                         static_cast<uint32_t>(cap),
+    k_rank_hist<<<grid_for(cap, 256), 256, 0, s>>>(masks, static_cast<uint32_t>(cap), table);
+    k_list_candidates<<<grid_for(cap, 256), 256, 0, s>>>(masks, static_cast<uint32_t>(cap), table,
                                                          ctx->merge_cands.as<BatchCand>(),
                                                          ctx->d_counters);
   }
@@ -665,9 +687,8 @@ static int32_t project_batch(const cg_layer* const* submaps, const BatchSubmap* 
     const unsigned grid = static_cast<unsigned>(
         std::min<size_t>(cand_bound, static_cast<size_t>(ctx->num_sms) * 2));
     k_project_batch<<<grid, kMergeThreads, smem, s>>>(
-        d_desc + i0, G->v, ctx->cand_keys.as<uint64_t>(), ctx->merge_cands.as<BatchCand>(),
-        ctx->stage_c.as<uint32_t>(), static_cast<uint32_t>(cap), done, ctx->d_work_counter,
-        ctx->d_counters);
+        d_desc + i0, G->v, ctx->cand_keys.as<uint64_t>(), ctx->merge_cands.as<BatchCand>(), table,
+        done, ctx->d_work_counter, ctx->d_counters);
   }
   CG_CUDA(cudaGetLastError());
   return CG_OK;
