@@ -10,6 +10,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
 
 #include <string>
 #include <vector>
@@ -130,16 +133,23 @@ struct DevBuf {
   size_t cap = 0;
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    const bool trace = getenv("CG_TRACE_ALLOC") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t old_cap = cap;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
+    size_t want = bytes + bytes / 2 + 256;  // geometric growth: every reallocation is a device-wide stall
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
       want = bytes;
       e = cudaMalloc(&p, want);
     }
     if (e == cudaSuccess) cap = want;
+    if (trace) {
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      fprintf(stderr, "[cg] scratch %zu -> %zu bytes in %.2f ms\n", old_cap, want, ms);
+    }
     return e;
   }
   void release() {

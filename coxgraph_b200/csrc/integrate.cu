@@ -2162,6 +2162,10 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
     // redo the group: with the extent just measured the box covers its points; if this pass did
     // not measure, the next one does (and may have to be redone once more)
     if (reachable) {
+      if (getenv("CG_TRACE_KEYS"))
+        fprintf(stderr, "[cg] bundle-key box exceeded (attempt %d, measured %d): box x[%d,%d] y[%d,%d] z[%d,%d]\n",
+                attempt, int(measured), ctx->key_lo[0], ctx->key_hi[0], ctx->key_lo[1], ctx->key_hi[1],
+                ctx->key_lo[2], ctx->key_hi[2]);
       ctx->key_retry_measured = measured;
       return integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, f1, stats, attempt + 1);
     }

@@ -168,7 +168,15 @@ __device__ __forceinline__ bool resample_voxel(const LayerView& A, const SlotTab
           slot = lookup_block(A, tab, nb[0], nb[1], nb[2]);
           if (slot < 0) ok = false;
         }
-        tap[i] = A.dist_plane(slot < 0 ? 0 : slot) + (nv[0] + kVps * (nv[1] + kVps * nv[2]));
+        // a voxel index of -1 left by the epsilon of the grid index (see the oracle's
+        // interp_trilinear): inside the block's array upstream's linear index is a definite voxel;
+        // outside it (undefined behaviour upstream) the trilinear attempt fails
+        int lin = nv[0] + kVps * (nv[1] + kVps * nv[2]);
+        if (lin < 0 || lin >= kVoxelsPerBlock) {
+          ok = false;
+          lin = 0;
+        }
+        tap[i] = A.dist_plane(slot < 0 ? 0 : slot) + lin;
       }
     }
     if (ok) {

@@ -132,8 +132,8 @@ class Layer:
         self.last_blocks_out = 0
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_layer_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None:  # module globals are gone at shutdown
+            _lib.orc_layer_destroy(self._h)
             self._h = None
 
     def clear(self):

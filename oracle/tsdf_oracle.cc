@@ -765,7 +765,14 @@ bool interp_trilinear(const orc_layer& L, V3 pos, Voxel* out) {
       q[6] = o.z * o.x;
       q[7] = o.x * o.y * o.z;
     }
-    const Voxel& v = blk->voxels[linear_of(nvi)];
+    // The epsilon of getGridIndexFromPoint can leave a voxel index of -1 that the shift above does
+    // not touch (pos within 1e-6 of a block face, centre offset >= 0).  Upstream then indexes
+    // voxels_[x + 16 (y + 16 z)] with it: inside the array that is a definite (if unintended)
+    // voxel and is kept; outside the array it is undefined behaviour — defined here as
+    // "not observed", i.e. the trilinear attempt fails and the nearest-neighbour fallback decides.
+    const int lin = linear_of(nvi);
+    if (lin < 0 || lin >= kVoxelsPerBlock) return false;
+    const Voxel& v = blk->voxels[lin];
     vox[i] = &v;
     if (!(v.weight > kEps)) return false;  // utils::isObservedVoxel
   }

@@ -57,6 +57,33 @@ def test_merge_matches_oracle(gpu_ctx, pose_id):
     gb.close()
 
 
+@pytest.mark.parametrize("src_voxel,dst_voxel", [(0.05, 0.10), (0.10, 0.05), (0.05, 0.04)])
+def test_merge_between_different_voxel_sizes(gpu_ctx, src_voxel, dst_voxel):
+    """mergeLayerAintoLayerB resamples, so the two layers need not share a grid: coarser and finer
+    destinations, single merge and batched projection (the slot table of the gather covers 4^3
+    source blocks; a coarser destination reaches beyond it and takes the hash path)."""
+    from coxgraph_b200 import Layer, getProjectedMap, mergeLayerAintoLayerB
+    from oracle import oracle_py as orc
+    ocfg, _ = util.make_cfgs()
+    subs_o = [_submap(orc, ocfg, k % 2, k, voxel_size=src_voxel) for k in range(3)]
+    subs_g = [_to_gpu(gpu_ctx, o) for o in subs_o]
+    poses = [POSES[2] / np.linalg.norm(POSES[2][:4]).astype(np.float32), POSES[3], POSES[4].copy()]
+    poses[2][:4] /= np.linalg.norm(poses[2][:4])
+    poses = [np.asarray(p, np.float32) for p in poses]
+    ob, gb = orc.Layer(dst_voxel), Layer(gpu_ctx, dst_voxel, max_blocks=16384)
+    ob.merge_from(subs_o[0], poses[0])
+    st = mergeLayerAintoLayerB(subs_g[0], poses[0], gb)
+    assert st.blocks_out == ob.last_blocks_out
+    util.compare_layers(gb.download(), ob.download(), "single merge", check_flags=True)
+    og, gg = orc.Layer(dst_voxel), Layer(gpu_ctx, dst_voxel, max_blocks=16384)
+    for o, T in zip(subs_o, poses):
+        og.merge_from(o, T)
+    getProjectedMap(subs_g, np.stack(poses), gg)
+    util.compare_layers(gg.download(), og.download(), "projection", check_flags=True)
+    for L in subs_g + [gb, gg]:
+        L.close()
+
+
 def test_dense_submaps_project_matches_oracle(gpu_ctx):
     """Submaps fused from full 640x480 frames (dense truncation bands, ~100 blocks each) projected
     into one global layer under oblique poses, batched on the device, against the oracle's

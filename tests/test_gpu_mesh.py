@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 def _same_mesh(layer, min_weight=1e-4, use_color=True, only_updated=False, what="mesh"):
     """Mesh `layer` on the GPU and its downloaded copy through the oracle; compare exactly."""
     idx, vox, flags = layer.download()
-    o = orc.Layer(0.05)
+    o = orc.Layer(layer.voxel_size)
     o.upload(idx, vox, flags)
     gi, gb, gv, gn, gc = layer.generateMesh(min_weight, use_color, only_updated)
     ob, ov, on, oc = o.mesh(min_weight, use_color, only_updated)
@@ -76,6 +76,22 @@ def test_mesh_of_a_projected_map_matches_oracle(gpu_ctx):
     assert len(out[2]) > 10000
     for L in subs + [g]:
         L.close()
+
+
+def test_mesh_of_fine_voxels_matches_oracle(gpu_ctx):
+    """configs[3] shape: 2 cm voxels, 1280x720 (sub-sampled), 6 cm truncation."""
+    import torch
+    from coxgraph_b200 import Layer, TsdfIntegrator, TsdfIntegratorConfig, synth
+    cfg = TsdfIntegratorConfig(use_const_weight=1, method=1, default_truncation_distance=0.06,
+                               max_ray_length_m=3.0)
+    L = Layer(gpu_ctx, 0.02, max_blocks=16384)
+    integ = TsdfIntegrator(cfg, L)
+    for (T, pts, cols) in synth.submap_frames(2, 0, 2, cam=synth.CAM_1280x720,
+                                              device=torch.device("cuda", 0), stride=4):
+        integ.integratePointCloud(T, pts, cols)
+    out = _same_mesh(L, what="2 cm layer")
+    assert len(out[2]) > 10000
+    L.close()
 
 
 def test_mesh_of_an_analytic_sphere_is_closed(gpu_ctx):
