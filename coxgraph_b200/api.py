@@ -173,7 +173,7 @@ class Layer:
         words = np.ascontiguousarray(data, np.uint32).reshape(len(idx), 3 * capi.VOXELS_PER_BLOCK)
         capi.check(capi.load().cg_layer_deserialize(self._h, len(idx), _ptr(idx), _ptr(words)))
 
-    def generateMesh(self, min_weight=1e-4, use_color=True, only_updated=False):
+    def generateMesh(self, min_weight=1e-4, use_color=True, only_updated=False, fetch=True):
         """voxblox::MeshIntegrator<TsdfVoxel>::generateMesh on the device (marching cubes per
         block) -> (block_idx int32 [B,3] in (z,y,x) order, vertex_begin u32 [B+1], vertices f32
         [V,3], normals f32 [V,3], colors u8 [V,4]); three consecutive vertices = one triangle."""
@@ -182,6 +182,8 @@ class Layer:
         capi.check(lib.cg_layer_mesh(self._h, min_weight, int(use_color), int(only_updated), 0, 0,
                                      None, None, None, None, None, C.byref(nb), C.byref(nv)))
         B, V = nb.value, nv.value
+        if not fetch:  # the mesh stays on the device (cg_mesh_fetch copies it out later)
+            return B, V
         idx = np.zeros((B, 3), np.int32)
         begin = np.zeros(B + 1, np.uint32)
         v = np.zeros((V, 3), np.float32)

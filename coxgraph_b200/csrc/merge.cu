@@ -152,7 +152,37 @@ __device__ __forceinline__ bool resample_voxel(const LayerView& A, const SlotTab
     if (moved) base_slot = lookup_block(A, tab, b[0], b[1], b[2]);
     bool ok = base_slot >= 0;
     const float* tap[8];  // distance plane address of every tap (weight / colour at fixed offsets)
-    if (ok) {
+    // Tap addresses.  Common case (every base index in [0, 15]): a tap leaves the base block only
+    // on axes where the base index is 15, so at most the 7 upper neighbour blocks are looked up —
+    // none at all for most voxels — and the offsets come from two values per axis.
+    const bool common = static_cast<unsigned>(v[0]) < kVps && static_cast<unsigned>(v[1]) < kVps &&
+                        static_cast<unsigned>(v[2]) < kVps;
+    if (ok && common) {
+      const bool cx = v[0] == kVps - 1, cy = v[1] == kVps - 1, cz = v[2] == kVps - 1;
+      const int s000 = base_slot;
+      int s100 = -1, s010 = -1, s001 = -1, s110 = -1, s101 = -1, s011 = -1, s111 = -1;
+      if (cx) s100 = lookup_block(A, tab, b[0] + 1, b[1], b[2]);
+      if (cy) s010 = lookup_block(A, tab, b[0], b[1] + 1, b[2]);
+      if (cz) s001 = lookup_block(A, tab, b[0], b[1], b[2] + 1);
+      if (cx && cy) s110 = lookup_block(A, tab, b[0] + 1, b[1] + 1, b[2]);
+      if (cx && cz) s101 = lookup_block(A, tab, b[0] + 1, b[1], b[2] + 1);
+      if (cy && cz) s011 = lookup_block(A, tab, b[0], b[1] + 1, b[2] + 1);
+      if (cx && cy && cz) s111 = lookup_block(A, tab, b[0] + 1, b[1] + 1, b[2] + 1);
+      ok = !((cx && s100 < 0) || (cy && s010 < 0) || (cz && s001 < 0) || (cx && cy && s110 < 0) ||
+             (cx && cz && s101 < 0) || (cy && cz && s011 < 0) || (cx && cy && cz && s111 < 0));
+      const int xo[2] = {v[0], cx ? 0 : v[0] + 1};
+      const int yo[2] = {kVps * v[1], cy ? 0 : kVps * (v[1] + 1)};
+      const int zo[2] = {kVps * kVps * v[2], cz ? 0 : kVps * kVps * (v[2] + 1)};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int tx = (i >> 2) & 1, ty = (i >> 1) & 1, tz = i & 1;  // compile-time after unrolling
+        const bool kx = tx && cx, ky = ty && cy, kz = tz && cz;
+        const int slot = kz ? (ky ? (kx ? s111 : s011) : (kx ? s101 : s001))
+                            : (ky ? (kx ? s110 : s010) : (kx ? s100 : s000));
+        tap[i] = A.dist_plane(slot < 0 ? 0 : slot) + (xo[tx] + yo[ty] + zo[tz]);
+      }
+    } else if (ok) {
+      // a base index of -1 or 16 left by the epsilon of the grid index: the general walk
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         int nv[3] = {v[0] + ((i >> 2) & 1), v[1] + ((i >> 1) & 1), v[2] + (i & 1)};

@@ -30,8 +30,9 @@ ls = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "launch_summa
                      os.path.join(go, f"launches_{tag}.csv")], capture_output=True, text=True).stdout
 with open(os.path.join(out_dir, f"{label}_launches.md"), "w") as f:
     f.write(f"# {label}: launch list of C2 steps (commit {head})\n\n"
-            "`ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^k_|^Device' "
-            "-s 190 -c 70 python bench.py --steps 2 --warmup 3 --profile-mode`\n\n"
+            "`ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include cg_step/ "
+            "-k 'regex:^k_|^Device' python bench.py --steps 2 --warmup 10 --profile-mode` — the NVTX "
+            "range brackets exactly one un-instrumented C2 step (bench.py).\n\n"
             "Per-launch times under ncu are cold-cache and serialised: compare the SHARES with "
             "`stages_ms_per_step` of the bench line, not the absolutes.\n\n" + ls)
 
@@ -102,9 +103,9 @@ if all(os.path.exists(r) for r in server):
                      "\n```\n")
 with open(os.path.join(out_dir, f"{label}_ncu_top_kernels.md"), "w") as f:
     f.write(f"# {label}: ncu --set full of the library's own kernels (commit {head})\n\n"
-            "`ncu --set full --clock-control none --import-source on -k regex:<kernels> -s 27 -c 10 "
-            "python bench.py --steps 2 --warmup 3 --profile-mode` — one launch per kernel, one C2 "
-            "step (25 x 640x480 frames).\n\n" + "\n".join(lines))
+            "`ncu --set full --clock-control none --import-source on --nvtx --nvtx-include cg_step/ "
+            "-k regex:<kernels> python bench.py --steps 2 --warmup 10 --profile-mode` — the kernels of "
+            "one C2 step (25 x 640x480 frames).\n\n" + "\n".join(lines))
 with open(os.path.join(out_dir, "traffic.json"), "w") as f:
     json.dump({"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch, from "
                            f"profiles/{label}_ncu_top_kernels.md", **traffic}, f, indent=1)

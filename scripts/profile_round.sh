@@ -4,13 +4,15 @@
 #   gpurun --timeout 1200 -- 'bash scripts/profile_round.sh r1'
 tag=${1:-r1}
 mkdir -p gpurun_out
-ARGS="--steps 2 --warmup 3 --profile-mode"
+# enough warm-up steps for the context's scratch buffers and bundle-key box to settle
+ARGS="--steps 2 --warmup 10 --profile-mode"
 python bench.py $ARGS > gpurun_out/plain_$tag.log 2>&1 || { echo "plain run failed"; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:^k_|^Device" -s 190 -c 70 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "cg_step/" -k "regex:^k_|^Device" --csv \
     --log-file gpurun_out/launches_$tag.csv python bench.py $ARGS > gpurun_out/ncu_launches_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on \
     -k "regex:k_block_accumulate|k_walk_segments|k_fold_wide|k_point_keys|k_voxel_update|k_long_finish|k_gather_sorted|k_resample_merge|k_fold_bundles|k_finalize_blocks" \
-    -s 27 -c 10 -o gpurun_out/prof_$tag -f python bench.py $ARGS > gpurun_out/ncu_full_$tag.log 2>&1
+    --nvtx --nvtx-include "cg_step/" -o gpurun_out/prof_$tag -f python bench.py $ARGS > gpurun_out/ncu_full_$tag.log 2>&1
+if [ -n "$SKIP_SERVER" ]; then echo profile_round done "(step only)"; exit 0; fi
 # server side: projection of 40 submaps, incremental re-projection, meshing (scripts/merge_probe.py)
 python scripts/merge_probe.py 40 > gpurun_out/merge_plain_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on \
