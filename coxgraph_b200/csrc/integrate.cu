@@ -1979,7 +1979,9 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   // point outside the box flags kErrKeyRange and the group is redone with the measured extent.
   constexpr int kKeySlack = 16, kKeyLimit = 8191;  // |rel| <= 8191: the anti-grazing set packs 14 bits
   // measuring the extent costs a few hundred thousand atomics: first job, retries, every 64th job
-  const bool measure = !ctx->key_box_valid || attempt > 0 || (ctx->key_jobs++ % 64) == 63;
+  // (CG_KEY_MEASURE_PERIOD overrides the 64; the tests set it to 1 to reach the shrinking window)
+  const unsigned period = static_cast<unsigned>(std::max<size_t>(1, env_size("CG_KEY_MEASURE_PERIOD", 64)));
+  const bool measure = !ctx->key_box_valid || attempt > 0 || (ctx->key_jobs++ % period) == period - 1;
   const int avail_total = 63 - frame_bits - kl.rank_bits - 1;
   // attempt 1 follows a point outside a box that was not being measured: the wide cube again
   if (!ctx->key_box_valid || (attempt == 1 && !ctx->key_retry_measured)) {

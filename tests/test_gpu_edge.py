@@ -97,3 +97,42 @@ def test_random_clouds_random_poses(gpu_ctx, seed):
         frames.append((_pose(rng), p, _colors(n, rng)))
     _compare(gpu_ctx, frames, batch=bool(seed & 1), use_const_weight=int(seed % 3 == 0),
              max_weight=50.0 if seed == 13 else 10000.0)
+
+
+def test_bundle_key_box_grows_and_shrinks(monkeypatch):
+    """The bundle keys cover a per-axis box of voxels around the sensor that the context learns
+    from its jobs: a fresh context, jobs whose extent grows step by step (every growth is a redo
+    of the group with the measured extent), one far outlier, then enough ordinary jobs for the
+    window over the last 8 measured jobs to shrink the box again.  Every result must match the
+    oracle whatever box was in force."""
+    from coxgraph_b200 import Context, Layer, TsdfIntegrator, synth
+    from oracle import oracle_py as orc
+    monkeypatch.setenv("CG_KEY_MEASURE_PERIOD", "1")   # measure on every job: the window fills fast
+    ctx = Context(0)
+    ocfg, gcfg = util.make_cfgs()
+    rng = np.random.default_rng(5)
+    T = synth.camera_pose((0.3, -0.2, 1.1), yaw=0.4)
+    gl, ol = Layer(ctx, 0.05, max_blocks=8192), orc.Layer(0.05)
+    integ = TsdfIntegrator(gcfg, gl)
+    reach = [0.6, 1.0, 1.8, 3.0, 4.5, 4.5]            # metres: the cloud's extent per job
+    reach += [60.0]                                   # one stray far return (a clearing ray)
+    reach += [1.5] * 12                               # back to ordinary clouds: the box shrinks
+    for k, r in enumerate(reach):
+        n = 4000
+        p = rng.uniform(-1, 1, (n, 3)).astype(np.float32) * np.float32(min(r, 4.5))
+        p[:, 2] = np.abs(p[:, 2]) + 0.3
+        if r > 10:
+            p[17] = (0.2, -0.1, r)
+        c = rng.integers(0, 256, (n, 4), dtype=np.uint8)
+        for batch in (False, True):                   # single frame, then the same cloud in a batch
+            if batch:
+                integ.integrateBatch(np.stack([T, T]), np.concatenate([p, p]), np.concatenate([c, c]),
+                                     np.array([0, n, 2 * n], np.uint64))
+                ol.integrate(ocfg, T, p, c)
+                ol.integrate(ocfg, T, p, c)
+            else:
+                integ.integratePointCloud(T, p, c)
+                ol.integrate(ocfg, T, p, c)
+        util.compare_layers(gl.download(), ol.download(), f"job {k} (reach {r} m)")
+    gl.close()
+    ctx.close()
