@@ -601,7 +601,9 @@ int32_t cg_layer_clear(cg_layer* L) {
   }
   CG_CUDA(cudaMemsetAsync(v.num_blocks, 0, sizeof(int32_t), s));
   L->num_blocks = 0;
-  CG_CUDA(cudaStreamSynchronize(s));
+  // no host synchronisation: everything that touches the layer afterwards is ordered behind these
+  // fills on the context's stream, and a round trip to the host costs more than the fills
+  CG_CUDA(cudaGetLastError());
   return CG_OK;
 }
 
