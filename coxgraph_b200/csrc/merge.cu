@@ -382,11 +382,12 @@ static int32_t enqueue_merge(const cg_layer* A, const float T_B_A[7], cg_layer* 
   const unsigned grid = static_cast<unsigned>(
       std::min<size_t>(27 * nA, static_cast<size_t>(ctx->num_sms) * 4));
   const size_t smem = 3 * kVoxelsPerBlock * sizeof(float) + sizeof(SlotTable);
-  static bool attr_set = false;
-  if (!attr_set) {
+  // per device (a process may hold contexts on several GPUs): one flag per device ordinal
+  static bool attr_set[64] = {};
+  if (ctx->device < 0 || ctx->device >= 64 || !attr_set[ctx->device]) {
     CG_CUDA(cudaFuncSetAttribute(k_resample_merge, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
-    attr_set = true;
+    if (ctx->device >= 0 && ctx->device < 64) attr_set[ctx->device] = true;
   }
   {
     StageScope sc(ctx, kStageMergeResample, 1);
@@ -714,11 +715,11 @@ static int32_t project_batch(const cg_layer* const* submaps, const BatchSubmap* 
                                                          ctx->d_counters);
   }
   const size_t smem = 3 * kVoxelsPerBlock * sizeof(float) + sizeof(SlotTable);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per device ordinal
+  if (ctx->device < 0 || ctx->device >= 64 || !attr_set[ctx->device]) {
     CG_CUDA(cudaFuncSetAttribute(k_project_batch, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
-    attr_set = true;
+    if (ctx->device >= 0 && ctx->device < 64) attr_set[ctx->device] = true;
   }
   {
     StageScope sc(ctx, kStageMergeResample, 1);
