@@ -64,6 +64,52 @@ def jump(t0, ts, k):
     return t, real_adds
 
 
+def jump_bits(t0, ts, k):
+    """The same in integer arithmetic on the float32 bit patterns (what a CUDA kernel would do: no
+    float64, one real addition per binade crossing).  Handles t0 <= 0 (the 1e-6 of the grid index
+    can make the first boundary slightly negative) by real additions until t is positive."""
+    t, left = f32(t0), k
+    sb = int(f32(ts).view(np.uint32))
+    s_exp, s_man = (sb >> 23) & 0xFF, (sb & 0x7FFFFF) | 0x800000      # ts = s_man * 2^(s_exp - 150)
+    while left > 0:
+        tb = int(t.view(np.uint32))
+        t_exp = (tb >> 23) & 0xFF
+        if t <= 0 or t_exp == 0 or s_exp == 0:      # non-positive or denormal: plain additions
+            t = f32(t + ts)
+            left -= 1
+            continue
+        t_man = (tb & 0x7FFFFF) | 0x800000
+        shift = t_exp - s_exp                       # ulp(t) = 2^shift * ulp(ts)
+        if shift < 0 or shift == 0:                 # the step is at least as coarse as t: crossing soon
+            t = f32(t + ts)
+            left -= 1
+            continue
+        if shift > 25:                              # the step is below half an ulp of t: t stalls
+            return t
+        whole, rem, half = s_man >> shift, s_man & ((1 << shift) - 1), 1 << (shift - 1)
+        if rem == half:                             # ties: the first one for real, then constant
+            t_next = f32(t + ts)
+            left -= 1
+            if left == 0 or ((int(t_next.view(np.uint32)) >> 23) & 0xFF) != t_exp:
+                t = t_next
+                continue
+            t = t_next
+            t_man = (int(t.view(np.uint32)) & 0x7FFFFF) | 0x800000
+            inc = whole if whole % 2 == 0 else whole + 1
+        else:
+            inc = whole + (1 if rem > half else 0)
+        if inc == 0:
+            return t
+        n = min(left, (0xFFFFFF - t_man) // inc)    # additions that keep the mantissa below 2^24
+        if n > 0:
+            t = np.uint32((t_exp << 23) | ((t_man + n * inc) & 0x7FFFFF)).view(f32)
+            left -= n
+        if left > 0:                                # the addition that reaches the next binade
+            t = f32(t + ts)
+            left -= 1
+    return t
+
+
 def main(cases):
     rng = np.random.default_rng(7)
     worst = 0
@@ -76,8 +122,13 @@ def main(cases):
         got, real_adds = jump(t0, ts, k)
         assert got.view(np.uint32) == want.view(np.uint32), (c, float(t0), float(ts), k, float(got), float(want))
         worst = max(worst, real_adds)
-    print(f"{cases} cases: closed form == sequential float32 accumulation bit for bit; "
-          f"at most {worst} real additions per jump")
+        if c % 3 == 0:                       # a first boundary at or slightly below zero
+            t0 = f32(-rng.uniform(0, 2e-5) * float(ts)) if c % 6 == 0 else f32(0.0)
+            want = sequential(t0, ts, k)
+        got = jump_bits(t0, ts, k)
+        assert np.uint32(got.view(np.uint32)) == want.view(np.uint32), ("bits", c, float(t0), float(ts), k)
+    print(f"{cases} cases: closed form (float64 and integer-bit versions) == sequential float32 "
+          f"accumulation bit for bit; at most {worst} real additions per jump")
 
 
 if __name__ == "__main__":
