@@ -89,8 +89,8 @@ lines = summarise(rows[2:], hdr, units, traffic)
 server = [os.path.join(go, f"prof_{k}_{tag}.ncu-rep") for k in ("merge", "mesh")]
 if all(os.path.exists(r) for r in server):
     lines.append("# server side: `ncu --set full ... python scripts/merge_probe.py 40` — the first "
-                 "projection of 40 C2 submaps (`-k regex:k_project_batch|k_mark_batch|"
-                 "k_list_candidates -c 3`) and the meshing of the projected map (`-k k_mesh_blocks "
+                 "projection of 40 C2 submaps (`-k regex:k_project_batch|k_mark_batch|k_rank_hist|"
+                 "k_list_candidates -c 4`) and the meshing of the projected map (`-k k_mesh_blocks "
                  "-c 2`: count pass, write pass)\n")
     for rep2 in server:
         raw2 = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True,
