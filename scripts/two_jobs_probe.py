@@ -8,16 +8,17 @@ import bench
 from coxgraph_b200 import Context, Layer, TsdfIntegrator, TsdfIntegratorConfig, mergeLayerAintoLayerB, synth
 dev = torch.device("cuda", 0)
 cfg = TsdfIntegratorConfig(**bench.CFG)
+LANES = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 jobs = []
-for robot in range(2):
+for robot in range(LANES):
     ctx = Context(0)
     sub, glob = Layer(ctx, 0.05, max_blocks=4096), Layer(ctx, 0.05, max_blocks=32768)
     ents = []
     for sm in range(4):
-        poses, pts, cols = bench.host_frames(robot, sm, 25, dev)
+        poses, pts, cols = bench.host_frames(robot % 2, sm + 4 * (robot // 2), 25, dev)
         ents.append((poses, torch.cat(pts).contiguous(), torch.cat(cols).contiguous(),
                      np.cumsum([0] + [len(p) for p in pts]).astype(np.uint64)))
-    jobs.append((ctx, sub, glob, TsdfIntegrator(cfg, sub), ents, synth.robot_map_offset(robot)))
+    jobs.append((ctx, sub, glob, TsdfIntegrator(cfg, sub), ents, synth.robot_map_offset(robot % 2)))
 torch.cuda.synchronize()
 
 def run(job, steps):
@@ -41,6 +42,6 @@ t0 = time.perf_counter()
 for t in th: t.start()
 for t in th: t.join()
 par = time.perf_counter() - t0
-pts = 2 * STEPS * 7.68e6
-print(f"one job at a time: {seq/(2*STEPS)*1e3:.3f} ms per submap ({pts/seq/1e9:.2f} G points/s); "
-      f"two in flight: {par/(2*STEPS)*1e3:.3f} ms per submap ({pts/par/1e9:.2f} G points/s)")
+pts = LANES * STEPS * 7.68e6
+print(f"one job at a time: {seq/(LANES*STEPS)*1e3:.3f} ms per submap ({pts/seq/1e9:.2f} G points/s); "
+      f"{LANES} in flight: {par/(LANES*STEPS)*1e3:.3f} ms per submap ({pts/par/1e9:.2f} G points/s)")
