@@ -8,7 +8,7 @@ NVFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -prec-div=true -prec-sqrt
 SRC  = coxgraph_b200/csrc
 OBJ  = build/obj
 LIB  = coxgraph_b200/lib/libcoxgraph_b200.so
-HDRS = $(SRC)/cg_math.cuh $(SRC)/cg_internal.cuh include/coxgraph_b200.h
+HDRS = $(SRC)/cg_math.cuh $(SRC)/cg_internal.cuh $(SRC)/cg_raycast_direct.cuh include/coxgraph_b200.h
 OBJS = $(OBJ)/layer.o $(OBJ)/integrate.o $(OBJ)/merge.o $(OBJ)/exchange.o $(OBJ)/mesh_recover.o $(OBJ)/mesh.o $(OBJ)/selftest.o
 
 HOSTCHK = build/host_api_check

@@ -1,5 +1,6 @@
 // selftest.cu — device-side self checks of arithmetic shortcuts (used by tests/test_gpu_math.py).
 #include "cg_internal.cuh"
+#include "cg_raycast_direct.cuh"
 
 namespace cg {
 
@@ -50,6 +51,51 @@ __global__ void k_check_round(uint64_t seed, uint64_t per_thread, unsigned long 
   if (bad) atomicAdd(mismatches, bad);
 }
 
+// raycast_state_after (cg_raycast_direct.cuh) against the sequential RayCaster: random rays of the
+// integrator's shapes (sensor origin, point up to ~6 m away, 5 cm or 2 cm voxels, carving); at every
+// step that crosses a block face the directly computed state must equal the walked one — step
+// index, voxel index and t_to_next_boundary bit for bit.  counters[0] = mismatches, [1] = block
+// entries compared.
+__global__ void k_check_direct_raycast(uint64_t seed, uint64_t per_thread,
+                                       unsigned long long* counters) {
+  uint64_t s = seed + 0xA24BAED4963EE407ULL * (blockIdx.x * static_cast<uint64_t>(blockDim.x) +
+                                               threadIdx.x + 1);
+  unsigned long long bad = 0, seen = 0;
+  for (uint64_t i = 0; i < per_thread; ++i) {
+    auto uni = [&](float lo, float hi) { return lo + (hi - lo) * (lcg(s) >> 8) * (1.0f / 16777216.0f); };
+    const V3 origin = V3{uni(-6.0f, 6.0f), uni(-4.0f, 4.0f), uni(0.0f, 3.0f)};
+    const V3 dir = V3{uni(-1.0f, 1.0f), uni(-1.0f, 1.0f), uni(-1.0f, 1.0f)};
+    const float len = uni(0.2f, 6.0f);
+    const V3 point = origin + normalized3(dir) * len;
+    const bool fine = (lcg(s) & 1u) != 0;
+    RayCaster rc;
+    rc.init(origin, point, (lcg(s) & 7u) == 0, true, 5.0f, fine ? 50.0f : 20.0f, fine ? 0.06f : 0.16f);
+    if (!rc.valid || rc.steps == 0 || rc.sx == 0 || rc.sy == 0 || rc.sz == 0) continue;
+    const int c0[3] = {rc.cx, rc.cy, rc.cz}, sign[3] = {rc.sx, rc.sy, rc.sz};
+    const float t0[3] = {rc.tnx, rc.tny, rc.tnz}, ts[3] = {rc.tsx, rc.tsy, rc.tsz};
+    const unsigned steps = rc.steps;
+    unsigned k[3] = {0, 0, 0};
+    for (unsigned n = 1; n <= steps; ++n) {
+      const int px = rc.cx, py = rc.cy, pz = rc.cz;
+      rc.step();
+      const int a = rc.cx != px ? 0 : (rc.cy != py ? 1 : 2);
+      ++k[a];
+      const int before = a == 0 ? px : (a == 1 ? py : pz);
+      const int after = a == 0 ? rc.cx : (a == 1 ? rc.cy : rc.cz);
+      if ((before >> 4) == (after >> 4)) continue;  // stays inside the block
+      const DirectState d = raycast_state_after(c0, sign, t0, ts, steps, a, k[a]);
+      ++seen;
+      const bool ok = d.valid && d.n == n && d.c[0] == rc.cx && d.c[1] == rc.cy && d.c[2] == rc.cz &&
+                      __float_as_uint(d.t[0]) == __float_as_uint(rc.tnx) &&
+                      __float_as_uint(d.t[1]) == __float_as_uint(rc.tny) &&
+                      __float_as_uint(d.t[2]) == __float_as_uint(rc.tnz);
+      if (!ok) ++bad;
+    }
+  }
+  if (bad) atomicAdd(&counters[0], bad);
+  if (seen) atomicAdd(&counters[1], seen);
+}
+
 }  // namespace cg
 
 using namespace cg;
@@ -59,20 +105,23 @@ extern "C" int32_t cg_debug_selftest(cg_context* ctx, int32_t which, uint64_t sa
   if (!ctx || !mismatches) return CG_ERR_INVALID_ARG;
   CG_CUDA(cudaSetDevice(ctx->device));
   unsigned long long* d = nullptr;
-  CG_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
-  CG_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
+  CG_CUDA(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+  CG_CUDA(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), ctx->stream));
   const unsigned blocks = ctx->num_sms * 8, threads = 256;
   const uint64_t per_thread = samples / (static_cast<uint64_t>(blocks) * threads) + 1;
   if (which == 0)
     k_check_div<<<blocks, threads, 0, ctx->stream>>>(0x1234567ULL, per_thread, d);
   else if (which == 1)
     k_check_round<<<blocks, threads, 0, ctx->stream>>>(0x7654321ULL, per_thread, d);
+  else if (which == 2 || which == 3)  // samples = rays; 2 -> mismatches, 3 -> block entries compared
+    k_check_direct_raycast<<<blocks, threads, 0, ctx->stream>>>(0x2468ACEULL, per_thread, d);
   else {
     cudaFree(d);
     return CG_ERR_INVALID_ARG;
   }
   unsigned long long h = 0;
-  CG_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CG_CUDA(cudaMemcpyAsync(&h, d + (which == 3 ? 1 : 0), sizeof(h), cudaMemcpyDeviceToHost,
+                          ctx->stream));
   CG_CUDA(cudaStreamSynchronize(ctx->stream));
   CG_CUDA(cudaGetLastError());
   cudaFree(d);

@@ -313,7 +313,9 @@ int32_t cg_layer_pack_by_owner(const cg_layer* layer, int32_t nranks, void* d_pa
 int32_t cg_layer_merge_packed(cg_layer* layer, const void* d_packed, size_t num_blocks);
 
 /* --- self checks of device arithmetic shortcuts (which: 0 = exact division through a
- * precomputed reciprocal, 1 = round-half-away); *mismatches must come back 0. */
+ * precomputed reciprocal, 1 = round-half-away, 2 = RayCaster state at block entries computed
+ * without walking, `samples` random rays); *mismatches must come back 0.  which = 3 runs the same
+ * rays as 2 and returns the number of block entries it compared instead. */
 int32_t cg_debug_selftest(cg_context* ctx, int32_t which, uint64_t samples, uint64_t* mismatches);
 
 #ifdef __cplusplus
