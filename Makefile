@@ -3,7 +3,10 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH  = -gencode arch=compute_100a,code=sm_100a
 # -fmad=false / -ffp-contract=off: no FMA contraction anywhere — every float op on the path is
 # the plain IEEE single-precision one, which is what makes block allocation bit-exact.
-NVFLAGS = $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
+# alpha byte of a default-constructed voxblox::Color (csrc/cg_math.cuh); pass the same value to
+# the oracle (`make -C oracle DEFAULT_ALPHA=...`) when changing it
+DEFAULT_ALPHA ?= 255
+NVFLAGS = $(ARCH) -DCG_DEFAULT_ALPHA=$(DEFAULT_ALPHA) -O3 -std=c++17 -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
           -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-Wall -Iinclude --expt-relaxed-constexpr
 SRC  = coxgraph_b200/csrc
 OBJ  = build/obj
@@ -24,7 +27,7 @@ $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
 
 oracle:
-	$(MAKE) -C oracle -s
+	$(MAKE) -C oracle -s DEFAULT_ALPHA=$(DEFAULT_ALPHA)
 
 # C++ host API driver (tests/test_host_cpp.py): plain g++, links only the C ABI
 $(HOSTCHK): tests/host/host_api_check.cc coxgraph_b200/host/coxgraph_b200.hpp include/coxgraph_b200.h $(LIB)

@@ -52,6 +52,16 @@ class Context:
     def synchronize(self):
         capi.check(capi.load().cg_context_synchronize(self._h))
 
+    def wait_stream(self, producer_stream):
+        """Order the context's stream behind `producer_stream` (a raw cudaStream_t value)."""
+        capi.check(capi.load().cg_context_wait_stream(self._h, C.c_void_p(producer_stream or 0)))
+
+    def wait_torch(self):
+        """Device tensors handed to the `*_device` entry points are read on the context's stream:
+        order it behind torch's current stream, which produced them."""
+        import torch
+        self.wait_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
     def set_profiling(self, enable=True):
         """Bracket every pipeline stage with CUDA events (voxblox::timing::Timer counterpart)."""
         capi.check(capi.load().cg_context_set_profiling(self._h, int(bool(enable))))
@@ -219,6 +229,7 @@ class TsdfIntegrator:
             assert points_C.is_contiguous() and colors.is_contiguous() and _is_cuda_tensor(colors)
             n = points_C.numel() // 3
             assert colors.numel() * colors.element_size() == 4 * n
+            self.layer.ctx.wait_torch()
             capi.check(lib.cg_integrate_pointcloud_device(
                 self.layer._h, C.byref(self.config), _ptr(T), C.c_void_p(points_C.data_ptr()),
                 C.c_void_p(colors.data_ptr()), n, int(freespace_points),
@@ -242,6 +253,7 @@ class TsdfIntegrator:
             raise ValueError("frame_offsets must have F+1 entries")
         if _is_cuda_tensor(points_C):
             assert points_C.is_contiguous() and colors.is_contiguous() and _is_cuda_tensor(colors)
+            self.layer.ctx.wait_torch()
             capi.check(lib.cg_integrate_batch_device(
                 self.layer._h, C.byref(self.config), len(P), _ptr(P),
                 C.c_void_p(points_C.data_ptr()), C.c_void_p(colors.data_ptr()), _ptr(offs),

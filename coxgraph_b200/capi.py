@@ -104,6 +104,7 @@ SYMBOLS = {
     "cg_context_create": (C.c_int32, [C.c_int32, _P, C.POINTER(_P)]),
     "cg_context_destroy": (C.c_int32, [_P]),
     "cg_context_synchronize": (C.c_int32, [_P]),
+    "cg_context_wait_stream": (C.c_int32, [_P, _P]),
     "cg_context_set_profiling": (C.c_int32, [_P, C.c_int32]),
     "cg_context_get_profile": (C.c_int32, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "cg_context_reset_profile": (C.c_int32, [_P]),

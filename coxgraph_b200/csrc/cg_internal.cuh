@@ -214,6 +214,7 @@ struct cg_context {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaEvent_t wait_event = nullptr;         // cg_context_wait_stream
   cudaStream_t copy_stream = nullptr;       // pipelined host->device transfers (lazy)
   std::vector<cudaEvent_t> copy_events;
   void* h_tables = nullptr;                 // pinned + mapped: poses / frame offsets of the job

@@ -15,7 +15,14 @@ namespace cg {
 constexpr float kEps = 1e-6f;  // voxblox kEpsilon / kFloatEpsilon / kCoordinateEpsilon
 constexpr int kVps = 16;
 constexpr int kVoxelsPerBlock = 4096;
-constexpr uint32_t kDefaultColor = 0xFF000000u;  // r=g=b=0, a=255 (bytes r,g,b,a)
+// A default-constructed voxblox::Color: r = g = b = 0 and alpha CG_DEFAULT_ALPHA (255 unless the
+// library is built with `make DEFAULT_ALPHA=0` for a fork whose Color() zeroes the alpha as well;
+// only alpha bytes depend on it).  Bytes r,g,b,a.
+#ifndef CG_DEFAULT_ALPHA
+#define CG_DEFAULT_ALPHA 255
+#endif
+constexpr uint32_t kDefaultColor = static_cast<uint32_t>(CG_DEFAULT_ALPHA) << 24;
+constexpr float kDefaultAlpha = static_cast<float>(CG_DEFAULT_ALPHA);
 
 struct V3 {
   float x, y, z;
@@ -123,7 +130,7 @@ __device__ __forceinline__ void fold_reset(FoldState& s) {
   s.m = V3{0.0f, 0.0f, 0.0f};
   s.W = 0.0f;
   s.cr = s.cg = s.cb = 0.0f;
-  s.ca = 255.0f;
+  s.ca = kDefaultAlpha;
 }
 __device__ __forceinline__ uint32_t fold_color(const FoldState& s) {
   return pack_rgba(static_cast<uint32_t>(s.cr), static_cast<uint32_t>(s.cg),

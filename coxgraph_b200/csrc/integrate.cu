@@ -381,7 +381,7 @@ k_fold_wide(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ keys,
       key = bi.key;
     }
     float W = 0.0f;                            // running weight (same in the 8 lanes of a group)
-    float val = (chain == 6) ? 255.0f : 0.0f;  // this lane's chain state (alpha starts at 255)
+    float val = (chain == 6) ? kDefaultAlpha : 0.0f;  // this lane's chain state (default colour)
     float4 pt = (start + l8 < end) ? sorted[start + l8] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     for (uint32_t c0 = start; __any_sync(full, c0 < end); c0 += kWideGroup) {
       const uint32_t cnt = c0 < end ? min(static_cast<uint32_t>(kWideGroup), end - c0) : 0u;
@@ -1286,7 +1286,15 @@ __device__ __forceinline__ void replay_segment(const IntegratorParams& P,
     const bool act = c0 + lane < end;
     Visit v = make_visit(P, poses, ray, center);
     if (!act) v.w = 0.0f;
-    const float sdf = v.sdf, w = v.w;
+    const float sdf = v.sdf;
+    // "new_weight < kFloatEpsilon -> return" leaves the voxel untouched, weight included.  The
+    // weights are >= 0, so updates are skipped only while the stored weight is still below
+    // epsilon: every update before the first one with W + w >= epsilon (all of them see the same
+    // W), none after it.  Skipped updates must not enter the running weight.
+    const unsigned okb = __ballot_sync(full, act && !(W + v.w < kEps));
+    const int first_ok = okb ? __ffs(okb) - 1 : 32;
+    const bool skip = !act || lane < first_ok;
+    const float w = skip ? 0.0f : v.w;
     // weights: W_k = min(max_weight, W_{k-1} + w_k)  ==  min(max_weight, W_0 + sum w)
     float pre = w;
 #pragma unroll
@@ -1296,8 +1304,7 @@ __device__ __forceinline__ void replay_segment(const IntegratorParams& P,
     }
     const float w_prev = fminf(P.max_weight, W + (pre - w));
     const float w_new = w_prev + w;
-    const bool skip = !act || w_new < kEps;  // "new_weight < kFloatEpsilon -> return"
-    const float inv = __fdividef(1.0f, w_new);
+    const float inv = 1.0f / w_new;
     ClampedAffine f;
     f.a = skip ? 1.0f : w_prev * inv;
     f.b = skip ? 0.0f : (sdf * w) * inv;

@@ -357,6 +357,14 @@ int32_t finish_call(cg_layer* layer, CallCounters* out) {
   if (out) *out = *ctx->h_counters;
   const int err = ctx->h_counters->err;
   if (err & kErrPoolFull) {
+    // the keys that found no slot are still in the hash (value -1): rebuild it from block_keys
+    // so that later calls do not find them and silently skip those blocks
+    const LayerView& v = layer->v;
+    const uint32_t keep = static_cast<uint32_t>(layer->num_blocks);
+    cudaMemsetAsync(v.hash_keys, 0xFF, layer->hash_cap * sizeof(uint64_t), ctx->stream);
+    cudaMemsetAsync(v.hash_vals, 0xFF, layer->hash_cap * sizeof(int32_t), ctx->stream);
+    if (keep > 0) k_rehash<<<grid_for(keep, 256), 256, 0, ctx->stream>>>(v, keep);
+    cudaStreamSynchronize(ctx->stream);
     set_error("block pool exhausted (max_blocks = %zu)", layer->max_blocks);
     return CG_ERR_POOL_FULL;
   }
@@ -471,6 +479,7 @@ int32_t cg_context_destroy(cg_context* ctx) {
     if (ctx->stage_ready[i]) cudaEventDestroy(ctx->stage_ready[i]);
   }
   if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
+  if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -513,6 +522,17 @@ uint64_t cg_context_kernel_launches(const cg_context* ctx) { return ctx ? ctx->o
 int32_t cg_context_synchronize(cg_context* ctx) {
   if (!ctx) return CG_ERR_INVALID_ARG;
   CG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CG_OK;
+}
+
+int32_t cg_context_wait_stream(cg_context* ctx, void* producer_stream) {
+  if (!ctx) return CG_ERR_INVALID_ARG;
+  cudaStream_t ps = static_cast<cudaStream_t>(producer_stream);
+  if (ps == ctx->stream) return CG_OK;
+  CG_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->wait_event) CG_CUDA(cudaEventCreateWithFlags(&ctx->wait_event, cudaEventDisableTiming));
+  CG_CUDA(cudaEventRecord(ctx->wait_event, ps));
+  CG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->wait_event, 0));
   return CG_OK;
 }
 

@@ -346,15 +346,26 @@ __global__ void k_reset_merge_counters(CallCounters* c) {
   c->blocks_out = 0;
 }
 
+// transformLayer's forward pass marks at most this many destination blocks for `blocks` source
+// blocks: per axis the grid x in [c - r, c + r) step block_size_out with r = sqrt(3)/2 block_size_in
+// has at most floor(sqrt(3) block_in / block_out) + 2 samples
+static size_t mark_bound(const cg_layer* A, const cg_layer* G, size_t blocks) {
+  const double per_axis = std::floor(1.7320508075688772 * A->v.block_size / G->v.block_size) + 2.0;
+  return blocks * static_cast<size_t>(per_axis * per_axis * per_axis);
+}
+
 static int32_t enqueue_merge(const cg_layer* A, const float T_B_A[7], cg_layer* B) {
   cg_context* ctx = B->ctx;
   cudaStream_t s = ctx->stream;
   const size_t nA = static_cast<size_t>(A->num_blocks);
   if (nA == 0) return CG_OK;
+  // candidate set / list sized from the forward pass's own bound (a coarse source layer merged
+  // into a fine one marks more than 27 destination blocks per source block)
+  const size_t cand_bound = mark_bound(A, B, nA);
   size_t cap = 1024;
-  while (cap < 32 * nA) cap <<= 1;
+  while (cap < 2 * cand_bound) cap <<= 1;
   CG_CUDA(ctx->cand_keys.reserve(cap * sizeof(uint64_t)));
-  CG_CUDA(ctx->cand_list.reserve(27 * nA * sizeof(uint64_t)));
+  CG_CUDA(ctx->cand_list.reserve(cand_bound * sizeof(uint64_t)));
   const Xform T = make_xform(T_B_A);
   {
     StageScope sc(ctx, kStageMergeMark, 2);
@@ -380,7 +391,7 @@ static int32_t enqueue_merge(const cg_layer* A, const float T_B_A[7], cg_layer* 
     Ti.t = V3{-r.x, -r.y, -r.z};
   }
   const unsigned grid = static_cast<unsigned>(
-      std::min<size_t>(27 * nA, static_cast<size_t>(ctx->num_sms) * 4));
+      std::min<size_t>(cand_bound, static_cast<size_t>(ctx->num_sms) * 4));
   const size_t smem = 3 * kVoxelsPerBlock * sizeof(float) + sizeof(SlotTable);
   // per device (a process may hold contexts on several GPUs): one flag per device ordinal
   static bool attr_set[64] = {};
@@ -671,11 +682,6 @@ static Xform inverse_host(const Xform& T) {
 
 // submaps [i0, i1) as one batch (descriptors already on the device); everything is enqueued on the
 // context's stream, nothing is read back
-static size_t mark_bound(const cg_layer* A, const cg_layer* G, size_t blocks) {
-  const double per_axis = std::floor(1.7320508075688772 * A->v.block_size / G->v.block_size) + 2.0;
-  return blocks * static_cast<size_t>(per_axis * per_axis * per_axis);
-}
-
 static int32_t project_batch(const cg_layer* const* submaps, const BatchSubmap* h_desc,
                              const BatchSubmap* d_desc, size_t i0, size_t i1, cg_layer* G,
                              const uint64_t* filter_keys = nullptr, uint32_t filter_mask = 0) {

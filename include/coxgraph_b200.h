@@ -104,6 +104,11 @@ const char* cg_version(void);
 int32_t cg_context_create(int32_t device, void* stream, cg_context** out);
 int32_t cg_context_destroy(cg_context* ctx);
 int32_t cg_context_synchronize(cg_context* ctx);
+/* Orders the context's stream behind everything queued so far on `producer_stream` (a
+ * cudaStream_t as void*; NULL = the legacy default stream).  The `*_device` entry points read the
+ * caller's device buffers on the context's stream: call this first when another stream produced
+ * them (no-op when it is the context's own stream). */
+int32_t cg_context_wait_stream(cg_context* ctx, void* producer_stream);
 
 /* Named stage timers (CUDA events on the context's stream) and launch counters — the
  * counterpart of the voxblox::timing::Timer scopes the reference wraps around this path

@@ -72,8 +72,16 @@ inline Xform inverse(const Xform& T) {  // (q*, -(q* (x) t))
 }
 
 // ---------------------------------------------------------------- voxel / colour
+// Alpha of a default-constructed voxblox::Color.  Upstream core/color.h is not in the reference
+// tree; this restatement takes (0, 0, 0, 255).  A fork whose Color() zeroes the alpha too is matched
+// by building with -DORC_DEFAULT_ALPHA=0 (and the library with CG_DEFAULT_ALPHA=0, see the
+// Makefiles): only alpha bytes change (voxels that
+// were carved before they were coloured, and the vertices taking their colour).
+#ifndef ORC_DEFAULT_ALPHA
+#define ORC_DEFAULT_ALPHA 255
+#endif
 struct Color {
-  uint8_t r = 0, g = 0, b = 0, a = 255;
+  uint8_t r = 0, g = 0, b = 0, a = ORC_DEFAULT_ALPHA;
 };
 struct Voxel {  // voxblox::TsdfVoxel, 12 bytes
   float distance = 0.0f;

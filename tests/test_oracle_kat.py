@@ -291,3 +291,49 @@ def test_fast_integrator_is_deterministic_subset():
     fast_blocks = {tuple(i) for i in f1.download()[0]}
     simple_blocks = {tuple(i) for i in s.download()[0]}
     assert fast_blocks <= simple_blocks and len(fast_blocks) > 0.5 * len(simple_blocks)
+
+
+def test_default_alpha_switch(tmp_path):
+    """The alpha byte of a default-constructed Color is a build switch (ORC_DEFAULT_ALPHA /
+    CG_DEFAULT_ALPHA): with 0 instead of 255 only alpha bytes change."""
+    import ctypes as C
+    import os
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    so = str(tmp_path / "liborc_alpha0.so")
+    subprocess.check_call(["g++", "-O1", "-DORC_DEFAULT_ALPHA=0", "-std=c++17", "-fPIC",
+                           "-ffp-contract=off", "-fno-fast-math", "-pthread", "-shared", "-o", so,
+                           os.path.join(here, "tsdf_oracle.cc")])
+    alt = C.CDLL(so)
+    alt.orc_layer_create.restype = C.c_void_p
+    alt.orc_layer_create.argtypes = [C.c_float, C.c_int32]
+    alt.orc_layer_num_blocks.restype = C.c_size_t
+    alt.orc_layer_num_blocks.argtypes = [C.c_void_p]
+    alt.orc_layer_download.argtypes = [C.c_void_p] * 4
+    alt.orc_integrate_pointcloud.restype = C.c_int32
+    alt.orc_integrate_pointcloud.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]
+    cfg = orc.default_config(default_truncation_distance=0.15, use_const_weight=1, method=1)
+    (T, pts, cols), = util.small_frames(1, stride=16)
+    ref = orc.Layer(0.05)
+    ref.integrate(cfg, T, pts, cols)
+    ri, rv, _ = ref.download()
+    h = alt.orc_layer_create(0.05, 16)
+    T = np.ascontiguousarray(T, np.float32)
+    assert alt.orc_integrate_pointcloud(h, C.byref(cfg), T.ctypes.data, pts.ctypes.data,
+                                        cols.ctypes.data, len(pts), 0, None) == 0
+    n = alt.orc_layer_num_blocks(h)
+    ai = np.zeros((n, 3), np.int32)
+    av = np.zeros((n, 4096), orc.VOXEL_DTYPE)
+    af = np.zeros(n, np.uint8)
+    alt.orc_layer_download(h, ai.ctypes.data, av.ctypes.data, af.ctypes.data)
+    assert np.array_equal(ai, ri)
+    assert np.array_equal(av["distance"], rv["distance"]) and np.array_equal(av["weight"], rv["weight"])
+    assert np.array_equal(av["rgba"][..., :3], rv["rgba"][..., :3])
+    differs = av["rgba"][..., 3] != rv["rgba"][..., 3]
+    # voxels that only ever saw free space keep the default colour; a voxel carved first and
+    # coloured later blends the default alpha in: alpha bytes differ, nothing else does
+    assert differs.any()
+    assert (av["rgba"][..., 3][differs] < rv["rgba"][..., 3][differs]).all()
+    untouched_colour = (rv["rgba"][..., :3] == 0).all(axis=-1) & (rv["weight"] > 0) & differs
+    assert (av["rgba"][..., 3][untouched_colour] == 0).all()
