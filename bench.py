@@ -6,7 +6,8 @@ synthetic 640x480 depth frames each, 5 cm voxels, 16 cm truncation, Merged integ
 fused submap merged into the rank's global TSDF.  One STEP = clear the submap layer, fuse the 25
 frames of one submap (7.68 M points) into it, merge it into the global layer.
 
-  python bench.py --gpus N --steps K --warmup W              our arm (CUDA, C ABI)
+  python bench.py --gpus N --steps K --warmup W              our arm (CUDA, C ABI), config C2
+  python bench.py --config C1|C3|C4|C5 ...                   the other BASELINE.json configs
   python bench.py --impl reference --gpus N --steps K ...    the CPU oracle port, all host threads
 
 Multi-GPU (torchrun, one rank per GPU): robots shard over ranks, no data-path collective in the
@@ -100,6 +101,56 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def stage_alg_bytes(stage, n_pts, rays, pairs, general, blocks, b_in=0, b_out=0):
+    """Compulsory HBM bytes of one pipeline stage (what it must read and write once; DESIGN.md
+    §7.1), per step.  (ray, block) segments are not in the job statistics: estimated as visits /
+    11.5, the ratio ncu shows at the C2 shape."""
+    segs = pairs / 11.5
+    table = {
+        "point_keys": 20 * n_pts, "bundle_sort": 16 * n_pts, "bundle_scan": 8 * n_pts + 4 * rays,
+        "gather_sorted": 40 * n_pts, "bundle_order": 12 * rays,
+        "fold_wide": 8 * n_pts + 12 * rays, "fold_bundles": 8 * n_pts + 12 * rays,
+        "bundle_rays": 48 * rays, "ray_scan": 24 * rays, "walk_segments": 24 * rays + 40 * segs,
+        "segment_sort": 16 * segs, "block_accumulate": 40 * segs + 8 * general + 65536 * blocks,
+        "pair_sort": 16 * general, "segments": 12 * general, "voxel_update": 44 * general,
+        "replay_wide": 44 * general, "finalize": 98304 * blocks, "merge_mark": 8 * b_in,
+        "merge_resample": BLOCK_BYTES * (b_in + 2 * b_out),
+    }
+    return float(table.get(stage, 0.0))
+
+
+def roofline_record(prof, steps, step_ms, bytes_step, per_step, traffic_file="traffic.json"):
+    """The `roofline` object of the JSON line.  The dominant stage is chosen over ALL stages of the
+    step, library kernels (cub sorts / selects: no own launches) included and flagged; `frac` is
+    that stage's own algorithmic bytes over its own time; `step_frac` — the contract figure of
+    SURVEY.md §8d over the whole step — is the headline."""
+    peak, peak_src = measured_peak_gbs()
+    stages = {k: v for k, v in prof.items() if k != "transfer" and v[0] > 0}
+    top = max(stages, key=lambda k: stages[k][0])
+    top_ms = stages[top][0] / steps
+    alg = stage_alg_bytes(top, **per_step)
+    achieved = alg / (top_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # dram bytes of one launch of that stage from the ncu capture of the same command
+        if traffic_file:
+            with open(os.path.join(ROOT, "profiles", traffic_file)) as f:
+                traffic = json.load(f).get(top)
+    except Exception:  # noqa: BLE001
+        pass
+    lib_ms = sum(v[0] for v in stages.values() if v[1] == 0) / steps
+    return {"bound": "hbm", "kernel": top, "library_kernel": stages[top][1] == 0,
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg, "ms_per_launch": top_ms,
+            "step_frac": bytes_step / (step_ms * 1e-3) / 1e9 / peak,
+            "step_algorithmic_bytes": bytes_step,
+            "library_stages_ms_per_step": lib_ms,
+            "note": "frac = the dominant stage's own compulsory bytes / its own time (a stage is "
+                    "one kernel or one library call); step_frac = the step's contract bytes "
+                    "(16 N + 2 x 49152 B_touched per call, 49152 (B_in + 2 B_out) per merge) / "
+                    "the whole step: the headline fraction"}
+
+
 def submap_of_step(step, rank, world):
     """(robot, submap) fused at `step` on `rank`.  The 2 x 20 submaps of the C2 shape shard over
     the ranks; every rank alternates between the two robots (their scenes differ in cost), so the
@@ -164,6 +215,58 @@ def run_reference(args, rank, world):
                 "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def layer_diff(got, ref):
+    """Margins of a CUDA layer against the oracle's: block sets, max |d_d| / tol, max |d_w| / tol
+    (tol = max(1e-5, 1e-4 |ref|), BASELINE.json north_star) and the colour LSB histogram."""
+    gi, gv, _ = got
+    ri, rv, _ = ref
+    out = {"blocks": int(len(gi)), "blocks_oracle": int(len(ri)),
+           "block_sets_equal": bool(gi.shape == ri.shape and np.array_equal(gi, ri))}
+    if not out["block_sets_equal"]:
+        out["within_tolerance"] = False
+        return out
+    for name in ("distance", "weight"):
+        g, r = gv[name].astype(np.float64), rv[name].astype(np.float64)
+        tol = np.maximum(1e-5, 1e-4 * np.abs(r))
+        out[f"max_{name}_err_over_tol"] = float((np.abs(g - r) / tol).max(initial=0.0))
+    dc = np.abs(gv["rgba"].astype(np.int16) - rv["rgba"].astype(np.int16)).max(axis=-1)
+    out["colour_lsb_hist"] = [int(x) for x in np.bincount(dc.ravel(), minlength=4)[:8]]
+    out["within_tolerance"] = bool(out["max_distance_err_over_tol"] <= 1.0 and
+                                   out["max_weight_err_over_tol"] <= 1.0 and dc.max(initial=0) <= 1)
+    return out
+
+
+def sharded_parity(subs, poses, partial, owned, rank, world):
+    """Parity evidence for the multi-GPU merge inside the bench run (the pytest for it is skipped
+    on one-GPU boxes): the union of the ranks' owned layers after a sharded projection of a few
+    submaps per rank, against the SINGLE-PROCESS oracle left fold of the same submaps in rank-major
+    order (the sharded plan re-associates the merge).  Rank 0 runs the oracle."""
+    import torch.distributed as dist
+    from coxgraph_b200 import sharding
+    owned.clear()
+    sharding.project_sharded(subs, poses, partial, owned)
+    mine = {"owned": owned.download(), "subs": [L.download() for L in subs],
+            "poses": np.asarray(poses)}
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0)
+    if rank != 0:
+        return None
+    from oracle import oracle_py as orc
+    og = orc.Layer(VOXEL_SIZE)
+    for r in range(world):
+        for (idx, vox, fl), T in zip(gathered[r]["subs"], gathered[r]["poses"]):
+            ol = orc.Layer(VOXEL_SIZE)
+            ol.upload(idx, vox, fl)
+            og.merge_from(ol, T)
+    idx = np.concatenate([g["owned"][0] for g in gathered])
+    vox = np.concatenate([g["owned"][1] for g in gathered])
+    order = np.lexsort((idx[:, 0], idx[:, 1], idx[:, 2]))
+    out = layer_diff((idx[order], vox[order], None), og.download())
+    out["submaps"] = len(subs) * world
+    out["oracle"] = "single-process left fold, rank-major submap order"
+    return out
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -256,6 +359,15 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    def all_ranks(x):
+        """x of every rank, in rank order (tells imbalance from stalls: SCALE runs)."""
+        if world == 1:
+            return [float(x)]
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     # pinned result buffers for the e2e leg (the fused submap layer, voxblox layout)
     out_idx = torch.empty((4096, 3), dtype=torch.int32, pin_memory=True).numpy()
     out_vox_t = torch.empty((4096, 4096 * 12), dtype=torch.uint8, pin_memory=True)
@@ -332,6 +444,7 @@ def run_ours(args, rank, world, local_rank):
         total_ms = max_over_ranks(ev_a.elapsed_time(ev_b))
         used = [pool[(args.warmup + k) % pool_n] for k in range(args.steps)]
         res = dict(total_ms=total_ms, clocks=clocks, launches=ctx.kernel_launches - launches0,
+                   per_rank_ms=[v / args.steps for v in all_ranks(ev_a.elapsed_time(ev_b))],
                    points=sum_over_ranks(sum(e["n"] for e in used)),
                    h2d=sum(16 * e["n"] for e in used) / args.steps, d2h=d2h / args.steps)
         if leg != "e2e":
@@ -436,6 +549,8 @@ def run_ours(args, rank, world, local_rank):
                                   "submaps_total": args.project_submaps * world,
                                   "blocks_sent": int(sum_over_ranks(float(sum(sent)))),
                                   "collective": "nccl all_to_all_single"}
+            project["sharded"]["parity"] = sharded_parity(
+                subs[:args.parity_submaps], T_all[:args.parity_submaps], partial, owned, rank, world)
             partial.close()
             owned.close()
         for L in subs:
@@ -566,19 +681,17 @@ def run_ours(args, rank, world, local_rank):
         used_dev = [pool[(args.warmup + k) % pool_n] for k in range(args.steps)]
         peak, peak_src = measured_peak_gbs()
         prof = dv["profile"]
-        # dominant stage among the library's OWN kernels; every stage runs once per step (all
-        # 25 frames of the submap go through each kernel together)
-        top = max((k for k in prof if k != "transfer" and prof[k][1] > 0), key=lambda k: prof[k][0])
-        is_merge = top.startswith("merge")
-        top_ms_per_launch = prof[top][0] / args.steps
-        alg_bytes = (dv["bytes_merge"] if is_merge else dv["bytes_int"]) / args.steps
-        achieved = alg_bytes / (top_ms_per_launch * 1e-3) / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(top)
-        except Exception:
-            pass
+        n_used = float(len(used_dev))
+        per_step = dict(n_pts=sum(e["n"] for e in used_dev) / n_used,
+                        rays=sum(e["rays"] for e in used_dev) / n_used,
+                        pairs=sum(e["pairs"] for e in used_dev) / n_used,
+                        general=sum(e["general"] for e in used_dev) / n_used,
+                        blocks=sum(e["blocks_in"] for e in used_dev) / n_used,
+                        b_in=sum(e["blocks_in"] for e in used_dev) / n_used,
+                        b_out=sum(e["bytes_merge"] / BLOCK_BYTES - e["blocks_in"] for e in used_dev)
+                        / n_used / 2)
+        roof = roofline_record(prof, args.steps, dv["total_ms"] / args.steps,
+                               (dv["bytes_int"] + dv["bytes_merge"]) / args.steps, per_step)
         line = {
             "metric": "tsdf_points_integrated_per_s",
             "value": dv["points"] / (dv["total_ms"] * 1e-3),
@@ -608,19 +721,8 @@ def run_ours(args, rank, world, local_rank):
                     "ms_per_step": ee["total_ms"] / args.steps,
                     "h2d_bytes_per_step": ee["h2d"], "d2h_bytes_per_step": ee["d2h"]},
             "gpu_launches": dv["launches"],
-            "roofline": {"bound": "hbm", "kernel": top,
-                         "library_kernel": prof[top][1] == 0, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "ms_per_launch": top_ms_per_launch,
-                         # the same bytes over the WHOLE step (all kernels + library sorts): the
-                         # pipeline-level fraction, which is the honest summary of this path
-                         "step_frac": (dv["bytes_int"] + dv["bytes_merge"]) / args.steps /
-                         (dv["total_ms"] / args.steps * 1e-3) / 1e9 / peak,
-                         "note": "one step = ~20 kernels; 'achieved' divides the step's algorithmic "
-                                 "bytes by the dominant kernel's time only, 'step_frac' by the "
-                                 "whole step"},
+            "roofline": roof,
+            "per_rank_ms_per_step": dv.get("per_rank_ms"),
             "stages_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "per_step": {"rays": sum(e["rays"] for e in used_dev) / args.steps,
                          "voxel_updates": sum(e["pairs"] for e in used_dev) / args.steps,
@@ -650,6 +752,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--project-submaps", type=int, default=40,
                     help="submaps of the separate getProjectedMap timing (0 = skip)")
+    ap.add_argument("--parity-submaps", type=int, default=3,
+                    help="submaps per rank of the in-bench parity check of the sharded merge (N > 1)")
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5"],
+                    help="BASELINE.json config (default C2 = the headline; see configs.py docstrings)")
+    ap.add_argument("--c4-blocks", type=int, default=2_000_000,
+                    help="C4: integrate along the trajectory until this many blocks are allocated")
+    ap.add_argument("--c3-submaps", type=int, default=64, help="C3 / C5: submaps per robot")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-mode", action="store_true",
                     help="skip the accounting pass and the CPU baseline (for runs under ncu)")
@@ -663,7 +772,11 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
-    run_ours(args, rank, world, local_rank)
+    if args.config == "C2":
+        run_ours(args, rank, world, local_rank)
+    else:
+        import bench_configs
+        bench_configs.run(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

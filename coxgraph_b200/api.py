@@ -205,6 +205,21 @@ class Layer:
                                          _ptr(c) if V else None))
         return idx, begin, v, n, c
 
+    def download_blocks(self, block_indices):
+        """The listed blocks only -> (voxels [n,4096] VOXEL_DTYPE, flags u8 [n], found bool [n])."""
+        idx = np.ascontiguousarray(block_indices, np.int32).reshape(-1, 3)
+        vox = np.zeros((len(idx), capi.VOXELS_PER_BLOCK), VOXEL_DTYPE)
+        flags = np.zeros(len(idx), np.uint8)
+        found = np.zeros(len(idx), np.uint8)
+        capi.check(capi.load().cg_layer_download_blocks(self._h, len(idx), _ptr(idx), _ptr(vox),
+                                                        _ptr(flags), _ptr(found)))
+        return vox, flags, found.astype(bool)
+
+    def hash_stats(self):
+        st = capi.HashStats()
+        capi.check(capi.load().cg_layer_hash_stats(self._h, C.byref(st)))
+        return st
+
     def upload(self, block_idx, voxels, flags=None):
         idx = np.ascontiguousarray(block_idx, np.int32).reshape(-1, 3)
         vox = np.ascontiguousarray(voxels, VOXEL_DTYPE).reshape(len(idx), capi.VOXELS_PER_BLOCK)

@@ -85,6 +85,12 @@ class StageProfile(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("ms", C.c_double), ("launches", C.c_uint64)]
 
 
+class HashStats(C.Structure):
+    _fields_ = [("num_blocks", C.c_uint64), ("max_blocks", C.c_uint64),
+                ("hash_capacity", C.c_uint64), ("load_factor", C.c_double),
+                ("mean_probe_length", C.c_double), ("max_probe_length", C.c_uint64)]
+
+
 class MergeStats(C.Structure):
     _fields_ = [("blocks_in", C.c_uint64), ("blocks_candidate", C.c_uint64),
                 ("blocks_out", C.c_uint64)]
@@ -116,6 +122,8 @@ SYMBOLS = {
     "cg_layer_num_blocks": (C.c_int64, [_P]),
     "cg_layer_voxel_size": (C.c_float, [_P]),
     "cg_layer_download": (C.c_int32, [_P, C.c_size_t, _P, _P, _P, C.POINTER(C.c_size_t)]),
+    "cg_layer_download_blocks": (C.c_int32, [_P, C.c_size_t, _P, _P, _P, _P]),
+    "cg_layer_hash_stats": (C.c_int32, [_P, C.POINTER(HashStats)]),
     "cg_layer_upload": (C.c_int32, [_P, C.c_size_t, _P, _P, _P]),
     "cg_layer_serialize": (C.c_int32, [_P, C.c_int32, C.c_size_t, _P, _P, C.POINTER(C.c_size_t)]),
     "cg_layer_reset_updated": (C.c_int32, [_P]),

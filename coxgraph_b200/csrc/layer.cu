@@ -3,6 +3,7 @@
 // TsdfVoxel as consumed at coxgraph/include/coxgraph/utils/msg_converter.h:49-50,107-109.
 #include <cub/cub.cuh>
 #include <stdarg.h>
+#include <string.h>
 #include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
@@ -177,6 +178,46 @@ __global__ void k_deserialize_write(LayerView L, const int32_t* entries, const u
   if (threadIdx.x == 0) {
     L.has_data[slot] = 1;  // Block::deserializeFromIntegers
     L.updated[slot] = 1;
+  }
+}
+
+// listed block indices -> pool slots (-1: not allocated) and packed keys, for k_gather_aos
+__global__ void k_lookup_listed(LayerView L, const int32_t* __restrict__ idx, int n,
+                                uint32_t* __restrict__ slots, uint64_t* __restrict__ keys,
+                                uint8_t* __restrict__ found) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = idx[3 * i], y = idx[3 * i + 1], z = idx[3 * i + 2];
+  constexpr int lim = kVoxIdxOffset / kVps;
+  int slot = -1;
+  uint64_t key = 0;
+  if (x >= -lim && x < lim && y >= -lim && y < lim && z >= -lim && z < lim) {
+    key = pack_block_key(x, y, z);
+    slot = L.find_slot(key);
+  }
+  slots[i] = slot < 0 ? 0u : static_cast<uint32_t>(slot);
+  keys[i] = key;
+  found[i] = slot >= 0 ? 1 : 0;
+}
+
+// probe lengths of the block hash: [0] sum over the allocated blocks, [1] maximum
+__global__ void k_probe_lengths(LayerView L, int n, unsigned long long* out) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned len = 0;
+  if (slot < n) {
+    const uint64_t key = L.block_keys[slot];
+    uint32_t h = hash_key(key) & L.hash_mask;
+    len = 1;
+    while (L.hash_keys[h] != key) {
+      h = (h + 1) & L.hash_mask;
+      ++len;
+    }
+  }
+  const unsigned sum = __reduce_add_sync(0xFFFFFFFFu, len);
+  const unsigned mx = __reduce_max_sync(0xFFFFFFFFu, len);
+  if ((threadIdx.x & 31) == 0 && sum) {
+    atomicAdd(&out[0], static_cast<unsigned long long>(sum));
+    atomicMax(&out[1], static_cast<unsigned long long>(mx));
   }
 }
 
@@ -708,6 +749,67 @@ int32_t cg_layer_download(const cg_layer* L, size_t capacity, int32_t* idx, cg_t
     CG_CUDA(cudaStreamSynchronize(s));
   }
   CG_CUDA(cudaGetLastError());
+  return CG_OK;
+}
+
+int32_t cg_layer_download_blocks(const cg_layer* L, size_t n, const int32_t* idx,
+                                 cg_tsdf_voxel* voxels, uint8_t* flags, uint8_t* found) {
+  if (!L || (n && (!idx || !found))) {
+    set_error("cg_layer_download_blocks: null argument");
+    return CG_ERR_INVALID_ARG;
+  }
+  if (n == 0) return CG_OK;
+  cg_context* ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  const size_t chunk = 2048;
+  CG_CUDA(ctx->stage_a.reserve(std::min(chunk, n) * CG_BLOCK_BYTES));
+  CG_CUDA(ctx->stage_b.reserve(std::min(chunk, n) * 3 * sizeof(int32_t)));
+  CG_CUDA(ctx->stage_c.reserve(std::min(chunk, n) * 2));
+  CG_CUDA(ctx->key_b.reserve(std::min(chunk, n) * sizeof(uint64_t)));
+  CG_CUDA(ctx->val_b.reserve(std::min(chunk, n) * sizeof(uint32_t)));
+  for (size_t first = 0; first < n; first += chunk) {
+    const size_t cnt = std::min(chunk, n - first);
+    uint8_t* d_flags = ctx->stage_c.as<uint8_t>();
+    uint8_t* d_found = d_flags + cnt;
+    CG_CUDA(cudaMemcpyAsync(ctx->stage_b.p, idx + 3 * first, cnt * 3 * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, s));
+    k_lookup_listed<<<grid_for(cnt, 256), 256, 0, s>>>(L->v, ctx->stage_b.as<int32_t>(),
+                                                       static_cast<int>(cnt), ctx->val_b.as<uint32_t>(),
+                                                       ctx->key_b.as<uint64_t>(), d_found);
+    // blocks that are not allocated come back as whatever slot 0 holds; `found` tells
+    k_gather_aos<<<static_cast<unsigned>(cnt), 256, 0, s>>>(
+        L->v, ctx->val_b.as<uint32_t>(), 0, static_cast<int>(cnt), ctx->stage_a.as<uint32_t>(),
+        nullptr, d_flags, ctx->key_b.as<uint64_t>());
+    if (voxels)
+      CG_CUDA(cudaMemcpyAsync(voxels + first * kVoxelsPerBlock, ctx->stage_a.p,
+                              cnt * CG_BLOCK_BYTES, cudaMemcpyDeviceToHost, s));
+    if (flags) CG_CUDA(cudaMemcpyAsync(flags + first, d_flags, cnt, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(cudaMemcpyAsync(found + first, d_found, cnt, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(cudaStreamSynchronize(s));
+  }
+  CG_CUDA(cudaGetLastError());
+  return CG_OK;
+}
+
+int32_t cg_layer_hash_stats(const cg_layer* L, cg_hash_stats* out) {
+  if (!L || !out) return CG_ERR_INVALID_ARG;
+  cg_context* ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  memset(out, 0, sizeof(*out));
+  out->num_blocks = static_cast<uint64_t>(L->num_blocks);
+  out->max_blocks = L->max_blocks;
+  out->hash_capacity = L->hash_cap;
+  out->load_factor = static_cast<double>(L->num_blocks) / static_cast<double>(L->hash_cap);
+  if (L->num_blocks == 0) return CG_OK;
+  CG_CUDA(ctx->stage_c.reserve(2 * sizeof(unsigned long long)));
+  CG_CUDA(cudaMemsetAsync(ctx->stage_c.p, 0, 2 * sizeof(unsigned long long), s));
+  k_probe_lengths<<<grid_for(static_cast<size_t>(L->num_blocks), 256), 256, 0, s>>>(
+      L->v, static_cast<int>(L->num_blocks), ctx->stage_c.as<unsigned long long>());
+  unsigned long long h[2] = {0, 0};
+  CG_CUDA(cudaMemcpyAsync(h, ctx->stage_c.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  CG_CUDA(cudaStreamSynchronize(s));
+  out->mean_probe_length = static_cast<double>(h[0]) / static_cast<double>(L->num_blocks);
+  out->max_probe_length = h[1];
   return CG_OK;
 }
 

@@ -125,8 +125,17 @@ def _hash_color(p):
     return torch.stack([r, g, b, a], dim=1)
 
 
-def render_frame(T_G_C, cam=CAM_640x480, device="cpu", near_box=False, stride=1):
-    """Exact ray-cast of the scene.  Returns (points_C float32 [N,3], colors uint8 [N,4])."""
+PERIOD = ROOM[0]      # the corridor scene repeats the room's objects every 12 m along x
+CORRIDOR_CAP = 40.0   # virtual end walls this far ahead of / behind the camera (every pixel hits)
+
+
+def render_frame(T_G_C, cam=CAM_640x480, device="cpu", near_box=False, stride=1, scene="room"):
+    """Exact ray-cast of the scene.  Returns (points_C float32 [N,3], colors uint8 [N,4]).
+
+    scene="room": the closed 12 x 8 x 3 m room.  scene="corridor": the same cross-section without
+    end walls, the objects repeated every 12 m along x — an unbounded environment for the long
+    trajectories of configs C3 / C4 / C5; rays along the axis end on a virtual wall
+    40 m from the camera (far beyond max_ray: they become clearing rays)."""
     dev = torch.device(device)
     W, H = cam["width"], cam["height"]
     us = torch.arange(0, W, stride, device=dev, dtype=torch.float64)
@@ -140,12 +149,23 @@ def render_frame(T_G_C, cam=CAM_640x480, device="cpu", near_box=False, stride=1)
     inf = torch.full((d_w.shape[0],), float("inf"), device=dev, dtype=torch.float64)
     t_best = inf.clone()
     # room walls (camera is inside: take the exit distance)
+    corridor = scene == "corridor"
+    ox = float(T_G_C[4])
     for a in range(3):
         da = d_w[:, a]
-        t_hi = torch.where(da > 0, (ROOM[a] - o[a]) / da, inf)
-        t_lo = torch.where(da < 0, (0.0 - o[a]) / da, inf)
+        lo_a, hi_a = 0.0, ROOM[a]
+        if corridor and a == 0:
+            lo_a, hi_a = ox - CORRIDOR_CAP, ox + CORRIDOR_CAP
+        t_hi = torch.where(da > 0, (hi_a - o[a]) / da, inf)
+        t_lo = torch.where(da < 0, (lo_a - o[a]) / da, inf)
         t_best = torch.minimum(t_best, torch.minimum(t_hi, t_lo))
-    for (cx, cy, cz, r) in SPHERES:
+    # periodic copies of the objects that can be within sensor range of the camera
+    shifts = [0.0]
+    if corridor:
+        k0 = math.floor(ox / PERIOD)
+        shifts = [PERIOD * k for k in range(k0 - 1, k0 + 2)]
+    spheres = [(cx + dx, cy, cz, r) for dx in shifts for (cx, cy, cz, r) in SPHERES]
+    for (cx, cy, cz, r) in spheres:
         c = torch.tensor([cx, cy, cz], device=dev, dtype=torch.float64)
         oc = o - c
         A = (d_w * d_w).sum(1)
@@ -156,7 +176,8 @@ def render_frame(T_G_C, cam=CAM_640x480, device="cpu", near_box=False, stride=1)
         t0 = (-B - sq) / (2 * A)
         t_hit = torch.where((disc > 0) & (t0 > 1e-6), t0, inf)
         t_best = torch.minimum(t_best, t_hit)
-    boxes = list(BOXES)
+    boxes = [(x0 + dx, y0, z0, x1 + dx, y1, z1) for dx in shifts
+             for (x0, y0, z0, x1, y1, z1) in BOXES]
     if near_box:  # a small object 5 cm in front of the lens: every point on it is closer than
         # min_ray_length_m and must be rejected (about a third of the frame)
         fwd = R[:, 2].cpu().numpy()
@@ -187,6 +208,34 @@ def submap_frames(robot, submap, frames, cam=CAM_640x480, device="cpu", stride=1
     for f in range(frames):
         pts, cols = render_frame(poses[f], cam=cam, device=device, stride=stride,
                                  near_box=((submap * frames + f) % 20 == 7))
+        out.append((poses[f], pts, cols))
+    return out
+
+
+def corridor_trajectory(first_frame, num_frames, robot=0, advance=0.2, start_x=0.0):
+    """Drive along the unbounded corridor scene: `advance` metres per frame in +x from
+    start_x, robots on different lanes (y) and heights, the camera sweeping across the walls and
+    the objects (never axis-aligned).  Frame k of a robot is the same whatever the batching."""
+    poses = []
+    for f in range(num_frames):
+        k = first_frame + f
+        s = 0.045 * k
+        y = 2.6 + 0.35 * (robot % 8) + 0.12 * math.sin(0.31 * s + robot)
+        z = 1.2 + 0.05 * (robot % 4) + 0.1 * math.sin(0.7 * s + 0.5 * robot)
+        yaw = (-1.0 if robot % 2 == 0 else 1.0) * (math.pi / 2 - 0.75) + 0.55 * math.sin(0.23 * s + 0.8 * robot)
+        pitch = 0.08 * math.sin(0.5 * s + robot)
+        roll = 0.03 * math.cos(0.4 * s)
+        poses.append(camera_pose((start_x + advance * k, y, z), yaw, pitch, roll))
+    return np.stack(poses)
+
+
+def corridor_frames(first_frame, num_frames, robot=0, advance=0.2, start_x=0.0, cam=CAM_640x480,
+                    device="cpu", stride=1):
+    """Poses + rendered frames [first_frame, first_frame + num_frames) of a corridor drive."""
+    poses = corridor_trajectory(first_frame, num_frames, robot, advance, start_x)
+    out = []
+    for f in range(num_frames):
+        pts, cols = render_frame(poses[f], cam=cam, device=device, stride=stride, scene="corridor")
         out.append((poses[f], pts, cols))
     return out
 

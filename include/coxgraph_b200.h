@@ -148,6 +148,24 @@ float cg_layer_voxel_size(const cg_layer* layer);
  * (coxgraph/include/coxgraph/map_comm/tsdf_recover.h:95). */
 int32_t cg_layer_download(const cg_layer* layer, size_t capacity_blocks, int32_t* block_idx_xyz,
                           cg_tsdf_voxel* voxels, uint8_t* flags, size_t* num_blocks_out);
+/* The listed blocks only (Layer::getBlockPtrByIndex for each index), in the order given:
+ * voxels cg_tsdf_voxel[n*4096], flags uint8[n] (either may be NULL), found uint8[n] = 1 where the
+ * block is allocated (the other outputs of a missing block are unspecified).  For layers too
+ * large to copy out whole (config C4: ~2 M blocks = 98 GB) and for incremental consumers. */
+int32_t cg_layer_download_blocks(const cg_layer* layer, size_t num_blocks,
+                                 const int32_t* block_idx_xyz, cg_tsdf_voxel* voxels,
+                                 uint8_t* flags, uint8_t* found);
+/* Occupancy of the block hash (AnyIndexHash replacement): probe length = table entries visited
+ * to find an allocated block, measured over all allocated blocks. */
+typedef struct cg_hash_stats {
+  uint64_t num_blocks;
+  uint64_t max_blocks;
+  uint64_t hash_capacity;
+  double load_factor;
+  double mean_probe_length;
+  uint64_t max_probe_length;
+} cg_hash_stats;
+int32_t cg_layer_hash_stats(const cg_layer* layer, cg_hash_stats* out);
 /* Insert / overwrite blocks (deserializeMsgToLayer hand-off,
  * coxgraph/include/coxgraph/utils/msg_converter.h:107-109). flags may be NULL (has_data). */
 int32_t cg_layer_upload(cg_layer* layer, size_t num_blocks, const int32_t* block_idx_xyz,

@@ -1,0 +1,3 @@
+timeout 900 python bench.py --config C4 --cpu-seconds 10 > gpurun_out/c4_full.json 2> gpurun_out/c4_full.err; tail -c 600 gpurun_out/c4_full.err
+timeout 600 python bench.py --config C5 --steps 5 --warmup 3 --cpu-seconds 10 > gpurun_out/c5_full.json 2> gpurun_out/c5_full.err; tail -c 600 gpurun_out/c5_full.err
+nvidia-smi --query-gpu=memory.used,memory.total --format=csv

@@ -56,3 +56,42 @@ def exact_fraction(got, ref):
            (gv["weight"].view(np.uint32) == rv["weight"].view(np.uint32)) & \
            (gv["rgba"] == rv["rgba"]).all(axis=-1)
     return float(same.mean()) if same.size else 1.0
+
+
+def margins(got, ref):
+    """How far inside the tolerance a CUDA layer is: max |d| / tol for distance and weight
+    (tol = max(ATOL, RTOL |ref|)), the colour LSB histogram and the bit-exact fraction."""
+    gi, gv, _ = got
+    ri, rv, _ = ref
+    out = {"blocks": int(len(gi)), "block_sets_equal": bool(gi.shape == ri.shape and np.array_equal(gi, ri))}
+    if not out["block_sets_equal"]:
+        return out
+    for name in ("distance", "weight"):
+        g, r = gv[name].astype(np.float64), rv[name].astype(np.float64)
+        tol = np.maximum(ATOL, RTOL * np.abs(r))
+        out[f"max_{name}_err_over_tol"] = float((np.abs(g - r) / tol).max(initial=0.0))
+    dc = np.abs(gv["rgba"].astype(np.int16) - rv["rgba"].astype(np.int16)).max(axis=-1)
+    out["colour_lsb_hist"] = [int(x) for x in np.bincount(dc.ravel(), minlength=3)[:8]]
+    out["exact_fraction"] = exact_fraction(got, ref)
+    return out
+
+
+def record_margins(name, m):
+    """Append the margins of a parity case to gpurun_out/parity_margins.json (brought back from
+    the GPU box; summarised under profiles/)."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "gpurun_out", "parity_margins.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        data = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                data = json.load(f)
+        data[name] = m
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1)
+    except OSError:
+        pass
+    print(f"[parity margins] {name}: {m}")
