@@ -238,6 +238,49 @@ def layer_diff(got, ref):
     return out
 
 
+def time_sharded(subs, poses, partial, owned, ctx, barrier, max_over_ranks, sum_over_ranks, vox,
+                 stream):
+    """The server's global merge over all ranks, timed on the device (max over ranks): every rank
+    projects its submaps into a partial layer and the partial blocks go to their owners.  Two
+    exchanges are timed: `native` = cg_project_submaps_sharded (csrc/comm.cu: the owner's fold
+    kernel pulls the blocks over NVLink peer memory, NCCL only as bootstrap and barrier, no host
+    in the data path) — the headline — and `packed` = pack + NCCL all-to-all through
+    torch.distributed + fold (round 1's path)."""
+    import torch
+    from coxgraph_b200 import sharding
+    out = {"unit": "voxels/s"}
+    native_err = None
+    try:
+        sharding.init_native(ctx)
+    except Exception as exc:  # noqa: BLE001 - reported in the JSON line, the packed path still runs
+        native_err = repr(exc)
+    for name in ("native", "packed"):
+        if name == "native" and native_err:
+            out["native_error"] = native_err
+            continue
+        times = []
+        for it in range(5):
+            owned.clear()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            if name == "native":
+                sharding.project_sharded_native(subs, poses, partial, owned)
+            else:
+                sharding.project_sharded(subs, poses, partial, owned)
+            b.record(stream)
+            barrier()
+            times.append(max_over_ranks(a.elapsed_time(b)))
+        ms = min(times[1:])
+        out[name] = {"ms": ms, "value": vox / (ms * 1e-3),
+                     "global_blocks": int(sum_over_ranks(float(owned.num_blocks)))}
+    best = "native" if "native" in out else "packed"
+    out.update(value=out[best]["value"], ms=out[best]["ms"], exchange=best,
+               collective="owner-pull over NVLink peer memory (CUDA IPC), NCCL barrier"
+               if best == "native" else "nccl all_to_all_single of packed blocks")
+    return out
+
+
 def sharded_parity(subs, poses, partial, owned, rank, world):
     """Parity evidence for the multi-GPU merge inside the bench run (the pytest for it is skipped
     on one-GPU boxes): the union of the ranks' owned layers after a sharded projection of a few
@@ -246,7 +289,10 @@ def sharded_parity(subs, poses, partial, owned, rank, world):
     import torch.distributed as dist
     from coxgraph_b200 import sharding
     owned.clear()
-    sharding.project_sharded(subs, poses, partial, owned)
+    if partial.ctx.has_comm:
+        sharding.project_sharded_native(subs, poses, partial, owned)
+    else:
+        sharding.project_sharded(subs, poses, partial, owned)
     mine = {"owned": owned.download(), "subs": [L.download() for L in subs],
             "poses": np.asarray(poses)}
     gathered = [None] * world if rank == 0 else None
@@ -534,21 +580,9 @@ def run_ours(args, rank, world, local_rank):
             from coxgraph_b200 import sharding
             partial = Layer(ctx, VOXEL_SIZE, max_blocks=65536)
             owned = Layer(ctx, VOXEL_SIZE, max_blocks=65536)
-            times = []
-            for it in range(4):
-                owned.clear()
-                barrier()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream)
-                sent, got = sharding.project_sharded(subs, T_all, partial, owned)
-                b.record(stream)
-                barrier()
-                times.append(max_over_ranks(a.elapsed_time(b)))
-            ms_sh = min(times[1:])
-            project["sharded"] = {"value": vox / (ms_sh * 1e-3), "unit": "voxels/s", "ms": ms_sh,
-                                  "submaps_total": args.project_submaps * world,
-                                  "blocks_sent": int(sum_over_ranks(float(sum(sent)))),
-                                  "collective": "nccl all_to_all_single"}
+            project["sharded"] = time_sharded(subs, T_all, partial, owned, ctx, barrier,
+                                              max_over_ranks, sum_over_ranks, vox, stream)
+            project["sharded"]["submaps_total"] = args.project_submaps * world
             project["sharded"]["parity"] = sharded_parity(
                 subs[:args.parity_submaps], T_all[:args.parity_submaps], partial, owned, rank, world)
             partial.close()

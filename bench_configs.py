@@ -328,24 +328,13 @@ def run_c3(env):
                        hbm_frac=B.BLOCK_BYTES * (st.blocks_in + 2 * st.blocks_out) / (ms * 1e-3) / 1e9 /
                        B.measured_peak_gbs()[0])
     else:
-        from coxgraph_b200 import sharding
         partial = Layer(env.ctx, 0.05, max_blocks=131072)
         owned = Layer(env.ctx, 0.05, max_blocks=131072)
-        times = []
-        for it in range(4):
-            owned.clear()
-            env.barrier()
-            a, b = env.event(), env.event()
-            a.record(env.stream)
-            sharding.project_sharded(subs, poses, partial, owned)
-            b.record(env.stream)
-            env.barrier()
-            times.append(env.reduce(a.elapsed_time(b)))
-        ms = min(times[1:])
-        project.update(ms=ms, value=vox / (ms * 1e-3), collective="all-to-all of partial blocks",
-                       global_blocks=int(env.reduce(owned.num_blocks, "sum")),
-                       parity=B.sharded_parity(subs[:args.parity_submaps], poses[:args.parity_submaps],
-                                               partial, owned, env.rank, env.world))
+        project.update(B.time_sharded(subs, poses, partial, owned, env.ctx, env.barrier,
+                                      lambda x: env.reduce(x, "max"), lambda x: env.reduce(x, "sum"),
+                                      vox, env.stream))
+        project["parity"] = B.sharded_parity(subs[:args.parity_submaps], poses[:args.parity_submaps],
+                                             partial, owned, env.rank, env.world)
         partial.close()
         owned.close()
     extra = {"project_submaps": project}

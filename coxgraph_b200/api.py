@@ -48,6 +48,7 @@ class Context:
         capi.check(capi.load().cg_context_create(int(device), C.c_void_p(stream or 0),
                                                  C.byref(self._h)))
         self.device = int(device)
+        self.has_comm = False   # commInit done (multi-GPU merge through the C ABI)
 
     def synchronize(self):
         capi.check(capi.load().cg_context_synchronize(self._h))
@@ -362,6 +363,37 @@ def getProjectedMap(submap_layers, submap_poses, global_layer, want_stats=False)
     capi.check(capi.load().cg_project_submaps(arr, _ptr(P), n, global_layer._h,
                                               C.byref(st) if want_stats else None))
     return st if want_stats else None
+
+
+def commUniqueId():
+    """ncclGetUniqueId as bytes: made on one rank, handed to every rank by the host."""
+    buf = (C.c_uint8 * 128)()
+    capi.check(capi.load().cg_comm_get_unique_id(buf))
+    return bytes(buf)
+
+
+def commInit(ctx, unique_id, rank, nranks):
+    """Communicator of the multi-GPU merge on the context's GPU (collective over the ranks)."""
+    buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+    capi.check(capi.load().cg_comm_init(ctx._h, buf, int(rank), int(nranks)))
+    ctx.has_comm = True
+
+
+def gatherGlobal(partial_layer, owned_layer):
+    """Collective: every rank's partial global blocks go to their owners (fold over NVLink peer
+    memory, ascending source rank).  Returns the number of blocks folded into owned_layer."""
+    n = C.c_uint64(0)
+    capi.check(capi.load().cg_gather_global(partial_layer._h, owned_layer._h, C.byref(n)))
+    return int(n.value)
+
+
+def getProjectedMapSharded(submap_layers, submap_poses, partial_layer, owned_layer):
+    """getProjectedMap() over all ranks: this rank's submaps -> partial_layer, then gatherGlobal."""
+    n = len(submap_layers)
+    P = np.ascontiguousarray(submap_poses, np.float32).reshape(n, 7)
+    arr = (C.c_void_p * max(n, 1))(*[l._h for l in submap_layers])
+    capi.check(capi.load().cg_project_submaps_sharded(arr, _ptr(P) if n else None, n,
+                                                      partial_layer._h, owned_layer._h, None))
 
 
 def reprojectSubmaps(submap_layers, poses_old, poses_new, global_layer, eps_translation=0.0,

@@ -156,6 +156,11 @@ SYMBOLS = {
     "cg_block_owner": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "cg_layer_pack_by_owner": (C.c_int32, [_P, C.c_int32, _P, C.c_size_t, _P]),
     "cg_layer_merge_packed": (C.c_int32, [_P, _P, C.c_size_t]),
+    "cg_comm_get_unique_id": (C.c_int32, [_P]),
+    "cg_comm_init": (C.c_int32, [_P, _P, C.c_int32, C.c_int32]),
+    "cg_comm_destroy": (C.c_int32, [_P]),
+    "cg_gather_global": (C.c_int32, [_P, _P, C.POINTER(C.c_uint64)]),
+    "cg_project_submaps_sharded": (C.c_int32, [_P, _P, C.c_size_t, _P, _P, C.POINTER(MergeStats)]),
     "cg_debug_selftest": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.POINTER(C.c_uint64)]),
 }
 

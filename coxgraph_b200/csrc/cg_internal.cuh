@@ -210,8 +210,11 @@ struct PendingEvent {
 
 }  // namespace cg
 
+struct cg_comm;  // comm.cu: communicator + peer mappings of the multi-GPU merge
+
 struct cg_context {
   int device = 0;
+  cg_comm* comm = nullptr;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t wait_event = nullptr;         // cg_context_wait_stream

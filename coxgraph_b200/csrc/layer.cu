@@ -494,6 +494,7 @@ int32_t cg_context_destroy(cg_context* ctx) {
   if (!ctx) return CG_ERR_INVALID_ARG;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  cg_comm_destroy(ctx);
   DevBuf* bufs[] = {&ctx->points, &ctx->colors, &ctx->poses, &ctx->frame_base, &ctx->key_a,
                     &ctx->key_b, &ctx->val_a, &ctx->val_b, &ctx->flags, &ctx->scan,
                     &ctx->cub_tmp, &ctx->rays, &ctx->ray_count, &ctx->ray_offset, &ctx->sorted_pts, &ctx->pkey_a,

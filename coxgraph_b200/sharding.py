@@ -126,3 +126,22 @@ def project_sharded(local_submaps, local_poses, partial_layer, owned_layer, grou
     if len(local_submaps):
         getProjectedMap(local_submaps, local_poses, partial_layer)
     return gather_global(partial_layer, owned_layer, group)
+
+
+def init_native(ctx, group=None):
+    """cg_comm_init for every rank of a torch.distributed group: rank 0's ncclGetUniqueId goes
+    round with broadcast_object_list (host plumbing only; the exchange itself is in the library,
+    csrc/comm.cu)."""
+    import torch.distributed as dist
+    from .api import commInit, commUniqueId
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [commUniqueId() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    commInit(ctx, box[0], rank, world)
+
+
+def project_sharded_native(local_submaps, local_poses, partial_layer, owned_layer):
+    """project_sharded through the C ABI alone (cg_project_submaps_sharded): owner-pull over
+    NVLink peer memory, no torch in the data path.  Needs init_native(ctx) once."""
+    from .api import getProjectedMapSharded
+    getProjectedMapSharded(local_submaps, local_poses, partial_layer, owned_layer)

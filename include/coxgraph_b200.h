@@ -335,6 +335,31 @@ int32_t cg_layer_pack_by_owner(const cg_layer* layer, int32_t nranks, void* d_pa
 /* Fold `num_blocks` packed records (device memory) into `layer` in record order. */
 int32_t cg_layer_merge_packed(cg_layer* layer, const void* d_packed, size_t num_blocks);
 
+/* --- the same exchange without the host in the data path (SURVEY.md §8b cg_comm_init /
+ * cg_gather_global): one process per GPU of one box.  Rank 0 makes a unique id
+ * (cg_comm_get_unique_id = ncclGetUniqueId) and the host hands it to every rank (MPI, a TCP store,
+ * a ROS parameter ...); cg_comm_init builds the NCCL communicator on the context's GPU.
+ * cg_gather_global is collective: every rank passes ITS partial global layer (all created with
+ * the same voxel size and max_blocks) and the layer it owns; on return `owned` has received, in
+ * ascending source-rank order, every partial block of every rank that cg_block_owner assigns to
+ * this rank (2-argument mergeLayerAintoLayerB semantics, coxgraph/src/server/
+ * submap_collection.cpp:31-33), read by the fold kernel straight from the peers' block pools over
+ * NVLink (CUDA IPC peer mappings, opened the first time a partial layer is used); NCCL is the
+ * bootstrap and the stream-ordered barrier.  The partial layer may be cleared or refilled as soon
+ * as the call returns.  cg_project_submaps_sharded = cg_layer_clear(partial) +
+ * cg_project_submaps(this rank's submaps -> partial) + cg_gather_global: cblox getProjectedMap()
+ * (coxgraph/src/server/visualizer/server_visualizer.cpp:123-126) over all ranks. */
+#define CG_COMM_ID_BYTES 128
+int32_t cg_comm_get_unique_id(uint8_t id[CG_COMM_ID_BYTES]);
+int32_t cg_comm_init(cg_context* ctx, const uint8_t id[CG_COMM_ID_BYTES], int32_t rank,
+                     int32_t nranks);
+int32_t cg_comm_destroy(cg_context* ctx);
+int32_t cg_gather_global(const cg_layer* partial_layer, cg_layer* owned_layer,
+                         uint64_t* blocks_folded);
+int32_t cg_project_submaps_sharded(const cg_layer* const* submaps, const float* T_M_S_poses,
+                                   size_t num_submaps, cg_layer* partial_layer,
+                                   cg_layer* owned_layer, cg_merge_stats* stats);
+
 /* --- self checks of device arithmetic shortcuts (which: 0 = exact division through a
  * precomputed reciprocal, 1 = round-half-away, 2 = RayCaster state at block entries computed
  * without walking, `samples` random rays); *mismatches must come back 0.  which = 3 runs the same

@@ -52,8 +52,27 @@ def main():
                                          partial, owned)
     oi, ov, of = owned.download()
     assert (sharding.block_owners(oi, world) == rank).all(), "a rank holds a block it does not own"
+    # the same exchange through the C ABI alone (csrc/comm.cu: owner-pull over NVLink peer memory,
+    # NCCL as bootstrap and barrier): must give bit-identical owned layers, twice in a row (the
+    # second call reuses the peer mappings and the cleared partial layer)
+    native_ok, native_err = True, ""
+    try:
+        sharding.init_native(ctx)
+        owned2 = Layer(ctx, 0.05, max_blocks=8192)
+        for rep in range(2):
+            owned2.clear()
+            sharding.project_sharded_native(layers, np.stack(poses) if poses else np.zeros((0, 7)),
+                                            partial, owned2)
+            ni, nv, nf = owned2.download()
+            native_ok = native_ok and np.array_equal(ni, oi) and \
+                np.array_equal(nv["distance"].view(np.uint32), ov["distance"].view(np.uint32)) and \
+                np.array_equal(nv["weight"].view(np.uint32), ov["weight"].view(np.uint32)) and \
+                np.array_equal(nv["rgba"], ov["rgba"]) and np.array_equal(nf & 1, of & 1)
+        owned2.close()
+    except Exception as e:  # noqa: BLE001 - reported through the gathered flags below
+        native_ok, native_err = False, repr(e)
     gathered = [None] * world
-    dist.all_gather_object(gathered, (oi, ov, of, sent, got))
+    dist.all_gather_object(gathered, (oi, ov, of, sent, got, native_ok, native_err))
     ok = True
     if rank == 0:
         from oracle import oracle_py as orc
@@ -75,8 +94,25 @@ def main():
             util.compare_layers((gi[order], gv[order], gf[order]), expect.download(),
                                 f"{world}-GPU sharded merge")
             assert sum(sum(g[3]) for g in gathered) == sum(sum(g[4]) for g in gathered)
+            assert all(g[5] for g in gathered), \
+                f"native (C ABI) exchange differs from the packed one: {[g[6] for g in gathered]}"
+            # against the reference's single left fold over all submaps (rank-major
+            # order), where the sharded plan re-associates: margins, not only pass / fail
+            single = orc.Layer(0.05)
+            for r in range(world):
+                for sid in sharding.assign_submaps(ROBOTS, SUBMAPS_PER_ROBOT, world)[r]:
+                    fr, T_M_S = frames_of(sid)
+                    L = orc.Layer(0.05)
+                    for (T, p, c) in fr:
+                        L.integrate(ocfg, T, p, c)
+                    single.merge_from(L, T_M_S)
+            m = util.margins((gi[order], gv[order], gf[order]), single.download())
+            print(f"margins vs the single-process left fold: {m}", flush=True)
+            util.compare_layers((gi[order], gv[order], gf[order]), single.download(),
+                                f"{world}-GPU sharded merge vs single left fold")
             print(f"multigpu_check ok: world {world}, {len(gi)} global blocks, "
-                  f"records exchanged {sum(sum(g[3]) for g in gathered)}", flush=True)
+                  f"records exchanged {sum(sum(g[3]) for g in gathered)}, native exchange identical",
+                  flush=True)
         except AssertionError as e:
             print("multigpu_check FAILED:", e, flush=True)
             ok = False
