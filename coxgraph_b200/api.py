@@ -309,8 +309,47 @@ def _integrate_staged(self, slot, poses, frame_offsets, freespace_points=False):
     return self.last_stats
 
 
+def _prepare_batch(self, slot, poses, points_C, colors, frame_offsets, freespace_points=False):
+    """Queue the layer-independent first half of a LATER integrateBatch job (device tensors) on the
+    context's second stream; integratePrepared(slot) completes it.  Keep the tensors alive and
+    unchanged until then."""
+    P = np.ascontiguousarray(poses, np.float32).reshape(-1, 7)
+    offs = np.ascontiguousarray(frame_offsets, np.uint64).reshape(-1)
+    if len(offs) != len(P) + 1:
+        raise ValueError("frame_offsets must have F+1 entries")
+    assert _is_cuda_tensor(points_C) and _is_cuda_tensor(colors)
+    assert points_C.is_contiguous() and colors.is_contiguous()
+    self.layer.ctx.wait_torch()
+    capi.check(capi.load().cg_prepare_batch_device(
+        self.layer._h, C.byref(self.config), len(P), _ptr(P), C.c_void_p(points_C.data_ptr()),
+        C.c_void_p(colors.data_ptr()), _ptr(offs), int(freespace_points), int(slot)))
+    self._prepared = getattr(self, "_prepared", {})
+    self._prepared[int(slot)] = (points_C, colors)
+
+
+def _prepare_staged(self, slot, stage_slot, poses, frame_offsets, freespace_points=False):
+    """The same for inputs staged with stageBatch(stage_slot, ...)."""
+    P = np.ascontiguousarray(poses, np.float32).reshape(-1, 7)
+    offs = np.ascontiguousarray(frame_offsets, np.uint64).reshape(-1)
+    if len(offs) != len(P) + 1:
+        raise ValueError("frame_offsets must have F+1 entries")
+    capi.check(capi.load().cg_prepare_batch_staged(
+        self.layer._h, C.byref(self.config), len(P), _ptr(P), int(stage_slot), _ptr(offs),
+        int(freespace_points), int(slot)))
+
+
+def _integrate_prepared(self, slot):
+    capi.check(capi.load().cg_integrate_prepared(self.layer._h, int(slot),
+                                                 C.byref(self.last_stats)))
+    getattr(self, "_prepared", {}).pop(int(slot), None)
+    return self.last_stats
+
+
 TsdfIntegrator.stageBatch = _stage_batch
 TsdfIntegrator.integrateStaged = _integrate_staged
+TsdfIntegrator.prepareBatch = _prepare_batch
+TsdfIntegrator.prepareStaged = _prepare_staged
+TsdfIntegrator.integratePrepared = _integrate_prepared
 
 
 def meshToFrames(ctx, mesh, interpolate_voxel_size, poses, stamps_sec):

@@ -142,6 +142,11 @@ SYMBOLS = {
     "cg_stage_batch_async": (C.c_int32, [_P, C.c_int32, _P, _P, C.c_size_t]),
     "cg_integrate_batch_staged": (C.c_int32, [_P, C.POINTER(IntegratorConfig), C.c_size_t, _P,
                                               C.c_int32, _P, C.c_int32, C.POINTER(IntegrateStats)]),
+    "cg_prepare_batch_device": (C.c_int32, [_P, C.POINTER(IntegratorConfig), C.c_size_t, _P, _P, _P,
+                                            _P, C.c_int32, C.c_int32]),
+    "cg_prepare_batch_staged": (C.c_int32, [_P, C.POINTER(IntegratorConfig), C.c_size_t, _P,
+                                            C.c_int32, _P, C.c_int32, C.c_int32]),
+    "cg_integrate_prepared": (C.c_int32, [_P, C.c_int32, C.POINTER(IntegrateStats)]),
     "cg_mesh_to_frames": (C.c_int32, [_P, C.POINTER(Mesh), C.c_float, C.c_size_t, _P, _P, _P, _P, _P,
                                       C.c_size_t]),
     "cg_recover_mesh": (C.c_int32, [_P, C.POINTER(IntegratorConfig), C.POINTER(Mesh), C.c_float,

@@ -208,11 +208,36 @@ struct PendingEvent {
   cudaEvent_t start, stop;
 };
 
+// Everything a job's layer-independent front half (points -> one ray per bundle, integrate.cu)
+// writes and its back half reads.  The context is set 0 (plain calls); cg_prepare_batch_* uses
+// further sets on a second stream so that the front half of a later job overlaps the back half of
+// the current one.
+struct FrontBufs {
+  void* h_tables = nullptr;                 // pinned + mapped: poses / frame offsets of the job
+  size_t h_tables_cap = 0;
+  const float* group_poses = nullptr;       // device poses of the group being fused
+  int group_frames = 0;
+  CallCounters* h_counters = nullptr;       // pinned
+  CallCounters* d_counters = nullptr;
+  DevBuf poses, frame_base;
+  DevBuf key_a, key_b, scan, cub_tmp;
+  DevBuf rays, ray_count, ray_offset, sorted_pts;
+  DevBuf scan_partials;
+  DevBuf grazing_keys, grazing_ray_key;     // anti-grazing: the scan's bundle voxels
+  uint32_t grazing_mask = 0;
+  uint32_t* d_class_count = nullptr;        // bundle size-class histogram + scatter cursors
+  int* d_key_bounds = nullptr;              // [6] running min / max of the bundle voxel fields
+  uint32_t* d_select_count = nullptr;       // output count of the stream compactions
+  int32_t* d_front_err = nullptr;           // error bits of a prepared front half (sets > 0)
+};
+cudaError_t init_front_words(FrontBufs& fb);  // the small device / pinned words of a set
+void release_front(FrontBufs& fb);
+
 }  // namespace cg
 
 struct cg_comm;  // comm.cu: communicator + peer mappings of the multi-GPU merge
 
-struct cg_context {
+struct cg_context : cg::FrontBufs {
   int device = 0;
   cg_comm* comm = nullptr;
   cudaStream_t stream = nullptr;
@@ -220,32 +245,21 @@ struct cg_context {
   cudaEvent_t wait_event = nullptr;         // cg_context_wait_stream
   cudaStream_t copy_stream = nullptr;       // pipelined host->device transfers (lazy)
   std::vector<cudaEvent_t> copy_events;
-  void* h_tables = nullptr;                 // pinned + mapped: poses / frame offsets of the job
-  size_t h_tables_cap = 0;
   cg::DevBuf stage_pts[2], stage_cols[2];   // cg_stage_batch_async double buffer
   cudaEvent_t stage_ready[2] = {nullptr, nullptr};
   size_t stage_points[2] = {0, 0};
-  const float* group_poses = nullptr;       // device poses of the group being fused
-  int group_frames = 0;
   int num_sms = 148;
-  cg::CallCounters* h_counters = nullptr;  // pinned
-  cg::CallCounters* d_counters = nullptr;
   // integration scratch
-  cg::DevBuf points, colors, poses, frame_base;
-  cg::DevBuf key_a, key_b, val_a, val_b, flags, scan, cub_tmp;
-  cg::DevBuf rays, ray_count, ray_offset, sorted_pts;
+  cg::DevBuf points, colors;
+  cg::DevBuf val_a, val_b, flags;
   cg::DevBuf pkey_a, pkey_b, seg_start, long_list, long_partials;
   cg::DevBuf seg_keys_a, seg_keys_b, seg_idx_a, seg_idx_b, seg_recs;  // (ray, block) segments
   cg::DevBuf seg_order;  // update lists in size-class order
-  cg::DevBuf scan_partials, seg_bins;
-  cg::DevBuf grazing_keys, grazing_ray_key;  // anti-grazing: the scan's bundle voxels
-  uint32_t grazing_mask = 0;
+  cg::DevBuf seg_bins;
   // per-call touch set (integrate.cu "back half"): kept all-clear between calls
   cg::DevBuf touch_ord, touch_entry, touch_acc, touch_bits;
   uint32_t* d_touch_count = nullptr;  // [0] blocks touched, [1] general (voxel, ray) keys emitted
-  uint32_t* d_class_count = nullptr;    // bundle size-class histogram + scatter cursors
   uint32_t* d_walk_counters = nullptr;  // [0],[1] dynamic work counters, [2] bundle key reach
-  int* d_key_bounds = nullptr;          // [6] running min / max of the bundle voxel fields
   bool key_box_valid = false;           // bundle key layout (adaptive): union of the extents
   int key_lo[3] = {0, 0, 0}, key_hi[3] = {0, 0, 0};  // measured by the jobs of this context
   int key_win_lo[3] = {0, 0, 0}, key_win_hi[3] = {0, 0, 0}, key_win_jobs = 0;  // last <= 8 measured jobs
@@ -254,7 +268,6 @@ struct cg_context {
   size_t touch_cap = 0;               // blocks the scratch holds
   bool touch_clean = false;
   unsigned long long* d_long_counter = nullptr;  // (#long segments << 32) | #sub-blocks
-  uint32_t* d_select_count = nullptr;  // output count of the stream compactions
   uint32_t* d_work_counter = nullptr;  // dynamic work distribution of the persistent kernels
   // merge / transfer scratch
   cg::DevBuf cand_keys, cand_list, stage_a, stage_b, stage_c;
@@ -268,6 +281,21 @@ struct cg_context {
   // instrumentation
   bool profiling = false;
   uint64_t own_launches = 0;  // kernels of this library launched (library sorts/scans excluded)
+  // pipelined jobs (cg_prepare_batch_*): two further front-half sets on their own stream
+  cg::FrontBufs prep[2];
+  cudaStream_t prep_stream = nullptr;
+  cudaEvent_t prep_done[2] = {nullptr, nullptr};
+  struct PreparedJob {
+    bool valid = false;
+    cg_integrator_config cfg;
+    std::vector<float> poses;
+    std::vector<uint64_t> offs;  // relative to the job's first point
+    const float* d_points = nullptr;
+    const uint8_t* d_colors = nullptr;
+    int freespace = 0;
+    float voxel_size = 0.0f;
+    bool front_queued = false;   // false: the job did not fit the one-group fast path
+  } prepared[2];
   double stage_ms[cg::kNumStages] = {};
   uint64_t stage_launches[cg::kNumStages] = {};
   std::vector<cg::PendingEvent> pending;
@@ -306,18 +334,20 @@ struct StageScope {
   cg_context* ctx;
   int stage;
   cudaEvent_t start = nullptr, stop = nullptr;
-  StageScope(cg_context* c, int st, int own_kernels) : ctx(c), stage(st) {
+  cudaStream_t stream;
+  StageScope(cg_context* c, int st, int own_kernels, cudaStream_t on = nullptr)
+      : ctx(c), stage(st), stream(on ? on : c->stream) {
     ctx->own_launches += own_kernels;
     ctx->stage_launches[st] += own_kernels;
     if (ctx->profiling) {
       start = take();
       stop = take();
-      cudaEventRecord(start, ctx->stream);
+      cudaEventRecord(start, stream);
     }
   }
   ~StageScope() {
     if (start) {
-      cudaEventRecord(stop, ctx->stream);
+      cudaEventRecord(stop, stream);
       ctx->pending.push_back(PendingEvent{stage, start, stop});
     }
   }

@@ -622,9 +622,10 @@ k_scan_totals(const uint32_t* __restrict__ num_rays, unsigned long long* __restr
   Scan(tmp).ExclusiveSum(v, v, total);
   if (static_cast<int>(threadIdx.x) < num_partials) partials[threadIdx.x] = v;
   if (threadIdx.x == 0) {
-    const int e = *err;  // a point outside the group's key layout: the host widens it / regroups
-    c->err = e & kErrKeyRange;
-    if (e & kErrKeyRange) *err = e & ~kErrKeyRange;
+    // a point outside the group's key layout: the host widens it / regroups (atomic: a prepared
+    // front half runs beside another job's back half, which may flag errors in the same word)
+    const int e = atomicAnd(err, ~kErrKeyRange);
+    c->err = e & (kErrKeyRange | kErrOutOfRange);
     for (int a = 0; a < 3; ++a) {
       c->key_lo[a] = key_bounds[a];
       c->key_hi[a] = key_bounds[3 + a];
@@ -1732,9 +1733,9 @@ __global__ void k_collect_walk(LayerView L, const uint32_t* touch_count, CallCou
   if (e & (kErrTouchFull | kErrSegmentFull)) *L.err = e & ~(kErrTouchFull | kErrSegmentFull);
 }
 
-static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParams& P,
-                             uint32_t num_rays, size_t num_pairs, size_t num_segments,
-                             cg_integrate_stats* stats) {
+static int32_t run_back_half(cg_context* ctx, const FrontBufs& fb, cg_layer* L,
+                             const IntegratorParams& P, uint32_t num_rays, size_t num_pairs,
+                             size_t num_segments, cg_integrate_stats* stats) {
   cudaStream_t s = ctx->stream;
   if (num_pairs >= 0xFFFFFFF0ull) {
     set_error("too many voxel visits in one group");
@@ -1784,18 +1785,18 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
     CG_CUDA(fill_bytes(ctx->d_walk_counters, 0, 2 * sizeof(uint32_t), s));
     {
       StageScope sc(ctx, kStageWalkSegments, 2);
-      const GrazingSet gz{ctx->grazing_keys.as<unsigned long long>(), ctx->grazing_mask,
-                          ctx->grazing_ray_key.as<unsigned long long>()};
+      const GrazingSet gz{fb.grazing_keys.as<unsigned long long>(), fb.grazing_mask,
+                          fb.grazing_ray_key.as<unsigned long long>()};
       if (P.anti_grazing)
         k_walk_segments<true><<<walk_grid, kWalkThreads, 0, s>>>(
-            P, ctx->group_poses, ctx->rays.as<Ray>(), num_rays,
-            ctx->ray_count.as<unsigned long long>(), ctx->ray_offset.as<unsigned long long>(),
+            P, fb.group_poses, fb.rays.as<Ray>(), num_rays,
+            fb.ray_count.as<unsigned long long>(), fb.ray_offset.as<unsigned long long>(),
             slack, L->v, tv, tail_visits, null_key, ctx->d_walk_counters, sk.Current(),
             sv.Current(), ctx->seg_recs.as<uint4>(), gz);
       else
         k_walk_segments<false><<<walk_grid, kWalkThreads, 0, s>>>(
-            P, ctx->group_poses, ctx->rays.as<Ray>(), num_rays,
-            ctx->ray_count.as<unsigned long long>(), ctx->ray_offset.as<unsigned long long>(),
+            P, fb.group_poses, fb.rays.as<Ray>(), num_rays,
+            fb.ray_count.as<unsigned long long>(), fb.ray_offset.as<unsigned long long>(),
             slack, L->v, tv, tail_visits, null_key, ctx->d_walk_counters, sk.Current(),
             sv.Current(), ctx->seg_recs.as<uint4>(), gz);
       if (L->num_blocks > 0)
@@ -1839,7 +1840,7 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
     {
       StageScope sc(ctx, kStageBlockAccumulate, 2);
       k_block_accumulate<<<ctx->num_sms * 5, kAccThreads, 0, s>>>(
-          P, ctx->rays.as<Ray>(), sorted_keys, sorted_idx, ctx->seg_recs.as<uint4>(),
+          P, fb.rays.as<Ray>(), sorted_keys, sorted_idx, ctx->seg_recs.as<uint4>(),
           static_cast<uint32_t>(num_slots), num_real, null_key, tv, acc_scale, ray_bits,
           ctx->pkey_a.as<unsigned long long>(), ctx->d_touch_count + 1,
           static_cast<uint32_t>(num_pairs), ctx->d_walk_counters + 1);
@@ -1916,18 +1917,18 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
       k_segment_order<<<ogrid, 256, 0, s>>>(ctx->seg_start.as<uint32_t>(), d_num, n_general,
                                             ctx->d_class_count, ctx->seg_order.as<uint32_t>());
       k_voxel_update<<<ctx->num_sms * 8, 128, 0, s>>>(
-          P, ctx->group_poses, ctx->rays.as<Ray>(), dk.Current(), ray_bits, n_general,
+          P, fb.group_poses, fb.rays.as<Ray>(), dk.Current(), ray_bits, n_general,
           ctx->seg_start.as<uint32_t>(), d_num, ctx->seg_order.as<uint32_t>(), ctx->d_work_counter,
-          ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv, ctx->group_frames);
+          ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv, fb.group_frames);
     }
     {
       StageScope sc(ctx, kStageReplayWide, 2);
       k_long_partials<<<ctx->num_sms * 8, 256, 0, s>>>(
-          P, ctx->group_poses, ctx->rays.as<Ray>(), dk.Current(), ray_bits,
+          P, fb.group_poses, fb.rays.as<Ray>(), dk.Current(), ray_bits,
           ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv,
           ctx->long_partials.as<LongPartial>());
       k_long_finish<<<ctx->num_sms * 4, 256, 0, s>>>(
-          P, ctx->group_poses, ctx->rays.as<Ray>(), dk.Current(), ray_bits,
+          P, fb.group_poses, fb.rays.as<Ray>(), dk.Current(), ray_bits,
           ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv,
           ctx->long_partials.as<LongPartial>());
     }
@@ -1946,31 +1947,30 @@ static int32_t run_back_half(cg_context* ctx, cg_layer* L, const IntegratorParam
   return CG_OK;
 }
 
-// frames [f0, f1) of the job as one group; splits itself when the pair list would not fit
-static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
-                               const IntegratorParams& P, const float* h_poses,
-                               const float* d_points, const uint8_t* d_colors,
-                               const uint64_t* offs, size_t f0, size_t f1,
-                               cg_integrate_stats* stats, int attempt = 0) {
-  cg_context* ctx = L->ctx;
-  cudaStream_t s = ctx->stream;
+constexpr int kKeySlack = 16, kKeyLimit = 8191;  // |rel| <= 8191: the anti-grazing set packs 14 bits
+
+// Front half of frames [f0, f1) of a job (points -> one ray per bundle, R1 / R2 / R6), queued on
+// stream `s` into the set `fb`: nothing here touches the layer.  The counters the back half needs
+// (rays, voxel visits, segments, key extent, errors) are copied to fb.h_counters at the end; the
+// caller synchronises.  *need_split: the bundle keys do not fit, the caller halves the group.
+static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int32_t* d_err,
+                             const cg_layer* L, const cg_integrator_config* cfg,
+                             const IntegratorParams& P, const float* d_points,
+                             const uint8_t* d_colors, const uint64_t* offs, size_t f0, size_t f1,
+                             int attempt, bool* need_split) {
+  *need_split = false;
   const size_t F = f1 - f0;
   const size_t total = offs[f1] - offs[f0];  // points of the group = upper bound on rays
-  if (total == 0) return CG_OK;
-  if (total > 0x7FFFFFF0ull || F > (1u << 20)) {
-    set_error("too many points / frames in one group");
-    return CG_ERR_INVALID_ARG;
-  }
   const size_t upper = total + 1;  // + the sentinel bundle of dropped points
-  CG_CUDA(ctx->rays.reserve(upper * sizeof(Ray)));
-  CG_CUDA(ctx->ray_count.reserve(upper * sizeof(unsigned long long)));
-  CG_CUDA(ctx->ray_offset.reserve(upper * sizeof(unsigned long long)));
-  CG_CUDA(ctx->scan.reserve(upper * sizeof(uint32_t)));  // bundle heads / valid slots
+  CG_CUDA(fb.rays.reserve(upper * sizeof(Ray)));
+  CG_CUDA(fb.ray_count.reserve(upper * sizeof(unsigned long long)));
+  CG_CUDA(fb.ray_offset.reserve(upper * sizeof(unsigned long long)));
+  CG_CUDA(fb.scan.reserve(upper * sizeof(uint32_t)));  // bundle heads / valid slots
   const bool merged = cfg->method == CG_METHOD_MERGED;
   if (merged) {
-    CG_CUDA(ctx->key_a.reserve(total * sizeof(uint64_t)));
-    CG_CUDA(ctx->key_b.reserve(total * sizeof(uint64_t)));
-    CG_CUDA(ctx->sorted_pts.reserve(total * sizeof(float4)));
+    CG_CUDA(fb.key_a.reserve(total * sizeof(uint64_t)));
+    CG_CUDA(fb.key_b.reserve(total * sizeof(uint64_t)));
+    CG_CUDA(fb.sorted_pts.reserve(total * sizeof(float4)));
   }
   // bundle key layout of this group: as many bits per voxel axis as fit beside the frame field
   // and the visit rank (at most 13: +-4096 voxels around the sensor)
@@ -1984,7 +1984,6 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   // some slack around it), or — first job — a cube around the sensor sized for the sensor range
   // with x4 head room for clearing points beyond max_ray.  Fewer bits = fewer radix passes.  A
   // point outside the box flags kErrKeyRange and the group is redone with the measured extent.
-  constexpr int kKeySlack = 16, kKeyLimit = 8191;  // |rel| <= 8191: the anti-grazing set packs 14 bits
   // measuring the extent costs a few hundred thousand atomics: first job, retries, every 64th job
   // (CG_KEY_MEASURE_PERIOD overrides the 64; the tests set it to 1 to reach the shrinking window)
   const unsigned period = static_cast<unsigned>(std::max<size_t>(1, env_size("CG_KEY_MEASURE_PERIOD", 64)));
@@ -2006,142 +2005,147 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   }
   if (merged && kl.bits[0] + kl.bits[1] + kl.bits[2] > avail_total) {
     if (F > 1) {  // fewer frames per group leave more bits for the voxel fields
-      const size_t mid = f0 + F / 2;
-      int32_t rc = integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, mid, stats);
-      if (rc) return rc;
-      return integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, mid, f1, stats);
+      *need_split = true;
+      return CG_OK;
     }
     set_error("a single frame of %zu points is too large; split the point cloud", total);
     return CG_ERR_INVALID_ARG;
   }
   const int bundle_end_bit = kl.frame_shift() + frame_bits;
-  cub::DoubleBuffer<uint64_t> dk(ctx->key_a.as<uint64_t>(), ctx->key_b.as<uint64_t>());
+  cub::DoubleBuffer<uint64_t> dk(fb.key_a.as<uint64_t>(), fb.key_b.as<uint64_t>());
   thrust::counting_iterator<uint32_t> iota(0);
-  uint32_t* d_num = ctx->d_select_count;
+  uint32_t* d_num = fb.d_select_count;
   // the job's poses and frame offsets were uploaded once by integrate_job
   const float* pts = d_points + 3 * offs[f0];
   const uint32_t* cols = reinterpret_cast<const uint32_t*>(d_colors) + offs[f0];
-  const FrameTable ft{ctx->frame_base.as<uint64_t>() + f0, offs[f0] - offs[0], static_cast<int>(F)};
-  ctx->group_poses = ctx->poses.as<float>() + 7 * f0;
-  ctx->group_frames = static_cast<int>(F);
+  const FrameTable ft{fb.frame_base.as<uint64_t>() + f0, offs[f0] - offs[0], static_cast<int>(F)};
+  fb.group_poses = fb.poses.as<float>() + 7 * f0;
+  fb.group_frames = static_cast<int>(F);
   ValidSlot valid{P, ft, pts};
   size_t tmp_sort = 0, tmp_sel = 0;
   if (merged) {
     cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, dk, static_cast<int>(total), kl.rank_bits,
                                    bundle_end_bit, s);
-    cub::DeviceSelect::If(nullptr, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
+    cub::DeviceSelect::If(nullptr, tmp_sel, iota, fb.scan.as<uint32_t>(), d_num,
                           static_cast<int>(total), BundleHead{nullptr, 0}, s);
   } else {
-    cub::DeviceSelect::If(nullptr, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
+    cub::DeviceSelect::If(nullptr, tmp_sel, iota, fb.scan.as<uint32_t>(), d_num,
                           static_cast<int>(total), valid, s);
   }
-  CG_CUDA(ctx->cub_tmp.reserve(std::max(tmp_sort, tmp_sel)));
+  CG_CUDA(fb.cub_tmp.reserve(std::max(tmp_sort, tmp_sel)));
   if (merged) {
     {
-      StageScope sc(ctx, kStagePointKeys, 1);
-      k_point_keys<<<grid_for(total, 256), 256, 0, s>>>(P, kl, ctx->group_poses, ft, pts, total,
-                                                        ctx->key_a.as<uint64_t>(), L->v.err,
-                                                        measure ? ctx->d_key_bounds : nullptr);
+      StageScope sc(ctx, kStagePointKeys, 1, s);
+      k_point_keys<<<grid_for(total, 256), 256, 0, s>>>(P, kl, fb.group_poses, ft, pts, total,
+                                                        fb.key_a.as<uint64_t>(), d_err,
+                                                        measure ? fb.d_key_bounds : nullptr);
     }
     {
-      StageScope sc(ctx, kStageBundleSort, 0);
-      CG_CUDA(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tmp_sort, dk, static_cast<int>(total),
+      StageScope sc(ctx, kStageBundleSort, 0, s);
+      CG_CUDA(cub::DeviceRadixSort::SortKeys(fb.cub_tmp.p, tmp_sort, dk, static_cast<int>(total),
                                              kl.rank_bits, bundle_end_bit, s));
     }
     {
-      StageScope sc(ctx, kStageBundleScan, 0);
-      CG_CUDA(cub::DeviceSelect::If(ctx->cub_tmp.p, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
+      StageScope sc(ctx, kStageBundleScan, 0, s);
+      CG_CUDA(cub::DeviceSelect::If(fb.cub_tmp.p, tmp_sel, iota, fb.scan.as<uint32_t>(), d_num,
                                     static_cast<int>(total), BundleHead{dk.Current(), kl.rank_bits}, s));
     }
     // upper bound on the number of bundles: one per point + the sentinel
     const unsigned bgrid = std::min<unsigned>(grid_for(upper, 256), ctx->num_sms * 8u);
     {
-      StageScope sc(ctx, kStageGather, 1);
+      StageScope sc(ctx, kStageGather, 1, s);
       k_gather_sorted<<<grid_for(total, 256), 256, 0, s>>>(
           kl, P.order_mode, dk.Current(), static_cast<uint32_t>(total), ft, pts, cols,
-          ctx->sorted_pts.as<float4>());
+          fb.sorted_pts.as<float4>());
     }
     {
-      StageScope sc(ctx, kStageBundleOrder, 3);
-      CG_CUDA(fill_bytes(ctx->d_class_count, 0, 2 * kSizeClasses * sizeof(uint32_t), s));
+      StageScope sc(ctx, kStageBundleOrder, 3, s);
+      CG_CUDA(fill_bytes(fb.d_class_count, 0, 2 * kSizeClasses * sizeof(uint32_t), s));
       k_bundle_histogram<<<bgrid, 256, 0, s>>>(kl, dk.Current(), static_cast<uint32_t>(total),
-                                               ctx->scan.as<uint32_t>(), d_num, ctx->d_class_count,
-                                               ctx->rays.as<Ray>());
+                                               fb.scan.as<uint32_t>(), d_num, fb.d_class_count,
+                                               fb.rays.as<Ray>());
       k_bundle_order<<<bgrid, 256, 0, s>>>(kl, dk.Current(), static_cast<uint32_t>(total),
-                                           ctx->scan.as<uint32_t>(), d_num, ctx->d_class_count,
-                                           ctx->ray_offset.as<uint32_t>());
+                                           fb.scan.as<uint32_t>(), d_num, fb.d_class_count,
+                                           fb.ray_offset.as<uint32_t>());
     }
     {
-      StageScope sc(ctx, kStageFoldWide, 1);
+      StageScope sc(ctx, kStageFoldWide, 1, s);
       k_fold_wide<<<ctx->num_sms * 12, kWideWarps * 32, 0, s>>>(
-          P, kl, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
-          ctx->sorted_pts.as<float4>(), ctx->d_class_count, ctx->ray_offset.as<uint32_t>(),
-          ctx->rays.as<Ray>());
+          P, kl, dk.Current(), static_cast<uint32_t>(total), fb.scan.as<uint32_t>(), d_num,
+          fb.sorted_pts.as<float4>(), fb.d_class_count, fb.ray_offset.as<uint32_t>(),
+          fb.rays.as<Ray>());
     }
     {
-      StageScope sc(ctx, kStageFold, 1);
+      StageScope sc(ctx, kStageFold, 1, s);
       k_fold_bundles<<<ctx->num_sms * 12, 128, 0, s>>>(
-          P, kl, dk.Current(), static_cast<uint32_t>(total), ctx->scan.as<uint32_t>(), d_num,
-          ctx->sorted_pts.as<float4>(), ctx->d_class_count, ctx->ray_offset.as<uint32_t>(),
-          ctx->rays.as<Ray>());
+          P, kl, dk.Current(), static_cast<uint32_t>(total), fb.scan.as<uint32_t>(), d_num,
+          fb.sorted_pts.as<float4>(), fb.d_class_count, fb.ray_offset.as<uint32_t>(),
+          fb.rays.as<Ray>());
     }
     {
-      StageScope sc(ctx, kStageBundleRays, 1);
-      k_bundle_rays<<<bgrid, 256, 0, s>>>(P, ctx->group_poses, d_num, ctx->rays.as<Ray>(),
-                                          ctx->ray_count.as<unsigned long long>());
+      StageScope sc(ctx, kStageBundleRays, 1, s);
+      k_bundle_rays<<<bgrid, 256, 0, s>>>(P, fb.group_poses, d_num, fb.rays.as<Ray>(),
+                                          fb.ray_count.as<unsigned long long>());
     }
     if (P.anti_grazing) {  // set of the scan's bundle voxels (at most one per point)
       size_t gcap = 1024;
       while (gcap < 2 * total) gcap <<= 1;
-      CG_CUDA(ctx->grazing_keys.reserve(gcap * sizeof(unsigned long long)));
-      CG_CUDA(ctx->grazing_ray_key.reserve(upper * sizeof(unsigned long long)));
-      ctx->grazing_mask = static_cast<uint32_t>(gcap - 1);
-      CG_CUDA(fill_bytes(ctx->grazing_keys.p, 0xFF, gcap * sizeof(unsigned long long), s));
+      CG_CUDA(fb.grazing_keys.reserve(gcap * sizeof(unsigned long long)));
+      CG_CUDA(fb.grazing_ray_key.reserve(upper * sizeof(unsigned long long)));
+      fb.grazing_mask = static_cast<uint32_t>(gcap - 1);
+      CG_CUDA(fill_bytes(fb.grazing_keys.p, 0xFF, gcap * sizeof(unsigned long long), s));
       k_grazing_build<<<bgrid, 256, 0, s>>>(kl, dk.Current(), static_cast<uint32_t>(total),
-                                            ctx->scan.as<uint32_t>(), d_num,
-                                            ctx->grazing_keys.as<unsigned long long>(),
-                                            ctx->grazing_mask,
-                                            ctx->grazing_ray_key.as<unsigned long long>());
+                                            fb.scan.as<uint32_t>(), d_num,
+                                            fb.grazing_keys.as<unsigned long long>(),
+                                            fb.grazing_mask,
+                                            fb.grazing_ray_key.as<unsigned long long>());
     }
   } else {
     {
-      StageScope sc(ctx, kStageBundleScan, 0);
-      CG_CUDA(cub::DeviceSelect::If(ctx->cub_tmp.p, tmp_sel, iota, ctx->scan.as<uint32_t>(), d_num,
+      StageScope sc(ctx, kStageBundleScan, 0, s);
+      CG_CUDA(cub::DeviceSelect::If(fb.cub_tmp.p, tmp_sel, iota, fb.scan.as<uint32_t>(), d_num,
                                     static_cast<int>(total), valid, s));
     }
-    StageScope sc(ctx, kStageBundleRays, 1);
+    StageScope sc(ctx, kStageBundleRays, 1, s);
     k_simple_rays<<<grid_for(total, 256), 256, 0, s>>>(
-        P, ctx->group_poses, ft, ctx->scan.as<uint32_t>(), d_num, pts,
-        cols, ctx->rays.as<Ray>(), ctx->ray_count.as<unsigned long long>());
+        P, fb.group_poses, ft, fb.scan.as<uint32_t>(), d_num, pts,
+        cols, fb.rays.as<Ray>(), fb.ray_count.as<unsigned long long>());
   }
   {
-    StageScope sc(ctx, kStageRayScan, 3);
+    StageScope sc(ctx, kStageRayScan, 3, s);
     const int sgrid = std::min(1024, ctx->num_sms * 4);
-    CG_CUDA(ctx->scan_partials.reserve(1024 * sizeof(unsigned long long)));
-    k_scan_partials<<<sgrid, kScanThreads, 0, s>>>(d_num, ctx->ray_count.as<unsigned long long>(),
-                                                   ctx->scan_partials.as<unsigned long long>());
-    k_scan_totals<<<1, 1024, 0, s>>>(d_num, ctx->scan_partials.as<unsigned long long>(), sgrid,
-                                     ctx->d_counters, L->v.err, ctx->d_key_bounds);
-    k_scan_apply<<<sgrid, kScanThreads, 0, s>>>(d_num, ctx->ray_count.as<unsigned long long>(),
-                                                ctx->scan_partials.as<unsigned long long>(),
-                                                ctx->ray_offset.as<unsigned long long>());
+    CG_CUDA(fb.scan_partials.reserve(1024 * sizeof(unsigned long long)));
+    k_scan_partials<<<sgrid, kScanThreads, 0, s>>>(d_num, fb.ray_count.as<unsigned long long>(),
+                                                   fb.scan_partials.as<unsigned long long>());
+    k_scan_totals<<<1, 1024, 0, s>>>(d_num, fb.scan_partials.as<unsigned long long>(), sgrid,
+                                     fb.d_counters, d_err, fb.d_key_bounds);
+    k_scan_apply<<<sgrid, kScanThreads, 0, s>>>(d_num, fb.ray_count.as<unsigned long long>(),
+                                                fb.scan_partials.as<unsigned long long>(),
+                                                fb.ray_offset.as<unsigned long long>());
   }
-  CG_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(CallCounters),
+  CG_CUDA(cudaMemcpyAsync(fb.h_counters, fb.d_counters, sizeof(CallCounters),
                           cudaMemcpyDeviceToHost, s));
-  CG_CUDA(cudaStreamSynchronize(s));
   CG_CUDA(cudaGetLastError());
-  const uint32_t num_rays = static_cast<uint32_t>(ctx->h_counters->rays);
-  const size_t num_pairs = ctx->h_counters->pairs;
+  return CG_OK;
+}
+
+enum FrontVerdict { kFrontOk, kFrontRetry, kFrontSplit, kFrontFail };
+
+// After the host has synchronised on a front half: book-keeping of the bundle-key box from the
+// extent the job measured, and what has to happen next.
+static FrontVerdict front_digest(cg_context* ctx, const FrontBufs& fb, bool merged, size_t F,
+                                 int attempt, int32_t* rc) {
+  const size_t num_pairs = fb.h_counters->pairs;
   const size_t max_pairs = env_size("CG_MAX_PAIRS", size_t(768) << 20);
-  const bool key_range = (ctx->h_counters->err & kErrKeyRange) != 0;
+  const bool key_range = (fb.h_counters->err & kErrKeyRange) != 0;
   // The box = union of the extents measured by the jobs of this context (relative voxel indices
   // of every valid point).  A second union over a window of 8 jobs replaces it when it needs
   // fewer bits, so that one outlier (a stray far return) does not widen the keys for good.
-  if (merged && ctx->h_counters->key_lo[0] <= ctx->h_counters->key_hi[0]) {
+  if (merged && fb.h_counters->key_lo[0] <= fb.h_counters->key_hi[0]) {
     int lo[3], hi[3];
     for (int a = 0; a < 3; ++a) {
-      lo[a] = std::max(-kKeyLimit, ctx->h_counters->key_lo[a]);
-      hi[a] = std::min(kKeyLimit, ctx->h_counters->key_hi[a]);
+      lo[a] = std::max(-kKeyLimit, fb.h_counters->key_lo[a]);
+      hi[a] = std::min(kKeyLimit, fb.h_counters->key_hi[a]);
       ctx->key_lo[a] = ctx->key_box_valid ? std::min(ctx->key_lo[a], lo[a]) : lo[a];
       ctx->key_hi[a] = ctx->key_box_valid ? std::max(ctx->key_hi[a], hi[a]) : hi[a];
       ctx->key_win_lo[a] = ctx->key_win_jobs ? std::min(ctx->key_win_lo[a], lo[a]) : lo[a];
@@ -2163,11 +2167,11 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
     }
   }
   if (key_range) {
-    const bool measured = ctx->h_counters->key_lo[0] <= ctx->h_counters->key_hi[0];
+    const bool measured = fb.h_counters->key_lo[0] <= fb.h_counters->key_hi[0];
     bool reachable = attempt < 3;
     for (int a = 0; a < 3 && measured; ++a)
-      reachable = reachable && ctx->h_counters->key_lo[a] >= -kKeyLimit &&
-                  ctx->h_counters->key_hi[a] <= kKeyLimit;
+      reachable = reachable && fb.h_counters->key_lo[a] >= -kKeyLimit &&
+                  fb.h_counters->key_hi[a] <= kKeyLimit;
     // redo the group: with the extent just measured the box covers its points; if this pass did
     // not measure, the next one does (and may have to be redone once more)
     if (reachable) {
@@ -2176,60 +2180,100 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
                 attempt, int(measured), ctx->key_lo[0], ctx->key_hi[0], ctx->key_lo[1], ctx->key_hi[1],
                 ctx->key_lo[2], ctx->key_hi[2]);
       ctx->key_retry_measured = measured;
-      return integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, f1, stats, attempt + 1);
+      return kFrontRetry;
     }
     if (F == 1) {
       set_error("a point lies more than %d voxels from the sensor", kKeyLimit);
-      return CG_ERR_OUT_OF_RANGE;
+      *rc = CG_ERR_OUT_OF_RANGE;
+      return kFrontFail;
     }
   }
   if (key_range || num_pairs > max_pairs || num_pairs >= 0x7FFFFFF0ull) {
-    if (F > 1) {  // the front half never touches the layer: safe to redo in two halves
-      const size_t mid = f0 + F / 2;
-      int32_t rc = integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, mid, stats);
-      if (rc) return rc;
-      return integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, mid, f1, stats);
-    }
+    if (F > 1) return kFrontSplit;  // the front half never touches the layer: safe to redo in two halves
     if (num_pairs >= 0x7FFFFFF0ull) {
       set_error("a single frame produces %zu voxel updates; split the point cloud", num_pairs);
-      return CG_ERR_INVALID_ARG;
+      *rc = CG_ERR_INVALID_ARG;
+      return kFrontFail;
     }
   }
+  return kFrontOk;
+}
+
+// frames [f0, f1) of the job as one group; splits itself when the pair list would not fit
+static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
+                               const IntegratorParams& P, const float* h_poses,
+                               const float* d_points, const uint8_t* d_colors,
+                               const uint64_t* offs, size_t f0, size_t f1,
+                               cg_integrate_stats* stats, int attempt = 0) {
+  cg_context* ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  const size_t F = f1 - f0;
+  const size_t total = offs[f1] - offs[f0];  // points of the group = upper bound on rays
+  if (total == 0) return CG_OK;
+  if (total > 0x7FFFFFF0ull || F > (1u << 20)) {
+    set_error("too many points / frames in one group");
+    return CG_ERR_INVALID_ARG;
+  }
+  auto halves = [&]() -> int32_t {
+    const size_t mid = f0 + F / 2;
+    int32_t rc = integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, mid, stats);
+    if (rc) return rc;
+    return integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, mid, f1, stats);
+  };
+  bool need_split = false;
+  int32_t rc = front_enqueue(ctx, *ctx, s, L->v.err, L, cfg, P, d_points, d_colors, offs, f0, f1,
+                             attempt, &need_split);
+  if (rc) return rc;
+  if (need_split) return halves();
+  CG_CUDA(cudaStreamSynchronize(s));
+  CG_CUDA(cudaGetLastError());
+  switch (front_digest(ctx, *ctx, cfg->method == CG_METHOD_MERGED, F, attempt, &rc)) {
+    case kFrontRetry:
+      return integrate_group(L, cfg, P, h_poses, d_points, d_colors, offs, f0, f1, stats, attempt + 1);
+    case kFrontSplit:
+      return halves();
+    case kFrontFail:
+      return rc;
+    case kFrontOk:
+      break;
+  }
+  const uint32_t num_rays = static_cast<uint32_t>(ctx->h_counters->rays);
+  const size_t num_pairs = ctx->h_counters->pairs;
   if (num_rays == 0 || num_pairs == 0) return CG_OK;
   if (stats) {
     stats->rays += num_rays;
     stats->voxel_updates += num_pairs;
   }
-  return run_back_half(ctx, L, P, num_rays, num_pairs, ctx->h_counters->segments, stats);
+  return run_back_half(ctx, *ctx, L, P, num_rays, num_pairs, ctx->h_counters->segments, stats);
 }
 
 // The job's poses and frame offsets (relative to its first point) go up once per job, through a
 // pinned, device-mapped host buffer and a copy KERNEL: an H2D memcpy would be queued on the copy
 // engine behind the point data that the staging / pipelined paths have in flight.
-static int32_t upload_frame_tables(cg_context* ctx, size_t F, const float* h_poses,
+static int32_t upload_frame_tables(FrontBufs& fb, size_t F, const float* h_poses,
                                    const uint64_t* offs, cudaStream_t stream) {
   const size_t pose_words = F * 7, off_words = (F + 1) * 2;
   const size_t bytes = (pose_words + off_words) * sizeof(uint32_t);
-  if (bytes > ctx->h_tables_cap) {
-    if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
-    ctx->h_tables = nullptr;
-    ctx->h_tables_cap = 0;
-    CG_CUDA(cudaHostAlloc(&ctx->h_tables, bytes * 2, cudaHostAllocMapped));
-    ctx->h_tables_cap = bytes * 2;
+  if (bytes > fb.h_tables_cap) {
+    if (fb.h_tables) cudaFreeHost(fb.h_tables);
+    fb.h_tables = nullptr;
+    fb.h_tables_cap = 0;
+    CG_CUDA(cudaHostAlloc(&fb.h_tables, bytes * 2, cudaHostAllocMapped));
+    fb.h_tables_cap = bytes * 2;
   }
-  CG_CUDA(ctx->poses.reserve(pose_words * sizeof(float)));
-  CG_CUDA(ctx->frame_base.reserve((F + 1) * sizeof(uint64_t)));
-  uint32_t* h = static_cast<uint32_t*>(ctx->h_tables);
+  CG_CUDA(fb.poses.reserve(pose_words * sizeof(float)));
+  CG_CUDA(fb.frame_base.reserve((F + 1) * sizeof(uint64_t)));
+  uint32_t* h = static_cast<uint32_t*>(fb.h_tables);
   memcpy(h, h_poses, pose_words * sizeof(float));
   uint64_t* ho = reinterpret_cast<uint64_t*>(h + pose_words + (pose_words & 1));
   for (size_t f = 0; f <= F; ++f) ho[f] = offs[f] - offs[0];
   void* d_alias = nullptr;
-  CG_CUDA(cudaHostGetDevicePointer(&d_alias, ctx->h_tables, 0));
+  CG_CUDA(cudaHostGetDevicePointer(&d_alias, fb.h_tables, 0));
   const uint32_t* src = static_cast<const uint32_t*>(d_alias);
-  k_copy_words<<<grid_for(pose_words, 256), 256, 0, stream>>>(ctx->poses.as<uint32_t>(), src,
+  k_copy_words<<<grid_for(pose_words, 256), 256, 0, stream>>>(fb.poses.as<uint32_t>(), src,
                                                               pose_words);
   k_copy_words<<<grid_for(off_words, 256), 256, 0, stream>>>(
-      ctx->frame_base.as<uint32_t>(), src + pose_words + (pose_words & 1), off_words);
+      fb.frame_base.as<uint32_t>(), src + pose_words + (pose_words & 1), off_words);
   CG_CUDA(cudaGetLastError());
   return CG_OK;
 }
@@ -2266,7 +2310,7 @@ static int32_t integrate_job(cg_layer* L, const cg_integrator_config* cfg, size_
   // poses and frame offsets (relative to the job's first point) go up once per job; with a
   // transfer plan the caller already queued them on the copy stream ahead of the point data
   if (!plan) {
-    int32_t urc = upload_frame_tables(L->ctx, F, h_poses, offs, L->ctx->stream);
+    int32_t urc = upload_frame_tables(*L->ctx, F, h_poses, offs, L->ctx->stream);
     if (urc) return urc;
   }
   int32_t rc = CG_OK;
@@ -2302,11 +2346,142 @@ static int32_t stage_inputs(cg_context* ctx, const float* pts, const uint8_t* co
   return CG_OK;
 }
 
+
+// ---- pipelined jobs: the front half of a later job beside the back half of the current one
+static int32_t prepare_job(cg_layer* L, const cg_integrator_config* cfg, size_t F,
+                           const float* poses, const float* d_pts, const uint8_t* d_cols,
+                           const uint64_t* offs, int32_t freespace, int32_t slot,
+                           cudaEvent_t inputs_ready) {
+  if (!L || !cfg || !poses || !offs || slot < 0 || slot > 1) {
+    set_error("cg_prepare_batch: invalid argument");
+    return CG_ERR_INVALID_ARG;
+  }
+  for (size_t f = 0; f < F; ++f)
+    if (offs[f + 1] < offs[f]) {
+      set_error("frame_offsets must be non-decreasing");
+      return CG_ERR_INVALID_ARG;
+    }
+  cg_context* ctx = L->ctx;
+  CG_CUDA(cudaSetDevice(ctx->device));
+  FrontBufs& fb = ctx->prep[slot];
+  if (!ctx->prep_stream) CG_CUDA(cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking));
+  if (!ctx->prep_done[slot]) {
+    CG_CUDA(cudaEventCreateWithFlags(&ctx->prep_done[slot], cudaEventDisableTiming));
+    CG_CUDA(init_front_words(fb));
+  }
+  cg_context::PreparedJob& pj = ctx->prepared[slot];
+  pj.valid = true;
+  pj.front_queued = false;
+  pj.cfg = *cfg;
+  pj.poses.assign(poses, poses + 7 * F);
+  pj.offs.resize(F + 1);
+  for (size_t f = 0; f <= F; ++f) pj.offs[f] = offs[f] - offs[0];
+  pj.d_points = d_pts ? d_pts + 3 * offs[0] : nullptr;
+  pj.d_colors = d_cols ? d_cols + 4 * offs[0] : nullptr;
+  pj.freespace = freespace;
+  pj.voxel_size = L->v.voxel_size;
+  const size_t total = pj.offs[F];
+  const size_t max_group_points = env_size("CG_MAX_GROUP_POINTS", size_t(48) << 20);
+  // the fast path: a valid merged / simple job that is one group; everything else is left to the
+  // plain path inside cg_integrate_prepared (which also reports the errors)
+  if ((cfg->method != CG_METHOD_MERGED && cfg->method != CG_METHOD_SIMPLE) ||
+      !(cfg->default_truncation_distance > 0.0f) || !(cfg->max_ray_length_m > 0.0f) || total == 0 ||
+      total > max_group_points || total > 0x7FFFFFF0ull || F > (1u << 20) || !d_pts || !d_cols)
+    return CG_OK;
+  const IntegratorParams P = make_params(L, cfg, freespace);
+  cudaStream_t ps = ctx->prep_stream;
+  // the inputs were produced on the context's stream (or by the staged copy): order behind them
+  if (!ctx->wait_event) CG_CUDA(cudaEventCreateWithFlags(&ctx->wait_event, cudaEventDisableTiming));
+  CG_CUDA(cudaEventRecord(ctx->wait_event, ctx->stream));
+  CG_CUDA(cudaStreamWaitEvent(ps, ctx->wait_event, 0));
+  if (inputs_ready) CG_CUDA(cudaStreamWaitEvent(ps, inputs_ready, 0));
+  CG_CUDA(fill_bytes(fb.d_front_err, 0, sizeof(int32_t), ps));
+  int32_t rc = upload_frame_tables(fb, F, pj.poses.data(), pj.offs.data(), ps);
+  if (rc) return rc;
+  bool need_split = false;
+  rc = front_enqueue(ctx, fb, ps, fb.d_front_err, L, cfg, P, pj.d_points, pj.d_colors,
+                     pj.offs.data(), 0, F, 0, &need_split);
+  if (rc) return rc;
+  if (need_split) {  // does not fit one group: drain and leave the job to the plain path
+    CG_CUDA(cudaStreamSynchronize(ps));
+    return CG_OK;
+  }
+  CG_CUDA(cudaEventRecord(ctx->prep_done[slot], ps));
+  pj.front_queued = true;
+  return CG_OK;
+}
+
 }  // namespace cg
 
 using namespace cg;
 
 extern "C" {
+
+int32_t cg_prepare_batch_device(cg_layer* L, const cg_integrator_config* cfg, size_t F,
+                                const float* poses, const float* d_pts, const uint8_t* d_cols,
+                                const uint64_t* offs, int32_t freespace, int32_t slot) {
+  return prepare_job(L, cfg, F, poses, d_pts, d_cols, offs, freespace, slot, nullptr);
+}
+
+int32_t cg_prepare_batch_staged(cg_layer* L, const cg_integrator_config* cfg, size_t F,
+                                const float* poses, int32_t stage_slot, const uint64_t* offs,
+                                int32_t freespace, int32_t slot) {
+  if (!L || stage_slot < 0 || stage_slot > 1 || !offs || !L->ctx->stage_ready[stage_slot]) {
+    set_error("cg_prepare_batch_staged: invalid argument (nothing staged in this slot?)");
+    return CG_ERR_INVALID_ARG;
+  }
+  cg_context* ctx = L->ctx;
+  if (offs[0] != 0 || offs[F] != ctx->stage_points[stage_slot]) {
+    set_error("cg_prepare_batch_staged: frame_offsets must cover exactly the %zu staged points",
+              ctx->stage_points[stage_slot]);
+    return CG_ERR_INVALID_ARG;
+  }
+  return prepare_job(L, cfg, F, poses, ctx->stage_pts[stage_slot].as<float>(),
+                     ctx->stage_cols[stage_slot].as<uint8_t>(), offs, freespace, slot,
+                     ctx->stage_ready[stage_slot]);
+}
+
+int32_t cg_integrate_prepared(cg_layer* L, int32_t slot, cg_integrate_stats* stats) {
+  if (!L || slot < 0 || slot > 1 || !L->ctx->prepared[slot].valid) {
+    set_error("cg_integrate_prepared: nothing prepared in this slot");
+    return CG_ERR_INVALID_ARG;
+  }
+  cg_context* ctx = L->ctx;
+  CG_CUDA(cudaSetDevice(ctx->device));
+  cg_context::PreparedJob& pj = ctx->prepared[slot];
+  pj.valid = false;
+  const size_t F = pj.offs.size() - 1;
+  if (pj.front_queued && pj.voxel_size == L->v.voxel_size) {
+    FrontBufs& fb = ctx->prep[slot];
+    CG_CUDA(cudaEventSynchronize(ctx->prep_done[slot]));
+    int32_t rc = CG_OK;
+    const FrontVerdict v = front_digest(ctx, fb, pj.cfg.method == CG_METHOD_MERGED, F, 3, &rc);
+    if (v == kFrontOk && !(fb.h_counters->err & kErrOutOfRange)) {
+      const IntegratorParams P = make_params(L, &pj.cfg, pj.freespace);
+      const int64_t blocks_before = L->num_blocks;
+      if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->points_in = pj.offs[F];
+      }
+      const uint32_t num_rays = static_cast<uint32_t>(fb.h_counters->rays);
+      const size_t num_pairs = fb.h_counters->pairs;
+      if (num_rays > 0 && num_pairs > 0) {
+        if (stats) {
+          stats->rays = num_rays;
+          stats->voxel_updates = num_pairs;
+        }
+        rc = run_back_half(ctx, fb, L, P, num_rays, num_pairs, fb.h_counters->segments, stats);
+      }
+      const int32_t rc2 = finish_call(L, nullptr);
+      if (stats) stats->blocks_allocated = L->num_blocks - blocks_before;
+      return rc ? rc : rc2;
+    }
+    // a point outside the key box, too many voxel visits for one group, ...: the plain path
+    // handles it (regrouping, retries, the error report); the prepared front half is dropped
+  }
+  return cg_integrate_batch_device(L, &pj.cfg, F, pj.poses.data(), pj.d_points, pj.d_colors,
+                                   pj.offs.data(), pj.freespace, stats);
+}
 
 void cg_integrator_config_default(cg_integrator_config* c) {
   if (!c) return;
@@ -2379,7 +2554,7 @@ int32_t cg_integrate_batch(cg_layer* L, const cg_integrator_config* cfg, size_t 
     for (size_t f = 1; f <= F; ++f)
       if (f == F || rel[f] - rel[plan.bounds.back()] >= chunk_points) plan.bounds.push_back(f);
     const size_t G = plan.bounds.size() - 1;
-    int32_t urc = upload_frame_tables(ctx, F, poses, rel.data(), ctx->stream);
+    int32_t urc = upload_frame_tables(*ctx, F, poses, rel.data(), ctx->stream);
     if (urc) return urc;
     while (ctx->copy_events.size() < G) {
       cudaEvent_t e;

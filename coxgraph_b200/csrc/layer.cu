@@ -387,6 +387,35 @@ __global__ void k_flag_listed(LayerView L, const int32_t* __restrict__ idx, int 
   if (slot >= 0) remove[slot] = 1;
 }
 
+cudaError_t init_front_words(FrontBufs& fb) {
+  cudaError_t e;
+  if ((e = cudaMallocHost(&fb.h_counters, sizeof(CallCounters))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&fb.d_counters, sizeof(CallCounters))) != cudaSuccess) return e;
+  if ((e = cudaMemset(fb.d_counters, 0, sizeof(CallCounters))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&fb.d_select_count, sizeof(uint32_t))) != cudaSuccess) return e;
+  if ((e = cudaMemset(fb.d_select_count, 0, sizeof(uint32_t))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&fb.d_key_bounds, 6 * sizeof(int))) != cudaSuccess) return e;
+  const int init[6] = {0x3FFFFFFF, 0x3FFFFFFF, 0x3FFFFFFF, -0x3FFFFFFF, -0x3FFFFFFF, -0x3FFFFFFF};
+  if ((e = cudaMemcpy(fb.d_key_bounds, init, sizeof(init), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&fb.d_class_count, 128 * sizeof(uint32_t))) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&fb.d_front_err, sizeof(int32_t))) != cudaSuccess) return e;
+  return cudaMemset(fb.d_front_err, 0, sizeof(int32_t));
+}
+void release_front(FrontBufs& fb) {
+  DevBuf* bufs[] = {&fb.poses, &fb.frame_base, &fb.key_a, &fb.key_b, &fb.scan, &fb.cub_tmp, &fb.rays,
+                    &fb.ray_count, &fb.ray_offset, &fb.sorted_pts, &fb.scan_partials,
+                    &fb.grazing_keys, &fb.grazing_ray_key};
+  for (DevBuf* b : bufs) b->release();
+  if (fb.h_counters) cudaFreeHost(fb.h_counters);
+  if (fb.d_counters) cudaFree(fb.d_counters);
+  if (fb.d_select_count) cudaFree(fb.d_select_count);
+  if (fb.d_key_bounds) cudaFree(fb.d_key_bounds);
+  if (fb.d_class_count) cudaFree(fb.d_class_count);
+  if (fb.d_front_err) cudaFree(fb.d_front_err);
+  if (fb.h_tables) cudaFreeHost(fb.h_tables);
+  fb = FrontBufs();
+}
+
 int32_t finish_call(cg_layer* layer, CallCounters* out) {
   cg_context* ctx = layer->ctx;
   k_read_counters<<<1, 1, 0, ctx->stream>>>(layer->v, ctx->d_counters);
@@ -470,22 +499,12 @@ int32_t cg_context_create(int32_t device, void* stream, cg_context** out) {
     ctx->own_stream = true;
   }
   cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
-  CG_CUDA(cudaMallocHost(&ctx->h_counters, sizeof(CallCounters)));
-  CG_CUDA(cudaMalloc(&ctx->d_counters, sizeof(CallCounters)));
-  CG_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(CallCounters), ctx->stream));
+  CG_CUDA(init_front_words(*ctx));
   CG_CUDA(cudaMalloc(&ctx->d_work_counter, sizeof(uint32_t)));
   CG_CUDA(cudaMalloc(&ctx->d_long_counter, sizeof(unsigned long long)));
-  CG_CUDA(cudaMalloc(&ctx->d_select_count, sizeof(uint32_t)));
   CG_CUDA(cudaMalloc(&ctx->d_touch_count, 2 * sizeof(uint32_t)));
-  CG_CUDA(cudaMalloc(&ctx->d_key_bounds, 6 * sizeof(int)));
-  {
-    const int init[6] = {0x3FFFFFFF, 0x3FFFFFFF, 0x3FFFFFFF, -0x3FFFFFFF, -0x3FFFFFFF, -0x3FFFFFFF};
-    CG_CUDA(cudaMemcpy(ctx->d_key_bounds, init, sizeof(init), cudaMemcpyHostToDevice));
-  }
   CG_CUDA(cudaMalloc(&ctx->d_walk_counters, 4 * sizeof(uint32_t)));
   CG_CUDA(cudaMemsetAsync(ctx->d_walk_counters, 0, 4 * sizeof(uint32_t), ctx->stream));
-  CG_CUDA(cudaMalloc(&ctx->d_class_count, 128 * sizeof(uint32_t)));
-  CG_CUDA(cudaMemsetAsync(ctx->d_select_count, 0, sizeof(uint32_t), ctx->stream));
   *out = ctx;
   return CG_OK;
 }
@@ -495,23 +514,27 @@ int32_t cg_context_destroy(cg_context* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cg_comm_destroy(ctx);
-  DevBuf* bufs[] = {&ctx->points, &ctx->colors, &ctx->poses, &ctx->frame_base, &ctx->key_a,
-                    &ctx->key_b, &ctx->val_a, &ctx->val_b, &ctx->flags, &ctx->scan,
-                    &ctx->cub_tmp, &ctx->rays, &ctx->ray_count, &ctx->ray_offset, &ctx->sorted_pts, &ctx->pkey_a,
-                    &ctx->pkey_b, &ctx->seg_keys_a, &ctx->seg_keys_b, &ctx->seg_idx_a, &ctx->seg_idx_b, &ctx->seg_recs, &ctx->seg_order, &ctx->scan_partials, &ctx->seg_bins, &ctx->grazing_keys, &ctx->grazing_ray_key, &ctx->touch_ord, &ctx->touch_entry, &ctx->touch_acc, &ctx->touch_bits, &ctx->seg_start, &ctx->long_list, &ctx->long_partials, &ctx->cand_keys, &ctx->cand_list,
-                    &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->batch_desc, &ctx->merge_cands, &ctx->mc_counts, &ctx->mc_index, &ctx->mc_vertices, &ctx->mc_normals, &ctx->mc_colors, &ctx->mesh_in, &ctx->mesh_tri,
+  DevBuf* bufs[] = {&ctx->points, &ctx->colors, &ctx->val_a, &ctx->val_b, &ctx->flags,
+                    &ctx->pkey_a, &ctx->pkey_b, &ctx->seg_keys_a, &ctx->seg_keys_b, &ctx->seg_idx_a,
+                    &ctx->seg_idx_b, &ctx->seg_recs, &ctx->seg_order, &ctx->seg_bins,
+                    &ctx->touch_ord, &ctx->touch_entry, &ctx->touch_acc, &ctx->touch_bits,
+                    &ctx->seg_start, &ctx->long_list, &ctx->long_partials, &ctx->cand_keys,
+                    &ctx->cand_list, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->batch_desc,
+                    &ctx->merge_cands, &ctx->mc_counts, &ctx->mc_index, &ctx->mc_vertices,
+                    &ctx->mc_normals, &ctx->mc_colors, &ctx->mesh_in, &ctx->mesh_tri,
                     &ctx->mesh_pairs, &ctx->mesh_pts_g, &ctx->mesh_cols_g, &ctx->mesh_pts_c,
                     &ctx->mesh_cols_c, &ctx->mesh_frames};
   for (DevBuf* b : bufs) b->release();
   drain_events(ctx);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
-  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
-  if (ctx->d_counters) cudaFree(ctx->d_counters);
-  if (ctx->d_select_count) cudaFree(ctx->d_select_count);
+  release_front(*ctx);
+  for (int i = 0; i < 2; ++i) {
+    release_front(ctx->prep[i]);
+    if (ctx->prep_done[i]) cudaEventDestroy(ctx->prep_done[i]);
+  }
+  if (ctx->prep_stream) cudaStreamDestroy(ctx->prep_stream);
   if (ctx->d_touch_count) cudaFree(ctx->d_touch_count);
   if (ctx->d_walk_counters) cudaFree(ctx->d_walk_counters);
-  if (ctx->d_key_bounds) cudaFree(ctx->d_key_bounds);
-  if (ctx->d_class_count) cudaFree(ctx->d_class_count);
   if (ctx->d_work_counter) cudaFree(ctx->d_work_counter);
   if (ctx->d_long_counter) cudaFree(ctx->d_long_counter);
   for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
@@ -520,7 +543,6 @@ int32_t cg_context_destroy(cg_context* ctx) {
     ctx->stage_cols[i].release();
     if (ctx->stage_ready[i]) cudaEventDestroy(ctx->stage_ready[i]);
   }
-  if (ctx->h_tables) cudaFreeHost(ctx->h_tables);
   if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -231,6 +231,27 @@ int32_t cg_integrate_batch_staged(cg_layer* layer, const cg_integrator_config* c
                                   const uint64_t* frame_offsets, int32_t freespace_points,
                                   cg_integrate_stats* stats);
 
+/* Pipelined jobs.  The first half of a job — validity, T_G_C * p, bundling, one ray per bundle —
+ * never touches the layer, so it can run while the previous job is still being fused:
+ * cg_prepare_batch_device / _staged queue that half of a LATER job on the context's second stream
+ * (own scratch set per slot, 0 or 1) and return at once; cg_integrate_prepared(layer, slot) then
+ * runs the rest on the context's stream and returns when the job is complete, with the same
+ * result as cg_integrate_batch_device.  The counterpart, one level up, of the ROS subscriber queue
+ * that already holds the next clouds (tsdf_recover.h:71-86 knows every frame of the mesh in
+ * advance).  The input buffers (device memory, or the staged slot) must stay valid and unchanged
+ * until cg_integrate_prepared has returned; a job the fast path cannot take (several groups, a
+ * point outside the bundle-key box, an invalid config) is simply run the plain way there. */
+int32_t cg_prepare_batch_device(cg_layer* layer, const cg_integrator_config* cfg,
+                                size_t num_frames, const float* T_G_C_poses,
+                                const float* d_points_xyz, const uint8_t* d_colors_rgba,
+                                const uint64_t* frame_offsets, int32_t freespace_points,
+                                int32_t slot);
+int32_t cg_prepare_batch_staged(cg_layer* layer, const cg_integrator_config* cfg,
+                                size_t num_frames, const float* T_G_C_poses, int32_t stage_slot,
+                                const uint64_t* frame_offsets, int32_t freespace_points,
+                                int32_t slot);
+int32_t cg_integrate_prepared(cg_layer* layer, int32_t slot, cg_integrate_stats* stats);
+
 /* --- mesh recovery: the recover node's front end ----------------------
  * voxblox_msgs/Mesh (the fork's "mesh with observation history") flattened into plain arrays:
  * block b owns vertices [vertex_begin[b], vertex_begin[b+1]) (triangles: multiples of 3), x/y/z

@@ -258,3 +258,42 @@ def test_upload_download_roundtrip(gpu_ctx):
     util.compare_layers(gl.download(), (idx, vox, fl), "roundtrip", exact=True, check_flags=True)
     assert np.array_equal(gl.block_indices(), idx)
     gl.close()
+
+
+def test_prepared_jobs_equal_plain_calls(gpu_ctx):
+    """cg_prepare_batch_device / cg_integrate_prepared: the first half of job k+1 is queued (second
+    stream, own scratch set) before job k is completed.  Same layer, bit for bit, as the plain
+    cg_integrate_batch_device calls; a job the fast path cannot take (a point outside the
+    bundle-key box) silently goes the plain way."""
+    import torch
+    from coxgraph_b200 import Layer, TsdfIntegrator
+    _, gcfg = util.make_cfgs()
+    dev = torch.device("cuda", 0)
+    jobs = []
+    for k in range(4):
+        frames = util.small_frames(3, stride=4, robot=k % 2, submap=k)
+        if k == 2:   # a stray far return: outside the key box measured so far
+            T, p, c = frames[1]
+            p = p.copy()
+            p[5] = (0.4, 0.2, 90.0)
+            frames[1] = (T, p, c)
+        poses = np.stack([T for (T, _, _) in frames]).astype(np.float32)
+        pts = torch.from_numpy(np.concatenate([p for (_, p, _) in frames])).to(dev)
+        cols = torch.from_numpy(np.concatenate([c for (_, _, c) in frames])).to(dev)
+        offs = np.cumsum([0] + [len(p) for (_, p, _) in frames]).astype(np.uint64)
+        jobs.append((poses, pts, cols, offs))
+    a, b = Layer(gpu_ctx, 0.05, max_blocks=4096), Layer(gpu_ctx, 0.05, max_blocks=4096)
+    ia, ib = TsdfIntegrator(gcfg, a), TsdfIntegrator(gcfg, b)
+    for (poses, pts, cols, offs) in jobs:
+        ia.integrateBatch(poses, pts, cols, offs)
+    ib.prepareBatch(0, *jobs[0])
+    for k, job in enumerate(jobs):
+        if k + 1 < len(jobs):
+            ib.prepareBatch((k + 1) % 2, *jobs[k + 1])
+        st = ib.integratePrepared(k % 2)
+        assert st.points_in == int(job[3][-1]) and st.rays > 0
+    util.compare_layers(a.download(), b.download(), "prepared vs plain jobs", exact=True)
+    with pytest.raises(Exception):
+        ib.integratePrepared(0)   # nothing prepared any more
+    a.close()
+    b.close()
