@@ -702,6 +702,38 @@ def run_ours(args, rank, world, local_rank):
         except Exception as exc:  # noqa: BLE001 - an extra figure must not take the bench line down
             two_jobs = dict(two_jobs or {}, error=repr(exc))
 
+    # ---- the live path as a C++ host drives it: one integratePointCloud call per frame through
+    # the C++ mirror (coxgraph_b200/host/coxgraph_b200.hpp) with pageable std::vector inputs —
+    # what voxblox_ros TsdfServer / INTEGRATION.md's adapter pass (N = 1, rank 0 only)
+    per_frame_host = None
+    if rank == 0 and world == 1 and not args.profile_mode:
+        try:
+            import struct
+            import tempfile
+            binary = os.path.join(ROOT, "build", "host_api_check")
+            if not os.path.exists(binary):
+                subprocess.check_call(["make", "-C", ROOT, "-s", "build/host_api_check"])
+            e = pool[0]
+            with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+                f.write(struct.pack("<Iff", FRAMES_PER_SUBMAP, VOXEL_SIZE,
+                                    CFG["default_truncation_distance"]))
+                f.write(np.asarray(e["T_M_S"], np.float32).tobytes())
+                for k in range(FRAMES_PER_SUBMAP):
+                    a, b = int(e["offs"][k]), int(e["offs"][k + 1])
+                    f.write(np.asarray(e["poses"][k], np.float32).tobytes())
+                    f.write(struct.pack("<I", b - a))
+                    f.write(np.ascontiguousarray(e["h_pts"][a:b]).tobytes())
+                    f.write(np.ascontiguousarray(e["h_cols"][a:b]).tobytes())
+                path = f.name
+            r = subprocess.run([binary, "time", path, "3"], capture_output=True, text=True,
+                               timeout=120)
+            os.unlink(path)
+            per_frame_host = json.loads(r.stdout.strip().splitlines()[-1])
+            per_frame_host["what"] = ("cg_integrate_pointcloud through the C++ mirror, pageable "
+                                      "std::vector inputs (H2D inside the call)")
+        except Exception as exc:  # noqa: BLE001 - an extra figure must not take the bench line down
+            per_frame_host = {"error": repr(exc)}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle, all host threads, bounded
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile_mode:
@@ -785,7 +817,9 @@ def run_ours(args, rank, world, local_rank):
             # scratch buffers, and a cudaMalloc / cudaFree is a stall of milliseconds)
             "per_frame_call": {"ms": float(np.median([e["per_frame_ms"] for e in pool])),
                                "points_per_s": 307200.0 /
-                               max(1e-9, float(np.median([e["per_frame_ms"] for e in pool])) * 1e-3)},
+                               max(1e-9, float(np.median([e["per_frame_ms"] for e in pool])) * 1e-3),
+                               "what": "cg_integrate_pointcloud_device, input resident in HBM",
+                               "host_pageable": per_frame_host},
             "integrate": {"value": dv["points"] / (dv["int_ms"] * 1e-3), "unit": "points/s",
                           "ms_per_step": dv["int_ms"] / args.steps,
                           "hbm_frac_phase": dv["bytes_int"] / (dv["int_ms"] * 1e-3) / 1e9 / peak},

@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kMergeThreads)
 k_project_batch(const BatchSubmap* __restrict__ desc, LayerView B,
                 const uint64_t* __restrict__ map_keys, const BatchCand* __restrict__ list,
                 const RankTable* __restrict__ table, unsigned long long* done,
-                uint32_t* work_counter, CallCounters* counters) {
+                uint32_t* work_counter, CallCounters* counters, int bulk_prefetch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_d = reinterpret_cast<float*>(smem_raw);  // resampled block, planar
   float* s_w = s_d + kVoxelsPerBlock;
@@ -588,11 +588,27 @@ k_project_batch(const BatchSubmap* __restrict__ desc, LayerView B,
       const int az = __float2int_rd((pc.z - reach) * A.block_size_inv);
       const int t = threadIdx.x;
       const int dx = t % kTab, dy = (t / kTab) % kTab, dz = t / (kTab * kTab);
-      tab.slot[t] = A.find_slot(pack_block_key(ax + dx, ay + dy, az + dz));
+      const int slot = A.find_slot(pack_block_key(ax + dx, ay + dy, az + dz));
+      tab.slot[t] = slot;
       if (t == 0) {
         tab.ax = ax;
         tab.ay = ay;
         tab.az = az;
+      }
+      // Optional (CG_MERGE_BULK_PREFETCH=1; measured, off by default — DESIGN.md §4.3): the TMA
+      // unit pulls the three planes of every source block the rotated destination block can
+      // reach into L2 (one cp.async.bulk.prefetch per block, 48 KB) while the taps are set up.
+      if (bulk_prefetch && slot >= 0) {
+        const V3 cb = V3{center_coord(ax + dx, A.block_size), center_coord(ay + dy, A.block_size),
+                         center_coord(az + dz, A.block_size)};
+        const V3 dv = cb - pc;
+        const float lim = reach + 0.8660254f * A.block_size;
+        if (dot3(dv, dv) <= lim * lim) {
+          const float* src = A.dist_plane(slot);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src),
+                       "r"(static_cast<uint32_t>(3 * kVoxelsPerBlock * sizeof(float)))
+                       : "memory");
+        }
       }
     }
     __syncthreads();
@@ -729,11 +745,15 @@ static int32_t project_batch(const cg_layer* const* submaps, const BatchSubmap* 
   }
   {
     StageScope sc(ctx, kStageMergeResample, 1);
+    static const int bulk_prefetch = [] {
+      const char* e = getenv("CG_MERGE_BULK_PREFETCH");
+      return (e && *e == '1') ? 1 : 0;
+    }();
     const unsigned grid = static_cast<unsigned>(
         std::min<size_t>(cand_bound, static_cast<size_t>(ctx->num_sms) * 2));
     k_project_batch<<<grid, kMergeThreads, smem, s>>>(
         d_desc + i0, G->v, ctx->cand_keys.as<uint64_t>(), ctx->merge_cands.as<BatchCand>(), table,
-        done, ctx->d_work_counter, ctx->d_counters);
+        done, ctx->d_work_counter, ctx->d_counters, bulk_prefetch);
   }
   CG_CUDA(cudaGetLastError());
   return CG_OK;

@@ -4,10 +4,15 @@
 // with the CPU oracle.
 //   host_api_check nogpu                       -> exit 0 iff creating a context fails loudly
 //   host_api_check run <in.bin> <out.bin>      -> integrate frames, merge, dump both layers
+//   host_api_check time <in.bin> <passes>      -> the live path as a C++ host drives it: one
+//                                                 integratePointCloud call per frame with pageable
+//                                                 std::vector inputs; prints the mean ms per call
 // in.bin : u32 F, f32 voxel_size, f32 trunc, f32 T_M_S[7], then per frame: f32 T[7], u32 n,
 //          n * 3 f32 points, n * 4 u8 colours
 // out.bin: per layer (submap, global): u32 B, B * 3 i32, B * 4096 * 12 B voxels
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -41,6 +46,48 @@ int main(int argc, char** argv) {
     }
     std::printf("a CUDA device is present\n");
     return 3;
+  }
+  if (argc >= 4 && std::string(argv[1]) == "time") {
+    FILE* in = fopen(argv[2], "rb");
+    if (!in) return 65;
+    const int passes = std::atoi(argv[3]);
+    uint32_t F = 0;
+    float voxel_size = 0, trunc = 0;
+    cg::Transformation T_M_S;
+    if (!rd(in, &F) || !rd(in, &voxel_size) || !rd(in, &trunc) || !rd(in, &T_M_S.qw, 7)) return 66;
+    std::vector<cg::Transformation> poses(F);
+    std::vector<cg::Pointcloud> clouds(F);
+    std::vector<cg::Colors> colours(F);
+    size_t points = 0;
+    for (uint32_t f = 0; f < F; ++f) {
+      uint32_t n = 0;
+      if (!rd(in, &poses[f].qw, 7) || !rd(in, &n)) return 67;
+      clouds[f].resize(n);
+      colours[f].resize(n);
+      if (n && (!rd(in, clouds[f].data(), n) || !rd(in, colours[f].data(), n))) return 68;
+      points += n;
+    }
+    fclose(in);
+    cg::Context ctx(0);
+    cg::TsdfLayer submap(ctx, voxel_size, 16, 4096);
+    cg::TsdfIntegratorBase::Config config;
+    config.default_truncation_distance = trunc;
+    config.use_const_weight = 1;
+    auto integrator = cg::TsdfIntegratorFactory::create("merged", config, &submap);
+    double best = 1e30;
+    for (int p = 0; p < passes + 1; ++p) {  // pass 0 warms up (scratch buffers, key box)
+      submap.removeAllBlocks();
+      const auto t0 = std::chrono::steady_clock::now();
+      for (uint32_t f = 0; f < F; ++f)
+        integrator->integratePointCloud(poses[f], clouds[f], colours[f], false);
+      const double ms =
+          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (p > 0 && ms < best) best = ms;
+    }
+    std::printf("{\"ms_per_call\": %.6f, \"frames\": %u, \"points_per_call\": %.1f, "
+                "\"blocks\": %lld}\n",
+                best / F, F, double(points) / F, static_cast<long long>(submap.getNumberOfAllocatedBlocks()));
+    return 0;
   }
   if (argc < 4 || std::string(argv[1]) != "run") return 64;
   FILE* in = fopen(argv[2], "rb");

@@ -136,3 +136,32 @@ def test_bundle_key_box_grows_and_shrinks(monkeypatch):
         util.compare_layers(gl.download(), ol.download(), f"job {k} (reach {r} m)")
     gl.close()
     ctx.close()
+
+
+def test_listed_blocks_download_and_hash_stats(gpu_ctx):
+    """cg_layer_download_blocks returns exactly what cg_layer_download holds for the listed
+    indices and flags the ones that are not allocated; cg_layer_hash_stats reports the occupancy
+    of the block hash."""
+    from coxgraph_b200 import Layer, TsdfIntegrator
+    _, gcfg = util.make_cfgs()
+    gl = Layer(gpu_ctx, 0.05, max_blocks=2048)
+    integ = TsdfIntegrator(gcfg, gl)
+    for (T, p, c) in util.small_frames(2, stride=8):
+        integ.integratePointCloud(T, p, c)
+    idx, vox, flags = gl.download()
+    pick = idx[::3]
+    missing = np.array([[1000, 1000, 1000], [-999, 5, 7]], np.int32)
+    ask = np.concatenate([pick[:5], missing, pick[5:]])
+    v, f, found = gl.download_blocks(ask)
+    assert found.tolist() == [True] * 5 + [False, False] + [True] * (len(pick) - 5)
+    got = np.concatenate([v[:5], v[7:]])
+    ref = vox[::3]
+    for name in ("distance", "weight"):
+        assert np.array_equal(got[name].view(np.uint32), ref[name].view(np.uint32))
+    assert np.array_equal(got["rgba"], ref["rgba"])
+    assert np.array_equal(np.concatenate([f[:5], f[7:]]), flags[::3])
+    st = gl.hash_stats()
+    assert st.num_blocks == len(idx) and st.hash_capacity >= 2 * gl.max_blocks
+    assert 0 < st.load_factor < 0.5 and 1.0 <= st.mean_probe_length < 2.0
+    assert st.max_probe_length >= 1
+    gl.close()
