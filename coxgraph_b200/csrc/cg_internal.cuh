@@ -194,6 +194,7 @@ enum Stage {
   kStageBlockAccumulate,
   kStagePairSort,
   kStageSegments,
+  kStageVisits,
   kStageVoxelUpdate,
   kStageReplayWide,
   kStageFinalize,
@@ -252,7 +253,7 @@ struct cg_context : cg::FrontBufs {
   // integration scratch
   cg::DevBuf points, colors;
   cg::DevBuf val_a, val_b, flags;
-  cg::DevBuf pkey_a, pkey_b, seg_start, long_list, long_partials;
+  cg::DevBuf pkey_a, pkey_b, seg_start, long_list, long_partials, visits;
   cg::DevBuf seg_keys_a, seg_keys_b, seg_idx_a, seg_idx_b, seg_recs;  // (ray, block) segments
   cg::DevBuf seg_order;  // update lists in size-class order
   cg::DevBuf seg_bins;

@@ -1260,33 +1260,60 @@ __device__ __forceinline__ VoxelRef voxel_ref(const IntegratorParams& P, const L
   return r;
 }
 
+// The state-independent part of every ordered update — signed distance along the ray, effective
+// weight (drop-off, sparsity compensation), colour — computed by one thread per (voxel, ray) key,
+// fully parallel and with coalesced stores: what is left for the ordered replay is the short
+// dependent chain on (D, W, C).  Same operations, in the same order, as updateTsdfVoxel (R5).
+__global__ void __launch_bounds__(256)
+k_visit_precompute(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
+                   const unsigned long long* __restrict__ keys, uint32_t ray_bits,
+                   const uint32_t* __restrict__ num_keys_dev, uint32_t num_keys, LayerView L,
+                   TouchView Tv, float4* __restrict__ visits) {
+  const uint32_t n = num_keys_dev ? min(*num_keys_dev, num_keys) : num_keys;
+  const uint32_t ray_mask = (1u << ray_bits) - 1u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long key = keys[i];
+    const uint32_t vid = static_cast<uint32_t>(key >> ray_bits);
+    const uint32_t entry = Tv.entry[vid >> 12];
+    const int lin = static_cast<int>(vid & 4095u);
+    int bx, by, bz;
+    unpack_block_key(L.hash_keys[entry], bx, by, bz);
+    const V3 center = V3{center_coord(bx * 16 + (lin & 15), P.voxel_size),
+                         center_coord(by * 16 + ((lin >> 4) & 15), P.voxel_size),
+                         center_coord(bz * 16 + (lin >> 8), P.voxel_size)};
+    const Visit v = make_visit(P, poses, rays[static_cast<uint32_t>(key) & ray_mask], center);
+    visits[i] = make_float4(v.sdf, v.w, __uint_as_float(v.col), 0.0f);
+  }
+}
+// second half of updateTsdfVoxel: one precomputed visit applied to the voxel state
+__device__ __forceinline__ void apply_visit(const IntegratorParams& p, float sdf, float updated_weight,
+                                            uint32_t color, VoxelState& v) {
+  const float new_weight = v.w + updated_weight;
+  if (new_weight < kEps) return;
+  const float new_sdf = (sdf * updated_weight + v.d * v.w) / new_weight;
+  if (fabsf(sdf) < p.trunc) v.c = blend_colors(v.c, v.w, color, updated_weight);
+  v.d = (new_sdf > 0.0f) ? fminf(p.trunc, new_sdf) : fmaxf(-p.trunc, new_sdf);
+  v.w = fminf(p.max_weight, new_weight);
+}
+
 // Replays updates [start, end) of one voxel on (D, W, C), 32 at a time: weights by prefix sum,
 // the clamped weighted average as an ordered tree reduction of clamped affine maps, colours
 // sequentially for the updates inside the truncation band.  The ray records of chunk c+1 and the
 // ray ids of chunk c+2 are in flight while chunk c is reduced.
 __device__ __forceinline__ void replay_segment(const IntegratorParams& P,
-                                               const float* __restrict__ poses,
-                                               const Ray* __restrict__ rays,
-                                               const unsigned long long* __restrict__ keys,
-                                               uint32_t ray_mask, uint32_t start, uint32_t end,
-                                               V3 center, int lane, float& D, float& W,
+                                               const float4* __restrict__ visits, uint32_t start,
+                                               uint32_t end, int lane, float& D, float& W,
                                                uint32_t& C) {
   const unsigned full = 0xFFFFFFFFu;
-  auto ray_id = [&](uint32_t j) -> uint32_t {
-    return (j < end) ? static_cast<uint32_t>(keys[j]) & ray_mask : 0u;
-  };
-  uint32_t id_next = ray_id(start + lane);
-  Ray ray_next = rays[id_next];
-  id_next = ray_id(start + 32 + lane);
+  float4 next = (start + lane < end) ? visits[start + lane] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   for (uint32_t c0 = start; c0 < end; c0 += 32) {
-    const Ray ray = ray_next;
-    if (c0 + 32 < end) {
-      ray_next = rays[id_next];
-      id_next = ray_id(c0 + 64 + lane);
-    }
+    const float4 cur = next;
+    if (c0 + 32 + lane < end) next = visits[c0 + 32 + lane];  // next chunk in flight
     const bool act = c0 + lane < end;
-    Visit v = make_visit(P, poses, ray, center);
-    if (!act) v.w = 0.0f;
+    Visit v;
+    v.sdf = cur.x;
+    v.w = act ? cur.y : 0.0f;
+    v.col = __float_as_uint(cur.z);
     const float sdf = v.sdf;
     // "new_weight < kFloatEpsilon -> return" leaves the voxel untouched, weight included.  The
     // weights are >= 0, so updates are skipped only while the stored weight is still below
@@ -1427,98 +1454,76 @@ __global__ void k_segment_order(const uint32_t* __restrict__ seg_start,
 // order).  Lists of kWideSegment updates or more go to a list for the warp-cooperative kernels
 // below (k_long_partials / k_long_finish).
 constexpr uint32_t kWideSegment = 96;
-constexpr int kUpdateInner = 4;
+constexpr int kUpdateInner = 8;
 __global__ void __launch_bounds__(128)
-k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
+k_voxel_update(IntegratorParams P, const float4* __restrict__ visits,
                const unsigned long long* __restrict__ keys, uint32_t ray_bits, uint32_t num_pairs,
                const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ num_segs,
                const uint32_t* __restrict__ order, uint32_t* work_counter,
                unsigned long long* long_counter, LongSeg* long_list, uint32_t long_cap, LayerView L,
-               TouchView Tv, int num_frames) {
-  // sensor origins of the group's frames in shared memory: the per-update chain key -> ray ->
-  // pose would otherwise end in a global load that nothing hides (few lists, few warps)
-  constexpr int kOriginFrames = 256;
-  __shared__ float s_origin[3 * kOriginFrames];
-  const bool origins_staged = num_frames <= kOriginFrames;
-  if (origins_staged)
-    for (int i = threadIdx.x; i < 3 * num_frames; i += blockDim.x)
-      s_origin[i] = poses[7 * (i / 3) + 4 + (i % 3)];
-  __syncthreads();
+               TouchView Tv) {
+  // A warp takes 32 consecutive lists of the size-class order (nearly equal lengths), one per
+  // lane, and runs them to the end of the longest before it fetches the next 32: the chain of
+  // dependent loads that sets a list up (order -> list bounds -> key -> block -> voxel state) is
+  // paid once per batch.  (Handing a lane its next list as soon as it ran out stalled the whole
+  // warp on that chain every few updates: 0.09 ms for 3 M warp instructions.)
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
   const uint32_t ns = *num_segs;
-  const uint32_t ray_mask = (1u << ray_bits) - 1u;
-  uint32_t cur = 0, end = 0;
-  bool finished = false;
-  VoxelRef vr;
-  vr.dp = vr.wp = nullptr;
-  vr.cp = nullptr;
-  vr.center = V3{0.0f, 0.0f, 0.0f};
-  VoxelState st{0.0f, 0.0f, 0u};
-  Ray ray_next = rays[0], ray_next2 = ray_next;
-  uint32_t id_next = 0;
   for (;;) {
-    const bool need = !finished && cur >= end;
-    const unsigned m = __ballot_sync(full, need);
-    if (m) {
-      const int leader = __ffs(m) - 1;
-      uint32_t base = 0;
-      if (lane == leader) base = atomicAdd(work_counter, static_cast<uint32_t>(__popc(m)));
-      base = __shfl_sync(full, base, leader);
-      if (need) {
-        const uint32_t oidx = base + __popc(m & lt);
-        if (oidx < ns) {
-          const uint32_t sidx = order[oidx];  // lists in size-class order
-          const uint32_t start = seg_start[sidx];
-          const uint32_t stop = (sidx + 1 < ns) ? seg_start[sidx + 1] : num_pairs;
-          vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[start] >> ray_bits));
-          cur = end = 0;
-          if (vr.slot >= 0) {  // else: pool exhausted, error already flagged
-            if (stop - start >= kWideSegment) {
-              const uint32_t nsub =
-                  stop - start >= kLongSegment ? (stop - start + kLongSub - 1) / kLongSub : 0u;
-              // one 64-bit atomic hands out the list index (high word) and the sub-block range
-              const unsigned long long old =
-                  atomicAdd(long_counter, (1ull << 32) | static_cast<unsigned long long>(nsub));
-              const uint32_t idx = static_cast<uint32_t>(old >> 32);
-              if (idx < long_cap)
-                long_list[idx] = LongSeg{start, stop, static_cast<uint32_t>(old), 0u};
-            } else {
-              cur = start;
-              end = stop;
-              st.d = *vr.dp;
-              st.w = *vr.wp;
-              st.c = *vr.cp;
-              ray_next = rays[static_cast<uint32_t>(keys[start]) & ray_mask];
-              ray_next2 = rays[(start + 1 < stop) ? static_cast<uint32_t>(keys[start + 1]) & ray_mask : 0u];
-              id_next = (start + 2 < stop) ? static_cast<uint32_t>(keys[start + 2]) & ray_mask : 0u;
-            }
-          }
+    uint32_t batch = 0;
+    if (lane == 0) batch = atomicAdd(work_counter, 1u);
+    batch = __shfl_sync(full, batch, 0);
+    if (batch * 32u >= ns) break;
+    const uint32_t oidx = batch * 32u + lane;
+    uint32_t cur = 0, end = 0;
+    VoxelRef vr;
+    vr.dp = vr.wp = nullptr;
+    vr.cp = nullptr;
+    VoxelState st{0.0f, 0.0f, 0u};
+    float4 q[kUpdateInner];  // the next visits of this lane's list, in flight
+#pragma unroll
+    for (int u = 0; u < kUpdateInner; ++u) q[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (oidx < ns) {
+      const uint32_t sidx = order[oidx];
+      const uint32_t start = seg_start[sidx];
+      const uint32_t stop = (sidx + 1 < ns) ? seg_start[sidx + 1] : num_pairs;
+      vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[start] >> ray_bits));
+      if (vr.slot >= 0) {  // else: pool exhausted, error already flagged
+        if (stop - start >= kWideSegment) {
+          const uint32_t nsub =
+              stop - start >= kLongSegment ? (stop - start + kLongSub - 1) / kLongSub : 0u;
+          // one 64-bit atomic hands out the list index (high word) and the sub-block range
+          const unsigned long long old =
+              atomicAdd(long_counter, (1ull << 32) | static_cast<unsigned long long>(nsub));
+          const uint32_t idx = static_cast<uint32_t>(old >> 32);
+          if (idx < long_cap) long_list[idx] = LongSeg{start, stop, static_cast<uint32_t>(old), 0u};
         } else {
-          finished = true;
+          cur = start;
+          end = stop;
+#pragma unroll
+          for (int u = 0; u < kUpdateInner; ++u)
+            if (start + u < stop) q[u] = visits[start + u];
+          st.d = *vr.dp;
+          st.w = *vr.wp;
+          st.c = *vr.cp;
         }
       }
     }
-    if (__all_sync(full, finished)) break;
-#pragma unroll 1
-    for (int t = 0; t < kUpdateInner; ++t) {
-      if (cur < end) {
-        // software pipeline: the key of update cur+3 and the ray records of updates cur+1 and
-        // cur+2 are in flight while update cur is applied (a ray record is a dependent, random
-        // load: one update of head start does not cover its latency)
-        const Ray ray = ray_next;
-        ray_next = ray_next2;
-        ray_next2 = rays[id_next];
-        id_next = (cur + 3 < end) ? static_cast<uint32_t>(keys[cur + 3]) & ray_mask : 0u;
-        const uint32_t fr = ray.frame_clr & 0x7FFFFFFFu;
-        const float* T = origins_staged ? s_origin + 3 * fr : poses + 7 * fr + 4;
-        update_tsdf_voxel(P, V3{T[0], T[1], T[2]}, V3{ray.px, ray.py, ray.pz}, vr.center, ray.color,
-                          ray.weight, st);
-        if (++cur >= end) {
-          *vr.dp = st.d;
-          *vr.wp = st.w;
-          *vr.cp = st.c;
+    // the precomputed visits stream through a kUpdateInner-deep register queue; what is sequential
+    // per update is the short chain of apply_visit
+    while (__any_sync(full, cur < end)) {
+#pragma unroll
+      for (int t = 0; t < kUpdateInner; ++t) {
+        if (cur < end) {
+          const float4 v = q[t];
+          if (cur + kUpdateInner < end) q[t] = visits[cur + kUpdateInner];
+          apply_visit(P, v.x, v.y, __float_as_uint(v.z), st);
+          if (++cur >= end) {
+            *vr.dp = st.d;
+            *vr.wp = st.w;
+            *vr.cp = st.c;
+          }
         }
       }
     }
@@ -1527,10 +1532,9 @@ k_voxel_update(IntegratorParams P, const float* __restrict__ poses, const Ray* _
 
 // sub-block t of the long segments: sum of weights + "all free space" flag (one warp each)
 __global__ void __launch_bounds__(256)
-k_long_partials(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
-                const unsigned long long* __restrict__ keys, uint32_t ray_bits,
+k_long_partials(IntegratorParams P, const float4* __restrict__ visits,
                 const unsigned long long* __restrict__ long_counter,
-                const LongSeg* __restrict__ long_list, uint32_t long_cap, LayerView L, TouchView Tv,
+                const LongSeg* __restrict__ long_list, uint32_t long_cap,
                 LongPartial* __restrict__ partials) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
@@ -1539,7 +1543,6 @@ k_long_partials(IntegratorParams P, const float* __restrict__ poses, const Ray* 
   const unsigned long long cnt = *long_counter;
   const uint32_t nlong = min(static_cast<uint32_t>(cnt >> 32), long_cap);
   const uint32_t nitems = static_cast<uint32_t>(cnt);
-  const uint32_t ray_mask = (1u << ray_bits) - 1u;
   for (uint32_t t = warp; t < nitems; t += num_warps) {
     // long_list is ordered by item_base (both come from the same atomic): binary search
     uint32_t lo = 0, hi = nlong;
@@ -1551,17 +1554,15 @@ k_long_partials(IntegratorParams P, const float* __restrict__ poses, const Ray* 
     if (t < seg.item_base) continue;
     const uint32_t a = seg.start + (t - seg.item_base) * kLongSub;
     const uint32_t b = min(seg.end, a + kLongSub);
-    const VoxelRef vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[seg.start] >> ray_bits));
     float sum = 0.0f;
     bool not_free = false;
     for (uint32_t c0 = a; c0 < b; c0 += 32) {
       const uint32_t j = c0 + lane;
       float w = 0.0f;
       if (j < b) {
-        const Visit v =
-            make_visit(P, poses, rays[static_cast<uint32_t>(keys[j]) & ray_mask], vr.center);
-        w = v.w;
-        not_free = not_free || !(v.sdf >= P.trunc);
+        const float4 v = visits[j];
+        w = v.y;
+        not_free = not_free || !(v.x >= P.trunc);
       }
 #pragma unroll
       for (int d = 16; d >= 1; d >>= 1) w += __shfl_xor_sync(full, w, d);
@@ -1575,7 +1576,7 @@ k_long_partials(IntegratorParams P, const float* __restrict__ poses, const Ray* 
 // one warp per long segment: closed form when every update is a free-space observation of a
 // voxel that is fresh or already at +truncation, otherwise the general replay.
 __global__ void __launch_bounds__(256)
-k_long_finish(IntegratorParams P, const float* __restrict__ poses, const Ray* __restrict__ rays,
+k_long_finish(IntegratorParams P, const float4* __restrict__ visits,
               const unsigned long long* __restrict__ keys, uint32_t ray_bits,
               const unsigned long long* __restrict__ long_counter,
               const LongSeg* __restrict__ long_list, uint32_t long_cap, LayerView L, TouchView Tv,
@@ -1585,7 +1586,6 @@ k_long_finish(IntegratorParams P, const float* __restrict__ poses, const Ray* __
   const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
   const unsigned long long cnt = *long_counter;
   const uint32_t nlong = min(static_cast<uint32_t>(cnt >> 32), long_cap);
-  const uint32_t ray_mask = (1u << ray_bits) - 1u;
   for (uint32_t i = warp; i < nlong; i += num_warps) {
     const LongSeg seg = long_list[i];
     const VoxelRef vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[seg.start] >> ray_bits));
@@ -1608,7 +1608,7 @@ k_long_finish(IntegratorParams P, const float* __restrict__ poses, const Ray* __
         W = fminf(P.max_weight, w_total);
       }
     } else {
-      replay_segment(P, poses, rays, keys, ray_mask, seg.start, seg.end, vr.center, lane, D, W, C);
+      replay_segment(P, visits, seg.start, seg.end, lane, D, W, C);
     }
     if (lane == 0) {
       *vr.dp = D;
@@ -1901,6 +1901,13 @@ static int32_t run_back_half(cg_context* ctx, const FrontBufs& fb, cg_layer* L,
                                     static_cast<int>(n_general),
                                     SegmentHead{dk.Current(), ray_bits}, s));
     }
+    {  // the state-independent part of every ordered update, one thread per key
+      StageScope sc(ctx, kStageVisits, 1);
+      CG_CUDA(ctx->visits.reserve(size_t(n_general) * sizeof(float4)));
+      k_visit_precompute<<<std::min<unsigned>(grid_for(n_general, 256), ctx->num_sms * 16u), 256, 0, s>>>(
+          P, fb.group_poses, fb.rays.as<Ray>(), dk.Current(), ray_bits, nullptr, n_general, L->v, tv,
+          ctx->visits.as<float4>());
+    }
     const uint32_t long_cap = static_cast<uint32_t>(n_general / kWideSegment + 1);
     const size_t max_items = n_general / kLongSub + long_cap + 1;
     CG_CUDA(ctx->long_list.reserve(long_cap * sizeof(LongSeg)));
@@ -1917,18 +1924,17 @@ static int32_t run_back_half(cg_context* ctx, const FrontBufs& fb, cg_layer* L,
       k_segment_order<<<ogrid, 256, 0, s>>>(ctx->seg_start.as<uint32_t>(), d_num, n_general,
                                             ctx->d_class_count, ctx->seg_order.as<uint32_t>());
       k_voxel_update<<<ctx->num_sms * 8, 128, 0, s>>>(
-          P, fb.group_poses, fb.rays.as<Ray>(), dk.Current(), ray_bits, n_general,
+          P, ctx->visits.as<float4>(), dk.Current(), ray_bits, n_general,
           ctx->seg_start.as<uint32_t>(), d_num, ctx->seg_order.as<uint32_t>(), ctx->d_work_counter,
-          ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv, fb.group_frames);
+          ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv);
     }
     {
       StageScope sc(ctx, kStageReplayWide, 2);
       k_long_partials<<<ctx->num_sms * 8, 256, 0, s>>>(
-          P, fb.group_poses, fb.rays.as<Ray>(), dk.Current(), ray_bits,
-          ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv,
+          P, ctx->visits.as<float4>(), ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap,
           ctx->long_partials.as<LongPartial>());
       k_long_finish<<<ctx->num_sms * 4, 256, 0, s>>>(
-          P, fb.group_poses, fb.rays.as<Ray>(), dk.Current(), ray_bits,
+          P, ctx->visits.as<float4>(), dk.Current(), ray_bits,
           ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv,
           ctx->long_partials.as<LongPartial>());
     }

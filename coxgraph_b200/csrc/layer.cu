@@ -29,7 +29,7 @@ const char* stage_name(int s) {
   static const char* names[kNumStages] = {
       "point_keys",    "bundle_sort",  "bundle_scan",      "gather_sorted", "bundle_order",
       "fold_wide",     "fold_bundles", "bundle_rays",      "ray_scan",      "walk_segments",
-      "segment_sort",  "block_accumulate", "pair_sort",    "segments",      "voxel_update",
+      "segment_sort",  "block_accumulate", "pair_sort",    "segments",   "visits",   "voxel_update",
       "replay_wide",   "finalize",     "merge_mark",       "merge_resample", "transfer"};
   return (s >= 0 && s < kNumStages) ? names[s] : "?";
 }
@@ -518,7 +518,7 @@ int32_t cg_context_destroy(cg_context* ctx) {
                     &ctx->pkey_a, &ctx->pkey_b, &ctx->seg_keys_a, &ctx->seg_keys_b, &ctx->seg_idx_a,
                     &ctx->seg_idx_b, &ctx->seg_recs, &ctx->seg_order, &ctx->seg_bins,
                     &ctx->touch_ord, &ctx->touch_entry, &ctx->touch_acc, &ctx->touch_bits,
-                    &ctx->seg_start, &ctx->long_list, &ctx->long_partials, &ctx->cand_keys,
+                    &ctx->seg_start, &ctx->long_list, &ctx->long_partials, &ctx->visits, &ctx->cand_keys,
                     &ctx->cand_list, &ctx->stage_a, &ctx->stage_b, &ctx->stage_c, &ctx->batch_desc,
                     &ctx->merge_cands, &ctx->mc_counts, &ctx->mc_index, &ctx->mc_vertices,
                     &ctx->mc_normals, &ctx->mc_colors, &ctx->mesh_in, &ctx->mesh_tri,

@@ -5,7 +5,8 @@
 tag=${1:-r1}
 mkdir -p gpurun_out
 # enough warm-up steps for the context's scratch buffers and bundle-key box to settle
-ARGS="--steps 2 --warmup 10 --profile-mode"
+# STEPS=2 ends on robot 1's submap, STEPS=3 on robot 0's (the steps alternate between the robots)
+ARGS="--steps ${STEPS:-2} --warmup 10 --profile-mode"
 if [ -z "$SKIP_STEP" ]; then
 python bench.py $ARGS > gpurun_out/plain_$tag.log 2>&1 || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "cg_step/" -k "regex:^k_|^Device" --csv \
