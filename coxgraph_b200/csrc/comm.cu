@@ -1,19 +1,25 @@
 // comm.cu — the server's global merge across the GPUs of one box, behind the C ABI (SURVEY.md
 // §8b cg_comm_init / cg_gather_global, §8e).
 //
-// Every rank projects its submaps into a *partial* global layer; a global block is owned by rank
-// cg_block_owner(index).  The exchange is an owner-pull over NVLink peer memory: each rank lists
-// the slots of its partial blocks per owner, and the owner's fold kernel reads those blocks
-// straight out of the peers' block pools (peer pointers opened through CUDA IPC) while it folds
-// them into its own layer with voxblox::mergeLayerAintoLayerB's aligned form (Block::mergeBlock /
-// mergeVoxelAIntoVoxelB, R10; reference call site of that overload:
-// coxgraph/src/server/submap_collection.cpp:31-33) — gather and fold are ONE kernel, there is no
-// packing pass, no staging copy and no host synchronisation between listing, exchange and fold.
-// NCCL (loaded at run time from libnccl.so.2, the one torch has loaded if there is one) is the
-// bootstrap and the barrier only: unique id -> communicator, one all-gather of the IPC handles
-// when a partial layer is bound, and a one-word all-reduce on the stream before and after the fold
-// kernels (all partial layers complete / all peers done reading).  Sources are folded in ascending
-// rank order, one launch per source, so the result is deterministic.
+// Every rank projects its submaps into a *partial* global layer.  The exchange is an owner-pull
+// over NVLink peer memory (peer pointers opened through CUDA IPC):
+//   k_build_holders  every rank reads the block keys of every rank's partial layer (8 B per block)
+//                    and builds the same map  block -> set of ranks that hold it
+//   k_list_owned     the owner of a block is one of its HOLDERS, picked by a hash of the index: a
+//                    block only one rank holds never crosses NVLink, contested blocks spread
+//                    evenly over their holders
+//   k_fold_owned     one CTA per owned block: the holders' copies are read straight out of their
+//                    block pools, in ascending rank order, and folded in shared memory with
+//                    voxblox::mergeLayerAintoLayerB's aligned form (Block::mergeBlock /
+//                    mergeVoxelAIntoVoxelB, R10; reference call site of that overload:
+//                    coxgraph/src/server/submap_collection.cpp:31-33); the block is written once
+// — gather and fold are ONE kernel, there is no packing pass, no staging copy and no host
+// synchronisation between listing, exchange and fold.  NCCL (loaded at run time from
+// libnccl.so.2, the one torch has loaded if there is one) is the bootstrap and the barrier only:
+// unique id -> communicator, one all-gather of the IPC handles when a partial layer is bound, and a
+// one-word all-reduce on the stream before and after the kernels (all partial layers complete /
+// all peers done reading).  The fold order is fixed, so the result is deterministic and equal to
+// the packed exchange of exchange.cu (hash owner, NCCL all-to-all) block for block.
 #include <dlfcn.h>
 #include <string.h>
 
@@ -78,8 +84,7 @@ struct PeerLayer {
   const float* pool;
   const uint64_t* block_keys;
   const uint8_t* has_data;
-  const uint32_t* lists;   // [nranks][list_cap] pool slots, grouped by owner
-  const uint32_t* counts;  // [nranks]
+  const uint32_t* shared;  // [0] number of blocks of the partial layer (written per call)
 };
 constexpr int kMaxRanks = 64;
 
@@ -99,76 +104,187 @@ struct cg_comm {
   int* d_token = nullptr;             // barrier word
   // binding of one partial layer
   const cg_layer* bound = nullptr;
-  uint32_t* shared = nullptr;         // [nranks * list_cap] lists, then [nranks] counts (this rank's)
-  size_t list_cap = 0;
+  uint32_t* shared = nullptr;         // peer-visible: [0] blocks of this rank's partial layer
   std::vector<void*> opened;          // peer mappings to close
   cg::PeerLayer* d_peers = nullptr;   // [nranks]
+  // the holder map (scratch, rebuilt every call): block key -> set of ranks holding the block
+  unsigned long long* hkeys = nullptr;
+  unsigned long long* hmask = nullptr;
+  uint32_t* hbase = nullptr;          // owned entries: first element of the block's slot list
+  uint32_t* mine = nullptr;           // entries this rank owns
+  uint32_t* slots = nullptr;          // pool slots of the holders' copies, per owned block
+  uint32_t* counters = nullptr;       // [0] owned entries, [1] slot list cursor, [2] overflow
+  size_t hcap = 0, list_cap = 0;
 };
 
 namespace cg {
 
-static __host__ __device__ __forceinline__ uint32_t comm_owner_of(uint64_t key, uint32_t nranks) {
-  return (hash_key(key ^ 0x9E3779B97F4A7C15ULL) >> 7) % nranks;  // == cg_block_owner
+__device__ __forceinline__ uint32_t holder_find(const unsigned long long* __restrict__ hkeys,
+                                                uint32_t hmask_cap, unsigned long long key) {
+  uint32_t h = hash_key(key) & hmask_cap;
+  while (hkeys[h] != key) h = (h + 1) & hmask_cap;
+  return h;
+}
+// the owner of a block: one of its holders, picked by a hash of the block index
+__device__ __forceinline__ int pick_owner(unsigned long long key, unsigned long long mask) {
+  int n = static_cast<int>((hash_key(key ^ 0x9E3779B97F4A7C15ULL) >> 7) %
+                           static_cast<uint32_t>(__popcll(mask)));
+  unsigned long long m = mask;
+  while (n-- > 0) m &= m - 1;
+  return __ffsll(static_cast<long long>(m)) - 1;
 }
 
-// slots of the partial layer's blocks, grouped by owner
-__global__ void k_owner_lists(LayerView L, int n, uint32_t nranks, uint32_t list_cap,
-                              uint32_t* __restrict__ lists, uint32_t* __restrict__ counts) {
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= n) return;
-  const uint32_t o = comm_owner_of(L.block_keys[slot], nranks);
-  const uint32_t pos = atomicAdd(&counts[o], 1u);
-  if (pos < list_cap) lists[static_cast<size_t>(o) * list_cap + pos] = static_cast<uint32_t>(slot);
+// Every block key of every rank's partial layer (read through the peer mappings) enters the map
+// with its rank's bit.  Grid y = rank.
+__global__ void k_build_holders(const PeerLayer* __restrict__ peers, unsigned long long* hkeys,
+                                unsigned long long* hmask, uint32_t hcap_mask, uint32_t* counters) {
+  const int r = blockIdx.y;
+  const PeerLayer P = peers[r];
+  const uint32_t n = P.shared[0];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long key = P.block_keys[i];
+    uint32_t h = hash_key(key) & hcap_mask;
+    for (uint32_t tries = 0;; ++tries) {
+      const unsigned long long k = hkeys[h];
+      if (k == key) break;
+      if (k == kEmptyKey) {
+        const unsigned long long old = atomicCAS(&hkeys[h], kEmptyKey, key);
+        if (old == kEmptyKey || old == key) break;
+      }
+      h = (h + 1) & hcap_mask;
+      if (tries > hcap_mask) {  // cannot happen: the map holds every block of every rank
+        atomicExch(&counters[2], 1u);
+        return;
+      }
+    }
+    atomicOr(&hmask[h], 1ull << r);
+  }
+}
+// entries this rank owns, each with room for its holders' slots
+__global__ void k_list_owned(const unsigned long long* __restrict__ hkeys,
+                             const unsigned long long* __restrict__ hmask, uint32_t hcap, int me,
+                             uint32_t* __restrict__ hbase, uint32_t* __restrict__ mine,
+                             uint32_t list_cap, uint32_t* counters) {
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < hcap; e += gridDim.x * blockDim.x) {
+    const unsigned long long mask = hmask[e];
+    if (!mask || pick_owner(hkeys[e], mask) != me) continue;
+    const uint32_t pos = atomicAdd(&counters[0], 1u);
+    const uint32_t base = atomicAdd(&counters[1], static_cast<uint32_t>(__popcll(mask)));
+    if (pos < list_cap) {
+      mine[pos] = e;
+      hbase[e] = base;
+    } else {
+      atomicExch(&counters[2], 1u);
+    }
+  }
+}
+// the pool slot of every holder's copy of the blocks this rank owns.  Grid y = rank.
+__global__ void k_holder_slots(const PeerLayer* __restrict__ peers,
+                               const unsigned long long* __restrict__ hkeys,
+                               const unsigned long long* __restrict__ hmask,
+                               const uint32_t* __restrict__ hbase, uint32_t hcap_mask, int me,
+                               uint32_t* __restrict__ slots, uint32_t slots_cap) {
+  const int r = blockIdx.y;
+  const PeerLayer P = peers[r];
+  const uint32_t n = P.shared[0];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long key = P.block_keys[i];
+    const uint32_t e = holder_find(hkeys, hcap_mask, key);
+    const unsigned long long mask = hmask[e];
+    if (pick_owner(key, mask) != me) continue;
+    const uint32_t at = hbase[e] + __popcll(mask & ((1ull << r) - 1ull));
+    if (at < slots_cap) slots[at] = i;
+  }
 }
 
-// The blocks rank `src` holds for this rank, read through the peer mapping and folded into the
-// owner's layer: one CTA per block (grid-stride), 16-byte loads across NVLink.
-__global__ void __launch_bounds__(256)
-k_fold_pull(LayerView B, const PeerLayer* __restrict__ peers, int src, int me, uint32_t list_cap,
-            unsigned long long* folded) {
-  const PeerLayer P = peers[src];
-  const uint32_t n = min(P.counts[me], list_cap);
+// One CTA per owned block: the destination block (fresh blocks are in the default state) is staged
+// in shared memory, every holder's copy is read through its mapping — 16-byte loads, across
+// NVLink for the peers — and folded in ascending rank order, and the result is written once.
+constexpr int kFoldThreads = 256;
+__global__ void __launch_bounds__(kFoldThreads)
+k_fold_owned(LayerView B, const PeerLayer* __restrict__ peers,
+             const unsigned long long* __restrict__ hkeys,
+             const unsigned long long* __restrict__ hmask, const uint32_t* __restrict__ hbase,
+             const uint32_t* __restrict__ mine, const uint32_t* __restrict__ slots,
+             const uint32_t* __restrict__ counters, uint32_t list_cap, unsigned long long* folded) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4* t_d = reinterpret_cast<uint4*>(smem_raw);  // three planes of 4096 words
+  uint4* t_w = t_d + kVoxelsPerBlock / 4;
+  uint4* t_c = t_w + kVoxelsPerBlock / 4;
   __shared__ int s_slot;
+  const uint32_t n = min(counters[0], list_cap);
   for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-    const uint32_t a = P.lists[static_cast<size_t>(me) * list_cap + i];
-    __syncthreads();
+    const uint32_t e = mine[i];
+    const unsigned long long key = hkeys[e];
+    unsigned long long mask = hmask[e];
+    const uint32_t base = hbase[e];
+    // Block::mergeBlock skips a source block without data: is there one with data at all?
+    bool any = false;
+    {
+      unsigned long long m = mask;
+      for (int j = 0; m; ++j, m &= m - 1)
+        any = any || peers[__ffsll(static_cast<long long>(m)) - 1].has_data[slots[base + j]] != 0;
+    }
+    __syncthreads();  // the previous block's tile has been written out
+    if (!any) continue;
     if (threadIdx.x == 0) {
-      s_slot = -1;
-      if (P.has_data[a]) {  // Block::mergeBlock: a source block without data is skipped
-        const int e = B.insert_entry(P.block_keys[a]);
-        s_slot = B.hash_vals[e];
-        if (s_slot >= 0) {
-          B.has_data[s_slot] = 1;
-          B.updated[s_slot] = 1;
-          atomicAdd(folded, 1ull);
-        }
+      const int he = B.insert_entry(key);
+      s_slot = B.hash_vals[he];
+      if (s_slot >= 0) {
+        B.has_data[s_slot] = 1;
+        B.updated[s_slot] = 1;
+        atomicAdd(folded, static_cast<unsigned long long>(__popcll(mask)));
       }
     }
     __syncthreads();
     const int slot = s_slot;
-    if (slot < 0) continue;
-    const uint4* sd = reinterpret_cast<const uint4*>(P.pool + static_cast<size_t>(a) * (3 * kVoxelsPerBlock));
-    const uint4* sw = sd + kVoxelsPerBlock / 4;
-    const uint4* sc = sw + kVoxelsPerBlock / 4;
+    if (slot < 0) continue;  // pool exhausted: flagged by insert_entry
     uint4* dd = reinterpret_cast<uint4*>(B.dist_plane(slot));
     uint4* dw = reinterpret_cast<uint4*>(B.weight_plane(slot));
     uint4* dc = reinterpret_cast<uint4*>(B.color_plane(slot));
-    for (int q = threadIdx.x; q < kVoxelsPerBlock / 4; q += blockDim.x) {
-      const uint4 ad = sd[q], aw = sw[q], ac = sc[q];
-      uint4 bd = dd[q], bw = dw[q], bc = dc[q];
-      VoxelState v0{__uint_as_float(bd.x), __uint_as_float(bw.x), bc.x};
-      VoxelState v1{__uint_as_float(bd.y), __uint_as_float(bw.y), bc.y};
-      VoxelState v2{__uint_as_float(bd.z), __uint_as_float(bw.z), bc.z};
-      VoxelState v3{__uint_as_float(bd.w), __uint_as_float(bw.w), bc.w};
-      merge_voxel(__uint_as_float(ad.x), __uint_as_float(aw.x), ac.x, v0);
-      merge_voxel(__uint_as_float(ad.y), __uint_as_float(aw.y), ac.y, v1);
-      merge_voxel(__uint_as_float(ad.z), __uint_as_float(aw.z), ac.z, v2);
-      merge_voxel(__uint_as_float(ad.w), __uint_as_float(aw.w), ac.w, v3);
-      dd[q] = make_uint4(__float_as_uint(v0.d), __float_as_uint(v1.d), __float_as_uint(v2.d), __float_as_uint(v3.d));
-      dw[q] = make_uint4(__float_as_uint(v0.w), __float_as_uint(v1.w), __float_as_uint(v2.w), __float_as_uint(v3.w));
-      dc[q] = make_uint4(v0.c, v1.c, v2.c, v3.c);
+    for (int q = threadIdx.x; q < kVoxelsPerBlock / 4; q += kFoldThreads) {
+      t_d[q] = dd[q];
+      t_w[q] = dw[q];
+      t_c[q] = dc[q];
+    }
+    for (int j = 0; mask; ++j, mask &= mask - 1) {  // ascending rank: the fold order is fixed
+      const PeerLayer P = peers[__ffsll(static_cast<long long>(mask)) - 1];
+      const uint32_t a = slots[base + j];
+      if (!P.has_data[a]) continue;
+      const uint4* sd =
+          reinterpret_cast<const uint4*>(P.pool + static_cast<size_t>(a) * (3 * kVoxelsPerBlock));
+      const uint4* sw = sd + kVoxelsPerBlock / 4;
+      const uint4* sc = sw + kVoxelsPerBlock / 4;
+      // each thread folds the same quads in every round: no synchronisation between sources
+      for (int q = threadIdx.x; q < kVoxelsPerBlock / 4; q += kFoldThreads) {
+        const uint4 ad = sd[q], aw = sw[q], ac = sc[q];
+        const uint4 bd = t_d[q], bw = t_w[q], bc = t_c[q];
+        VoxelState v0{__uint_as_float(bd.x), __uint_as_float(bw.x), bc.x};
+        VoxelState v1{__uint_as_float(bd.y), __uint_as_float(bw.y), bc.y};
+        VoxelState v2{__uint_as_float(bd.z), __uint_as_float(bw.z), bc.z};
+        VoxelState v3{__uint_as_float(bd.w), __uint_as_float(bw.w), bc.w};
+        merge_voxel(__uint_as_float(ad.x), __uint_as_float(aw.x), ac.x, v0);
+        merge_voxel(__uint_as_float(ad.y), __uint_as_float(aw.y), ac.y, v1);
+        merge_voxel(__uint_as_float(ad.z), __uint_as_float(aw.z), ac.z, v2);
+        merge_voxel(__uint_as_float(ad.w), __uint_as_float(aw.w), ac.w, v3);
+        t_d[q] = make_uint4(__float_as_uint(v0.d), __float_as_uint(v1.d), __float_as_uint(v2.d),
+                            __float_as_uint(v3.d));
+        t_w[q] = make_uint4(__float_as_uint(v0.w), __float_as_uint(v1.w), __float_as_uint(v2.w),
+                            __float_as_uint(v3.w));
+        t_c[q] = make_uint4(v0.c, v1.c, v2.c, v3.c);
+      }
+    }
+    for (int q = threadIdx.x; q < kVoxelsPerBlock / 4; q += kFoldThreads) {
+      dd[q] = t_d[q];
+      dw[q] = t_w[q];
+      dc[q] = t_c[q];
     }
   }
+}
+
+__global__ void k_publish_blocks(uint32_t* shared, int n) { shared[0] = static_cast<uint32_t>(n); }
+__global__ void k_comm_overflow(const uint32_t* counters, int32_t* err) {
+  if (counters[2]) atomicOr(err, kErrPoolFull);
 }
 
 // pointer -> (allocation base handle, offset): cudaMalloc may place small buffers inside a larger
@@ -200,8 +316,11 @@ static int32_t ipc_of(const void* p, cudaIpcMemHandle_t* h, unsigned long long* 
 static void unbind(cg_comm* c) {
   for (void* p : c->opened) cudaIpcCloseMemHandle(p);
   c->opened.clear();
-  if (c->shared) cudaFree(c->shared);
-  c->shared = nullptr;
+  void* bufs[] = {c->shared, c->hkeys, c->hmask, c->hbase, c->mine, c->slots, c->counters};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  c->shared = c->hbase = c->mine = c->slots = c->counters = nullptr;
+  c->hkeys = c->hmask = nullptr;
   c->bound = nullptr;
 }
 
@@ -211,17 +330,25 @@ static int32_t barrier(cg_context* ctx) {
   return CG_OK;
 }
 
-// All ranks call this with their own partial layer (collective): lists + IPC handles exchanged,
-// peer mappings opened.  Done once per partial layer (it stays bound until another one is used).
+// All ranks call this with their own partial layer (collective): IPC handles exchanged, peer
+// mappings opened, scratch of the holder map sized for every block of every rank.  Done once per
+// partial layer (it stays bound until another one is used).
 static int32_t bind_partial(cg_context* ctx, const cg_layer* partial) {
   cg_comm* c = ctx->comm;
   unbind(c);
   cudaStream_t s = ctx->stream;
   const int R = c->nranks;
-  c->list_cap = partial->max_blocks;
-  const size_t words = static_cast<size_t>(R) * c->list_cap + R;
-  CG_CUDA(cudaMalloc(&c->shared, words * sizeof(uint32_t)));
-  CG_CUDA(cudaMemsetAsync(c->shared, 0, words * sizeof(uint32_t), s));
+  c->list_cap = partial->max_blocks * static_cast<size_t>(R);  // blocks over all ranks
+  c->hcap = 1024;
+  while (c->hcap < 2 * c->list_cap) c->hcap <<= 1;
+  CG_CUDA(cudaMalloc(&c->shared, 64));
+  CG_CUDA(cudaMalloc(&c->hkeys, c->hcap * sizeof(unsigned long long)));
+  CG_CUDA(cudaMalloc(&c->hmask, c->hcap * sizeof(unsigned long long)));
+  CG_CUDA(cudaMalloc(&c->hbase, c->hcap * sizeof(uint32_t)));
+  CG_CUDA(cudaMalloc(&c->mine, c->list_cap * sizeof(uint32_t)));
+  CG_CUDA(cudaMalloc(&c->slots, c->list_cap * sizeof(uint32_t)));
+  CG_CUDA(cudaMalloc(&c->counters, 4 * sizeof(uint32_t)));
+  CG_CUDA(cudaMemsetAsync(c->shared, 0, 64, s));
   IpcRecord mine;
   memset(&mine, 0, sizeof(mine));
   int32_t rc;
@@ -248,8 +375,7 @@ static int32_t bind_partial(cg_context* ctx, const cg_layer* partial) {
       return CG_ERR_INVALID_ARG;
     }
     if (r == c->rank) {
-      peers[r] = PeerLayer{partial->v.pool, partial->v.block_keys, partial->v.has_data, c->shared,
-                           c->shared + static_cast<size_t>(R) * c->list_cap};
+      peers[r] = PeerLayer{partial->v.pool, partial->v.block_keys, partial->v.has_data, c->shared};
       continue;
     }
     // several buffers of a peer may live in one allocation: a handle can be opened once only
@@ -272,11 +398,10 @@ static int32_t bind_partial(cg_context* ctx, const cg_layer* partial) {
         mapped[k] = static_cast<char*>(p);
       }
     }
-    const uint32_t* sh = reinterpret_cast<const uint32_t*>(mapped[3] + offs[3]);
     peers[r] = PeerLayer{reinterpret_cast<const float*>(mapped[0] + offs[0]),
                          reinterpret_cast<const uint64_t*>(mapped[1] + offs[1]),
-                         reinterpret_cast<const uint8_t*>(mapped[2] + offs[2]), sh,
-                         sh + static_cast<size_t>(R) * c->list_cap};
+                         reinterpret_cast<const uint8_t*>(mapped[2] + offs[2]),
+                         reinterpret_cast<const uint32_t*>(mapped[3] + offs[3])};
   }
   CG_CUDA(cudaMemcpyAsync(c->d_peers, peers.data(), sizeof(PeerLayer) * R, cudaMemcpyHostToDevice, s));
   CG_CUDA(cudaStreamSynchronize(s));
@@ -369,21 +494,33 @@ int32_t cg_gather_global(const cg_layer* partial, cg_layer* owned, uint64_t* blo
   int32_t rc;
   if (c->bound != partial && (rc = bind_partial(ctx, partial))) return rc;
   const int R = c->nranks;
-  uint32_t* counts = c->shared + static_cast<size_t>(R) * c->list_cap;
-  const int n = static_cast<int>(partial->num_blocks);
-  ctx->own_launches += 1 + R;
-  CG_CUDA(cudaMemsetAsync(counts, 0, R * sizeof(uint32_t), s));
-  if (n > 0)
-    k_owner_lists<<<grid_for(n, 256), 256, 0, s>>>(partial->v, n, static_cast<uint32_t>(R),
-                                                   static_cast<uint32_t>(c->list_cap), c->shared,
-                                                   counts);
-  // every rank's partial layer and lists are complete (stream-ordered, no host wait)
-  if ((rc = barrier(ctx))) return rc;
+  const uint32_t hmask_cap = static_cast<uint32_t>(c->hcap - 1);
+  const uint32_t list_cap = static_cast<uint32_t>(std::min<size_t>(c->list_cap, 0xFFFFFFF0u));
+  ctx->own_launches += 6;
+  k_publish_blocks<<<1, 1, 0, s>>>(c->shared, static_cast<int>(partial->num_blocks));
+  CG_CUDA(cudaMemsetAsync(c->hkeys, 0xFF, c->hcap * sizeof(unsigned long long), s));
+  CG_CUDA(cudaMemsetAsync(c->hmask, 0, c->hcap * sizeof(unsigned long long), s));
+  CG_CUDA(cudaMemsetAsync(c->counters, 0, 4 * sizeof(uint32_t), s));
   CG_CUDA(cudaMemsetAsync(&ctx->d_counters->blocks_out, 0, sizeof(unsigned long long), s));
-  for (int src = 0; src < R; ++src)  // ascending source rank: the fold order is fixed
-    k_fold_pull<<<ctx->num_sms * 8, 256, 0, s>>>(owned->v, c->d_peers, src, c->rank,
-                                                 static_cast<uint32_t>(c->list_cap),
-                                                 &ctx->d_counters->blocks_out);
+  // every rank's partial layer is complete and its block count published (stream-ordered)
+  if ((rc = barrier(ctx))) return rc;
+  const dim3 per_rank(static_cast<unsigned>(ctx->num_sms), static_cast<unsigned>(R));
+  k_build_holders<<<per_rank, 256, 0, s>>>(c->d_peers, c->hkeys, c->hmask, hmask_cap, c->counters);
+  k_list_owned<<<ctx->num_sms * 4, 256, 0, s>>>(c->hkeys, c->hmask, static_cast<uint32_t>(c->hcap),
+                                                c->rank, c->hbase, c->mine, list_cap, c->counters);
+  k_holder_slots<<<per_rank, 256, 0, s>>>(c->d_peers, c->hkeys, c->hmask, c->hbase, hmask_cap,
+                                          c->rank, c->slots, list_cap);
+  const size_t smem = 3 * kVoxelsPerBlock * sizeof(uint32_t);
+  static bool attr_set[64] = {};
+  if (ctx->device < 0 || ctx->device >= 64 || !attr_set[ctx->device]) {
+    CG_CUDA(cudaFuncSetAttribute(k_fold_owned, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+    if (ctx->device >= 0 && ctx->device < 64) attr_set[ctx->device] = true;
+  }
+  k_fold_owned<<<ctx->num_sms * 4, kFoldThreads, smem, s>>>(
+      owned->v, c->d_peers, c->hkeys, c->hmask, c->hbase, c->mine, c->slots, c->counters, list_cap,
+      &ctx->d_counters->blocks_out);
+  k_comm_overflow<<<1, 1, 0, s>>>(c->counters, owned->v.err);
   // nobody clears or refills its partial layer while a peer still reads it
   if ((rc = barrier(ctx))) return rc;
   CallCounters cc;

@@ -361,13 +361,15 @@ int32_t cg_layer_merge_packed(cg_layer* layer, const void* d_packed, size_t num_
  * (cg_comm_get_unique_id = ncclGetUniqueId) and the host hands it to every rank (MPI, a TCP store,
  * a ROS parameter ...); cg_comm_init builds the NCCL communicator on the context's GPU.
  * cg_gather_global is collective: every rank passes ITS partial global layer (all created with
- * the same voxel size and max_blocks) and the layer it owns; on return `owned` has received, in
- * ascending source-rank order, every partial block of every rank that cg_block_owner assigns to
- * this rank (2-argument mergeLayerAintoLayerB semantics, coxgraph/src/server/
- * submap_collection.cpp:31-33), read by the fold kernel straight from the peers' block pools over
- * NVLink (CUDA IPC peer mappings, opened the first time a partial layer is used); NCCL is the
- * bootstrap and the stream-ordered barrier.  The partial layer may be cleared or refilled as soon
- * as the call returns.  cg_project_submaps_sharded = cg_layer_clear(partial) +
+ * the same voxel size and max_blocks) and the layer it owns.  Every block of every partial layer
+ * ends up in exactly one rank's `owned` layer: the owner is one of the ranks that HOLD the block,
+ * picked by a hash of its index (a block only one rank holds never leaves that GPU), and it folds
+ * the holders' copies in ascending rank order (2-argument mergeLayerAintoLayerB semantics,
+ * coxgraph/src/server/submap_collection.cpp:31-33) — the union of the owned layers is bit-identical
+ * to the packed exchange above.  The fold kernel reads the peers' copies straight from their block
+ * pools over NVLink (CUDA IPC peer mappings, opened the first time a partial layer is used); NCCL
+ * is the bootstrap and the stream-ordered barrier.  The partial layer may be cleared or refilled as
+ * soon as the call returns.  cg_project_submaps_sharded = cg_layer_clear(partial) +
  * cg_project_submaps(this rank's submaps -> partial) + cg_gather_global: cblox getProjectedMap()
  * (coxgraph/src/server/visualizer/server_visualizer.cpp:123-126) over all ranks. */
 #define CG_COMM_ID_BYTES 128
