@@ -2,7 +2,9 @@
 """Turn the artefacts of scripts/profile_round.sh (gpurun_out/) into the committed summaries under
 profiles/: the launch list, the ncu --set full summary of the top kernels, and traffic.json (DRAM
 bytes per launch per pipeline stage, read by bench.py for roofline.traffic).
-Usage: make_profiles.py <tag> [<round-label>]"""
+Usage: make_profiles.py <tag> [<round-label>] [<second tag> ...]
+With several tags (one capture per robot of the C2 shape: the steps alternate between two scenes of
+different cost) traffic.json holds the mean over the captures and the per-capture values."""
 import csv
 import io
 import json
@@ -22,7 +24,7 @@ STAGE = {"k_point_keys": "point_keys", "k_gather_sorted": "gather_sorted", "k_fo
          "k_fold_bundles": "fold_bundles", "k_walk_segments": "walk_segments",
          "k_block_accumulate": "block_accumulate", "k_voxel_update": "voxel_update",
          "k_long_finish": "replay_wide", "k_finalize_blocks": "finalize",
-         "k_resample_merge": "merge_resample"}
+         "k_resample_merge": "merge_resample", "k_visit_precompute": "visits"}
 
 head = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True,
                       text=True).stdout.strip()
@@ -76,10 +78,24 @@ def summarise(rows, hdr, units, traffic):
                     pass
         top = ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)[:4])
         lines.append(f"| top stalls (warps per issue) | {top} |\n")
-        if traffic is not None and name in STAGE and STAGE[name] not in traffic:
-            traffic[STAGE[name]] = \
-                to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + \
-                to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
+        if traffic is None:
+            continue
+        dram = to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + \
+            to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
+        if name in STAGE and STAGE[name] not in traffic:
+            traffic[STAGE[name]] = dram
+        # library kernels, in launch order: the first radix sort of the step (histogram + its
+        # onesweep passes) is the bundle sort, the second the (voxel, ray) pair sort; the first
+        # select compacts the bundle heads, the second the update-list heads
+        if "DeviceRadixSortHistogramKernel" in name:
+            traffic["_sorts"] = traffic.get("_sorts", 0) + 1
+        if "DeviceRadixSort" in name:
+            key = "bundle_sort" if traffic.get("_sorts", 1) <= 1 else "pair_sort"
+            traffic[key] = traffic.get(key, 0.0) + dram
+        if "DeviceSelectSweepKernel" in name:
+            traffic["_selects"] = traffic.get("_selects", 0) + 1
+            key = "bundle_scan" if traffic["_selects"] == 1 else "segments"
+            traffic[key] = traffic.get(key, 0.0) + dram
     return lines
 
 
@@ -106,7 +122,30 @@ with open(os.path.join(out_dir, f"{label}_ncu_top_kernels.md"), "w") as f:
             "`ncu --set full --clock-control none --import-source on --nvtx --nvtx-include cg_step/ "
             "-k regex:<kernels> python bench.py --steps 2 --warmup 10 --profile-mode` — the kernels of "
             "one C2 step (25 x 640x480 frames).\n\n" + "\n".join(lines))
+traffic = {k: v for k, v in traffic.items() if not k.startswith("_")}
+per_capture = {tag: traffic}
+for extra in sys.argv[3:]:
+    rep2 = os.path.join(go, f"prof_{extra}.ncu-rep")
+    raw2 = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True,
+                          text=True).stdout
+    rows2 = list(csv.reader(io.StringIO(raw2)))
+    t2 = {}
+    extra_lines = summarise(rows2[2:], rows2[0], rows2[1], t2)
+    per_capture[extra] = {k: v for k, v in t2.items() if not k.startswith("_")}
+    with open(os.path.join(out_dir, f"{label}_ncu_top_kernels_{extra}.md"), "w") as f:
+        f.write(f"# {label}: ncu --set full, capture {extra} (commit {head})\n\n" + "\n".join(extra_lines))
+    ls2 = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "launch_summary.py"),
+                          os.path.join(go, f"launches_{extra}.csv")], capture_output=True, text=True).stdout
+    with open(os.path.join(out_dir, f"{label}_launches_{extra}.md"), "w") as f:
+        f.write(f"# {label}: launch list of one C2 step, capture {extra} (commit {head})\n\n" + ls2)
+mean = {}
+for k in sorted({k for t in per_capture.values() for k in t}):
+    vals = [t[k] for t in per_capture.values() if k in t]
+    mean[k] = sum(vals) / len(vals)
 with open(os.path.join(out_dir, "traffic.json"), "w") as f:
-    json.dump({"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch, from "
-                           f"profiles/{label}_ncu_top_kernels.md", **traffic}, f, indent=1)
+    json.dump({"_comment": "dram__bytes_read.sum + dram__bytes_write.sum of one step per pipeline "
+                           "stage (a stage = one kernel or one library call; the passes of a "
+                           f"library sort are summed), ncu --set full, profiles/{label}_ncu_top_kernels*.md; "
+                           "mean over the captures below (one per robot of the C2 shape)",
+               **mean, "_per_capture": per_capture}, f, indent=1)
 print("wrote", sorted(os.listdir(out_dir)))
