@@ -35,6 +35,10 @@ WORKLOAD = ("C2 two-client CVG shape: per step one submap = 25 x 640x480 depth f
             "(7.68 M points), 5 cm voxels, 16 cm truncation, merged integrator, voxel carving, "
             "fused into a cleared submap layer then merged into the global TSDF")
 BLOCK_BYTES = 49152
+# the `config` object of the JSON line: the same for both arms (the driver compares them)
+CONFIG = {"workload": WORKLOAD,
+          "l2": "no explicit flush: each step streams > 300 MB of fresh points, keys and update "
+                "lists (L2 is 126 MB) and a different submap than the step before"}
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -206,7 +210,9 @@ def run_reference(args, rank, world):
         "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_region / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        # the same `config` object as our arm prints (the driver compares them); what this run
+        # sampled is in cpu_baseline.sample
+        "config": dict(CONFIG),
         "integrate": {"value": pts_total / t_int, "unit": "points/s"},
         "merge": {"value": vox_total / t_merge, "unit": "voxels/s"},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port",
@@ -798,15 +804,16 @@ def run_ours(args, rank, world, local_rank):
             "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": hv["total_ms"] / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": f"submaps sharded over {world} GPU(s), no data-path collective",
-                       "l2": "each step streams >300 MB of fresh points and update lists "
-                             "(> 126 MB L2); distinct submap per step",
-                       "pool_submaps": pool_n,
-                       "pipelining": "value / e2e: the layer-independent first half of step k+1 "
-                                     "(points -> rays) runs on a second stream beside the second "
-                                     "half and the merge of step k; plain_calls / e2e_plain_calls: "
-                                     "one cg_integrate_batch call after the other"
-                       if "pipelined" in results else "none"},
+            "config": dict(CONFIG),
+            "run": {"parallelism": f"submaps sharded over {world} GPU(s), no data-path collective",
+                    "l2": "each step streams >300 MB of fresh points and update lists "
+                          "(> 126 MB L2); distinct submap per step",
+                    "pool_submaps": pool_n,
+                    "pipelining": "value / e2e: the layer-independent first half of step k+1 "
+                                  "(points -> rays) runs on a second stream beside the second "
+                                  "half and the merge of step k; plain_calls / e2e_plain_calls: "
+                                  "one cg_integrate_batch call after the other"
+                    if "pipelined" in results else "none"},
             "plain_calls": {"value": dv["points"] / (dv["total_ms"] * 1e-3), "unit": "points/s",
                             "ms_per_step": dv["total_ms"] / args.steps},
             "project_submaps": project,

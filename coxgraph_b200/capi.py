@@ -49,7 +49,8 @@ class IntegratorConfig(C.Structure):
 
 class IntegrateStats(C.Structure):
     _fields_ = [("points_in", C.c_uint64), ("rays", C.c_uint64), ("voxel_updates", C.c_uint64),
-                ("general_updates", C.c_uint64), ("blocks_touched", C.c_uint64), ("blocks_allocated", C.c_uint64)]
+                ("general_updates", C.c_uint64), ("blocks_touched", C.c_uint64), ("blocks_allocated", C.c_uint64),
+                ("points_beyond_reach", C.c_uint64)]
 
 
 class Mesh(C.Structure):

@@ -173,6 +173,8 @@ struct CallCounters {
   int key_lo[3], key_hi[3];  // extent of the job's points (voxel indices relative to the sensor voxel)
   unsigned long long candidates;
   unsigned long long blocks_out;
+  unsigned long long far_points;   // points beyond the key reach, counted by the running front half
+  unsigned long long far_dropped;  // ... of the front half the host has just synchronised on
   int err;
   int num_blocks;
 };

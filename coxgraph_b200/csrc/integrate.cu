@@ -105,6 +105,12 @@ struct KeyLayout {
   }
 };
 constexpr int kMaxRelBits = 13;
+// |rel| <= 8191 voxels: what a single frame's key can hold (14 bits per axis; the anti-grazing set
+// packs the same).  A point further from the sensor than that — 410 m at 5 cm voxels, 164 m at
+// 2 cm: a stray return; it can only be a clearing point — is dropped and counted
+// (cg_integrate_stats.points_beyond_reach) instead of failing the frame; the reference would carve
+// along its first max_ray_length metres.
+constexpr int kKeySlack = 16, kKeyLimit = 8191;
 
 __device__ __forceinline__ int order_index(int k, int n, int mode) {
   // voxblox MixedThreadSafeIndex: groups of 1024 visited round-robin
@@ -148,7 +154,8 @@ struct FrameTable {
 // rank k (the scattered 8-byte writes of a wave merge in L2).
 __global__ void k_point_keys(IntegratorParams P, KeyLayout kl, const float* __restrict__ poses,
                              FrameTable ft, const float* __restrict__ pts, uint64_t total,
-                             uint64_t* __restrict__ keys, int32_t* err, int* key_bounds) {
+                             uint64_t* __restrict__ keys, int32_t* err, int* key_bounds,
+                             CallCounters* counters) {
   // key_bounds != nullptr: also measure the extent of the job's points (see below)
   __shared__ int s_bounds[6];
   if (key_bounds && threadIdx.x < 6) s_bounds[threadIdx.x] = threadIdx.x < 3 ? 0x3FFFFFFF : -0x3FFFFFFF;
@@ -174,10 +181,13 @@ __global__ void k_point_keys(IntegratorParams P, KeyLayout kl, const float* __re
         rx = grid_index(pg.x, P.voxel_size_inv) - grid_index(T.t.x, P.voxel_size_inv);
         ry = grid_index(pg.y, P.voxel_size_inv) - grid_index(T.t.y, P.voxel_size_inv);
         rz = grid_index(pg.z, P.voxel_size_inv) - grid_index(T.t.z, P.voxel_size_inv);
-        have = true;
+        const bool far = max(max(abs(rx), abs(ry)), abs(rz)) > kKeyLimit;
+        have = !far;
         const uint32_t ux = static_cast<uint32_t>(rx - kl.lo[0]), uy = static_cast<uint32_t>(ry - kl.lo[1]),
                        uz = static_cast<uint32_t>(rz - kl.lo[2]);
-        if ((ux >> kl.bits[0]) == 0 && (uy >> kl.bits[1]) == 0 && (uz >> kl.bits[2]) == 0) {
+        if (far) {
+          atomicAdd(&counters->far_points, 1ull);  // beyond any key box: dropped, counted
+        } else if ((ux >> kl.bits[0]) == 0 && (uy >> kl.bits[1]) == 0 && (uz >> kl.bits[2]) == 0) {
           key = (static_cast<uint64_t>(f) << kl.frame_shift()) |
                 (static_cast<uint64_t>(clearing) << kl.clear_bit()) |
                 (static_cast<uint64_t>(uz) << kl.shift(2)) | (static_cast<uint64_t>(uy) << kl.shift(1)) |
@@ -633,6 +643,8 @@ k_scan_totals(const uint32_t* __restrict__ num_rays, unsigned long long* __restr
       key_bounds[3 + a] = -0x3FFFFFFF;
     }
     c->rays = *num_rays;
+    c->far_dropped = c->far_points;  // counted by k_point_keys; reset for the next front half
+    c->far_points = 0;
     c->pairs = total & 0xFFFFFFFFull;  // voxel visits (the host splits jobs that reach 2^32)
     c->segments = total >> 32;         // (ray, block) segments
     c->touched = 0;
@@ -1953,8 +1965,6 @@ static int32_t run_back_half(cg_context* ctx, const FrontBufs& fb, cg_layer* L,
   return CG_OK;
 }
 
-constexpr int kKeySlack = 16, kKeyLimit = 8191;  // |rel| <= 8191: the anti-grazing set packs 14 bits
-
 // Front half of frames [f0, f1) of a job (points -> one ray per bundle, R1 / R2 / R6), queued on
 // stream `s` into the set `fb`: nothing here touches the layer.  The counters the back half needs
 // (rays, voxel visits, segments, key extent, errors) are copied to fb.h_counters at the end; the
@@ -2044,7 +2054,8 @@ static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int
       StageScope sc(ctx, kStagePointKeys, 1, s);
       k_point_keys<<<grid_for(total, 256), 256, 0, s>>>(P, kl, fb.group_poses, ft, pts, total,
                                                         fb.key_a.as<uint64_t>(), d_err,
-                                                        measure ? fb.d_key_bounds : nullptr);
+                                                        measure ? fb.d_key_bounds : nullptr,
+                                                        fb.d_counters);
     }
     {
       StageScope sc(ctx, kStageBundleSort, 0, s);
@@ -2245,6 +2256,7 @@ static int32_t integrate_group(cg_layer* L, const cg_integrator_config* cfg,
   }
   const uint32_t num_rays = static_cast<uint32_t>(ctx->h_counters->rays);
   const size_t num_pairs = ctx->h_counters->pairs;
+  if (stats) stats->points_beyond_reach += ctx->h_counters->far_dropped;
   if (num_rays == 0 || num_pairs == 0) return CG_OK;
   if (stats) {
     stats->rays += num_rays;
@@ -2468,6 +2480,7 @@ int32_t cg_integrate_prepared(cg_layer* L, int32_t slot, cg_integrate_stats* sta
       if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->points_in = pj.offs[F];
+        stats->points_beyond_reach = fb.h_counters->far_dropped;
       }
       const uint32_t num_rays = static_cast<uint32_t>(fb.h_counters->rays);
       const size_t num_pairs = fb.h_counters->pairs;

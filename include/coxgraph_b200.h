@@ -88,6 +88,9 @@ typedef struct cg_integrate_stats {
   uint64_t general_updates; /* visits replayed in order (voxels inside the truncation band) */
   uint64_t blocks_touched;  /* distinct blocks visited by any ray of the call */
   uint64_t blocks_allocated;/* new blocks */
+  uint64_t points_beyond_reach; /* valid points more than 8191 voxels from the sensor (MERGED):
+                                   dropped — the reference would integrate them as clearing rays
+                                   cut at max_ray_length_m */
 } cg_integrate_stats;
 
 typedef struct cg_merge_stats {

@@ -71,8 +71,10 @@ def test_batch_pipelined_transfer(gpu_ctx, monkeypatch):
 def test_far_points_regroup_then_out_of_range(gpu_ctx):
     """The bundle keys cover the box of voxels (relative to the sensor) that earlier jobs measured;
     a point outside it makes the library redo the group with the measured extent instead of
-    failing, and only a point more than 8191 voxels from the sensor is an error."""
-    from coxgraph_b200 import Layer, TsdfIntegrator, capi
+    failing.  A stray return more than 8191 voxels from the sensor (410 m at 5 cm) is dropped and
+    counted — the frame is integrated without it — where round 1 failed the whole frame."""
+    from coxgraph_b200 import Layer, TsdfIntegrator
+    from oracle import oracle_py as orc
     frames = util.small_frames(5, stride=8)
     T, p, c = frames[2]
     p = p.copy()
@@ -81,13 +83,19 @@ def test_far_points_regroup_then_out_of_range(gpu_ctx):
     got, ref, gl = _run_both(gpu_ctx, frames, batch=True)
     util.compare_layers(got, ref, "far clearing point in a batch")
     gl.close()
-    _, gcfg = util.make_cfgs()
+    ocfg, gcfg = util.make_cfgs()
     gl = Layer(gpu_ctx, 0.05, max_blocks=2048)
     p2 = p.copy()
-    p2[7] = (0.0, 0.0, 1000.0)         # 20000 voxels: some axis is beyond 8191 whatever the pose
-    with pytest.raises(capi.CgError) as e:
-        TsdfIntegrator(gcfg, gl).integratePointCloud(T, p2, c)
-    assert e.value.status == capi.CG_ERR_OUT_OF_RANGE
+    # 20000 voxels: some axis is beyond 8191 whatever the pose.  The last point of the cloud: it
+    # lies in the tail the "mixed" order visits in natural order, so removing it leaves the
+    # visiting order of all the others as it is
+    assert len(p2) % 1024 != 0 and (len(p2) - 1) // 1024 == len(p2) // 1024
+    p2[-1] = (0.0, 0.0, 1000.0)
+    st = TsdfIntegrator(gcfg, gl).integratePointCloud(T, p2, c)
+    assert st.points_beyond_reach == 1 and st.points_in == len(p2)
+    ol = orc.Layer(0.05)
+    ol.integrate(ocfg, T, p2[:-1], c[:-1])   # the oracle without the dropped point
+    util.compare_layers(gl.download(), ol.download(), "frame with one point beyond the key reach")
     gl.close()
 
 
