@@ -338,7 +338,10 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.Stream(device=dev)
+    # the context's stream at high priority: with pipelined calls its kernels (the second half of
+    # the current job, the merge) are scheduled ahead of the next job's first half on the
+    # library's second stream, which has default priority
+    stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("CG_BENCH_STREAM_PRIORITY", "-1")))
     torch.cuda.set_stream(stream)
     ctx = Context(local_rank, stream=stream.cuda_stream)
     gcfg = TsdfIntegratorConfig(**CFG)

@@ -100,7 +100,7 @@ class MergeStats(C.Structure):
 class ReprojectStats(C.Structure):
     _fields_ = [("submaps_moved", C.c_uint64), ("blocks_dirty", C.c_uint64),
                 ("candidates", C.c_uint64), ("blocks_folded", C.c_uint64),
-                ("blocks_removed", C.c_uint64)]
+                ("blocks_removed", C.c_uint64), ("full_rebuild", C.c_uint64)]
 
 
 # every symbol include/coxgraph_b200.h declares: name -> (restype, argtypes)

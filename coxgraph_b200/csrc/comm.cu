@@ -206,12 +206,13 @@ k_fold_owned(LayerView B, const PeerLayer* __restrict__ peers,
              const unsigned long long* __restrict__ hkeys,
              const unsigned long long* __restrict__ hmask, const uint32_t* __restrict__ hbase,
              const uint32_t* __restrict__ mine, const uint32_t* __restrict__ slots,
-             const uint32_t* __restrict__ counters, uint32_t list_cap, unsigned long long* folded) {
+             const uint32_t* __restrict__ counters, uint32_t list_cap, int blocks_before,
+             unsigned long long* folded) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint4* t_d = reinterpret_cast<uint4*>(smem_raw);  // three planes of 4096 words
   uint4* t_w = t_d + kVoxelsPerBlock / 4;
   uint4* t_c = t_w + kVoxelsPerBlock / 4;
-  __shared__ int s_slot;
+  __shared__ int s_slot, s_fresh;
   const uint32_t n = min(counters[0], list_cap);
   for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
     const uint32_t e = mine[i];
@@ -230,7 +231,11 @@ k_fold_owned(LayerView B, const PeerLayer* __restrict__ peers,
     if (threadIdx.x == 0) {
       const int he = B.insert_entry(key);
       s_slot = B.hash_vals[he];
+      s_fresh = 0;
       if (s_slot >= 0) {
+        // a slot claimed during this call holds a default-constructed block (the pool keeps
+        // unclaimed slots in that state): nothing to read
+        s_fresh = s_slot >= blocks_before;
         B.has_data[s_slot] = 1;
         B.updated[s_slot] = 1;
         atomicAdd(folded, static_cast<unsigned long long>(__popcll(mask)));
@@ -242,10 +247,18 @@ k_fold_owned(LayerView B, const PeerLayer* __restrict__ peers,
     uint4* dd = reinterpret_cast<uint4*>(B.dist_plane(slot));
     uint4* dw = reinterpret_cast<uint4*>(B.weight_plane(slot));
     uint4* dc = reinterpret_cast<uint4*>(B.color_plane(slot));
-    for (int q = threadIdx.x; q < kVoxelsPerBlock / 4; q += kFoldThreads) {
-      t_d[q] = dd[q];
-      t_w[q] = dw[q];
-      t_c[q] = dc[q];
+    if (s_fresh) {
+      for (int q = threadIdx.x; q < kVoxelsPerBlock / 4; q += kFoldThreads) {
+        t_d[q] = make_uint4(0u, 0u, 0u, 0u);
+        t_w[q] = make_uint4(0u, 0u, 0u, 0u);
+        t_c[q] = make_uint4(kDefaultColor, kDefaultColor, kDefaultColor, kDefaultColor);
+      }
+    } else {
+      for (int q = threadIdx.x; q < kVoxelsPerBlock / 4; q += kFoldThreads) {
+        t_d[q] = dd[q];
+        t_w[q] = dw[q];
+        t_c[q] = dc[q];
+      }
     }
     for (int j = 0; mask; ++j, mask &= mask - 1) {  // ascending rank: the fold order is fixed
       const PeerLayer P = peers[__ffsll(static_cast<long long>(mask)) - 1];
@@ -519,7 +532,7 @@ int32_t cg_gather_global(const cg_layer* partial, cg_layer* owned, uint64_t* blo
   }
   k_fold_owned<<<ctx->num_sms * 4, kFoldThreads, smem, s>>>(
       owned->v, c->d_peers, c->hkeys, c->hmask, c->hbase, c->mine, c->slots, c->counters, list_cap,
-      &ctx->d_counters->blocks_out);
+      static_cast<int>(owned->num_blocks), &ctx->d_counters->blocks_out);
   k_comm_overflow<<<1, 1, 0, s>>>(c->counters, owned->v.err);
   // nobody clears or refills its partial layer while a peer still reads it
   if ((rc = barrier(ctx))) return rc;

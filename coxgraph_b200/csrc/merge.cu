@@ -904,6 +904,13 @@ int32_t cg_project_submaps(const cg_layer* const* submaps, const float* poses, s
   return rc;
 }
 
+// dirty blocks / blocks of the map above which cg_reproject_submaps rebuilds the whole map
+// (CG_REPROJECT_FULL_FRACTION overrides it; the tests use 2 to force the block-by-block path)
+static double full_rebuild_fraction() {
+  const char* e = getenv("CG_REPROJECT_FULL_FRACTION");
+  return (e && *e) ? atof(e) : 0.3;
+}
+
 int32_t cg_reproject_submaps(const cg_layer* const* submaps, const float* poses_old,
                              const float* poses_new, size_t n, float eps_translation,
                              float eps_rotation, cg_layer* G, uint8_t* changed_out,
@@ -988,6 +995,38 @@ int32_t cg_reproject_submaps(const cg_layer* const* submaps, const float* poses_
           ctx->stage_a.as<uint64_t>(), nullptr, static_cast<uint32_t>(cap - 1), G->v.err, nullptr, 0);
       k_dirty_slots<<<grid_for(cap, 256), 256, 0, s>>>(G->v, ctx->stage_a.as<uint64_t>(),
                                                        static_cast<uint32_t>(cap), slots, counts);
+    }
+    // When the moved submaps dirty a large part of the map (a corridor map where every block is
+    // shared by a few submaps: a tenth of the poses dirties more than half of the blocks),
+    // rebuilding the dirty blocks from ALL submaps that reach them plus the block removal costs
+    // more than the full rebuild, which gives the same layer by definition: take that instead.
+    {
+      uint32_t h_dirty[2] = {0, 0};
+      CG_CUDA(cudaMemcpyAsync(h_dirty, counts, sizeof(h_dirty), cudaMemcpyDeviceToHost, s));
+      CG_CUDA(cudaStreamSynchronize(s));
+      if (static_cast<double>(h_dirty[0]) > full_rebuild_fraction() * static_cast<double>(g_blocks)) {
+        std::vector<float> eff(7 * n);
+        size_t mi = 0;
+        for (size_t i = 0; i < n; ++i) {
+          const bool ch = mi < moved.size() && moved[mi] == i;
+          if (ch) ++mi;
+          memcpy(&eff[7 * i], (ch ? poses_new : poses_old) + 7 * i, 7 * sizeof(float));
+        }
+        int32_t rc = cg_layer_clear(G);
+        if (rc) return rc;
+        cg_merge_stats ms;
+        rc = cg_project_submaps(submaps, eff.data(), n, G, &ms);
+        if (stats) {
+          stats->blocks_dirty = h_dirty[1];
+          stats->candidates = ms.blocks_candidate;
+          stats->blocks_folded = ms.blocks_out;
+          stats->full_rebuild = 1;
+        }
+        return rc;
+      }
+    }
+    {
+      StageScope sc(ctx, kStageMergeMark, 1);
       k_reset_blocks<<<ctx->num_sms * 8, 256, 0, s>>>(G->v, slots, counts);
     }
     // every submap that reaches a dirty block is folded into it again, in submap order

@@ -339,6 +339,8 @@ typedef struct cg_reproject_stats {
   uint64_t candidates;      /* (dirty block, submap) pairs resampled */
   uint64_t blocks_folded;   /* pairs that carried data */
   uint64_t blocks_removed;  /* dirty blocks left without data: removed from the layer */
+  uint64_t full_rebuild;    /* 1: more than 30 % of the map was dirty, the whole map was rebuilt
+                               (same result, cheaper than rebuilding block by block) */
 } cg_reproject_stats;
 int32_t cg_reproject_submaps(const cg_layer* const* submaps, const float* poses_old,
                              const float* poses_new, size_t num_submaps, float eps_translation,
