@@ -38,9 +38,16 @@ with open(os.path.join(out_dir, f"{label}_launches.md"), "w") as f:
             "Per-launch times under ncu are cold-cache and serialised: compare the SHARES with "
             "`stages_ms_per_step` of the bench line, not the absolutes.\n\n" + ls)
 
-rep = os.path.join(go, f"prof_{tag}.ncu-rep")
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
-                     text=True).stdout
+def raw_page(name):
+    """--page raw --csv of a capture: the exported CSV if the report itself did not travel."""
+    csv_path = os.path.join(go, f"prof_{name}.raw.csv")
+    if os.path.exists(csv_path):
+        return open(csv_path).read()
+    return subprocess.run(["ncu", "-i", os.path.join(go, f"prof_{name}.ncu-rep"), "--page", "raw",
+                           "--csv"], capture_output=True, text=True).stdout
+
+
+raw = raw_page(tag)
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
@@ -62,8 +69,9 @@ def summarise(rows, hdr, units, traffic):
     lines = []
     for r in rows:
         name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").strip()
-        lines.append(f"## {name}\n")
-        name = name.split("<")[0]
+        short = name.split("<")[0]  # template arguments of the library kernels run to a page
+        lines.append(f"## {short if short.startswith('cub::') else name}\n")
+        name = short.replace("cg::", "")
         lines.append("| metric | value |\n|---|---|")
         for w in want:
             if w in ix:
@@ -125,10 +133,7 @@ with open(os.path.join(out_dir, f"{label}_ncu_top_kernels.md"), "w") as f:
 traffic = {k: v for k, v in traffic.items() if not k.startswith("_")}
 per_capture = {tag: traffic}
 for extra in sys.argv[3:]:
-    rep2 = os.path.join(go, f"prof_{extra}.ncu-rep")
-    raw2 = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True,
-                          text=True).stdout
-    rows2 = list(csv.reader(io.StringIO(raw2)))
+    rows2 = list(csv.reader(io.StringIO(raw_page(extra))))
     t2 = {}
     extra_lines = summarise(rows2[2:], rows2[0], rows2[1], t2)
     per_capture[extra] = {k: v for k, v in t2.items() if not k.startswith("_")}
