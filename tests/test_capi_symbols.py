@@ -31,8 +31,26 @@ def test_struct_layouts_match_the_header():
     from oracle import oracle_py as orc
     assert C.sizeof(capi.IntegratorConfig) == 15 * 4
     assert [f[0] for f in capi.IntegratorConfig._fields_] == [f[0] for f in orc.IntegratorConfig._fields_]
-    assert C.sizeof(capi.IntegrateStats) == 48 and C.sizeof(capi.MergeStats) == 24
+    assert C.sizeof(capi.IntegrateStats) == 56 and C.sizeof(capi.MergeStats) == 24
+    assert C.sizeof(capi.ReprojectStats) == 48 and C.sizeof(capi.HashStats) == 48
     assert C.sizeof(capi.StageProfile) == 48
+    # the structs as the C compiler lays them out (the header is plain C)
+    import subprocess
+    import sys
+    import tempfile
+    src = ('#include <stdio.h>\n#include "coxgraph_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+           'sizeof(cg_integrator_config),sizeof(cg_integrate_stats),sizeof(cg_merge_stats),'
+           'sizeof(cg_reproject_stats),sizeof(cg_hash_stats),sizeof(cg_stage_profile));return 0;}')
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "s.c"), "w") as f:
+            f.write(src)
+        subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"),
+                               os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
+        sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "s")]).split()]
+    assert sizes == [C.sizeof(t) for t in (capi.IntegratorConfig, capi.IntegrateStats,
+                                           capi.MergeStats, capi.ReprojectStats, capi.HashStats,
+                                           capi.StageProfile)], sizes
+    del sys
     assert capi.PACKED_BLOCK_BYTES == 16 + 4096 * 12
 
 
