@@ -92,6 +92,14 @@ class Context {
   cg_context* handle() const { return ctx_; }
   void synchronize() const { check(cg_context_synchronize(ctx_)); }
   uint64_t kernelLaunches() const { return cg_context_kernel_launches(ctx_); }
+  // queue the host->device copy of a LATER job's clouds into staging slot 0 / 1 and return at
+  // once; the vectors must stay alive and unchanged until that job has been integrated
+  void stageBatchAsync(int stage_slot, const Pointcloud& points_C, const Colors& colors) const {
+    if (points_C.size() != colors.size())
+      fatal_handler()(CG_ERR_INVALID_ARG, "stageBatchAsync: points_C.size() != colors.size()");
+    check(cg_stage_batch_async(ctx_, stage_slot, points_C.empty() ? nullptr : &points_C[0].x,
+                               colors.empty() ? nullptr : &colors[0].r, points_C.size()));
+  }
 
  private:
   cg_context* ctx_ = nullptr;
@@ -171,6 +179,21 @@ class TsdfLayer {
     check(cg_layer_deserialize(layer_, indices.size(), indices.empty() ? nullptr : &indices[0].x,
                                data.data()));
   }
+  // Layer::getBlockPtrByIndex for the listed blocks only: found[i] tells whether block i is
+  // allocated (for layers too large to copy out whole)
+  void downloadBlocks(const BlockIndexList& indices, std::vector<TsdfVoxel>* voxels,
+                      std::vector<uint8_t>* found, std::vector<uint8_t>* flags = nullptr) const {
+    voxels->resize(indices.size() * CG_VOXELS_PER_BLOCK);
+    found->resize(indices.size());
+    if (flags) flags->resize(indices.size());
+    check(cg_layer_download_blocks(layer_, indices.size(), indices.empty() ? nullptr : &indices[0].x,
+                                   voxels->data(), flags ? flags->data() : nullptr, found->data()));
+  }
+  cg_hash_stats hashStats() const {
+    cg_hash_stats st;
+    check(cg_layer_hash_stats(layer_, &st));
+    return st;
+  }
   // insert / overwrite blocks (deserializeMsgToLayer hand-off,
   // coxgraph/include/coxgraph/utils/msg_converter.h:107-109)
   void upload(const BlockIndexList& indices, const std::vector<TsdfVoxel>& voxels,
@@ -230,6 +253,35 @@ class TsdfIntegratorBase {
                              pts.empty() ? nullptr : &pts[0].x, cols.empty() ? nullptr : &cols[0].r,
                              offs.data(), freespace_points ? 1 : 0, &stats_));
   }
+  // Pipelined jobs for a host that knows its next job (the recover loop does: tsdf_recover.h:
+  // 71-86): prepareDevice queues the layer-independent first half of a LATER job — points already
+  // on the device, or staged with cg_stage_batch_async — into slot 0 / 1 and returns at once;
+  // integratePrepared completes it.  Same result as integratePointClouds.
+  void prepareDevice(int slot, const std::vector<Transformation>& T_G_C, const float* d_points_xyz,
+                     const uint8_t* d_colors_rgba, const std::vector<uint64_t>& frame_offsets,
+                     const bool freespace_points = false) {
+    if (frame_offsets.size() != T_G_C.size() + 1)
+      fatal_handler()(CG_ERR_INVALID_ARG, "prepareDevice: F + 1 frame offsets expected");
+    std::vector<float> poses(7 * T_G_C.size());
+    for (size_t f = 0; f < T_G_C.size(); ++f)
+      std::copy(T_G_C[f].data(), T_G_C[f].data() + 7, poses.begin() + 7 * f);
+    check(cg_prepare_batch_device(layer_->handle(), &config_, T_G_C.size(), poses.data(),
+                                  d_points_xyz, d_colors_rgba, frame_offsets.data(),
+                                  freespace_points ? 1 : 0, slot));
+  }
+  // the same for clouds staged with Context::stageBatchAsync(stage_slot, ...)
+  void prepareStaged(int slot, const std::vector<Transformation>& T_G_C, int stage_slot,
+                     const std::vector<uint64_t>& frame_offsets,
+                     const bool freespace_points = false) {
+    if (frame_offsets.size() != T_G_C.size() + 1)
+      fatal_handler()(CG_ERR_INVALID_ARG, "prepareStaged: F + 1 frame offsets expected");
+    std::vector<float> poses(7 * T_G_C.size());
+    for (size_t f = 0; f < T_G_C.size(); ++f)
+      std::copy(T_G_C[f].data(), T_G_C[f].data() + 7, poses.begin() + 7 * f);
+    check(cg_prepare_batch_staged(layer_->handle(), &config_, T_G_C.size(), poses.data(),
+                                  stage_slot, frame_offsets.data(), freespace_points ? 1 : 0, slot));
+  }
+  void integratePrepared(int slot) { check(cg_integrate_prepared(layer_->handle(), slot, &stats_)); }
   void setLayer(TsdfLayer* layer) { layer_ = layer; }
   const Config& getConfig() const { return config_; }
   const cg_integrate_stats& lastStats() const { return stats_; }
@@ -305,6 +357,34 @@ inline void getProjectedMap(const std::vector<const TsdfLayer*>& submap_layers,
   }
   check(cg_project_submaps(handles.data(), poses.data(), handles.size(), projected_layer->handle(),
                            stats));
+}
+
+// ---- the same over the GPUs of one box, one process per GPU: every rank passes ITS submaps, a
+// scratch partial layer and the layer it owns (all ranks: same voxel size and max_blocks for the
+// partial layers).  commInit once per context with the 128-byte id rank 0 made (commUniqueId)
+// and the host handed round.
+inline std::vector<uint8_t> commUniqueId() {
+  std::vector<uint8_t> id(CG_COMM_ID_BYTES);
+  check(cg_comm_get_unique_id(id.data()));
+  return id;
+}
+inline void commInit(const Context& ctx, const std::vector<uint8_t>& id, int rank, int nranks) {
+  if (id.size() != CG_COMM_ID_BYTES) fatal_handler()(CG_ERR_INVALID_ARG, "commInit: 128-byte id expected");
+  check(cg_comm_init(ctx.handle(), id.data(), rank, nranks));
+}
+inline void getProjectedMapSharded(const std::vector<const TsdfLayer*>& my_submap_layers,
+                                   const std::vector<Transformation>& T_M_S, TsdfLayer* partial_layer,
+                                   TsdfLayer* owned_layer, cg_merge_stats* stats = nullptr) {
+  if (my_submap_layers.size() != T_M_S.size())
+    fatal_handler()(CG_ERR_INVALID_ARG, "getProjectedMapSharded: one pose per submap expected");
+  std::vector<const cg_layer*> handles(my_submap_layers.size());
+  std::vector<float> poses(7 * T_M_S.size());
+  for (size_t i = 0; i < my_submap_layers.size(); ++i) {
+    handles[i] = my_submap_layers[i]->handle();
+    std::copy(T_M_S[i].data(), T_M_S[i].data() + 7, poses.begin() + 7 * i);
+  }
+  check(cg_project_submaps_sharded(handles.data(), poses.data(), handles.size(),
+                                   partial_layer->handle(), owned_layer->handle(), stats));
 }
 
 // ---- voxblox::MeshIntegrator<TsdfVoxel>::generateMesh over a device-resident layer (what

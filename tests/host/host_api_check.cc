@@ -10,6 +10,7 @@
 // in.bin : u32 F, f32 voxel_size, f32 trunc, f32 T_M_S[7], then per frame: f32 T[7], u32 n,
 //          n * 3 f32 points, n * 4 u8 colours
 // out.bin: per layer (submap, global): u32 B, B * 3 i32, B * 4096 * 12 B voxels
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -131,6 +132,53 @@ int main(int argc, char** argv) {
   const std::vector<uint8_t> moved =
       cg::reprojectSubmaps({&submap}, {T_M_S}, {T_M_S}, &combined);
   if (moved[0] != 0 || combined.getNumberOfAllocatedBlocks() != before) return 71;
+  // listed-block download and the hash statistics: every allocated block found, an absent one not
+  {
+    cg::BlockIndexList all, ask;
+    std::vector<cg::TsdfVoxel> vox, got;
+    std::vector<uint8_t> found;
+    combined.download(&all, &vox);
+    ask.assign(all.begin(), all.begin() + std::min<size_t>(all.size(), 5));
+    cg::BlockIndex absent;
+    absent.x = 30000, absent.y = -30000, absent.z = 7;
+    ask.push_back(absent);
+    combined.downloadBlocks(ask, &got, &found);
+    for (size_t i = 0; i + 1 < ask.size(); ++i)
+      if (!found[i] || std::memcmp(&got[i * CG_VOXELS_PER_BLOCK], &vox[i * CG_VOXELS_PER_BLOCK],
+                                   CG_VOXELS_PER_BLOCK * sizeof(cg::TsdfVoxel)) != 0)
+        return 72;
+    if (found.back()) return 73;
+    const cg_hash_stats hs = combined.hashStats();
+    if (hs.num_blocks != all.size()) return 74;
+  }
+  // the same frames as ONE pipelined job (staged copy, prepared first half) into a second
+  // submap: same block count as the per-frame calls
+  {
+    FILE* again = fopen(argv[2], "rb");
+    if (!again) return 75;
+    uint32_t F2 = 0;
+    float skip[9];
+    if (!rd(again, &F2) || !rd(again, skip, 9)) return 76;
+    std::vector<cg::Transformation> poses(F2);
+    std::vector<uint64_t> offs(F2 + 1, 0);
+    cg::Pointcloud pts;
+    cg::Colors cols;
+    for (uint32_t f = 0; f < F2; ++f) {
+      uint32_t n = 0;
+      if (!rd(again, &poses[f].qw, 7) || !rd(again, &n)) return 77;
+      pts.resize(offs[f] + n);
+      cols.resize(offs[f] + n);
+      if (n && (!rd(again, pts.data() + offs[f], n) || !rd(again, cols.data() + offs[f], n))) return 78;
+      offs[f + 1] = offs[f] + n;
+    }
+    fclose(again);
+    cg::TsdfLayer submap2(ctx, voxel_size, 16, 2048);
+    auto integ2 = cg::TsdfIntegratorFactory::create("fast", config, &submap2);
+    ctx.stageBatchAsync(0, pts, cols);
+    integ2->prepareStaged(0, poses, 0, offs);
+    integ2->integratePrepared(0);
+    if (submap2.getNumberOfAllocatedBlocks() != submap.getNumberOfAllocatedBlocks()) return 79;
+  }
   std::printf("mesh: %zu triangles over %zu blocks\n", mesh.vertices.size() / 3,
               mesh.block_indices.size());
   std::printf("ok: submap %zu blocks, combined %zu blocks, %llu kernel launches\n",
