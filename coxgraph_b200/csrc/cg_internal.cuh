@@ -225,6 +225,7 @@ struct FrontBufs {
   DevBuf poses, frame_base;
   DevBuf key_a, key_b, scan, cub_tmp;
   DevBuf rays, ray_count, ray_offset, sorted_pts;
+  DevBuf ray_id, frame_count;               // bundle -> ray id; (frame, chunk) bundle counts
   DevBuf scan_partials;
   DevBuf grazing_keys, grazing_ray_key;     // anti-grazing: the scan's bundle voxels
   uint32_t grazing_mask = 0;

@@ -71,30 +71,37 @@ struct Ray {           // 24 B
 };
 constexpr uint32_t kNoRay = 0xFFFFFFFFu;
 
-// Bundle key (u64): [frame | clearing(1) | z | y | x | visit rank (rank_bits)].
+// Bundle key (u64): [clearing(1) | z | y | x | frame (frame_bits) | visit rank (rank_bits)].
 // z, y, x: voxel index of the point relative to the voxel holding the sensor origin, minus the
 // lower corner `lo` of the box the layout covers, bits[a] wide; visit rank: position of the point in
-// the reference's visiting order of its frame.  The keys are sorted on the bits above the rank
-// only (keys-only radix sort, begin_bit = rank_bits): a stable sort keeps equal bundles in
-// visiting order, and the point index is recovered from (frame, rank), so no value array travels
-// through the sort.  The box is chosen per group by the host (make_key_layout) from the extent
+// the reference's visiting order of its frame.  The keys are written in (frame, rank) order and
+// sorted on the (clearing, voxel) bits only (keys-only radix sort, begin_bit = rank_bits +
+// frame_bits): a stable sort keeps the points of one (clearing, voxel) in (frame, rank) order, so a
+// bundle — one frame's points in one voxel — is a contiguous run in visiting order, the point
+// index is recovered from (frame, rank) and no value array travels through the sort; leaving the
+// frame field out of the sorted bits saves a radix pass at the C2 shape (24 bits instead of 29).
+// The position of a bundle in the canonical (frame, clearing, voxel) order the back half replays
+// in — its ray id — is then a stable partition of the bundles by frame (k_bundle_histogram /
+// k_frame_scan / k_bundle_order).  The box is chosen per group by the host from the extent
 // earlier jobs on the context measured — a room-sized scene needs 9 + 8 + 6 bits where a cube
-// around the sensor wide enough for clearing points needs 3 x 10, one radix pass less; a point
-// outside the box is detected on the device and the group is redone with the measured extent.
+// around the sensor wide enough for clearing points needs 3 x 10; a point outside the box is
+// detected on the device and the group is redone with the measured extent.
 struct KeyLayout {
   int rank_bits;
+  int frame_bits;
   int bits[3];  // x, y, z
   int lo[3];
+  __host__ __device__ __forceinline__ int frame_shift() const { return rank_bits; }
+  __host__ __device__ __forceinline__ int voxel_shift() const { return rank_bits + frame_bits; }
   __host__ __device__ __forceinline__ int shift(int a) const {
-    return rank_bits + (a > 0 ? bits[0] : 0) + (a > 1 ? bits[1] : 0);
+    return voxel_shift() + (a > 0 ? bits[0] : 0) + (a > 1 ? bits[1] : 0);
   }
   __host__ __device__ __forceinline__ int clear_bit() const {
-    return rank_bits + bits[0] + bits[1] + bits[2];
+    return voxel_shift() + bits[0] + bits[1] + bits[2];
   }
-  __host__ __device__ __forceinline__ int frame_shift() const { return clear_bit() + 1; }
   __device__ __forceinline__ bool clearing(uint64_t key) const { return (key >> clear_bit()) & 1; }
   __device__ __forceinline__ uint32_t frame(uint64_t key) const {
-    return static_cast<uint32_t>(key >> frame_shift());
+    return static_cast<uint32_t>(key >> frame_shift()) & ((1u << frame_bits) - 1u);
   }
   __device__ __forceinline__ uint32_t rank(uint64_t key) const {
     return static_cast<uint32_t>(key & ((1ull << rank_bits) - 1ull));
@@ -111,6 +118,7 @@ constexpr int kMaxRelBits = 13;
 // (cg_integrate_stats.points_beyond_reach) instead of failing the frame; the reference would carve
 // along its first max_ray_length metres.
 constexpr int kKeySlack = 16, kKeyLimit = 8191;
+constexpr size_t kMaxGroupFrames = 8192;  // frames per group: per-frame bins in shared memory
 
 __device__ __forceinline__ int order_index(int k, int n, int mode) {
   // voxblox MixedThreadSafeIndex: groups of 1024 visited round-robin
@@ -187,7 +195,9 @@ __global__ void k_point_keys(IntegratorParams P, KeyLayout kl, const float* __re
                        uz = static_cast<uint32_t>(rz - kl.lo[2]);
         if (far) {
           atomicAdd(&counters->far_points, 1ull);  // beyond any key box: dropped, counted
-        } else if ((ux >> kl.bits[0]) == 0 && (uy >> kl.bits[1]) == 0 && (uz >> kl.bits[2]) == 0) {
+        } else if ((ux >> kl.bits[0]) == 0 && (uy >> kl.bits[1]) == 0 && ((uz + 1u) >> kl.bits[2]) == 0) {
+          // (uz + 1: the z field is never all ones, so that the key of a dropped point — all ones —
+          // sorts behind every real key on the sorted bits alone)
           key = (static_cast<uint64_t>(f) << kl.frame_shift()) |
                 (static_cast<uint64_t>(clearing) << kl.clear_bit()) |
                 (static_cast<uint64_t>(uz) << kl.shift(2)) | (static_cast<uint64_t>(uy) << kl.shift(1)) |
@@ -287,34 +297,79 @@ __device__ __forceinline__ uint32_t fold_length(const KeyLayout& kl, const Bundl
   return kl.clearing(bi.key) ? 1u : bi.n;
 }
 
+// Ray ids.  Bundle b (position in the sorted keys: (clearing, voxel)-major, frames interleaved)
+// becomes ray  frame_start[f] + #{b' < b of the same frame f}: within a frame the bundles already
+// are in (clearing, voxel) order, so this stable partition by frame IS the canonical (frame,
+// clearing, voxel) order.  Every CTA owns a contiguous chunk of bundles; frame_count[f * G + cta]
+// holds its bundles of frame f (bin F: the sentinel bundle of dropped points, which so gets the
+// last id), an exclusive scan over that array in (f, cta) order gives each (frame, chunk) its
+// first id, and k_bundle_order ranks the bundles of a chunk in ascending b.
+__device__ __forceinline__ void bundle_chunk(uint32_t nb, uint32_t& lo, uint32_t& hi) {
+  const uint32_t per = (nb + gridDim.x - 1) / gridDim.x;
+  lo = min(nb, blockIdx.x * per);
+  hi = min(nb, lo + per);
+}
+
 // class_count[0 .. kSizeClasses): histogram; [kSizeClasses .. 2 kSizeClasses): scatter cursors
 __global__ void k_bundle_histogram(KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
                                    const uint32_t* __restrict__ heads,
                                    const uint32_t* __restrict__ num_heads, uint32_t* class_count,
-                                   Ray* __restrict__ folded) {
+                                   uint32_t* __restrict__ frame_count, int F) {
+  extern __shared__ uint32_t s_frames[];  // F + 1 bins
   __shared__ uint32_t hist[kSizeClasses];
   if (threadIdx.x < kSizeClasses) hist[threadIdx.x] = 0;
+  for (int f = threadIdx.x; f <= F; f += blockDim.x) s_frames[f] = 0;
   __syncthreads();
   const uint32_t nb = *num_heads;
-  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+  uint32_t lo, hi;
+  bundle_chunk(nb, lo, hi);
+  for (uint32_t b = lo + threadIdx.x; b < hi; b += blockDim.x) {
     const BundleInfo bi = bundle_info(keys, total, heads, nb, b);
-    if (bi.key == kInvalidPointKey)
-      folded[b].frame_clr = kNoRay;  // sentinel bundle of dropped points
-    else
+    if (bi.key == kInvalidPointKey) {
+      atomicAdd(&s_frames[F], 1u);
+    } else {
+      atomicAdd(&s_frames[kl.frame(bi.key)], 1u);
       atomicAdd(&hist[size_class(fold_length(kl, bi))], 1u);
+    }
   }
   __syncthreads();
   if (threadIdx.x < kSizeClasses && hist[threadIdx.x])
     atomicAdd(&class_count[threadIdx.x], hist[threadIdx.x]);
+  for (int f = threadIdx.x; f <= F; f += blockDim.x)
+    frame_count[static_cast<size_t>(f) * gridDim.x + blockIdx.x] = s_frames[f];
 }
 
-__global__ void k_bundle_order(KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
-                               const uint32_t* __restrict__ heads,
-                               const uint32_t* __restrict__ num_heads, uint32_t* class_count,
-                               uint32_t* __restrict__ order) {
+// exclusive scan of the (frame, chunk) counts, in place; one CTA
+__global__ void __launch_bounds__(1024) k_frame_scan(uint32_t* __restrict__ counts, uint32_t n) {
+  typedef cub::BlockScan<uint32_t, 1024> Scan;
+  __shared__ typename Scan::TempStorage tmp;
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t i0 = 0; i0 < n; i0 += 1024) {
+    const uint32_t i = i0 + threadIdx.x;
+    const uint32_t v = i < n ? counts[i] : 0u;
+    uint32_t ex, sum;
+    Scan(tmp).ExclusiveSum(v, ex, sum);
+    if (i < n) counts[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += sum;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bundle_order(KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
+               const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
+               uint32_t* class_count, const uint32_t* __restrict__ frame_base, int F,
+               uint32_t* __restrict__ order, uint32_t* __restrict__ ray_id,
+               Ray* __restrict__ folded) {
+  extern __shared__ uint32_t s_next[];  // F + 1: next ray id of each frame within this chunk
   __shared__ uint32_t base[kSizeClasses];
   __shared__ uint32_t hist[kSizeClasses];
   __shared__ uint32_t offs[kSizeClasses];
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     uint32_t acc = 0;
     for (int c = 0; c < kSizeClasses; ++c) {
@@ -322,26 +377,50 @@ __global__ void k_bundle_order(KeyLayout kl, const uint64_t* __restrict__ keys, 
       acc += class_count[c];
     }
   }
+  for (int f = threadIdx.x; f <= F; f += blockDim.x)
+    s_next[f] = frame_base[static_cast<size_t>(f) * gridDim.x + blockIdx.x];
   const uint32_t nb = *num_heads;
-  for (uint32_t b0 = blockIdx.x * blockDim.x; b0 < nb; b0 += gridDim.x * blockDim.x) {
+  uint32_t lo, hi;
+  bundle_chunk(nb, lo, hi);
+  for (uint32_t b0 = lo; b0 < hi; b0 += blockDim.x) {
     __syncthreads();
     if (threadIdx.x < kSizeClasses) hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t b = b0 + threadIdx.x;
     int c = -1;
     uint32_t rank = 0;
-    if (b < nb) {
+    uint32_t f = static_cast<uint32_t>(F) + 1u;  // no bundle in this lane
+    if (b < hi) {
       const BundleInfo bi = bundle_info(keys, total, heads, nb, b);
       if (bi.key != kInvalidPointKey) {
         c = size_class(fold_length(kl, bi));
         rank = atomicAdd(&hist[c], 1u);
+        f = kl.frame(bi.key);
+      } else {
+        f = static_cast<uint32_t>(F);
       }
     }
-    __syncthreads();
+    // ray id: lanes of the same frame in lane order, warps in turn
+    const unsigned same = __match_any_sync(full, f);
+    const int leader = __ffs(same) - 1;
+    const uint32_t before = __popc(same & ((1u << lane) - 1u));
+    uint32_t first = 0;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) {
+      if (wib == w && lane == leader && f <= static_cast<uint32_t>(F)) {
+        first = s_next[f];
+        s_next[f] = first + __popc(same);
+      }
+      __syncthreads();
+    }
+    first = __shfl_sync(full, first, leader);
     if (threadIdx.x < kSizeClasses && hist[threadIdx.x])
       offs[threadIdx.x] = atomicAdd(&class_count[kSizeClasses + threadIdx.x], hist[threadIdx.x]);
     __syncthreads();
     if (c >= 0) order[base[c] + offs[c] + rank] = b;
+    if (b < hi) {
+      ray_id[b] = first + before;
+      if (c < 0) folded[first + before].frame_clr = kNoRay;  // sentinel bundle of dropped points
+    }
   }
 }
 
@@ -367,7 +446,8 @@ __global__ void __launch_bounds__(kWideWarps * 32)
 k_fold_wide(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
             const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
             const float4* __restrict__ sorted, const uint32_t* __restrict__ class_count,
-            const uint32_t* __restrict__ order, Ray* __restrict__ folded) {
+            const uint32_t* __restrict__ order, const uint32_t* __restrict__ ray_id,
+            Ray* __restrict__ folded) {
   // per point of the chunk: W_{k-1}, W_k, 1/W_k, a = W_{k-1}/W_k, and the 7 chain operands
   __shared__ float s_wprev[kWideWarps][32], s_w[kWideWarps][32], s_r[kWideWarps][32],
       s_a[kWideWarps][32], s_op[kWideWarps][8][32];
@@ -459,7 +539,7 @@ k_fold_wide(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ keys,
       ray.color = pack_rgba(static_cast<uint32_t>(cr), static_cast<uint32_t>(cg),
                             static_cast<uint32_t>(cb), static_cast<uint32_t>(ca));
       ray.frame_clr = kl.frame(key);
-      folded[b] = ray;
+      folded[ray_id[b]] = ray;
     }
   }
 }
@@ -470,7 +550,8 @@ __global__ void __launch_bounds__(128)
 k_fold_bundles(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
                const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
                const float4* __restrict__ sorted, const uint32_t* __restrict__ class_count,
-               const uint32_t* __restrict__ order, Ray* __restrict__ folded) {
+               const uint32_t* __restrict__ order, const uint32_t* __restrict__ ray_id,
+               Ray* __restrict__ folded) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const uint32_t nb = *num_heads;
@@ -527,7 +608,7 @@ k_fold_bundles(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ ke
       r.weight = st.W;
       r.color = fold_color(st);
       r.frame_clr = frame_clr;
-      folded[b] = r;
+      folded[ray_id[b]] = r;
     }
   }
 }
@@ -830,6 +911,7 @@ __device__ __forceinline__ bool grazing_contains(const GrazingSet& G, unsigned l
 __global__ void k_grazing_build(KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
                                 const uint32_t* __restrict__ heads,
                                 const uint32_t* __restrict__ num_heads,
+                                const uint32_t* __restrict__ ray_id,
                                 unsigned long long* set_keys, uint32_t set_mask,
                                 unsigned long long* __restrict__ ray_key) {
   const uint32_t nb = *num_heads;
@@ -838,7 +920,7 @@ __global__ void k_grazing_build(KeyLayout kl, const uint64_t* __restrict__ keys,
     if (bi.key == kInvalidPointKey) continue;
     const int rx = kl.rel(bi.key, 0), ry = kl.rel(bi.key, 1), rz = kl.rel(bi.key, 2);
     const unsigned long long gk = grazing_key(kl.frame(bi.key), rx, ry, rz);
-    ray_key[b] = gk;
+    ray_key[ray_id[b]] = gk;
     if (kl.clearing(bi.key)) continue;  // only non-clearing bundles are in the set
     uint32_t h = hash_key(gk) & set_mask;
     for (;;) {
@@ -1996,6 +2078,11 @@ static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int
   for (size_t f = f0; f < f1; ++f) max_frame_points = std::max<size_t>(max_frame_points, offs[f + 1] - offs[f]);
   KeyLayout kl;
   kl.rank_bits = std::max(1, ceil_log2(max_frame_points));
+  kl.frame_bits = frame_bits;
+  if (merged && F > kMaxGroupFrames) {  // per-frame bins of the ray-id partition (shared memory)
+    *need_split = true;
+    return CG_OK;
+  }
   // voxel fields: the box earlier jobs on this context measured (kept as a running union, with
   // some slack around it), or — first job — a cube around the sensor sized for the sensor range
   // with x4 head room for clearing points beyond max_ray.  Fewer bits = fewer radix passes.  A
@@ -2027,7 +2114,8 @@ static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int
     set_error("a single frame of %zu points is too large; split the point cloud", total);
     return CG_ERR_INVALID_ARG;
   }
-  const int bundle_end_bit = kl.frame_shift() + frame_bits;
+  // sorted bits: (clearing, voxel); the frame and rank fields below stay in input order
+  const int bundle_begin_bit = kl.voxel_shift(), bundle_end_bit = kl.clear_bit() + 1;
   cub::DoubleBuffer<uint64_t> dk(fb.key_a.as<uint64_t>(), fb.key_b.as<uint64_t>());
   thrust::counting_iterator<uint32_t> iota(0);
   uint32_t* d_num = fb.d_select_count;
@@ -2040,8 +2128,8 @@ static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int
   ValidSlot valid{P, ft, pts};
   size_t tmp_sort = 0, tmp_sel = 0;
   if (merged) {
-    cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, dk, static_cast<int>(total), kl.rank_bits,
-                                   bundle_end_bit, s);
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, dk, static_cast<int>(total),
+                                   bundle_begin_bit, bundle_end_bit, s);
     cub::DeviceSelect::If(nullptr, tmp_sel, iota, fb.scan.as<uint32_t>(), d_num,
                           static_cast<int>(total), BundleHead{nullptr, 0}, s);
   } else {
@@ -2060,7 +2148,7 @@ static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int
     {
       StageScope sc(ctx, kStageBundleSort, 0, s);
       CG_CUDA(cub::DeviceRadixSort::SortKeys(fb.cub_tmp.p, tmp_sort, dk, static_cast<int>(total),
-                                             kl.rank_bits, bundle_end_bit, s));
+                                             bundle_begin_bit, bundle_end_bit, s));
     }
     {
       StageScope sc(ctx, kStageBundleScan, 0, s);
@@ -2069,6 +2157,11 @@ static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int
     }
     // upper bound on the number of bundles: one per point + the sentinel
     const unsigned bgrid = std::min<unsigned>(grid_for(upper, 256), ctx->num_sms * 8u);
+    // chunks of the ray-id partition (contiguous bundles per CTA)
+    const unsigned cgrid = std::min<unsigned>(grid_for(upper, 256), ctx->num_sms * 2u);
+    const size_t frame_smem = (F + 1) * sizeof(uint32_t);
+    CG_CUDA(fb.frame_count.reserve((F + 1) * cgrid * sizeof(uint32_t)));
+    CG_CUDA(fb.ray_id.reserve(upper * sizeof(uint32_t)));
     {
       StageScope sc(ctx, kStageGather, 1, s);
       k_gather_sorted<<<grid_for(total, 256), 256, 0, s>>>(
@@ -2076,28 +2169,31 @@ static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int
           fb.sorted_pts.as<float4>());
     }
     {
-      StageScope sc(ctx, kStageBundleOrder, 3, s);
+      StageScope sc(ctx, kStageBundleOrder, 4, s);
       CG_CUDA(fill_bytes(fb.d_class_count, 0, 2 * kSizeClasses * sizeof(uint32_t), s));
-      k_bundle_histogram<<<bgrid, 256, 0, s>>>(kl, dk.Current(), static_cast<uint32_t>(total),
-                                               fb.scan.as<uint32_t>(), d_num, fb.d_class_count,
-                                               fb.rays.as<Ray>());
-      k_bundle_order<<<bgrid, 256, 0, s>>>(kl, dk.Current(), static_cast<uint32_t>(total),
-                                           fb.scan.as<uint32_t>(), d_num, fb.d_class_count,
-                                           fb.ray_offset.as<uint32_t>());
+      k_bundle_histogram<<<cgrid, 256, frame_smem, s>>>(
+          kl, dk.Current(), static_cast<uint32_t>(total), fb.scan.as<uint32_t>(), d_num,
+          fb.d_class_count, fb.frame_count.as<uint32_t>(), static_cast<int>(F));
+      k_frame_scan<<<1, 1024, 0, s>>>(fb.frame_count.as<uint32_t>(),
+                                      static_cast<uint32_t>((F + 1) * cgrid));
+      k_bundle_order<<<cgrid, 256, frame_smem, s>>>(
+          kl, dk.Current(), static_cast<uint32_t>(total), fb.scan.as<uint32_t>(), d_num,
+          fb.d_class_count, fb.frame_count.as<uint32_t>(), static_cast<int>(F),
+          fb.ray_offset.as<uint32_t>(), fb.ray_id.as<uint32_t>(), fb.rays.as<Ray>());
     }
     {
       StageScope sc(ctx, kStageFoldWide, 1, s);
       k_fold_wide<<<ctx->num_sms * 12, kWideWarps * 32, 0, s>>>(
           P, kl, dk.Current(), static_cast<uint32_t>(total), fb.scan.as<uint32_t>(), d_num,
           fb.sorted_pts.as<float4>(), fb.d_class_count, fb.ray_offset.as<uint32_t>(),
-          fb.rays.as<Ray>());
+          fb.ray_id.as<uint32_t>(), fb.rays.as<Ray>());
     }
     {
       StageScope sc(ctx, kStageFold, 1, s);
       k_fold_bundles<<<ctx->num_sms * 12, 128, 0, s>>>(
           P, kl, dk.Current(), static_cast<uint32_t>(total), fb.scan.as<uint32_t>(), d_num,
           fb.sorted_pts.as<float4>(), fb.d_class_count, fb.ray_offset.as<uint32_t>(),
-          fb.rays.as<Ray>());
+          fb.ray_id.as<uint32_t>(), fb.rays.as<Ray>());
     }
     {
       StageScope sc(ctx, kStageBundleRays, 1, s);
@@ -2112,7 +2208,7 @@ static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int
       fb.grazing_mask = static_cast<uint32_t>(gcap - 1);
       CG_CUDA(fill_bytes(fb.grazing_keys.p, 0xFF, gcap * sizeof(unsigned long long), s));
       k_grazing_build<<<bgrid, 256, 0, s>>>(kl, dk.Current(), static_cast<uint32_t>(total),
-                                            fb.scan.as<uint32_t>(), d_num,
+                                            fb.scan.as<uint32_t>(), d_num, fb.ray_id.as<uint32_t>(),
                                             fb.grazing_keys.as<unsigned long long>(),
                                             fb.grazing_mask,
                                             fb.grazing_ray_key.as<unsigned long long>());

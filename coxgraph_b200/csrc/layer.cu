@@ -403,7 +403,8 @@ cudaError_t init_front_words(FrontBufs& fb) {
 }
 void release_front(FrontBufs& fb) {
   DevBuf* bufs[] = {&fb.poses, &fb.frame_base, &fb.key_a, &fb.key_b, &fb.scan, &fb.cub_tmp, &fb.rays,
-                    &fb.ray_count, &fb.ray_offset, &fb.sorted_pts, &fb.scan_partials,
+                    &fb.ray_count, &fb.ray_offset, &fb.sorted_pts, &fb.scan_partials, &fb.ray_id,
+                    &fb.frame_count,
                     &fb.grazing_keys, &fb.grazing_ray_key};
   for (DevBuf* b : bufs) b->release();
   if (fb.h_counters) cudaFreeHost(fb.h_counters);
