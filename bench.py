@@ -668,6 +668,37 @@ def run_ours(args, rank, world, local_rank):
             two_jobs = {"value": pts2 / dt, "unit": "points/s", "jobs_in_flight": 2,
                         "ms_per_submap": dt * 1e3 / (2 * args.steps),
                         "timing": "wall clock around both threads, device synchronised on both sides"}
+            # the same with each lane issuing the pipelined calls of `value` (the two clients of the
+            # C2 shape, one context each)
+            def run_lane_pipelined(lane, steps):
+                c2, sub2, glob2, ents = lane
+                integ2 = TsdfIntegrator(gcfg, sub2)
+                e = ents[0]
+                integ2.prepareBatch(0, e["poses"], e["d_pts"], e["d_cols"], e["offs"])
+                for k in range(steps):
+                    e = ents[k % len(ents)]
+                    if k + 1 < steps:
+                        n = ents[(k + 1) % len(ents)]
+                        integ2.prepareBatch((k + 1) % 2, n["poses"], n["d_pts"], n["d_cols"], n["offs"])
+                    sub2.clear()
+                    integ2.integratePrepared(k % 2)
+                    mergeLayerAintoLayerB(sub2, e["T_M_S"], glob2)
+                c2.synchronize()
+
+            for lane in lanes:
+                run_lane_pipelined(lane, 3)
+            torch.cuda.synchronize()
+            threads = [threading.Thread(target=run_lane_pipelined, args=(lane, args.steps))
+                       for lane in lanes]
+            t0 = time.perf_counter()
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            two_jobs["pipelined"] = {"value": pts2 / dt, "unit": "points/s",
+                                     "ms_per_submap": dt * 1e3 / (2 * args.steps)}
             # the same with host buffers: every lane stages its next submap (pinned memory,
             # double buffered), fuses, merges and reads the fused submap back, like the e2e leg
             def run_lane_e2e(lane, steps, bufs):

@@ -436,30 +436,39 @@ __device__ __forceinline__ uint32_t wide_count(const uint32_t* __restrict__ clas
 // Long bundles: 8 lanes per bundle, 4 bundles per warp.  The recurrence itself stays sequential,
 // but everything that does not depend on the running mean is taken off its critical path: per
 // chunk of 8 points the lanes compute, in parallel, the point weights, then (one short
-// sequential pass) the running weight W_k, then the per-point reciprocal and blend factors and
-// the products p_k w_k, c_k b_k; what remains per point is the 7-operation chain
+// sequential pass over the chunk's weights, read back from shared memory) the running weight W_k,
+// then the per-point reciprocal and blend factors and the products p_k w_k, c_k b_k; what remains
+// per point is the 7-operation chain
 //   m <- (m W_{k-1} + p_k w_k) / W_k          (div_with_rcp: exact IEEE quotient)
-// and the colour blend, run as 7 independent chains (x, y, z, r, g, b, a) on 7 of the 8 lanes.
+// and the colour blend, run as 7 independent chains (x, y, z, r, g, b, a) on 7 of the 8 lanes; a
+// chain step reads its point's four factors with one 16-byte load and its operand with another.
+// The warps take groups of 4 bundles from a queue over the longest-first order: the kernel lasts
+// as long as its longest bundle (it is bound by that chain, not by instruction issue: 4 lanes per
+// bundle and 8 bundles per warp issue a third fewer instructions and take 0.126 ms against 0.100),
+// and few resident warps per scheduler keep the chains fed.
 constexpr int kWideWarps = 4;
 constexpr int kWideGroup = 8;  // lanes per bundle = points per chunk
-__global__ void __launch_bounds__(kWideWarps * 32)
-k_fold_wide(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
-            const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
-            const float4* __restrict__ sorted, const uint32_t* __restrict__ class_count,
-            const uint32_t* __restrict__ order, const uint32_t* __restrict__ ray_id,
-            Ray* __restrict__ folded) {
-  // per point of the chunk: W_{k-1}, W_k, 1/W_k, a = W_{k-1}/W_k, and the 7 chain operands
-  __shared__ float s_wprev[kWideWarps][32], s_w[kWideWarps][32], s_r[kWideWarps][32],
-      s_a[kWideWarps][32], s_op[kWideWarps][8][32];
+constexpr int kWideOpStride = 72;  // words per bundle in s_op: 8 points x 8 chains + 8 (banks)
+__device__ __forceinline__ void
+fold_wide(const IntegratorParams& P, const KeyLayout& kl, const uint64_t* __restrict__ keys,
+          uint32_t total, const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
+          const float4* __restrict__ sorted, const uint32_t* __restrict__ class_count,
+          const uint32_t* __restrict__ order, const uint32_t* __restrict__ ray_id, uint32_t* queue,
+          Ray* __restrict__ folded) {
+  __shared__ __align__(16) float s_wt[kWideWarps][32];    // the chunk's point weights
+  __shared__ float4 s_fac[kWideWarps][32];                // per point: W_{k-1}, W_k, 1/W_k, W_{k-1}/W_k
+  __shared__ __align__(16) float s_op[kWideWarps][4 * kWideOpStride];  // [bundle][point][chain]
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int sub = lane >> 3, l8 = lane & 7, gbase = lane & ~7;
   const uint32_t nb = *num_heads;
   const uint32_t n_wide = wide_count(class_count, lane);
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
   const int chain = l8;  // 0..2 mean, 3..6 colour, 7 idle
-  for (uint32_t g = warp * 4u; g < n_wide; g += num_warps * 4u) {
+  for (;;) {
+    uint32_t g = 0;
+    if (lane == 0) g = atomicAdd(queue, 4u);
+    g = __shfl_sync(full, g, 0);
+    if (g >= n_wide) break;
     const bool have = g + sub < n_wide;
     uint32_t b = 0, start = 0, end = 0;
     uint64_t key = 0;
@@ -480,48 +489,46 @@ k_fold_wide(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ keys,
       const bool valid = static_cast<uint32_t>(l8) < cnt;
       const float w = valid ? voxel_weight(P, p.z) : 0.0f;
       const bool skip = !valid || w < kEps;  // reference: "if (w < kEps) continue"
-      const float w_eff = skip ? 0.0f : w;
-      // running weight: the reference's sequential float sum
+      s_wt[wib][lane] = skip ? 0.0f : w;
+      const unsigned skip_bits = (__ballot_sync(full, skip) >> gbase) & 0xFFu;
+      __syncwarp();
+      // running weight: the reference's sequential float sum, every lane over its bundle's chunk
+      const float4 wa = *reinterpret_cast<const float4*>(&s_wt[wib][gbase]);
+      const float4 wb = *reinterpret_cast<const float4*>(&s_wt[wib][gbase + 4]);
+      const float wt[kWideGroup] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
       float w_prev_mine = 0.0f, w_mine = 0.0f;
 #pragma unroll
       for (int t = 0; t < kWideGroup; ++t) {
-        const float wt = __shfl_sync(full, w_eff, gbase + t);
-        const float Wn = W + wt;
+        const float Wn = W + wt[t];
         if (l8 == t) {
           w_prev_mine = W;
           w_mine = Wn;
         }
         W = Wn;
       }
-      // per-point factors, all lanes in parallel (same operations as fold_step)
+      // per-point factors, all lanes in parallel (same values as fold_step: r = RN(1 / W_k) makes
+      // div_with_rcp the exact quotient)
       const float r = 1.0f / w_mine;
-      const float a = w_prev_mine / w_mine;
-      const float bb = w / w_mine;
+      const float a = div_with_rcp(w_prev_mine, w_mine, r);
+      const float bb = div_with_rcp(w, w_mine, r);
       const uint32_t col = __float_as_uint(p.w);
-      __syncwarp();
-      s_wprev[wib][lane] = w_prev_mine;
-      s_w[wib][lane] = w_mine;
-      s_r[wib][lane] = r;
-      s_a[wib][lane] = a;
-      s_op[wib][0][lane] = p.x * w;
-      s_op[wib][1][lane] = p.y * w;
-      s_op[wib][2][lane] = p.z * w;
-      s_op[wib][3][lane] = static_cast<float>(col & 255u) * bb;
-      s_op[wib][4][lane] = static_cast<float>((col >> 8) & 255u) * bb;
-      s_op[wib][5][lane] = static_cast<float>((col >> 16) & 255u) * bb;
-      s_op[wib][6][lane] = static_cast<float>(col >> 24) * bb;
-      s_op[wib][7][lane] = 0.0f;
-      const unsigned skip_bits = (__ballot_sync(full, skip) >> gbase) & 0xFFu;
+      s_fac[wib][lane] = make_float4(w_prev_mine, w_mine, r, a);
+      float* ops = &s_op[wib][sub * kWideOpStride + l8 * 8];
+      *reinterpret_cast<float4*>(ops) =
+          make_float4(p.x * w, p.y * w, p.z * w, static_cast<float>(col & 255u) * bb);
+      *reinterpret_cast<float4*>(ops + 4) =
+          make_float4(static_cast<float>((col >> 8) & 255u) * bb,
+                      static_cast<float>((col >> 16) & 255u) * bb,
+                      static_cast<float>(col >> 24) * bb, 0.0f);
       __syncwarp();
       // the sequential chains of the 4 bundles side by side
-      const float* op = s_op[wib][chain] + gbase;
+      const float* op = &s_op[wib][sub * kWideOpStride + chain];
 #pragma unroll
       for (int t = 0; t < kWideGroup; ++t) {
-        const float wp = s_wprev[wib][gbase + t], wn = s_w[wib][gbase + t];
-        const float rr = s_r[wib][gbase + t], aa = s_a[wib][gbase + t];
-        const float o = op[t];
-        const float mean = div_with_rcp(val * wp + o, wn, rr);
-        const float colr = round_half_away_pos(val * aa + o);
+        const float4 fc = s_fac[wib][gbase + t];
+        const float o = op[t * 8];
+        const float mean = div_with_rcp(val * fc.x + o, fc.y, fc.z);
+        const float colr = round_half_away_pos(val * fc.w + o);
         const float nv = chain < 3 ? mean : colr;
         if (!((skip_bits >> t) & 1u)) val = nv;
       }
@@ -546,12 +553,15 @@ k_fold_wide(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ keys,
 
 constexpr int kFoldDepth = 4;  // points in flight per lane
 
-__global__ void __launch_bounds__(128)
-k_fold_bundles(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
-               const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
-               const float4* __restrict__ sorted, const uint32_t* __restrict__ class_count,
-               const uint32_t* __restrict__ order, const uint32_t* __restrict__ ray_id,
-               Ray* __restrict__ folded) {
+// Shorter bundles: one lane each, the 32 lanes of a warp on 32 consecutive bundles of the
+// longest-first order (nearly equal lengths), kFoldDepth points in flight per lane.  `cta` of
+// `num_ctas`: the CTAs of k_fold that run this part.
+__device__ __forceinline__ void
+fold_short(const IntegratorParams& P, const KeyLayout& kl, const uint64_t* __restrict__ keys,
+           uint32_t total, const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
+           const float4* __restrict__ sorted, const uint32_t* __restrict__ class_count,
+           const uint32_t* __restrict__ order, const uint32_t* __restrict__ ray_id,
+           Ray* __restrict__ folded, uint32_t cta, uint32_t num_ctas) {
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const uint32_t nb = *num_heads;
@@ -561,8 +571,8 @@ k_fold_bundles(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ ke
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) n_order += __shfl_xor_sync(full, n_order, d);
   const uint32_t n_wide = wide_count(class_count, lane);
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t warp = (cta * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t num_warps = (num_ctas * blockDim.x) >> 5;
   for (uint32_t g = warp; n_wide + g * 32u < n_order; g += num_warps) {
     const uint32_t i = n_wide + g * 32u + lane;
     uint32_t b = 0, cur = 0, n = 0, frame_clr = 0;
@@ -611,6 +621,23 @@ k_fold_bundles(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ ke
       folded[ray_id[b]] = r;
     }
   }
+}
+
+// Both folds in one launch: the first `wide_ctas` CTAs run the long bundles (bound by the longest
+// chain, few warps busy towards the end), the others the short ones, which fill the machine
+// meanwhile.
+static_assert(kWideWarps * 32 == 128, "k_fold: one CTA shape for both parts");
+__global__ void __launch_bounds__(128)
+k_fold(IntegratorParams P, KeyLayout kl, const uint64_t* __restrict__ keys, uint32_t total,
+       const uint32_t* __restrict__ heads, const uint32_t* __restrict__ num_heads,
+       const float4* __restrict__ sorted, const uint32_t* __restrict__ class_count,
+       const uint32_t* __restrict__ order, const uint32_t* __restrict__ ray_id, uint32_t* queue,
+       Ray* __restrict__ folded, uint32_t wide_ctas) {
+  if (blockIdx.x < wide_ctas)
+    fold_wide(P, kl, keys, total, heads, num_heads, sorted, class_count, order, ray_id, queue, folded);
+  else
+    fold_short(P, kl, keys, total, heads, num_heads, sorted, class_count, order, ray_id, folded,
+               blockIdx.x - wide_ctas, gridDim.x - wide_ctas);
 }
 
 // one thread per bundle: T_G_C * merged point, ray set-up, pair count
@@ -2170,7 +2197,7 @@ static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int
     }
     {
       StageScope sc(ctx, kStageBundleOrder, 4, s);
-      CG_CUDA(fill_bytes(fb.d_class_count, 0, 2 * kSizeClasses * sizeof(uint32_t), s));
+      CG_CUDA(fill_bytes(fb.d_class_count, 0, 128 * sizeof(uint32_t), s));  // + the fold queue
       k_bundle_histogram<<<cgrid, 256, frame_smem, s>>>(
           kl, dk.Current(), static_cast<uint32_t>(total), fb.scan.as<uint32_t>(), d_num,
           fb.d_class_count, fb.frame_count.as<uint32_t>(), static_cast<int>(F));
@@ -2182,18 +2209,17 @@ static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int
           fb.ray_offset.as<uint32_t>(), fb.ray_id.as<uint32_t>(), fb.rays.as<Ray>());
     }
     {
+      // 4 CTAs per SM for the long bundles: measured 0.126 / 0.100 / 0.104 / 0.106 ms for
+      // 2 / 4 / 8 / 12 with the long bundles alone
       StageScope sc(ctx, kStageFoldWide, 1, s);
-      k_fold_wide<<<ctx->num_sms * 12, kWideWarps * 32, 0, s>>>(
+      static const unsigned wide_per_sm = static_cast<unsigned>(env_size("CG_FOLD_WIDE_CTAS", 4));
+      static const unsigned short_per_sm = static_cast<unsigned>(env_size("CG_FOLD_SHORT_CTAS", 4));
+      const unsigned wide_ctas = ctx->num_sms * wide_per_sm;
+      k_fold<<<wide_ctas + ctx->num_sms * short_per_sm, 128, 0, s>>>(
           P, kl, dk.Current(), static_cast<uint32_t>(total), fb.scan.as<uint32_t>(), d_num,
           fb.sorted_pts.as<float4>(), fb.d_class_count, fb.ray_offset.as<uint32_t>(),
-          fb.ray_id.as<uint32_t>(), fb.rays.as<Ray>());
-    }
-    {
-      StageScope sc(ctx, kStageFold, 1, s);
-      k_fold_bundles<<<ctx->num_sms * 12, 128, 0, s>>>(
-          P, kl, dk.Current(), static_cast<uint32_t>(total), fb.scan.as<uint32_t>(), d_num,
-          fb.sorted_pts.as<float4>(), fb.d_class_count, fb.ray_offset.as<uint32_t>(),
-          fb.ray_id.as<uint32_t>(), fb.rays.as<Ray>());
+          fb.ray_id.as<uint32_t>(), fb.d_class_count + 2 * kSizeClasses, fb.rays.as<Ray>(),
+          wide_ctas);
     }
     {
       StageScope sc(ctx, kStageBundleRays, 1, s);
