@@ -233,7 +233,13 @@ struct FrontBufs {
   int* d_key_bounds = nullptr;              // [6] running min / max of the bundle voxel fields
   uint32_t* d_select_count = nullptr;       // output count of the stream compactions
   int32_t* d_front_err = nullptr;           // error bits of a prepared front half (sets > 0)
+  // independent stages of one job side by side (gather || bundle heads + order; short || long
+  // update lists): a second stream forked from / joined to the job's stream by events
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
+// creates fb.side at the priority of `like` on first use; false: run everything on one stream
+bool side_stream(FrontBufs& fb, cudaStream_t like);
 cudaError_t init_front_words(FrontBufs& fb);  // the small device / pinned words of a set
 void release_front(FrontBufs& fb);
 

@@ -1503,8 +1503,10 @@ __device__ __forceinline__ void replay_segment(const IntegratorParams& P,
   }
 }
 
-// Long segments (>= kLongSegment updates) are split into sub-blocks that many warps reduce in
+// Lists of kWideSegment updates or more are replayed by a warp each (k_long_finish); long
+// segments (>= kLongSegment updates) are first split into sub-blocks that many warps reduce in
 // parallel, see k_long_partials.
+constexpr uint32_t kWideSegment = 96;
 constexpr uint32_t kLongSegment = 2048;
 constexpr uint32_t kLongSub = 1024;
 struct LongSeg {
@@ -1537,9 +1539,13 @@ __global__ void k_segment_histogram(const uint32_t* __restrict__ seg_start,
   if (threadIdx.x < kSizeClasses && hist[threadIdx.x])
     atomicAdd(&class_count[threadIdx.x], hist[threadIdx.x]);
 }
+// ... and the lists of kWideSegment updates or more go to the list of the warp-cooperative
+// kernels, which so do not have to wait for k_voxel_update.
 __global__ void k_segment_order(const uint32_t* __restrict__ seg_start,
                                 const uint32_t* __restrict__ num_segs, uint32_t num_pairs,
-                                uint32_t* class_count, uint32_t* __restrict__ order) {
+                                uint32_t* class_count, uint32_t* __restrict__ order,
+                                unsigned long long* long_counter, LongSeg* __restrict__ long_list,
+                                uint32_t long_cap) {
   __shared__ uint32_t base[kSizeClasses];
   __shared__ uint32_t hist[kSizeClasses];
   __shared__ uint32_t offs[kSizeClasses];
@@ -1559,8 +1565,18 @@ __global__ void k_segment_order(const uint32_t* __restrict__ seg_start,
     int c = -1;
     uint32_t rank = 0;
     if (i < ns) {
-      c = size_class(segment_length(seg_start, ns, num_pairs, i));
+      const uint32_t len = segment_length(seg_start, ns, num_pairs, i);
+      c = size_class(len);
       rank = atomicAdd(&hist[c], 1u);
+      if (len >= kWideSegment) {
+        const uint32_t start = seg_start[i];
+        const uint32_t nsub = len >= kLongSegment ? (len + kLongSub - 1) / kLongSub : 0u;
+        // one 64-bit atomic hands out the list index (high word) and the sub-block range
+        const unsigned long long old =
+            atomicAdd(long_counter, (1ull << 32) | static_cast<unsigned long long>(nsub));
+        const uint32_t idx = static_cast<uint32_t>(old >> 32);
+        if (idx < long_cap) long_list[idx] = LongSeg{start, start + len, static_cast<uint32_t>(old), 0u};
+      }
     }
     __syncthreads();
     if (threadIdx.x < kSizeClasses && hist[threadIdx.x])
@@ -1574,14 +1590,12 @@ __global__ void k_segment_order(const uint32_t* __restrict__ seg_start,
 // reference's updateTsdfVoxel applied update by update (R5, in the reference's own operation
 // order).  Lists of kWideSegment updates or more go to a list for the warp-cooperative kernels
 // below (k_long_partials / k_long_finish).
-constexpr uint32_t kWideSegment = 96;
 constexpr int kUpdateInner = 8;
 __global__ void __launch_bounds__(128)
 k_voxel_update(IntegratorParams P, const float4* __restrict__ visits,
                const unsigned long long* __restrict__ keys, uint32_t ray_bits, uint32_t num_pairs,
                const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ num_segs,
-               const uint32_t* __restrict__ order, uint32_t* work_counter,
-               unsigned long long* long_counter, LongSeg* long_list, uint32_t long_cap, LayerView L,
+               const uint32_t* __restrict__ order, uint32_t* work_counter, LayerView L,
                TouchView Tv) {
   // A warp takes 32 consecutive lists of the size-class order (nearly equal lengths), one per
   // lane, and runs them to the end of the longest before it fetches the next 32: the chain of
@@ -1609,17 +1623,9 @@ k_voxel_update(IntegratorParams P, const float4* __restrict__ visits,
       const uint32_t sidx = order[oidx];
       const uint32_t start = seg_start[sidx];
       const uint32_t stop = (sidx + 1 < ns) ? seg_start[sidx + 1] : num_pairs;
-      vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[start] >> ray_bits));
-      if (vr.slot >= 0) {  // else: pool exhausted, error already flagged
-        if (stop - start >= kWideSegment) {
-          const uint32_t nsub =
-              stop - start >= kLongSegment ? (stop - start + kLongSub - 1) / kLongSub : 0u;
-          // one 64-bit atomic hands out the list index (high word) and the sub-block range
-          const unsigned long long old =
-              atomicAdd(long_counter, (1ull << 32) | static_cast<unsigned long long>(nsub));
-          const uint32_t idx = static_cast<uint32_t>(old >> 32);
-          if (idx < long_cap) long_list[idx] = LongSeg{start, stop, static_cast<uint32_t>(old), 0u};
-        } else {
+      if (stop - start < kWideSegment) {  // the others: k_long_partials / k_long_finish
+        vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[start] >> ray_bits));
+        if (vr.slot >= 0) {  // else: pool exhausted, error already flagged
           cur = start;
           end = stop;
 #pragma unroll
@@ -1710,6 +1716,7 @@ k_long_finish(IntegratorParams P, const float4* __restrict__ visits,
   for (uint32_t i = warp; i < nlong; i += num_warps) {
     const LongSeg seg = long_list[i];
     const VoxelRef vr = voxel_ref(P, L, Tv, static_cast<uint32_t>(keys[seg.start] >> ray_bits));
+    if (vr.slot < 0) continue;  // pool exhausted, error already flagged
     float D = *vr.dp, W = *vr.wp;
     uint32_t C = *vr.cp;
     const bool is_long = seg.end - seg.start >= kLongSegment;
@@ -2034,6 +2041,11 @@ static int32_t run_back_half(cg_context* ctx, const FrontBufs& fb, cg_layer* L,
     CG_CUDA(ctx->long_list.reserve(long_cap * sizeof(LongSeg)));
     CG_CUDA(ctx->long_partials.reserve(max_items * sizeof(LongPartial)));
     CG_CUDA(ctx->seg_order.reserve(size_t(n_general) * sizeof(uint32_t)));
+    // lists shorter than kWideSegment (one lane each) beside the longer ones (a warp each): they
+    // update different voxels
+    FrontBufs& own = *ctx;  // the context's own side stream (fb may be a prepared set)
+    const bool forked = side_stream(own, s);
+    const cudaStream_t ls = forked ? own.side : s;
     {
       StageScope sc(ctx, kStageVoxelUpdate, 3);
       CG_CUDA(fill_bytes(ctx->d_work_counter, 0, sizeof(uint32_t), s));
@@ -2043,21 +2055,30 @@ static int32_t run_back_half(cg_context* ctx, const FrontBufs& fb, cg_layer* L,
       k_segment_histogram<<<ogrid, 256, 0, s>>>(ctx->seg_start.as<uint32_t>(), d_num, n_general,
                                                 ctx->d_class_count);
       k_segment_order<<<ogrid, 256, 0, s>>>(ctx->seg_start.as<uint32_t>(), d_num, n_general,
-                                            ctx->d_class_count, ctx->seg_order.as<uint32_t>());
+                                            ctx->d_class_count, ctx->seg_order.as<uint32_t>(),
+                                            ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap);
+      if (forked) {
+        CG_CUDA(cudaEventRecord(own.ev_fork, s));
+        CG_CUDA(cudaStreamWaitEvent(own.side, own.ev_fork, 0));
+      }
       k_voxel_update<<<ctx->num_sms * 8, 128, 0, s>>>(
           P, ctx->visits.as<float4>(), dk.Current(), ray_bits, n_general,
           ctx->seg_start.as<uint32_t>(), d_num, ctx->seg_order.as<uint32_t>(), ctx->d_work_counter,
-          ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv);
+          L->v, tv);
     }
     {
-      StageScope sc(ctx, kStageReplayWide, 2);
-      k_long_partials<<<ctx->num_sms * 8, 256, 0, s>>>(
+      StageScope sc(ctx, kStageReplayWide, 2, ls);
+      k_long_partials<<<ctx->num_sms * 8, 256, 0, ls>>>(
           P, ctx->visits.as<float4>(), ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap,
           ctx->long_partials.as<LongPartial>());
-      k_long_finish<<<ctx->num_sms * 4, 256, 0, s>>>(
+      k_long_finish<<<ctx->num_sms * 4, 256, 0, ls>>>(
           P, ctx->visits.as<float4>(), dk.Current(), ray_bits,
           ctx->d_long_counter, ctx->long_list.as<LongSeg>(), long_cap, L->v, tv,
           ctx->long_partials.as<LongPartial>());
+    }
+    if (forked) {
+      CG_CUDA(cudaEventRecord(own.ev_join, own.side));
+      CG_CUDA(cudaStreamWaitEvent(s, own.ev_join, 0));
     }
   }
   if (n_touched > 0) {
@@ -2177,6 +2198,20 @@ static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int
       CG_CUDA(cub::DeviceRadixSort::SortKeys(fb.cub_tmp.p, tmp_sort, dk, static_cast<int>(total),
                                              bundle_begin_bit, bundle_end_bit, s));
     }
+    // the gather only needs the sorted keys: it runs beside the bundle heads and their ordering
+    const bool forked = side_stream(fb, s);
+    const cudaStream_t gs = forked ? fb.side : s;
+    if (forked) {
+      CG_CUDA(cudaEventRecord(fb.ev_fork, s));
+      CG_CUDA(cudaStreamWaitEvent(fb.side, fb.ev_fork, 0));
+    }
+    {
+      StageScope sc(ctx, kStageGather, 1, gs);
+      k_gather_sorted<<<grid_for(total, 256), 256, 0, gs>>>(
+          kl, P.order_mode, dk.Current(), static_cast<uint32_t>(total), ft, pts, cols,
+          fb.sorted_pts.as<float4>());
+    }
+    if (forked) CG_CUDA(cudaEventRecord(fb.ev_join, fb.side));
     {
       StageScope sc(ctx, kStageBundleScan, 0, s);
       CG_CUDA(cub::DeviceSelect::If(fb.cub_tmp.p, tmp_sel, iota, fb.scan.as<uint32_t>(), d_num,
@@ -2190,12 +2225,6 @@ static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int
     CG_CUDA(fb.frame_count.reserve((F + 1) * cgrid * sizeof(uint32_t)));
     CG_CUDA(fb.ray_id.reserve(upper * sizeof(uint32_t)));
     {
-      StageScope sc(ctx, kStageGather, 1, s);
-      k_gather_sorted<<<grid_for(total, 256), 256, 0, s>>>(
-          kl, P.order_mode, dk.Current(), static_cast<uint32_t>(total), ft, pts, cols,
-          fb.sorted_pts.as<float4>());
-    }
-    {
       StageScope sc(ctx, kStageBundleOrder, 4, s);
       CG_CUDA(fill_bytes(fb.d_class_count, 0, 128 * sizeof(uint32_t), s));  // + the fold queue
       k_bundle_histogram<<<cgrid, 256, frame_smem, s>>>(
@@ -2208,6 +2237,7 @@ static int32_t front_enqueue(cg_context* ctx, FrontBufs& fb, cudaStream_t s, int
           fb.d_class_count, fb.frame_count.as<uint32_t>(), static_cast<int>(F),
           fb.ray_offset.as<uint32_t>(), fb.ray_id.as<uint32_t>(), fb.rays.as<Ray>());
     }
+    if (forked) CG_CUDA(cudaStreamWaitEvent(s, fb.ev_join, 0));
     {
       // 4 CTAs per SM for the long bundles: measured 0.126 / 0.100 / 0.104 / 0.106 ms for
       // 2 / 4 / 8 / 12 with the long bundles alone

@@ -1,6 +1,7 @@
 // layer.cu — context and Layer<TsdfVoxel> replacement: creation, clear, upload, download.
 // Boundary: include/coxgraph_b200.h.  Reference data contract: voxblox Layer / Block /
 // TsdfVoxel as consumed at coxgraph/include/coxgraph/utils/msg_converter.h:49-50,107-109.
+#include <cstdlib>
 #include <cub/cub.cuh>
 #include <stdarg.h>
 #include <string.h>
@@ -401,6 +402,29 @@ cudaError_t init_front_words(FrontBufs& fb) {
   if ((e = cudaMalloc(&fb.d_front_err, sizeof(int32_t))) != cudaSuccess) return e;
   return cudaMemset(fb.d_front_err, 0, sizeof(int32_t));
 }
+bool side_stream(FrontBufs& fb, cudaStream_t like) {
+  static const bool enabled = [] {
+    const char* v = std::getenv("CG_SIDE_STREAM");
+    return !(v && v[0] == '0');
+  }();
+  if (!enabled) return false;
+  if (fb.side) return true;
+  int prio = 0;
+  if (cudaStreamGetPriority(like, &prio) != cudaSuccess) prio = 0;
+  if (cudaStreamCreateWithPriority(&fb.side, cudaStreamNonBlocking, prio) != cudaSuccess ||
+      cudaEventCreateWithFlags(&fb.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&fb.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    if (fb.side) cudaStreamDestroy(fb.side);
+    if (fb.ev_fork) cudaEventDestroy(fb.ev_fork);
+    if (fb.ev_join) cudaEventDestroy(fb.ev_join);
+    fb.side = nullptr;
+    fb.ev_fork = fb.ev_join = nullptr;
+    return false;
+  }
+  return true;
+}
+
 void release_front(FrontBufs& fb) {
   DevBuf* bufs[] = {&fb.poses, &fb.frame_base, &fb.key_a, &fb.key_b, &fb.scan, &fb.cub_tmp, &fb.rays,
                     &fb.ray_count, &fb.ray_offset, &fb.sorted_pts, &fb.scan_partials, &fb.ray_id,
@@ -414,6 +438,9 @@ void release_front(FrontBufs& fb) {
   if (fb.d_class_count) cudaFree(fb.d_class_count);
   if (fb.d_front_err) cudaFree(fb.d_front_err);
   if (fb.h_tables) cudaFreeHost(fb.h_tables);
+  if (fb.side) cudaStreamDestroy(fb.side);
+  if (fb.ev_fork) cudaEventDestroy(fb.ev_fork);
+  if (fb.ev_join) cudaEventDestroy(fb.ev_join);
   fb = FrontBufs();
 }
 
