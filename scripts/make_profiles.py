@@ -20,8 +20,8 @@ os.makedirs(out_dir, exist_ok=True)
 go = os.path.join(ROOT, "gpurun_out")
 
 # kernel -> bench.py stage name
-STAGE = {"k_point_keys": "point_keys", "k_gather_sorted": "gather_sorted", "k_fold_wide": "fold_wide",
-         "k_fold_bundles": "fold_bundles", "k_walk_segments": "walk_segments",
+STAGE = {"k_point_keys": "point_keys", "k_gather_sorted": "gather_sorted", "k_fold": "fold_wide",
+         "k_bundle_order": "bundle_order", "k_walk_segments": "walk_segments",
          "k_block_accumulate": "block_accumulate", "k_voxel_update": "voxel_update",
          "k_long_finish": "replay_wide", "k_finalize_blocks": "finalize",
          "k_resample_merge": "merge_resample", "k_visit_precompute": "visits"}

@@ -12,7 +12,7 @@ python bench.py $ARGS > gpurun_out/plain_$tag.log 2>&1 || { echo "plain run fail
 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "cg_step/" -k "regex:^k_|^Device" --csv \
     --log-file gpurun_out/launches_$tag.csv python bench.py $ARGS > gpurun_out/ncu_launches_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k "regex:k_block_accumulate|k_walk_segments|k_fold_wide|k_point_keys|k_voxel_update|k_visit_precompute|k_long_finish|k_gather_sorted|k_resample_merge|k_fold_bundles|k_finalize_blocks|DeviceRadixSortOnesweepKernel|DeviceRadixSortHistogramKernel|DeviceSelectSweepKernel" \
+    -k "regex:k_block_accumulate|k_walk_segments|k_fold|k_point_keys|k_voxel_update|k_visit_precompute|k_long_finish|k_gather_sorted|k_resample_merge|k_bundle_order|k_finalize_blocks|DeviceRadixSortOnesweepKernel|DeviceRadixSortHistogramKernel|DeviceSelectSweepKernel" \
     --nvtx --nvtx-include "cg_step/" -o gpurun_out/prof_$tag -f python bench.py $ARGS > gpurun_out/ncu_full_$tag.log 2>&1
 # only the raw page travels back (gpurun_out/ is limited to 64 MiB): KEEP_REP=1 keeps the report
 ncu -i gpurun_out/prof_$tag.ncu-rep --page raw --csv > gpurun_out/prof_$tag.raw.csv 2>/dev/null

@@ -50,6 +50,28 @@ def test_batch_equals_sequential(gpu_ctx):
     gl.close()
 
 
+def test_batch_many_ragged_frames(gpu_ctx):
+    """40 small frames of different sizes in ONE group, one of them empty, one with dropped (NaN /
+    too close) points only at its end: the bundles of all frames interleave in the voxel-major
+    sort and the ray ids must still come out in (frame, clearing, voxel) order — a wrong order
+    shows up in every voxel that two frames update."""
+    base = util.small_frames(8, stride=16)
+    frames = []
+    for k in range(40):
+        T, p, c = base[k % len(base)]
+        n = len(p) - 37 * (k % 5)              # ragged
+        p, c = p[:n].copy(), c[:n].copy()
+        if k == 7:
+            p, c = p[:0], c[:0]                # an empty frame
+        if k == 11:
+            p[-200:] = np.nan                  # dropped points
+            p[-400:-200] *= 0.001              # closer than min_ray_length
+        frames.append((T, p, c))
+    got, ref, gl = _run_both(gpu_ctx, frames, batch=True)
+    util.compare_layers(got, ref, "40 ragged frames in one group")
+    gl.close()
+
+
 def test_batch_split_path(gpu_ctx, monkeypatch):
     monkeypatch.setenv("CG_MAX_PAIRS", "100000")
     frames = util.small_frames(4, stride=8)
