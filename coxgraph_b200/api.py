@@ -40,6 +40,17 @@ def TsdfIntegratorConfig(**overrides):
     return cfg
 
 
+def esdfConfig(**overrides):
+    """voxblox::EsdfIntegrator::Config with upstream defaults."""
+    cfg = capi.EsdfConfig()
+    capi.load().cg_esdf_config_default(C.byref(cfg))
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
 class Context:
     """One per GPU (per process rank)."""
 
@@ -205,6 +216,41 @@ class Layer:
                                          _ptr(v) if V else None, _ptr(n) if V else None,
                                          _ptr(c) if V else None))
         return idx, begin, v, n, c
+
+    def updateEsdfBatch(self, config=None, fetch=True):
+        """voxblox::EsdfIntegrator::updateFromTsdfLayerBatch on the device
+        (coxgraph/include/coxgraph/client/map_server.h:141-145).  The ESDF stays in the context;
+        with fetch -> dict(idx int32 [B,3] in (z,y,x) order, distance f32 [B,4096], flags u8
+        [B,4096] (1 observed, 2 hallucinated, 8 fixed), parent i8 [B,4096,3], stats)."""
+        lib = capi.load()
+        cfg = config if config is not None else esdfConfig()
+        st = capi.EsdfStats()
+        capi.check(lib.cg_layer_esdf_batch(self._h, C.byref(cfg), C.byref(st)))
+        if not fetch:
+            return st
+        B = st.blocks
+        idx = np.zeros((B, 3), np.int32)
+        dist = np.zeros((B, capi.VOXELS_PER_BLOCK), np.float32)
+        packed = np.zeros((B, capi.VOXELS_PER_BLOCK), np.uint32)
+        if B:
+            capi.check(lib.cg_esdf_fetch(self.ctx._h, B, _ptr(idx), _ptr(dist), _ptr(packed), None))
+        parent = np.stack([(packed >> 24).astype(np.uint8).view(np.int8),
+                           ((packed >> 16) & 0xFF).astype(np.uint8).view(np.int8),
+                           ((packed >> 8) & 0xFF).astype(np.uint8).view(np.int8)], axis=-1)
+        return dict(idx=idx, distance=dist, flags=(packed & 0xFF).astype(np.uint8), parent=parent,
+                    packed=packed, stats=st)
+
+    def esdfFreePoints(self, min_distance):
+        """voxblox::createFreePointcloudFromEsdfLayer (coxgraph/src/client/map_server.cpp:112-113)
+        on the ESDF the last updateEsdfBatch left in the context -> f32 [N,4] (x, y, z, distance)."""
+        lib = capi.load()
+        n = C.c_size_t(0)
+        capi.check(lib.cg_esdf_free_points(self.ctx._h, float(min_distance), 0, None, C.byref(n)))
+        out = np.zeros((n.value, 4), np.float32)
+        if n.value:
+            capi.check(lib.cg_esdf_free_points(self.ctx._h, float(min_distance), n.value, _ptr(out),
+                                               C.byref(n)))
+        return out
 
     def download_blocks(self, block_indices):
         """The listed blocks only -> (voxels [n,4096] VOXEL_DTYPE, flags u8 [n], found bool [n])."""

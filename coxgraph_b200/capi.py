@@ -103,6 +103,20 @@ class ReprojectStats(C.Structure):
                 ("blocks_removed", C.c_uint64), ("full_rebuild", C.c_uint64)]
 
 
+class EsdfConfig(C.Structure):
+    """cg_esdf_config == voxblox::EsdfIntegrator::Config."""
+
+    _fields_ = [("max_distance_m", C.c_float), ("default_distance_m", C.c_float),
+                ("min_distance_m", C.c_float), ("min_diff_m", C.c_float), ("min_weight", C.c_float),
+                ("num_buckets", C.c_int32), ("multi_queue", C.c_int32),
+                ("add_occupied_crust", C.c_int32), ("full_euclidean_distance", C.c_int32)]
+
+
+class EsdfStats(C.Structure):
+    _fields_ = [("blocks", C.c_uint64), ("observed_voxels", C.c_uint64),
+                ("fixed_voxels", C.c_uint64), ("sweeps", C.c_uint64), ("block_passes", C.c_uint64)]
+
+
 # every symbol include/coxgraph_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -157,6 +171,10 @@ SYMBOLS = {
     "cg_layer_mesh": (C.c_int32, [_P, C.c_float, C.c_int32, C.c_int32, C.c_size_t, C.c_size_t, _P, _P,
                                   _P, _P, _P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "cg_mesh_fetch": (C.c_int32, [_P, C.c_size_t, C.c_size_t, _P, _P, _P, _P, _P]),
+    "cg_esdf_config_default": (None, [C.POINTER(EsdfConfig)]),
+    "cg_layer_esdf_batch": (C.c_int32, [_P, C.POINTER(EsdfConfig), C.POINTER(EsdfStats)]),
+    "cg_esdf_fetch": (C.c_int32, [_P, C.c_size_t, _P, _P, _P, C.POINTER(C.c_size_t)]),
+    "cg_esdf_free_points": (C.c_int32, [_P, C.c_float, C.c_size_t, _P, C.POINTER(C.c_size_t)]),
     "cg_reproject_submaps": (C.c_int32, [_P, _P, _P, C.c_size_t, C.c_float, C.c_float, _P, _P,
                                          C.POINTER(ReprojectStats)]),
     "cg_block_owner": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

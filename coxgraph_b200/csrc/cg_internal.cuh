@@ -288,6 +288,12 @@ struct cg_context : cg::FrontBufs {
   // marching cubes (mesh.cu)
   cg::DevBuf mc_counts, mc_index, mc_vertices, mc_normals, mc_colors;
   size_t mc_blocks = 0, mc_total = 0;  // size of the retained result (cg_mesh_fetch)
+  // ESDF of a layer (esdf.cu): working / result planes in (z, y, x) block order, retained until
+  // the next cg_layer_esdf_batch on this context
+  cg::DevBuf esdf_keys, esdf_slots, esdf_work, esdf_dist, esdf_packed, esdf_fixed, esdf_slot_to_b,
+      esdf_dirty, esdf_list, esdf_index, esdf_counters;
+  size_t esdf_blocks = 0;
+  float esdf_voxel_size = 0.0f, esdf_block_size = 0.0f;
   // instrumentation
   bool profiling = false;
   uint64_t own_launches = 0;  // kernels of this library launched (library sorts/scans excluded)

@@ -551,7 +551,10 @@ int32_t cg_context_destroy(cg_context* ctx) {
                     &ctx->merge_cands, &ctx->mc_counts, &ctx->mc_index, &ctx->mc_vertices,
                     &ctx->mc_normals, &ctx->mc_colors, &ctx->mesh_in, &ctx->mesh_tri,
                     &ctx->mesh_pairs, &ctx->mesh_pts_g, &ctx->mesh_cols_g, &ctx->mesh_pts_c,
-                    &ctx->mesh_cols_c, &ctx->mesh_frames};
+                    &ctx->mesh_cols_c, &ctx->mesh_frames, &ctx->esdf_keys, &ctx->esdf_slots,
+                    &ctx->esdf_work, &ctx->esdf_dist, &ctx->esdf_packed, &ctx->esdf_fixed,
+                    &ctx->esdf_slot_to_b, &ctx->esdf_dirty, &ctx->esdf_list, &ctx->esdf_index,
+                    &ctx->esdf_counters};
   for (DevBuf* b : bufs) b->release();
   drain_events(ctx);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);

@@ -323,6 +323,60 @@ int32_t cg_mesh_fetch(cg_context* ctx, size_t capacity_blocks, size_t capacity_v
                       int32_t* block_idx_xyz, uint32_t* vertex_begin, float* vertices_xyz,
                       float* normals_xyz, uint8_t* colors_rgba);
 
+/* --- ESDF of the device-resident layer (second half): replaces
+ * voxblox::EsdfIntegrator::updateFromTsdfLayerBatch() as the client's MapServer runs it after the
+ * merge (coxgraph/include/coxgraph/client/map_server.h:141-145, from
+ * coxgraph/src/client/map_server.cpp:99) and voxblox::createFreePointcloudFromEsdfLayer
+ * (coxgraph/src/client/map_server.cpp:112-113).  Mirrors voxblox::EsdfIntegrator::Config (upstream
+ * defaults in comments; coxgraph/config/coxgraph_client.yaml:68-69 sets esdf_max/min_distance).
+ * The ESDF gets one block per allocated TSDF block; a voxel with tsdf weight >= min_weight is
+ * observed; |tsdf distance| < min_distance_m copies the distance and fixes the voxel; every other
+ * observed voxel starts at +-default_distance_m and takes the quasi-Euclidean 26-neighbour
+ * wavefront distance from voxels of equal sign with |distance| < max_distance_m (processOpenSet).
+ * The device computes the FIXED POINT of that relaxation, i.e. upstream's result for
+ * min_diff_m = 0 (unique, order-independent, bit-identical to a sequential run); with upstream's
+ * min_diff_m > 0 the sequential queue may stop above it by less than min_diff_m per hop.
+ * min_diff_m, num_buckets and multi_queue are therefore accepted and ignored;
+ * full_euclidean_distance != 0 returns CG_ERR_UNSUPPORTED; default_distance_m must be >=
+ * max_distance_m (what voxblox_ros' parameter loader enforces). */
+typedef struct cg_esdf_config {
+  float max_distance_m;             /* 2.0 */
+  float default_distance_m;         /* 2.0 */
+  float min_distance_m;             /* 0.2 */
+  float min_diff_m;                 /* 0.001 (ignored: see above) */
+  float min_weight;                 /* 1e-6 */
+  int32_t num_buckets;              /* 20 (ignored) */
+  int32_t multi_queue;              /* 0 (ignored) */
+  int32_t add_occupied_crust;       /* 0 */
+  int32_t full_euclidean_distance;  /* 0 */
+} cg_esdf_config;
+typedef struct cg_esdf_stats {
+  uint64_t blocks;           /* ESDF blocks = allocated TSDF blocks */
+  uint64_t observed_voxels;
+  uint64_t fixed_voxels;
+  uint64_t sweeps;           /* rounds over the dirty blocks until none was left */
+  uint64_t block_passes;     /* blocks relaxed, summed over the sweeps */
+} cg_esdf_stats;
+void cg_esdf_config_default(cg_esdf_config* cfg);
+/* Rebuilds the ESDF of `tsdf_layer` on the device; the result stays in the layer's context until
+ * the next call. */
+int32_t cg_layer_esdf_batch(const cg_layer* tsdf_layer, const cg_esdf_config* cfg,
+                            cg_esdf_stats* stats);
+/* Copies the retained ESDF out: blocks in (z, y, x) order, distance float[B*4096] and
+ * packed uint32[B*4096] by linear voxel index — the two words Block<EsdfVoxel>::serializeToIntegers
+ * emits per voxel: packed = parent.x << 24 | parent.y << 16 | parent.z << 8 | flags (int8 parent
+ * components; flags: 1 observed, 2 hallucinated, 4 in_queue (always 0), 8 fixed).  `parent` points
+ * to the first neighbour (faces, edges, corners; dz, dy, dx ascending) that attains the distance
+ * (upstream: whichever the queue order met).  Any pointer may be NULL. */
+int32_t cg_esdf_fetch(cg_context* ctx, size_t capacity_blocks, int32_t* block_idx_xyz,
+                      float* distance, uint32_t* packed, size_t* num_blocks_out);
+/* createFreePointcloudFromEsdfLayer(esdf, min_distance): (x, y, z, intensity = distance) of every
+ * observed voxel with distance >= min_distance, blocks in (z, y, x) order, voxels by linear index.
+ * *num_points_out is always set; xyzi (float[4*capacity_points], may be NULL) is filled when the
+ * capacity suffices. */
+int32_t cg_esdf_free_points(cg_context* ctx, float min_distance, size_t capacity_points,
+                            float* xyzi, size_t* num_points_out);
+
 /* --- incremental re-projection.  The reference rebuilds the whole global map
  * on every trigger (coxgraph/include/coxgraph/server/coxgraph_server.h:275-283 ->
  * coxgraph/src/server/visualizer/server_visualizer.cpp:123-126) although it knows which submap

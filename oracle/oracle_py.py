@@ -39,6 +39,21 @@ class IntegratorConfig(C.Structure):
     ]
 
 
+class EsdfConfig(C.Structure):
+    """Mirror of orc_esdf_config (voxblox EsdfIntegrator::Config)."""
+
+    _fields_ = [
+        ("max_distance_m", C.c_float),
+        ("default_distance_m", C.c_float),
+        ("min_distance_m", C.c_float),
+        ("min_diff_m", C.c_float),
+        ("min_weight", C.c_float),
+        ("num_buckets", C.c_int32),
+        ("multi_queue", C.c_int32),
+        ("add_occupied_crust", C.c_int32),
+    ]
+
+
 def build(force=False):
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
         os.path.getmtime(os.path.join(_HERE, f)) for f in ("tsdf_oracle.cc", "tsdf_oracle.h")
@@ -93,6 +108,17 @@ def lib():
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_triangle_table.restype = C.POINTER(C.c_int)
         L.orc_triangle_table.argtypes = []
+        L.orc_esdf_default_config.argtypes = [C.POINTER(EsdfConfig)]
+        L.orc_esdf_batch.restype = C.c_void_p
+        L.orc_esdf_batch.argtypes = [C.c_void_p, C.POINTER(EsdfConfig)]
+        L.orc_esdf_destroy.argtypes = [C.c_void_p]
+        L.orc_esdf_num_blocks.restype = C.c_size_t
+        L.orc_esdf_num_blocks.argtypes = [C.c_void_p]
+        L.orc_esdf_updates.restype = C.c_uint64
+        L.orc_esdf_updates.argtypes = [C.c_void_p]
+        L.orc_esdf_download.argtypes = [C.c_void_p] * 5
+        L.orc_esdf_free_points.restype = C.c_size_t
+        L.orc_esdf_free_points.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_size_t]
         L.orc_interp_voxel.restype = C.c_int32
         L.orc_interp_voxel.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_float),
                                        C.POINTER(C.c_float), C.c_void_p]
@@ -102,6 +128,16 @@ def lib():
 def default_config(**over):
     cfg = IntegratorConfig()
     lib().orc_default_config(C.byref(cfg))
+    for k, v in over.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def default_esdf_config(**over):
+    cfg = EsdfConfig()
+    lib().orc_esdf_default_config(C.byref(cfg))
     for k, v in over.items():
         if not hasattr(cfg, k):
             raise AttributeError(k)
@@ -209,6 +245,33 @@ class Layer:
             lib().orc_layer_mesh(self._h, min_weight, int(use_color), int(only_updated),
                                  _ptr(begin), _ptr(v), _ptr(nr), _ptr(c), n)
         return begin, v, nr, c
+
+    def esdf_batch(self, cfg=None, free_min_distance=None):
+        """EsdfIntegrator::updateFromTsdfLayerBatch on this TSDF layer -> dict(idx int32 [B,3] in
+        (z,y,x) order, distance f32 [B,4096], flags u8 [B,4096] (1 observed, 2 hallucinated,
+        4 in_queue, 8 fixed), parent i8 [B,4096,3], updates); with free_min_distance also
+        free_points f32 [N,4] (createFreePointcloudFromEsdfLayer)."""
+        cfg = cfg if cfg is not None else default_esdf_config()
+        h = lib().orc_esdf_batch(self._h, C.byref(cfg))
+        try:
+            n = lib().orc_esdf_num_blocks(h)
+            out = dict(idx=np.zeros((n, 3), np.int32),
+                       distance=np.zeros((n, VOXELS_PER_BLOCK), np.float32),
+                       flags=np.zeros((n, VOXELS_PER_BLOCK), np.uint8),
+                       parent=np.zeros((n, VOXELS_PER_BLOCK, 3), np.int8),
+                       updates=lib().orc_esdf_updates(h))
+            if n:
+                lib().orc_esdf_download(h, _ptr(out["idx"]), _ptr(out["distance"]),
+                                        _ptr(out["flags"]), _ptr(out["parent"]))
+            if free_min_distance is not None:
+                m = lib().orc_esdf_free_points(h, float(free_min_distance), None, 0)
+                pts = np.zeros((m, 4), np.float32)
+                if m:
+                    lib().orc_esdf_free_points(h, float(free_min_distance), _ptr(pts), m)
+                out["free_points"] = pts
+        finally:
+            lib().orc_esdf_destroy(h)
+        return out
 
     def interp(self, pos, interpolate=True):
         p = _f32(pos, (3,))

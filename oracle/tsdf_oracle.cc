@@ -17,6 +17,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -1626,5 +1627,286 @@ size_t orc_layer_mesh(const orc_layer* l, float min_weight, int32_t use_color, i
 }
 
 const int* orc_triangle_table(void) { return &kTriangleTable[0][0]; }
+
+}  // extern "C"
+
+// ================================================================ ESDF (second half)
+// voxblox::EsdfIntegrator::updateFromTsdfLayerBatch as called by the client's MapServer
+// (coxgraph/include/coxgraph/client/map_server.h:141-145 <- coxgraph/src/client/map_server.cpp:99)
+// and voxblox::createFreePointcloudFromEsdfLayer (coxgraph/src/client/map_server.cpp:112-113).
+// [EXT] upstream voxblox integrator/esdf_integrator.cc, utils/bucket_queue.h,
+// utils/neighbor_tools.h; PARITY UNPINNED like the rest of this file.  Sequential, in upstream's
+// order of work: blocks in (z, y, x) order (upstream: hash-map order), voxels by linear index,
+// then the bucketed open queue.  `parent` follows the queue order and is order-dependent upstream.
+namespace {
+
+struct EsdfVoxel {  // voxblox::EsdfVoxel
+  float distance = 0.0f;
+  bool observed = false;
+  bool hallucinated = false;
+  bool in_queue = false;
+  bool fixed = false;
+  int8_t parent[3] = {0, 0, 0};
+};
+struct EsdfBlock {
+  EsdfVoxel voxels[kVoxelsPerBlock];
+};
+
+// NeighborhoodLookupTables (26-connectivity): 6 faces, 12 edges, 8 corners; kDistances in voxels
+struct Neighbor {
+  int dx, dy, dz;
+  float dist;
+};
+std::vector<Neighbor> make_neighbors() {
+  std::vector<Neighbor> n;
+  const float s2 = std::sqrt(2.0f), s3 = std::sqrt(3.0f);
+  for (int order = 1; order <= 3; ++order)
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx)
+          if (std::abs(dx) + std::abs(dy) + std::abs(dz) == order)
+            n.push_back({dx, dy, dz, order == 1 ? 1.0f : order == 2 ? s2 : s3});
+  return n;
+}
+
+// utils/bucket_queue.h: num_buckets FIFO queues over |priority| in [0, max_val]
+struct BucketQueue {
+  std::vector<std::deque<L3>> buckets;
+  int num_buckets = 0, last = 0;
+  double max_val = 0.0;
+  size_t count = 0;
+  void set(int n, double max_value) {
+    num_buckets = n;
+    max_val = max_value;
+    buckets.assign(static_cast<size_t>(n), {});
+    last = 0;
+    count = 0;
+  }
+  void push(const L3& key, double value) {
+    if (value > max_val) value = max_val;
+    int b = static_cast<int>(std::floor(std::abs(value) / max_val * (num_buckets - 1)));
+    if (b >= num_buckets) b = num_buckets - 1;
+    if (b < last) last = b;
+    buckets[static_cast<size_t>(b)].push_back(key);
+    ++count;
+  }
+  bool empty() const { return count == 0; }
+  L3 pop_front() {
+    while (buckets[static_cast<size_t>(last)].empty() && last < num_buckets - 1) ++last;
+    L3 k = buckets[static_cast<size_t>(last)].front();
+    buckets[static_cast<size_t>(last)].pop_front();
+    --count;
+    return k;
+  }
+};
+
+inline float signum(float x) { return x == 0.0f ? 0.0f : (x < 0.0f ? -1.0f : 1.0f); }
+
+struct EsdfMap {
+  std::unordered_map<I3, std::unique_ptr<EsdfBlock>, I3Hash> blocks;
+  EsdfVoxel* voxel(const L3& g) {  // Layer::getVoxelPtrByGlobalIndex
+    const I3 b = {static_cast<int32_t>(g.x >> 4), static_cast<int32_t>(g.y >> 4),
+                  static_cast<int32_t>(g.z >> 4)};
+    auto it = blocks.find(b);
+    if (it == blocks.end()) return nullptr;
+    return &it->second->voxels[(g.x & 15) + 16 * ((g.y & 15) + 16 * (g.z & 15))];
+  }
+};
+
+}  // namespace
+
+struct orc_esdf {
+  EsdfMap map;
+  std::vector<I3> keys;  // (z, y, x) order
+  float voxel_size = 0.0f, block_size = 0.0f;
+  uint64_t updates = 0;
+};
+
+extern "C" {
+
+void orc_esdf_default_config(orc_esdf_config* c) {
+  c->max_distance_m = 2.0f;
+  c->default_distance_m = 2.0f;
+  c->min_distance_m = 0.2f;
+  c->min_diff_m = 0.001f;
+  c->min_weight = 1e-6f;
+  c->num_buckets = 20;
+  c->multi_queue = 0;
+  c->add_occupied_crust = 0;
+}
+
+orc_esdf* orc_esdf_batch(const orc_layer* tsdf, const orc_esdf_config* cfg) {
+  static const std::vector<Neighbor> kNeighbors = make_neighbors();
+  orc_esdf* E = new orc_esdf();
+  E->voxel_size = tsdf->voxel_size;
+  E->block_size = tsdf->block_size;
+  const float vs = tsdf->voxel_size;
+  BucketQueue open;
+  open.set(cfg->num_buckets, cfg->max_distance_m);
+  for (const auto& kv : tsdf->blocks) E->keys.push_back(kv.first);
+  std::sort(E->keys.begin(), E->keys.end(), zyx_less_i);
+  EsdfMap& M = E->map;
+
+  // EsdfIntegrator::updateVoxelFromNeighbors: lower |distance| of a fresh voxel from the
+  // neighbours already in the map
+  auto update_from_neighbors = [&](const L3& g, EsdfVoxel* v) -> bool {
+    bool updated = false;
+    for (const Neighbor& nb : kNeighbors) {
+      EsdfVoxel* n = M.voxel({g.x + nb.dx, g.y + nb.dy, g.z + nb.dz});
+      if (!n || !n->observed || n->hallucinated) continue;
+      const float d = nb.dist * vs;
+      if (v->distance > 0.0f && n->distance > 0.0f) {
+        if (n->distance + d + cfg->min_diff_m < v->distance) {
+          v->distance = n->distance + d;
+          v->parent[0] = static_cast<int8_t>(nb.dx);
+          v->parent[1] = static_cast<int8_t>(nb.dy);
+          v->parent[2] = static_cast<int8_t>(nb.dz);
+          updated = true;
+        }
+      } else if (v->distance < 0.0f && n->distance < 0.0f) {
+        if (n->distance - d - cfg->min_diff_m > v->distance) {
+          v->distance = n->distance - d;
+          v->parent[0] = static_cast<int8_t>(nb.dx);
+          v->parent[1] = static_cast<int8_t>(nb.dy);
+          v->parent[2] = static_cast<int8_t>(nb.dz);
+          updated = true;
+        }
+      }
+    }
+    return updated;
+  };
+
+  // updateFromTsdfBlocks(all allocated blocks, incremental = false)
+  for (const I3& bi : E->keys) {
+    const Block* tb = tsdf->find(bi);
+    auto& eb = M.blocks[bi];
+    if (!eb) eb.reset(new EsdfBlock());
+    for (int lin = 0; lin < kVoxelsPerBlock; ++lin) {
+      const Voxel& tv = tb->voxels[lin];
+      EsdfVoxel& ev = eb->voxels[lin];
+      if (tv.weight < cfg->min_weight) {
+        if (cfg->add_occupied_crust) {
+          ev.distance = -cfg->default_distance_m;
+          ev.observed = true;
+          ev.hallucinated = true;
+          ev.fixed = false;
+        }
+        continue;
+      }
+      const L3 g = {int64_t(bi.x) * 16 + (lin & 15), int64_t(bi.y) * 16 + ((lin >> 4) & 15),
+                    int64_t(bi.z) * 16 + (lin >> 8)};
+      const bool tsdf_fixed = std::abs(tv.distance) < cfg->min_distance_m;  // isFixed
+      if (tsdf_fixed) {
+        ev.distance = tv.distance;
+        ev.observed = true;
+        ev.hallucinated = false;
+        ev.fixed = true;
+        ev.parent[0] = ev.parent[1] = ev.parent[2] = 0;
+        ev.in_queue = true;
+        open.push(g, ev.distance);
+      } else {
+        ev.distance = signum(tv.distance) * cfg->default_distance_m;
+        ev.observed = true;
+        ev.hallucinated = false;
+        ev.fixed = false;
+        ev.parent[0] = ev.parent[1] = ev.parent[2] = 0;
+        if (update_from_neighbors(g, &ev)) {
+          ev.in_queue = true;
+          open.push(g, ev.distance);
+        }
+      }
+    }
+  }
+  // processRaiseSet: nothing to raise in a batch rebuild.  processOpenSet:
+  while (!open.empty()) {
+    const L3 g = open.pop_front();
+    EsdfVoxel* v = M.voxel(g);
+    v->in_queue = false;
+    if (!v->observed || v->distance >= cfg->max_distance_m || v->distance <= -cfg->max_distance_m)
+      continue;
+    for (const Neighbor& nb : kNeighbors) {
+      const L3 ng = {g.x + nb.dx, g.y + nb.dy, g.z + nb.dz};
+      EsdfVoxel* n = M.voxel(ng);
+      if (!n || !n->observed || n->fixed) continue;
+      const float d = nb.dist * vs;
+      bool lowered = false;
+      if (v->distance > 0.0f && n->distance > 0.0f) {  // both outside the surface
+        if (v->distance + d + cfg->min_diff_m < n->distance) {
+          n->distance = v->distance + d;
+          lowered = true;
+        }
+      } else if (v->distance < 0.0f && n->distance < 0.0f) {  // both inside
+        if (v->distance - d - cfg->min_diff_m > n->distance) {
+          n->distance = v->distance - d;
+          lowered = true;
+        }
+      }
+      if (lowered) {
+        ++E->updates;
+        n->parent[0] = static_cast<int8_t>(-nb.dx);
+        n->parent[1] = static_cast<int8_t>(-nb.dy);
+        n->parent[2] = static_cast<int8_t>(-nb.dz);
+        if (cfg->multi_queue || !n->in_queue) {
+          open.push(ng, n->distance);
+          n->in_queue = true;
+        }
+      }
+    }
+  }
+  return E;
+}
+
+void orc_esdf_destroy(orc_esdf* e) { delete e; }
+size_t orc_esdf_num_blocks(const orc_esdf* e) { return e->keys.size(); }
+uint64_t orc_esdf_updates(const orc_esdf* e) { return e->updates; }
+
+void orc_esdf_download(const orc_esdf* e, int32_t* block_idx_xyz, float* distance, uint8_t* flags,
+                       int8_t* parent) {
+  for (size_t b = 0; b < e->keys.size(); ++b) {
+    const I3 k = e->keys[b];
+    if (block_idx_xyz) {
+      block_idx_xyz[3 * b] = k.x;
+      block_idx_xyz[3 * b + 1] = k.y;
+      block_idx_xyz[3 * b + 2] = k.z;
+    }
+    const EsdfBlock& blk = *e->map.blocks.find(k)->second;
+    for (int i = 0; i < kVoxelsPerBlock; ++i) {
+      const EsdfVoxel& v = blk.voxels[i];
+      const size_t o = b * kVoxelsPerBlock + static_cast<size_t>(i);
+      if (distance) distance[o] = v.distance;
+      if (flags)
+        flags[o] = static_cast<uint8_t>((v.observed ? 1 : 0) | (v.hallucinated ? 2 : 0) |
+                                        (v.in_queue ? 4 : 0) | (v.fixed ? 8 : 0));
+      if (parent) {
+        parent[3 * o] = v.parent[0];
+        parent[3 * o + 1] = v.parent[1];
+        parent[3 * o + 2] = v.parent[2];
+      }
+    }
+  }
+}
+
+// createFreePointcloudFromEsdfLayer (voxblox_ros ptcloud_vis.h): observed voxels with
+// distance >= min_distance, as (x, y, z, intensity = distance); blocks in (z, y, x) order
+size_t orc_esdf_free_points(const orc_esdf* e, float min_distance, float* xyzi, size_t capacity) {
+  size_t n = 0;
+  for (const I3& k : e->keys) {
+    const EsdfBlock& blk = *e->map.blocks.find(k)->second;
+    const V3 origin = origin_point(k, e->block_size);
+    for (int i = 0; i < kVoxelsPerBlock; ++i) {
+      const EsdfVoxel& v = blk.voxels[i];
+      if (!(v.observed && v.distance >= min_distance)) continue;
+      if (xyzi && n < capacity) {
+        // Block::computeCoordinatesFromVoxelIndex: origin + getCenterPointFromGridIndex
+        xyzi[4 * n] = origin.x + center_coord(i & 15, e->voxel_size);
+        xyzi[4 * n + 1] = origin.y + center_coord((i >> 4) & 15, e->voxel_size);
+        xyzi[4 * n + 2] = origin.z + center_coord(i >> 8, e->voxel_size);
+        xyzi[4 * n + 3] = v.distance;
+      }
+      ++n;
+    }
+  }
+  return n;
+}
 
 }  // extern "C"

@@ -142,6 +142,39 @@ size_t orc_layer_mesh(const orc_layer* layer, float min_weight, int32_t use_colo
 /* kTriangleTable[256][16] */
 const int* orc_triangle_table(void);
 
+/* ---- EsdfIntegrator::updateFromTsdfLayerBatch ([EXT] voxblox integrator/esdf_integrator.cc,
+ * utils/bucket_queue.h, utils/neighbor_tools.h; parity unpinned), the call of
+ * coxgraph/include/coxgraph/client/map_server.h:141-145: the ESDF layer is rebuilt from every
+ * allocated TSDF block — voxels inside |distance| < min_distance_m are copied and fixed, the others
+ * start at +-default_distance_m and are lowered by the quasi-Euclidean 26-neighbour wavefront of
+ * processOpenSet (bucketed open queue, an update is taken when it improves by more than
+ * min_diff_m).  Sequential; blocks in (z, y, x) order.  Mirrors voxblox::EsdfIntegrator::Config
+ * (upstream defaults in comments); full_euclidean_distance is not restated. */
+typedef struct orc_esdf_config {
+  float max_distance_m;      /* 2.0 */
+  float default_distance_m;  /* 2.0 */
+  float min_distance_m;      /* 0.2 */
+  float min_diff_m;          /* 0.001 */
+  float min_weight;          /* 1e-6 */
+  int32_t num_buckets;       /* 20 */
+  int32_t multi_queue;       /* 0 */
+  int32_t add_occupied_crust; /* 0 */
+} orc_esdf_config;
+typedef struct orc_esdf orc_esdf;
+void orc_esdf_default_config(orc_esdf_config* cfg);
+orc_esdf* orc_esdf_batch(const orc_layer* tsdf, const orc_esdf_config* cfg);
+void orc_esdf_destroy(orc_esdf* esdf);
+size_t orc_esdf_num_blocks(const orc_esdf* esdf);
+uint64_t orc_esdf_updates(const orc_esdf* esdf); /* neighbour updates taken by processOpenSet */
+/* blocks in (z, y, x) order; distance float[B*4096]; flags uint8[B*4096]: bit0 observed,
+ * bit1 hallucinated, bit2 in_queue, bit3 fixed; parent int8[B*4096*3].  Any pointer may be NULL. */
+void orc_esdf_download(const orc_esdf* esdf, int32_t* block_idx_xyz, float* distance,
+                       uint8_t* flags, int8_t* parent);
+/* voxblox::createFreePointcloudFromEsdfLayer (coxgraph/src/client/map_server.cpp:112-113):
+ * (x, y, z, intensity = distance) of every observed voxel with distance >= min_distance, blocks in
+ * (z, y, x) order, voxels by linear index.  Returns the count; fills up to `capacity` points. */
+size_t orc_esdf_free_points(const orc_esdf* esdf, float min_distance, float* xyzi, size_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,3 +95,68 @@ def record_margins(name, m):
     except OSError:
         pass
     print(f"[parity margins] {name}: {m}")
+
+
+def esdf_fixed_point_numpy(idx, vox, cfg, voxel_size):
+    """The fixed point of EsdfIntegrator's relaxation (min_diff_m = 0) by dense Jacobi iteration
+    in numpy float32 — an independent statement of what both the sequential oracle (any queue
+    order) and the block-parallel CUDA kernels must end in, bit for bit.  idx [B,3], vox [B,4096]
+    VOXEL_DTYPE -> distance f32 [B,4096] (0 where unobserved), observed bool, fixed bool."""
+    idx = np.asarray(idx, np.int64)
+    lo = idx.min(axis=0)
+    ext = (idx.max(axis=0) - lo + 1) * 16
+    D = np.full((ext[2] + 2, ext[1] + 2, ext[0] + 2), np.nan, np.float32)  # z, y, x + 1-voxel rim
+    fixed = np.zeros(D.shape, bool)
+    crust = np.zeros(D.shape, bool)
+    sl = []
+    dflt = np.float32(cfg.default_distance_m)
+    for b, bi in enumerate(idx):
+        o = (bi - lo) * 16 + 1
+        s = (slice(o[2], o[2] + 16), slice(o[1], o[1] + 16), slice(o[0], o[0] + 16))
+        sl.append(s)
+        d = vox[b]["distance"].reshape(16, 16, 16)
+        w = vox[b]["weight"].reshape(16, 16, 16)
+        obs = ~(w < np.float32(cfg.min_weight))
+        fx = obs & (np.abs(d) < np.float32(cfg.min_distance_m))
+        init = np.where(fx, d, np.sign(d).astype(np.float32) * dflt).astype(np.float32)
+        if cfg.add_occupied_crust:
+            init = np.where(obs, init, -dflt)
+            crust[s] = ~obs
+        else:
+            init = np.where(obs, init, np.float32(np.nan))
+        D[s] = init
+        fixed[s] = fx
+    vs = np.float32(voxel_size)
+    w_cls = {1: np.float32(1.0) * vs, 2: np.float32(np.sqrt(np.float32(2.0))) * vs,
+             3: np.float32(np.sqrt(np.float32(3.0))) * vs}
+    mx = np.float32(cfg.max_distance_m)
+    inner = (slice(1, -1),) * 3
+    while True:
+        sgn = np.where(D < 0, np.float32(-1), np.float32(1))
+        mag = np.abs(D)
+        best = mag[inner].copy()
+        for dz in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    order = abs(dx) + abs(dy) + abs(dz)
+                    if order == 0:
+                        continue
+                    nb = D[1 + dz:D.shape[0] - 1 + dz, 1 + dy:D.shape[1] - 1 + dy,
+                           1 + dx:D.shape[2] - 1 + dx]
+                    a = sgn[inner] * nb
+                    with np.errstate(invalid="ignore"):
+                        ok = (a > 0) & (a < mx)
+                        cand = np.where(ok, (a + w_cls[order]).astype(np.float32), np.float32(np.inf))
+                        best = np.minimum(best, cand)
+        with np.errstate(invalid="ignore"):
+            lower = (best < mag[inner]) & ~fixed[inner] & ~np.isnan(D[inner]) & (D[inner] != 0)
+        if not lower.any():
+            break
+        new = D[inner].copy()
+        new[lower] = (sgn[inner] * best)[lower]
+        D[inner] = new
+    dist = np.stack([D[s].reshape(4096) for s in sl])
+    observed = ~np.isnan(dist)
+    return (np.where(observed, dist, np.float32(0)).astype(np.float32), observed,
+            np.stack([fixed[s].reshape(4096) for s in sl]),
+            np.stack([crust[s].reshape(4096) for s in sl]))
