@@ -448,6 +448,11 @@ def run_c5(env):
                                   "candidates": int(rst.candidates)},
         "setup_s": build_s, "clocks": clocks,
     }
+    # the ESDF of the re-merged map (the client's updateEsdfBatch, map_server.h:141-145), on the
+    # full-rebuild result
+    glob.clear()
+    getProjectedMap(subs, poses_new, glob)
+    line["esdf"] = B.time_esdf(glob)
     if not args.no_cpu_baseline:
         # the reference merges single-threaded: time a bounded number of submaps with the oracle
         from oracle import oracle_py as orc

@@ -418,6 +418,67 @@ inline void generateMesh(const TsdfLayer& layer, LayerMesh* mesh,
                       nv ? &mesh->colors[0].r : nullptr));
 }
 
+// ---- voxblox::EsdfIntegrator / EsdfMap over a device-resident TSDF layer: the client's
+// MapServer::updateEsdfBatch (coxgraph/include/coxgraph/client/map_server.h:141-145) and
+// publishTraversable's createFreePointcloudFromEsdfLayer (src/client/map_server.cpp:112-113).
+// The ESDF stays on the device (in the layer's context) between updateFromTsdfLayerBatch and the
+// getters.
+struct EsdfVoxel {  // voxblox::EsdfVoxel
+  float distance = 0.0f;
+  bool observed = false, hallucinated = false, in_queue = false, fixed = false;
+  int8_t parent[3] = {0, 0, 0};
+};
+struct PointXYZI {  // pcl::PointXYZI
+  float x, y, z, intensity;
+};
+class EsdfIntegrator {
+ public:
+  struct Config : cg_esdf_config {
+    Config() { cg_esdf_config_default(this); }
+  };
+  // EsdfIntegrator(config, tsdf_layer, esdf_layer): the ESDF layer lives on the device
+  EsdfIntegrator(const Config& config, const TsdfLayer* tsdf_layer)
+      : config_(config), tsdf_layer_(tsdf_layer) {}
+  void updateFromTsdfLayerBatch(cg_esdf_stats* stats = nullptr) {
+    check(cg_layer_esdf_batch(tsdf_layer_->handle(), &config_, stats));
+  }
+  // Layer<EsdfVoxel>: blocks in (z, y, x) order, 4096 voxels each
+  void getEsdfLayer(BlockIndexList* block_indices, std::vector<EsdfVoxel>* voxels) const {
+    size_t nb = 0;
+    check(cg_esdf_fetch(tsdf_layer_->context(), 0, nullptr, nullptr, nullptr, &nb));
+    block_indices->resize(nb);
+    voxels->assign(nb * 4096, EsdfVoxel());
+    if (nb == 0) return;
+    std::vector<float> dist(nb * 4096);
+    std::vector<uint32_t> packed(nb * 4096);
+    check(cg_esdf_fetch(tsdf_layer_->context(), nb, &(*block_indices)[0].x, dist.data(),
+                        packed.data(), nullptr));
+    for (size_t i = 0; i < dist.size(); ++i) {
+      EsdfVoxel& v = (*voxels)[i];
+      const uint32_t w = packed[i];
+      v.distance = dist[i];
+      v.observed = w & 1u;
+      v.hallucinated = w & 2u;
+      v.in_queue = w & 4u;
+      v.fixed = w & 8u;
+      v.parent[0] = static_cast<int8_t>(w >> 24);
+      v.parent[1] = static_cast<int8_t>((w >> 16) & 0xFF);
+      v.parent[2] = static_cast<int8_t>((w >> 8) & 0xFF);
+    }
+  }
+  // voxblox::createFreePointcloudFromEsdfLayer(esdf_layer, min_distance, &pointcloud)
+  void createFreePointcloud(float min_distance, std::vector<PointXYZI>* pointcloud) const {
+    size_t n = 0;
+    check(cg_esdf_free_points(tsdf_layer_->context(), min_distance, 0, nullptr, &n));
+    pointcloud->resize(n);
+    if (n) check(cg_esdf_free_points(tsdf_layer_->context(), min_distance, n, &(*pointcloud)[0].x, &n));
+  }
+
+ private:
+  Config config_;
+  const TsdfLayer* tsdf_layer_;
+};
+
 // ---- the same map after a pose-graph update, rebuilt only where a moved submap reaches
 // (the reference re-projects everything, coxgraph_server.h:275-283).  The layer must
 // hold getProjectedMap(submap_layers, T_M_S_old); afterwards it is bit-identical to

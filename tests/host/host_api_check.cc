@@ -128,6 +128,32 @@ int main(int argc, char** argv) {
   if (mesh.vertices.size() % 3 != 0 || mesh.vertex_begin.size() != mesh.block_indices.size() + 1 ||
       mesh.vertex_begin.back() != mesh.vertices.size())
     return 70;
+  // ... and what the client's MapServer does with its combined map (map_server.h:141-145,
+  // map_server.cpp:112-113): batch ESDF, then the traversable cloud
+  {
+    cg::EsdfIntegrator::Config ecfg;
+    ecfg.min_distance_m = 0.1f;  // coxgraph_client.yaml:69
+    cg::EsdfIntegrator esdf(ecfg, &combined);
+    cg_esdf_stats est;
+    esdf.updateFromTsdfLayerBatch(&est);
+    cg::BlockIndexList eidx;
+    std::vector<cg::EsdfVoxel> evox;
+    esdf.getEsdfLayer(&eidx, &evox);
+    if (eidx.size() != combined.getNumberOfAllocatedBlocks() || est.blocks != eidx.size()) return 72;
+    size_t observed = 0, fixed = 0, free_voxels = 0;
+    for (const cg::EsdfVoxel& v : evox) {
+      observed += v.observed;
+      fixed += v.fixed;
+      free_voxels += (v.observed && v.distance >= 0.3f);
+      if (v.in_queue || (v.fixed && !v.observed)) return 73;
+    }
+    if (observed != est.observed_voxels || fixed != est.fixed_voxels || fixed == 0) return 74;
+    std::vector<cg::PointXYZI> cloud;
+    esdf.createFreePointcloud(0.3f, &cloud);
+    if (cloud.size() != free_voxels) return 75;
+    for (const cg::PointXYZI& p : cloud)
+      if (!(p.intensity >= 0.3f)) return 76;
+  }
   const size_t before = combined.getNumberOfAllocatedBlocks();
   const std::vector<uint8_t> moved =
       cg::reprojectSubmaps({&submap}, {T_M_S}, {T_M_S}, &combined);
