@@ -12,7 +12,7 @@ SRC  = coxgraph_b200/csrc
 OBJ  = build/obj
 LIB  = coxgraph_b200/lib/libcoxgraph_b200.so
 HDRS = $(SRC)/cg_math.cuh $(SRC)/cg_internal.cuh $(SRC)/cg_raycast_direct.cuh include/coxgraph_b200.h
-OBJS = $(OBJ)/layer.o $(OBJ)/integrate.o $(OBJ)/merge.o $(OBJ)/exchange.o $(OBJ)/comm.o $(OBJ)/mesh_recover.o $(OBJ)/mesh.o $(OBJ)/esdf.o $(OBJ)/selftest.o
+OBJS = $(OBJ)/layer.o $(OBJ)/integrate.o $(OBJ)/merge.o $(OBJ)/exchange.o $(OBJ)/comm.o $(OBJ)/mesh_recover.o $(OBJ)/mesh.o $(OBJ)/mesh_connect.o $(OBJ)/esdf.o $(OBJ)/selftest.o
 
 HOSTCHK = build/host_api_check
 

@@ -217,6 +217,24 @@ class Layer:
                                          _ptr(c) if V else None))
         return idx, begin, v, n, c
 
+    def getConnectedMesh(self, fetch=True):
+        """MeshLayer::getConnectedMesh (voxblox::createConnectedMesh) of the mesh the last
+        generateMesh left on the device -> (vertices f32 [U,3], normals f32 [U,3], colors u8 [U,4],
+        indices u32 [V]); with fetch=False only (U, V)."""
+        lib = capi.load()
+        nu, ni = C.c_size_t(0), C.c_size_t(0)
+        capi.check(lib.cg_mesh_connect(self.ctx._h, 0, 0, None, None, None, None, C.byref(nu),
+                                       C.byref(ni)))
+        U, V = nu.value, ni.value
+        if not fetch:
+            return U, V
+        v, n = np.zeros((U, 3), np.float32), np.zeros((U, 3), np.float32)
+        c, idx = np.zeros((U, 4), np.uint8), np.zeros(V, np.uint32)
+        if V:
+            capi.check(lib.cg_mesh_connect(self.ctx._h, U, V, _ptr(v), _ptr(n), _ptr(c), _ptr(idx),
+                                           C.byref(nu), C.byref(ni)))
+        return v, n, c, idx
+
     def updateEsdfBatch(self, config=None, fetch=True):
         """voxblox::EsdfIntegrator::updateFromTsdfLayerBatch on the device
         (coxgraph/include/coxgraph/client/map_server.h:141-145).  The ESDF stays in the context;

@@ -171,6 +171,8 @@ SYMBOLS = {
     "cg_layer_mesh": (C.c_int32, [_P, C.c_float, C.c_int32, C.c_int32, C.c_size_t, C.c_size_t, _P, _P,
                                   _P, _P, _P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "cg_mesh_fetch": (C.c_int32, [_P, C.c_size_t, C.c_size_t, _P, _P, _P, _P, _P]),
+    "cg_mesh_connect": (C.c_int32, [_P, C.c_size_t, C.c_size_t, _P, _P, _P, _P,
+                                    C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "cg_esdf_config_default": (None, [C.POINTER(EsdfConfig)]),
     "cg_layer_esdf_batch": (C.c_int32, [_P, C.POINTER(EsdfConfig), C.POINTER(EsdfStats)]),
     "cg_esdf_fetch": (C.c_int32, [_P, C.c_size_t, _P, _P, _P, C.POINTER(C.c_size_t)]),

@@ -288,6 +288,7 @@ struct cg_context : cg::FrontBufs {
   // marching cubes (mesh.cu)
   cg::DevBuf mc_counts, mc_index, mc_vertices, mc_normals, mc_colors;
   size_t mc_blocks = 0, mc_total = 0;  // size of the retained result (cg_mesh_fetch)
+  cg::DevBuf weld_keys, weld_words, weld_out;  // vertex welding (mesh_connect.cu)
   // ESDF of a layer (esdf.cu): working / result planes in (z, y, x) block order, retained until
   // the next cg_layer_esdf_batch on this context
   cg::DevBuf esdf_keys, esdf_slots, esdf_work, esdf_dist, esdf_packed, esdf_fixed, esdf_slot_to_b,

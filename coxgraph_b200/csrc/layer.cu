@@ -554,7 +554,7 @@ int32_t cg_context_destroy(cg_context* ctx) {
                     &ctx->mesh_cols_c, &ctx->mesh_frames, &ctx->esdf_keys, &ctx->esdf_slots,
                     &ctx->esdf_work, &ctx->esdf_dist, &ctx->esdf_packed, &ctx->esdf_fixed,
                     &ctx->esdf_slot_to_b, &ctx->esdf_dirty, &ctx->esdf_list, &ctx->esdf_index,
-                    &ctx->esdf_counters};
+                    &ctx->esdf_counters, &ctx->weld_keys, &ctx->weld_words, &ctx->weld_out};
   for (DevBuf* b : bufs) b->release();
   drain_events(ctx);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);

@@ -418,6 +418,42 @@ inline void generateMesh(const TsdfLayer& layer, LayerMesh* mesh,
                       nv ? &mesh->colors[0].r : nullptr));
 }
 
+// ---- MeshLayer::getConnectedMesh + io::outputMeshAsPly: what saveAndPubCombinedMesh does with a
+// file path (server_visualizer.cpp:118-126).  Operates on the mesh the last generateMesh of this
+// layer's context left on the device.
+struct ConnectedMesh {  // voxblox::Mesh with shared vertices
+  std::vector<Point> vertices, normals;
+  std::vector<Color> colors;
+  std::vector<uint32_t> indices;  // three per triangle
+};
+inline void getConnectedMesh(const TsdfLayer& layer, ConnectedMesh* mesh) {
+  size_t nu = 0, ni = 0;
+  check(cg_mesh_connect(layer.context(), 0, 0, nullptr, nullptr, nullptr, nullptr, &nu, &ni));
+  mesh->vertices.resize(nu);
+  mesh->normals.resize(nu);
+  mesh->colors.resize(nu);
+  mesh->indices.resize(ni);
+  if (ni == 0) return;
+  check(cg_mesh_connect(layer.context(), nu, ni, &mesh->vertices[0].x, &mesh->normals[0].x,
+                        &mesh->colors[0].r, mesh->indices.data(), &nu, &ni));
+}
+// voxblox::outputMeshAsPly (io/mesh_ply.h): ascii PLY with vertex colours and triangle faces
+inline bool outputMeshAsPly(const std::string& filename, const ConnectedMesh& mesh) {
+  FILE* f = std::fopen(filename.c_str(), "w");
+  if (!f) return false;
+  std::fprintf(f, "ply\nformat ascii 1.0\nelement vertex %zu\nproperty float x\nproperty float y\n"
+                  "property float z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\n"
+                  "property uchar alpha\nelement face %zu\nproperty list uchar int vertex_indices\n"
+                  "end_header\n", mesh.vertices.size(), mesh.indices.size() / 3);
+  for (size_t i = 0; i < mesh.vertices.size(); ++i)
+    std::fprintf(f, "%f %f %f %d %d %d %d\n", mesh.vertices[i].x, mesh.vertices[i].y,
+                 mesh.vertices[i].z, mesh.colors[i].r, mesh.colors[i].g, mesh.colors[i].b,
+                 mesh.colors[i].a);
+  for (size_t t = 0; t + 2 < mesh.indices.size(); t += 3)
+    std::fprintf(f, "3 %u %u %u\n", mesh.indices[t], mesh.indices[t + 1], mesh.indices[t + 2]);
+  return std::fclose(f) == 0;
+}
+
 // ---- voxblox::EsdfIntegrator / EsdfMap over a device-resident TSDF layer: the client's
 // MapServer::updateEsdfBatch (coxgraph/include/coxgraph/client/map_server.h:141-145) and
 // publishTraversable's createFreePointcloudFromEsdfLayer (src/client/map_server.cpp:112-113).

@@ -323,6 +323,18 @@ int32_t cg_mesh_fetch(cg_context* ctx, size_t capacity_blocks, size_t capacity_v
                       int32_t* block_idx_xyz, uint32_t* vertex_begin, float* vertices_xyz,
                       float* normals_xyz, uint8_t* colors_rgba);
 
+/* MeshLayer::getConnectedMesh (voxblox::createConnectedMesh, [EXT] mesh/mesh_utils.h) of the mesh
+ * the last cg_layer_mesh left in the context — the PLY step of saveAndPubCombinedMesh when a file
+ * path is given (coxgraph/src/server/visualizer/server_visualizer.cpp:118-126 ->
+ * io::outputMeshLayerAsPly).  Vertices that fall into the same cell of the 1e-10 m grid
+ * (round(double(v) / double(1e-10f)) per axis) are merged into the first of them, block meshes
+ * taken in (z, y, x) block order: vertices / normals / colours of the first occurrences in order
+ * of first occurrence, indices[i] = new index of old vertex i (three per triangle).  Counts are
+ * always reported; arrays (any may be NULL) are filled when the capacities suffice. */
+int32_t cg_mesh_connect(cg_context* ctx, size_t capacity_vertices, size_t capacity_indices,
+                        float* vertices_xyz, float* normals_xyz, uint8_t* colors_rgba,
+                        uint32_t* indices, size_t* num_vertices_out, size_t* num_indices_out);
+
 /* --- ESDF of the device-resident layer (second half): replaces
  * voxblox::EsdfIntegrator::updateFromTsdfLayerBatch() as the client's MapServer runs it after the
  * merge (coxgraph/include/coxgraph/client/map_server.h:141-145, from

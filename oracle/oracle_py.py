@@ -106,6 +106,8 @@ def lib():
         L.orc_layer_mesh.restype = C.c_size_t
         L.orc_layer_mesh.argtypes = [C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_connect_mesh.restype = C.c_size_t
+        L.orc_connect_mesh.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.orc_triangle_table.restype = C.POINTER(C.c_int)
         L.orc_triangle_table.argtypes = []
         L.orc_esdf_default_config.argtypes = [C.POINTER(EsdfConfig)]
@@ -280,6 +282,16 @@ class Layer:
         ok = lib().orc_interp_voxel(self._h, _ptr(p), int(interpolate), C.byref(d), C.byref(w),
                                     _ptr(rgba))
         return bool(ok), d.value, w.value, rgba
+
+
+def connect_mesh(vertices):
+    """voxblox::createConnectedMesh on a flat triangle list -> (indices u32 [V], first_old u32 [U]:
+    the old index of every unique vertex, in order of first occurrence)."""
+    v = _f32(vertices, (-1, 3))
+    idx = np.zeros(len(v), np.uint32)
+    first = np.zeros(len(v), np.uint32)
+    u = lib().orc_connect_mesh(_ptr(v), len(v), _ptr(idx), _ptr(first)) if len(v) else 0
+    return idx, first[:u].copy()
 
 
 def triangle_table():

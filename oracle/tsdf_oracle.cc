@@ -1628,6 +1628,28 @@ size_t orc_layer_mesh(const orc_layer* l, float min_weight, int32_t use_color, i
 
 const int* orc_triangle_table(void) { return &kTriangleTable[0][0]; }
 
+size_t orc_connect_mesh(const float* vertices, size_t n, uint32_t* out_indices,
+                        uint32_t* first_old_index) {
+  std::unordered_map<L3, size_t, L3Hash> uniques;  // LongIndexHashMapType<size_t>
+  const float threshold = 1e-10f;                  // approximate_vertex_proximity_threshold
+  const double threshold_inv = 1.0 / static_cast<double>(threshold);
+  size_t new_vertex_index = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const L3 cell = {static_cast<int64_t>(std::round(static_cast<double>(vertices[3 * i]) * threshold_inv)),
+                     static_cast<int64_t>(std::round(static_cast<double>(vertices[3 * i + 1]) * threshold_inv)),
+                     static_cast<int64_t>(std::round(static_cast<double>(vertices[3 * i + 2]) * threshold_inv))};
+    auto it = uniques.find(cell);
+    if (it == uniques.end()) {
+      uniques.emplace(cell, new_vertex_index);
+      if (first_old_index) first_old_index[new_vertex_index] = static_cast<uint32_t>(i);
+      out_indices[i] = static_cast<uint32_t>(new_vertex_index++);
+    } else {
+      out_indices[i] = static_cast<uint32_t>(it->second);
+    }
+  }
+  return new_vertex_index;
+}
+
 }  // extern "C"
 
 // ================================================================ ESDF (second half)

@@ -139,6 +139,13 @@ size_t orc_mesh_to_frames(const orc_mesh* mesh, float interpolate_voxel_size, si
 size_t orc_layer_mesh(const orc_layer* layer, float min_weight, int32_t use_color,
                       int32_t only_updated, uint32_t* vertex_begin, float* vertices, float* normals,
                       uint8_t* colors, size_t capacity_vertices);
+/* voxblox::createConnectedMesh ([EXT] mesh/mesh_utils.h; MeshLayer::getConnectedMesh, the PLY step
+ * of saveAndPubCombinedMesh, coxgraph/src/server/visualizer/server_visualizer.cpp:118-126) of a
+ * flat triangle list (n vertices in block order): a hash map from round(double(v) / double(1e-10f))
+ * per axis to the first vertex of that cell.  out_indices[n]; the unique vertices' old indices go to
+ * first_old_index (capacity n).  Returns the number of unique vertices. */
+size_t orc_connect_mesh(const float* vertices, size_t n, uint32_t* out_indices,
+                        uint32_t* first_old_index);
 /* kTriangleTable[256][16] */
 const int* orc_triangle_table(void);
 

@@ -128,6 +128,19 @@ int main(int argc, char** argv) {
   if (mesh.vertices.size() % 3 != 0 || mesh.vertex_begin.size() != mesh.block_indices.size() + 1 ||
       mesh.vertex_begin.back() != mesh.vertices.size())
     return 70;
+  {  // the PLY step of saveAndPubCombinedMesh: shared vertices, three indices per triangle
+    cg::ConnectedMesh connected;
+    cg::getConnectedMesh(combined, &connected);
+    if (connected.indices.size() != mesh.vertices.size() ||
+        connected.vertices.size() >= mesh.vertices.size() || connected.vertices.empty())
+      return 77;
+    for (size_t i = 0; i < connected.indices.size(); ++i) {
+      const cg::Point& a = connected.vertices[connected.indices[i]];
+      const cg::Point& b = mesh.vertices[i];
+      if (a.x != b.x || a.y != b.y || a.z != b.z) return 78;
+    }
+    if (!cg::outputMeshAsPly("/tmp/cg_host_api_check.ply", connected)) return 79;
+  }
   // ... and what the client's MapServer does with its combined map (map_server.h:141-145,
   // map_server.cpp:112-113): batch ESDF, then the traversable cloud
   {

@@ -121,3 +121,24 @@ def test_mesh_of_an_analytic_sphere_is_closed(gpu_ctx):
     L.removeAllBlocks()
     assert len(L.generateMesh()[2]) == 0
     L.close()
+
+
+def test_connected_mesh_matches_the_sequential_hash_map_walk(gpu_ctx):
+    """cg_mesh_connect (MeshLayer::getConnectedMesh / createConnectedMesh on the device: sorts and
+    scans) against the oracle's sequential hash-map walk: same unique vertices in order of first
+    occurrence, same renumbered indices, normals and colours of the first occurrences."""
+    L, integ = _fused_submap(gpu_ctx, frames=3, stride=2)
+    gi, gb, gv, gn, gc = L.generateMesh()
+    cv, cn, cc, cidx = L.getConnectedMesh()
+    oidx, first = orc.connect_mesh(gv)
+    assert len(cv) == len(first) and 0 < len(first) < len(gv) / 2
+    assert np.array_equal(cidx, oidx)
+    assert np.array_equal(cv.view(np.uint32), gv[first].view(np.uint32))
+    assert np.array_equal(cn.view(np.uint32), gn[first].view(np.uint32))
+    assert np.array_equal(cc, gc[first])
+    assert L.getConnectedMesh(fetch=False) == (len(first), len(gv))
+    # an empty mesh
+    from coxgraph_b200 import Layer
+    E = Layer(gpu_ctx, 0.05, max_blocks=16)
+    E.generateMesh()
+    assert E.getConnectedMesh(fetch=False) == (0, 0)

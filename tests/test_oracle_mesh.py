@@ -107,3 +107,26 @@ def test_unobserved_corners_and_missing_neighbours_make_no_triangles():
     tri = L.mesh(min_weight=1e-5)[1].reshape(-1, 3, 3)
     area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1).sum()
     assert abs(area - (15 * VS) ** 2) < 1e-4
+
+
+def test_connected_mesh_merges_exactly_coincident_vertices():
+    """createConnectedMesh (MeshLayer::getConnectedMesh, the PLY step of saveAndPubCombinedMesh,
+    server_visualizer.cpp:118-126) welds the per-block triangle soup with a 1e-10 m cell: only
+    vertices whose coordinates agree to the bit (or within 1e-10 m near the origin) merge — an
+    edge vertex interpolated from its two corners in the other order may differ in the last bit and
+    stays separate, upstream too.  Unique vertices come in order of first occurrence."""
+    blocks = [(x, y, z) for z in (-1, 0) for y in (-1, 0) for x in (-1, 0)]
+    ctr = np.array([0.013, -0.021, 0.007])
+    L = dense_layer(lambda c: np.linalg.norm(c - ctr, axis=-1) - 0.5, blocks)
+    begin, v, n, c = L.mesh()
+    idx, first = orc.connect_mesh(v)
+    assert len(idx) == len(v) and len(first) < len(v) / 2
+    assert np.array_equal(v[first][idx], v)  # every corner maps to a vertex with its own position
+    assert (np.diff(first.astype(np.int64)) > 0).all()  # order of first occurrence
+    assert np.array_equal(idx[first], np.arange(len(first)))
+    # distinct unique vertices have distinct positions
+    assert len(np.unique(v[first], axis=0)) == len(first)
+    # hand case: -0.0 joins +0.0, 1e-12 m falls into the same 1e-10 m cell, a real neighbour does not
+    pts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [-0.0, 0, 0], [0, 0, 1e-12], [0, 0, 1e-6]], np.float32)
+    idx, first = orc.connect_mesh(pts)
+    assert idx.tolist() == [0, 1, 2, 0, 0, 3] and first.tolist() == [0, 1, 2, 5]
