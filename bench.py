@@ -371,7 +371,7 @@ def run_ours(args, rank, world, local_rank):
     for e in pool:
         if args.profile_mode:
             e.update(bytes_integrate=0, blocks_in=0, bytes_merge=0, voxels_in=0, rays=0, pairs=0,
-                     general=0, per_frame_ms=0.0)
+                     general=0, per_frame_ms=0.0, per_frame_queued_ms=0.0)
             continue
         submap.clear()
         touched = 0
@@ -384,6 +384,25 @@ def run_ours(args, rank, world, local_rank):
         ev1.record(stream)
         torch.cuda.synchronize()
         e["per_frame_ms"] = ev0.elapsed_time(ev1) / FRAMES_PER_SUBMAP
+        # the same 25 calls with the subscriber queue two deep (voxblox_ros TsdfServer holds the
+        # next PointCloud2 while the current one is integrated): the layer-independent first half
+        # of frame f+1 is queued before frame f is completed (cg_prepare_batch_device with one
+        # frame + cg_integrate_prepared); same result as the plain calls
+        submap.clear()
+
+        def one(f):
+            a, b = int(e["offs"][f]), int(e["offs"][f + 1])
+            return (e["poses"][f:f + 1], e["d_pts"][a:b], e["d_cols"][a:b],
+                    np.array([0, b - a], np.uint64))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        integ.prepareBatch(0, *one(0))
+        for f in range(FRAMES_PER_SUBMAP):
+            if f + 1 < FRAMES_PER_SUBMAP:
+                integ.prepareBatch((f + 1) % 2, *one(f + 1))
+            integ.integratePrepared(f % 2)
+        torch.cuda.synchronize()
+        e["per_frame_queued_ms"] = (time.perf_counter() - t0) * 1e3 / FRAMES_PER_SUBMAP
         e["bytes_integrate"] = 16 * e["n"] + 2 * BLOCK_BYTES * touched
         submap.clear()
         st = integ.integrateBatch(e["poses"], e["d_pts"], e["d_cols"], e["offs"])
@@ -861,6 +880,10 @@ def run_ours(args, rank, world, local_rank):
                                "points_per_s": 307200.0 /
                                max(1e-9, float(np.median([e["per_frame_ms"] for e in pool])) * 1e-3),
                                "what": "cg_integrate_pointcloud_device, input resident in HBM",
+                               "queued_ms": float(np.median([e["per_frame_queued_ms"] for e in pool])),
+                               "queued_what": "the same frames with the next one queued: "
+                                              "cg_prepare_batch_device(frame f+1) before "
+                                              "cg_integrate_prepared(frame f); wall clock",
                                "host_pageable": per_frame_host},
             "integrate": {"value": dv["points"] / (dv["int_ms"] * 1e-3), "unit": "points/s",
                           "ms_per_step": dv["int_ms"] / args.steps,

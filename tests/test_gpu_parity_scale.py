@@ -99,3 +99,70 @@ def test_c4_shaped_frame_against_oracle(gpu_ctx):
     util.record_margins("c4_shaped_two_frames", util.margins(got, ref))
     util.compare_layers(got, ref, "C4-shaped frames")
     gl.close()
+
+
+def test_c1_hundred_frames_into_one_submap(gpu_ctx):
+    """configs[0] at full size: 100 stride-1 640x480 frames (30.72 M points) fused into ONE 5 cm
+    submap as one job, against the sequential oracle frame by frame."""
+    from coxgraph_b200 import Layer, TsdfIntegrator
+    from oracle import oracle_py as orc
+    ocfg, gcfg = util.make_cfgs(**C2)
+    sub, o_sub = Layer(gpu_ctx, 0.05, max_blocks=8192), orc.Layer(0.05)
+    frames = []
+    import torch
+    from coxgraph_b200 import synth
+    for sm in range(4):  # four consecutive stretches of robot 0's trajectory: 100 distinct frames
+        frames += [(T, p.cpu().numpy(), c.cpu().numpy()) for (T, p, c) in
+                   synth.submap_frames(0, sm, 25, device=torch.device("cuda", 0))]
+    poses, pts, cols, offs = _batch(frames)
+    st = TsdfIntegrator(gcfg, sub).integrateBatch(poses, pts, cols, offs)
+    assert st.points_in == 100 * 307200
+    for (T, p, c) in frames:
+        o_sub.integrate(ocfg, T, p, c)
+    got, ref = sub.download(), o_sub.download()
+    util.record_margins("c1_100_frames_one_submap", util.margins(got, ref))
+    util.compare_layers(got, ref, "C1: 100 frames into one submap")
+    sub.close()
+
+
+def test_c3_shaped_corridor_submaps_projected(gpu_ctx):
+    """configs[2] / configs[4] shape: submaps that follow one another ALONG a trajectory (corridor
+    scene, 10 full frames each, 2 m per submap) fused on the device and projected into the global
+    map under perturbed poses (the re-merge after a pose-graph update), against the oracle's
+    fusion and its sequential mergeLayerAintoLayerB."""
+    import torch
+    from coxgraph_b200 import Layer, TsdfIntegrator, getProjectedMap, synth
+    from oracle import oracle_py as orc
+    ocfg, gcfg = util.make_cfgs(**C2)
+    rng = np.random.default_rng(5)
+    subs, o_subs, poses = [], [], []
+    for sm in range(12):
+        frames = [(T, p.cpu().numpy(), c.cpu().numpy()) for (T, p, c) in
+                  synth.corridor_frames(sm * 10, 10, robot=0, advance=0.2, start_x=0.0,
+                                        device=torch.device("cuda", 0))]
+        L, ol = Layer(gpu_ctx, 0.05, max_blocks=768), orc.Layer(0.05)
+        p, pts, cols, offs = _batch(frames)
+        TsdfIntegrator(gcfg, L).integrateBatch(p, pts, cols, offs)
+        for (T, q, c) in frames:
+            ol.integrate(ocfg, T, q, c)
+        if sm == 0:  # the fusion itself on this scene
+            got, ref = L.download(), ol.download()
+            util.record_margins("c3_corridor_submap_fused", util.margins(got, ref))
+            util.compare_layers(got, ref, "corridor submap fused")
+        subs.append(L)
+        o_subs.append(ol)
+        poses.append(synth.perturb_pose(synth.robot_map_offset(0), rng))  # sigma 5 cm / 1 deg (C5)
+    poses = np.stack(poses)
+    glob, o_glob = Layer(gpu_ctx, 0.05, max_blocks=16384), orc.Layer(0.05)
+    getProjectedMap(subs, poses, glob)
+    for L, T in zip(subs, poses):
+        ol = orc.Layer(0.05)
+        ol.upload(*L.download())
+        o_glob.merge_from(ol, T)
+    got, ref = glob.download(), o_glob.download()
+    assert len(got[0]) > 1000  # a map along a trajectory, not one room
+    util.record_margins("c3_12_corridor_submaps_projected", util.margins(got, ref))
+    util.compare_layers(got, ref, "12 corridor submaps projected")
+    for L in subs:
+        L.close()
+    glob.close()
