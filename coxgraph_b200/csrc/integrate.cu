@@ -36,6 +36,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "cg_internal.cuh"
@@ -1034,34 +1035,41 @@ k_walk_segments(IntegratorParams P, const float* __restrict__ poses, const Ray* 
       }
       ++seg_pos;
     };
-    // The lanes are aligned at the END of their rays: a lane joins when the countdown reaches
-    // its own length, so all rays of the warp finish together and the costly tail (sdf of the
-    // last visits, closing the last segment) runs converged instead of a few lanes at a time.
-    for (uint32_t left = __reduce_max_sync(full, w.remaining); left > 0; --left) {
-      if (w.remaining >= left) {
-        bool skip = false;
-        if (kGrazing) {
-          const int rx = rc.cx - svx, ry = rc.cy - svy, rz = rc.cz - svz;
-          if (abs(rx) < 8192 && abs(ry) < 8192 && abs(rz) < 8192) {
-            const unsigned long long gk = grazing_key(g_frame, rx, ry, rz);
-            skip = gk != own_key && grazing_contains(G, gk);
-          }
-        }
-        if (skip) {
-          // the reference "continue"s before it even looks the voxel up: no allocation, no
-          // update; the segment ends here and a new one starts at the next voxel that counts
-          if (s_visits) emit();
-          s_visits = 0;
-          rc.step();
-          --w.remaining;
-          continue;
-        }
-        const int bx = rc.cx >> 4, by = rc.cy >> 4, bz = rc.cz >> 4;
-        if (bx != lbx || by != lby || bz != lbz) {
-          if (s_visits) emit();
-          lbx = bx;
-          lby = by;
-          lbz = bz;
+    if constexpr (!kGrazing) {
+      // Same walk with the per-visit work cut down (the kernel is bound by instruction issue, at
+      // ~40 instructions per visit in the general form below).  (1) The lanes are aligned at the
+      // END of their rays, so an active lane's remaining count IS the warp's countdown `left`:
+      // "in the tail" and "last visit" are warp-uniform, the tail code sits in a second loop, and
+      // neither a per-lane counter nor a visit counter is kept (a segment's visit count is the
+      // difference of two countdown values).  (2) The position inside the current block is one
+      // packed word, (l + 64) per byte for x, y, z: a step is one add of the stepped axis'
+      // increment, "left the block" one mask test; global voxel coordinates are rebuilt from the
+      // block origin only where they are needed (a new block, the tail).
+      const uint32_t len = w.remaining;
+      // the first voxel must look like a block entry: its x field is given one block too many
+      int ox = (rc.cx & ~15) - 16, oy = rc.cy & ~15, oz = rc.cz & ~15;  // origin voxel of the block
+      uint32_t loc = static_cast<uint32_t>(((rc.cx & 15) + 16 + 64) | (((rc.cy & 15) + 64) << 8) |
+                                           (((rc.cz & 15) + 64) << 16));
+      const int dx = rc.sx, dy = rc.sy * 256, dz = rc.sz * 65536;
+      float tnx = rc.tnx, tny = rc.tny, tnz = rc.tnz;
+      const float tsx = rc.tsx, tsy = rc.tsy, tsz = rc.tsz;
+      uint32_t seg_left = 0;  // countdown value at the first voxel of the open segment (0: none)
+      auto close_segment = [&](uint32_t left) {
+        s_visits = seg_left - left;
+        emit();
+      };
+      auto visit = [&](uint32_t left, auto tail) {
+        if ((loc & 0x707070u) != 0x404040u) {  // the voxel lies in another block than the last one
+          if (seg_left) close_segment(left);
+          const int cx = ox + static_cast<int>(loc & 0xFFu) - 64,
+                    cy = oy + static_cast<int>((loc >> 8) & 0xFFu) - 64,
+                    cz = oz + static_cast<int>((loc >> 16) & 0xFFu) - 64;
+          ox = cx & ~15;
+          oy = cy & ~15;
+          oz = cz & ~15;
+          s_entry = static_cast<uint32_t>((cx & 15) | ((cy & 15) << 4) | ((cz & 15) << 8));
+          loc = static_cast<uint32_t>((cx & 15) | ((cy & 15) << 8) | ((cz & 15) << 16)) + 0x404040u;
+          const int bx = cx >> 4, by = cy >> 4, bz = cz >> 4;
           unsigned long long tag = 0ull;
           uint32_t ci = 0;
           const bool cacheable = block_cache_tag(bx, by, bz, tag, ci);
@@ -1073,27 +1081,104 @@ k_walk_segments(IntegratorParams P, const float* __restrict__ poses, const Ray* 
             ord = touch_ordinal(Tv, entry, L.err);
             if (cacheable) cache[ci] = (tag << 20) | ord;
           }
-          s_visits = 0;
+          seg_left = left;
+          s_tnx = tnx;
+          s_tny = tny;
+          s_tnz = tnz;
         }
-        if (s_visits == 0) {  // first voxel of a segment (new block, or right after a skipped voxel)
-          s_entry = static_cast<uint32_t>((rc.cx & 15) | ((rc.cy & 15) << 4) | ((rc.cz & 15) << 8));
-          s_tnx = rc.tnx;
-          s_tny = rc.tny;
-          s_tnz = rc.tnz;
-        }
-        ++s_visits;
-        if (w.remaining <= tail_visits) {
-          const V3 center = V3{center_coord(rc.cx, P.voxel_size), center_coord(rc.cy, P.voxel_size),
-                               center_coord(rc.cz, P.voxel_size)};
+        if (decltype(tail)::value) {
+          const int lx = static_cast<int>(loc & 0xFFu) - 64, ly = static_cast<int>((loc >> 8) & 0xFFu) - 64,
+                    lz = static_cast<int>((loc >> 16) & 0xFFu) - 64;
+          const V3 center = V3{center_coord(ox + lx, P.voxel_size), center_coord(oy + ly, P.voxel_size),
+                               center_coord(oz + lz, P.voxel_size)};
           const float sdf = make_visit(P, w.origin, w.ray, center).sdf;
           if (!(sdf >= P.trunc)) {
-            const uint32_t vid = (ord << 12) | static_cast<uint32_t>((rc.cx & 15) + 16 * ((rc.cy & 15) +
-                                                                     16 * (rc.cz & 15)));
+            const uint32_t vid = (ord << 12) | static_cast<uint32_t>(lx + 16 * (ly + 16 * lz));
             atomicOr(Tv.general + (vid >> 5), 1u << (vid & 31));
           }
         }
-        rc.step();
-        if (--w.remaining == 0) emit();
+        // RayCaster::step: first minimum wins ties, NaN in x sticks
+        const bool yx = tny < tnx;
+        const bool pz = tnz < (yx ? tny : tnx);
+        int d = yx ? dy : dx;
+        d = pz ? dz : d;
+        loc += static_cast<uint32_t>(d);
+        if (pz) {
+          tnz += tsz;
+        } else if (yx) {
+          tny += tsy;
+        } else {
+          tnx += tsx;
+        }
+      };
+      uint32_t left = __reduce_max_sync(full, len);
+      for (; left > tail_visits; --left)
+        if (left <= len) visit(left, std::false_type());
+      for (; left > 0; --left)
+        if (left <= len) visit(left, std::true_type());
+      if (len > 0) close_segment(0u);
+    } else {
+      // The lanes are aligned at the END of their rays: a lane joins when the countdown reaches
+      // its own length, so all rays of the warp finish together and the costly tail (sdf of the
+      // last visits, closing the last segment) runs converged instead of a few lanes at a time.
+      for (uint32_t left = __reduce_max_sync(full, w.remaining); left > 0; --left) {
+        if (w.remaining >= left) {
+          bool skip = false;
+          if (kGrazing) {
+            const int rx = rc.cx - svx, ry = rc.cy - svy, rz = rc.cz - svz;
+            if (abs(rx) < 8192 && abs(ry) < 8192 && abs(rz) < 8192) {
+              const unsigned long long gk = grazing_key(g_frame, rx, ry, rz);
+              skip = gk != own_key && grazing_contains(G, gk);
+            }
+          }
+          if (skip) {
+            // the reference "continue"s before it even looks the voxel up: no allocation, no
+            // update; the segment ends here and a new one starts at the next voxel that counts
+            if (s_visits) emit();
+            s_visits = 0;
+            rc.step();
+            --w.remaining;
+            continue;
+          }
+          const int bx = rc.cx >> 4, by = rc.cy >> 4, bz = rc.cz >> 4;
+          if (bx != lbx || by != lby || bz != lbz) {
+            if (s_visits) emit();
+            lbx = bx;
+            lby = by;
+            lbz = bz;
+            unsigned long long tag = 0ull;
+            uint32_t ci = 0;
+            const bool cacheable = block_cache_tag(bx, by, bz, tag, ci);
+            const unsigned long long cw = cacheable ? cache[ci] : 0ull;
+            if (cacheable && (cw >> 20) == tag) {
+              ord = static_cast<uint32_t>(cw & 0xFFFFFu);
+            } else {
+              const int entry = L.insert_entry(pack_block_key(bx, by, bz));
+              ord = touch_ordinal(Tv, entry, L.err);
+              if (cacheable) cache[ci] = (tag << 20) | ord;
+            }
+            s_visits = 0;
+          }
+          if (s_visits == 0) {  // first voxel of a segment (new block, or right after a skipped voxel)
+            s_entry = static_cast<uint32_t>((rc.cx & 15) | ((rc.cy & 15) << 4) | ((rc.cz & 15) << 8));
+            s_tnx = rc.tnx;
+            s_tny = rc.tny;
+            s_tnz = rc.tnz;
+          }
+          ++s_visits;
+          if (w.remaining <= tail_visits) {
+            const V3 center = V3{center_coord(rc.cx, P.voxel_size), center_coord(rc.cy, P.voxel_size),
+                                 center_coord(rc.cz, P.voxel_size)};
+            const float sdf = make_visit(P, w.origin, w.ray, center).sdf;
+            if (!(sdf >= P.trunc)) {
+              const uint32_t vid = (ord << 12) | static_cast<uint32_t>((rc.cx & 15) + 16 * ((rc.cy & 15) +
+                                                                       16 * (rc.cz & 15)));
+              atomicOr(Tv.general + (vid >> 5), 1u << (vid & 31));
+            }
+          }
+          rc.step();
+          if (--w.remaining == 0) emit();
+        }
       }
     }
     for (; seg_pos < seg_end; ++seg_pos) {  // unused slots sort behind every real segment
@@ -1211,6 +1296,12 @@ k_block_accumulate(IntegratorParams P, const Ray* __restrict__ rays,
   const unsigned full = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
+  // (through an opaque move: otherwise the compiler rematerialises the window base — five uniform
+  // instructions — next to every use inside the loop)
+  uint32_t s_lo, s_hi, s_bits;
+  asm volatile("mov.u32 %0, %1;" : "=r"(s_lo) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(tile_lo))));
+  asm volatile("mov.u32 %0, %1;" : "=r"(s_hi) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(tile_hi))));
+  asm volatile("mov.u32 %0, %1;" : "=r"(s_bits) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(bits))));
   // counting-sort path: bin_base[o] = first sorted segment of block ordinal o, bin_base[null_key]
   // = number of real segments (only known on the device)
   const uint32_t num_slots = bin_base ? bin_base[null_key] : num_slots_host;
@@ -1254,20 +1345,18 @@ k_block_accumulate(IntegratorParams P, const Ray* __restrict__ rays,
       unsigned long long* acc = Tv.acc + size_t(o) * kVoxelsPerBlock;
       for (uint32_t i0 = pos + wib * 32; i0 < hi; i0 += kAccThreads) {
         const uint32_t i = i0 + lane;
-        uint32_t visits = 0, ray = 0;
-        int lx = 0, ly = 0, lz = 0, sx = 0, sy = 0, sz = 0;
+        uint32_t visits = 0, ray = 0, lin = 0;
+        int dx = 0, dy = 0, dz = 0;  // change of the linear voxel index per step along x / y / z
         float tnx = 0.0f, tny = 0.0f, tnz = 0.0f, tsx = 0.0f, tsy = 0.0f, tsz = 0.0f;
         unsigned long long wq = 0ull;
         if (i < hi) {
           const uint32_t slot = seg_idx[i];
           const uint4 ra = seg_recs[2 * size_t(slot)], rb = seg_recs[2 * size_t(slot) + 1];
           ray = ra.x;
-          lx = ra.y & 15;
-          ly = (ra.y >> 4) & 15;
-          lz = (ra.y >> 8) & 15;
-          sx = static_cast<int>((ra.y >> 12) & 3) - 1;
-          sy = static_cast<int>((ra.y >> 14) & 3) - 1;
-          sz = static_cast<int>((ra.y >> 16) & 3) - 1;
+          lin = (ra.y & 15u) + 16u * (((ra.y >> 4) & 15u) + 16u * ((ra.y >> 8) & 15u));
+          dx = static_cast<int>((ra.y >> 12) & 3) - 1;
+          dy = (static_cast<int>((ra.y >> 14) & 3) - 1) * 16;
+          dz = (static_cast<int>((ra.y >> 16) & 3) - 1) * 256;
           visits = ra.y >> 18;
           tnx = __uint_as_float(ra.z);
           tny = __uint_as_float(ra.w);
@@ -1277,46 +1366,51 @@ k_block_accumulate(IntegratorParams P, const Ray* __restrict__ rays,
           tsz = __uint_as_float(rb.w);
           wq = __float2ull_rn(fminf(fmaxf(rays[ray].weight, 0.0f), P.max_weight) * acc_scale);
         }
+        const uint32_t w_lo = static_cast<uint32_t>(wq) & 0xFFFFFu, w_hi = static_cast<uint32_t>(wq >> 20);
         const uint32_t vmax = __reduce_max_sync(full, visits);
-        for (uint32_t v = 0; v < vmax; ++v) {
-          bool g = false;
-          uint32_t lin = 0;
-          if (v < visits) {
-            lin = static_cast<uint32_t>(lx + 16 * (ly + 16 * lz));
-            if (use_tile) {
-              atomicAdd(&tile_lo[lin], static_cast<uint32_t>(wq) & 0xFFFFFu);
-              atomicAdd(&tile_hi[lin], static_cast<uint32_t>(wq >> 20));
-            } else {
-              atomicAdd(acc + lin, wq);
+        // the per-visit loop is what this kernel issues (~50 instructions per visit before): the
+        // shared-memory operands are addressed through 32-bit shared-window addresses computed once
+        // (the generic form recomputes the window base every iteration), the tile / no-tile choice
+        // is made outside the loop, the step works on the linear voxel index
+        auto replay = [&](auto tile) {
+          for (uint32_t v = 0; v < vmax; ++v) {
+            uint32_t g = 0;
+            const uint32_t cur = lin;
+            if (v < visits) {
+              if (decltype(tile)::value) {
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(s_lo + cur * 4u), "r"(w_lo) : "memory");
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(s_hi + cur * 4u), "r"(w_hi) : "memory");
+              } else {
+                atomicAdd(acc + cur, wq);
+              }
+              uint32_t word;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(s_bits + (cur >> 5) * 4u));
+              g = (word >> (cur & 31u)) & 1u;
+              // RayCaster::step (first minimum wins ties) on the linear index: the segment ends
+              // before the walk leaves the block, so the index stays inside it while it is used
+              const bool yx = tny < tnx;
+              const bool pz = tnz < (yx ? tny : tnx);
+              int d = yx ? dy : dx;
+              d = pz ? dz : d;
+              lin += static_cast<uint32_t>(d);
+              if (pz) {
+                tnz += tsz;
+              } else if (yx) {
+                tny += tsy;
+              } else {
+                tnx += tsx;
+              }
             }
-            g = (bits[lin >> 5] >> (lin & 31)) & 1u;
-            // RayCaster::step (first minimum wins ties)
-            int m = 0;
-            float best = tnx;
-            if (tny < best) {
-              best = tny;
-              m = 1;
-            }
-            if (tnz < best) m = 2;
-            if (m == 0) {
-              lx += sx;
-              tnx += tsx;
-            } else if (m == 1) {
-              ly += sy;
-              tny += tsy;
-            } else {
-              lz += sz;
-              tnz += tsz;
+            const unsigned gm = __ballot_sync(full, g != 0u);
+            if (gm) {
+              if (g) buf[wib][cnt + __popc(gm & lt)] =
+                  (static_cast<unsigned long long>((o << 12) | cur) << ray_bits) | ray;
+              cnt += __popc(gm);
+              if (cnt > kEmitBuf - 32) flush();
             }
           }
-          const unsigned gm = __ballot_sync(full, g);
-          if (gm) {
-            if (g) buf[wib][cnt + __popc(gm & lt)] =
-                (static_cast<unsigned long long>((o << 12) | lin) << ray_bits) | ray;
-            cnt += __popc(gm);
-            if (cnt > kEmitBuf - 32) flush();
-          }
-        }
+        };
+        if (use_tile) replay(std::true_type()); else replay(std::false_type());
       }
       __syncthreads();
       if (use_tile)
