@@ -168,12 +168,20 @@ __global__ void k_point_keys(IntegratorParams P, KeyLayout kl, const float* __re
   // key_bounds != nullptr: also measure the extent of the job's points (see below)
   __shared__ int s_bounds[6];
   if (key_bounds && threadIdx.x < 6) s_bounds[threadIdx.x] = threadIdx.x < 3 ? 0x3FFFFFFF : -0x3FFFFFFF;
-  if (key_bounds) __syncthreads();
   const uint64_t g = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+  // the CTA's points are consecutive: one binary search for its first point, then each thread
+  // walks on from that frame (zero or one step unless the frames are tiny)
+  __shared__ int s_first_frame;
+  if (threadIdx.x == 0) {
+    const uint64_t g0 = blockIdx.x * static_cast<uint64_t>(blockDim.x);
+    s_first_frame = ft.frame_of(g0 < total ? g0 : total - 1);
+  }
+  __syncthreads();
   int rx = 0, ry = 0, rz = 0;
   bool have = false;
   if (g < total) {
-    const int f = ft.frame_of(g);
+    int f = s_first_frame;
+    while (f + 1 < ft.F && ft.start(f + 1) <= g) ++f;
     const uint64_t base = ft.start(f);
     const int n = static_cast<int>(ft.start(f + 1) - base);
     const int i = static_cast<int>(g - base);
