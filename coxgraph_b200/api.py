@@ -270,6 +270,20 @@ class Layer:
                                                C.byref(n)))
         return out
 
+    def download_updated(self):
+        """Blocks whose `updated` flag is set (Layer::getAllUpdatedBlocks), (z,y,x) order ->
+        (block_idx int32 [B,3], voxels [B,4096] VOXEL_DTYPE, flags u8 [B])."""
+        lib = capi.load()
+        n = C.c_size_t(0)
+        capi.check(lib.cg_layer_download_updated(self._h, 0, None, None, None, C.byref(n)))
+        idx = np.zeros((n.value, 3), np.int32)
+        vox = np.zeros((n.value, capi.VOXELS_PER_BLOCK), VOXEL_DTYPE)
+        flags = np.zeros(n.value, np.uint8)
+        if n.value:
+            capi.check(lib.cg_layer_download_updated(self._h, n.value, _ptr(idx), _ptr(vox),
+                                                     _ptr(flags), C.byref(n)))
+        return idx, vox, flags
+
     def download_blocks(self, block_indices):
         """The listed blocks only -> (voxels [n,4096] VOXEL_DTYPE, flags u8 [n], found bool [n])."""
         idx = np.ascontiguousarray(block_indices, np.int32).reshape(-1, 3)

@@ -137,6 +137,7 @@ SYMBOLS = {
     "cg_layer_num_blocks": (C.c_int64, [_P]),
     "cg_layer_voxel_size": (C.c_float, [_P]),
     "cg_layer_download": (C.c_int32, [_P, C.c_size_t, _P, _P, _P, C.POINTER(C.c_size_t)]),
+    "cg_layer_download_updated": (C.c_int32, [_P, C.c_size_t, _P, _P, _P, C.POINTER(C.c_size_t)]),
     "cg_layer_download_blocks": (C.c_int32, [_P, C.c_size_t, _P, _P, _P, _P]),
     "cg_layer_hash_stats": (C.c_int32, [_P, C.POINTER(HashStats)]),
     "cg_layer_upload": (C.c_int32, [_P, C.c_size_t, _P, _P, _P]),

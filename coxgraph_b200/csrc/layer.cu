@@ -131,6 +131,14 @@ __global__ void k_serialize_blocks(LayerView L, const uint32_t* slots, int count
     out_idx[3 * b + 2] = z;
   }
 }
+__global__ void k_compact_blocks(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ slots,
+                                 const uint32_t* __restrict__ order, uint32_t n,
+                                 uint64_t* __restrict__ keys_out, uint32_t* __restrict__ slots_out) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  keys_out[j] = keys[order[j]];
+  slots_out[j] = slots[order[j]];
+}
 __global__ void k_select_updated(LayerView L, const uint32_t* slots, int n, uint32_t* order,
                                  uint32_t* count) {
   // sorted position i -> kept, in order (single CTA, n is a few thousand blocks at most per call)
@@ -792,6 +800,60 @@ int32_t cg_layer_download(const cg_layer* L, size_t capacity, int32_t* idx, cg_t
     k_gather_aos<<<static_cast<unsigned>(cnt), 256, 0, s>>>(
         L->v, slots, static_cast<int>(first), static_cast<int>(cnt), ctx->stage_a.as<uint32_t>(),
         ctx->stage_b.as<int32_t>(), ctx->stage_c.as<uint8_t>(), keys);
+    if (voxels)
+      CG_CUDA(cudaMemcpyAsync(voxels + first * kVoxelsPerBlock, ctx->stage_a.p,
+                              cnt * CG_BLOCK_BYTES, cudaMemcpyDeviceToHost, s));
+    if (idx)
+      CG_CUDA(cudaMemcpyAsync(idx + first * 3, ctx->stage_b.p, cnt * 3 * sizeof(int32_t),
+                              cudaMemcpyDeviceToHost, s));
+    if (flags)
+      CG_CUDA(cudaMemcpyAsync(flags + first, ctx->stage_c.p, cnt, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(cudaStreamSynchronize(s));
+  }
+  CG_CUDA(cudaGetLastError());
+  return CG_OK;
+}
+
+int32_t cg_layer_download_updated(const cg_layer* L, size_t capacity, int32_t* idx,
+                                  cg_tsdf_voxel* voxels, uint8_t* flags, size_t* n_out) {
+  if (!L) return CG_ERR_INVALID_ARG;
+  cg_context* ctx = L->ctx;
+  cudaStream_t s = ctx->stream;
+  const size_t n_all = static_cast<size_t>(L->num_blocks);
+  if (n_out) *n_out = 0;
+  if (n_all == 0) return CG_OK;
+  const uint64_t* keys;
+  const uint32_t* slots;
+  int32_t rc = sort_blocks(L, &keys, &slots);
+  if (rc) return rc;
+  // Layer::getAllUpdatedBlocks, in (z, y, x) order
+  CG_CUDA(ctx->val_a.reserve(sizeof(uint32_t) * (2 * n_all + 1)));  // val_a is free after the sort
+  CG_CUDA(ctx->flags.reserve(sizeof(uint64_t) * n_all));
+  uint32_t* d_order = ctx->val_a.as<uint32_t>();
+  uint32_t* d_slots = d_order + n_all + 1;
+  uint64_t* d_keys = ctx->flags.as<uint64_t>();
+  k_select_updated<<<1, 1024, 0, s>>>(L->v, slots, static_cast<int>(n_all), d_order, d_order + n_all);
+  uint32_t cnt_upd = 0;
+  CG_CUDA(cudaMemcpyAsync(&cnt_upd, d_order + n_all, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CG_CUDA(cudaStreamSynchronize(s));
+  const size_t n = cnt_upd;
+  if (n_out) *n_out = n;
+  if (n == 0 || (!idx && !voxels && !flags)) return CG_OK;
+  if (capacity < n) {
+    set_error("cg_layer_download_updated: capacity %zu < %zu blocks", capacity, n);
+    return CG_ERR_INVALID_ARG;
+  }
+  k_compact_blocks<<<grid_for(n, 256), 256, 0, s>>>(keys, slots, d_order, static_cast<uint32_t>(n),
+                                                    d_keys, d_slots);
+  const size_t chunk = 2048;  // 96 MB staging
+  CG_CUDA(ctx->stage_a.reserve(std::min(chunk, n) * CG_BLOCK_BYTES));
+  CG_CUDA(ctx->stage_b.reserve(std::min(chunk, n) * 3 * sizeof(int32_t)));
+  CG_CUDA(ctx->stage_c.reserve(std::min(chunk, n)));
+  for (size_t first = 0; first < n; first += chunk) {
+    const size_t cnt = std::min(chunk, n - first);
+    k_gather_aos<<<static_cast<unsigned>(cnt), 256, 0, s>>>(
+        L->v, d_slots, static_cast<int>(first), static_cast<int>(cnt), ctx->stage_a.as<uint32_t>(),
+        ctx->stage_b.as<int32_t>(), ctx->stage_c.as<uint8_t>(), d_keys);
     if (voxels)
       CG_CUDA(cudaMemcpyAsync(voxels + first * kVoxelsPerBlock, ctx->stage_a.p,
                               cnt * CG_BLOCK_BYTES, cudaMemcpyDeviceToHost, s));

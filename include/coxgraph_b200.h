@@ -151,6 +151,13 @@ float cg_layer_voxel_size(const cg_layer* layer);
  * (coxgraph/include/coxgraph/map_comm/tsdf_recover.h:95). */
 int32_t cg_layer_download(const cg_layer* layer, size_t capacity_blocks, int32_t* block_idx_xyz,
                           cg_tsdf_voxel* voxels, uint8_t* flags, size_t* num_blocks_out);
+/* Only the blocks whose `updated` flag is set (Layer::getAllUpdatedBlocks), in (z, y, x) order —
+ * what a consumer that keeps a host copy of the layer needs after integratePointCloud calls
+ * (the adapter's syncLayerToHost); clear the flags with cg_layer_reset_updated.
+ * Call with NULL arrays for the count. */
+int32_t cg_layer_download_updated(const cg_layer* layer, size_t capacity_blocks,
+                                  int32_t* block_idx_xyz, cg_tsdf_voxel* voxels, uint8_t* flags,
+                                  size_t* num_blocks_out);
 /* The listed blocks only (Layer::getBlockPtrByIndex for each index), in the order given:
  * voxels cg_tsdf_voxel[n*4096], flags uint8[n] (either may be NULL), found uint8[n] = 1 where the
  * block is allocated (the other outputs of a missing block are unspecified).  For layers too

@@ -56,5 +56,12 @@ def test_serialize_matches_voxblox_block_format_and_round_trips(gpu_ctx):
     gi2, gv2, gf2 = gl.download()
     keep = (gf2 & 2) != 0
     assert np.array_equal(idx1, gi2[keep]) and np.array_equal(data1, serialize_to_integers(gv2[keep]))
+    # cg_layer_download_updated: the same blocks as voxblox TsdfVoxel records (what an adapter that
+    # mirrors the layer on the host copies back after integratePointCloud)
+    ui, uv, uf = gl.download_updated()
+    assert np.array_equal(ui, gi2[keep]) and np.array_equal(uv.tobytes(), gv2[keep].tobytes())
+    assert np.array_equal(uf, gf2[keep]) and (uf & 2).all()
+    gl.resetUpdated()
+    assert len(gl.download_updated()[0]) == 0
     for L in (gl, back):
         L.close()
