@@ -291,7 +291,7 @@ struct cg_context : cg::FrontBufs {
   cg::DevBuf weld_keys, weld_words, weld_out;  // vertex welding (mesh_connect.cu)
   // ESDF of a layer (esdf.cu): working / result planes in (z, y, x) block order, retained until
   // the next cg_layer_esdf_batch on this context
-  cg::DevBuf esdf_keys, esdf_slots, esdf_work, esdf_dist, esdf_packed, esdf_fixed, esdf_slot_to_b,
+  cg::DevBuf esdf_keys, esdf_slots, esdf_dist, esdf_packed, esdf_fixed, esdf_slot_to_b,
       esdf_dirty, esdf_list, esdf_index, esdf_counters;
   size_t esdf_blocks = 0;
   float esdf_voxel_size = 0.0f, esdf_block_size = 0.0f;

@@ -233,14 +233,14 @@ k_esdf_sweep(LayerView L, const uint64_t* __restrict__ keys, const uint32_t* __r
   }
 }
 
-// flag byte + parent of every voxel; unobserved voxels become the default-constructed EsdfVoxel.
+// flag byte + parent of every voxel; unobserved voxels become the default-constructed EsdfVoxel
+// (distance 0) in the working plane itself, which then is the result plane.
 // packed = parent.x << 24 | parent.y << 16 | parent.z << 8 | flags (Block<EsdfVoxel>::
 // serializeToIntegers' second word); flags: 1 observed, 2 hallucinated, 4 in_queue, 8 fixed
 __global__ void __launch_bounds__(kEsdfThreads)
 k_esdf_finish(LayerView L, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ slots,
-              uint32_t n, EsdfParams P, const float* __restrict__ dist,
-              const uint32_t* __restrict__ fixed_bits, const int32_t* __restrict__ slot_to_b,
-              float* __restrict__ out_dist, uint32_t* __restrict__ packed) {
+              uint32_t n, EsdfParams P, float* dist, const uint32_t* __restrict__ fixed_bits,
+              const int32_t* __restrict__ slot_to_b, uint32_t* __restrict__ packed) {
   __shared__ float tile[kTileVoxels];
   __shared__ int table[27];
   const int x = threadIdx.x & 15, y = threadIdx.x >> 4;
@@ -274,7 +274,9 @@ k_esdf_finish(LayerView L, const uint64_t* __restrict__ keys, const uint32_t* __
           }
         }
       }
-      out_dist[static_cast<size_t>(b) * kVoxelsPerBlock + lin] = observed ? cur : 0.0f;
+      // in place: only NaNs are rewritten, and a 0 in a neighbour's halo is no source either
+      // (sources need s * d > 0), so blocks finished earlier do not disturb later ones
+      if (!observed) dist[static_cast<size_t>(b) * kVoxelsPerBlock + lin] = 0.0f;
       packed[static_cast<size_t>(b) * kVoxelsPerBlock + lin] = word;
     }
   }
@@ -420,7 +422,6 @@ int32_t cg_layer_esdf_batch(const cg_layer* L, const cg_esdf_config* cfg, cg_esd
   CG_CUDA(cudaMemcpyAsync(ctx->esdf_slots.p, slots, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
   keys = ctx->esdf_keys.as<uint64_t>();
   slots = ctx->esdf_slots.as<uint32_t>();
-  CG_CUDA(ctx->esdf_work.reserve(n * kVoxelsPerBlock * sizeof(float)));
   CG_CUDA(ctx->esdf_dist.reserve(n * kVoxelsPerBlock * sizeof(float)));
   CG_CUDA(ctx->esdf_packed.reserve(n * kVoxelsPerBlock * sizeof(uint32_t)));
   CG_CUDA(ctx->esdf_fixed.reserve(n * 128 * sizeof(uint32_t)));
@@ -444,7 +445,7 @@ int32_t cg_layer_esdf_batch(const cg_layer* L, const cg_esdf_config* cfg, cg_esd
   const unsigned wide = static_cast<unsigned>(std::min<size_t>(n, static_cast<size_t>(ctx->num_sms) * 16));
   ctx->own_launches += 2;
   k_esdf_init<<<wide, kEsdfThreads, 0, s>>>(L->v, slots, static_cast<uint32_t>(n), P,
-                                            ctx->esdf_work.as<float>(), ctx->esdf_fixed.as<uint32_t>(),
+                                            ctx->esdf_dist.as<float>(), ctx->esdf_fixed.as<uint32_t>(),
                                             ctx->esdf_slot_to_b.as<int32_t>(),
                                             ctx->esdf_dirty.as<uint8_t>(), counters);
   k_esdf_unpack_idx<<<grid_for(n, 256), 256, 0, s>>>(keys, static_cast<uint32_t>(n),
@@ -468,17 +469,16 @@ int32_t cg_layer_esdf_batch(const cg_layer* L, const cg_esdf_config* cfg, cg_esd
     const unsigned grid = std::min<unsigned>(h_count, static_cast<unsigned>(ctx->num_sms) * 8u);
     ctx->own_launches += 1;
     k_esdf_sweep<<<grid, kEsdfThreads, 0, s>>>(L->v, keys, ctx->esdf_list.as<uint32_t>(), d_count, P,
-                                               ctx->esdf_work.as<float>(),
+                                               ctx->esdf_dist.as<float>(),
                                                ctx->esdf_fixed.as<uint32_t>(),
                                                ctx->esdf_slot_to_b.as<int32_t>(),
                                                ctx->esdf_dirty.as<uint8_t>());
   }
   ctx->own_launches += 1;
   k_esdf_finish<<<wide, kEsdfThreads, 0, s>>>(L->v, keys, slots, static_cast<uint32_t>(n), P,
-                                              ctx->esdf_work.as<float>(),
+                                              ctx->esdf_dist.as<float>(),
                                               ctx->esdf_fixed.as<uint32_t>(),
                                               ctx->esdf_slot_to_b.as<int32_t>(),
-                                              ctx->esdf_dist.as<float>(),
                                               ctx->esdf_packed.as<uint32_t>());
   unsigned long long h_counters[2] = {0, 0};
   CG_CUDA(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, s));

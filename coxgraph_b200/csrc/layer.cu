@@ -560,7 +560,7 @@ int32_t cg_context_destroy(cg_context* ctx) {
                     &ctx->mc_normals, &ctx->mc_colors, &ctx->mesh_in, &ctx->mesh_tri,
                     &ctx->mesh_pairs, &ctx->mesh_pts_g, &ctx->mesh_cols_g, &ctx->mesh_pts_c,
                     &ctx->mesh_cols_c, &ctx->mesh_frames, &ctx->esdf_keys, &ctx->esdf_slots,
-                    &ctx->esdf_work, &ctx->esdf_dist, &ctx->esdf_packed, &ctx->esdf_fixed,
+                    &ctx->esdf_dist, &ctx->esdf_packed, &ctx->esdf_fixed,
                     &ctx->esdf_slot_to_b, &ctx->esdf_dirty, &ctx->esdf_list, &ctx->esdf_index,
                     &ctx->esdf_counters, &ctx->weld_keys, &ctx->weld_words, &ctx->weld_out};
   for (DevBuf* b : bufs) b->release();

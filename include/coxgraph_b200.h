@@ -377,8 +377,8 @@ typedef struct cg_esdf_stats {
   uint64_t block_passes;     /* blocks relaxed, summed over the sweeps */
 } cg_esdf_stats;
 void cg_esdf_config_default(cg_esdf_config* cfg);
-/* Rebuilds the ESDF of `tsdf_layer` on the device; the result stays in the layer's context until
- * the next call. */
+/* Rebuilds the ESDF of `tsdf_layer` on the device; the result (8 bytes per voxel: 32 KB per block)
+ * stays in the layer's context until the next call. */
 int32_t cg_layer_esdf_batch(const cg_layer* tsdf_layer, const cg_esdf_config* cfg,
                             cg_esdf_stats* stats);
 /* Copies the retained ESDF out: blocks in (z, y, x) order, distance float[B*4096] and
@@ -392,7 +392,8 @@ int32_t cg_esdf_fetch(cg_context* ctx, size_t capacity_blocks, int32_t* block_id
 /* createFreePointcloudFromEsdfLayer(esdf, min_distance): (x, y, z, intensity = distance) of every
  * observed voxel with distance >= min_distance, blocks in (z, y, x) order, voxels by linear index.
  * *num_points_out is always set; xyzi (float[4*capacity_points], may be NULL) is filled when the
- * capacity suffices. */
+ * capacity suffices.  Uses the scratch of cg_layer_mesh: a mesh retained for cg_mesh_fetch /
+ * cg_mesh_connect is gone afterwards. */
 int32_t cg_esdf_free_points(cg_context* ctx, float min_distance, size_t capacity_points,
                             float* xyzi, size_t* num_points_out);
 
