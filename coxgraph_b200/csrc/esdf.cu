@@ -528,6 +528,10 @@ int32_t cg_esdf_free_points(cg_context* ctx, float min_distance, size_t capacity
   const size_t n = ctx->esdf_blocks;
   if (num_points_out) *num_points_out = 0;
   if (n == 0) return CG_OK;
+  if (n > (0xFFFFFFFFull / kVoxelsPerBlock)) {  // the per-block ranges are 32-bit
+    set_error("cg_esdf_free_points: %zu blocks hold more than 2^32 voxels", n);
+    return CG_ERR_UNSUPPORTED;
+  }
   cudaStream_t s = ctx->stream;
   CG_CUDA(ctx->mc_counts.reserve(2 * (n + 1) * sizeof(uint32_t)));
   uint32_t* counts = ctx->mc_counts.as<uint32_t>();
