@@ -506,6 +506,17 @@ int32_t cg_gather_global(const cg_layer* partial, cg_layer* owned, uint64_t* blo
   cudaStream_t s = ctx->stream;
   int32_t rc;
   if (c->bound != partial && (rc = bind_partial(ctx, partial))) return rc;
+  // CG_TRACE_COMM=1: per-phase device times of the exchange on stderr (diagnostics only)
+  static const bool trace = getenv("CG_TRACE_COMM") != nullptr;
+  cudaEvent_t tev[6] = {};
+  int tn = 0;
+  auto mark = [&]() {
+    if (trace && tn < 6) {
+      cudaEventCreate(&tev[tn]);
+      cudaEventRecord(tev[tn++], s);
+    }
+  };
+  mark();
   const int R = c->nranks;
   const uint32_t hmask_cap = static_cast<uint32_t>(c->hcap - 1);
   const uint32_t list_cap = static_cast<uint32_t>(std::min<size_t>(c->list_cap, 0xFFFFFFF0u));
@@ -517,12 +528,14 @@ int32_t cg_gather_global(const cg_layer* partial, cg_layer* owned, uint64_t* blo
   CG_CUDA(cudaMemsetAsync(&ctx->d_counters->blocks_out, 0, sizeof(unsigned long long), s));
   // every rank's partial layer is complete and its block count published (stream-ordered)
   if ((rc = barrier(ctx))) return rc;
+  mark();
   const dim3 per_rank(static_cast<unsigned>(ctx->num_sms), static_cast<unsigned>(R));
   k_build_holders<<<per_rank, 256, 0, s>>>(c->d_peers, c->hkeys, c->hmask, hmask_cap, c->counters);
   k_list_owned<<<ctx->num_sms * 4, 256, 0, s>>>(c->hkeys, c->hmask, static_cast<uint32_t>(c->hcap),
                                                 c->rank, c->hbase, c->mine, list_cap, c->counters);
   k_holder_slots<<<per_rank, 256, 0, s>>>(c->d_peers, c->hkeys, c->hmask, c->hbase, hmask_cap,
                                           c->rank, c->slots, list_cap);
+  mark();
   const size_t smem = 3 * kVoxelsPerBlock * sizeof(uint32_t);
   static bool attr_set[64] = {};
   if (ctx->device < 0 || ctx->device >= 64 || !attr_set[ctx->device]) {
@@ -534,10 +547,20 @@ int32_t cg_gather_global(const cg_layer* partial, cg_layer* owned, uint64_t* blo
       owned->v, c->d_peers, c->hkeys, c->hmask, c->hbase, c->mine, c->slots, c->counters, list_cap,
       static_cast<int>(owned->num_blocks), &ctx->d_counters->blocks_out);
   k_comm_overflow<<<1, 1, 0, s>>>(c->counters, owned->v.err);
+  mark();
   // nobody clears or refills its partial layer while a peer still reads it
   if ((rc = barrier(ctx))) return rc;
+  mark();
   CallCounters cc;
   rc = finish_call(owned, &cc);
+  if (trace && tn == 5) {
+    float t[4];
+    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
+    fprintf(stderr, "[cg comm rank %d] reset+barrier %.3f  holders+list+slots %.3f  fold %.3f  barrier %.3f ms "
+            "(partial %lld blocks, hash %zu)\n", c->rank, t[0], t[1], t[2], t[3],
+            static_cast<long long>(partial->num_blocks), c->hcap);
+  }
+  for (int i = 0; i < tn; ++i) cudaEventDestroy(tev[i]);
   if (blocks_folded) *blocks_folded = cc.blocks_out;
   return rc;
 }
