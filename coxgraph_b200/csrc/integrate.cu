@@ -1010,7 +1010,6 @@ k_walk_segments(IntegratorParams P, const float* __restrict__ poses, const Ray* 
       seg_pos = static_cast<uint32_t>(ray_offset[r] >> 32) + r * slack;
       seg_end = seg_pos + static_cast<uint32_t>(ray_count[r] >> 32) + slack;
     }
-    int lbx = 0x7FFFFFFF, lby = 0, lbz = 0;
     uint32_t ord = 0, s_entry = 0, s_visits = 0;
     float s_tnx = 0.0f, s_tny = 0.0f, s_tnz = 0.0f;
     // anti-grazing: sensor voxel of the ray's frame and the ray's own bundle voxel
@@ -1043,16 +1042,17 @@ k_walk_segments(IntegratorParams P, const float* __restrict__ poses, const Ray* 
       }
       ++seg_pos;
     };
-    if constexpr (!kGrazing) {
-      // Same walk with the per-visit work cut down (the kernel is bound by instruction issue, at
-      // ~40 instructions per visit in the general form below).  (1) The lanes are aligned at the
-      // END of their rays, so an active lane's remaining count IS the warp's countdown `left`:
-      // "in the tail" and "last visit" are warp-uniform, the tail code sits in a second loop, and
-      // neither a per-lane counter nor a visit counter is kept (a segment's visit count is the
-      // difference of two countdown values).  (2) The position inside the current block is one
-      // packed word, (l + 64) per byte for x, y, z: a step is one add of the stepped axis'
-      // increment, "left the block" one mask test; global voxel coordinates are rebuilt from the
-      // block origin only where they are needed (a new block, the tail).
+    {
+      // The per-visit work is what this kernel issues.  (1) The lanes are aligned at the END of
+      // their rays — a lane joins when the warp's countdown `left` reaches its own length, so all
+      // rays of the warp finish together and the costly tail (sdf of the last visits) runs
+      // converged — hence an active lane's remaining count IS `left`: "in the tail" and "last
+      // visit" are warp-uniform, the tail code sits in a second loop, and neither a per-lane
+      // counter nor a visit counter is kept (a segment's visit count is the difference of two
+      // countdown values).  (2) The position inside the current block is one packed word,
+      // (l + 64) per byte for x, y, z: a step is one add of the stepped axis' increment, "left the
+      // block" one mask test; global voxel coordinates are rebuilt from the block origin only
+      // where they are needed (a new block, the tail, the anti-grazing test).
       const uint32_t len = w.remaining;
       // the first voxel must look like a block entry: its x field is given one block too many
       int ox = (rc.cx & ~15) - 16, oy = rc.cy & ~15, oz = rc.cz & ~15;  // origin voxel of the block
@@ -1062,12 +1062,50 @@ k_walk_segments(IntegratorParams P, const float* __restrict__ poses, const Ray* 
       float tnx = rc.tnx, tny = rc.tny, tnz = rc.tnz;
       const float tsx = rc.tsx, tsy = rc.tsy, tsz = rc.tsz;
       uint32_t seg_left = 0;  // countdown value at the first voxel of the open segment (0: none)
+      bool after_skip = false;  // anti-grazing: the voxel before was skipped, a new segment starts
       auto close_segment = [&](uint32_t left) {
         s_visits = seg_left - left;
         emit();
+        seg_left = 0;
+      };
+      // RayCaster::step: first minimum wins ties, NaN in x sticks
+      auto step = [&]() {
+        const bool yx = tny < tnx;
+        const bool pz = tnz < (yx ? tny : tnx);
+        int d = yx ? dy : dx;
+        d = pz ? dz : d;
+        loc += static_cast<uint32_t>(d);
+        if (pz) {
+          tnz += tsz;
+        } else if (yx) {
+          tny += tsy;
+        } else {
+          tnx += tsx;
+        }
       };
       auto visit = [&](uint32_t left, auto tail) {
-        if ((loc & 0x707070u) != 0x404040u) {  // the voxel lies in another block than the last one
+        if (kGrazing) {
+          const int cx = ox + static_cast<int>(loc & 0xFFu) - 64,
+                    cy = oy + static_cast<int>((loc >> 8) & 0xFFu) - 64,
+                    cz = oz + static_cast<int>((loc >> 16) & 0xFFu) - 64;
+          const int rx = cx - svx, ry = cy - svy, rz = cz - svz;
+          bool skip = false;
+          if (abs(rx) < 8192 && abs(ry) < 8192 && abs(rz) < 8192) {
+            const unsigned long long gk = grazing_key(g_frame, rx, ry, rz);
+            skip = gk != own_key && grazing_contains(G, gk);
+          }
+          if (skip) {
+            // the reference "continue"s before it even looks the voxel up: no allocation, no
+            // update; the segment ends here and a new one starts at the next voxel that counts
+            if (seg_left) close_segment(left);
+            after_skip = true;
+            step();
+            return;
+          }
+        }
+        if ((loc & 0x707070u) != 0x404040u || (kGrazing && after_skip)) {
+          // the voxel lies in another block than the last one (or follows a skipped voxel)
+          after_skip = false;
           if (seg_left) close_segment(left);
           const int cx = ox + static_cast<int>(loc & 0xFFu) - 64,
                     cy = oy + static_cast<int>((loc >> 8) & 0xFFu) - 64,
@@ -1105,89 +1143,14 @@ k_walk_segments(IntegratorParams P, const float* __restrict__ poses, const Ray* 
             atomicOr(Tv.general + (vid >> 5), 1u << (vid & 31));
           }
         }
-        // RayCaster::step: first minimum wins ties, NaN in x sticks
-        const bool yx = tny < tnx;
-        const bool pz = tnz < (yx ? tny : tnx);
-        int d = yx ? dy : dx;
-        d = pz ? dz : d;
-        loc += static_cast<uint32_t>(d);
-        if (pz) {
-          tnz += tsz;
-        } else if (yx) {
-          tny += tsy;
-        } else {
-          tnx += tsx;
-        }
+        step();
       };
       uint32_t left = __reduce_max_sync(full, len);
       for (; left > tail_visits; --left)
         if (left <= len) visit(left, std::false_type());
       for (; left > 0; --left)
         if (left <= len) visit(left, std::true_type());
-      if (len > 0) close_segment(0u);
-    } else {
-      // The lanes are aligned at the END of their rays: a lane joins when the countdown reaches
-      // its own length, so all rays of the warp finish together and the costly tail (sdf of the
-      // last visits, closing the last segment) runs converged instead of a few lanes at a time.
-      for (uint32_t left = __reduce_max_sync(full, w.remaining); left > 0; --left) {
-        if (w.remaining >= left) {
-          bool skip = false;
-          if (kGrazing) {
-            const int rx = rc.cx - svx, ry = rc.cy - svy, rz = rc.cz - svz;
-            if (abs(rx) < 8192 && abs(ry) < 8192 && abs(rz) < 8192) {
-              const unsigned long long gk = grazing_key(g_frame, rx, ry, rz);
-              skip = gk != own_key && grazing_contains(G, gk);
-            }
-          }
-          if (skip) {
-            // the reference "continue"s before it even looks the voxel up: no allocation, no
-            // update; the segment ends here and a new one starts at the next voxel that counts
-            if (s_visits) emit();
-            s_visits = 0;
-            rc.step();
-            --w.remaining;
-            continue;
-          }
-          const int bx = rc.cx >> 4, by = rc.cy >> 4, bz = rc.cz >> 4;
-          if (bx != lbx || by != lby || bz != lbz) {
-            if (s_visits) emit();
-            lbx = bx;
-            lby = by;
-            lbz = bz;
-            unsigned long long tag = 0ull;
-            uint32_t ci = 0;
-            const bool cacheable = block_cache_tag(bx, by, bz, tag, ci);
-            const unsigned long long cw = cacheable ? cache[ci] : 0ull;
-            if (cacheable && (cw >> 20) == tag) {
-              ord = static_cast<uint32_t>(cw & 0xFFFFFu);
-            } else {
-              const int entry = L.insert_entry(pack_block_key(bx, by, bz));
-              ord = touch_ordinal(Tv, entry, L.err);
-              if (cacheable) cache[ci] = (tag << 20) | ord;
-            }
-            s_visits = 0;
-          }
-          if (s_visits == 0) {  // first voxel of a segment (new block, or right after a skipped voxel)
-            s_entry = static_cast<uint32_t>((rc.cx & 15) | ((rc.cy & 15) << 4) | ((rc.cz & 15) << 8));
-            s_tnx = rc.tnx;
-            s_tny = rc.tny;
-            s_tnz = rc.tnz;
-          }
-          ++s_visits;
-          if (w.remaining <= tail_visits) {
-            const V3 center = V3{center_coord(rc.cx, P.voxel_size), center_coord(rc.cy, P.voxel_size),
-                                 center_coord(rc.cz, P.voxel_size)};
-            const float sdf = make_visit(P, w.origin, w.ray, center).sdf;
-            if (!(sdf >= P.trunc)) {
-              const uint32_t vid = (ord << 12) | static_cast<uint32_t>((rc.cx & 15) + 16 * ((rc.cy & 15) +
-                                                                       16 * (rc.cz & 15)));
-              atomicOr(Tv.general + (vid >> 5), 1u << (vid & 31));
-            }
-          }
-          rc.step();
-          if (--w.remaining == 0) emit();
-        }
-      }
+      if (seg_left) close_segment(0u);
     }
     for (; seg_pos < seg_end; ++seg_pos) {  // unused slots sort behind every real segment
       seg_keys[seg_pos] = null_key;
