@@ -246,6 +246,9 @@ void release_front(FrontBufs& fb);
 }  // namespace cg
 
 struct cg_comm;  // comm.cu: communicator + peer mappings of the multi-GPU merge
+namespace cg {
+struct HostStager;  // host_stage.cu: worker threads + pinned bounce buffer for pageable inputs
+}
 
 struct cg_context : cg::FrontBufs {
   int device = 0;
@@ -253,6 +256,7 @@ struct cg_context : cg::FrontBufs {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t wait_event = nullptr;         // cg_context_wait_stream
+  cg::HostStager* stager = nullptr;         // pageable inputs (lazy, host_stage.cu)
   cudaStream_t copy_stream = nullptr;       // pipelined host->device transfers (lazy)
   std::vector<cudaEvent_t> copy_events;
   cg::DevBuf stage_pts[2], stage_cols[2];   // cg_stage_batch_async double buffer

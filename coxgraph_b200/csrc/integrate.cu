@@ -40,6 +40,7 @@
 #include <vector>
 
 #include "cg_internal.cuh"
+#include "host_stage.cuh"
 
 namespace cg {
 
@@ -2575,9 +2576,13 @@ static int32_t stage_inputs(cg_context* ctx, const float* pts, const uint8_t* co
   CG_CUDA(ctx->points.reserve(n * 3 * sizeof(float)));
   CG_CUDA(ctx->colors.reserve(n * 4));
   StageScope sc(ctx, kStageTransfer, 0);
-  CG_CUDA(cudaMemcpyAsync(ctx->points.p, pts, n * 3 * sizeof(float), cudaMemcpyHostToDevice,
-                          ctx->stream));
-  CG_CUDA(cudaMemcpyAsync(ctx->colors.p, cols, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  // pageable inputs (std::vector clouds of the drop-in call) go through worker threads and a
+  // pinned bounce buffer (host_stage.cu); CG_STAGE_THREADS=0 restores the plain copies
+  static const int threads = static_cast<int>(env_size("CG_STAGE_THREADS", 3));
+  CG_CUDA(stage_begin(ctx->stager, ctx->stream));
+  CG_CUDA(stage_to_device(&ctx->stager, ctx->points.p, pts, n * 3 * sizeof(float), ctx->stream,
+                          threads));
+  CG_CUDA(stage_to_device(&ctx->stager, ctx->colors.p, cols, n * 4, ctx->stream, threads));
   return CG_OK;
 }
 

@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "cg_internal.cuh"
+#include "host_stage.cuh"
 
 namespace cg {
 
@@ -583,6 +584,8 @@ int32_t cg_context_destroy(cg_context* ctx) {
     if (ctx->stage_ready[i]) cudaEventDestroy(ctx->stage_ready[i]);
   }
   if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);
+  cg::destroy_stager(ctx->stager);
+  ctx->stager = nullptr;
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
