@@ -21,7 +21,8 @@ int main(int argc, char** argv) {
   for (int it = 0; it < iterations; ++it) {
     if (cg::stage_begin(st, nullptr) != 0) return 3;
     for (int part = 0; part < 2; ++part) {
-      const size_t n = (it % 7 == 0) ? (rng() % (30u << 20)) + 1 : (rng() % (6u << 20)) + 1;
+      // copies of 16 MB and more go through the pool, smaller ones take the direct path
+      const size_t n = (it % 3 != 2) ? (16u << 20) + rng() % (24u << 20) : (rng() % (6u << 20)) + 1;
       const size_t off = rng() % (src.size() - n);
       memset(dst.data() + off, 0, n);
       if (cg::stage_to_device(&st, dst.data() + off, src.data() + off, n, nullptr, 3) != 0) return 1;

@@ -26,7 +26,7 @@ def test_stage_pool_copies_every_byte(tmp_path, tsan):
     if build.returncode != 0 and tsan:
         pytest.skip("ThreadSanitizer is not available: " + build.stderr[-200:])
     assert build.returncode == 0, build.stderr
-    run = subprocess.run([str(exe), "150" if tsan else "600"], capture_output=True, text=True, timeout=600)
+    run = subprocess.run([str(exe), "60" if tsan else "300"], capture_output=True, text=True, timeout=600)
     assert run.returncode == 0, run.stdout + run.stderr
     assert "stage_stress ok" in run.stdout
     assert "ThreadSanitizer" not in run.stderr, run.stderr[-2000:]
