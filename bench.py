@@ -793,6 +793,30 @@ def run_ours(args, rank, world, local_rank):
                                       "std::vector inputs (H2D inside the call)")
         except Exception as exc:  # noqa: BLE001 - an extra figure must not take the bench line down
             per_frame_host = {"error": repr(exc)}
+        # the plain call with PAGEABLE host arrays for a whole step (what an adapter's std::vector
+        # clouds are): cg_integrate_batch copies them through its worker threads and pinned bounce
+        # buffer (csrc/host_stage.cu); the merge follows as in a step
+        try:
+            e = pool[0]
+            pg_pts = np.array(e["h_pts"], copy=True)   # ordinary (pageable) numpy memory
+            pg_cols = np.array(e["h_cols"], copy=True)
+            t_pg = []
+            for it in range(4):
+                submap.clear()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                integ.integrateBatch(e["poses"], pg_pts, pg_cols, e["offs"])
+                mergeLayerAintoLayerB(submap, e["T_M_S"], glob)
+                torch.cuda.synchronize()
+                t_pg.append((time.perf_counter() - t0) * 1e3)
+            if isinstance(per_frame_host, dict):
+                per_frame_host["pageable_step"] = {
+                    "ms_per_step": min(t_pg[1:]), "points_per_s": e["n"] / (min(t_pg[1:]) * 1e-3),
+                    "what": "one C2 step through cg_integrate_batch with pageable host arrays "
+                            "(123 MB staged by the library's worker threads), then the merge"}
+        except Exception as exc:  # noqa: BLE001
+            if isinstance(per_frame_host, dict):
+                per_frame_host["pageable_step"] = {"error": repr(exc)}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle, all host threads, bounded
     cpu = None
